@@ -1,0 +1,85 @@
+"""The oracle (oracle/unet_oracle.py) against the fixtures generated from the real
+reference (tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+from conftest import SMALL_CASES, golden_state, load_golden, rel_l2
+from oracle import unet_oracle as O
+
+TOL = 2e-5   # fp32 CPU vs fp32 CPU, different summation order only
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_forward_matches_reference(name):
+    meta, rec = load_golden(name)
+    cfg = O.UNetConfig(**meta["kwargs"])
+    sd = golden_state(rec)
+    out = O.forward(sd, cfg, rec["x"], training=meta["training"])
+    assert rel_l2(out["logits"], rec["logits"]) < TOL
+    assert rel_l2(out["seg"], rec["seg"]) < TOL
+    if "heat" in rec:
+        assert rel_l2(out["heat"], rec["heat"]) < TOL
+    else:
+        assert out["heat"] is None
+    if meta["training"]:
+        after = golden_state(rec, "state_after/")
+        for k, v in after.items():
+            if "num_batches" in k:
+                assert int(out["new_stats"][k]) == int(v)
+            else:
+                assert rel_l2(out["new_stats"][k], v) < TOL, k
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_backward_matches_reference_autograd(name):
+    meta, rec = load_golden(name)
+    cfg = O.UNetConfig(**meta["kwargs"])
+    sd = golden_state(rec)
+    out = O.forward(sd, cfg, rec["x"], training=meta["training"], want_tape=True)
+    grads = O.backward(sd, cfg, out["tape"], rec["d_seg"], rec.get("d_heat"))
+    ref = golden_state(rec, "grad/")
+    assert set(grads) == set(ref), set(grads) ^ set(ref)
+    for k in meta["none_grads"]:
+        assert k not in grads
+    for k, g in ref.items():
+        assert grads[k].shape == g.shape, k
+        assert rel_l2(grads[k], g) < 2e-4, (k, rel_l2(grads[k], g))
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_schema_matches_reference_state_dict(name):
+    meta, rec = load_golden(name)
+    cfg = O.UNetConfig(**meta["kwargs"])
+    sd = golden_state(rec)
+    schema = O.param_schema(cfg)
+    assert [n for n, _, _ in schema] == list(sd.keys())
+    for n, shape, _ in schema:
+        assert tuple(sd[n].shape) == tuple(shape), n
+
+
+def test_paper_config_eval_matches_reference():
+    """BASELINE.json config 1.  Weights are rebuilt from the seed through the oracle's own
+    schema using torch's default initialisers in reference order (see test_module_cpu for the
+    engine-side module); here we only need forward parity on identical weights, so rebuild
+    via torch modules in the reference's construction order."""
+    from conftest import load_pkg
+    meta, rec = load_golden("paper_eval_192")
+    pkg = load_pkg()
+    torch.manual_seed(0)
+    net = pkg.UNet(**meta["kwargs"])
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k, (s, sa) in meta["param_sums"].items():
+        assert abs(float(sd[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(s)), k
+        assert abs(float(sd[k].double().abs().sum()) - sa) <= 1e-9 * max(1.0, sa), k
+    cfg = O.UNetConfig(**meta["kwargs"])
+    g = torch.Generator().manual_seed(meta["warm"]["seed"])
+    for _ in range(meta["warm"]["n_iter"]):
+        out = O.forward(sd, cfg, torch.randn(*meta["warm"]["shape"], generator=g), training=True)
+        sd.update(out["new_stats"])
+    for k, v in golden_state(rec, "bn_after/").items():
+        assert rel_l2(sd[k], v) < 1e-4, k
+    out = O.forward(sd, cfg, rec["x"], training=False)
+    assert rel_l2(out["logits"][:, :, ::4, ::4], rec["logits_s4"]) < 1e-4
+    assert rel_l2(out["seg"][:, :, ::4, ::4], rec["seg_s4"]) < 1e-4
+    assert rel_l2(out["heat"][:, :, ::4, ::4], rec["heat_s4"]) < 1e-4
+    assert abs(float(out["heat"].double().sum()) - float(rec["heat_moments"][0])) < 1e-3 * abs(float(rec["heat_moments"][0])) + 1e-2
