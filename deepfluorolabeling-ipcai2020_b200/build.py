@@ -1,0 +1,54 @@
+"""In-tree build of the CUDA library (sm_100a only).
+
+    python -m importlib ... or:  python deepfluorolabeling-ipcai2020_b200/build.py
+
+nvcc cross-compiles without a GPU; the resulting libfluorounet.so lives next to
+this file (git-ignored, but it travels to the GPU box with the tree)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libfluorounet.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+def sources():
+    out = [os.path.join(INCLUDE, "fluoro_unet.h")]
+    for f in sorted(os.listdir(CSRC)):
+        out.append(os.path.join(CSRC, f))
+    return out
+
+
+def up_to_date():
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(s) <= t for s in sources())
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB + ".tmp", os.path.join(CSRC, "engine.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    os.replace(LIB + ".tmp", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

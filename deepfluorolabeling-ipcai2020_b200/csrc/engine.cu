@@ -1,0 +1,1066 @@
+// The U-Net forward/backward engine behind include/fluoro_unet.h.
+//
+// Host side: builds the layer table of the reference network (unet.py:41-159),
+// plans an NHWC activation arena for a given (B,H,W), and enqueues the kernels of
+// kernels_simt.cuh / kernels_tc.cuh on the caller's stream.  No host
+// synchronisation on the step path, no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fluoro_unet.h"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+using namespace fu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct View {
+  char* p = nullptr;  // address of channel 0 of this view
+  int C = 0;          // channels in the view
+  int ld = 0;         // pixel stride, in elements
+};
+
+struct TensorSlot {
+  fu_tensor_info info;
+  void* data = nullptr;
+  int64_t numel = 0;
+};
+
+struct ConvW {
+  int Cin = 0, Cout = 0, k = 0;
+  bool transposed = false;
+  int w_idx = -1, b_idx = -1;
+  float* wp_fwd = nullptr;    // CUDA-core packing for the forward GEMM
+  float* wp_dgrad = nullptr;  // CUDA-core packing for the data-gradient GEMM
+  int npad_fwd = 0, npad_dgrad = 0, n_fwd = 0, n_dgrad = 0;
+  double* bsum = nullptr;     // [Cout] bias-gradient accumulator
+  TcConv tc;                  // tensor-core packings / descriptors (throughput mode)
+};
+
+struct BNL {
+  int C = 0;
+  int i_gamma = -1, i_beta = -1, i_rm = -1, i_rv = -1, i_nbt = -1;
+  double *stat = nullptr, *bstat = nullptr;
+  float *mean = nullptr, *invstd = nullptr, *a = nullptr, *b = nullptr, *ga = nullptr, *m1 = nullptr,
+        *m2 = nullptr;
+};
+
+struct Block {
+  int Cin = 0, C = 0;
+  bool has_res = false;
+  ConvW res;
+  std::vector<ConvW> convs;
+  std::vector<BNL> bns;
+  // plan-dependent
+  std::vector<View> r, z, dy, dz;
+};
+
+struct Plan {
+  int B = 0, H = 0, W = 0;
+  bool valid = false;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  View xin;
+  std::vector<View> cat, d_cat, down, d_down, decout, d_decout;
+  View bott, d_bott, hcat, d_hcat, dheat;
+  std::vector<View> hmid, d_hmid;
+};
+
+}  // namespace
+
+struct fu_engine {
+  fu_config cfg;
+  int device = 0;
+  int esz = 4;
+  std::string err;
+  std::vector<TensorSlot> tensors;
+  int64_t grad_numel = 0;
+  bool bound = false;
+  std::vector<int> chans;
+  std::vector<Block> enc, dec;
+  std::vector<ConvW> downc, upc;  // downsample convs (depth-1 used), up convs
+  ConvW seg;
+  std::vector<ConvW> lands;
+  int Cf = 0, Cpad = 0;
+  // persistent device memory
+  char* wmem = nullptr;
+  size_t wmem_bytes = 0;
+  double* dscr_fwd = nullptr; size_t dscr_fwd_bytes = 0;
+  double* dscr_bwd = nullptr; size_t dscr_bwd_bytes = 0;
+  float *ones = nullptr, *zeros = nullptr;
+  int64_t packed_version = -1;
+  bool packed_once = false;
+  Plan plan;
+  bool saved = false;
+  int saved_training = 0;
+  fu_counters cnt;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CUDA_TRY(e, expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _ce = (expr);                                                              \
+    if (_ce != cudaSuccess)                                                                \
+      return (e)->fail(FU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_ce), \
+                       __FILE__, __LINE__);                                                \
+  } while (0)
+
+#define LAUNCH(e, kern, grid, block, ...)                                                   \
+  do {                                                                                      \
+    auto _kfn = kern;                                                                       \
+    _kfn<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__);                                 \
+    (e)->cnt.kernel_launches++;                                                             \
+    cudaError_t _ce = cudaPeekAtLastError();                                                \
+    if (_ce != cudaSuccess)                                                                 \
+      return (e)->fail(FU_ERR_CUDA, "launch %s failed: %s (%s:%d)", #kern,                  \
+                       cudaGetErrorString(_ce), __FILE__, __LINE__);                        \
+  } while (0)
+
+namespace {
+
+inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+inline View slice(const View& v, int c0, int C, int esz) {
+  View o;
+  o.p = v.p + (size_t)c0 * esz;
+  o.C = C;
+  o.ld = v.ld;
+  return o;
+}
+inline unsigned grid1d(long long total, int block, int sms) {
+  long long g = (total + block - 1) / block;
+  long long cap = (long long)sms * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+// ---------------------------------------------------------------------------
+// schema (state_dict order of unet.py; must match oracle/unet_oracle.py:param_schema)
+// ---------------------------------------------------------------------------
+int add_tensor(fu_engine* e, const std::string& name, std::vector<int64_t> shape, int kind, int dtype,
+               bool has_grad) {
+  TensorSlot s;
+  memset(&s.info, 0, sizeof(s.info));
+  snprintf(s.info.name, sizeof(s.info.name), "%s", name.c_str());
+  s.info.ndim = (int)shape.size();
+  int64_t n = 1;
+  for (size_t i = 0; i < shape.size(); ++i) {
+    s.info.shape[i] = shape[i];
+    n *= shape[i];
+  }
+  s.numel = n;
+  s.info.kind = kind;
+  s.info.dtype = dtype;
+  s.info.grad_offset = -1;
+  if (has_grad) {
+    s.info.grad_offset = e->grad_numel;
+    e->grad_numel += (n + 3) / 4 * 4;  // keep every gradient 16-byte aligned
+  }
+  e->tensors.push_back(s);
+  return (int)e->tensors.size() - 1;
+}
+
+ConvW make_conv(fu_engine* e, const std::string& prefix, int cin, int cout, int k, bool bias, bool transposed,
+                bool reachable) {
+  ConvW c;
+  c.Cin = cin; c.Cout = cout; c.k = k; c.transposed = transposed;
+  if (transposed)
+    c.w_idx = add_tensor(e, prefix + ".weight", {cin, cout, k, k}, FU_KIND_PARAM, FU_DTYPE_F32, reachable);
+  else
+    c.w_idx = add_tensor(e, prefix + ".weight", {cout, cin, k, k}, FU_KIND_PARAM, FU_DTYPE_F32, reachable);
+  if (bias) c.b_idx = add_tensor(e, prefix + ".bias", {cout}, FU_KIND_PARAM, FU_DTYPE_F32, reachable);
+  return c;
+}
+
+void make_block(fu_engine* e, Block& b, const std::string& prefix, int cin, int cout) {
+  const fu_config& c = e->cfg;
+  b.Cin = cin; b.C = cout; b.has_res = c.do_res != 0;
+  if (b.has_res) b.res = make_conv(e, prefix + ".res_conv1x1", cin, cout, 1, true, false, true);
+  int idx = 0, ci = cin;
+  for (int d = 0; d < c.block_depth; ++d) {
+    b.convs.push_back(make_conv(e, prefix + ".block." + std::to_string(idx), ci, cout, 3, true, false, true));
+    idx += 2;
+    if (c.batch_norm) {
+      BNL bn;
+      bn.C = cout;
+      const std::string p = prefix + ".block." + std::to_string(idx);
+      bn.i_gamma = add_tensor(e, p + ".weight", {cout}, FU_KIND_PARAM, FU_DTYPE_F32, true);
+      bn.i_beta = add_tensor(e, p + ".bias", {cout}, FU_KIND_PARAM, FU_DTYPE_F32, true);
+      bn.i_rm = add_tensor(e, p + ".running_mean", {cout}, FU_KIND_BUFFER, FU_DTYPE_F32, false);
+      bn.i_rv = add_tensor(e, p + ".running_var", {cout}, FU_KIND_BUFFER, FU_DTYPE_F32, false);
+      bn.i_nbt = add_tensor(e, p + ".num_batches_tracked", {}, FU_KIND_BUFFER, FU_DTYPE_I64, false);
+      b.bns.push_back(bn);
+      idx += 1;
+    }
+    ci = cout;
+  }
+}
+
+int build_schema(fu_engine* e) {
+  const fu_config& c = e->cfg;
+  e->chans.clear();
+  for (int i = 0; i < c.depth; ++i) e->chans.push_back(1 << (c.wf + i));
+  if (!c.max_pool)
+    for (int i = 0; i < c.depth; ++i)
+      e->downc.push_back(make_conv(e, "downsample_convs." + std::to_string(i), e->chans[i], e->chans[i], 2,
+                                   true, false, i != c.depth - 1));
+  int prev = c.in_channels;
+  e->enc.resize(c.depth);
+  for (int i = 0; i < c.depth; ++i) {
+    make_block(e, e->enc[i], "down_path." + std::to_string(i), prev, e->chans[i]);
+    prev = e->chans[i];
+  }
+  e->dec.resize(c.depth - 1);
+  for (int j = 0; j < c.depth - 1; ++j) {
+    const int lvl = c.depth - 2 - j;
+    const int co = e->chans[lvl];
+    e->upc.push_back(make_conv(e, "up_path." + std::to_string(j) + ".up", prev, co, 2, true, true, true));
+    make_block(e, e->dec[j], "up_path." + std::to_string(j) + ".conv_block", prev, co);
+    prev = co;
+  }
+  e->Cf = prev;
+  e->seg = make_conv(e, "seg_conv", prev, c.n_classes, 1, false, false, true);
+  if (c.num_lands > 0) {
+    int nf = c.lands_num_1x1 > 1 ? c.num_lands + c.n_classes : c.num_lands;
+    e->lands.push_back(make_conv(e, "lands_1x1.0", prev + c.n_classes, nf, 1, false, false, true));
+    for (int k = 0; k < c.lands_num_1x1 - 1; ++k) {
+      e->lands.push_back(make_conv(e, "lands_1x1." + std::to_string(k + 1), nf, c.num_lands, 1, false, false, true));
+      nf = c.num_lands;
+    }
+  }
+  e->Cpad = pad_to(e->Cf + c.n_classes, 8);
+  return FU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// persistent device memory: packed weights, BN scratch
+// ---------------------------------------------------------------------------
+
+void conv_pack_sizes(ConvW& c, bool shuffle_fwd, bool shuffle_dgrad) {
+  // forward GEMM columns / data-gradient GEMM columns
+  if (c.transposed) {           // ConvTranspose2d(Cin,Cout,2,2): fwd = shuffle GEMM, dgrad = 2x2/s2 conv
+    c.n_fwd = 4 * c.Cout; c.n_dgrad = c.Cin;
+  } else if (c.k == 2) {        // Conv2d(C,C,2,stride 2): fwd = 2x2/s2 conv, dgrad = shuffle GEMM
+    c.n_fwd = c.Cout; c.n_dgrad = 4 * c.Cin;
+  } else {
+    c.n_fwd = c.Cout; c.n_dgrad = c.Cin;
+  }
+  c.npad_fwd = pad_to(c.n_fwd, 4);
+  c.npad_dgrad = pad_to(c.n_dgrad, 4);
+  (void)shuffle_fwd; (void)shuffle_dgrad;
+}
+
+template <typename F>
+void for_each_conv(fu_engine* e, F f) {
+  for (auto& c : e->downc) f(c);
+  for (auto& b : e->enc) { if (b.has_res) f(b.res); for (auto& c : b.convs) f(c); }
+  for (auto& c : e->upc) f(c);
+  for (auto& b : e->dec) { if (b.has_res) f(b.res); for (auto& c : b.convs) f(c); }
+  f(e->seg);
+  for (auto& c : e->lands) f(c);
+}
+template <typename F>
+void for_each_bn(fu_engine* e, F f) {
+  for (auto& b : e->enc) for (auto& bn : b.bns) f(bn);
+  for (auto& b : e->dec) for (auto& bn : b.bns) f(bn);
+}
+
+void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db) {
+  int maxc = 4;
+  for_each_conv(e, [&](ConvW& c) {
+    conv_pack_sizes(c, false, false);
+    const int taps_f = c.transposed ? 1 : c.k * c.k;
+    const int k_f = c.Cin;
+    c.wp_fwd = w.take<float>((size_t)taps_f * k_f * c.npad_fwd);
+    const int taps_d = c.transposed ? 4 : (c.k == 2 ? 1 : c.k * c.k);
+    c.wp_dgrad = w.take<float>((size_t)taps_d * c.Cout * c.npad_dgrad);
+    c.bsum = db.take<double>(c.Cout);
+    if (c.Cout > maxc) maxc = c.Cout;
+    if (c.Cin > maxc) maxc = c.Cin;
+    tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision == FU_PRECISION_BF16, w);
+  });
+  for_each_bn(e, [&](BNL& b) {
+    b.stat = df.take<double>(2 * b.C);
+    b.bstat = db.take<double>(2 * b.C);
+    b.mean = w.take<float>(b.C); b.invstd = w.take<float>(b.C);
+    b.a = w.take<float>(b.C); b.b = w.take<float>(b.C);
+    b.ga = w.take<float>(b.C); b.m1 = w.take<float>(b.C); b.m2 = w.take<float>(b.C);
+  });
+  e->ones = w.take<float>(maxc);
+  e->zeros = w.take<float>(maxc);
+}
+
+int alloc_persistent(fu_engine* e) {
+  Bump w, df, db;
+  carve_persistent(e, w, df, db);
+  e->wmem_bytes = w.off + 256;
+  e->dscr_fwd_bytes = df.off + 256;
+  e->dscr_bwd_bytes = db.off + 256;
+  CUDA_TRY(e, cudaMalloc(&e->wmem, e->wmem_bytes));
+  CUDA_TRY(e, cudaMalloc(&e->dscr_fwd, e->dscr_fwd_bytes));
+  CUDA_TRY(e, cudaMalloc(&e->dscr_bwd, e->dscr_bwd_bytes));
+  CUDA_TRY(e, cudaMemset(e->wmem, 0, e->wmem_bytes));
+  Bump w2, df2, db2;
+  w2.base = e->wmem; df2.base = reinterpret_cast<char*>(e->dscr_fwd); db2.base = reinterpret_cast<char*>(e->dscr_bwd);
+  carve_persistent(e, w2, df2, db2);
+  // ones / zeros
+  int maxc = 4;
+  for_each_conv(e, [&](ConvW& c) { if (c.Cout > maxc) maxc = c.Cout; if (c.Cin > maxc) maxc = c.Cin; });
+  std::vector<float> h(maxc, 1.f);
+  CUDA_TRY(e, cudaMemcpy(e->ones, h.data(), maxc * sizeof(float), cudaMemcpyHostToDevice));
+  return FU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// plan: activation arena for (B,H,W)
+// ---------------------------------------------------------------------------
+View take_view(Bump& b, long long pixels, int C, int ld, int esz) {
+  View v;
+  v.p = b.take<char>((size_t)pixels * ld * esz);
+  v.C = C;
+  v.ld = ld;
+  return v;
+}
+
+void carve_plan(fu_engine* e, Plan& pl, Bump& b, int B, int H, int W) {
+  const fu_config& c = e->cfg;
+  const int esz = e->esz;
+  const int D = c.depth;
+  auto pix = [&](int lvl) { return (long long)B * (H >> lvl) * (W >> lvl); };
+  pl.xin = take_view(b, pix(0), c.in_channels, c.in_channels, esz);
+  pl.cat.assign(D, View()); pl.d_cat.assign(D, View());
+  pl.down.assign(D, View()); pl.d_down.assign(D, View());
+  pl.decout.assign(D, View()); pl.d_decout.assign(D, View());
+  pl.hcat = take_view(b, pix(0), e->Cpad, e->Cpad, esz);
+  pl.d_hcat = take_view(b, pix(0), e->Cpad, e->Cpad, esz);
+  for (int l = 0; l < D - 1; ++l) {
+    pl.cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz);
+    pl.d_cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz);
+  }
+  for (int l = 1; l < D; ++l) {
+    pl.down[l] = take_view(b, pix(l), e->chans[l - 1], e->chans[l - 1], esz);
+    pl.d_down[l] = take_view(b, pix(l), e->chans[l - 1], e->chans[l - 1], esz);
+  }
+  if (D > 1) {
+    pl.bott = take_view(b, pix(D - 1), e->chans[D - 1], e->chans[D - 1], esz);
+    pl.d_bott = take_view(b, pix(D - 1), e->chans[D - 1], e->chans[D - 1], esz);
+  }
+  for (int l = 1; l < D - 1; ++l) {
+    pl.decout[l] = take_view(b, pix(l), e->chans[l], e->chans[l], esz);
+    pl.d_decout[l] = take_view(b, pix(l), e->chans[l], e->chans[l], esz);
+  }
+  // the last block of the network writes its output straight into the head's concat buffer
+  pl.decout[0] = slice(pl.hcat, 0, e->Cf, esz);
+  pl.d_decout[0] = slice(pl.d_hcat, 0, e->Cf, esz);
+  auto carve_block = [&](Block& blk, int lvl, const View& outv) {
+    const int nd = (int)blk.convs.size();
+    blk.r.assign(nd, View()); blk.z.assign(nd, View()); blk.dy.assign(nd, View()); blk.dz.assign(nd, View());
+    for (int i = 0; i < nd; ++i) {
+      if (i == nd - 1 && blk.bns.empty() && !blk.has_res) blk.r[i] = outv;  // ReLU output IS the block output
+      else blk.r[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
+      if (!blk.bns.empty() && i < nd - 1) blk.z[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
+      blk.dy[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
+      if (i > 0) blk.dz[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
+    }
+  };
+  for (int l = 0; l < D; ++l)
+    carve_block(e->enc[l], l, D == 1 ? pl.decout[0] : (l < D - 1 ? slice(pl.cat[l], e->chans[l], e->chans[l], esz) : pl.bott));
+  for (int j = 0; j < D - 1; ++j) carve_block(e->dec[j], D - 2 - j, pl.decout[D - 2 - j]);
+  pl.hmid.clear(); pl.d_hmid.clear();
+  for (size_t k = 0; k + 1 < e->lands.size(); ++k) {
+    const int n = e->lands[k].Cout;
+    pl.hmid.push_back(take_view(b, pix(0), n, pad_to(n, 8), esz));
+    pl.d_hmid.push_back(take_view(b, pix(0), n, pad_to(n, 8), esz));
+  }
+  if (c.num_lands > 0) pl.dheat = take_view(b, pix(0), c.num_lands, pad_to(c.num_lands, 8), esz);
+}
+
+int ensure_plan(fu_engine* e, int B, int H, int W) {
+  Plan& pl = e->plan;
+  if (pl.valid && pl.B == B && pl.H == H && pl.W == W) return FU_OK;
+  const int D = e->cfg.depth;
+  if (B < 1 || H < 1 || W < 1 || (H % (1 << (D - 1))) || (W % (1 << (D - 1))))
+    return e->fail(FU_ERR_UNSUPPORTED_SHAPE,
+                   "input %dx%dx%d: H and W must be positive multiples of 2^(depth-1)=%d (the reference "
+                   "pads tiles to --unet-img-dim, dataset.py:26-40)", B, H, W, 1 << (D - 1));
+  if ((long long)B * H * W > (1ll << 31) - 1)
+    return e->fail(FU_ERR_UNSUPPORTED_SHAPE, "B*H*W too large");
+  Bump dry;
+  Plan tmp;
+  carve_plan(e, tmp, dry, B, H, W);
+  const size_t need = dry.off + 256;
+  if (need > pl.arena_bytes) {
+    if (pl.arena) {
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      CUDA_TRY(e, cudaFree(pl.arena));
+      pl.arena = nullptr;
+      pl.arena_bytes = 0;
+    }
+    CUDA_TRY(e, cudaMalloc(&pl.arena, need));
+    pl.arena_bytes = need;
+  }
+  Bump real;
+  real.base = pl.arena;
+  carve_plan(e, pl, real, B, H, W);
+  pl.B = B; pl.H = H; pl.W = W;
+  pl.valid = true;
+  e->saved = false;
+  e->cnt.arena_bytes = (int64_t)pl.arena_bytes;
+  return FU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// weight packing (CUDA-core layouts); tensor-core layouts are packed in kernels_tc.cuh
+// ---------------------------------------------------------------------------
+int pack_one(fu_engine* e, const float* src, float* dst, int T, int K, int N, int Npad, int Ninner, int flip,
+             long long st, long long sk, long long snh, long long snl) {
+  PackArgs a;
+  a.src = src; a.dst = dst; a.T = T; a.K = K; a.N = N; a.Npad = Npad; a.Ninner = Ninner; a.flip = flip;
+  a.st = st; a.sk = sk; a.snh = snh; a.snl = snl;
+  const long long total = (long long)T * K * Npad;
+  LAUNCH(e, pack_weights_kernel, grid1d(total, 256, e->num_sms), 256, a);
+  return FU_OK;
+}
+
+int pack_conv(fu_engine* e, ConvW& c) {
+  const float* w = reinterpret_cast<const float*>(e->tensors[c.w_idx].data);
+  int rc;
+  if (c.transposed) {
+    // W[ci][co][ab].  fwd: [1][Cin][(ab)*Cout+co];  dgrad (2x2/s2 conv over dY): [tap=ab][Cout][Cin]
+    if ((rc = pack_one(e, w, c.wp_fwd, 1, c.Cin, 4 * c.Cout, c.npad_fwd, c.Cout, 0, 0, (long long)c.Cout * 4, 1, 4))) return rc;
+    if ((rc = pack_one(e, w, c.wp_dgrad, 4, c.Cout, c.Cin, c.npad_dgrad, c.Cin, 0, 1, 4, 0, (long long)c.Cout * 4))) return rc;
+  } else if (c.k == 2) {
+    // W[co][ci][ab].  fwd: [tap=ab][Cin][Cout];  dgrad (shuffle GEMM): [1][Cout][(ab)*Cin+ci]
+    if ((rc = pack_one(e, w, c.wp_fwd, 4, c.Cin, c.Cout, c.npad_fwd, c.Cout, 0, 1, 4, 0, (long long)c.Cin * 4))) return rc;
+    if ((rc = pack_one(e, w, c.wp_dgrad, 1, c.Cout, 4 * c.Cin, c.npad_dgrad, c.Cin, 0, 0, (long long)c.Cin * 4, 1, 4))) return rc;
+  } else {
+    const int kk = c.k * c.k;
+    // W[co][ci][tap].  fwd: [tap][Cin][Cout];  dgrad: [flip(tap)][Cout][Cin]
+    if ((rc = pack_one(e, w, c.wp_fwd, kk, c.Cin, c.Cout, c.npad_fwd, c.Cout, 0, 1, kk, 0, (long long)c.Cin * kk))) return rc;
+    if ((rc = pack_one(e, w, c.wp_dgrad, kk, c.Cout, c.Cin, c.npad_dgrad, c.Cin, 1, 1, (long long)c.Cin * kk, 0, kk))) return rc;
+  }
+  if (e->cfg.precision == FU_PRECISION_BF16) {
+    if ((rc = tc_pack(c.tc, w, e->stream, &e->cnt))) return e->fail(FU_ERR_CUDA, "tensor-core weight pack failed");
+  }
+  return FU_OK;
+}
+
+int pack_all(fu_engine* e, bool training) {
+  int rc = FU_OK;
+  const int last = e->cfg.depth - 1;
+  int di = 0;
+  for (auto& c : e->downc) { if (di++ != last && rc == FU_OK) rc = pack_conv(e, c); }
+  auto blk = [&](Block& b) {
+    if (b.has_res && rc == FU_OK) rc = pack_conv(e, b.res);
+    for (auto& c : b.convs) if (rc == FU_OK) rc = pack_conv(e, c);
+  };
+  for (auto& b : e->enc) blk(b);
+  for (auto& c : e->upc) if (rc == FU_OK) rc = pack_conv(e, c);
+  for (auto& b : e->dec) blk(b);
+  if (rc == FU_OK) rc = pack_conv(e, e->seg);
+  for (auto& c : e->lands) if (rc == FU_OK) rc = pack_conv(e, c);
+  (void)training;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+struct ConvCall {
+  View x; int B = 0, Hi = 0, Wi = 0;
+  View y; int Ho = 0, Wo = 0;
+  const float* w = nullptr; int N = 0, Npad = 0;
+  const float* bias = nullptr; int bias_mod = 1;
+  int KH = 1, stride = 1, pad = 0;
+  int relu = 0, accumulate = 0, shuffle = 0;
+  float* nchw_out = nullptr;
+  View t; const float* bn_a = nullptr; const float* bn_b = nullptr; bool has_t = false;
+  double* stat = nullptr;
+};
+
+template <typename T>
+int run_igemm(fu_engine* e, const ConvCall& c) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = c.x.p; a.x_ld = c.x.ld;
+  a.y = c.nchw_out ? (void*)c.nchw_out : (void*)c.y.p; a.y_ld = c.y.ld;
+  a.w = c.w; a.bias = c.bias; a.bias_mod = c.bias_mod > 0 ? c.bias_mod : 1;
+  a.B = c.B; a.Hi = c.Hi; a.Wi = c.Wi; a.Cin = c.x.C;
+  a.Ho = c.Ho; a.Wo = c.Wo; a.N = c.N; a.Npad = c.Npad;
+  a.KH = c.KH; a.KW = c.KH; a.stride = c.stride; a.pad = c.pad;
+  a.relu = c.relu; a.accumulate = c.accumulate; a.shuffle = c.shuffle;
+  a.nchw_out = c.nchw_out ? 1 : 0;
+  if (c.has_t) { a.t = c.t.p; a.t_ld = c.t.ld; a.bn_a = c.bn_a; a.bn_b = c.bn_b; }
+  a.stat = c.stat;
+  const size_t va = 4 * sizeof(T);
+  const bool vec_in = (c.x.C % 4 == 0) && (c.x.ld % 4 == 0) && aligned(c.x.p, va);
+  bool vec_out = !c.nchw_out && (c.N % 4 == 0) && (c.y.ld % 4 == 0) && aligned(c.y.p, va);
+  if (c.shuffle && ((c.N / 4) % 4 != 0)) vec_out = false;
+  if (c.has_t && !((c.t.ld % 4 == 0) && aligned(c.t.p, va))) vec_out = false;
+  a.vec_out = vec_out ? 1 : 0;
+  const long long M = (long long)c.B * c.Ho * c.Wo;
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((c.N + 63) / 64));
+  if (vec_in) LAUNCH(e, (igemm_simt_kernel<T, true>), grid, 256, a);
+  else LAUNCH(e, (igemm_simt_kernel<T, false>), grid, 256, a);
+  return FU_OK;
+}
+
+struct WgradCall {
+  View big; int Hb = 0, Wb = 0;
+  View small; int Hs = 0, Ws = 0;
+  int B = 0, KH = 1, stride = 1, pad = 0;
+  float* dw = nullptr; long long s_tap = 0, s_big = 0, s_small = 0;
+};
+
+template <typename T>
+int run_wgrad(fu_engine* e, const WgradCall& c) {
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.big = c.big.p; a.big_ld = c.big.ld; a.Hb = c.Hb; a.Wb = c.Wb; a.Cb = c.big.C;
+  a.small = c.small.p; a.small_ld = c.small.ld; a.Hs = c.Hs; a.Ws = c.Ws; a.Cs = c.small.C;
+  a.B = c.B; a.KH = c.KH; a.KW = c.KH; a.stride = c.stride; a.pad = c.pad;
+  a.dw = c.dw; a.s_tap = c.s_tap; a.s_big = c.s_big; a.s_small = c.s_small;
+  const int tb = (c.big.C + 63) / 64, ts = (c.small.C + 63) / 64, taps = c.KH * c.KH;
+  a.tiles_small = ts;
+  const long long M = (long long)c.B * c.Hs * c.Ws;
+  long long tiles = (long long)tb * ts * taps;
+  long long splits = ((long long)e->num_sms * 4 + tiles - 1) / tiles;
+  const long long max_splits = (M + 63) / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  long long pps = (M + splits - 1) / splits;
+  pps = (pps + 15) / 16 * 16;
+  splits = (M + pps - 1) / pps;
+  a.pix_per_split = (int)pps;
+  const size_t va = 4 * sizeof(T);
+  const bool vec = (c.big.C % 4 == 0) && (c.big.ld % 4 == 0) && aligned(c.big.p, va) &&
+                   (c.small.C % 4 == 0) && (c.small.ld % 4 == 0) && aligned(c.small.p, va);
+  dim3 grid((unsigned)(tb * ts), (unsigned)taps, (unsigned)splits);
+  if (vec) LAUNCH(e, (wgrad_simt_kernel<T, true>), grid, 256, a);
+  else LAUNCH(e, (wgrad_simt_kernel<T, false>), grid, 256, a);
+  return FU_OK;
+}
+
+inline dim3 red_grid(fu_engine* e, long long P, int C) {
+  const int cvecs = C / 4;
+  const int lanes = cvecs < 256 ? cvecs : 256;
+  const int rows = 256 / lanes;
+  long long gx = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);
+  const long long cap = (long long)e->num_sms * 8;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)((cvecs + lanes - 1) / lanes));
+}
+
+float* tdata(fu_engine* e, int idx) { return idx < 0 ? nullptr : reinterpret_cast<float*>(e->tensors[idx].data); }
+float* gptr(fu_engine* e, float* flat, int idx) {
+  if (idx < 0) return nullptr;
+  const int64_t off = e->tensors[idx].info.grad_offset;
+  return off < 0 ? nullptr : flat + off;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+template <typename T>
+int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, int H, int W, int relu,
+                 double* stat, const View* t, const float* bn_a, const float* bn_b) {
+  // 3x3/pad1 or 1x1 convolution, stride 1
+  if (tc_conv_eligible(cw.tc, x.p, x.ld, y.p, y.ld, t ? t->p : nullptr, t ? t->ld : 0)) {
+    int rc = tc_conv_forward(cw.tc, x.p, x.ld, y.p, y.ld, B, H, W, tdata(e, cw.b_idx), relu, stat,
+                             t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt);
+    if (rc) return e->fail(FU_ERR_CUDA, "tensor-core conv launch failed: %s", tc_last_error());
+    return FU_OK;
+  }
+  ConvCall c;
+  c.x = x; c.B = B; c.Hi = H; c.Wi = W; c.y = y; c.Ho = H; c.Wo = W;
+  c.w = cw.wp_fwd; c.N = cw.n_fwd; c.Npad = cw.npad_fwd;
+  c.bias = tdata(e, cw.b_idx); c.bias_mod = cw.Cout;
+  c.KH = cw.k; c.stride = 1; c.pad = cw.k / 2; c.relu = relu; c.stat = stat;
+  if (t) { c.t = *t; c.has_t = true; c.bn_a = bn_a; c.bn_b = bn_b; }
+  return run_igemm<T>(e, c);
+}
+
+template <typename T>
+int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, int B, int H, int W, int training) {
+  const int nd = (int)blk.convs.size();
+  const bool bn = !blk.bns.empty();
+  const long long P = (long long)B * H * W;
+  View cur = x_in;
+  int rc;
+  for (int i = 0; i < nd; ++i) {
+    View r = blk.r[i];   // (aliases `out` when the block ends in a bare ReLU, see carve_plan)
+    double* stat = (bn && training) ? blk.bns[i].stat : nullptr;
+    if ((rc = conv_forward<T>(e, blk.convs[i], cur, r, B, H, W, 1, stat, nullptr, nullptr, nullptr))) return rc;
+    if (bn) {
+      BNL& b = blk.bns[i];
+      LAUNCH(e, bn_finalize_kernel, (b.C + 127) / 128, 128, b.stat, P, b.C, training, tdata(e, b.i_gamma),
+             tdata(e, b.i_beta), tdata(e, b.i_rm), tdata(e, b.i_rv),
+             reinterpret_cast<long long*>(e->tensors[b.i_nbt].data), 0.1f, 1e-5f, b.mean, b.invstd, b.a, b.b);
+      if (i < nd - 1 || !blk.has_res) {
+        View z = (i == nd - 1) ? out : blk.z[i];
+        LAUNCH(e, (bn_apply_kernel<T>), grid1d(P * (b.C / 4), 256, e->num_sms), 256,
+               reinterpret_cast<const T*>(r.p), r.ld, reinterpret_cast<T*>(z.p), z.ld, b.a, b.b, P, b.C);
+        cur = z;
+      } else {
+        cur = r;
+      }
+    } else {
+      cur = r;
+    }
+  }
+  if (blk.has_res) {
+    // out = BN_last(r_last) + res_conv1x1(x_in)   (unet.py:229-231), one pass
+    const View& t = blk.r[nd - 1];
+    const float* a = bn ? blk.bns[nd - 1].a : e->ones;
+    const float* b = bn ? blk.bns[nd - 1].b : e->zeros;
+    if ((rc = conv_forward<T>(e, blk.res, x_in, out, B, H, W, 0, nullptr, &t, a, b))) return rc;
+  }
+  return FU_OK;
+}
+
+template <typename T>
+int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, float* seg, float* logits,
+              float* heat) {
+  const fu_config& c = e->cfg;
+  Plan& pl = e->plan;
+  const int D = c.depth;
+  const int esz = e->esz;
+  int rc;
+  if (training && c.batch_norm) CUDA_TRY(e, cudaMemsetAsync(e->dscr_fwd, 0, e->dscr_fwd_bytes, e->stream));
+  const long long HW = (long long)H * W;
+  LAUNCH(e, (nchw_to_nhwc_kernel<T>), grid1d((long long)B * HW, 256, e->num_sms), 256, x,
+         reinterpret_cast<T*>(pl.xin.p), pl.xin.ld, B, c.in_channels, HW);
+  View cur = pl.xin;
+  for (int l = 0; l < D; ++l) {
+    const int h = H >> l, w = W >> l;
+    View outv = (D == 1) ? pl.decout[0] : (l < D - 1 ? slice(pl.cat[l], e->chans[l], e->chans[l], esz) : pl.bott);
+    if ((rc = block_forward<T>(e, e->enc[l], cur, outv, B, h, w, training))) return rc;
+    if (l < D - 1) {
+      View dn = pl.down[l + 1];
+      if (c.max_pool) {
+        LAUNCH(e, (maxpool_fwd_kernel<T>), grid1d((long long)B * (h / 2) * (w / 2) * (outv.C / 4), 256, e->num_sms),
+               256, reinterpret_cast<const T*>(outv.p), outv.ld, reinterpret_cast<T*>(dn.p), dn.ld, B, h / 2,
+               w / 2, outv.C);
+      } else {
+        ConvW& cw = e->downc[l];
+        if (tc_down_eligible(cw.tc, outv.p, outv.ld, dn.p, dn.ld)) {
+          if (tc_down_forward(cw.tc, outv.p, outv.ld, dn.p, dn.ld, B, h, w, tdata(e, cw.b_idx), e->stream, &e->cnt))
+            return e->fail(FU_ERR_CUDA, "tensor-core downsample launch failed: %s", tc_last_error());
+        } else {
+          ConvCall cc;
+          cc.x = outv; cc.B = B; cc.Hi = h; cc.Wi = w; cc.y = dn; cc.Ho = h / 2; cc.Wo = w / 2;
+          cc.w = cw.wp_fwd; cc.N = cw.n_fwd; cc.Npad = cw.npad_fwd; cc.bias = tdata(e, cw.b_idx);
+          cc.bias_mod = cw.Cout; cc.KH = 2; cc.stride = 2; cc.pad = 0;
+          if ((rc = run_igemm<T>(e, cc))) return rc;
+        }
+      }
+      cur = dn;
+    } else {
+      cur = outv;
+    }
+  }
+  for (int j = 0; j < D - 1; ++j) {
+    const int l = D - 2 - j;
+    const int h = H >> l, w = W >> l;
+    ConvW& up = e->upc[j];
+    View upv = slice(pl.cat[l], 0, e->chans[l], esz);
+    if (tc_up_eligible(up.tc, cur.p, cur.ld, upv.p, upv.ld)) {
+      if (tc_up_forward(up.tc, cur.p, cur.ld, upv.p, upv.ld, B, h / 2, w / 2, tdata(e, up.b_idx), e->stream, &e->cnt))
+        return e->fail(FU_ERR_CUDA, "tensor-core upconv launch failed: %s", tc_last_error());
+    } else {
+      ConvCall cc;
+      cc.x = cur; cc.B = B; cc.Hi = h / 2; cc.Wi = w / 2; cc.y = upv; cc.Ho = h / 2; cc.Wo = w / 2;
+      cc.w = up.wp_fwd; cc.N = up.n_fwd; cc.Npad = up.npad_fwd; cc.bias = tdata(e, up.b_idx);
+      cc.bias_mod = up.Cout; cc.KH = 1; cc.stride = 1; cc.pad = 0; cc.shuffle = 1;
+      if ((rc = run_igemm<T>(e, cc))) return rc;
+    }
+    if ((rc = block_forward<T>(e, e->dec[j], pl.cat[l], pl.decout[l], B, h, w, training))) return rc;
+    cur = pl.decout[l];
+  }
+  // ---- heads (unet.py:176-191) ----
+  View feat = slice(pl.hcat, 0, e->Cf, esz);
+  View lg = slice(pl.hcat, e->Cf, c.n_classes, esz);
+  {
+    ConvCall cc;
+    cc.x = feat; cc.B = B; cc.Hi = H; cc.Wi = W; cc.y = lg; cc.Ho = H; cc.Wo = W;
+    cc.w = e->seg.wp_fwd; cc.N = e->seg.n_fwd; cc.Npad = e->seg.npad_fwd;
+    if ((rc = run_igemm<T>(e, cc))) return rc;
+  }
+  LAUNCH(e, (softmax_fwd_kernel<T>), grid1d((long long)B * HW, 128, e->num_sms), 128,
+         reinterpret_cast<const T*>(lg.p), lg.ld, B, c.n_classes, HW, c.do_soft_max, seg, logits);
+  if (c.num_lands > 0) {
+    View hc = slice(pl.hcat, 0, e->Cf + c.n_classes, esz);
+    for (size_t k = 0; k < e->lands.size(); ++k) {
+      ConvCall cc;
+      cc.x = hc; cc.B = B; cc.Hi = H; cc.Wi = W; cc.Ho = H; cc.Wo = W;
+      cc.w = e->lands[k].wp_fwd; cc.N = e->lands[k].n_fwd; cc.Npad = e->lands[k].npad_fwd;
+      if (k + 1 == e->lands.size()) cc.nchw_out = heat;
+      else cc.y = pl.hmid[k];
+      if ((rc = run_igemm<T>(e, cc))) return rc;
+      if (k + 1 < e->lands.size()) hc = pl.hmid[k];
+    }
+  }
+  return FU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------
+template <typename T>
+int channel_sum_to(fu_engine* e, const View& d, long long P, double* scratch, float* dst) {
+  LAUNCH(e, (channel_sum_kernel<T>), red_grid(e, P, d.C), 256, reinterpret_cast<const T*>(d.p), d.ld, P, d.C, scratch);
+  LAUNCH(e, sum_to_float_kernel, (d.C + 127) / 128, 128, scratch, dst, d.C);
+  return FU_OK;
+}
+
+// gradient of a stride-1 conv (3x3/pad1 or 1x1) w.r.t. its input
+template <typename T>
+int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, int H, int W, int accumulate) {
+  if (tc_dgrad_eligible(cw.tc, dy.p, dy.ld, dx.p, dx.ld)) {
+    if (tc_conv_dgrad(cw.tc, dy.p, dy.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt))
+      return e->fail(FU_ERR_CUDA, "tensor-core dgrad launch failed: %s", tc_last_error());
+    return FU_OK;
+  }
+  ConvCall c;
+  c.x = dy; c.B = B; c.Hi = H; c.Wi = W; c.y = dx; c.Ho = H; c.Wo = W;
+  c.w = cw.wp_dgrad; c.N = cw.n_dgrad; c.Npad = cw.npad_dgrad;
+  c.KH = cw.k; c.stride = 1; c.pad = cw.k / 2; c.accumulate = accumulate;
+  return run_igemm<T>(e, c);
+}
+
+// gradient of a stride-1 conv w.r.t. its weight, written in the torch layout (Cout,Cin,k,k)
+template <typename T>
+int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, int H, int W, float* dw) {
+  if (tc_wgrad_eligible(cw.tc, x.p, x.ld, dy.p, dy.ld)) {
+    if (tc_conv_wgrad(cw.tc, x.p, x.ld, dy.p, dy.ld, B, H, W, dw, e->stream, &e->cnt))
+      return e->fail(FU_ERR_CUDA, "tensor-core wgrad launch failed: %s", tc_last_error());
+    return FU_OK;
+  }
+  WgradCall c;
+  c.big = x; c.Hb = H; c.Wb = W; c.small = dy; c.Hs = H; c.Ws = W; c.B = B;
+  c.KH = cw.k; c.stride = 1; c.pad = cw.k / 2;
+  c.dw = dw; c.s_tap = 1; c.s_big = (long long)cw.k * cw.k; c.s_small = (long long)cw.Cin * cw.k * cw.k;
+  return run_wgrad<T>(e, c);
+}
+
+template <typename T>
+int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, const View* d_in, int B, int H,
+                   int W, int training, float* flat) {
+  const int nd = (int)blk.convs.size();
+  const bool bn = !blk.bns.empty();
+  const long long P = (long long)B * H * W;
+  int rc;
+  if (blk.has_res) {
+    if ((rc = conv_wgrad<T>(e, blk.res, x_in, g, B, H, W, gptr(e, flat, blk.res.w_idx)))) return rc;
+    if (!bn && (rc = channel_sum_to<T>(e, g, P, blk.res.bsum, gptr(e, flat, blk.res.b_idx)))) return rc;
+  }
+  View d = g;
+  for (int i = nd - 1; i >= 0; --i) {
+    View r = blk.r[i];
+    ConvW& cw = blk.convs[i];
+    const T* dp = reinterpret_cast<const T*>(d.p);
+    if (bn) {
+      BNL& b = blk.bns[i];
+      LAUNCH(e, (bn_bwd_reduce_kernel<T>), red_grid(e, P, b.C), 256, dp, d.ld, reinterpret_cast<const T*>(r.p),
+             r.ld, b.mean, b.invstd, P, b.C, b.bstat);
+      float* g_extra = (i == nd - 1 && blk.has_res) ? gptr(e, flat, blk.res.b_idx) : nullptr;
+      LAUNCH(e, bn_bwd_finalize_kernel, (b.C + 127) / 128, 128, b.bstat, P, b.C, training, tdata(e, b.i_gamma),
+             b.invstd, gptr(e, flat, b.i_gamma), gptr(e, flat, b.i_beta), g_extra, b.ga, b.m1, b.m2);
+      LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, b.C), 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
+             reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, 1, b.mean, b.invstd, b.ga, b.m1, b.m2, P, b.C,
+             cw.bsum);
+    } else {
+      LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, blk.C), 256, dp, d.ld,
+             reinterpret_cast<const T*>(blk.r[i].p), blk.r[i].ld, reinterpret_cast<T*>(blk.dy[i].p),
+             blk.dy[i].ld, 0, nullptr, nullptr, nullptr, nullptr, nullptr, P, blk.C, cw.bsum);
+    }
+    LAUNCH(e, sum_to_float_kernel, (blk.C + 127) / 128, 128, cw.bsum, gptr(e, flat, cw.b_idx), blk.C);
+    View conv_in = (i == 0) ? x_in : (bn ? blk.z[i - 1] : blk.r[i - 1]);
+    if ((rc = conv_wgrad<T>(e, cw, conv_in, blk.dy[i], B, H, W, gptr(e, flat, cw.w_idx)))) return rc;
+    if (i > 0) {
+      if ((rc = conv_dgrad<T>(e, cw, blk.dy[i], blk.dz[i], B, H, W, 0))) return rc;
+      d = blk.dz[i];
+    } else if (d_in) {
+      if ((rc = conv_dgrad<T>(e, cw, blk.dy[0], *d_in, B, H, W, 0))) return rc;
+      if (blk.has_res && (rc = conv_dgrad<T>(e, blk.res, g, *d_in, B, H, W, 1))) return rc;
+    }
+  }
+  return FU_OK;
+}
+
+template <typename T>
+int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* flat) {
+  const fu_config& c = e->cfg;
+  Plan& pl = e->plan;
+  const int D = c.depth, esz = e->esz;
+  const int B = pl.B, H = pl.H, W = pl.W;
+  const long long HW = (long long)H * W, P0 = (long long)B * HW;
+  const int training = e->saved_training;
+  int rc;
+  CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
+  CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
+  // ---- heads ----
+  View feat = slice(pl.hcat, 0, e->Cf, esz);
+  View lg = slice(pl.hcat, e->Cf, c.n_classes, esz);
+  View d_feat = slice(pl.d_hcat, 0, e->Cf, esz);
+  View d_lg = slice(pl.d_hcat, e->Cf, c.n_classes, esz);
+  if (c.num_lands > 0 && d_heat) {
+    LAUNCH(e, (nchw_to_nhwc_kernel<T>), grid1d(P0, 256, e->num_sms), 256, d_heat, reinterpret_cast<T*>(pl.dheat.p),
+           pl.dheat.ld, B, c.num_lands, HW);
+    View dcur = pl.dheat;
+    for (int k = (int)e->lands.size() - 1; k >= 0; --k) {
+      ConvW& cw = e->lands[k];
+      View in_k = (k == 0) ? slice(pl.hcat, 0, e->Cf + c.n_classes, esz) : pl.hmid[k - 1];
+      View din_k = (k == 0) ? slice(pl.d_hcat, 0, e->Cf + c.n_classes, esz) : pl.d_hmid[k - 1];
+      if ((rc = conv_wgrad<T>(e, cw, in_k, dcur, B, H, W, gptr(e, flat, cw.w_idx)))) return rc;
+      if ((rc = conv_dgrad<T>(e, cw, dcur, din_k, B, H, W, 0))) return rc;
+      dcur = din_k;
+    }
+  } else {
+    CUDA_TRY(e, cudaMemsetAsync(pl.d_hcat.p, 0, (size_t)P0 * pl.d_hcat.ld * esz, e->stream));
+  }
+  if (d_seg) {
+    LAUNCH(e, (softmax_bwd_kernel<T>), grid1d(P0, 128, e->num_sms), 128, reinterpret_cast<const T*>(lg.p), lg.ld,
+           d_seg, reinterpret_cast<T*>(d_lg.p), d_lg.ld, B, c.n_classes, HW, c.do_soft_max, 1);
+  }
+  if ((rc = conv_wgrad<T>(e, e->seg, feat, d_lg, B, H, W, gptr(e, flat, e->seg.w_idx)))) return rc;
+  if ((rc = conv_dgrad<T>(e, e->seg, d_lg, d_feat, B, H, W, 1))) return rc;
+
+  // ---- decoder ----
+  View g = d_feat;
+  for (int j = D - 2; j >= 0; --j) {
+    const int l = D - 2 - j;
+    const int h = H >> l, w = W >> l;
+    if ((rc = block_backward<T>(e, e->dec[j], pl.cat[l], g, &pl.d_cat[l], B, h, w, training, flat))) return rc;
+    ConvW& up = e->upc[j];
+    View d_up = slice(pl.d_cat[l], 0, e->chans[l], esz);
+    View u = (l == D - 2) ? pl.bott : pl.decout[l + 1];
+    View d_u = (l == D - 2) ? pl.d_bott : pl.d_decout[l + 1];
+    if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
+    {
+      WgradCall wc;  // dW[ci][co][ab] = sum x[n,i,j,ci] * dY[n,2i+a,2j+b,co]
+      wc.big = d_up; wc.Hb = h; wc.Wb = w; wc.small = u; wc.Hs = h / 2; wc.Ws = w / 2; wc.B = B;
+      wc.KH = 2; wc.stride = 2; wc.pad = 0;
+      wc.dw = gptr(e, flat, up.w_idx); wc.s_tap = 1; wc.s_big = 4; wc.s_small = (long long)up.Cout * 4;
+      if ((rc = run_wgrad<T>(e, wc))) return rc;
+    }
+    {
+      ConvCall cc;  // dX[n,i,j,ci] = sum_{ab,co} dY[n,2i+a,2j+b,co] W[ci][co][ab]
+      cc.x = d_up; cc.B = B; cc.Hi = h; cc.Wi = w; cc.y = d_u; cc.Ho = h / 2; cc.Wo = w / 2;
+      cc.w = up.wp_dgrad; cc.N = up.n_dgrad; cc.Npad = up.npad_dgrad; cc.KH = 2; cc.stride = 2; cc.pad = 0;
+      if ((rc = run_igemm<T>(e, cc))) return rc;
+    }
+    g = d_u;
+  }
+  // ---- encoder ----
+  for (int l = D - 1; l >= 0; --l) {
+    const int h = H >> l, w = W >> l;
+    View gl = (D == 1) ? g : (l == D - 1 ? g : slice(pl.d_cat[l], e->chans[l], e->chans[l], esz));
+    View x_in = (l == 0) ? pl.xin : pl.down[l];
+    if ((rc = block_backward<T>(e, e->enc[l], x_in, gl, l == 0 ? nullptr : &pl.d_down[l], B, h, w, training, flat)))
+      return rc;
+    if (l > 0) {
+      View src = slice(pl.cat[l - 1], e->chans[l - 1], e->chans[l - 1], esz);     // encoder output of level l-1
+      View d_src = slice(pl.d_cat[l - 1], e->chans[l - 1], e->chans[l - 1], esz);  // already holds the skip gradient
+      if (c.max_pool) {
+        LAUNCH(e, (maxpool_bwd_kernel<T>), grid1d((long long)B * h * w * (src.C / 4), 256, e->num_sms), 256,
+               reinterpret_cast<const T*>(src.p), src.ld, reinterpret_cast<const T*>(pl.d_down[l].p),
+               pl.d_down[l].ld, reinterpret_cast<T*>(d_src.p), d_src.ld, B, h, w, src.C, 1);
+      } else {
+        ConvW& cw = e->downc[l - 1];
+        if ((rc = channel_sum_to<T>(e, pl.d_down[l], (long long)B * h * w, cw.bsum, gptr(e, flat, cw.b_idx)))) return rc;
+        WgradCall wc;  // dW[co][ci][ab] = sum x[n,2i+a,2j+b,ci] * dY[n,i,j,co]
+        wc.big = src; wc.Hb = 2 * h; wc.Wb = 2 * w; wc.small = pl.d_down[l]; wc.Hs = h; wc.Ws = w; wc.B = B;
+        wc.KH = 2; wc.stride = 2; wc.pad = 0;
+        wc.dw = gptr(e, flat, cw.w_idx); wc.s_tap = 1; wc.s_big = 4; wc.s_small = (long long)cw.Cin * 4;
+        if ((rc = run_wgrad<T>(e, wc))) return rc;
+        ConvCall cc;  // dX[n,2i+a,2j+b,ci] += sum_co dY[n,i,j,co] W[co][ci][ab]
+        cc.x = pl.d_down[l]; cc.B = B; cc.Hi = h; cc.Wi = w; cc.y = d_src; cc.Ho = h; cc.Wo = w;
+        cc.w = cw.wp_dgrad; cc.N = cw.n_dgrad; cc.Npad = cw.npad_dgrad; cc.KH = 1; cc.stride = 1; cc.pad = 0;
+        cc.shuffle = 1; cc.accumulate = 1;
+        if ((rc = run_igemm<T>(e, cc))) return rc;
+      }
+    }
+  }
+  return FU_OK;
+}
+
+int validate(const fu_config* c, std::string& why) {
+  char buf[256];
+  auto bad = [&](const char* m) { why = m; return FU_ERR_INVALID_CONFIG; };
+  if (!c->padding) return bad("padding=False is not supported (it also crashes the reference with do_res=True, unet.py:227-231); use padding=True");
+  if (!c->pad_mode_zeros) return bad("pad_mode must be 'zeros'");
+  if (!c->up_mode_upconv) return bad("up_mode='upsample' is not supported; use 'upconv'");
+  if (c->lands_block_depth != 0) return bad("lands_block_depth > 0 is not supported");
+  if (c->depth < 1 || c->depth > 8) return bad("depth must be in [1,8]");
+  if (c->wf < 2 || c->wf + c->depth - 1 > 12) return bad("wf must be >= 2 and 2^(wf+depth-1) <= 4096");
+  if (c->in_channels < 1 || c->in_channels > 64) return bad("in_channels must be in [1,64]");
+  if (c->n_classes < 1 || c->n_classes > kMaxClasses) return bad("n_classes must be in [1,32]");
+  if (c->num_lands < 0 || c->num_lands > 256) return bad("num_lands must be in [0,256]");
+  if (c->block_depth < 1 || c->block_depth > 8) return bad("block_depth must be in [1,8]");
+  if (c->num_lands > 0 && (c->lands_num_1x1 < 1 || c->lands_num_1x1 > 8)) return bad("lands_num_1x1 must be in [1,8]");
+  if (c->precision != FU_PRECISION_FP32 && c->precision != FU_PRECISION_BF16) return bad("precision must be FU_PRECISION_FP32 or FU_PRECISION_BF16");
+  (void)buf;
+  return FU_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int fu_engine_create(const fu_config* cfg, int device, fu_engine** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return FU_ERR_ARG; }
+  *out = nullptr;
+  std::string why;
+  int rc = validate(cfg, why);
+  if (rc) { g_create_error = why; return rc; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || device < 0 || device >= ndev) {
+    g_create_error = std::string("no usable CUDA device ") + std::to_string(device) + ": " +
+                     (ce != cudaSuccess ? cudaGetErrorString(ce) : "ordinal out of range") +
+                     " (this engine has no CPU fallback)";
+    return FU_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                     "; this library is built for sm_100a (B200) only";
+    return FU_ERR_CUDA;
+  }
+  fu_engine* e = new fu_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->esz = cfg->precision == FU_PRECISION_BF16 ? 2 : 4;
+  e->num_sms = prop.multiProcessorCount;
+  memset(&e->cnt, 0, sizeof(e->cnt));
+  cudaSetDevice(device);
+  build_schema(e);
+  rc = alloc_persistent(e);
+  if (rc) { g_create_error = e->err; delete e; return rc; }
+  *out = e;
+  return FU_OK;
+}
+
+void fu_engine_destroy(fu_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (e->plan.arena) cudaFree(e->plan.arena);
+  if (e->wmem) cudaFree(e->wmem);
+  if (e->dscr_fwd) cudaFree(e->dscr_fwd);
+  if (e->dscr_bwd) cudaFree(e->dscr_bwd);
+  delete e;
+}
+
+const char* fu_last_error(const fu_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int fu_num_tensors(const fu_engine* e) { return e ? (int)e->tensors.size() : FU_ERR_ARG; }
+
+int fu_tensor_get_info(const fu_engine* e, int index, fu_tensor_info* out) {
+  if (!e || !out || index < 0 || index >= (int)e->tensors.size()) return FU_ERR_ARG;
+  *out = e->tensors[index].info;
+  return FU_OK;
+}
+
+int64_t fu_grad_numel(const fu_engine* e) { return e ? e->grad_numel : FU_ERR_ARG; }
+
+int fu_bind_tensors(fu_engine* e, void* const* data_ptrs, int n) {
+  if (!e || !data_ptrs) return FU_ERR_ARG;
+  if (n != (int)e->tensors.size()) return e->fail(FU_ERR_ARG, "fu_bind_tensors: expected %d pointers, got %d", (int)e->tensors.size(), n);
+  bool changed = false;
+  for (int i = 0; i < n; ++i) {
+    if (!data_ptrs[i]) return e->fail(FU_ERR_ARG, "fu_bind_tensors: null pointer for %s", e->tensors[i].info.name);
+    if (!aligned(data_ptrs[i], e->tensors[i].info.dtype == FU_DTYPE_I64 ? 8 : 4))
+      return e->fail(FU_ERR_ARG, "fu_bind_tensors: misaligned pointer for %s", e->tensors[i].info.name);
+    if (e->tensors[i].data != data_ptrs[i]) changed = true;
+    e->tensors[i].data = data_ptrs[i];
+  }
+  if (changed) e->packed_once = false;
+  e->bound = true;
+  return FU_OK;
+}
+
+int fu_forward(fu_engine* e, const float* x, int B, int H, int W, int training, int save, int64_t weights_version,
+               float* seg, float* logits, float* heat, void* stream) {
+  if (!e) return FU_ERR_ARG;
+  if (!e->bound) return e->fail(FU_ERR_NOT_BOUND, "fu_forward before fu_bind_tensors");
+  if (!x || !seg) return e->fail(FU_ERR_ARG, "fu_forward: x and seg must be non-null");
+  if (e->cfg.num_lands > 0 && !heat) return e->fail(FU_ERR_ARG, "fu_forward: heat must be non-null when num_lands > 0");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  e->stream = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t l0 = e->cnt.kernel_launches;
+  int rc = ensure_plan(e, B, H, W);
+  if (rc) return rc;
+  if (!e->packed_once || e->packed_version != weights_version) {
+    if ((rc = pack_all(e, training != 0))) return rc;
+    e->packed_once = true;
+    e->packed_version = weights_version;
+  }
+  e->saved = false;
+  if (e->cfg.precision == FU_PRECISION_BF16) rc = forward_t<bf16>(e, x, B, H, W, training, seg, logits, heat);
+  else rc = forward_t<float>(e, x, B, H, W, training, seg, logits, heat);
+  if (rc) return rc;
+  e->saved = save != 0;
+  e->saved_training = training;
+  e->cnt.forward_calls++;
+  e->cnt.last_fwd_launches = e->cnt.kernel_launches - l0;
+  return FU_OK;
+}
+
+int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* flat_grads, void* stream) {
+  if (!e) return FU_ERR_ARG;
+  if (!e->saved) return e->fail(FU_ERR_STATE, "fu_backward without a saved forward (call fu_forward with save=1 first)");
+  if (!flat_grads) return e->fail(FU_ERR_ARG, "fu_backward: flat_grads must be non-null");
+  if (!aligned(flat_grads, 16)) return e->fail(FU_ERR_ARG, "fu_backward: flat_grads must be 16-byte aligned");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  e->stream = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t l0 = e->cnt.kernel_launches;
+  int rc;
+  if (e->cfg.precision == FU_PRECISION_BF16) rc = backward_t<bf16>(e, d_seg, d_heat, flat_grads);
+  else rc = backward_t<float>(e, d_seg, d_heat, flat_grads);
+  if (rc) return rc;
+  e->cnt.backward_calls++;
+  e->cnt.last_bwd_launches = e->cnt.kernel_launches - l0;
+  return FU_OK;
+}
+
+int fu_get_counters(const fu_engine* e, fu_counters* out) {
+  if (!e || !out) return FU_ERR_ARG;
+  *out = e->cnt;
+  return FU_OK;
+}
+
+const char* fu_build_info(void) {
+  return "fluoro_unet;arch=sm_100a;tcgen05=" FU_TC_BUILD ";cuda=" FU_STR(CUDART_VERSION);
+}
+
+}  // extern "C"
+
+#include "test_hooks.inl"

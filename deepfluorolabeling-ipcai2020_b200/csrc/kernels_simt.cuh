@@ -1,0 +1,689 @@
+// CUDA-core kernels of the engine (sm_100a).  They are (a) the whole parity-mode
+// (fp32) path, (b) in throughput mode every op that is HBM-bound or too thin for
+// tensor cores (BN statistics/apply, pooling, heads, C_in=1 first conv, ...), and
+// (c) the in-library cross-check for the tcgen05 kernels in kernels_tc.cuh.
+// Layout: NHWC, channel-contiguous, arbitrary pixel stride `ld` (so a tensor can
+// be a channel slice of a wider concat buffer without a copy, unet.py:257).
+#pragma once
+#include "common.cuh"
+
+namespace fu {
+
+// --------------------------------------------------------------------------
+// Implicit-GEMM convolution, generic in (k, stride, pad) and in its epilogue.
+//   Y[m, col] = sum_{tap, ci} X[pix(m) @ tap, ci] * Wp[tap][ci][col]
+// covers conv3x3/pad1, conv1x1, conv2x2/s2, their data gradients (with
+// transposed/flipped packings of the weights) and, with the pixel-shuffle
+// store, ConvTranspose2d(k=2,s=2) and the data gradient of conv2x2/s2.
+// --------------------------------------------------------------------------
+struct ConvArgs {
+  const void* x; int x_ld;
+  void* y; int y_ld;
+  const float* w;      // packed [taps][Cin][Npad], zero padded columns
+  const float* bias;   // nullable; indexed by col % bias_mod
+  int bias_mod;
+  int B, Hi, Wi, Cin;
+  int Ho, Wo, N, Npad;
+  int KH, KW, stride, pad;
+  int relu, accumulate;
+  int shuffle;         // 1: col = (a*2+b)*Cout + co -> y[n, 2oh+a, 2ow+b, co]  (N = 4*Cout)
+  int nchw_out;        // 1: y is fp32 NCHW (B,N,Ho,Wo)
+  int vec_out;         // 4 consecutive columns may be stored as one vector
+  const void* t; int t_ld; const float* bn_a; const float* bn_b;  // + bn_a[col]*t[m,col] + bn_b[col]
+  double* stat;        // nullable; [2*N]: per-column sum / sum of squares of the stored value
+};
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) igemm_simt_kernel(const ConvArgs p) {
+  constexpr int BM = 128, BN = 64, BK = 16, AP = BM + 4;
+  __shared__ __align__(16) float As[BK][AP];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const long long M = (long long)p.B * p.Ho * p.Wo;
+  const long long m_base = (long long)blockIdx.x * BM;
+  const int n_base = blockIdx.y * BN;
+  const T* xp = reinterpret_cast<const T*>(p.x);
+
+  const int a_k = (tid & 3) * 4;
+  const int a_m = tid >> 2;
+  int an[2], aoh[2], aow[2];
+  bool amv[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    long long m = m_base + a_m + i * 64;
+    amv[i] = m < M;
+    long long mm = amv[i] ? m : 0;
+    aow[i] = (int)(mm % p.Wo);
+    long long t = mm / p.Wo;
+    aoh[i] = (int)(t % p.Ho);
+    an[i] = (int)(t / p.Ho);
+  }
+  const int b_k = tid >> 4;
+  const int b_n = (tid & 15) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int kchunks = (p.Cin + BK - 1) / BK;
+  const int total = p.KH * p.KW * kchunks;
+  float4 ra[2], rb;
+
+  auto gload = [&](int it) {
+    const int tap = it / kchunks;
+    const int c0 = (it - tap * kchunks) * BK;
+    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ih = aoh[i] * p.stride + kh - p.pad, iw = aow[i] * p.stride + kw - p.pad;
+      if (amv[i] && ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi) {
+        const int c = c0 + a_k;
+        const T* src = xp + ((long long)(an[i] * p.Hi + ih) * p.Wi + iw) * p.x_ld + c;
+        if (VEC) {
+          if (c < p.Cin) v = ld4(src);
+        } else {
+          if (c < p.Cin) v.x = ld1(src);
+          if (c + 1 < p.Cin) v.y = ld1(src + 1);
+          if (c + 2 < p.Cin) v.z = ld1(src + 2);
+          if (c + 3 < p.Cin) v.w = ld1(src + 3);
+        }
+      }
+      ra[i] = v;
+    }
+    const int c = c0 + b_k;
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < p.Cin && n_base + b_n < p.Npad)
+      rb = *reinterpret_cast<const float4*>(p.w + ((long long)tap * p.Cin + c) * p.Npad + n_base + b_n);
+  };
+
+  gload(0);
+  for (int it = 0; it < total; ++it) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      As[a_k + 0][a_m + i * 64] = ra[i].x;
+      As[a_k + 1][a_m + i * 64] = ra[i].y;
+      As[a_k + 2][a_m + i * 64] = ra[i].z;
+      As[a_k + 3][a_m + i * 64] = ra[i].w;
+    }
+    *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = rb;
+    __syncthreads();
+    if (it + 1 < total) gload(it + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const int col0 = n_base + tx * 4;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+  float bias[4] = {0.f, 0.f, 0.f, 0.f}, bna[4] = {0.f, 0.f, 0.f, 0.f}, bnb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = col0 + j;
+    if (col < p.N) {
+      if (p.bias) bias[j] = p.bias[col % p.bias_mod];
+      if (p.t) { bna[j] = p.bn_a[col]; bnb[j] = p.bn_b[col]; }
+    }
+  }
+  T* yp = reinterpret_cast<T*>(p.y);
+  const T* tp = reinterpret_cast<const T*>(p.t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m_base + ty * 8 + i;
+    if (m >= M || col0 >= p.N) continue;
+    const int ow = (int)(m % p.Wo);
+    const long long tt = m / p.Wo;
+    const int oh = (int)(tt % p.Ho);
+    const int n = (int)(tt / p.Ho);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias[j];
+    if (p.t) {
+      const T* ts = tp + m * p.t_ld + col0;
+      if (p.vec_out) {
+        float4 tv = ld4(ts);
+        v[0] += bna[0] * tv.x + bnb[0]; v[1] += bna[1] * tv.y + bnb[1];
+        v[2] += bna[2] * tv.z + bnb[2]; v[3] += bna[3] * tv.w + bnb[3];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col0 + j < p.N) v[j] += bna[j] * ld1(ts + j) + bnb[j];
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.nchw_out) {
+      float* yf = reinterpret_cast<float*>(p.y);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col0 + j < p.N) yf[(((long long)n * p.N + col0 + j) * p.Ho + oh) * p.Wo + ow] = v[j];
+      continue;
+    }
+    T* dst;
+    if (p.shuffle) {
+      const int cout = p.N >> 2;
+      const int ab = col0 / cout, co = col0 - ab * cout;   // 4 consecutive columns share ab (cout % 4 == 0)
+      const int a = ab >> 1, b = ab & 1;
+      dst = yp + ((long long)(n * (2 * p.Ho) + 2 * oh + a) * (2 * p.Wo) + 2 * ow + b) * p.y_ld + co;
+    } else {
+      dst = yp + m * p.y_ld + col0;
+    }
+    if (p.vec_out) {
+      if (p.accumulate) {
+        float4 o = ld4(dst);
+        v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+      }
+      st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float r = rnd(v[j], dst); cs[j] += r; cq[j] += r * r; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (col0 + j < p.N) {
+          if (p.accumulate) v[j] += ld1(dst + j);
+          st1(dst + j, v[j]);
+          float r = rnd(v[j], dst); cs[j] += r; cq[j] += r * r;
+        }
+      }
+    }
+  }
+  if (p.stat) {
+    float* red = &As[0][0];   // 2 x [16][64]
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[ty * 64 + tx * 4 + j] = cs[j];
+      red[1024 + ty * 64 + tx * 4 + j] = cq[j];
+    }
+    __syncthreads();
+    if (tid < 128) {
+      const int which = tid >> 6, c = tid & 63;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s += red[which * 1024 + r * 64 + c];
+      const int col = n_base + c;
+      if (col < p.N) atomicAdd(&p.stat[which * p.N + col], (double)s);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Weight gradient: dW[tap][cb][cs] += sum_m BIG[pix(m)@tap, cb] * SMALL[m, cs]
+// (split over pixel ranges, fp32 atomics into a zeroed buffer, arbitrary output
+// strides so the result lands directly in the torch parameter layout).
+// --------------------------------------------------------------------------
+struct WgradArgs {
+  const void* big; int big_ld; int Hb, Wb, Cb;
+  const void* small; int small_ld; int Hs, Ws, Cs;
+  int B, KH, KW, stride, pad;
+  float* dw; long long s_tap, s_big, s_small;
+  int pix_per_split;   // multiple of 16
+  int tiles_small;     // number of 64-wide tiles over Cs
+};
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradArgs p) {
+  constexpr int BK = 16, TP = 64 + 4;
+  __shared__ __align__(16) float Bg[BK][TP];
+  __shared__ __align__(16) float Sm[BK][TP];
+  const int tid = threadIdx.x;
+  const int tile_b = blockIdx.x / p.tiles_small, tile_s = blockIdx.x - tile_b * p.tiles_small;
+  const int cb0 = tile_b * 64, cs0 = tile_s * 64;
+  const int tap = blockIdx.y;
+  const int kh = tap / p.KW, kw = tap - kh * p.KW;
+  const long long M = (long long)p.B * p.Hs * p.Ws;
+  const long long m_begin = (long long)blockIdx.z * p.pix_per_split;
+  long long m_end = m_begin + p.pix_per_split;
+  if (m_end > M) m_end = M;
+  const T* bigp = reinterpret_cast<const T*>(p.big);
+  const T* smallp = reinterpret_cast<const T*>(p.small);
+  const int l_pix = tid >> 4, l_c = (tid & 15) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float4 rb, rs;
+  auto gload = [&](long long mb) {
+    const long long m = mb + l_pix;
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    rs = rb;
+    if (m < m_end) {
+      const int ow = (int)(m % p.Ws);
+      const long long t = m / p.Ws;
+      const int oh = (int)(t % p.Hs);
+      const int n = (int)(t / p.Hs);
+      const int cs = cs0 + l_c;
+      const T* ss = smallp + m * p.small_ld + cs;
+      if (VEC) {
+        if (cs < p.Cs) rs = ld4(ss);
+      } else {
+        if (cs < p.Cs) rs.x = ld1(ss);
+        if (cs + 1 < p.Cs) rs.y = ld1(ss + 1);
+        if (cs + 2 < p.Cs) rs.z = ld1(ss + 2);
+        if (cs + 3 < p.Cs) rs.w = ld1(ss + 3);
+      }
+      const int ih = oh * p.stride + kh - p.pad, iw = ow * p.stride + kw - p.pad;
+      if (ih >= 0 && ih < p.Hb && iw >= 0 && iw < p.Wb) {
+        const int cb = cb0 + l_c;
+        const T* bs = bigp + ((long long)(n * p.Hb + ih) * p.Wb + iw) * p.big_ld + cb;
+        if (VEC) {
+          if (cb < p.Cb) rb = ld4(bs);
+        } else {
+          if (cb < p.Cb) rb.x = ld1(bs);
+          if (cb + 1 < p.Cb) rb.y = ld1(bs + 1);
+          if (cb + 2 < p.Cb) rb.z = ld1(bs + 2);
+          if (cb + 3 < p.Cb) rb.w = ld1(bs + 3);
+        }
+      }
+    }
+  };
+  if (m_begin < m_end) gload(m_begin);
+  for (long long mb = m_begin; mb < m_end; mb += BK) {
+    *reinterpret_cast<float4*>(&Bg[l_pix][l_c]) = rb;
+    *reinterpret_cast<float4*>(&Sm[l_pix][l_c]) = rs;
+    __syncthreads();
+    if (mb + BK < m_end) gload(mb + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&Bg[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Sm[k][tx * 4]);
+      const float aa[4] = {a.x, a.y, a.z, a.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cb = cb0 + ty * 4 + i;
+    if (cb >= p.Cb) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cs = cs0 + tx * 4 + j;
+      if (cs < p.Cs) atomicAdd(p.dw + tap * p.s_tap + cb * p.s_big + cs * p.s_small, acc[i][j]);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Weight packing: dst[t][k][nh*Ninner + nl] = src[tmap(t)*st + k*sk + nh*snh + nl*snl]
+// (columns >= N are zero).  One kernel covers every layout in the engine.
+// --------------------------------------------------------------------------
+struct PackArgs {
+  const float* src; float* dst;
+  int T, K, N, Npad, Ninner, flip;
+  long long st, sk, snh, snl;
+};
+__global__ void pack_weights_kernel(const PackArgs p) {
+  const long long total = (long long)p.T * p.K * p.Npad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % p.Npad);
+    const long long r = i / p.Npad;
+    const int k = (int)(r % p.K);
+    const int t = (int)(r / p.K);
+    float v = 0.f;
+    if (n < p.N) {
+      const int tm = p.flip ? (p.T - 1 - t) : t;
+      const int nh = n / p.Ninner, nl = n - nh * p.Ninner;
+      v = p.src[tm * p.st + k * p.sk + nh * p.snh + nl * p.snl];
+    }
+    p.dst[i] = v;
+  }
+}
+
+// --------------------------------------------------------------------------
+// BatchNorm (nn.BatchNorm2d, unet.py:214-215,221-222)
+// --------------------------------------------------------------------------
+// stat[0:C] = sum x, stat[C:2C] = sum x^2 over the P = B*H*W positions (train) -> per-channel
+// mean / invstd, affine fold a = gamma*invstd, b = beta - mean*a, running-stat update.
+__global__ void bn_finalize_kernel(const double* stat, long long P, int C, int training,
+                                   const float* gamma, const float* beta, float* rmean, float* rvar,
+                                   long long* nbt, float momentum, float eps,
+                                   float* mean_o, float* invstd_o, float* a_o, float* b_o) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt) *nbt += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    const double m = stat[c] / (double)P;
+    double v = stat[C + c] / (double)P - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    const double unb = P > 1 ? v * ((double)P / (double)(P - 1)) : v;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  } else {
+    mean = rmean[c];
+    var = rvar[c];
+  }
+  const float invstd = rsqrtf(var + eps);
+  const float a = gamma[c] * invstd;
+  mean_o[c] = mean;
+  invstd_o[c] = invstd;
+  a_o[c] = a;
+  b_o[c] = beta[c] - mean * a;
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const float* a, const float* b,
+                                long long P, int C) {
+  const int cv = C >> 2;
+  const long long total = P * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    const long long pix = i / cv;
+    float4 v = ld4(r + pix * r_ld + c);
+    const float4 aa = *reinterpret_cast<const float4*>(a + c);
+    const float4 bb = *reinterpret_cast<const float4*>(b + c);
+    v.x = fmaf(aa.x, v.x, bb.x); v.y = fmaf(aa.y, v.y, bb.y);
+    v.z = fmaf(aa.z, v.z, bb.z); v.w = fmaf(aa.w, v.w, bb.w);
+    st4(z + pix * z_ld + c, v);
+  }
+}
+
+// Shared thread mapping of the per-channel reductions: lanes = min(C/4, 256) channel
+// vectors across, 256/lanes pixel rows down; grid.y covers C/4 > 256.
+struct RedMap {
+  int lanes, rows, cv, prow;
+  __device__ RedMap(int C) {
+    const int cvecs = C >> 2;
+    lanes = cvecs < 256 ? cvecs : 256;
+    rows = 256 / lanes;
+    cv = blockIdx.y * lanes + (threadIdx.x % lanes);
+    prow = threadIdx.x / lanes;
+  }
+};
+
+__device__ __forceinline__ void block_channel_reduce(const RedMap& mp, float4 s, double* out, int C,
+                                                     float4* sm) {
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  if (mp.prow == 0 && mp.cv * 4 < C) {
+    float4 t = s;
+    for (int r = 1; r < mp.rows; ++r) {
+      const float4 o = sm[r * mp.lanes + (threadIdx.x % mp.lanes)];
+      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+    }
+    atomicAdd(out + mp.cv * 4 + 0, (double)t.x);
+    atomicAdd(out + mp.cv * 4 + 1, (double)t.y);
+    atomicAdd(out + mp.cv * 4 + 2, (double)t.z);
+    atomicAdd(out + mp.cv * 4 + 3, (double)t.w);
+  }
+  __syncthreads();
+}
+
+// out[0:C] += sum d ; out[C:2C] += sum d * xhat, xhat = (r - mean) * invstd
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* d, int d_ld, const T* r, int r_ld,
+                                                            const float* mean, const float* invstd,
+                                                            long long P, int C, double* out) {
+  __shared__ float4 sm[256];
+  RedMap mp(C);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (mp.cv * 4 < C) {
+    const int c = mp.cv * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+    for (long long pix = (long long)blockIdx.x * mp.rows + mp.prow; pix < P;
+         pix += (long long)gridDim.x * mp.rows) {
+      const float4 dv = ld4(d + pix * d_ld + c);
+      const float4 rv = ld4(r + pix * r_ld + c);
+      s1.x += dv.x; s1.y += dv.y; s1.z += dv.z; s1.w += dv.w;
+      s2.x += dv.x * (rv.x - mu.x) * is.x; s2.y += dv.y * (rv.y - mu.y) * is.y;
+      s2.z += dv.z * (rv.z - mu.z) * is.z; s2.w += dv.w * (rv.w - mu.w) * is.w;
+    }
+  }
+  block_channel_reduce(mp, s1, out, C, sm);
+  block_channel_reduce(mp, s2, out + C, C, sm);
+}
+
+// bstat -> d(gamma), d(beta) [, d(res bias) = sum d], and the coefficients of the
+// elementwise pass: ga = gamma*invstd, m1 = mean(d), m2 = mean(d*xhat) (0 in eval mode).
+__global__ void bn_bwd_finalize_kernel(const double* bstat, long long P, int C, int training,
+                                       const float* gamma, const float* invstd, float* g_gamma,
+                                       float* g_beta, float* g_extra, float* ga, float* m1, float* m2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = bstat[c], s2 = bstat[C + c];
+  g_gamma[c] = (float)s2;
+  g_beta[c] = (float)s1;
+  if (g_extra) g_extra[c] = (float)s1;
+  ga[c] = gamma[c] * invstd[c];
+  m1[c] = training ? (float)(s1 / (double)P) : 0.f;
+  m2[c] = training ? (float)(s2 / (double)P) : 0.f;
+}
+
+// dy = relu'(r) * (has_bn ? ga*(d - m1 - xhat*m2) : d); out[0:C] += sum dy  (= conv bias gradient)
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* d, int d_ld, const T* r, int r_ld,
+                                                      T* dy, int dy_ld, int has_bn, const float* mean,
+                                                      const float* invstd, const float* ga,
+                                                      const float* m1, const float* m2, long long P, int C,
+                                                      double* out) {
+  __shared__ float4 sm[256];
+  RedMap mp(C);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mp.cv * 4 < C) {
+    const int c = mp.cv * 4;
+    float4 mu = s, is = s, g = s, a1 = s, a2 = s;
+    if (has_bn) {
+      mu = *reinterpret_cast<const float4*>(mean + c);
+      is = *reinterpret_cast<const float4*>(invstd + c);
+      g = *reinterpret_cast<const float4*>(ga + c);
+      a1 = *reinterpret_cast<const float4*>(m1 + c);
+      a2 = *reinterpret_cast<const float4*>(m2 + c);
+    }
+    for (long long pix = (long long)blockIdx.x * mp.rows + mp.prow; pix < P;
+         pix += (long long)gridDim.x * mp.rows) {
+      const float4 dv = ld4(d + pix * d_ld + c);
+      const float4 rv = ld4(r + pix * r_ld + c);
+      float4 o;
+      if (has_bn) {
+        o.x = rv.x > 0.f ? g.x * (dv.x - a1.x - (rv.x - mu.x) * is.x * a2.x) : 0.f;
+        o.y = rv.y > 0.f ? g.y * (dv.y - a1.y - (rv.y - mu.y) * is.y * a2.y) : 0.f;
+        o.z = rv.z > 0.f ? g.z * (dv.z - a1.z - (rv.z - mu.z) * is.z * a2.z) : 0.f;
+        o.w = rv.w > 0.f ? g.w * (dv.w - a1.w - (rv.w - mu.w) * is.w * a2.w) : 0.f;
+      } else {
+        o.x = rv.x > 0.f ? dv.x : 0.f; o.y = rv.y > 0.f ? dv.y : 0.f;
+        o.z = rv.z > 0.f ? dv.z : 0.f; o.w = rv.w > 0.f ? dv.w : 0.f;
+      }
+      T* dst = dy + pix * dy_ld + c;
+      st4(dst, o);
+      s.x += rnd(o.x, dst); s.y += rnd(o.y, dst); s.z += rnd(o.z, dst); s.w += rnd(o.w, dst);
+    }
+  }
+  block_channel_reduce(mp, s, out, C, sm);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_kernel(const T* d, int d_ld, long long P, int C,
+                                                          double* out) {
+  __shared__ float4 sm[256];
+  RedMap mp(C);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mp.cv * 4 < C) {
+    const int c = mp.cv * 4;
+    for (long long pix = (long long)blockIdx.x * mp.rows + mp.prow; pix < P;
+         pix += (long long)gridDim.x * mp.rows) {
+      const float4 dv = ld4(d + pix * d_ld + c);
+      s.x += dv.x; s.y += dv.y; s.z += dv.z; s.w += dv.w;
+    }
+  }
+  block_channel_reduce(mp, s, out, C, sm);
+}
+
+__global__ void sum_to_float_kernel(const double* src, float* dst, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) dst[c] = (float)src[c];
+}
+
+// --------------------------------------------------------------------------
+// F.max_pool2d(x, 2) (unet.py:169) and its backward: the first maximum in
+// row-major window order receives the gradient.
+// --------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* x, int x_ld, T* y, int y_ld, int B, int Ho, int Wo, int C) {
+  const int cv = C >> 2;
+  const long long total = (long long)B * Ho * Wo * cv;
+  const int Wi = Wo * 2, Hi = Ho * 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    long long pix = i / cv;
+    const int ow = (int)(pix % Wo);
+    const long long t = pix / Wo;
+    const int oh = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const T* s = x + ((long long)(n * Hi + 2 * oh) * Wi + 2 * ow) * x_ld + c;
+    const float4 v0 = ld4(s), v1 = ld4(s + x_ld), v2 = ld4(s + (long long)Wi * x_ld),
+                 v3 = ld4(s + (long long)(Wi + 1) * x_ld);
+    float4 m;
+    m.x = fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x));
+    m.y = fmaxf(fmaxf(v0.y, v1.y), fmaxf(v2.y, v3.y));
+    m.z = fmaxf(fmaxf(v0.z, v1.z), fmaxf(v2.z, v3.z));
+    m.w = fmaxf(fmaxf(v0.w, v1.w), fmaxf(v2.w, v3.w));
+    st4(y + pix * y_ld + c, m);
+  }
+}
+
+__device__ __forceinline__ int first_max4(float a, float b, float c, float d) {
+  int k = 0; float m = a;
+  if (b > m) { m = b; k = 1; }
+  if (c > m) { m = c; k = 2; }
+  if (d > m) { m = d; k = 3; }
+  return k;
+}
+
+// dx (B,2Ho,2Wo,C) (+)= route(dy); accumulate=1 adds onto the existing dx (the skip gradient).
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* x, int x_ld, const T* dy, int dy_ld, T* dx, int dx_ld,
+                                   int B, int Ho, int Wo, int C, int accumulate) {
+  const int cv = C >> 2;
+  const long long total = (long long)B * Ho * Wo * cv;
+  const int Wi = Wo * 2, Hi = Ho * 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 4;
+    long long pix = i / cv;
+    const int ow = (int)(pix % Wo);
+    const long long t = pix / Wo;
+    const int oh = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const long long base = (long long)(n * Hi + 2 * oh) * Wi + 2 * ow;
+    const long long off[4] = {base, base + 1, base + Wi, base + Wi + 1};
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ld4(x + off[k] * x_ld + c);
+    const float4 g = ld4(dy + pix * dy_ld + c);
+    const int kx = first_max4(v[0].x, v[1].x, v[2].x, v[3].x);
+    const int ky = first_max4(v[0].y, v[1].y, v[2].y, v[3].y);
+    const int kz = first_max4(v[0].z, v[1].z, v[2].z, v[3].z);
+    const int kw = first_max4(v[0].w, v[1].w, v[2].w, v[3].w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 o = make_float4(kx == k ? g.x : 0.f, ky == k ? g.y : 0.f, kz == k ? g.z : 0.f,
+                             kw == k ? g.w : 0.f);
+      T* dst = dx + off[k] * dx_ld + c;
+      if (accumulate) {
+        const float4 old = ld4(dst);
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      st4(dst, o);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Boundary layout changes and the softmax head (nn.Softmax2d, unet.py:103-104,179)
+// --------------------------------------------------------------------------
+// fp32 NCHW (B,C,H,W) -> T NHWC with pixel stride ld
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* src, T* dst, int ld, int B, int C, long long HW) {
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, hw = i - n * HW;
+    for (int c = 0; c < C; ++c) st1(dst + i * ld + c, src[(n * C + c) * HW + hw]);
+  }
+}
+
+constexpr int kMaxClasses = 32;
+
+// logits (T NHWC, stride ld) -> seg (fp32 NCHW) [softmax over channels], optional fp32 NCHW logits copy
+template <typename T>
+__global__ void softmax_fwd_kernel(const T* logits, int ld, int B, int ncls, long long HW, int do_softmax,
+                                   float* seg, float* logits_out) {
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, hw = i - n * HW;
+    float v[kMaxClasses];
+    float mx = -INFINITY;
+    for (int c = 0; c < ncls; ++c) {
+      v[c] = ld1(logits + i * ld + c);
+      mx = fmaxf(mx, v[c]);
+    }
+    if (logits_out)
+      for (int c = 0; c < ncls; ++c) logits_out[(n * ncls + c) * HW + hw] = v[c];
+    if (do_softmax) {
+      float s = 0.f;
+      for (int c = 0; c < ncls; ++c) { v[c] = expf(v[c] - mx); s += v[c]; }
+      const float inv = 1.f / s;
+      for (int c = 0; c < ncls; ++c) v[c] *= inv;
+    }
+    for (int c = 0; c < ncls; ++c) seg[(n * ncls + c) * HW + hw] = v[c];
+  }
+}
+
+// d_logits[c] (+)= p_c * (d_seg_c - sum_k d_seg_k p_k)   (p recomputed from the stored logits)
+template <typename T>
+__global__ void softmax_bwd_kernel(const T* logits, int ld, const float* d_seg, T* d_logits, int d_ld,
+                                   int B, int ncls, long long HW, int do_softmax, int accumulate) {
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, hw = i - n * HW;
+    float p[kMaxClasses], g[kMaxClasses];
+    for (int c = 0; c < ncls; ++c) g[c] = d_seg[(n * ncls + c) * HW + hw];
+    if (do_softmax) {
+      float mx = -INFINITY;
+      for (int c = 0; c < ncls; ++c) { p[c] = ld1(logits + i * ld + c); mx = fmaxf(mx, p[c]); }
+      float s = 0.f;
+      for (int c = 0; c < ncls; ++c) { p[c] = expf(p[c] - mx); s += p[c]; }
+      const float inv = 1.f / s;
+      float dot = 0.f;
+      for (int c = 0; c < ncls; ++c) { p[c] *= inv; dot += p[c] * g[c]; }
+      for (int c = 0; c < ncls; ++c) g[c] = p[c] * (g[c] - dot);
+    }
+    for (int c = 0; c < ncls; ++c) {
+      T* dst = d_logits + i * d_ld + c;
+      st1(dst, accumulate ? ld1(dst) + g[c] : g[c]);
+    }
+  }
+}
+
+}  // namespace fu

@@ -1,0 +1,158 @@
+/*
+ * fluoro_unet.h -- C ABI of the B200-native U-Net forward/backward engine.
+ *
+ * The reference (rg2/DeepFluoroLabeling-IPCAI2020) has no FFI of its own: its hot
+ * path is the Python nn.Module `UNet` in train_test_code/unet.py.  This header
+ * is the boundary a binding of that module talks to; every entry point names
+ * the reference interface it stands in for (file:line into the reference).
+ *
+ * Conventions
+ *   - plain C types only; all tensor pointers are DEVICE pointers on the
+ *     engine's device; `stream` is a cudaStream_t passed as void*.
+ *   - every call returns 0 (FU_OK) or a negative status; fu_last_error() gives
+ *     the message.  Nothing here falls back to the CPU.
+ *   - boundary tensors are fp32 NCHW exactly as the reference passes them
+ *     (unet.py:161, :190-193); the engine's internal layout (NHWC, fp32 or
+ *     bf16) never shows through.
+ *   - ownership: the caller (PyTorch) owns parameters, BN buffers, inputs,
+ *     outputs and the flat gradient buffer; the engine owns only its
+ *     activation/workspace arena and its packed weight copies.
+ *   - threading: one caller thread per engine (train.py:376-443 drives the net
+ *     from one thread); all work is enqueued on the caller's stream, no host
+ *     synchronisation inside fu_forward / fu_backward.
+ */
+#ifndef FLUORO_UNET_H_
+#define FLUORO_UNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FU_OK 0
+#define FU_ERR_INVALID_CONFIG (-1)   /* constructor argument the engine rejects */
+#define FU_ERR_UNSUPPORTED_SHAPE (-2)
+#define FU_ERR_CUDA (-3)
+#define FU_ERR_NOT_BOUND (-4)        /* parameters / gradients not bound yet */
+#define FU_ERR_STATE (-5)            /* e.g. backward without a saved training forward */
+#define FU_ERR_ARG (-6)
+
+#define FU_PRECISION_FP32 0  /* parity mode: fp32 storage + fp32 FMA, matches unet.py to ~1e-5 */
+#define FU_PRECISION_BF16 1  /* throughput mode: bf16 NHWC storage, tcgen05 bf16 MMA, fp32 accumulate */
+
+#define FU_KIND_PARAM 0
+#define FU_KIND_BUFFER 1
+#define FU_DTYPE_F32 0
+#define FU_DTYPE_I64 1
+
+typedef struct fu_engine fu_engine;
+
+/* Mirrors the keyword arguments of UNet.__init__ (unet.py:41-45), one field each. */
+typedef struct fu_config {
+  int32_t in_channels;
+  int32_t n_classes;
+  int32_t depth;
+  int32_t wf;
+  int32_t padding;            /* must be 1 (unet.py:42; padding=False crashes the reference with do_res) */
+  int32_t pad_mode_zeros;     /* must be 1 ('zeros', unet.py:42) */
+  int32_t batch_norm;
+  int32_t up_mode_upconv;     /* must be 1 ('upconv', unet.py:43) */
+  int32_t max_pool;
+  int32_t num_lands;
+  int32_t do_res;
+  int32_t block_depth;
+  int32_t lands_block_depth;  /* must be 0 (unet.py:44; dead in every reference script) */
+  int32_t lands_num_1x1;
+  int32_t do_soft_max;
+  int32_t precision;          /* FU_PRECISION_* (not a reference argument) */
+} fu_config;
+
+typedef struct fu_tensor_info {
+  char name[96];     /* state_dict key, e.g. "down_path.0.block.0.weight" */
+  int32_t ndim;
+  int64_t shape[4];
+  int32_t kind;      /* FU_KIND_* */
+  int32_t dtype;     /* FU_DTYPE_* */
+  int64_t grad_offset; /* element offset into the flat fp32 gradient buffer, -1 if the
+                          tensor receives no gradient (buffers; downsample_convs.{depth-1},
+                          which unet.py:165-171 never calls) */
+} fu_tensor_info;
+
+typedef struct fu_counters {
+  int64_t kernel_launches;      /* engine kernels launched since creation */
+  int64_t tc_kernel_launches;   /* of which tcgen05 tensor-core kernels */
+  int64_t forward_calls;
+  int64_t backward_calls;
+  int64_t arena_bytes;          /* current activation/workspace arena */
+  int64_t last_fwd_launches;    /* launches of the most recent fu_forward */
+  int64_t last_bwd_launches;    /* launches of the most recent fu_backward */
+} fu_counters;
+
+/* UNet.__init__ (unet.py:41-159): validates the configuration, builds the layer
+ * table.  Rejects what no reference script selects with
+ * FU_ERR_INVALID_CONFIG.  `device` is the CUDA ordinal (util.py:28-29 hard-wires 0). */
+int fu_engine_create(const fu_config* cfg, int device, fu_engine** out);
+/* nn.Module destruction. */
+void fu_engine_destroy(fu_engine* e);
+/* Message of the most recent failure on `e` (or of fu_engine_create when e == NULL). */
+const char* fu_last_error(const fu_engine* e);
+
+/* nn.Module.state_dict() schema (train.py:476): number of entries and
+ * the i-th entry, in the reference's state_dict order. */
+int fu_num_tensors(const fu_engine* e);
+int fu_tensor_get_info(const fu_engine* e, int index, fu_tensor_info* out);
+/* Number of fp32 elements of the flat gradient buffer fu_backward fills. */
+int64_t fu_grad_numel(const fu_engine* e);
+
+/* nn.Module.to(dev) / load_state_dict (train.py:316-319): hand the engine the device
+ * address of every state_dict tensor, in schema order (fp32, or int64 for
+ * num_batches_tracked).  May be called again whenever an address changes. */
+int fu_bind_tensors(fu_engine* e, void* const* data_ptrs, int n);
+
+/* UNet.forward (unet.py:161-193), called at train.py:407, util.py:144,202,271,331.
+ *   x        (B,in_channels,H,W) fp32 NCHW
+ *   training nn.Module.train()/eval() state: batch statistics + running-stat
+ *            update (1) or running statistics (0)
+ *   save     keep activations for fu_backward (0 under torch.no_grad())
+ *   weights_version  any integer that changes whenever a parameter value changed
+ *            since the last call (the engine re-packs its weight copies then)
+ *   seg      (B,n_classes,H,W) softmax probabilities (logits if do_soft_max=0)
+ *   logits   optional (may be NULL): seg_x of unet.py:176, same shape
+ *   heat     (B,num_lands,H,W); NULL iff num_lands == 0
+ */
+int fu_forward(fu_engine* e, const float* x, int B, int H, int W, int training, int save,
+               int64_t weights_version, float* seg, float* logits, float* heat, void* stream);
+
+/* autograd backward of the above, entered at train.py:422.  d_seg / d_heat are
+ * dL/dseg, dL/dheat (same shapes as the outputs, fp32 NCHW); either may be NULL
+ * (= zero).  flat_grads (fu_grad_numel() floats) is overwritten with the gradient
+ * of every reachable parameter at its fu_tensor_info.grad_offset.  d_x is not
+ * produced: the input never requires grad in the reference (train.py:395-407). */
+int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* flat_grads,
+                void* stream);
+
+int fu_get_counters(const fu_engine* e, fu_counters* out);
+
+/* Build information: "sm_100a;tcgen05=1;..." */
+const char* fu_build_info(void);
+
+/* ---- kernel-level test hooks (used by tests/ only; no reference counterpart) ----
+ * Run one convolution layer through the engine's kernels on caller-provided NHWC
+ * tensors so each kernel can be checked against the oracle in isolation.
+ *   mode 0: forward 3x3/1x1/2x2s2 conv   y = conv(x, w) + bias [+relu]
+ *   mode 1: data gradient                dx = conv^T(dy, w)
+ *   mode 2: weight gradient              dw = x (*) dy
+ * `impl` 0 = fp32/bf16 CUDA-core path, 1 = tcgen05 path (bf16 only).
+ * Tensors: x (B,H,W,Cin), y/dy (B,Ho,Wo,Cout) in the engine precision's storage
+ * type (fp32 or bf16 bits); w, bias, dw fp32 in the torch layout (Cout,Cin,k,k). */
+int fu_test_conv(int precision, int impl, int mode, int B, int H, int W, int Cin, int Cout,
+                 int ksize, int stride, int pad, int relu,
+                 const void* x, const float* w, const float* bias, void* y_or_dx,
+                 const void* dy, float* dw, double* stats_or_null, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUORO_UNET_H_ */

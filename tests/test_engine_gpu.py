@@ -1,0 +1,208 @@
+"""Parity tests proper: the CUDA engine (through the C ABI, via the UNet module) against
+the golden fixtures generated from the reference and against the oracle.  GPU only."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import SMALL_CASES, golden_state, load_golden, load_pkg, rel_l2, ROOT
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# fp32 parity mode: different summation order only.  bf16 throughput mode: reported, loose.
+TOL = {"fp32": dict(out=5e-5, grad=1e-3, stats=1e-4), "bf16": dict(out=6e-2, grad=2.5e-1, stats=3e-2)}
+REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
+
+
+def _report(**kw):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    assert torch.cuda.is_available()
+    p = load_pkg()
+    p._capi.lib()
+    return p
+
+
+def _run_case(pkg, name, precision):
+    meta, rec = load_golden(name)
+    dev = torch.device("cuda:0")
+    net = pkg.UNet(precision=precision, **meta["kwargs"])
+    net.load_state_dict(golden_state(rec))
+    net.to(dev)
+    net.train(meta["training"])
+    net.keep_logits = True
+    out = net(rec["x"].to(dev))
+    seg, heat = out if isinstance(out, tuple) else (out, None)
+    loss = (seg * rec["d_seg"].to(dev)).sum()
+    if heat is not None:
+        loss = loss + (heat * rec["d_heat"].to(dev)).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    errs = {"seg": rel_l2(seg.detach().cpu(), rec["seg"]),
+            "logits": rel_l2(net.last_logits.cpu(), rec["logits"])}
+    if heat is not None:
+        errs["heat"] = rel_l2(heat.detach().cpu(), rec["heat"])
+    gerrs = {}
+    ref_g = golden_state(rec, "grad/")
+    for n, p in net.named_parameters():
+        if n in meta["none_grads"]:
+            assert p.grad is None, n
+            continue
+        assert p.grad is not None, n
+        gerrs[n] = rel_l2(p.grad.cpu(), ref_g[n])
+    serrs = {}
+    if meta["training"]:
+        sd = net.state_dict()
+        for k, v in golden_state(rec, "state_after/").items():
+            if "num_batches" in k:
+                assert int(sd[k]) == int(v), k
+            else:
+                serrs[k] = rel_l2(sd[k].cpu(), v)
+    return meta, errs, gerrs, serrs
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_golden_case(pkg, name, precision):
+    meta, errs, gerrs, serrs = _run_case(pkg, name, precision)
+    worst_g = max(gerrs.items(), key=lambda kv: kv[1])
+    _report(test="golden", case=name, precision=precision, out=errs, worst_grad=worst_g,
+            worst_stat=max(serrs.values()) if serrs else None)
+    tol = TOL[precision]
+    for k, v in errs.items():
+        assert v < tol["out"], (k, v)
+    for k, v in gerrs.items():
+        assert v < tol["grad"], (k, v)
+    for k, v in serrs.items():
+        assert v < tol["stats"], (k, v)
+
+
+def _paper_net(pkg, precision, meta):
+    """Paper network with the seeded default init + BN warm-up of make_golden.run_paper
+    (warm-up done with the oracle on the host CPU: 3 training forwards at B=2)."""
+    torch.manual_seed(0)
+    net = pkg.UNet(precision=precision, **meta["kwargs"])
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = O.UNetConfig(**meta["kwargs"])
+    g = torch.Generator().manual_seed(meta["warm"]["seed"])
+    for _ in range(meta["warm"]["n_iter"]):
+        out = O.forward(sd, cfg, torch.randn(*meta["warm"]["shape"], generator=g), training=True)
+        sd.update(out["new_stats"])
+    net.load_state_dict(sd)
+    return net, sd, cfg
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_paper_config_eval_192_matches_reference(pkg, precision):
+    """BASELINE.json config 1: single-image eval forward, logits/probs/heat-maps within 1e-3 rel
+    of the reference PyTorch-CPU forward (parity mode).  Throughput mode is reported."""
+    meta, rec = load_golden("paper_eval_192")
+    net, sd, cfg = _paper_net(pkg, precision, meta)
+    dev = torch.device("cuda:0")
+    net.to(dev).eval()
+    net.keep_logits = True
+    with torch.no_grad():
+        seg, heat = net(rec["x"].to(dev))
+    torch.cuda.synchronize()
+    e = {"logits": rel_l2(net.last_logits.cpu()[:, :, ::4, ::4], rec["logits_s4"]),
+         "seg": rel_l2(seg.cpu()[:, :, ::4, ::4], rec["seg_s4"]),
+         "heat": rel_l2(heat.cpu()[:, :, ::4, ::4], rec["heat_s4"]),
+         "heat_vs_fp64": rel_l2(heat.cpu()[:, :, ::4, ::4], rec["heat64_s4"])}
+    _report(test="paper_eval_192", precision=precision, **e)
+    tol = 1e-3 if precision == "fp32" else 5e-2
+    assert e["logits"] < tol and e["seg"] < tol and e["heat"] < tol, e
+    assert seg.shape == (1, 7, 192, 192) and heat.shape == (1, 14, 192, 192)
+
+
+def test_paper_config_train_step_matches_oracle(pkg):
+    """fwd+bwd of the paper network, B=2 at 96x96 (oracle finishes in seconds), every gradient."""
+    meta, _ = load_golden("paper_eval_192")
+    net, sd, cfg = _paper_net(pkg, "fp32", meta)
+    dev = torch.device("cuda:0")
+    net.to(dev).train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, 96, 96, generator=g)
+    seg, heat = net(x.to(dev))
+    d_seg = torch.randn(seg.shape, generator=g)
+    d_heat = torch.randn(heat.shape, generator=g)
+    ((seg * d_seg.to(dev)).sum() + (heat * d_heat.to(dev)).sum()).backward()
+    ref = O.forward(sd, cfg, x, training=True, want_tape=True)
+    rg = O.backward(sd, cfg, ref["tape"], d_seg, d_heat)
+    assert rel_l2(seg.detach().cpu(), ref["seg"]) < 1e-4
+    assert rel_l2(heat.detach().cpu(), ref["heat"]) < 1e-4
+    worst = ("", 0.0)
+    for n, p in net.named_parameters():
+        if n.startswith("downsample_convs.5"):
+            assert p.grad is None
+            continue
+        err = rel_l2(p.grad.cpu(), rg[n])
+        if err > worst[1]:
+            worst = (n, err)
+    _report(test="paper_train_96", worst_grad=worst)
+    assert worst[1] < 2e-3, worst
+
+
+def test_module_semantics_on_gpu(pkg):
+    dev = torch.device("cuda:0")
+    kw = dict(n_classes=3, depth=2, wf=2, batch_norm=True, padding=True, max_pool=False, num_lands=0)
+    torch.manual_seed(3)
+    net = pkg.UNet(**kw).to(dev)
+    x = torch.randn(2, 1, 8, 8, device=dev)
+    # seg-only nets return a tensor, dual-head nets a tuple (util.py:145 tests type(net_out) is tuple)
+    out = net(x)
+    assert isinstance(out, torch.Tensor) and out.shape == (2, 3, 8, 8)
+    # eval + no_grad leaves BN buffers untouched; train updates them
+    before = {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}
+    net.eval()
+    with torch.no_grad():
+        net(x)
+    for k, v in before.items():
+        assert torch.equal(net.state_dict()[k], v), k
+    net.train()
+    net(x)
+    assert int(net.state_dict()["down_path.0.block.2.num_batches_tracked"]) == int(before["down_path.0.block.2.num_batches_tracked"]) + 1
+    # unsupported shape is rejected, not padded silently
+    with pytest.raises(ValueError):
+        net(torch.randn(1, 1, 9, 8, device=dev))
+    # a stale backward is refused
+    o1 = net(x)
+    net(x)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        o1.sum().backward()
+    # gradients accumulate like autograd's
+    net.zero_grad()
+    net(x).square().sum().backward()
+    g1 = net.seg_conv.weight.grad.clone()
+    net(x).square().sum().backward()
+    # (BN running stats moved between the two calls, but batch-stat normalisation makes the output identical)
+    assert torch.allclose(net.seg_conv.weight.grad, 2 * g1, rtol=1e-4, atol=1e-6)
+    assert net.engine_counters()["kernel_launches"] > 0
+
+
+def test_training_loop_reduces_loss_like_reference_loop(pkg):
+    """A few SGD steps of the train.py:405-424 loop shape; the loss must go down."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net = pkg.UNet(n_classes=7, depth=3, wf=3, batch_norm=True, padding=True, max_pool=False, num_lands=14).to(dev)
+    opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4, 1, 32, 32, generator=g).to(dev)
+    tgt_seg = torch.nn.functional.one_hot(torch.randint(0, 7, (4, 28, 28), generator=g), 7).permute(0, 3, 1, 2).float().to(dev)
+    tgt_heat = torch.rand(4, 14, 28, 28, generator=g).to(dev)
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        seg, heat = net(x)
+        loss = O.dice_and_heatmap_loss(pkg.center_crop(seg, tgt_seg.shape), pkg.center_crop(heat, tgt_heat.shape),
+                                       tgt_seg, tgt_heat)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] - 0.02, losses

@@ -1,0 +1,91 @@
+"""Kernel-level parity through the C ABI test hook (fu_test_conv): each convolution kernel of the
+engine against torch-CPU fp32 convolutions on odd shapes (ragged tiles, channel tails)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_pkg, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    assert torch.cuda.is_available()
+    return load_pkg()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def run_conv(pkg, precision, impl, mode, x, w, bias, dy, k, stride, pad, relu=0, want_stats=False):
+    """x: (B,Cin,H,W) cpu fp32; returns torch cpu fp32 result in NCHW."""
+    L = pkg._capi.lib()
+    dev = torch.device("cuda:0")
+    dt = torch.bfloat16 if precision == 1 else torch.float32
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    xg = x.permute(0, 2, 3, 1).contiguous().to(dev, dt)
+    wg = w.contiguous().to(dev)
+    bg = bias.to(dev) if bias is not None else None
+    dyg = dy.permute(0, 2, 3, 1).contiguous().to(dev, dt) if dy is not None else None
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if want_stats else None
+    if mode == 0:
+        out = torch.empty(B, Ho, Wo, Cout, device=dev, dtype=dt)
+        dw = None
+    elif mode == 1:
+        out = torch.empty(B, H, W, Cin, device=dev, dtype=dt)
+        dw = None
+    else:
+        out = None
+        dw = torch.empty_like(wg)
+    rc = L.fu_test_conv(precision, impl, mode, B, H, W, Cin, Cout, k, stride, pad, relu, _p(xg), _p(wg), _p(bg),
+                        _p(out), _p(dyg), _p(dw), _p(stats), None)
+    assert rc == 0, pkg._capi.last_error(None)
+    torch.cuda.synchronize()
+    if mode == 2:
+        return dw.cpu()
+    res = out.float().cpu().permute(0, 3, 1, 2).contiguous()
+    return (res, stats.cpu()) if want_stats else res
+
+
+SHAPES = [  # B, Cin, Cout, H, W, k, stride, pad
+    (2, 1, 8, 12, 20, 3, 1, 1),
+    (3, 16, 24, 9, 7, 3, 1, 1),
+    (1, 7, 5, 6, 6, 1, 1, 0),
+    (2, 8, 8, 8, 12, 2, 2, 0),
+    (2, 64, 96, 24, 24, 3, 1, 1),
+    (1, 39, 21, 10, 10, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("precision", [0, 1])
+def test_simt_conv_fwd_dgrad_wgrad(pkg, shape, precision):
+    B, Cin, Cout, H, W, k, stride, pad = shape
+    g = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    if precision == 1:
+        x = x.bfloat16().float()
+    tol = 1e-5 if precision == 0 else 1e-2
+    y_ref = F.conv2d(x, w, b, stride=stride, padding=pad)
+    y, stats = run_conv(pkg, precision, 0, 0, x, w, b, None, k, stride, pad, relu=1, want_stats=True)
+    assert rel_l2(y, torch.relu(y_ref)) < tol
+    assert rel_l2(stats[:Cout], y.double().sum(dim=(0, 2, 3))) < 1e-4
+    assert rel_l2(stats[Cout:], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+    dy = torch.randn(y_ref.shape, generator=g)
+    if precision == 1:
+        dy = dy.bfloat16().float()
+    dw = run_conv(pkg, precision, 0, 2, x, w, None, dy, k, stride, pad)
+    dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=stride, padding=pad)
+    assert rel_l2(dw, dw_ref) < tol
+    if stride == 1:
+        dx = run_conv(pkg, precision, 0, 1, x, w, None, dy, k, stride, pad)
+        dx_ref = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=stride, padding=pad)
+        assert rel_l2(dx, dx_ref) < tol

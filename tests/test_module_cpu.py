@@ -1,0 +1,99 @@
+"""Host-side checks that need no GPU: the module mirrors the reference's interface,
+the C-ABI library loads and exports every declared symbol, and invalid
+configurations are rejected loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, golden_state, load_golden, load_pkg
+from oracle import unet_oracle as O
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    p = load_pkg()
+    p.build_library()
+    return p
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "fluoro_unet.h")).read()
+    declared = set(re.findall(r"\b(fu_[a-z_0-9]+)\s*\(", hdr))
+    L = pkg._capi.lib()
+    assert declared, "no declarations found"
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert declared == set(pkg._capi.EXPORTS)
+    assert b"sm_100a" in L.fu_build_info()
+
+
+def test_library_has_no_torch_dependency(pkg):
+    import subprocess
+    out = subprocess.run(["ldd", pkg._capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "c10" not in out
+
+
+@pytest.mark.parametrize("name", ["dual_conv_down_train", "dual_maxpool_train", "seg_only_plain_train",
+                                  "seg_only_bn_nores_train", "lands1_nosoftmax_train"])
+def test_state_dict_schema_matches_reference(pkg, name):
+    meta, rec = load_golden(name)
+    net = pkg.UNet(**meta["kwargs"])
+    ref = golden_state(rec)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+        assert sd[k].dtype == ref[k].dtype, k
+    net.load_state_dict(ref)          # train.py:316 / test_ensemble.py:100
+    assert [n for n, _, _ in O.param_schema(O.UNetConfig(**meta["kwargs"]))] == list(sd.keys())
+
+
+def test_default_init_is_rng_identical_to_reference(pkg):
+    meta, _ = load_golden("paper_eval_192")
+    torch.manual_seed(0)
+    net = pkg.UNet(**meta["kwargs"])
+    assert sum(p.numel() for p in net.parameters()) == 38100089
+    for k, v in net.state_dict().items():
+        s, sa = meta["param_sums"][k]
+        assert abs(float(v.double().sum()) - s) <= 1e-9 * max(1.0, abs(s)), k
+        assert abs(float(v.double().abs().sum()) - sa) <= 1e-9 * max(1.0, sa), k
+
+
+@pytest.mark.parametrize("kw", [dict(padding=False), dict(padding=True, pad_mode="circular"),
+                                dict(padding=True, up_mode="upsample"), dict(padding=True, lands_block_depth=1),
+                                dict(padding=True, precision="fp8")])
+def test_unsupported_configs_are_rejected(pkg, kw):
+    with pytest.raises(ValueError):
+        pkg.UNet(**kw)
+
+
+def test_cpu_input_raises_instead_of_falling_back(pkg):
+    net = pkg.UNet(padding=True, depth=2, wf=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 1, 8, 8))
+
+
+def test_engine_create_without_gpu_fails_loudly(pkg):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = pkg._capi.lib()
+    cfg = pkg._capi.FuConfig(in_channels=1, n_classes=2, depth=2, wf=2, padding=1, pad_mode_zeros=1, batch_norm=1,
+                             up_mode_upconv=1, max_pool=0, num_lands=0, do_res=1, block_depth=2,
+                             lands_block_depth=0, lands_num_1x1=2, do_soft_max=1, precision=0)
+    h = ctypes.c_void_p()
+    rc = L.fu_engine_create(ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc == -3 and h.value is None
+    assert b"no CPU fallback" in L.fu_last_error(None)
+    cfg.padding = 0
+    assert L.fu_engine_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
+
+
+def test_center_crop_matches_reference_semantics(pkg):
+    x = torch.arange(2 * 3 * 10 * 12, dtype=torch.float32).reshape(2, 3, 10, 12)
+    y = pkg.center_crop(x, (2, 3, 6, 7))
+    assert y.shape == (2, 3, 6, 7) and torch.equal(y, x[:, :, 2:8, 2:9])
+    assert pkg.center_crop(x, x.shape) is x
+    assert torch.equal(pkg.center_crop(x[0], (3, 4, 4)), x[0][:, 3:7, 4:8])
