@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the U-Net hot path: images/s of one training step (fwd + Dice/NCC loss + bwd + SGD)
+of the paper's dual-head network on synthetic 1x180x180 fluoroscopy tiles (reflect-padded to 192),
+per-GPU batch 32 (BASELINE.json configs[1]); one process per GPU, NCCL gradient all-reduce for N>1.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU path (the oracle
+port of unet.py + dice.py/ncc.py; the Python reference itself cannot travel to the GPU box) on the
+host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "deepfluorolabeling-ipcai2020_b200"
+
+PAPER = dict(n_classes=7, depth=6, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=14,
+             do_res=True, block_depth=2)
+# algorithmic conv/convT FLOPs per image (MACs x 2), SURVEY.md 8d
+GF_PER_IMG = {192: 54.475, 736: 796.856, 1440: 3064.196}
+GF3x3_PER_IMG = {192: 47.946}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=192, help="network input size (tile 180 padded to 192)")
+    ap.add_argument("--tile", type=int, default=180)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def make_targets(B, tile, n_classes, n_lands, gen, torch):
+    """Targets shaped like dataset.py's: one-hot float masks (dataset.py:448-452) and Gaussian
+    heat-maps, sigma 2.5, peak 1/(2 pi sigma^2) at random in-bounds pixels (dataset.py:295-325)."""
+    labels = torch.randint(0, n_classes, (B, tile, tile), generator=gen)
+    mask = torch.nn.functional.one_hot(labels, n_classes).permute(0, 3, 1, 2).contiguous().float()
+    sigma = 2.5
+    ys = torch.arange(tile, dtype=torch.float32).view(1, 1, tile, 1)
+    xs = torch.arange(tile, dtype=torch.float32).view(1, 1, 1, tile)
+    cy = torch.randint(0, tile, (B, n_lands, 1, 1), generator=gen).float()
+    cx = torch.randint(0, tile, (B, n_lands, 1, 1), generator=gen).float()
+    heat = torch.exp(-((ys - cy) ** 2 + (xs - cx) ** 2) / (2 * sigma * sigma)) / (2 * math.pi * sigma * sigma)
+    return mask, heat.contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm_sorted = sorted(sm)
+        # median over the busiest half of the samples (the sampler also sees the idle edges)
+        busy = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+
+
+def cpu_reference_run(torch, steps, warmup, batch, size, tile, threads):
+    """The reference's CPU path for one training step, through the oracle port (checker code, used
+    here only as the CPU baseline): the functional restatement of unet.py over the same ATen CPU
+    primitives, differentiated by autograd and stepped by torch.optim.SGD exactly as train.py does."""
+    from oracle import unet_oracle as O
+    pkg = importlib.import_module(PKG)
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = pkg.UNet(precision="fp32", **PAPER)          # parameter container only (CPU); same init as the reference
+    cfg = O.UNetConfig(**PAPER)
+    O.NATIVE_BN = True      # same fused ATen batch_norm the reference's nn.BatchNorm2d calls
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    leaves = []
+    for k, _, kind in O.param_schema(cfg):
+        if kind == "param":
+            sd[k].requires_grad_(True)
+            leaves.append(sd[k])
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(batch, 1, size, size, generator=g)
+    mask, heat = make_targets(batch, tile, 7, 14, g, torch)
+    opt = torch.optim.SGD(leaves, lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True)   # train.py:333-334
+
+    def step():
+        opt.zero_grad()                                            # train.py:405
+        out = O.forward(sd, cfg, x, training=True)                 # train.py:407
+        loss = O.dice_and_heatmap_loss(O.center_crop(out["seg"], mask.shape), O.center_crop(out["heat"], heat.shape),
+                                       mask, heat, skip_bg=False, heatmap_wgt=0.5)      # train.py:414-418
+        loss.backward()                                            # train.py:422 (ATen autograd, as the reference)
+        opt.step()                                                 # train.py:424
+        return loss.item()                                         # train.py:430
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt * 1e3
+
+
+def config_dict(args, world):
+    return {"workload": f"paper dual-head U-Net (depth 6, wf 5, BN, learned 2x2/s2 downsample, res 1x1; 7-class seg + "
+                        f"14 heat-maps), {args.batch} tiles/GPU of 1x{args.tile}x{args.tile} reflect-padded to "
+                        f"{args.size}x{args.size}, train step = fwd + DiceAndHeatMapLoss2D + bwd + SGD(nesterov)",
+            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "net_input": args.size, "tile": args.tile,
+            "parallelism": f"dp{world}", "precision": args.precision,
+            "l2": "per-step working set (~1.5 GB of NHWC activations + 300 MB of weights/grads) >> 126 MB L2; no flush needed"}
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    b = args.cpu_sample_batch
+    steps = min(args.steps, 10)
+    warm = min(args.warmup, 1)
+    ips, ms = cpu_reference_run(torch, steps, warm, b, args.size, args.tile, threads)
+    line = {"metric": "images/sec fwd+bwd U-Net (1x180x180, 7+14 heads)", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, world), "impl": "reference",
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} train steps of {b} tiles (fwd+loss+bwd+SGD) through the oracle port "
+                                       f"of unet.py on torch-CPU ({threads} threads)"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a GPU (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    net = pkg.UNet(precision=args.precision, **PAPER).to(dev)
+    net.train()
+    if world > 1:
+        pkg.parallel.data_parallel(net)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    crit = pkg.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
+    B, S, T = args.batch, args.size, args.tile
+    g = torch.Generator().manual_seed(100 + rank)
+    n_host = 2
+    host = []
+    for _ in range(n_host):
+        x = torch.randn(B, 1, S, S, generator=g)
+        mask, heat = make_targets(B, T, 7, 14, g, torch)
+        host.append(tuple(t.pin_memory() for t in (x, mask, heat)))
+    resident = tuple(t.to(dev) for t in host[0])
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def train_step(x, mask, heat):
+        opt.zero_grad(set_to_none=True)
+        seg, hm = net(x)
+        loss = crit((pkg.center_crop(seg, mask.shape), pkg.center_crop(hm, heat.shape)), (mask, heat))
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        barrier()
+        return ms
+
+    # ---- device-resident inputs: `value` ----
+    for _ in range(args.warmup):
+        train_step(*resident)
+    c0 = net.engine_counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda i: train_step(*resident), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = net.engine_counters()
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    ms_step = ms / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host -> device every step, loss read back every step (train.py:395-430) ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for d, h in zip(slots[s], host[i % n_host]):
+                d.copy_(h, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_step(i):
+        s = i % 2
+        if i == 0:
+            prefetch(0)
+        prefetch(i + 1)                      # the next step's inputs travel while this step computes
+        torch.cuda.current_stream().wait_event(ready[s])
+        loss = train_step(*slots[s])
+        freed[s].record(torch.cuda.current_stream())
+        return loss.item()                   # device -> host read of the step's result, every step
+
+    for s in range(2):
+        freed[s].record(torch.cuda.current_stream())
+    for i in range(2):
+        e2e_step(i)
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_value = B * world / (e2e_ms * 1e-3)
+
+    # ---- per-kernel device time (CUDA events inside the engine) -> roofline of the 3x3 conv family ----
+    roof = None
+    breakdown = None
+    if not args.no_profile:
+        net.profile(True)
+        nprof = 3
+        for _ in range(nprof):
+            train_step(*resident)
+        torch.cuda.synchronize()
+        rep = net.profile_report()
+        net.profile(False)
+        fam = {}
+        for r in rep:
+            key = r["tag"].split(" ")[0]
+            a = fam.setdefault(key, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            a["ms"] += r["ms"] / nprof; a["flops"] += r["flops"] / nprof; a["launches"] += r["launches"] / nprof
+        conv_ms = sum(v["ms"] for k, v in fam.items() if k.startswith("conv3_"))
+        conv_fl = sum(v["flops"] for k, v in fam.items() if k.startswith("conv3_"))
+        peak, _, how = peaks()
+        ach = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "3x3 conv family (fwd + dgrad + wgrad, 22 layers x 3)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": how, "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms_per_step": conv_ms}
+        tot = sum(v["ms"] for v in fam.values())
+        breakdown = {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        breakdown["_engine_total_ms"] = round(tot, 4)
+
+    line = None
+    if rank == 0:
+        line = {"metric": "images/sec fwd+bwd U-Net (1x180x180, 7+14 heads)", "value": value, "unit": "images/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": config_dict(args, world), "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d_bytes),
+                        "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+                "roofline": roof, "engine_ms_by_family": breakdown,
+                "model_tflops": value * GF_PER_IMG.get(S, 0.0) / 1e3,
+                "build": pkg._capi.lib().fu_build_info().decode()}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            ips, cms = cpu_reference_run(torch, 3, 1, args.cpu_sample_batch, S, T, threads)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"3 train steps of {args.cpu_sample_batch} tiles (fwd+loss+bwd+SGD), oracle "
+                                              f"port of unet.py on torch-CPU, {threads} threads, {cms:.0f} ms/step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -104,6 +104,28 @@ struct fu_engine {
   fu_counters cnt;
   cudaStream_t stream = nullptr;
   int num_sms = 148;
+  // optional per-launch CUDA-event profiling (fu_profile_enable)
+  bool prof = false;
+  struct ProfRec { std::string tag; const char* kern; cudaEvent_t a, b; double flops, bytes; };
+  std::vector<ProfRec> prof_recs;
+  std::string tag = "other";
+  double tag_flops = 0, tag_bytes = 0;
+  void set_tag(double flops, double bytes, const char* fmt, ...) {
+    if (!prof) return;
+    char buf[160];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    tag = buf; tag_flops = flops; tag_bytes = bytes;
+  }
+  void prof_begin(const char* kern) {
+    ProfRec r; r.tag = tag; r.kern = kern; r.flops = tag_flops; r.bytes = tag_bytes;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, stream);
+    prof_recs.push_back(r);
+  }
+  void prof_end() { cudaEventRecord(prof_recs.back().b, stream); }
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -127,7 +149,9 @@ struct fu_engine {
 #define LAUNCH(e, kern, grid, block, ...)                                                   \
   do {                                                                                      \
     auto _kfn = kern;                                                                       \
+    if ((e)->prof) (e)->prof_begin(#kern);                                                  \
     _kfn<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__);                                 \
+    if ((e)->prof) (e)->prof_end();                                                         \
     (e)->cnt.kernel_launches++;                                                             \
     cudaError_t _ce = cudaPeekAtLastError();                                                \
     if (_ce != cudaSuccess)                                                                 \
@@ -434,6 +458,7 @@ int ensure_plan(fu_engine* e, int B, int H, int W) {
 // ---------------------------------------------------------------------------
 int pack_one(fu_engine* e, const float* src, float* dst, int T, int K, int N, int Npad, int Ninner, int flip,
              long long st, long long sk, long long snh, long long snl) {
+  e->set_tag(0, 0, "weight_pack");
   PackArgs a;
   a.src = src; a.dst = dst; a.T = T; a.K = K; a.N = N; a.Npad = Npad; a.Ninner = Ninner; a.flip = flip;
   a.st = st; a.sk = sk; a.snh = snh; a.snl = snl;
@@ -587,6 +612,11 @@ template <typename T>
 int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, int H, int W, int relu,
                  double* stat, const View* t, const float* bn_a, const float* bn_b) {
   // 3x3/pad1 or 1x1 convolution, stride 1
+  {
+    const double M = (double)B * H * W;
+    e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (x.C + y.C)) * e->esz + 2.0 * cw.Cin * cw.Cout * cw.k * cw.k,
+               "conv%d_fwd %dx%d %d->%d", cw.k, H, W, cw.Cin, cw.Cout);
+  }
   if (tc_conv_eligible(cw.tc, x.p, x.ld, y.p, y.ld, t ? t->p : nullptr, t ? t->ld : 0)) {
     int rc = tc_conv_forward(cw.tc, x.p, x.ld, y.p, y.ld, B, H, W, tdata(e, cw.b_idx), relu, stat,
                              t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt);
@@ -615,6 +645,7 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
     if ((rc = conv_forward<T>(e, blk.convs[i], cur, r, B, H, W, 1, stat, nullptr, nullptr, nullptr))) return rc;
     if (bn) {
       BNL& b = blk.bns[i];
+      e->set_tag(0, 2.0 * P * b.C * e->esz, "bn_fwd %dx%d C%d", H, W, b.C);
       LAUNCH(e, bn_finalize_kernel, (b.C + 127) / 128, 128, b.stat, P, b.C, training, tdata(e, b.i_gamma),
              tdata(e, b.i_beta), tdata(e, b.i_rm), tdata(e, b.i_rv),
              reinterpret_cast<long long*>(e->tensors[b.i_nbt].data), 0.1f, 1e-5f, b.mean, b.invstd, b.a, b.b);
@@ -650,6 +681,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
   int rc;
   if (training && c.batch_norm) CUDA_TRY(e, cudaMemsetAsync(e->dscr_fwd, 0, e->dscr_fwd_bytes, e->stream));
   const long long HW = (long long)H * W;
+  e->set_tag(0, 0, "input_cast");
   LAUNCH(e, (nchw_to_nhwc_kernel<T>), grid1d((long long)B * HW, 256, e->num_sms), 256, x,
          reinterpret_cast<T*>(pl.xin.p), pl.xin.ld, B, c.in_channels, HW);
   View cur = pl.xin;
@@ -659,6 +691,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     if ((rc = block_forward<T>(e, e->enc[l], cur, outv, B, h, w, training))) return rc;
     if (l < D - 1) {
       View dn = pl.down[l + 1];
+      e->set_tag(2.0 * B * (h / 2) * (w / 2) * 4.0 * outv.C * outv.C, 0, "down_fwd %dx%d C%d", h, w, outv.C);
       if (c.max_pool) {
         LAUNCH(e, (maxpool_fwd_kernel<T>), grid1d((long long)B * (h / 2) * (w / 2) * (outv.C / 4), 256, e->num_sms),
                256, reinterpret_cast<const T*>(outv.p), outv.ld, reinterpret_cast<T*>(dn.p), dn.ld, B, h / 2,
@@ -686,6 +719,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     const int h = H >> l, w = W >> l;
     ConvW& up = e->upc[j];
     View upv = slice(pl.cat[l], 0, e->chans[l], esz);
+    e->set_tag(2.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_fwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
     if (tc_up_eligible(up.tc, cur.p, cur.ld, upv.p, upv.ld)) {
       if (tc_up_forward(up.tc, cur.p, cur.ld, upv.p, upv.ld, B, h / 2, w / 2, tdata(e, up.b_idx), e->stream, &e->cnt))
         return e->fail(FU_ERR_CUDA, "tensor-core upconv launch failed: %s", tc_last_error());
@@ -700,6 +734,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     cur = pl.decout[l];
   }
   // ---- heads (unet.py:176-191) ----
+  e->set_tag(0, 0, "heads_fwd");
   View feat = slice(pl.hcat, 0, e->Cf, esz);
   View lg = slice(pl.hcat, e->Cf, c.n_classes, esz);
   {
@@ -738,6 +773,11 @@ int channel_sum_to(fu_engine* e, const View& d, long long P, double* scratch, fl
 // gradient of a stride-1 conv (3x3/pad1 or 1x1) w.r.t. its input
 template <typename T>
 int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, int H, int W, int accumulate) {
+  {
+    const double M = (double)B * H * W;
+    e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (dx.C + dy.C)) * e->esz + 2.0 * cw.Cin * cw.Cout * cw.k * cw.k,
+               "conv%d_dgrad %dx%d %d->%d", cw.k, H, W, cw.Cout, cw.Cin);
+  }
   if (tc_dgrad_eligible(cw.tc, dy.p, dy.ld, dx.p, dx.ld)) {
     if (tc_conv_dgrad(cw.tc, dy.p, dy.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt))
       return e->fail(FU_ERR_CUDA, "tensor-core dgrad launch failed: %s", tc_last_error());
@@ -753,6 +793,11 @@ int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, i
 // gradient of a stride-1 conv w.r.t. its weight, written in the torch layout (Cout,Cin,k,k)
 template <typename T>
 int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, int H, int W, float* dw) {
+  {
+    const double M = (double)B * H * W;
+    e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (x.C + dy.C)) * e->esz + 4.0 * cw.Cin * cw.Cout * cw.k * cw.k,
+               "conv%d_wgrad %dx%d %d->%d", cw.k, H, W, cw.Cin, cw.Cout);
+  }
   if (tc_wgrad_eligible(cw.tc, x.p, x.ld, dy.p, dy.ld)) {
     if (tc_conv_wgrad(cw.tc, x.p, x.ld, dy.p, dy.ld, B, H, W, dw, e->stream, &e->cnt))
       return e->fail(FU_ERR_CUDA, "tensor-core wgrad launch failed: %s", tc_last_error());
@@ -781,6 +826,7 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
     View r = blk.r[i];
     ConvW& cw = blk.convs[i];
     const T* dp = reinterpret_cast<const T*>(d.p);
+    e->set_tag(0, 5.0 * P * blk.C * e->esz, "act_bwd %dx%d C%d", H, W, blk.C);
     if (bn) {
       BNL& b = blk.bns[i];
       LAUNCH(e, (bn_bwd_reduce_kernel<T>), red_grid(e, P, b.C), 256, dp, d.ld, reinterpret_cast<const T*>(r.p),
@@ -822,6 +868,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
   CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
   // ---- heads ----
+  e->set_tag(0, 0, "heads_bwd");
   View feat = slice(pl.hcat, 0, e->Cf, esz);
   View lg = slice(pl.hcat, e->Cf, c.n_classes, esz);
   View d_feat = slice(pl.d_hcat, 0, e->Cf, esz);
@@ -858,6 +905,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     View d_up = slice(pl.d_cat[l], 0, e->chans[l], esz);
     View u = (l == D - 2) ? pl.bott : pl.decout[l + 1];
     View d_u = (l == D - 2) ? pl.d_bott : pl.d_decout[l + 1];
+    e->set_tag(4.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_bwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
     if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
     {
       WgradCall wc;  // dW[ci][co][ab] = sum x[n,i,j,ci] * dY[n,2i+a,2j+b,co]
@@ -884,6 +932,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     if (l > 0) {
       View src = slice(pl.cat[l - 1], e->chans[l - 1], e->chans[l - 1], esz);     // encoder output of level l-1
       View d_src = slice(pl.d_cat[l - 1], e->chans[l - 1], e->chans[l - 1], esz);  // already holds the skip gradient
+      e->set_tag(4.0 * B * h * w * 4.0 * src.C * src.C, 0, "down_bwd %dx%d C%d", 2 * h, 2 * w, src.C);
       if (c.max_pool) {
         LAUNCH(e, (maxpool_bwd_kernel<T>), grid1d((long long)B * h * w * (src.C / 4), 256, e->num_sms), 256,
                reinterpret_cast<const T*>(src.p), src.ld, reinterpret_cast<const T*>(pl.d_down[l].p),
@@ -1055,6 +1104,48 @@ int fu_get_counters(const fu_engine* e, fu_counters* out) {
   if (!e || !out) return FU_ERR_ARG;
   *out = e->cnt;
   return FU_OK;
+}
+
+int fu_profile_enable(fu_engine* e, int on) {
+  if (!e) return FU_ERR_ARG;
+  for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->prof_recs.clear();
+  e->prof = on != 0;
+  e->tag = "other"; e->tag_flops = 0; e->tag_bytes = 0;
+  return FU_OK;
+}
+
+int64_t fu_profile_report(fu_engine* e, char* buf, int64_t cap) {
+  if (!e) return FU_ERR_ARG;
+  cudaSetDevice(e->device);
+  if (!e->prof_recs.empty()) cudaEventSynchronize(e->prof_recs.back().b);
+  struct Agg { std::string tag, kern; int n; double ms, flops, bytes; };
+  std::vector<Agg> aggs;
+  for (auto& r : e->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+    std::string k = r.kern;
+    const size_t lt = k.find('<');
+    if (lt != std::string::npos) k = k.substr(0, lt);
+    while (!k.empty() && (k[0] == '(' || k[0] == ' ')) k.erase(0, 1);
+    Agg* hit = nullptr;
+    for (auto& a : aggs) if (a.tag == r.tag && a.kern == k) { hit = &a; break; }
+    if (!hit) { aggs.push_back({r.tag, k, 0, 0, 0, 0}); hit = &aggs.back(); }
+    hit->n++; hit->ms += ms; hit->flops += r.flops; hit->bytes += r.bytes;
+  }
+  std::string out;
+  char line[512];
+  for (auto& a : aggs) {
+    snprintf(line, sizeof(line), "{\"tag\": \"%s\", \"kernel\": \"%s\", \"launches\": %d, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}\n",
+             a.tag.c_str(), a.kern.c_str(), a.n, a.ms, a.flops, a.bytes);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const int64_t n = (int64_t)out.size() < cap - 1 ? (int64_t)out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size() + 1;
 }
 
 const char* fu_build_info(void) {

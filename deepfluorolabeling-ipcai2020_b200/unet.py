@@ -299,6 +299,21 @@ class UNet(nn.Module):
         _capi.lib().fu_get_counters(self._handle, C.byref(cnt))
         return {n: int(getattr(cnt, n)) for n, _ in cnt._fields_}
 
+    def profile(self, on=True):
+        """Start/stop per-launch CUDA-event profiling inside the engine."""
+        if self._handle is None:
+            raise RuntimeError("run one forward first")
+        _capi.lib().fu_profile_enable(self._handle, int(on))
+
+    def profile_report(self):
+        """List of dicts {tag, kernel, launches, ms, flops, bytes} since profile(True)."""
+        import json
+        L = _capi.lib()
+        n = L.fu_profile_report(self._handle, None, 0)
+        buf = C.create_string_buffer(int(n) + 16)
+        L.fu_profile_report(self._handle, buf, n + 16)
+        return [json.loads(l) for l in buf.value.decode().splitlines() if l.strip()]
+
     # ------------------------------------------------------------------
     # nn.Module interface
     # ------------------------------------------------------------------

@@ -135,6 +135,13 @@ int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* fl
 
 int fu_get_counters(const fu_engine* e, fu_counters* out);
 
+/* Per-launch CUDA-event profiling (the reference's only tracing is time.time(), train.py:377,
+ * util.py:321).  While enabled every kernel launch is bracketed by events on the caller's stream;
+ * fu_profile_report() synchronises and writes one JSON line per (layer tag, kernel) with the summed
+ * device time, algorithmic FLOPs and bytes.  Returns the buffer size needed. */
+int fu_profile_enable(fu_engine* e, int on);
+int64_t fu_profile_report(fu_engine* e, char* buf, int64_t cap);
+
 /* Build information: "sm_100a;tcgen05=1;..." */
 const char* fu_build_info(void);
 

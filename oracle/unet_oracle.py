@@ -126,10 +126,18 @@ def param_schema(cfg: UNetConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
 # --------------------------------------------------------------------------
 # forward
 # --------------------------------------------------------------------------
+NATIVE_BN = False   # timing baseline only: call ATen's fused batch_norm like nn.BatchNorm2d does
+
+
 def _bn_forward(x, sd, prefix, training, tape, new_stats):
     """nn.BatchNorm2d, unet.py:214-215,221-222: batch statistics with biased
     variance for the normalisation, unbiased variance into running_var."""
     gamma, beta = sd[f"{prefix}.weight"], sd[f"{prefix}.bias"]
+    if NATIVE_BN:
+        rm, rv = sd[f"{prefix}.running_mean"], sd[f"{prefix}.running_var"]   # updated in place, like the module
+        if training:
+            sd[f"{prefix}.num_batches_tracked"] += 1
+        return F.batch_norm(x, rm, rv, gamma, beta, training, BN_MOMENTUM, BN_EPS)
     if training:
         n = x.shape[0] * x.shape[2] * x.shape[3]
         mean = x.mean(dim=(0, 2, 3))

@@ -147,9 +147,33 @@ def run_paper(unet):
     print("paper_eval_192 written")
 
 
+def run_losses():
+    """dice.py / ncc.py of the reference on seeded inputs (pins oracle + product loss mirrors)."""
+    sys.path.insert(0, REF)
+    import dice  # noqa: E402
+    g = torch.Generator().manual_seed(42)
+    seg = torch.softmax(torch.randn(3, 7, 24, 20, generator=g), dim=1).requires_grad_(True)
+    heat = torch.randn(3, 14, 24, 20, generator=g).requires_grad_(True)
+    tgt_seg = torch.nn.functional.one_hot(torch.randint(0, 7, (3, 24, 20), generator=g), 7).permute(0, 3, 1, 2).float()
+    tgt_heat = torch.rand(3, 14, 24, 20, generator=g)
+    l_dual = dice.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)((seg, heat), (tgt_seg, tgt_heat))
+    l_dual.backward()
+    l_dice_bg = dice.DiceLoss2D(skip_bg=True)(seg.detach(), tgt_seg)
+    l_dice = dice.DiceLoss2D(skip_bg=False)(seg.detach(), tgt_seg)
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), seg=seg.detach().numpy(), heat=heat.detach().numpy(),
+                        tgt_seg=tgt_seg.numpy(), tgt_heat=tgt_heat.numpy(), l_dual=l_dual.detach().numpy(),
+                        l_dice_bg=l_dice_bg.numpy(), l_dice=l_dice.numpy(), d_seg=seg.grad.numpy(),
+                        d_heat=heat.grad.numpy())
+    print("losses written")
+
+
 if __name__ == "__main__":
+    if "--losses-only" in sys.argv:
+        run_losses()
+        sys.exit(0)
     torch.set_num_threads(8)
     unet = _ref_unet()
     for i, (name, (kw, shape, training)) in enumerate(SMALL_CASES.items()):
         run_case(unet, name, kw, shape, training, seed=100 + i)
     run_paper(unet)
+    run_losses()

@@ -97,3 +97,17 @@ def test_center_crop_matches_reference_semantics(pkg):
     assert y.shape == (2, 3, 6, 7) and torch.equal(y, x[:, :, 2:8, 2:9])
     assert pkg.center_crop(x, x.shape) is x
     assert torch.equal(pkg.center_crop(x[0], (3, 4, 4)), x[0][:, 3:7, 4:8])
+
+
+def test_losses_match_reference_formulas(pkg):
+    """dice.py / ncc.py mirrors against the oracle's restatement (itself pinned on the reference
+    formulas) on CPU tensors."""
+    g = torch.Generator().manual_seed(0)
+    seg = torch.softmax(torch.randn(3, 7, 20, 20, generator=g), dim=1)
+    heat = torch.randn(3, 14, 20, 20, generator=g)
+    tgt_seg = torch.nn.functional.one_hot(torch.randint(0, 7, (3, 20, 20), generator=g), 7).permute(0, 3, 1, 2).float()
+    tgt_heat = torch.rand(3, 14, 20, 20, generator=g)
+    a = pkg.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)((seg, heat), (tgt_seg, tgt_heat))
+    b = O.dice_and_heatmap_loss(seg, heat, tgt_seg, tgt_heat, skip_bg=False, heatmap_wgt=0.5)
+    assert abs(float(a) - float(b)) < 1e-6
+    assert abs(float(pkg.DiceLoss2D(skip_bg=True)(seg, tgt_seg)) - float(O.dice_loss(seg, tgt_seg, True))) < 1e-6

@@ -83,3 +83,29 @@ def test_paper_config_eval_matches_reference():
     assert rel_l2(out["seg"][:, :, ::4, ::4], rec["seg_s4"]) < 1e-4
     assert rel_l2(out["heat"][:, :, ::4, ::4], rec["heat_s4"]) < 1e-4
     assert abs(float(out["heat"].double().sum()) - float(rec["heat_moments"][0])) < 1e-3 * abs(float(rec["heat_moments"][0])) + 1e-2
+
+
+def test_losses_match_reference_dice_and_ncc():
+    import numpy as np
+    import os
+    from conftest import GOLDEN, load_pkg
+    z = np.load(os.path.join(GOLDEN, "losses.npz"))
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    pkg = load_pkg()
+    for impl in ("oracle", "product"):
+        seg = t["seg"].clone().requires_grad_(True)
+        heat = t["heat"].clone().requires_grad_(True)
+        if impl == "oracle":
+            l = O.dice_and_heatmap_loss(seg, heat, t["tgt_seg"], t["tgt_heat"], skip_bg=False, heatmap_wgt=0.5)
+            l_bg = O.dice_loss(t["seg"], t["tgt_seg"], skip_bg=True)
+            l_d = O.dice_loss(t["seg"], t["tgt_seg"], skip_bg=False)
+        else:
+            l = pkg.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)((seg, heat), (t["tgt_seg"], t["tgt_heat"]))
+            l_bg = pkg.DiceLoss2D(skip_bg=True)(t["seg"], t["tgt_seg"])
+            l_d = pkg.DiceLoss2D(skip_bg=False)(t["seg"], t["tgt_seg"])
+        l.backward()
+        assert abs(float(l) - float(t["l_dual"])) < 1e-6
+        assert abs(float(l_bg) - float(t["l_dice_bg"])) < 1e-6
+        assert abs(float(l_d) - float(t["l_dice"])) < 1e-6
+        assert rel_l2(seg.grad, t["d_seg"]) < 1e-5
+        assert rel_l2(heat.grad, t["d_heat"]) < 1e-5
