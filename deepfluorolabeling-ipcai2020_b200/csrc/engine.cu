@@ -618,8 +618,10 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
                "conv%d_fwd %dx%d %d->%d", cw.k, H, W, cw.Cin, cw.Cout);
   }
   if (tc_conv_eligible(cw.tc, x.p, x.ld, y.p, y.ld, t ? t->p : nullptr, t ? t->ld : 0)) {
+    if (e->prof) e->prof_begin("tc_conv_kernel");
     int rc = tc_conv_forward(cw.tc, x.p, x.ld, y.p, y.ld, B, H, W, tdata(e, cw.b_idx), relu, stat,
                              t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt);
+    if (e->prof) e->prof_end();
     if (rc) return e->fail(FU_ERR_CUDA, "tensor-core conv launch failed: %s", tc_last_error());
     return FU_OK;
   }
@@ -779,7 +781,10 @@ int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, i
                "conv%d_dgrad %dx%d %d->%d", cw.k, H, W, cw.Cout, cw.Cin);
   }
   if (tc_dgrad_eligible(cw.tc, dy.p, dy.ld, dx.p, dx.ld)) {
-    if (tc_conv_dgrad(cw.tc, dy.p, dy.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt))
+    if (e->prof) e->prof_begin("tc_conv_kernel");
+    const int trc = tc_conv_dgrad(cw.tc, dy.p, dy.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt);
+    if (e->prof) e->prof_end();
+    if (trc)
       return e->fail(FU_ERR_CUDA, "tensor-core dgrad launch failed: %s", tc_last_error());
     return FU_OK;
   }

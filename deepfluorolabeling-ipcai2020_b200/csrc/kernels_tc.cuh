@@ -1,33 +1,698 @@
-// tcgen05 / TMA tensor-core kernels (throughput mode).  STUB: filled in by the next milestone.
+// tcgen05 / TMA tensor-core kernels of the engine (throughput mode, bf16 NHWC, sm_100a).
+//
+// Convolution = implicit GEMM without im2col:
+//   D[128 pixels, BN out-channels] += A_tap[128 pixels, KC in-channels] * W_tap[BN, KC]^T
+// for every filter tap and KC-channel chunk.  The A operand of a tap is ONE 4-D TMA box
+// (KC, tw, th, tn) of the NHWC activation tensor at coordinates shifted by the tap offset;
+// out-of-bounds rows/columns are zero-filled by TMA, which is exactly the zero padding of
+// nn.Conv2d(padding=1) (unet.py:211-212).  Both operands land in shared memory in the
+// canonical K-major swizzled layout tcgen05.mma reads; accumulators live in TMEM (double
+// buffered), the epilogue (bias, ReLU, BN-apply + residual, BN statistics) runs from TMEM
+// through registers into a swizzled staging tile that TMA stores back to NHWC global memory.
+// A channel slice of a wider buffer (skip concat, unet.py:257) is just a tensor map with a
+// larger pixel stride: no copy.
 #pragma once
-#include "common.cuh"
-#include "../../include/fluoro_unet.h"
+#include <cuda.h>
+#include <cuda_runtime.h>
 
-#define FU_TC_BUILD "0"
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fluoro_unet.h"
+#include "common.cuh"
+
+#define FU_TC_BUILD "1"
 
 namespace fu {
 
-struct TcConv {
-  bool enabled = false;
+// ===========================================================================
+// PTX wrappers
+// ===========================================================================
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("fluoro_unet: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace ptx
+
+// shared-memory matrix descriptor of a K-major operand tile whose rows are `row_bytes` wide
+// (row_bytes = swizzle span: 32/64/128 B), 8-row groups `8*row_bytes` apart.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);  // SWIZZLE_128B / 64B / 32B
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);            // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                                // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(((8u * row_bytes) >> 4) & 0x3FFF) << 32;  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
+  d |= layout << 61;
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ===========================================================================
+// the convolution kernel (forward and data gradient; 3x3/pad 1 and 1x1)
+// ===========================================================================
+struct TcConvParams {
+  int B, H, W;
+  int Cin, N;
+  int ksz, pad;
+  int KC, BN, CS;               // channels per k-chunk, N tile, channels per store box
+  int tw, th, tn;               // pixel tile (tw*th*tn <= 128)
+  int tiles_w, tiles_h, tiles_b, n_tiles;
+  int stages;
+  int relu;
+  const float* bias;            // [N] or null
+  const bf16* t; int t_ld;      // optional second operand of the epilogue, NHWC with pixel stride t_ld
+  const float* bn_a; const float* bn_b;   // out += bn_a[c]*t + bn_b[c]   (null: out += t)
+  double* stat;                 // optional [2N]: per-channel sum / sum of squares of the stored values
 };
 
-inline void tc_carve(TcConv&, int, int, int, bool, bool, Bump&) {}
-inline int tc_pack(TcConv&, const float*, cudaStream_t, fu_counters*) { return 0; }
-inline const char* tc_last_error() { return "tensor-core path not built"; }
-inline bool tc_conv_eligible(const TcConv&, const void*, int, const void*, int, const void*, int) { return false; }
-inline int tc_conv_forward(TcConv&, const void*, int, void*, int, int, int, int, const float*, int, double*,
-                           const void*, int, const float*, const float*, int, cudaStream_t, fu_counters*) { return -1; }
+constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kTcMaxStages = 8;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)p.KC * 2u;
+  const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t staging_off = (uint32_t)p.stages * stage_bytes;
+  const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;
+  const uint32_t bar_off = staging_off + staging_bytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kTcMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 2 + a); };
+  const uint32_t slot_addr = bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 4);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * kTcMaxStages + 4));
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)p.BN) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 128); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(slot_addr, tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int total_tiles = tiles_m * p.n_tiles;
+  const int cchunks = p.Cin / p.KC;
+  const int k_iters = p.ksz * p.ksz * cchunks;
+  const uint32_t a_tx = (uint32_t)(p.tw * p.th * p.tn) * row_bytes;
+
+  auto decode = [&](int tile, int& w0, int& h0, int& n0, int& nb) {
+    const int nt = tile % p.n_tiles;
+    int mt = tile / p.n_tiles;
+    nb = nt * p.BN;
+    w0 = (mt % p.tiles_w) * p.tw; mt /= p.tiles_w;
+    h0 = (mt % p.tiles_h) * p.th; mt /= p.tiles_h;
+    n0 = mt * p.tn;
+  };
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int w0, h0, n0, nb;
+        decode(tile, w0, h0, n0, nb);
+        for (int kit = 0; kit < k_iters; ++kit) {
+          const int tap = kit / cchunks, c0 = (kit - tap * cchunks) * p.KC;
+          const int kh = tap / p.ksz, kw = tap - kh * p.ksz;
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+          ptx::mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
+          ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+          ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), c0, tap, nb);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
+      const int ksteps = p.KC / 16;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int kit = 0; kit < k_iters; ++kit) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t b_addr = a_addr + a_bytes;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t ad = umma_desc_kmajor(a_addr + (uint32_t)j * 32u, row_bytes);
+            const uint64_t bd = umma_desc_kmajor(b_addr + (uint32_t)j * 32u, row_bytes);
+            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kit | j) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (4 warps, 128 threads) ------------------------------
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;          // accumulator row = pixel slot of the tile
+    const int et = threadIdx.x - 64;        // 0..127
+    const uint32_t pitch = (uint32_t)p.CS * 2u;
+    const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
+    const uint32_t sub_bytes = 128u * pitch;
+    uint8_t* staging = smem + staging_off;
+    const uint32_t staging_addr = smem_base + staging_off;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int rows_in_tile = p.tw * p.th * p.tn;
+    const int wi = row % p.tw, hi = (row / p.tw) % p.th, ni = row / (p.tw * p.th);
+    float s_sum[2] = {0.f, 0.f}, s_sq[2] = {0.f, 0.f};
+    int s_nb = -1;
+    auto flush_stats = [&]() {
+      if (p.stat && s_nb >= 0) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = et + u * 128;
+          if (c < p.BN) {
+            atomicAdd(p.stat + s_nb + c, (double)s_sum[u]);
+            atomicAdd(p.stat + p.N + s_nb + c, (double)s_sq[u]);
+          }
+          s_sum[u] = 0.f; s_sq[u] = 0.f;
+        }
+      }
+    };
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int w0, h0, n0, nb;
+      decode(tile, w0, h0, n0, nb);
+      const bool valid = row < rows_in_tile && (w0 + wi) < p.W && (h0 + hi) < p.H && (n0 + ni) < p.B;
+      const long long pix = ((long long)(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
+      if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
+      for (int j = 0; j < p.BN / 32; ++j) {
+        uint32_t v[32];
+        ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
+        ptx::tmem_ld_wait();
+        const int c0 = nb + j * 32;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + i);
+            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+          }
+        }
+        if (p.t && valid) {
+          const bf16* tp = p.t + pix * p.t_ld + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(tp + i);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k2]);
+              const float2 tf = __bfloat1622float2(h2);
+              const int c = i + 2 * k2;
+              if (p.bn_a) {
+                f[c] += p.bn_a[c0 + c] * tf.x + p.bn_b[c0 + c];
+                f[c + 1] += p.bn_a[c0 + c + 1] * tf.y + p.bn_b[c0 + c + 1];
+              } else {
+                f[c] += tf.x; f[c + 1] += tf.y;
+              }
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = 0.f;
+        }
+        // 32 channels -> 4 x 16-byte stores into the swizzled staging tile
+        const int colt = j * 32;                 // column within the BN tile
+        const int sub = colt / p.CS;             // store box this chunk belongs to
+        const uint32_t byte_in_row = (uint32_t)(colt % p.CS) * 2u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+          const uint32_t logical = (uint32_t)row * pitch + byte_in_row + (uint32_t)g * 16u;
+          const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
+          *reinterpret_cast<uint4*>(staging + (uint32_t)sub * sub_bytes + phys) = o;
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty_bar(acc));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      // staging tile complete -> TMA store
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1, 128);
+      if (et == 0) {
+        for (int s = 0; s < p.BN / p.CS; ++s)
+          ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s * sub_bytes, nb + s * p.CS, w0, h0, n0);
+        ptx::tma_store_commit();
+      }
+      if (p.stat) {
+        // per-channel statistics of the stored (bf16-rounded) tile; invalid rows hold zeros
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = et + u * 128;
+          if (c < p.BN) {
+            const int sub = c / p.CS;
+            const uint32_t bir = (uint32_t)(c % p.CS) * 2u;
+            float a = 0.f, b = 0.f;
+            for (int r = 0; r < 128; ++r) {
+              const uint32_t logical = (uint32_t)r * pitch + bir;
+              const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
+              const float x = __bfloat162float(*reinterpret_cast<const bf16*>(staging + (uint32_t)sub * sub_bytes + phys));
+              a += x; b += x * x;
+            }
+            s_sum[u] += a; s_sq[u] += b;
+          }
+        }
+      }
+      if (et == 0) ptx::tma_store_wait_read();     // staging may be overwritten after this
+      ptx::named_bar_sync(1, 128);
+    }
+    flush_stats();
+    if (et == 0) ptx::tma_store_wait_all();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// fp32 torch weights (Cout,Cin,k,k) -> bf16 [Cout][tap][Cin] (forward) and [Cin][flip(tap)][Cout] (data gradient)
+__global__ void tc_pack_conv_kernel(const float* w, bf16* fwd, bf16* dgrad, int Cout, int Cin, int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const long long r = i / Cin;
+    const int t = (int)(r % taps);
+    const int co = (int)(r / taps);
+    const float v = w[((long long)co * Cin + ci) * taps + t];
+    const bf16 h = __float2bfloat16_rn(v);
+    fwd[i] = h;                                                    // [co][t][ci]
+    dgrad[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = h;  // [ci][flip t][co]
+  }
+}
+
+// ===========================================================================
+// host side
+// ===========================================================================
+inline std::string& tc_err() {
+  static thread_local std::string s;
+  return s;
+}
+inline const char* tc_last_error() { return tc_err().c_str(); }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled tc_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+inline CUtensorMapSwizzle tc_swizzle_for(int inner_bytes) {
+  return inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// bf16 tensor map over up to 4 dims; dims[0] is the contiguous (channel) dim, strides in elements
+inline int tc_make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
+                       const int* box, int inner_bytes) {
+  PFN_encodeTiled fn = tc_encode_fn();
+  if (!fn) { tc_err() = "cuTensorMapEncodeTiled entry point not available"; return -1; }
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 2ull;
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle_for(inner_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): rank %d dims %lld,%lld,%lld,%lld box %d,%d,%d,%d", (int)r,
+             rank, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, box[0], box[1], rank > 2 ? box[2] : 0,
+             rank > 3 ? box[3] : 0);
+    tc_err() = buf;
+    return -1;
+  }
+  return 0;
+}
+
+// pixel tile (tw, th, tn), tw*th*tn <= 128, minimising the number of tiles
+inline void tc_pick_tile(int B, int H, int W, int& tw, int& th, int& tn) {
+  long long best = -1;
+  tw = 1; th = 1; tn = 1;
+  for (int a = 1; a <= 128 && a <= W; ++a) {
+    for (int b = 1; a * b <= 128 && b <= H; ++b) {
+      int c = 128 / (a * b);
+      if (c > B) c = B;
+      if (c < 1) continue;
+      const long long tiles = (long long)((W + a - 1) / a) * ((H + b - 1) / b) * ((B + c - 1) / c);
+      const long long key = tiles * 1024 - a;   // fewer tiles first, then longer rows
+      if (best < 0 || key < best) { best = key; tw = a; th = b; tn = c; }
+    }
+  }
+}
+
+struct TcConv {
+  bool enabled = false;
+  int Cin = 0, Cout = 0, k = 0;
+  bf16* w_fwd = nullptr;     // [Cout][taps][Cin]
+  bf16* w_dgrad = nullptr;   // [Cin][taps][Cout]
+  struct Cached {
+    const void *x, *y; int x_ld, y_ld, B, H, W, dir;
+    CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem;
+  };
+  std::vector<Cached> cache;
+};
+
+inline int tc_bn_max() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("FU_TC_BN_MAX");
+    v = s ? atoi(s) : 128;
+    if (v != 32 && v != 64 && v != 128 && v != 256) v = 128;
+  }
+  return v;
+}
+
+inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool enabled, Bump& w) {
+  t.Cin = Cin; t.Cout = Cout; t.k = k;
+  t.enabled = enabled && !transposed && (k == 3 || k == 1) && (Cin % 32 == 0) && (Cout % 32 == 0) &&
+              getenv("FU_TC_DISABLE") == nullptr;
+  if (!t.enabled) return;
+  const size_t n = (size_t)Cin * Cout * k * k;
+  t.w_fwd = w.take<bf16>(n);
+  t.w_dgrad = w.take<bf16>(n);
+  t.cache.clear();
+}
+
+inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* cnt) {
+  if (!t.enabled) return 0;
+  const long long total = (long long)t.Cin * t.Cout * t.k * t.k;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  tc_pack_conv_kernel<<<(unsigned)g, 256, 0, stream>>>(w, t.w_fwd, t.w_dgrad, t.Cout, t.Cin, t.k * t.k);
+  if (cnt) cnt->kernel_launches++;
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+inline bool tc_ptr_ok(const void* p, int ld) { return p && (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 8 == 0); }
+
+// Build (or fetch) the launch description: dir 0 = forward (A has Cin channels, N = Cout), dir 1 = data
+// gradient (A has Cout channels, N = Cin).
+inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W) {
+  for (auto& c : t.cache)
+    if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == H && c.W == W && c.dir == dir)
+      return &c;
+  TcConv::Cached c;
+  memset(&c, 0, sizeof(c));
+  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = H; c.W = W; c.dir = dir;
+  TcConvParams& p = c.p;
+  const int K = dir == 0 ? t.Cin : t.Cout;
+  const int N = dir == 0 ? t.Cout : t.Cin;
+  p.B = B; p.H = H; p.W = W; p.Cin = K; p.N = N; p.ksz = t.k; p.pad = t.k / 2;
+  p.KC = (K % 64 == 0) ? 64 : 32;
+  int bn = tc_bn_max();
+  while (N % bn) bn >>= 1;
+  p.BN = bn;
+  p.CS = bn >= 64 ? 64 : 32;
+  tc_pick_tile(B, H, W, p.tw, p.th, p.tn);
+  p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_b = (B + p.tn - 1) / p.tn;
+  p.n_tiles = N / p.BN;
+  const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
+  const size_t staging = (size_t)128 * p.BN * 2;
+  const size_t fixed = 1024 /*alignment slack*/ + staging + 8 * (2 * kTcMaxStages + 6);
+  const size_t budget = 227 * 1024;
+  int stages = (int)((budget - fixed) / stage_bytes);
+  if (stages > kTcMaxStages) stages = kTcMaxStages;
+  if (stages < 2) { tc_err() = "tile does not fit shared memory"; return nullptr; }
+  p.stages = stages;
+  c.smem = fixed + (size_t)stages * stage_bytes;
+  const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  c.grid = (int)(total_tiles < sms ? total_tiles : sms);
+  // A: activation (K channels, W, H, B)
+  {
+    long long dims[4] = {K, W, H, B};
+    long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
+    int box[4] = {p.KC, p.tw, p.th, p.tn};
+    if (tc_make_map(&c.a, x, 4, dims, str, box, p.KC * 2)) return nullptr;
+  }
+  // B: weights [N][taps][K]
+  {
+    const int taps = t.k * t.k;
+    long long dims[3] = {K, taps, N};
+    long long str[3] = {1, K, (long long)taps * K};
+    int box[3] = {p.KC, 1, p.BN};
+    if (tc_make_map(&c.b, dir == 0 ? t.w_fwd : t.w_dgrad, 3, dims, str, box, p.KC * 2)) return nullptr;
+  }
+  // C: output (N channels, W, H, B)
+  {
+    long long dims[4] = {N, W, H, B};
+    long long str[4] = {1, y_ld, (long long)W * y_ld, (long long)H * W * y_ld};
+    int box[4] = {p.CS, p.tw, p.th, p.tn};
+    if (tc_make_map(&c.c, y, 4, dims, str, box, p.CS * 2)) return nullptr;
+  }
+  t.cache.push_back(c);
+  return &t.cache.back();
+}
+
+inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      tc_err() = "cudaFuncSetAttribute(max dynamic smem) failed";
+      return -1;
+    }
+    attr_set = true;
+  }
+  tc_conv_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
+inline bool tc_conv_eligible(const TcConv& t, const void* x, int x_ld, const void* y, int y_ld, const void* tp, int t_ld) {
+  return t.enabled && tc_ptr_ok(x, x_ld) && tc_ptr_ok(y, y_ld) && (!tp || tc_ptr_ok(tp, t_ld));
+}
+
+inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, const float* bias,
+                           int relu, double* stat, const void* tp, int t_ld, const float* bn_a, const float* bn_b,
+                           int accumulate, cudaStream_t stream, fu_counters* cnt) {
+  TcConv::Cached* c = tc_prepare(t, 0, x, x_ld, y, y_ld, B, H, W);
+  if (!c) return -1;
+  c->p.bias = bias; c->p.relu = relu; c->p.stat = stat;
+  c->p.t = reinterpret_cast<const bf16*>(tp); c->p.t_ld = t_ld; c->p.bn_a = bn_a; c->p.bn_b = bn_b;
+  if (accumulate) { c->p.t = reinterpret_cast<const bf16*>(y); c->p.t_ld = y_ld; c->p.bn_a = nullptr; c->p.bn_b = nullptr; }
+  return tc_launch(c, stream, cnt);
+}
+
+inline bool tc_dgrad_eligible(const TcConv& t, const void* dy, int dy_ld, const void* dx, int dx_ld) {
+  return t.enabled && tc_ptr_ok(dy, dy_ld) && tc_ptr_ok(dx, dx_ld);
+}
+
+inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
+                         cudaStream_t stream, fu_counters* cnt) {
+  TcConv::Cached* c = tc_prepare(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
+  if (!c) return -1;
+  c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  c->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c->p.t_ld = dx_ld;
+  return tc_launch(c, stream, cnt);
+}
+
+// not yet on tensor cores (CUDA-core kernels are used): 2x2/s2 down conv, 2x2/s2 transposed conv, weight gradient
 inline bool tc_down_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
 inline int tc_down_forward(TcConv&, const void*, int, void*, int, int, int, int, const float*, cudaStream_t, fu_counters*) { return -1; }
 inline bool tc_up_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
 inline int tc_up_forward(TcConv&, const void*, int, void*, int, int, int, int, const float*, cudaStream_t, fu_counters*) { return -1; }
-inline bool tc_dgrad_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
-inline int tc_conv_dgrad(TcConv&, const void*, int, void*, int, int, int, int, int, cudaStream_t, fu_counters*) { return -1; }
 inline bool tc_wgrad_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
 inline int tc_conv_wgrad(TcConv&, const void*, int, const void*, int, int, int, int, float*, cudaStream_t, fu_counters*) { return -1; }
 
-}  // namespace fu
-namespace fu {
-inline int tc_test_conv(int, int, int, int, int, int, int, int, int, int, const void*, const float*, const float*,
-                        void*, const void*, float*, double*, cudaStream_t, fu_counters*) { return -1; }
+// kernel-level test hook (fu_test_conv, impl = 1): bf16 NHWC tensors, fp32 torch-layout weights
+inline int tc_test_conv(int mode, int B, int H, int W, int Cin, int Cout, int k, int stride, int pad, int relu,
+                        const void* x, const float* w, const float* bias, void* y_or_dx, const void* dy, float* dw,
+                        double* stats, cudaStream_t stream, fu_counters* cnt) {
+  (void)dw;
+  if (stride != 1 || pad != k / 2 || (k != 1 && k != 3)) { tc_err() = "tc_test_conv: only 3x3/pad1 and 1x1, stride 1"; return -1; }
+  if (mode == 2) { tc_err() = "tc_test_conv: weight gradient not on tensor cores yet"; return -1; }
+  TcConv t;
+  char* mem = nullptr;
+  Bump dry;
+  tc_carve(t, Cin, Cout, k, false, true, dry);
+  if (!t.enabled) { tc_err() = "tc_test_conv: shape not eligible (channels must be multiples of 32)"; return -1; }
+  if (cudaMalloc(&mem, dry.off + 256) != cudaSuccess) { tc_err() = "cudaMalloc failed"; return -1; }
+  Bump real; real.base = mem;
+  tc_carve(t, Cin, Cout, k, false, true, real);
+  int rc = tc_pack(t, w, stream, cnt);
+  if (!rc) {
+    if (mode == 0) rc = tc_conv_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, relu, stats, nullptr, 0, nullptr, nullptr, 0, stream, cnt);
+    else rc = tc_conv_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, 0, stream, cnt);
+  }
+  cudaError_t e = cudaStreamSynchronize(stream);
+  cudaFree(mem);
+  if (!rc && e != cudaSuccess) { tc_err() = std::string("tc_test_conv: ") + cudaGetErrorString(e); return -1; }
+  return rc;
 }
+
+}  // namespace fu

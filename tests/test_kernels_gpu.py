@@ -89,3 +89,40 @@ def test_simt_conv_fwd_dgrad_wgrad(pkg, shape, precision):
         dx = run_conv(pkg, precision, 0, 1, x, w, None, dy, k, stride, pad)
         dx_ref = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=stride, padding=pad)
         assert rel_l2(dx, dx_ref) < tol
+
+
+TC_SHAPES = [  # B, Cin, Cout, H, W, k
+    (2, 64, 64, 16, 16, 3),      # KC=64 (128B swizzle), BN=64
+    (2, 32, 32, 16, 16, 3),      # KC=32 (64B swizzle), BN=32, 64-byte store boxes
+    (1, 64, 128, 24, 24, 3),     # BN=128: two 64-channel store boxes
+    (3, 128, 256, 12, 12, 3),    # two N tiles, several images per pixel tile
+    (32, 64, 64, 6, 6, 3),       # 6x6 bottom level: (2,2,32) pixel tiles
+    (2, 64, 32, 20, 12, 1),      # 1x1
+    (2, 96, 64, 10, 14, 3),      # Cin not a multiple of 64 -> 3 chunks of 32
+    (3, 64, 64, 9, 7, 3),        # ragged: tiles overhang the image and the batch
+    (2, 256, 128, 24, 24, 3),    # long K loop (36 iterations) through the ring twice
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_conv_fwd_dgrad(pkg, shape):
+    """tcgen05 implicit-GEMM conv (forward + data gradient) against torch-CPU fp32 on bf16-representable
+    operands: only fp32 accumulation order and the bf16 rounding of the output differ."""
+    B, Cin, Cout, H, W, k = shape
+    pad = k // 2
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=g)
+    y_ref = torch.relu(F.conv2d(x, w, b, padding=pad))
+    y, stats = run_conv(pkg, 1, 1, 0, x, w, b, None, k, 1, pad, relu=1, want_stats=True)
+    err = rel_l2(y, y_ref)
+    assert err < 6e-3, err                      # bf16 output rounding: ~2^-9 relative
+    # exactness check modulo output rounding: compare against the reference rounded the same way
+    assert rel_l2(y, y_ref.bfloat16().float()) < 2e-3
+    assert rel_l2(stats[:Cout], y.double().sum(dim=(0, 2, 3))) < 1e-4
+    assert rel_l2(stats[Cout:], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+    dy = torch.randn(B, Cout, H, W, generator=g).bfloat16().float()
+    dx = run_conv(pkg, 1, 1, 1, x, w, None, dy, k, 1, pad)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=pad)
+    assert rel_l2(dx, dx_ref) < 6e-3
