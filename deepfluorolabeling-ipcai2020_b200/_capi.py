@@ -31,7 +31,7 @@ class FuCounters(C.Structure):
 
 EXPORTS = ["fu_engine_create", "fu_engine_destroy", "fu_last_error", "fu_num_tensors",
            "fu_tensor_get_info", "fu_grad_numel", "fu_bind_tensors", "fu_forward", "fu_backward",
-           "fu_get_counters", "fu_build_info", "fu_test_conv", "fu_profile_enable", "fu_profile_report"]
+           "fu_get_counters", "fu_build_info", "fu_test_conv", "fu_profile_enable", "fu_profile_report", "fu_debug_copy"]
 
 _lib = None
 
@@ -71,6 +71,8 @@ def lib():
     L.fu_profile_enable.restype = i32
     L.fu_profile_report.argtypes = [vp, C.c_char_p, i64]
     L.fu_profile_report.restype = i64
+    L.fu_debug_copy.argtypes = [vp, C.c_char_p, vp, i64, C.POINTER(C.c_int32)]
+    L.fu_debug_copy.restype = i32
     L.fu_build_info.argtypes = []
     L.fu_build_info.restype = C.c_char_p
     L.fu_test_conv.argtypes = [i32] * 12 + [vp] * 8

@@ -1111,6 +1111,50 @@ int fu_get_counters(const fu_engine* e, fu_counters* out) {
   return FU_OK;
 }
 
+int fu_debug_copy(fu_engine* e, const char* name, float* dst, int64_t capacity, int32_t* shape4) {
+  if (!e || !name || !shape4) return FU_ERR_ARG;
+  if (!e->plan.valid) return e->fail(FU_ERR_STATE, "fu_debug_copy: no forward has run yet");
+  Plan& pl = e->plan;
+  const int D = e->cfg.depth;
+  View v; int lvl = -1;
+  std::string nm(name);
+  auto level_of_dec = [&](int j) { return D - 2 - j; };
+  int idx = -1, sub = -1;
+  char kind[16] = {0};
+  if (sscanf(name, "enc%d.%15[a-z]%d", &idx, kind, &sub) == 3 && idx >= 0 && idx < D) {
+    Block& b = e->enc[idx]; lvl = idx;
+    std::string k(kind);
+    if (sub < 0 || sub >= (int)b.convs.size()) return e->fail(FU_ERR_ARG, "fu_debug_copy: bad index in %s", name);
+    v = k == "r" ? b.r[sub] : k == "z" ? b.z[sub] : k == "dy" ? b.dy[sub] : k == "dz" ? b.dz[sub] : View();
+  } else if (sscanf(name, "dec%d.%15[a-z]%d", &idx, kind, &sub) == 3 && idx >= 0 && idx < D - 1) {
+    Block& b = e->dec[idx]; lvl = level_of_dec(idx);
+    std::string k(kind);
+    if (sub < 0 || sub >= (int)b.convs.size()) return e->fail(FU_ERR_ARG, "fu_debug_copy: bad index in %s", name);
+    v = k == "r" ? b.r[sub] : k == "z" ? b.z[sub] : k == "dy" ? b.dy[sub] : k == "dz" ? b.dz[sub] : View();
+  } else if (sscanf(name, "d_cat%d", &idx) == 1 && idx >= 0 && idx < D - 1) { v = pl.d_cat[idx]; lvl = idx; }
+  else if (sscanf(name, "cat%d", &idx) == 1 && idx >= 0 && idx < D - 1) { v = pl.cat[idx]; lvl = idx; }
+  else if (sscanf(name, "d_down%d", &idx) == 1 && idx >= 1 && idx < D) { v = pl.d_down[idx]; lvl = idx; }
+  else if (sscanf(name, "down%d", &idx) == 1 && idx >= 1 && idx < D) { v = pl.down[idx]; lvl = idx; }
+  else if (sscanf(name, "d_decout%d", &idx) == 1 && idx >= 0 && idx < D - 1) { v = pl.d_decout[idx]; lvl = idx; }
+  else if (sscanf(name, "decout%d", &idx) == 1 && idx >= 0 && idx < D - 1) { v = pl.decout[idx]; lvl = idx; }
+  else if (nm == "bott") { v = pl.bott; lvl = D - 1; }
+  else if (nm == "d_bott") { v = pl.d_bott; lvl = D - 1; }
+  else if (nm == "hcat") { v = pl.hcat; lvl = 0; }
+  else if (nm == "d_hcat") { v = pl.d_hcat; lvl = 0; }
+  if (!v.p || lvl < 0) return e->fail(FU_ERR_ARG, "fu_debug_copy: unknown or unmaterialised tensor '%s'", name);
+  const int h = pl.H >> lvl, w = pl.W >> lvl;
+  shape4[0] = pl.B; shape4[1] = v.C; shape4[2] = h; shape4[3] = w;
+  const int64_t need = (int64_t)pl.B * v.C * h * w;
+  if (!dst) return FU_OK;
+  if (capacity < need) return e->fail(FU_ERR_ARG, "fu_debug_copy: buffer too small");
+  const long long HW = (long long)h * w;
+  if (e->esz == 2)
+    LAUNCH(e, (nhwc_to_nchw_kernel<bf16>), grid1d(pl.B * HW, 256, e->num_sms), 256, reinterpret_cast<const bf16*>(v.p), v.ld, dst, pl.B, v.C, HW);
+  else
+    LAUNCH(e, (nhwc_to_nchw_kernel<float>), grid1d(pl.B * HW, 256, e->num_sms), 256, reinterpret_cast<const float*>(v.p), v.ld, dst, pl.B, v.C, HW);
+  return FU_OK;
+}
+
 int fu_profile_enable(fu_engine* e, int on) {
   if (!e) return FU_ERR_ARG;
   for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

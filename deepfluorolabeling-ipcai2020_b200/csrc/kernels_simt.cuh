@@ -631,6 +631,17 @@ __global__ void nchw_to_nhwc_kernel(const float* src, T* dst, int ld, int B, int
   }
 }
 
+// T NHWC (pixel stride ld) -> fp32 NCHW (debug / per-layer parity read-back)
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* src, int ld, float* dst, int B, int C, long long HW) {
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, hw = i - n * HW;
+    for (int c = 0; c < C; ++c) dst[(n * C + c) * HW + hw] = ld1(src + i * ld + c);
+  }
+}
+
 constexpr int kMaxClasses = 32;
 
 // logits (T NHWC, stride ld) -> seg (fp32 NCHW) [softmax over channels], optional fp32 NCHW logits copy

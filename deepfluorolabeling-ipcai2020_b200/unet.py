@@ -299,6 +299,19 @@ class UNet(nn.Module):
         _capi.lib().fu_get_counters(self._handle, C.byref(cnt))
         return {n: int(getattr(cnt, n)) for n, _ in cnt._fields_}
 
+    def debug_tensor(self, name):
+        """fp32 NCHW copy of an internal engine tensor of the last forward/backward (see fu_debug_copy)."""
+        L = _capi.lib()
+        shape = (C.c_int32 * 4)()
+        rc = L.fu_debug_copy(self._handle, name.encode(), None, 0, shape)
+        if rc != 0:
+            raise KeyError(_capi.last_error(self._handle))
+        out = torch.empty(tuple(shape), device=self._handle_device, dtype=torch.float32)
+        rc = L.fu_debug_copy(self._handle, name.encode(), out.data_ptr(), out.numel(), shape)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error(self._handle))
+        return out
+
     def profile(self, on=True):
         """Start/stop per-launch CUDA-event profiling inside the engine."""
         if self._handle is None:

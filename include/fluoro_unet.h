@@ -142,6 +142,13 @@ int fu_get_counters(const fu_engine* e, fu_counters* out);
 int fu_profile_enable(fu_engine* e, int on);
 int64_t fu_profile_report(fu_engine* e, char* buf, int64_t cap);
 
+/* Read back one internal NHWC tensor of the last forward/backward as fp32 NCHW (per-layer parity
+ * tests).  Names: "enc<l>.r<i>" / ".z<i>" (post-ReLU / post-BN activations of conv i of
+ * encoder block l), ".dy<i>" / ".dz<i>" (their gradients), "dec<j>.*", "cat<l>", "d_cat<l>", "down<l>",
+ * "d_down<l>", "decout<l>", "d_decout<l>", "bott", "d_bott", "hcat", "d_hcat".  shape4 receives
+ * (B,C,H,W); with dst == NULL only the shape is returned.  Enqueued on the stream of the last call. */
+int fu_debug_copy(fu_engine* e, const char* name, float* dst, int64_t capacity, int32_t* shape4);
+
 /* Build information: "sm_100a;tcgen05=1;..." */
 const char* fu_build_info(void);
 
