@@ -95,6 +95,7 @@ struct fu_engine {
   size_t wmem_bytes = 0;
   double* dscr_fwd = nullptr; size_t dscr_fwd_bytes = 0;
   double* dscr_bwd = nullptr; size_t dscr_bwd_bytes = 0;
+  char* wgrad_scr = nullptr; size_t wgrad_scr_bytes = 0;   // tensor-core weight-gradient accumulators
   float *ones = nullptr, *zeros = nullptr;
   int64_t packed_version = -1;
   bool packed_once = false;
@@ -309,7 +310,7 @@ void for_each_bn(fu_engine* e, F f) {
   for (auto& b : e->dec) for (auto& bn : b.bns) f(bn);
 }
 
-void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db) {
+void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
   int maxc = 4;
   for_each_conv(e, [&](ConvW& c) {
     conv_pack_sizes(c, false, false);
@@ -321,7 +322,7 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db) {
     c.bsum = db.take<double>(c.Cout);
     if (c.Cout > maxc) maxc = c.Cout;
     if (c.Cin > maxc) maxc = c.Cin;
-    tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision == FU_PRECISION_BF16, w);
+    tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision == FU_PRECISION_BF16, w, ws);
   });
   for_each_bn(e, [&](BNL& b) {
     b.stat = df.take<double>(2 * b.C);
@@ -335,8 +336,10 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db) {
 }
 
 int alloc_persistent(fu_engine* e) {
-  Bump w, df, db;
-  carve_persistent(e, w, df, db);
+  Bump w, df, db, ws;
+  carve_persistent(e, w, df, db, ws);
+  e->wgrad_scr_bytes = ws.off + 256;
+  CUDA_TRY(e, cudaMalloc(&e->wgrad_scr, e->wgrad_scr_bytes));
   e->wmem_bytes = w.off + 256;
   e->dscr_fwd_bytes = df.off + 256;
   e->dscr_bwd_bytes = db.off + 256;
@@ -344,9 +347,10 @@ int alloc_persistent(fu_engine* e) {
   CUDA_TRY(e, cudaMalloc(&e->dscr_fwd, e->dscr_fwd_bytes));
   CUDA_TRY(e, cudaMalloc(&e->dscr_bwd, e->dscr_bwd_bytes));
   CUDA_TRY(e, cudaMemset(e->wmem, 0, e->wmem_bytes));
-  Bump w2, df2, db2;
+  Bump w2, df2, db2, ws2;
   w2.base = e->wmem; df2.base = reinterpret_cast<char*>(e->dscr_fwd); db2.base = reinterpret_cast<char*>(e->dscr_bwd);
-  carve_persistent(e, w2, df2, db2);
+  ws2.base = e->wgrad_scr;
+  carve_persistent(e, w2, df2, db2, ws2);
   // ones / zeros
   int maxc = 4;
   for_each_conv(e, [&](ConvW& c) { if (c.Cout > maxc) maxc = c.Cout; if (c.Cin > maxc) maxc = c.Cin; });
@@ -804,7 +808,10 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
                "conv%d_wgrad %dx%d %d->%d", cw.k, H, W, cw.Cin, cw.Cout);
   }
   if (tc_wgrad_eligible(cw.tc, x.p, x.ld, dy.p, dy.ld)) {
-    if (tc_conv_wgrad(cw.tc, x.p, x.ld, dy.p, dy.ld, B, H, W, dw, e->stream, &e->cnt))
+    if (e->prof) e->prof_begin("tc_wgrad_kernel");
+    const int trc = tc_conv_wgrad(cw.tc, x.p, x.ld, dy.p, dy.ld, B, H, W, dw, e->stream, &e->cnt);
+    if (e->prof) e->prof_end();
+    if (trc)
       return e->fail(FU_ERR_CUDA, "tensor-core wgrad launch failed: %s", tc_last_error());
     return FU_OK;
   }
@@ -872,6 +879,8 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   int rc;
   CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
   CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
+  if (e->cfg.precision == FU_PRECISION_BF16 && e->wgrad_scr_bytes > 512)
+    CUDA_TRY(e, cudaMemsetAsync(e->wgrad_scr, 0, e->wgrad_scr_bytes, e->stream));
   // ---- heads ----
   e->set_tag(0, 0, "heads_bwd");
   View feat = slice(pl.hcat, 0, e->Cf, esz);
@@ -1030,6 +1039,7 @@ void fu_engine_destroy(fu_engine* e) {
   if (e->wmem) cudaFree(e->wmem);
   if (e->dscr_fwd) cudaFree(e->dscr_fwd);
   if (e->dscr_bwd) cudaFree(e->dscr_bwd);
+  if (e->wgrad_scr) cudaFree(e->wgrad_scr);
   delete e;
 }
 

@@ -155,6 +155,22 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// shared-memory matrix descriptor of an MN-major operand: 64-element (128 B, SWIZZLE_128B) blocks along
+// M/N that are `lbo` bytes apart, K rows 128 B apart, 8-row K groups `sbo` = 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// bf16 x bf16 -> fp32, both operands MN-major (K = pixels is the strided dimension), M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
 // ===========================================================================
 // the convolution kernel (forward and data gradient; 3x3/pad 1 and 1x1)
 // ===========================================================================
@@ -422,6 +438,154 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ===========================================================================
+// weight gradient: dW[tap][co][ci] += sum over pixels dY[p][co] * X[p @ tap][ci]
+// A = dY tile (M = 128 out-channels), B = X tile shifted by the tap (N = 64/128 in-channels), K = 64 pixels
+// per pipeline stage.  Both operands are the NHWC tiles exactly as TMA delivers them (pixel rows of 64
+// channels) = MN-major for the MMA.  One CTA owns one (co tile, ci tile, filter row) and a range of pixel
+// tiles (split-K); the 3 taps of the filter row share the dY tile and accumulate in 3 TMEM regions.
+// ===========================================================================
+struct TcWgradParams {
+  int B, H, W, Cin, Cout;
+  int ksz, pad, taps_per_cta, groups;
+  int N;                        // in-channel tile (64 or 128)
+  int tw, th, tn;               // pixel tile, tw*th*tn == 64
+  int tiles_w, tiles_h, tiles_b;
+  int co_tiles, ci_tiles, splits, stages;
+  float* dw_acc;                // [taps][Cout][Cin] fp32, zeroed by the caller
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kBox = 64u * 128u;                 // 64 pixels x 64 channels bf16
+  const int nblk_b = p.N / 64;
+  const uint32_t a_bytes = 2u * kBox;
+  const uint32_t b_bytes = (uint32_t)(p.taps_per_cta * nblk_b) * kBox;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_off = (uint32_t)p.stages * stage_bytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kTcMaxStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (uint32_t)(2 * kTcMaxStages);
+  const uint32_t slot_addr = bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 1);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * kTcMaxStages + 1));
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(p.taps_per_cta * p.N)) tmem_cols <<= 1;
+
+  // work decode
+  int bid = blockIdx.x;
+  const int split = bid % p.splits; bid /= p.splits;
+  const int grp = bid % p.groups; bid /= p.groups;
+  const int ci_t = bid % p.ci_tiles;
+  const int co_t = bid / p.ci_tiles;
+  const int co0 = co_t * 128, ci0 = ci_t * p.N;
+  const int total_pt = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int per = (total_pt + p.splits - 1) / p.splits;
+  const int pt_begin = split * per;
+  const int pt_end = min(total_pt, pt_begin + per);
+  const int n_iters = max(pt_end - pt_begin, 0);
+  const int nblk_a = (p.Cout - co0 > 64) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmX);
+  }
+  if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        int pt = pt_begin + it;
+        const int w0 = (pt % p.tiles_w) * p.tw; pt /= p.tiles_w;
+        const int h0 = (pt % p.tiles_h) * p.th; pt /= p.tiles_h;
+        const int n0 = pt * p.tn;
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+        ptx::mbar_expect_tx(full_bar(stage), (uint32_t)nblk_a * kBox + b_bytes);
+        for (int blk = 0; blk < nblk_a; ++blk)
+          ptx::tma_load_4d(a_dst + (uint32_t)blk * kBox, &tmY, full_bar(stage), co0 + blk * 64, w0, h0, n0);
+        for (int t = 0; t < p.taps_per_cta; ++t) {
+          const int kh = p.ksz == 3 ? grp : 0, kw = p.ksz == 3 ? t : 0;
+          for (int blk = 0; blk < nblk_b; ++blk)
+            ptx::tma_load_4d(a_dst + a_bytes + (uint32_t)(t * nblk_b + blk) * kBox, &tmX, full_bar(stage),
+                             ci0 + blk * 64, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N);
+      for (int it = 0; it < n_iters; ++it) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int t = 0; t < p.taps_per_cta; ++t) {
+          for (int ks = 0; ks < 4; ++ks) {     // 64 pixels = 4 x K16; 16 pixel rows = 2048 B
+            const uint64_t ad = umma_desc_mnmajor(a_addr + (uint32_t)ks * 2048u, kBox, 1024u);
+            const uint64_t bd = umma_desc_mnmajor(b_addr + (uint32_t)(t * nblk_b) * kBox + (uint32_t)ks * 2048u, kBox, 1024u);
+            ptx::umma_bf16(tmem_base + (uint32_t)(t * p.N), ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(empty_bar(stage));
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::umma_commit(done_bar);
+    }
+  } else if (n_iters > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int co = co0 + row;
+    ptx::mbar_wait(done_bar, 0);
+    ptx::tc_fence_after();
+    for (int t = 0; t < p.taps_per_cta; ++t) {
+      const int tap = p.ksz == 3 ? p.ksz * (blockIdx.x / p.splits % p.groups) + t : 0;
+      for (int j = 0; j < p.N / 32; ++j) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + (uint32_t)(t * p.N + j * 32) + ((uint32_t)(q * 32) << 16), v);
+        ptx::tmem_ld_wait();
+        const int ci = ci0 + j * 32;
+        if (co < p.Cout && ci < p.Cin) {
+          float* dst = p.dw_acc + ((long long)tap * p.Cout + co) * p.Cin + ci;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + i),
+                      make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                  __uint_as_float(v[i + 3])));
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// [taps][Cout][Cin] fp32 accumulator -> torch layout (Cout,Cin,k,k)
+__global__ void tc_wgrad_unpack_kernel(const float* acc, float* dw, int Cout, int Cin, int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;   // co*Cin + ci
+    dw[i] = acc[(long long)t * Cout * Cin + r];
+  }
+}
+
 // fp32 torch weights (Cout,Cin,k,k) -> bf16 [Cout][tap][Cin] (forward) and [Cin][flip(tap)][Cout] (data gradient)
 __global__ void tc_pack_conv_kernel(const float* w, bf16* fwd, bf16* dgrad, int Cout, int Cin, int taps) {
   const long long total = (long long)Cout * Cin * taps;
@@ -516,6 +680,12 @@ struct TcConv {
   int Cin = 0, Cout = 0, k = 0;
   bf16* w_fwd = nullptr;     // [Cout][taps][Cin]
   bf16* w_dgrad = nullptr;   // [Cin][taps][Cout]
+  float* dw_acc = nullptr;   // [taps][Cout][Cin] fp32 weight-gradient accumulator
+  struct WCached {
+    const void *x, *dy; int x_ld, dy_ld, B, H, W;
+    CUtensorMap y, xm; TcWgradParams p; int grid; size_t smem;
+  };
+  std::vector<WCached> wcache;
   struct Cached {
     const void *x, *y; int x_ld, y_ld, B, H, W, dir;
     CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem;
@@ -533,7 +703,7 @@ inline int tc_bn_max() {
   return v;
 }
 
-inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool enabled, Bump& w) {
+inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool enabled, Bump& w, Bump& ws) {
   t.Cin = Cin; t.Cout = Cout; t.k = k;
   t.enabled = enabled && !transposed && (k == 3 || k == 1) && (Cin % 32 == 0) && (Cout % 32 == 0) &&
               getenv("FU_TC_DISABLE") == nullptr;
@@ -541,7 +711,9 @@ inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool 
   const size_t n = (size_t)Cin * Cout * k * k;
   t.w_fwd = w.take<bf16>(n);
   t.w_dgrad = w.take<bf16>(n);
+  t.dw_acc = ws.take<float>(n);
   t.cache.clear();
+  t.wcache.clear();
 }
 
 inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* cnt) {
@@ -666,31 +838,124 @@ inline bool tc_down_eligible(const TcConv&, const void*, int, const void*, int) 
 inline int tc_down_forward(TcConv&, const void*, int, void*, int, int, int, int, const float*, cudaStream_t, fu_counters*) { return -1; }
 inline bool tc_up_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
 inline int tc_up_forward(TcConv&, const void*, int, void*, int, int, int, int, const float*, cudaStream_t, fu_counters*) { return -1; }
-inline bool tc_wgrad_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
-inline int tc_conv_wgrad(TcConv&, const void*, int, const void*, int, int, int, int, float*, cudaStream_t, fu_counters*) { return -1; }
+inline bool tc_wgrad_eligible(const TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld) {
+  return t.enabled && tc_ptr_ok(x, x_ld) && tc_ptr_ok(dy, dy_ld) && getenv("FU_TC_NO_WGRAD") == nullptr;
+}
+
+inline void tc_pick_tile64(int B, int H, int W, int& tw, int& th, int& tn) {
+  long long best = -1;
+  tw = 8; th = 8; tn = 1;
+  for (int a = 1; a <= 64; a <<= 1)
+    for (int b = 1; a * b <= 64; b <<= 1) {
+      const int c = 64 / (a * b);
+      const long long tiles = (long long)((W + a - 1) / a) * ((H + b - 1) / b) * ((B + c - 1) / c);
+      const long long key = tiles * 1024 - a;
+      if (best < 0 || key < best) { best = key; tw = a; th = b; tn = c; }
+    }
+}
+
+// dw (torch layout, fp32) = weight gradient; t.dw_acc must have been zeroed since its last use.
+inline int tc_conv_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld, int B, int H, int W, float* dw,
+                         cudaStream_t stream, fu_counters* cnt) {
+  TcConv::WCached* c = nullptr;
+  for (auto& k : t.wcache)
+    if (k.x == x && k.dy == dy && k.x_ld == x_ld && k.dy_ld == dy_ld && k.B == B && k.H == H && k.W == W) { c = &k; break; }
+  if (!c) {
+    TcConv::WCached n;
+    memset(&n, 0, sizeof(n));
+    n.x = x; n.dy = dy; n.x_ld = x_ld; n.dy_ld = dy_ld; n.B = B; n.H = H; n.W = W;
+    TcWgradParams& p = n.p;
+    p.B = B; p.H = H; p.W = W; p.Cin = t.Cin; p.Cout = t.Cout; p.ksz = t.k; p.pad = t.k / 2;
+    p.taps_per_cta = t.k == 3 ? 3 : 1; p.groups = t.k == 3 ? 3 : 1;
+    p.N = t.Cin > 64 ? 128 : 64;
+    tc_pick_tile64(B, H, W, p.tw, p.th, p.tn);
+    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_b = (B + p.tn - 1) / p.tn;
+    p.co_tiles = (t.Cout + 127) / 128; p.ci_tiles = (t.Cin + p.N - 1) / p.N;
+    const size_t stage_bytes = (size_t)(2 + p.taps_per_cta * (p.N / 64)) * 8192;
+    const size_t fixed = 1024 + 8 * (2 * kTcMaxStages + 4);
+    int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+    if (stages > kTcMaxStages) stages = kTcMaxStages;
+    if (stages < 2) { tc_err() = "wgrad tile does not fit shared memory"; return -1; }
+    p.stages = stages;
+    n.smem = fixed + (size_t)stages * stage_bytes;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
+    const long long total_pt = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+    long long splits = (2ll * sms + units - 1) / units;       // ~2 CTAs per SM in flight over the launch
+    const long long max_splits = (total_pt + 3) / 4;          // at least 4 pixel tiles per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const long long per = (total_pt + splits - 1) / splits;
+    splits = (total_pt + per - 1) / per;
+    p.splits = (int)splits;
+    n.grid = (int)(units * splits);
+    p.dw_acc = t.dw_acc;
+    {
+      long long dims[4] = {t.Cout, W, H, B};
+      long long str[4] = {1, dy_ld, (long long)W * dy_ld, (long long)H * W * dy_ld};
+      int box[4] = {64, p.tw, p.th, p.tn};
+      if (tc_make_map(&n.y, dy, 4, dims, str, box, 128)) return -1;
+    }
+    {
+      long long dims[4] = {t.Cin, W, H, B};
+      long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
+      int box[4] = {64, p.tw, p.th, p.tn};
+      if (tc_make_map(&n.xm, x, 4, dims, str, box, 128)) return -1;
+    }
+    t.wcache.push_back(n);
+    c = &t.wcache.back();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      tc_err() = "cudaFuncSetAttribute(max dynamic smem, wgrad) failed";
+      return -1;
+    }
+    attr_set = true;
+  }
+  tc_wgrad_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
+  const long long total = (long long)t.Cin * t.Cout * t.k * t.k;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  tc_wgrad_unpack_kernel<<<(unsigned)g, 256, 0, stream>>>(t.dw_acc, dw, t.Cout, t.Cin, t.k * t.k);
+  if (cnt) { cnt->kernel_launches += 2; cnt->tc_kernel_launches++; }
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
+  return 0;
+}
 
 // kernel-level test hook (fu_test_conv, impl = 1): bf16 NHWC tensors, fp32 torch-layout weights
 inline int tc_test_conv(int mode, int B, int H, int W, int Cin, int Cout, int k, int stride, int pad, int relu,
                         const void* x, const float* w, const float* bias, void* y_or_dx, const void* dy, float* dw,
                         double* stats, cudaStream_t stream, fu_counters* cnt) {
-  (void)dw;
   if (stride != 1 || pad != k / 2 || (k != 1 && k != 3)) { tc_err() = "tc_test_conv: only 3x3/pad1 and 1x1, stride 1"; return -1; }
-  if (mode == 2) { tc_err() = "tc_test_conv: weight gradient not on tensor cores yet"; return -1; }
   TcConv t;
-  char* mem = nullptr;
-  Bump dry;
-  tc_carve(t, Cin, Cout, k, false, true, dry);
+  char *mem = nullptr, *mem2 = nullptr;
+  Bump dry, dry2;
+  tc_carve(t, Cin, Cout, k, false, true, dry, dry2);
   if (!t.enabled) { tc_err() = "tc_test_conv: shape not eligible (channels must be multiples of 32)"; return -1; }
-  if (cudaMalloc(&mem, dry.off + 256) != cudaSuccess) { tc_err() = "cudaMalloc failed"; return -1; }
-  Bump real; real.base = mem;
-  tc_carve(t, Cin, Cout, k, false, true, real);
-  int rc = tc_pack(t, w, stream, cnt);
-  if (!rc) {
+  if (cudaMalloc(&mem, dry.off + 256) != cudaSuccess || cudaMalloc(&mem2, dry2.off + 256) != cudaSuccess) {
+    tc_err() = "cudaMalloc failed";
+    return -1;
+  }
+  Bump real, real2; real.base = mem; real2.base = mem2;
+  tc_carve(t, Cin, Cout, k, false, true, real, real2);
+  int rc = 0;
+  if (mode == 2) {
+    cudaMemsetAsync(mem2, 0, dry2.off + 256, stream);
+    rc = tc_conv_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
+  } else {
+    rc = tc_pack(t, w, stream, cnt);
+  }
+  if (!rc && mode != 2) {
     if (mode == 0) rc = tc_conv_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, relu, stats, nullptr, 0, nullptr, nullptr, 0, stream, cnt);
     else rc = tc_conv_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, 0, stream, cnt);
   }
   cudaError_t e = cudaStreamSynchronize(stream);
   cudaFree(mem);
+  cudaFree(mem2);
   if (!rc && e != cudaSuccess) { tc_err() = std::string("tc_test_conv: ") + cudaGetErrorString(e); return -1; }
   return rc;
 }

@@ -126,3 +126,7 @@ def test_tc_conv_fwd_dgrad(pkg, shape):
     dx = run_conv(pkg, 1, 1, 1, x, w, None, dy, k, 1, pad)
     dx_ref = torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=pad)
     assert rel_l2(dx, dx_ref) < 6e-3
+    # weight gradient: bf16 operands, fp32 accumulation over all pixels (split-K + fp32 atomics)
+    dw = run_conv(pkg, 1, 1, 2, x, w, None, dy, k, 1, pad)
+    dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=pad)
+    assert rel_l2(dw, dw_ref) < 1e-4, rel_l2(dw, dw_ref)
