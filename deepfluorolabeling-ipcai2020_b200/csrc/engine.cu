@@ -41,6 +41,7 @@ struct ConvW {
   float* wp_fwd = nullptr;    // CUDA-core packing for the forward GEMM
   float* wp_dgrad = nullptr;  // CUDA-core packing for the data-gradient GEMM
   int npad_fwd = 0, npad_dgrad = 0, n_fwd = 0, n_dgrad = 0;
+  bool small_cin = false;     // first-layer kernels (Cin <= 2, Cout % 8 == 0)
   double* bsum = nullptr;     // [Cout] bias-gradient accumulator
   TcConv tc;                  // tensor-core packings / descriptors (throughput mode)
 };
@@ -320,6 +321,8 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
     const int taps_d = c.transposed ? 4 : (c.k == 2 ? 1 : c.k * c.k);
     c.wp_dgrad = w.take<float>((size_t)taps_d * c.Cout * c.npad_dgrad);
     c.bsum = db.take<double>(c.Cout);
+    c.small_cin = !c.transposed && (c.k == 3 || c.k == 1) && c.Cin <= 2 && (c.Cout % 8 == 0) && c.Cout <= 256 &&
+                  (c.Cout & (c.Cout - 1)) == 0;
     if (c.Cout > maxc) maxc = c.Cout;
     if (c.Cin > maxc) maxc = c.Cin;
     tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision == FU_PRECISION_BF16, w, ws);
@@ -474,6 +477,12 @@ int pack_one(fu_engine* e, const float* src, float* dst, int T, int K, int N, in
 int pack_conv(fu_engine* e, ConvW& c) {
   const float* w = reinterpret_cast<const float*>(e->tensors[c.w_idx].data);
   int rc;
+  if (c.tc.enabled) {
+    // tensor-core layer: only the bf16 packings are ever read
+    if ((rc = tc_pack(c.tc, w, e->stream, &e->cnt))) return e->fail(FU_ERR_CUDA, "tensor-core weight pack failed");
+    return FU_OK;
+  }
+  if (c.small_cin) return FU_OK;   // first-layer kernels read the torch layout directly
   if (c.transposed) {
     // W[ci][co][ab].  fwd: [1][Cin][(ab)*Cout+co];  dgrad (2x2/s2 conv over dY): [tap=ab][Cout][Cin]
     if ((rc = pack_one(e, w, c.wp_fwd, 1, c.Cin, 4 * c.Cout, c.npad_fwd, c.Cout, 0, 0, (long long)c.Cout * 4, 1, 4))) return rc;
@@ -487,9 +496,6 @@ int pack_conv(fu_engine* e, ConvW& c) {
     // W[co][ci][tap].  fwd: [tap][Cin][Cout];  dgrad: [flip(tap)][Cout][Cin]
     if ((rc = pack_one(e, w, c.wp_fwd, kk, c.Cin, c.Cout, c.npad_fwd, c.Cout, 0, 1, kk, 0, (long long)c.Cin * kk))) return rc;
     if ((rc = pack_one(e, w, c.wp_dgrad, kk, c.Cout, c.Cin, c.npad_dgrad, c.Cin, 1, 1, (long long)c.Cin * kk, 0, kk))) return rc;
-  }
-  if (e->cfg.precision == FU_PRECISION_BF16) {
-    if ((rc = tc_pack(c.tc, w, e->stream, &e->cnt))) return e->fail(FU_ERR_CUDA, "tensor-core weight pack failed");
   }
   return FU_OK;
 }
@@ -629,6 +635,26 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     if (rc) return e->fail(FU_ERR_CUDA, "tensor-core conv launch failed: %s", tc_last_error());
     return FU_OK;
   }
+  if (cw.tc.enabled) return e->fail(FU_ERR_STATE, "tensor-core layer with a misaligned view (internal error)");
+  const size_t va = 4 * sizeof(T);
+  if (cw.small_cin && (y.ld % 4 == 0) && aligned(y.p, va) && (!t || ((t->ld % 4 == 0) && aligned(t->p, va)))) {
+    SmallCinArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x.p; a.x_ld = x.ld; a.Cin = cw.Cin; a.y = y.p; a.y_ld = y.ld; a.Cout = cw.Cout;
+    a.w = tdata(e, cw.w_idx); a.bias = tdata(e, cw.b_idx);
+    a.B = B; a.H = H; a.W = W; a.k = cw.k; a.pad = cw.k / 2; a.relu = relu;
+    if (t) { a.t = t->p; a.t_ld = t->ld; a.bn_a = bn_a; a.bn_b = bn_b; }
+    a.stat = stat;
+    const long long total = (long long)B * H * W * (cw.Cout / 8);
+    const size_t smem = ((size_t)cw.k * cw.k * cw.Cin * cw.Cout + 3 * cw.Cout) * sizeof(float);
+    auto kfn = conv_small_cin_kernel<T>;
+    if (e->prof) e->prof_begin("conv_small_cin_kernel");
+    kfn<<<grid1d(total, 256, e->num_sms), 256, smem, e->stream>>>(a);
+    if (e->prof) e->prof_end();
+    e->cnt.kernel_launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) return e->fail(FU_ERR_CUDA, "conv_small_cin_kernel launch failed");
+    return FU_OK;
+  }
   ConvCall c;
   c.x = x; c.B = B; c.Hi = H; c.Wi = W; c.y = y; c.Ho = H; c.Wo = W;
   c.w = cw.wp_fwd; c.N = cw.n_fwd; c.Npad = cw.npad_fwd;
@@ -743,6 +769,21 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
   e->set_tag(0, 0, "heads_fwd");
   View feat = slice(pl.hcat, 0, e->Cf, esz);
   View lg = slice(pl.hcat, e->Cf, c.n_classes, esz);
+  if (e->Cf == 32 && c.n_classes == 7 && (c.num_lands == 0 || (c.num_lands == 14 && e->lands.size() == 2 && e->lands[0].Cout == 21))) {
+    // paper heads (7 classes, 39 -> 21 -> 14): one fused pass
+    const long long P = (long long)B * HW;
+    if (c.num_lands == 14)
+      LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 21, 14>), (unsigned)((P + 127) / 128), 128,
+             reinterpret_cast<const T*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx),
+             tdata(e, e->lands[1].w_idx), reinterpret_cast<T*>(lg.p), reinterpret_cast<T*>(pl.hmid[0].p),
+             pl.hmid[0].ld, seg, logits, heat, B, HW, c.do_soft_max);
+    else
+      LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 1, 0>), (unsigned)((P + 127) / 128), 128,
+             reinterpret_cast<const T*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), (const float*)nullptr,
+             (const float*)nullptr, reinterpret_cast<T*>(lg.p), (T*)nullptr, 0, seg, logits, (float*)nullptr, B, HW,
+             c.do_soft_max);
+    return FU_OK;
+  }
   {
     ConvCall cc;
     cc.x = feat; cc.B = B; cc.Hi = H; cc.Wi = W; cc.y = lg; cc.Ho = H; cc.Wo = W;
@@ -813,6 +854,21 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
     if (e->prof) e->prof_end();
     if (trc)
       return e->fail(FU_ERR_CUDA, "tensor-core wgrad launch failed: %s", tc_last_error());
+    return FU_OK;
+  }
+  if (cw.small_cin && (dy.ld % 4 == 0) && aligned(dy.p, 4 * sizeof(T))) {
+    SmallCinWgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x.p; a.x_ld = x.ld; a.Cin = cw.Cin; a.dy = dy.p; a.dy_ld = dy.ld; a.Cout = cw.Cout;
+    a.B = B; a.H = H; a.W = W; a.k = cw.k; a.pad = cw.k / 2; a.dw = dw;
+    const int rows = 256 / (cw.Cout / 4);
+    long long gx = ((long long)B * H * W + (long long)rows * 32 - 1) / ((long long)rows * 32);
+    if (gx > (long long)e->num_sms * 8) gx = (long long)e->num_sms * 8;
+    if (gx < 1) gx = 1;
+    const int kk = cw.k * cw.k * cw.Cin;
+    if (kk <= 2) LAUNCH(e, (wgrad_small_cin_kernel<T, 2>), (unsigned)gx, 256, a);
+    else if (kk <= 9) LAUNCH(e, (wgrad_small_cin_kernel<T, 9>), (unsigned)gx, 256, a);
+    else LAUNCH(e, (wgrad_small_cin_kernel<T, 18>), (unsigned)gx, 256, a);
     return FU_OK;
   }
   WgradCall c;

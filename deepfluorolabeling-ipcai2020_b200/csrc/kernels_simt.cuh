@@ -224,6 +224,250 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const ConvArgs p) {
 }
 
 // --------------------------------------------------------------------------
+// First-layer convolutions (C_in = in_channels, 1 in every reference script): K is 9 or 1, so
+// tensor cores are pointless and the op is bound by writing the C_out-channel output once.
+// One thread = one pixel x 8 output channels; weights live in shared memory.
+// y = [relu](conv_k(x) + bias) [+ bn_a*t + bn_b], optional per-channel sum / sum-of-squares.
+// --------------------------------------------------------------------------
+struct SmallCinArgs {
+  const void* x; int x_ld; int Cin;
+  void* y; int y_ld; int Cout;
+  const float* w;        // torch layout (Cout, Cin, k, k)
+  const float* bias;
+  int B, H, W, k, pad, relu;
+  const void* t; int t_ld; const float* bn_a; const float* bn_b;
+  double* stat;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallCinArgs p) {
+  extern __shared__ float sm_w[];            // [taps*Cin][Cout] + [Cout] bias + 2*[Cout] stats
+  const int taps = p.k * p.k, KK = taps * p.Cin;
+  float* sm_b = sm_w + KK * p.Cout;
+  float* sm_s = sm_b + p.Cout;
+  for (int i = threadIdx.x; i < KK * p.Cout; i += blockDim.x) {
+    const int co = i % p.Cout, kk = i / p.Cout;       // kk = tap*Cin + ci
+    const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
+    sm_w[i] = p.w[((long long)co * p.Cin + ci) * taps + tap];
+  }
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+    sm_b[i] = p.bias ? p.bias[i] : 0.f;
+    sm_s[i] = 0.f; sm_s[p.Cout + i] = 0.f;
+  }
+  __syncthreads();
+  const int groups = p.Cout >> 3;
+  const long long P = (long long)p.B * p.H * p.W;
+  const long long total = P * groups;
+  const T* xp = reinterpret_cast<const T*>(p.x);
+  const T* tp = reinterpret_cast<const T*>(p.t);
+  T* yp = reinterpret_cast<T*>(p.y);
+  float cs[8], cq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int w = (int)(pix % p.W);
+    const long long r = pix / p.W;
+    const int h = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sm_b[g * 8 + j];
+    for (int tap = 0; tap < taps; ++tap) {
+      const int ih = h + tap / p.k - p.pad, iw = w + tap % p.k - p.pad;
+      if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) continue;
+      const T* src = xp + ((long long)(n * p.H + ih) * p.W + iw) * p.x_ld;
+      for (int ci = 0; ci < p.Cin; ++ci) {
+        const float xv = ld1(src + ci);
+        const float4 w0 = *reinterpret_cast<const float4*>(sm_w + (tap * p.Cin + ci) * p.Cout + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sm_w + (tap * p.Cin + ci) * p.Cout + g * 8 + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+    if (p.t) {
+      const float4 t0 = ld4(tp + pix * p.t_ld + g * 8), t1 = ld4(tp + pix * p.t_ld + g * 8 + 4);
+      const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += p.bn_a[g * 8 + j] * tv[j] + p.bn_b[g * 8 + j];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    T* dst = yp + pix * p.y_ld + g * 8;
+    st4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float v = rnd(acc[j], dst); cs[j] += v; cq[j] += v * v; }
+  }
+  if (p.stat) {
+    // lanes with equal (lane % groups) hold the same channels (groups is a power of two <= 32)
+    for (int o = groups; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
+        cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], o);
+      }
+    }
+    const int lane = threadIdx.x & 31;
+    if (lane < groups || groups > 32) {
+      const int g = groups > 32 ? (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % groups) : lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sm_s[g * 8 + j], cs[j]);
+        atomicAdd(&sm_s[p.Cout + g * 8 + j], cq[j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) atomicAdd(&p.stat[i], (double)sm_s[i]);
+  }
+}
+
+// dW(Cout,Cin,k,k) += sum_pixels x[p@tap, ci] * dy[p, co]  for tiny Cin (first layer): reads dy once.
+struct SmallCinWgradArgs {
+  const void* x; int x_ld; int Cin;
+  const void* dy; int dy_ld; int Cout;
+  int B, H, W, k, pad;
+  float* dw;
+};
+
+template <typename T, int KK>   // KK = taps*Cin accumulators per thread (x4 channels)
+__global__ void __launch_bounds__(256) wgrad_small_cin_kernel(const SmallCinWgradArgs p) {
+  __shared__ float red[256 * 4];
+  const int cg = p.Cout >> 2;                 // channel groups of 4
+  const int g = threadIdx.x % cg, lane_p = threadIdx.x / cg, rows = 256 / cg;
+  const int taps = p.k * p.k;
+  const long long P = (long long)p.B * p.H * p.W;
+  const T* xp = reinterpret_cast<const T*>(p.x);
+  const T* dyp = reinterpret_cast<const T*>(p.dy);
+  float acc[KK][4];
+#pragma unroll
+  for (int i = 0; i < KK; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  for (long long pix = (long long)blockIdx.x * rows + lane_p; pix < P; pix += (long long)gridDim.x * rows) {
+    const float4 d = ld4(dyp + pix * p.dy_ld + g * 4);
+    const int w = (int)(pix % p.W);
+    const long long r = pix / p.W;
+    const int h = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
+      const int ih = h + tap / p.k - p.pad, iw = w + tap % p.k - p.pad;
+      float xv = 0.f;
+      if (tap < taps && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+        xv = ld1(xp + ((long long)(n * p.H + ih) * p.W + iw) * p.x_ld + ci);
+      acc[kk][0] = fmaf(xv, d.x, acc[kk][0]); acc[kk][1] = fmaf(xv, d.y, acc[kk][1]);
+      acc[kk][2] = fmaf(xv, d.z, acc[kk][2]); acc[kk][3] = fmaf(xv, d.w, acc[kk][3]);
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk) {
+    __syncthreads();
+    red[threadIdx.x * 4 + 0] = acc[kk][0]; red[threadIdx.x * 4 + 1] = acc[kk][1];
+    red[threadIdx.x * 4 + 2] = acc[kk][2]; red[threadIdx.x * 4 + 3] = acc[kk][3];
+    __syncthreads();
+    const int tap = kk / p.Cin, ci = kk - tap * p.Cin;
+    if (threadIdx.x < p.Cout && tap < taps) {
+      const int co = threadIdx.x, gg = co >> 2, j = co & 3;
+      float s = 0.f;
+      for (int r = 0; r < rows; ++r) s += red[(r * cg + gg) * 4 + j];
+      atomicAdd(p.dw + ((long long)co * p.Cin + ci) * taps + tap, s);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Fused heads (unet.py:176-191): per pixel  logits = Wseg feat ; seg = softmax(logits) ;
+// heat = W2 (W1 [feat ; logits]).  One thread per pixel, weights in shared memory, one pass over the
+// feature map; seg / heat / (optional) logits are written as fp32 NCHW boundary tensors.
+// --------------------------------------------------------------------------
+template <typename T, int CF, int NC, int NF, int NL>
+__global__ void __launch_bounds__(128) heads_fwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
+                                                              const float* w2, T* logits_nhwc, T* mid_nhwc, int mid_ld,
+                                                              float* seg, float* logits_out, float* heat, int B,
+                                                              long long HW, int do_softmax) {
+  __shared__ float s_wseg[NC * CF];
+  __shared__ float s_w1[NF * (CF + NC)];
+  __shared__ float s_w2[NL * NF > 0 ? NL * NF : 1];
+  __shared__ float s_mid[NL > 0 ? NF * 128 : 1];
+  for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
+  if (NL > 0) {
+    for (int i = threadIdx.x; i < NF * (CF + NC); i += blockDim.x) s_w1[i] = w1[i];
+    for (int i = threadIdx.x; i < NL * NF; i += blockDim.x) s_w2[i] = w2[i];
+  }
+  __syncthreads();
+  const long long P = (long long)B * HW;
+  // one pixel per thread, no grid-stride loop: a loop would let the compiler hoist every
+  // (loop-invariant) shared-memory weight into registers (255 regs + spills, measured)
+  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pix < P) {
+    const long long n = pix / HW, hw = pix - n * HW;
+    float f[CF];
+#pragma unroll
+    for (int c = 0; c < CF; c += 4) {
+      const float4 v = ld4(feat + pix * ld + c);
+      f[c] = v.x; f[c + 1] = v.y; f[c + 2] = v.z; f[c + 3] = v.w;
+    }
+    float lg[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < CF; ++c) a = fmaf(s_wseg[k * CF + c], f[c], a);
+      lg[k] = a;
+    }
+    if (logits_nhwc) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) st1(logits_nhwc + pix * ld + k, lg[k]);
+    }
+    if (logits_out) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) logits_out[(n * NC + k) * HW + hw] = lg[k];
+    }
+    if (do_softmax) {
+      float mx = lg[0];
+#pragma unroll
+      for (int k = 1; k < NC; ++k) mx = fmaxf(mx, lg[k]);
+      float pr[NC], ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) { pr[k] = expf(lg[k] - mx); ssum += pr[k]; }
+      const float inv = 1.f / ssum;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) seg[(n * NC + k) * HW + hw] = pr[k] * inv;
+    } else {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) seg[(n * NC + k) * HW + hw] = lg[k];
+    }
+    if (NL > 0) {
+      // mid = W1 [feat ; logits] kept in shared memory (one column per thread) so the m / l loops can
+      // stay rolled: registers hold only the feature vector
+#pragma unroll 1
+      for (int m = 0; m < NF; ++m) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < CF; ++c) a = fmaf(s_w1[m * (CF + NC) + c], f[c], a);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a = fmaf(s_w1[m * (CF + NC) + CF + k], lg[k], a);
+        s_mid[m * 128 + threadIdx.x] = a;
+        if (mid_nhwc) st1(mid_nhwc + pix * mid_ld + m, a);
+      }
+#pragma unroll 1
+      for (int l = 0; l < NL; ++l) {
+        float a = 0.f;
+#pragma unroll
+        for (int m = 0; m < NF; ++m) a = fmaf(s_w2[l * NF + m], s_mid[m * 128 + threadIdx.x], a);
+        heat[(n * NL + l) * HW + hw] = a;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
 // Weight gradient: dW[tap][cb][cs] += sum_m BIG[pix(m)@tap, cb] * SMALL[m, cs]
 // (split over pixel ranges, fp32 atomics into a zeroed buffer, arbitrary output
 // strides so the result lands directly in the torch parameter layout).
