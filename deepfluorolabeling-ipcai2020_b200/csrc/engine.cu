@@ -731,7 +731,10 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
       } else {
         ConvW& cw = e->downc[l];
         if (tc_down_eligible(cw.tc, outv.p, outv.ld, dn.p, dn.ld)) {
-          if (tc_down_forward(cw.tc, outv.p, outv.ld, dn.p, dn.ld, B, h, w, tdata(e, cw.b_idx), e->stream, &e->cnt))
+          if (e->prof) e->prof_begin("tc_conv_kernel");
+          const int trc = tc_down_forward(cw.tc, outv.p, outv.ld, dn.p, dn.ld, B, h, w, tdata(e, cw.b_idx), e->stream, &e->cnt);
+          if (e->prof) e->prof_end();
+          if (trc)
             return e->fail(FU_ERR_CUDA, "tensor-core downsample launch failed: %s", tc_last_error());
         } else {
           ConvCall cc;
@@ -753,7 +756,10 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     View upv = slice(pl.cat[l], 0, e->chans[l], esz);
     e->set_tag(2.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_fwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
     if (tc_up_eligible(up.tc, cur.p, cur.ld, upv.p, upv.ld)) {
-      if (tc_up_forward(up.tc, cur.p, cur.ld, upv.p, upv.ld, B, h / 2, w / 2, tdata(e, up.b_idx), e->stream, &e->cnt))
+      if (e->prof) e->prof_begin("tc_conv_kernel");
+      const int trc = tc_up_forward(up.tc, cur.p, cur.ld, upv.p, upv.ld, B, h / 2, w / 2, tdata(e, up.b_idx), e->stream, &e->cnt);
+      if (e->prof) e->prof_end();
+      if (trc)
         return e->fail(FU_ERR_CUDA, "tensor-core upconv launch failed: %s", tc_last_error());
     } else {
       ConvCall cc;
@@ -977,6 +983,16 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     View d_u = (l == D - 2) ? pl.d_bott : pl.d_decout[l + 1];
     e->set_tag(4.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_bwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
     if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
+    if (tc_up_eligible(up.tc, u.p, u.ld, d_up.p, d_up.ld)) {
+      if (e->prof) e->prof_begin("tc_wgrad_kernel");
+      int trc = tc_up_wgrad(up.tc, u.p, u.ld, d_up.p, d_up.ld, B, h / 2, w / 2, gptr(e, flat, up.w_idx), e->stream, &e->cnt);
+      if (e->prof) { e->prof_end(); e->prof_begin("tc_conv_kernel"); }
+      if (!trc) trc = tc_up_dgrad(up.tc, d_up.p, d_up.ld, d_u.p, d_u.ld, B, h / 2, w / 2, e->stream, &e->cnt);
+      if (e->prof) e->prof_end();
+      if (trc) return e->fail(FU_ERR_CUDA, "tensor-core upconv backward failed: %s", tc_last_error());
+      g = d_u;
+      continue;
+    }
     {
       WgradCall wc;  // dW[ci][co][ab] = sum x[n,i,j,ci] * dY[n,2i+a,2j+b,co]
       wc.big = d_up; wc.Hb = h; wc.Wb = w; wc.small = u; wc.Hs = h / 2; wc.Ws = w / 2; wc.B = B;
@@ -1010,6 +1026,17 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
       } else {
         ConvW& cw = e->downc[l - 1];
         if ((rc = channel_sum_to<T>(e, pl.d_down[l], (long long)B * h * w, cw.bsum, gptr(e, flat, cw.b_idx)))) return rc;
+        if (tc_down_eligible(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld)) {
+          if (e->prof) e->prof_begin("tc_wgrad_kernel");
+          int trc = tc_down_wgrad(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld, B, 2 * h, 2 * w,
+                                  gptr(e, flat, cw.w_idx), e->stream, &e->cnt);
+          if (e->prof) { e->prof_end(); e->prof_begin("tc_conv_kernel"); }
+          if (!trc) trc = tc_down_dgrad(cw.tc, pl.d_down[l].p, pl.d_down[l].ld, d_src.p, d_src.ld, B, 2 * h, 2 * w, 1,
+                                        e->stream, &e->cnt);
+          if (e->prof) e->prof_end();
+          if (trc) return e->fail(FU_ERR_CUDA, "tensor-core downsample backward failed: %s", tc_last_error());
+          continue;
+        }
         WgradCall wc;  // dW[co][ci][ab] = sum x[n,2i+a,2j+b,ci] * dY[n,i,j,co]
         wc.big = src; wc.Hb = 2 * h; wc.Wb = 2 * w; wc.small = pl.d_down[l]; wc.Hs = h; wc.Ws = w; wc.B = B;
         wc.KH = 2; wc.stride = 2; wc.pad = 0;

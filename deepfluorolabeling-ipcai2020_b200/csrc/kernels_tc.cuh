@@ -81,6 +81,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -187,6 +198,11 @@ struct TcConvParams {
   const bf16* t; int t_ld;      // optional second operand of the epilogue, NHWC with pixel stride t_ld
   const float* bn_a; const float* bn_b;   // out += bn_a[c]*t + bn_b[c]   (null: out += t)
   double* stat;                 // optional [2N]: per-channel sum / sum of squares of the stored values
+  // 2x2/stride-2 variants (Conv2d(C,C,2,2) and ConvTranspose2d(.,.,2,2), unet.py:93,240): the pixel grid
+  // is (W, H = B*rows) with B = 1 (image rows merged; no padding so tiles may span images)
+  int a5;                       // A operand gathered with stride 2: 5-D map (C,2,W,2,H), tap = (kh,kw)
+  int c5;                       // output scattered (pixel shuffle): 5-D map (Cst,2,W,2,H), GEMM column = (a,b,co)
+  int Cst;                      // channels of the scattered output tensor (N = 4*Cst)
 };
 
 constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
@@ -261,7 +277,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
           ptx::mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
-          ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+          if (p.a5) ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kw, w0, kh, h0);
+          else ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw - p.pad, h0 + kh - p.pad, n0);
           ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), c0, tap, nb);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -327,7 +344,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int w0, h0, n0, nb;
       decode(tile, w0, h0, n0, nb);
       const bool valid = row < rows_in_tile && (w0 + wi) < p.W && (h0 + hi) < p.H && (n0 + ni) < p.B;
-      const long long pix = ((long long)(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
+      long long pix = ((long long)(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
+      int cb = nb;            // channel base of this N tile in the bias / t / output tensors
+      int sh_a = 0, sh_b = 0;
+      if (p.c5) {
+        const int ab = nb / p.Cst;
+        cb = nb - ab * p.Cst;
+        sh_a = ab >> 1; sh_b = ab & 1;
+        pix = ((long long)(h0 + hi) * 2 + sh_a) * (2 * p.W) + 2 * (w0 + wi) + sh_b;
+      }
       if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
@@ -336,7 +361,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
         ptx::tmem_ld_wait();
-        const int c0 = nb + j * 32;
+        const int c0 = cb + j * 32;
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -401,8 +426,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(1, 128);
       if (et == 0) {
-        for (int s = 0; s < p.BN / p.CS; ++s)
-          ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s * sub_bytes, nb + s * p.CS, w0, h0, n0);
+        for (int s = 0; s < p.BN / p.CS; ++s) {
+          if (p.c5) ptx::tma_store_5d(&tmC, staging_addr + (uint32_t)s * sub_bytes, cb + s * p.CS, sh_b, w0, sh_a, h0);
+          else ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s * sub_bytes, nb + s * p.CS, w0, h0, n0);
+        }
         ptx::tma_store_commit();
       }
       if (p.stat) {
@@ -453,6 +480,7 @@ struct TcWgradParams {
   int tiles_w, tiles_h, tiles_b;
   int co_tiles, ci_tiles, splits, stages;
   float* dw_acc;                // [taps][Cout][Cin] fp32, zeroed by the caller
+  int b5;                       // B operand gathered with stride 2 (5-D map), taps = 2x2, pixel grid (W, H), B = 1
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -517,10 +545,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         for (int blk = 0; blk < nblk_a; ++blk)
           ptx::tma_load_4d(a_dst + (uint32_t)blk * kBox, &tmY, full_bar(stage), co0 + blk * 64, w0, h0, n0);
         for (int t = 0; t < p.taps_per_cta; ++t) {
-          const int kh = p.ksz == 3 ? grp : 0, kw = p.ksz == 3 ? t : 0;
-          for (int blk = 0; blk < nblk_b; ++blk)
-            ptx::tma_load_4d(a_dst + a_bytes + (uint32_t)(t * nblk_b + blk) * kBox, &tmX, full_bar(stage),
-                             ci0 + blk * 64, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+          const int kh = p.ksz > 1 ? grp : 0, kw = p.ksz > 1 ? t : 0;
+          for (int blk = 0; blk < nblk_b; ++blk) {
+            const uint32_t dst = a_dst + a_bytes + (uint32_t)(t * nblk_b + blk) * kBox;
+            if (p.b5) ptx::tma_load_5d(dst, &tmX, full_bar(stage), ci0 + blk * 64, kw, w0, kh, h0);
+            else ptx::tma_load_4d(dst, &tmX, full_bar(stage), ci0 + blk * 64, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+          }
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
@@ -553,7 +583,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
     for (int t = 0; t < p.taps_per_cta; ++t) {
-      const int tap = p.ksz == 3 ? p.ksz * (blockIdx.x / p.splits % p.groups) + t : 0;
+      const int tap = p.ksz > 1 ? p.ksz * grp + t : 0;
       for (int j = 0; j < p.N / 32; ++j) {
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + (uint32_t)(t * p.N + j * 32) + ((uint32_t)(q * 32) << 16), v);
@@ -583,6 +613,27 @@ __global__ void tc_wgrad_unpack_kernel(const float* acc, float* dw, int Cout, in
     const int t = (int)(i % taps);
     const long long r = i / taps;   // co*Cin + ci
     dw[i] = acc[(long long)t * Cout * Cin + r];
+  }
+}
+
+// generic bf16 pack of a GEMM B matrix [N][T][K] from a torch-layout weight:
+//   dst[(n*T + t)*K + k] = src[tmap(t)*st + k*sk + (n / Ninner)*snh + (n % Ninner)*snl]
+struct TcPackArgs {
+  const float* src; bf16* dst;
+  int N, T, K, Ninner, flip;
+  long long st, sk, snh, snl;
+};
+__global__ void tc_pack_generic_kernel(const TcPackArgs p) {
+  const long long total = (long long)p.N * p.T * p.K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % p.K);
+    const long long r = i / p.K;
+    const int t = (int)(r % p.T);
+    const int n = (int)(r / p.T);
+    const int tm = p.flip ? (p.T - 1 - t) : t;
+    const int nh = n / p.Ninner, nl = n - nh * p.Ninner;
+    p.dst[i] = __float2bfloat16_rn(p.src[tm * p.st + k * p.sk + nh * p.snh + nl * p.snl]);
   }
 }
 
@@ -678,6 +729,7 @@ inline void tc_pick_tile(int B, int H, int W, int& tw, int& th, int& tn) {
 struct TcConv {
   bool enabled = false;
   int Cin = 0, Cout = 0, k = 0;
+  int kind = 0;              // 0: Conv2d 3x3/1x1 stride 1; 1: Conv2d 2x2 stride 2; 2: ConvTranspose2d 2x2 stride 2
   bf16* w_fwd = nullptr;     // [Cout][taps][Cin]
   bf16* w_dgrad = nullptr;   // [Cin][taps][Cout]
   float* dw_acc = nullptr;   // [taps][Cout][Cin] fp32 weight-gradient accumulator
@@ -687,7 +739,7 @@ struct TcConv {
   };
   std::vector<WCached> wcache;
   struct Cached {
-    const void *x, *y; int x_ld, y_ld, B, H, W, dir;
+    const void *x, *y; int x_ld, y_ld, B, H, W, dir;   // H, W: spatial dims of the GEMM's pixel grid
     CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem;
   };
   std::vector<Cached> cache;
@@ -705,8 +757,10 @@ inline int tc_bn_max() {
 
 inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool enabled, Bump& w, Bump& ws) {
   t.Cin = Cin; t.Cout = Cout; t.k = k;
-  t.enabled = enabled && !transposed && (k == 3 || k == 1) && (Cin % 32 == 0) && (Cout % 32 == 0) &&
+  t.kind = transposed ? 2 : (k == 2 ? 1 : 0);
+  t.enabled = enabled && (k == 3 || k == 1 || k == 2) && (Cin % 32 == 0) && (Cout % 32 == 0) &&
               getenv("FU_TC_DISABLE") == nullptr;
+  if (t.kind != 0 && getenv("FU_TC_NO_UPDOWN") != nullptr) t.enabled = false;
   if (!t.enabled) return;
   const size_t n = (size_t)Cin * Cout * k * k;
   t.w_fwd = w.take<bf16>(n);
@@ -721,8 +775,25 @@ inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* 
   const long long total = (long long)t.Cin * t.Cout * t.k * t.k;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  tc_pack_conv_kernel<<<(unsigned)g, 256, 0, stream>>>(w, t.w_fwd, t.w_dgrad, t.Cout, t.Cin, t.k * t.k);
-  if (cnt) cnt->kernel_launches++;
+  if (t.kind == 0) {
+    tc_pack_conv_kernel<<<(unsigned)g, 256, 0, stream>>>(w, t.w_fwd, t.w_dgrad, t.Cout, t.Cin, t.k * t.k);
+    if (cnt) cnt->kernel_launches++;
+  } else {
+    TcPackArgs f, d;
+    f.src = d.src = w; f.dst = t.w_fwd; d.dst = t.w_dgrad; f.flip = d.flip = 0;
+    if (t.kind == 1) {
+      // W[co][ci][ab].  fwd (gather conv): [N=Cout][T=4][K=Cin];  dgrad (scatter GEMM): [N=(ab,ci)][1][K=Cout]
+      f.N = t.Cout; f.T = 4; f.K = t.Cin; f.Ninner = t.Cout; f.st = 1; f.sk = 4; f.snh = 0; f.snl = (long long)t.Cin * 4;
+      d.N = 4 * t.Cin; d.T = 1; d.K = t.Cout; d.Ninner = t.Cin; d.st = 0; d.sk = (long long)t.Cin * 4; d.snh = 1; d.snl = 4;
+    } else {
+      // W[ci][co][ab].  fwd (scatter GEMM): [N=(ab,co)][1][K=Cin];  dgrad (gather conv over dY): [N=Cin][T=4][K=Cout]
+      f.N = 4 * t.Cout; f.T = 1; f.K = t.Cin; f.Ninner = t.Cout; f.st = 0; f.sk = (long long)t.Cout * 4; f.snh = 1; f.snl = 4;
+      d.N = t.Cin; d.T = 4; d.K = t.Cout; d.Ninner = t.Cin; d.st = 1; d.sk = 4; d.snh = 0; d.snl = (long long)t.Cout * 4;
+    }
+    tc_pack_generic_kernel<<<(unsigned)g, 256, 0, stream>>>(f);
+    tc_pack_generic_kernel<<<(unsigned)g, 256, 0, stream>>>(d);
+    if (cnt) cnt->kernel_launches += 2;
+  }
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -789,6 +860,77 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   return &t.cache.back();
 }
 
+// 5-D view of an NHWC tensor (B, 2*Hg, 2*Wg, C) as (C, 2, Wg, 2, B*Hg): element (c, b, j, a, r) is
+// pixel (row 2*(r % Hg) + a of image r / Hg, column 2j + b).  Rows of consecutive images are contiguous.
+inline int tc_make_s2_map(CUtensorMap* m, const void* base, int C, int ld, int Wg, long long Rg, int box_c, int tw, int th) {
+  long long dims[5] = {C, 2, Wg, 2, Rg};
+  long long str[5] = {1, ld, 2ll * ld, 2ll * Wg * ld, 4ll * Wg * ld};
+  int box[5] = {box_c, 1, tw, 1, th};
+  return tc_make_map(m, base, 5, dims, str, box, box_c * 2);
+}
+
+// Strided layers.  gather = 1: y(Wg,Rg) = sum over the 2x2 taps of x(2Wg,2Rg)  (Conv2d k2s2 forward, ConvT dgrad)
+//                  gather = 0: y(2Wg,2Rg) scattered from x(Wg,Rg)               (ConvT forward, Conv2d k2s2 dgrad)
+// (Wg, Hg) is the COARSE grid; Rg = B*Hg merged rows.  K / N are the GEMM depth / columns.
+inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16* wmat, int K, int N, int Cst,
+                                      const void* x, int x_ld, void* y, int y_ld, int B, int Hg, int Wg) {
+  for (auto& c : t.cache)
+    if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == Hg && c.W == Wg && c.dir == dir)
+      return &c;
+  TcConv::Cached c;
+  memset(&c, 0, sizeof(c));
+  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = Hg; c.W = Wg; c.dir = dir;
+  TcConvParams& p = c.p;
+  const long long Rg = (long long)B * Hg;
+  p.B = 1; p.H = (int)Rg; p.W = Wg; p.Cin = K; p.N = N;
+  p.ksz = gather ? 2 : 1; p.pad = 0;
+  p.a5 = gather ? 1 : 0; p.c5 = gather ? 0 : 1; p.Cst = Cst;
+  p.KC = (K % 64 == 0) ? 64 : 32;
+  int bn = tc_bn_max();
+  const int ncol = gather ? N : Cst;      // an N tile must not straddle two (a,b) blocks
+  while (ncol % bn) bn >>= 1;
+  p.BN = bn;
+  p.CS = bn >= 64 ? 64 : 32;
+  tc_pick_tile(1, (int)Rg, Wg, p.tw, p.th, p.tn);
+  p.tn = 1;
+  p.tiles_w = (Wg + p.tw - 1) / p.tw; p.tiles_h = (int)((Rg + p.th - 1) / p.th); p.tiles_b = 1;
+  p.n_tiles = N / p.BN;
+  const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
+  const size_t staging = (size_t)128 * p.BN * 2;
+  const size_t fixed = 1024 + staging + 8 * (2 * kTcMaxStages + 6);
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (stages > kTcMaxStages) stages = kTcMaxStages;
+  p.stages = stages;
+  c.smem = fixed + (size_t)stages * stage_bytes;
+  const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.n_tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  c.grid = (int)(total_tiles < sms ? total_tiles : sms);
+  if (gather) {
+    if (tc_make_s2_map(&c.a, x, K, x_ld, Wg, Rg, p.KC, p.tw, p.th)) return nullptr;
+    long long dims[4] = {N, Wg, Rg, 1};
+    long long str[4] = {1, y_ld, (long long)Wg * y_ld, Rg * Wg * y_ld};
+    int box[4] = {p.CS, p.tw, p.th, 1};
+    if (tc_make_map(&c.c, y, 4, dims, str, box, p.CS * 2)) return nullptr;
+  } else {
+    long long dims[4] = {K, Wg, Rg, 1};
+    long long str[4] = {1, x_ld, (long long)Wg * x_ld, Rg * Wg * x_ld};
+    int box[4] = {p.KC, p.tw, p.th, 1};
+    if (tc_make_map(&c.a, x, 4, dims, str, box, p.KC * 2)) return nullptr;
+    if (tc_make_s2_map(&c.c, y, Cst, y_ld, Wg, Rg, p.CS, p.tw, p.th)) return nullptr;
+  }
+  {
+    const int taps = gather ? 4 : 1;
+    long long dims[3] = {K, taps, N};
+    long long str[3] = {1, K, (long long)taps * K};
+    int box[3] = {p.KC, 1, p.BN};
+    if (tc_make_map(&c.b, wmat, 3, dims, str, box, p.KC * 2)) return nullptr;
+  }
+  t.cache.push_back(c);
+  return &t.cache.back();
+}
+
 inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -833,11 +975,46 @@ inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_
   return tc_launch(c, stream, cnt);
 }
 
-// not yet on tensor cores (CUDA-core kernels are used): 2x2/s2 down conv, 2x2/s2 transposed conv, weight gradient
-inline bool tc_down_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
-inline int tc_down_forward(TcConv&, const void*, int, void*, int, int, int, int, const float*, cudaStream_t, fu_counters*) { return -1; }
-inline bool tc_up_eligible(const TcConv&, const void*, int, const void*, int) { return false; }
-inline int tc_up_forward(TcConv&, const void*, int, void*, int, int, int, int, const float*, cudaStream_t, fu_counters*) { return -1; }
+// ---- Conv2d(C,C,2,stride 2) (unet.py:93) : x (B,H,W,Cin) -> y (B,H/2,W/2,Cout) ----
+inline bool tc_down_eligible(const TcConv& t, const void* x, int x_ld, const void* y, int y_ld) {
+  return t.enabled && t.kind == 1 && tc_ptr_ok(x, x_ld) && tc_ptr_ok(y, y_ld);
+}
+inline int tc_down_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, const float* bias,
+                           cudaStream_t stream, fu_counters* cnt) {
+  TcConv::Cached* c = tc_prepare_s2(t, 0, 1, t.w_fwd, t.Cin, t.Cout, 0, x, x_ld, y, y_ld, B, H / 2, W / 2);
+  if (!c) return -1;
+  c->p.bias = bias; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  return tc_launch(c, stream, cnt);
+}
+// dx (B,H,W,Cin) (+)= scatter of dy (B,H/2,W/2,Cout)
+inline int tc_down_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
+                         cudaStream_t stream, fu_counters* cnt) {
+  TcConv::Cached* c = tc_prepare_s2(t, 1, 0, t.w_dgrad, t.Cout, 4 * t.Cin, t.Cin, dy, dy_ld, dx, dx_ld, B, H / 2, W / 2);
+  if (!c) return -1;
+  c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  c->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c->p.t_ld = dx_ld;
+  return tc_launch(c, stream, cnt);
+}
+// ---- ConvTranspose2d(Cin,Cout,2,stride 2) (unet.py:240) : x (B,h,w,Cin) -> y (B,2h,2w,Cout) ----
+inline bool tc_up_eligible(const TcConv& t, const void* x, int x_ld, const void* y, int y_ld) {
+  return t.enabled && t.kind == 2 && tc_ptr_ok(x, x_ld) && tc_ptr_ok(y, y_ld);
+}
+inline int tc_up_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int h, int w, const float* bias,
+                         cudaStream_t stream, fu_counters* cnt) {
+  TcConv::Cached* c = tc_prepare_s2(t, 0, 0, t.w_fwd, t.Cin, 4 * t.Cout, t.Cout, x, x_ld, y, y_ld, B, h, w);
+  if (!c) return -1;
+  c->p.bias = bias; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  return tc_launch(c, stream, cnt);
+}
+// dx (B,h,w,Cin) = gather of dy (B,2h,2w,Cout)
+inline int tc_up_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int h, int w, cudaStream_t stream,
+                       fu_counters* cnt) {
+  TcConv::Cached* c = tc_prepare_s2(t, 1, 1, t.w_dgrad, t.Cout, t.Cin, 0, dy, dy_ld, dx, dx_ld, B, h, w);
+  if (!c) return -1;
+  c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  return tc_launch(c, stream, cnt);
+}
+
 inline bool tc_wgrad_eligible(const TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld) {
   return t.enabled && tc_ptr_ok(x, x_ld) && tc_ptr_ok(dy, dy_ld) && getenv("FU_TC_NO_WGRAD") == nullptr;
 }
@@ -854,23 +1031,30 @@ inline void tc_pick_tile64(int B, int H, int W, int& tw, int& th, int& tn) {
     }
 }
 
-// dw (torch layout, fp32) = weight gradient; t.dw_acc must have been zeroed since its last use.
-inline int tc_conv_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld, int B, int H, int W, float* dw,
-                         cudaStream_t stream, fu_counters* cnt) {
+// Common weight-gradient launcher.  `a` = operand read at the pixel itself (M channels -> accumulator rows),
+// `b` = operand read at the tap-shifted pixel (Nn channels -> accumulator columns).  s2 = 0: 3x3/1x1 taps on the
+// same (B,H,W) grid; s2 = 1: `b` lives on the 2x finer grid and the 2x2 taps select its sub-pixels.
+// Result: dw[(m*Nn + n)*taps + tap] (torch layouts (Cout,Cin,k,k) resp. ConvTranspose's (Cin,Cout,2,2)).
+// t.dw_acc must have been zeroed since its last use.
+inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void* b, int b_ld, int Nn, int s2, int ksz,
+                           int B, int H, int W, float* dw, cudaStream_t stream, fu_counters* cnt) {
   TcConv::WCached* c = nullptr;
   for (auto& k : t.wcache)
-    if (k.x == x && k.dy == dy && k.x_ld == x_ld && k.dy_ld == dy_ld && k.B == B && k.H == H && k.W == W) { c = &k; break; }
+    if (k.x == b && k.dy == a && k.x_ld == b_ld && k.dy_ld == a_ld && k.B == B && k.H == H && k.W == W) { c = &k; break; }
   if (!c) {
     TcConv::WCached n;
     memset(&n, 0, sizeof(n));
-    n.x = x; n.dy = dy; n.x_ld = x_ld; n.dy_ld = dy_ld; n.B = B; n.H = H; n.W = W;
+    n.x = b; n.dy = a; n.x_ld = b_ld; n.dy_ld = a_ld; n.B = B; n.H = H; n.W = W;
     TcWgradParams& p = n.p;
-    p.B = B; p.H = H; p.W = W; p.Cin = t.Cin; p.Cout = t.Cout; p.ksz = t.k; p.pad = t.k / 2;
-    p.taps_per_cta = t.k == 3 ? 3 : 1; p.groups = t.k == 3 ? 3 : 1;
-    p.N = t.Cin > 64 ? 128 : 64;
-    tc_pick_tile64(B, H, W, p.tw, p.th, p.tn);
-    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_b = (B + p.tn - 1) / p.tn;
-    p.co_tiles = (t.Cout + 127) / 128; p.ci_tiles = (t.Cin + p.N - 1) / p.N;
+    const long long Rg = (long long)B * H;
+    p.Cin = Nn; p.Cout = M; p.ksz = ksz; p.pad = ksz == 3 ? 1 : 0; p.b5 = s2;
+    p.taps_per_cta = ksz; p.groups = ksz;
+    p.N = Nn > 64 ? 128 : 64;
+    if (s2) { p.B = 1; p.H = (int)Rg; p.W = W; tc_pick_tile64(1, (int)Rg, W, p.tw, p.th, p.tn); p.tn = 1; }
+    else { p.B = B; p.H = H; p.W = W; tc_pick_tile64(B, H, W, p.tw, p.th, p.tn); }
+    if (s2 && p.tw * p.th != 64) { tc_err() = "strided wgrad: no 64-pixel tile"; return -1; }
+    p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_b = (p.B + p.tn - 1) / p.tn;
+    p.co_tiles = (M + 127) / 128; p.ci_tiles = (Nn + p.N - 1) / p.N;
     const size_t stage_bytes = (size_t)(2 + p.taps_per_cta * (p.N / 64)) * 8192;
     const size_t fixed = 1024 + 8 * (2 * kTcMaxStages + 4);
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
@@ -893,16 +1077,18 @@ inline int tc_conv_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int
     n.grid = (int)(units * splits);
     p.dw_acc = t.dw_acc;
     {
-      long long dims[4] = {t.Cout, W, H, B};
-      long long str[4] = {1, dy_ld, (long long)W * dy_ld, (long long)H * W * dy_ld};
+      long long dims[4] = {M, p.W, p.H, p.B};
+      long long str[4] = {1, a_ld, (long long)p.W * a_ld, (long long)p.H * p.W * a_ld};
       int box[4] = {64, p.tw, p.th, p.tn};
-      if (tc_make_map(&n.y, dy, 4, dims, str, box, 128)) return -1;
+      if (tc_make_map(&n.y, a, 4, dims, str, box, 128)) return -1;
     }
-    {
-      long long dims[4] = {t.Cin, W, H, B};
-      long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
+    if (s2) {
+      if (tc_make_s2_map(&n.xm, b, Nn, b_ld, W, Rg, 64, p.tw, p.th)) return -1;
+    } else {
+      long long dims[4] = {Nn, W, H, B};
+      long long str[4] = {1, b_ld, (long long)W * b_ld, (long long)H * W * b_ld};
       int box[4] = {64, p.tw, p.th, p.tn};
-      if (tc_make_map(&n.xm, x, 4, dims, str, box, 128)) return -1;
+      if (tc_make_map(&n.xm, b, 4, dims, str, box, 128)) return -1;
     }
     t.wcache.push_back(n);
     c = &t.wcache.back();
@@ -916,42 +1102,71 @@ inline int tc_conv_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int
     attr_set = true;
   }
   tc_wgrad_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
-  const long long total = (long long)t.Cin * t.Cout * t.k * t.k;
+  const int taps = ksz * ksz;
+  const long long total = (long long)M * Nn * taps;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  tc_wgrad_unpack_kernel<<<(unsigned)g, 256, 0, stream>>>(t.dw_acc, dw, t.Cout, t.Cin, t.k * t.k);
+  tc_wgrad_unpack_kernel<<<(unsigned)g, 256, 0, stream>>>(t.dw_acc, dw, M, Nn, taps);
   if (cnt) { cnt->kernel_launches += 2; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
   return 0;
 }
 
+// Conv2d 3x3 / 1x1: x, dy on the same (B,H,W) grid
+inline int tc_conv_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld, int B, int H, int W, float* dw,
+                         cudaStream_t stream, fu_counters* cnt) {
+  return tc_wgrad_common(t, dy, dy_ld, t.Cout, x, x_ld, t.Cin, 0, t.k, B, H, W, dw, stream, cnt);
+}
+// Conv2d 2x2/s2: x (B,H,W,Cin) fine, dy (B,H/2,W/2,Cout) coarse -> dw (Cout,Cin,2,2)
+inline int tc_down_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld, int B, int H, int W, float* dw,
+                         cudaStream_t stream, fu_counters* cnt) {
+  return tc_wgrad_common(t, dy, dy_ld, t.Cout, x, x_ld, t.Cin, 1, 2, B, H / 2, W / 2, dw, stream, cnt);
+}
+// ConvTranspose2d 2x2/s2: x (B,h,w,Cin) coarse, dy (B,2h,2w,Cout) fine -> dw (Cin,Cout,2,2)
+inline int tc_up_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld, int B, int h, int w, float* dw,
+                       cudaStream_t stream, fu_counters* cnt) {
+  return tc_wgrad_common(t, x, x_ld, t.Cin, dy, dy_ld, t.Cout, 1, 2, B, h, w, dw, stream, cnt);
+}
+
 // kernel-level test hook (fu_test_conv, impl = 1): bf16 NHWC tensors, fp32 torch-layout weights
 inline int tc_test_conv(int mode, int B, int H, int W, int Cin, int Cout, int k, int stride, int pad, int relu,
                         const void* x, const float* w, const float* bias, void* y_or_dx, const void* dy, float* dw,
                         double* stats, cudaStream_t stream, fu_counters* cnt) {
-  if (stride != 1 || pad != k / 2 || (k != 1 && k != 3)) { tc_err() = "tc_test_conv: only 3x3/pad1 and 1x1, stride 1"; return -1; }
+  // k=3/1, stride 1: Conv2d.  k=2, stride 2: Conv2d(Cin,Cout,2,2) on x (B,H,W,Cin).  k=2, stride -2:
+  // ConvTranspose2d(Cin,Cout,2,2) on x (B,H,W,Cin) -> (B,2H,2W,Cout), w in its (Cin,Cout,2,2) layout.
+  const bool plain = (k == 1 || k == 3) && stride == 1 && pad == k / 2;
+  const bool down = k == 2 && stride == 2 && pad == 0;
+  const bool up = k == 2 && stride == -2 && pad == 0;
+  if (!plain && !down && !up) { tc_err() = "tc_test_conv: unsupported geometry"; return -1; }
   TcConv t;
   char *mem = nullptr, *mem2 = nullptr;
   Bump dry, dry2;
-  tc_carve(t, Cin, Cout, k, false, true, dry, dry2);
+  tc_carve(t, Cin, Cout, k, up, true, dry, dry2);
   if (!t.enabled) { tc_err() = "tc_test_conv: shape not eligible (channels must be multiples of 32)"; return -1; }
   if (cudaMalloc(&mem, dry.off + 256) != cudaSuccess || cudaMalloc(&mem2, dry2.off + 256) != cudaSuccess) {
     tc_err() = "cudaMalloc failed";
     return -1;
   }
   Bump real, real2; real.base = mem; real2.base = mem2;
-  tc_carve(t, Cin, Cout, k, false, true, real, real2);
+  tc_carve(t, Cin, Cout, k, up, true, real, real2);
   int rc = 0;
   if (mode == 2) {
     cudaMemsetAsync(mem2, 0, dry2.off + 256, stream);
-    rc = tc_conv_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
+    if (plain) rc = tc_conv_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
+    else if (down) rc = tc_down_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
+    else rc = tc_up_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
   } else {
     rc = tc_pack(t, w, stream, cnt);
-  }
-  if (!rc && mode != 2) {
-    if (mode == 0) rc = tc_conv_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, relu, stats, nullptr, 0, nullptr, nullptr, 0, stream, cnt);
-    else rc = tc_conv_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, 0, stream, cnt);
+    if (!rc && mode == 0) {
+      if (plain) rc = tc_conv_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, relu, stats, nullptr, 0, nullptr, nullptr, 0, stream, cnt);
+      else if (down) rc = tc_down_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, stream, cnt);
+      else rc = tc_up_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, stream, cnt);
+    } else if (!rc) {
+      if (plain) rc = tc_conv_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, 0, stream, cnt);
+      else if (down) rc = tc_down_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, 0, stream, cnt);
+      else rc = tc_up_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, stream, cnt);
+    }
   }
   cudaError_t e = cudaStreamSynchronize(stream);
   cudaFree(mem);

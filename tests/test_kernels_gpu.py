@@ -130,3 +130,64 @@ def test_tc_conv_fwd_dgrad(pkg, shape):
     dw = run_conv(pkg, 1, 1, 2, x, w, None, dy, k, 1, pad)
     dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=pad)
     assert rel_l2(dw, dw_ref) < 1e-4, rel_l2(dw, dw_ref)
+
+
+def _nhwc(t, dt, dev):
+    return t.permute(0, 2, 3, 1).contiguous().to(dev, dt)
+
+
+S2_SHAPES = [  # B, Cin, Cout, H, W  (H, W = spatial size of the layer INPUT)
+    (2, 64, 64, 16, 16),
+    (3, 32, 32, 8, 24),
+    (2, 128, 128, 12, 12),
+    (5, 256, 256, 6, 6),
+    (1, 64, 32, 10, 6),
+]
+
+
+@pytest.mark.parametrize("shape", S2_SHAPES)
+def test_tc_down_conv_2x2_s2(pkg, shape):
+    """Conv2d(C,C,2,stride 2) (unet.py:93): strided-gather forward, scatter data gradient, weight gradient."""
+    B, Cin, Cout, H, W = shape
+    L, dev = pkg._capi.lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, 2, 2, generator=g) / (Cin * 4) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, H // 2, W // 2, generator=g).bfloat16().float()
+    xg, wg, bg, dyg = _nhwc(x, torch.bfloat16, dev), w.to(dev), b.to(dev), _nhwc(dy, torch.bfloat16, dev)
+    y = torch.empty(B, H // 2, W // 2, Cout, device=dev, dtype=torch.bfloat16)
+    dx = torch.empty(B, H, W, Cin, device=dev, dtype=torch.bfloat16)
+    dw = torch.empty_like(wg)
+    for mode, out in ((0, y), (1, dx), (2, None)):
+        rc = L.fu_test_conv(1, 1, mode, B, H, W, Cin, Cout, 2, 2, 0, 0, _p(xg), _p(wg), _p(bg), _p(out), _p(dyg), _p(dw), None, None)
+        assert rc == 0, pkg._capi.last_error(None)
+    torch.cuda.synchronize()
+    assert rel_l2(y.float().cpu().permute(0, 3, 1, 2), F.conv2d(x, w, b, stride=2)) < 6e-3
+    assert rel_l2(dx.float().cpu().permute(0, 3, 1, 2), torch.nn.grad.conv2d_input(x.shape, w, dy, stride=2)) < 6e-3
+    assert rel_l2(dw.cpu(), torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2)) < 1e-4
+
+
+@pytest.mark.parametrize("shape", S2_SHAPES)
+def test_tc_up_conv_transpose_2x2_s2(pkg, shape):
+    """ConvTranspose2d(Cin,Cout,2,stride 2) (unet.py:240): scatter forward, gather data gradient, weight gradient."""
+    B, Cin, Cout, H, W = shape
+    L, dev = pkg._capi.lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Cin, Cout, 2, 2, generator=g) / Cin ** 0.5).bfloat16().float().requires_grad_(True)
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, 2 * H, 2 * W, generator=g).bfloat16().float()
+    y_ref = F.conv_transpose2d(x, w, b, stride=2)
+    y_ref.backward(dy)
+    xg, wg, bg, dyg = _nhwc(x.detach(), torch.bfloat16, dev), w.detach().to(dev), b.to(dev), _nhwc(dy, torch.bfloat16, dev)
+    y = torch.empty(B, 2 * H, 2 * W, Cout, device=dev, dtype=torch.bfloat16)
+    dx = torch.empty(B, H, W, Cin, device=dev, dtype=torch.bfloat16)
+    dw = torch.empty_like(wg)
+    for mode, out in ((0, y), (1, dx), (2, None)):
+        rc = L.fu_test_conv(1, 1, mode, B, H, W, Cin, Cout, 2, -2, 0, 0, _p(xg), _p(wg), _p(bg), _p(out), _p(dyg), _p(dw), None, None)
+        assert rc == 0, pkg._capi.last_error(None)
+    torch.cuda.synchronize()
+    assert rel_l2(y.float().cpu().permute(0, 3, 1, 2), y_ref.detach()) < 6e-3
+    assert rel_l2(dx.float().cpu().permute(0, 3, 1, 2), x.grad) < 6e-3
+    assert rel_l2(dw.cpu(), w.grad) < 1e-4
