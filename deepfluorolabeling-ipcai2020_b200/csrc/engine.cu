@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -98,6 +99,7 @@ struct fu_engine {
   double* dscr_bwd = nullptr; size_t dscr_bwd_bytes = 0;
   char* wgrad_scr = nullptr; size_t wgrad_scr_bytes = 0;   // tensor-core weight-gradient accumulators
   float *ones = nullptr, *zeros = nullptr;
+  float* heads_gacc = nullptr;   // [NL*(CF+NC) + NC*CF] accumulators of the fused heads backward
   int64_t packed_version = -1;
   bool packed_once = false;
   Plan plan;
@@ -336,6 +338,7 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
   });
   e->ones = w.take<float>(maxc);
   e->zeros = w.take<float>(maxc);
+  e->heads_gacc = w.take<float>((size_t)(e->cfg.num_lands + e->cfg.n_classes) * (e->Cf + e->cfg.n_classes) + 64);
 }
 
 int alloc_persistent(fu_engine* e) {
@@ -949,6 +952,26 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   View lg = slice(pl.hcat, e->Cf, c.n_classes, esz);
   View d_feat = slice(pl.d_hcat, 0, e->Cf, esz);
   View d_lg = slice(pl.d_hcat, e->Cf, c.n_classes, esz);
+  const bool fused_heads = e->Cf == 32 && c.n_classes == 7 &&
+                           (c.num_lands == 0 || (c.num_lands == 14 && e->lands.size() == 2 && e->lands[0].Cout == 21));
+  if (fused_heads) {
+    const size_t gbytes = ((size_t)(c.num_lands + c.n_classes) * (e->Cf + c.n_classes) + 64) * sizeof(float);
+    CUDA_TRY(e, cudaMemsetAsync(e->heads_gacc, 0, gbytes, e->stream));
+    const unsigned gridh = (unsigned)std::min<long long>((P0 + 127) / 128, (long long)e->num_sms * 4);
+    if (c.num_lands == 14) {
+      LAUNCH(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, reinterpret_cast<const T*>(feat.p), feat.ld,
+             tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,
+             reinterpret_cast<T*>(d_feat.p), d_feat.ld, e->heads_gacc, B, HW, c.do_soft_max);
+      LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
+             gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
+    } else {
+      LAUNCH(e, (heads_bwd_fused_kernel<T, 32, 7, 1, 0>), gridh, 128, reinterpret_cast<const T*>(feat.p), feat.ld,
+             tdata(e, e->seg.w_idx), (const float*)nullptr, (const float*)nullptr, d_seg, (const float*)nullptr,
+             reinterpret_cast<T*>(d_feat.p), d_feat.ld, e->heads_gacc, B, HW, c.do_soft_max);
+      LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
+             gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0);
+    }
+  } else {
   if (c.num_lands > 0 && d_heat) {
     LAUNCH(e, (nchw_to_nhwc_kernel<T>), grid1d(P0, 256, e->num_sms), 256, d_heat, reinterpret_cast<T*>(pl.dheat.p),
            pl.dheat.ld, B, c.num_lands, HW);
@@ -970,6 +993,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   }
   if ((rc = conv_wgrad<T>(e, e->seg, feat, d_lg, B, H, W, gptr(e, flat, e->seg.w_idx)))) return rc;
   if ((rc = conv_dgrad<T>(e, e->seg, d_lg, d_feat, B, H, W, 1))) return rc;
+  }
 
   // ---- decoder ----
   View g = d_feat;

@@ -467,6 +467,195 @@ __global__ void __launch_bounds__(128) heads_fwd_fused_kernel(const T* feat, int
   }
 }
 
+// Fused heads backward.  Per pixel (one thread each): recompute logits/softmax from the features,
+//   dmid = W2^T dheat ; dcat = W1^T dmid ; dlg = dcat[CF:] + softmax'(dseg) ; dfeat = dcat[:CF] + Wseg^T dlg.
+// Weight gradients: with cat = [feat ; logits] and mid = W1 cat,
+//   dW2 = sum dheat (x) mid = G1 W1^T ,  dW1 = sum dmid (x) cat = W2^T G1 ,  G1 = sum_pixels dheat (x) cat  (NL x (CF+NC))
+//   dWseg = Gseg = sum_pixels dlg (x) feat  (NC x CF)
+// so only G1 and Gseg (770 numbers for the paper heads) are reduced over pixels: per 128-pixel chunk the
+// per-pixel vectors go through shared memory and register-tiled outer products accumulate them; blocks are
+// persistent and add their partial G's to global memory once.  heads_bwd_finalize_kernel forms dW1, dW2.
+template <typename T, int CF, int NC, int NF, int NL>
+__global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
+                                                              const float* w2, const float* d_seg, const float* d_heat,
+                                                              T* d_feat, int d_ld, float* g_acc /*[NL*(CF+NC) + NC*CF]*/,
+                                                              int B, long long HW, int do_softmax) {
+  constexpr int NCAT = CF + NC;
+  constexpr int NLp = NL > 0 ? NL : 1;
+  constexpr int ROWS = NLp + NCAT + NC;          // dheat rows, cat rows, dlg rows
+  constexpr int TA = 2, TB = 3;                  // G1 register tile
+  constexpr int NTA = (NLp + TA - 1) / TA, NTB = (NCAT + TB - 1) / TB;
+  static_assert(NTA * NTB + CF <= 128, "outer-product tiles must fit one block");
+  __shared__ float s_wseg[NC * CF];
+  __shared__ float s_w1[NL > 0 ? NF * NCAT : 1];
+  __shared__ float s_w2[NL > 0 ? NL * NF : 1];
+  __shared__ __align__(16) float s_v[ROWS * 128];   // per-pixel vectors, one column per pixel
+  for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
+  if (NL > 0) {
+    for (int i = threadIdx.x; i < NF * NCAT; i += blockDim.x) s_w1[i] = w1[i];
+    for (int i = threadIdx.x; i < NL * NF; i += blockDim.x) s_w2[i] = w2[i];
+  }
+  const int tid = threadIdx.x;
+  // outer-product ownership
+  const bool own_g1 = NL > 0 && tid < NTA * NTB;
+  const int ta = own_g1 ? (tid / NTB) * TA : 0, tb = own_g1 ? (tid % NTB) * TB : 0;
+  const bool own_gs = tid >= 128 - CF;            // last CF threads: one feature column each, all NC rows
+  const int gs_c = tid - (128 - CF);
+  float g1[TA][TB], gs[NC];
+#pragma unroll
+  for (int i = 0; i < TA; ++i)
+#pragma unroll
+    for (int j = 0; j < TB; ++j) g1[i][j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) gs[k] = 0.f;
+  const long long P = (long long)B * HW;
+  const long long nchunks = (P + 127) / 128;
+  for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    __syncthreads();                              // previous chunk's outer products are done with s_v
+    const long long pix = chunk * 128 + tid;
+    float* col = s_v + tid;                       // row r of this pixel at col[r*128]
+    // z == 0, but opaque to the compiler: keeps it from hoisting all (loop-invariant) shared-memory
+    // weights out of the chunk loop into registers (255 registers + spills otherwise, measured)
+    const int z = (int)((unsigned long long)chunk >> 44);
+    const float* q_wseg = s_wseg + z;
+    const float* q_w1 = s_w1 + z;
+    const float* q_w2 = s_w2 + z;
+    if (pix < P) {
+      const long long n = pix / HW, hw = pix - n * HW;
+      float f[CF];
+#pragma unroll
+      for (int c = 0; c < CF; c += 4) {
+        const float4 v = ld4(feat + pix * ld + c);
+        f[c] = v.x; f[c + 1] = v.y; f[c + 2] = v.z; f[c + 3] = v.w;
+      }
+      float lg[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < CF; ++c) a = fmaf(q_wseg[k * CF + c], f[c], a);
+        lg[k] = a;
+      }
+#pragma unroll
+      for (int c = 0; c < CF; ++c) col[(NLp + c) * 128] = f[c];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) col[(NLp + CF + k) * 128] = lg[k];
+      // dL/dlogits from the segmentation output
+      float dlg[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) dlg[k] = d_seg ? d_seg[(n * NC + k) * HW + hw] : 0.f;
+      if (do_softmax && d_seg) {
+        float mx = lg[0];
+#pragma unroll
+        for (int k = 1; k < NC; ++k) mx = fmaxf(mx, lg[k]);
+        float pr[NC], ssum = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) { pr[k] = expf(lg[k] - mx); ssum += pr[k]; }
+        const float inv = 1.f / ssum;
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) { pr[k] *= inv; dot = fmaf(pr[k], dlg[k], dot); }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) dlg[k] = pr[k] * (dlg[k] - dot);
+      }
+      float df[CF];
+#pragma unroll
+      for (int c = 0; c < CF; ++c) df[c] = 0.f;
+      if (NL > 0) {
+        // dheat -> smem rows [0, NL); dmid[m] = sum_l W2[l][m] dheat[l]; dcat += W1[m][:] * dmid[m]
+#pragma unroll 1
+        for (int l = 0; l < NL; ++l) col[l * 128] = d_heat ? d_heat[(n * NL + l) * HW + hw] : 0.f;
+#pragma unroll 1
+        for (int m = 0; m < NF; ++m) {
+          float dm = 0.f;
+#pragma unroll
+          for (int l = 0; l < NL; ++l) dm = fmaf(q_w2[l * NF + m], col[l * 128], dm);
+#pragma unroll
+          for (int c = 0; c < CF; ++c) df[c] = fmaf(q_w1[m * NCAT + c], dm, df[c]);
+#pragma unroll
+          for (int k = 0; k < NC; ++k) dlg[k] = fmaf(q_w1[m * NCAT + CF + k], dm, dlg[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        col[(NLp + NCAT + k) * 128] = dlg[k];
+#pragma unroll
+        for (int c = 0; c < CF; ++c) df[c] = fmaf(q_wseg[k * CF + c], dlg[k], df[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < CF; c += 4) st4(d_feat + pix * d_ld + c, make_float4(df[c], df[c + 1], df[c + 2], df[c + 3]));
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < ROWS; ++r) col[r * 128] = 0.f;
+    }
+    __syncthreads();
+    // outer products over the chunk's 128 pixels (float4 along the pixel axis)
+    if (own_g1) {
+#pragma unroll 2
+      for (int p4 = 0; p4 < 32; ++p4) {
+        const int px = ((p4 + tid) & 31) * 4;     // staggered start: fewer bank conflicts between tiles
+        float4 a[TA], b[TB];
+#pragma unroll
+        for (int i = 0; i < TA; ++i) a[i] = (ta + i < NL) ? *reinterpret_cast<const float4*>(s_v + (ta + i) * 128 + px) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < TB; ++j) b[j] = (tb + j < NCAT) ? *reinterpret_cast<const float4*>(s_v + (NLp + tb + j) * 128 + px) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < TA; ++i)
+#pragma unroll
+          for (int j = 0; j < TB; ++j)
+            g1[i][j] += a[i].x * b[j].x + a[i].y * b[j].y + a[i].z * b[j].z + a[i].w * b[j].w;
+      }
+    }
+    if (own_gs) {
+#pragma unroll 1
+      for (int p4 = 0; p4 < 32; ++p4) {
+        const int px = ((p4 + tid) & 31) * 4;
+        const float4 fv = *reinterpret_cast<const float4*>(s_v + (NLp + gs_c) * 128 + px);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const float4 dv = *reinterpret_cast<const float4*>(s_v + (NLp + NCAT + k) * 128 + px);
+          gs[k] += dv.x * fv.x + dv.y * fv.y + dv.z * fv.z + dv.w * fv.w;
+        }
+      }
+    }
+  }
+  if (own_g1) {
+#pragma unroll
+    for (int i = 0; i < TA; ++i)
+#pragma unroll
+      for (int j = 0; j < TB; ++j)
+        if (ta + i < NL && tb + j < NCAT) atomicAdd(g_acc + (ta + i) * NCAT + tb + j, g1[i][j]);
+  }
+  if (own_gs) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) atomicAdd(g_acc + NLp * NCAT * (NL > 0 ? 1 : 0) + k * CF + gs_c, gs[k]);
+  }
+}
+
+// dW2 = G1 W1^T, dW1 = W2^T G1, dWseg = Gseg  (G's accumulated by heads_bwd_fused_kernel)
+__global__ void heads_bwd_finalize_kernel(const float* g_acc, const float* w1, const float* w2, float* dwseg, float* dw1,
+                                          float* dw2, int CF, int NC, int NF, int NL) {
+  const int NCAT = CF + NC;
+  const float* g1 = g_acc;
+  const float* gs = g_acc + (NL > 0 ? NL * NCAT : 0);
+  const int n_seg = NC * CF, n_w1 = NL > 0 ? NF * NCAT : 0, n_w2 = NL > 0 ? NL * NF : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_seg + n_w1 + n_w2; i += gridDim.x * blockDim.x) {
+    if (i < n_seg) {
+      dwseg[i] = gs[i];
+    } else if (i < n_seg + n_w1) {
+      const int j = i - n_seg, m = j / NCAT, c = j - m * NCAT;
+      float a = 0.f;
+      for (int l = 0; l < NL; ++l) a = fmaf(w2[l * NF + m], g1[l * NCAT + c], a);
+      dw1[j] = a;
+    } else {
+      const int j = i - n_seg - n_w1, l = j / NF, m = j - l * NF;
+      float a = 0.f;
+      for (int c = 0; c < NCAT; ++c) a = fmaf(g1[l * NCAT + c], w1[m * NCAT + c], a);
+      dw2[j] = a;
+    }
+  }
+}
+
 // --------------------------------------------------------------------------
 // Weight gradient: dW[tap][cb][cs] += sum_m BIG[pix(m)@tap, cb] * SMALL[m, cs]
 // (split over pixel ranges, fp32 atomics into a zeroed buffer, arbitrary output
