@@ -466,6 +466,344 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ===========================================================================
+// 3x3 convolution, second generation ("halo" kernel): forward and data gradient at levels whose width is
+// >= 24.  v1 above re-loads the input tile for each of the 9 taps and the weights for each pixel tile and is
+// bound by L2->SM traffic (profiles/r01_*).  Here
+//  * the input of a tile is loaded ONCE per 64-channel chunk as a halo box (twb x (th+2) pixels, twb = two+2)
+//    whose rows are the flattened padded-width pixel grid; tap (kh,kw) is the same shared-memory tile read
+//    through an MMA descriptor whose start address is advanced by kh*twb + kw rows (the swizzle is a
+//    function of the absolute shared-memory address, so a row-shifted view stays consistent).  The two
+//    padded columns of every row produce garbage accumulator rows that are never stored;
+//  * two pixel tiles share every weight tile (2 accumulators per TMEM stage);
+//  * for thin layers (all taps fit in shared memory) the weights are loaded once per CTA and stay resident.
+// ===========================================================================
+struct TcConv3Params {
+  int B, H, W, K, N;
+  int KC, BN, CS;
+  int twb, two, th;             // box width, valid output width (twb-2), tile height; twb*th <= 128
+  int tiles_w, tiles_h, n_tiles;
+  int halo1;                    // 1: one halo load per chunk (kw by row shift); 0: one load per (chunk, kw)
+  int npair;                    // pixel tiles per weight tile (1 or 2)
+  int resident;                 // weights resident in shared memory (n_tiles == 1)
+  int a_stages, b_stages;
+  unsigned a_tile_bytes;        // one halo tile, rounded up to 1024 B
+  int relu;
+  const float* bias;
+  const bf16* t; int t_ld;
+  const float* bn_a; const float* bn_b;
+  double* stat;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const TcConv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)p.KC * 2u;
+  const uint32_t b_bytes = (uint32_t)p.BN * row_bytes;
+  const int cchunks = p.K / p.KC;
+  const uint32_t a_stage_bytes = (uint32_t)p.npair * p.a_tile_bytes;
+  const uint32_t a_off = 0;
+  const uint32_t b_off = a_off + (uint32_t)p.a_stages * a_stage_bytes;
+  const uint32_t b_region = p.resident ? (uint32_t)(cchunks * 9) * b_bytes : (uint32_t)p.b_stages * b_bytes;
+  const uint32_t staging_off = b_off + b_region;
+  const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;
+  const uint32_t stat_off = staging_off + staging_bytes;          // [4 warps][2][BN] floats
+  const uint32_t bar_off = stat_off + 4u * 2u * (uint32_t)p.BN * 4u;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(8 + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(16 + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(24 + s); };
+  auto t_full = [&](int a) { return bar_base + 8u * (uint32_t)(32 + a); };
+  auto t_empty = [&](int a) { return bar_base + 8u * (uint32_t)(34 + a); };
+  const uint32_t res_bar = bar_base + 8u * 36u;
+  const uint32_t slot_addr = bar_base + 8u * 37u;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * 37u);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)(p.npair * p.BN)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) {
+      ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1);
+      ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(t_full(a), 1); ptx::mbar_init(t_empty(a), 128); }
+    ptx::mbar_init(res_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
+  }
+  if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  const int tiles_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = tiles_img * p.B;
+  const int supers_m = (m_tiles + p.npair - 1) / p.npair;
+  const int total_super = supers_m * p.n_tiles;
+  const int groups = p.halo1 ? 1 : 3;          // A loads per chunk
+  const int taps_per_group = p.halo1 ? 9 : 3;
+  const uint32_t box_bytes = (uint32_t)(p.twb * (p.th + 2)) * row_bytes;
+
+  auto decode_m = [&](int mt, int& w0, int& h0, int& n) {
+    n = mt / tiles_img;
+    const int r = mt - n * tiles_img;
+    h0 = (r / p.tiles_w) * p.th;
+    w0 = (r % p.tiles_w) * p.two;
+  };
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      if (p.resident) {
+        ptx::mbar_expect_tx(res_bar, (uint32_t)(cchunks * 9) * b_bytes);
+        for (int c = 0; c < cchunks; ++c)
+          for (int tap = 0; tap < 9; ++tap)
+            ptx::tma_load_3d(smem_base + b_off + (uint32_t)(c * 9 + tap) * b_bytes, &tmB, res_bar, c * p.KC, tap, 0);
+      }
+      int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+      for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
+        const int nt = st % p.n_tiles, sp = st / p.n_tiles;
+        const int nb = nt * p.BN;
+        for (int c = 0; c < cchunks; ++c) {
+          for (int g = 0; g < groups; ++g) {
+            ptx::mbar_wait(a_empty(as), aph ^ 1u);
+            int nvalid = 0;
+            for (int i = 0; i < p.npair; ++i) nvalid += (sp * p.npair + i) < m_tiles ? 1 : 0;
+            ptx::mbar_expect_tx(a_full(as), (uint32_t)nvalid * box_bytes);
+            for (int i = 0; i < p.npair; ++i) {
+              const int mt = sp * p.npair + i;
+              if (mt >= m_tiles) break;
+              int w0, h0, n;
+              decode_m(mt, w0, h0, n);
+              ptx::tma_load_4d(smem_base + a_off + (uint32_t)as * a_stage_bytes + (uint32_t)i * p.a_tile_bytes, &tmA,
+                               a_full(as), c * p.KC, w0 - 1 + (p.halo1 ? 0 : g), h0 - 1, n);
+            }
+            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+            if (!p.resident) {
+              for (int tt = 0; tt < taps_per_group; ++tt) {
+                const int tap = p.halo1 ? tt : tt * 3 + g;      // (kh = tt, kw = g) when one load per kw
+                ptx::mbar_wait(b_empty(bs), bph ^ 1u);
+                ptx::mbar_expect_tx(b_full(bs), b_bytes);
+                ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB, b_full(bs), c * p.KC, tap, nb);
+                if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
+      const int ksteps = p.KC / 16;
+      if (p.resident) { ptx::mbar_wait(res_bar, 0); ptx::tc_fence_after(); }
+      for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
+        const int sp = st / p.n_tiles;
+        ptx::mbar_wait(t_empty(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        bool first = true;
+        for (int c = 0; c < cchunks; ++c) {
+          for (int g = 0; g < groups; ++g) {
+            ptx::mbar_wait(a_full(as), aph);
+            ptx::tc_fence_after();
+            const uint32_t a_base = smem_base + a_off + (uint32_t)as * a_stage_bytes;
+            for (int tt = 0; tt < taps_per_group; ++tt) {
+              const int tap = p.halo1 ? tt : tt * 3 + g;
+              const int kh = tap / 3, kw = tap - kh * 3;
+              uint32_t b_addr;
+              if (p.resident) {
+                b_addr = smem_base + b_off + (uint32_t)(c * 9 + tap) * b_bytes;
+              } else {
+                ptx::mbar_wait(b_full(bs), bph);
+                ptx::tc_fence_after();
+                b_addr = smem_base + b_off + (uint32_t)bs * b_bytes;
+              }
+              const uint32_t rowoff = (uint32_t)(kh * p.twb + (p.halo1 ? kw : 0)) * row_bytes;
+              for (int i = 0; i < p.npair; ++i) {
+                if (sp * p.npair + i >= m_tiles) break;
+                const uint32_t d_tmem = tmem_base + (uint32_t)((acc * p.npair + i) * p.BN);
+                for (int j = 0; j < ksteps; ++j) {
+                  const uint64_t ad = umma_desc_kmajor(a_base + (uint32_t)i * p.a_tile_bytes + rowoff + (uint32_t)j * 32u, row_bytes);
+                  const uint64_t bd = umma_desc_kmajor(b_addr + (uint32_t)j * 32u, row_bytes);
+                  ptx::umma_bf16(d_tmem, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              if (!p.resident) {
+                ptx::umma_commit(b_empty(bs));
+                if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+              }
+            }
+            ptx::umma_commit(a_empty(as));
+            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+          }
+        }
+        ptx::umma_commit(t_full(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const uint32_t pitch = (uint32_t)p.CS * 2u;
+    const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
+    const uint32_t sub_bytes = 128u * pitch;
+    uint8_t* staging = smem + staging_off;
+    const uint32_t staging_addr = smem_base + staging_off;
+    float* wstat = reinterpret_cast<float*>(smem + stat_off) + q * 2 * p.BN;   // this warp's [2][BN]
+    float* allstat = reinterpret_cast<float*>(smem + stat_off);
+    if (p.stat) for (int i = lane; i < 2 * p.BN; i += 32) wstat[i] = 0.f;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int hi = row / p.twb, wq = row - hi * p.twb;
+    const bool row_ok = wq < p.two && hi < p.th;
+    const int mr = hi * p.two + wq;                 // compacted staging row (valid rows only)
+    int s_nb = -1;
+    auto flush_stats = [&]() {
+      if (p.stat && s_nb >= 0) {
+        ptx::named_bar_sync(1, 128);
+        for (int i = et; i < 2 * p.BN; i += 128) {
+          const float v = allstat[i] + allstat[2 * p.BN + i] + allstat[4 * p.BN + i] + allstat[6 * p.BN + i];
+          const int which = i / p.BN, c = i - which * p.BN;
+          atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
+        }
+        ptx::named_bar_sync(1, 128);
+        for (int i = lane; i < 2 * p.BN; i += 32) wstat[i] = 0.f;
+      }
+    };
+    for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
+      const int nt = st % p.n_tiles, sp = st / p.n_tiles;
+      const int nb = nt * p.BN;
+      if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
+      ptx::mbar_wait(t_full(acc), acc_phase);
+      ptx::tc_fence_after();
+      for (int i = 0; i < p.npair; ++i) {
+        const int mt = sp * p.npair + i;
+        if (mt >= m_tiles) break;
+        int w0, h0, n;
+        decode_m(mt, w0, h0, n);
+        const bool valid = row_ok && (w0 + wq) < p.W && (h0 + hi) < p.H;
+        const long long pix = ((long long)n * p.H + (h0 + hi)) * p.W + (w0 + wq);
+        const uint32_t t_base = tmem_base + (uint32_t)((acc * p.npair + i) * p.BN) + ((uint32_t)(q * 32) << 16);
+        for (int j = 0; j < p.BN / 32; ++j) {
+          uint32_t v[32];
+          ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
+          ptx::tmem_ld_wait();
+          const int c0 = nb + j * 32;
+          float f[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+          if (p.bias) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + k);
+              f[k] += b4.x; f[k + 1] += b4.y; f[k + 2] += b4.z; f[k + 3] += b4.w;
+            }
+          }
+          if (p.t && valid) {
+            const bf16* tp = p.t + pix * p.t_ld + c0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(tp + k);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float2 tf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k2]));
+                const int c = k + 2 * k2;
+                if (p.bn_a) {
+                  f[c] += p.bn_a[c0 + c] * tf.x + p.bn_b[c0 + c];
+                  f[c + 1] += p.bn_a[c0 + c + 1] * tf.y + p.bn_b[c0 + c + 1];
+                } else {
+                  f[c] += tf.x; f[c + 1] += tf.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
+          }
+          uint32_t packed[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(valid ? f[2 * k] : 0.f, valid ? f[2 * k + 1] : 0.f);
+            packed[k] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          if (valid) {
+            const int colt = j * 32;
+            const int sub = colt / p.CS;
+            const uint32_t byte_in_row = (uint32_t)(colt % p.CS) * 2u;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const uint32_t logical = (uint32_t)mr * pitch + byte_in_row + (uint32_t)g4 * 16u;
+              const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
+              *reinterpret_cast<uint4*>(staging + (uint32_t)sub * sub_bytes + phys) =
+                  make_uint4(packed[g4 * 4], packed[g4 * 4 + 1], packed[g4 * 4 + 2], packed[g4 * 4 + 3]);
+            }
+          }
+          if (p.stat) {
+            // column sums over the warp's 32 rows by a butterfly transpose-reduce (31 shuffles per quantity);
+            // lane l ends up with column l of this chunk.  Values are the bf16-rounded stored ones.
+            float a[32], b[32];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[k]));
+              a[2 * k] = r2.x; a[2 * k + 1] = r2.y;
+              b[2 * k] = r2.x * r2.x; b[2 * k + 1] = r2.y * r2.y;
+            }
+#pragma unroll
+            for (int off = 16, nn = 32; off >= 1; off >>= 1, nn >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int k = 0; k < nn / 2; ++k) {
+                const float sa = up ? a[k] : a[k + nn / 2];
+                const float sb = up ? b[k] : b[k + nn / 2];
+                const float ra = __shfl_xor_sync(0xffffffffu, sa, off);
+                const float rb = __shfl_xor_sync(0xffffffffu, sb, off);
+                a[k] = (up ? a[k + nn / 2] : a[k]) + ra;
+                b[k] = (up ? b[k + nn / 2] : b[k]) + rb;
+              }
+            }
+            wstat[j * 32 + lane] += a[0];
+            wstat[p.BN + j * 32 + lane] += b[0];
+          }
+        }
+        if (i == p.npair - 1 || mt + 1 >= m_tiles) {
+          // all accumulators of this TMEM stage drained
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(t_empty(acc));
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(1, 128);
+        if (et == 0) {
+          for (int s = 0; s < p.BN / p.CS; ++s)
+            ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s * sub_bytes, nb + s * p.CS, w0, h0, n);
+          ptx::tma_store_commit();
+          ptx::tma_store_wait_read();
+        }
+        ptx::named_bar_sync(1, 128);
+      }
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+    }
+    flush_stats();
+    if (et == 0) ptx::tma_store_wait_all();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ===========================================================================
 // weight gradient: dW[tap][co][ci] += sum over pixels dY[p][co] * X[p @ tap][ci]
 // A = dY tile (M = 128 out-channels), B = X tile shifted by the tap (N = 64/128 in-channels), K = 64 pixels
 // per pipeline stage.  Both operands are the NHWC tiles exactly as TMA delivers them (pixel rows of 64
@@ -738,6 +1076,11 @@ struct TcConv {
     CUtensorMap y, xm; TcWgradParams p; int grid; size_t smem;
   };
   std::vector<WCached> wcache;
+  struct Cached3 {
+    const void *x, *y; int x_ld, y_ld, B, H, W, dir;
+    CUtensorMap a, b, c; TcConv3Params p; int grid; size_t smem;
+  };
+  std::vector<Cached3> cache3;
   struct Cached {
     const void *x, *y; int x_ld, y_ld, B, H, W, dir;   // H, W: spatial dims of the GEMM's pixel grid
     CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem;
@@ -767,6 +1110,7 @@ inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool 
   t.w_dgrad = w.take<bf16>(n);
   t.dw_acc = ws.take<float>(n);
   t.cache.clear();
+  t.cache3.clear();
   t.wcache.clear();
 }
 
@@ -931,6 +1275,123 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   return &t.cache.back();
 }
 
+// ---------------------------------------------------------------------------
+// halo kernel (tc_conv3_kernel) host side
+// ---------------------------------------------------------------------------
+inline int tc_env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+inline bool tc_use_v2(const TcConv& t, int H, int W) {
+  return t.kind == 0 && t.k == 3 && W >= 24 && H >= 8 && tc_env_int("FU_TC_V2", 1) != 0;
+}
+
+inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
+  long long best = -1;
+  twb = 16; th = 8;
+  for (int a = 8; a <= 130; a += (halo1 ? 1 : 8)) {
+    int b = 128 / a;
+    if (b > H) b = H;
+    if (b < 1) continue;
+    const int two = a - 2;
+    if (two < 1) continue;
+    const long long tiles = (long long)((W + two - 1) / two) * ((H + b - 1) / b);
+    const long long key = tiles * 4096 + (long long)(b + 2) * a;
+    if (best < 0 || key < best) { best = key; twb = a; th = b; }
+  }
+}
+
+inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W) {
+  for (auto& c : t.cache3)
+    if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == H && c.W == W && c.dir == dir)
+      return &c;
+  TcConv::Cached3 c;
+  memset(&c, 0, sizeof(c));
+  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = H; c.W = W; c.dir = dir;
+  TcConv3Params& p = c.p;
+  const int K = dir == 0 ? t.Cin : t.Cout;
+  const int N = dir == 0 ? t.Cout : t.Cin;
+  p.B = B; p.H = H; p.W = W; p.K = K; p.N = N;
+  p.KC = (K % 64 == 0) ? 64 : 32;
+  int bn = 128;
+  while (N % bn) bn >>= 1;
+  p.BN = bn; p.CS = bn >= 64 ? 64 : 32;
+  p.n_tiles = N / bn;
+  p.halo1 = tc_env_int("FU_TC_HALO1", 1) ? 1 : 0;
+  p.npair = tc_env_int("FU_TC_PAIR", 1) ? 2 : 1;
+  tc_pick_halo_tile(H, W, p.halo1 != 0, p.twb, p.th);
+  p.two = p.twb - 2;
+  p.tiles_w = (W + p.two - 1) / p.two; p.tiles_h = (H + p.th - 1) / p.th;
+  const size_t row_bytes = (size_t)p.KC * 2;
+  size_t rows = (size_t)(p.th + 2) * p.twb + 2;
+  if (rows < (size_t)(2 * p.twb + 2 + 128)) rows = (size_t)(2 * p.twb + 2 + 128);
+  p.a_tile_bytes = (unsigned)((rows * row_bytes + 1023) / 1024 * 1024);
+  const size_t a_stage = (size_t)p.npair * p.a_tile_bytes;
+  const size_t b_bytes = (size_t)p.BN * row_bytes;
+  const size_t staging = (size_t)128 * p.BN * 2;
+  const size_t fixed = 1024 + staging + (size_t)32 * p.BN + 8 * 40;
+  const size_t budget = 227 * 1024;
+  const size_t wbytes = (size_t)9 * K * p.BN * 2;
+  p.resident = (p.n_tiles == 1 && fixed + wbytes + 2 * a_stage <= budget && tc_env_int("FU_TC_RESIDENT", 1)) ? 1 : 0;
+  if (p.resident) {
+    int as = (int)((budget - fixed - wbytes) / a_stage);
+    p.a_stages = as > 4 ? 4 : as;
+    p.b_stages = 1;
+    c.smem = fixed + wbytes + (size_t)p.a_stages * a_stage;
+  } else {
+    p.a_stages = 2;
+    if (fixed + 3 * a_stage + 6 * b_bytes <= budget) p.a_stages = 3;
+    int bs = (int)((budget - fixed - (size_t)p.a_stages * a_stage) / b_bytes);
+    if (bs > 8) bs = 8;
+    if (bs < 2) { tc_err() = "halo tile does not fit shared memory"; return nullptr; }
+    p.b_stages = bs;
+    c.smem = fixed + (size_t)p.a_stages * a_stage + (size_t)bs * b_bytes;
+  }
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * B;
+  const long long total_super = (m_tiles + p.npair - 1) / p.npair * p.n_tiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  c.grid = (int)(total_super < sms ? total_super : sms);
+  {
+    long long dims[4] = {K, W, H, B};
+    long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
+    int box[4] = {p.KC, p.twb, p.th + 2, 1};
+    if (tc_make_map(&c.a, x, 4, dims, str, box, p.KC * 2)) return nullptr;
+  }
+  {
+    long long dims[3] = {K, 9, N};
+    long long str[3] = {1, K, 9ll * K};
+    int box[3] = {p.KC, 1, p.BN};
+    if (tc_make_map(&c.b, dir == 0 ? t.w_fwd : t.w_dgrad, 3, dims, str, box, p.KC * 2)) return nullptr;
+  }
+  {
+    long long dims[4] = {N, W, H, B};
+    long long str[4] = {1, y_ld, (long long)W * y_ld, (long long)H * W * y_ld};
+    int box[4] = {p.CS, p.two, p.th, 1};
+    if (tc_make_map(&c.c, y, 4, dims, str, box, p.CS * 2)) return nullptr;
+  }
+  t.cache3.push_back(c);
+  return &t.cache3.back();
+}
+
+inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      tc_err() = "cudaFuncSetAttribute(max dynamic smem, conv3) failed";
+      return -1;
+    }
+    attr_set = true;
+  }
+  tc_conv3_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
 inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -954,6 +1415,14 @@ inline bool tc_conv_eligible(const TcConv& t, const void* x, int x_ld, const voi
 inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, const float* bias,
                            int relu, double* stat, const void* tp, int t_ld, const float* bn_a, const float* bn_b,
                            int accumulate, cudaStream_t stream, fu_counters* cnt) {
+  if (tc_use_v2(t, H, W)) {
+    TcConv::Cached3* c3 = tc_prepare3(t, 0, x, x_ld, y, y_ld, B, H, W);
+    if (!c3) return -1;
+    c3->p.bias = bias; c3->p.relu = relu; c3->p.stat = stat;
+    c3->p.t = reinterpret_cast<const bf16*>(tp); c3->p.t_ld = t_ld; c3->p.bn_a = bn_a; c3->p.bn_b = bn_b;
+    if (accumulate) { c3->p.t = reinterpret_cast<const bf16*>(y); c3->p.t_ld = y_ld; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr; }
+    return tc_launch3(c3, stream, cnt);
+  }
   TcConv::Cached* c = tc_prepare(t, 0, x, x_ld, y, y_ld, B, H, W);
   if (!c) return -1;
   c->p.bias = bias; c->p.relu = relu; c->p.stat = stat;
@@ -968,6 +1437,13 @@ inline bool tc_dgrad_eligible(const TcConv& t, const void* dy, int dy_ld, const 
 
 inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
                          cudaStream_t stream, fu_counters* cnt) {
+  if (tc_use_v2(t, H, W)) {
+    TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
+    if (!c3) return -1;
+    c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = nullptr; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
+    c3->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c3->p.t_ld = dx_ld;
+    return tc_launch3(c3, stream, cnt);
+  }
   TcConv::Cached* c = tc_prepare(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
   if (!c) return -1;
   c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;

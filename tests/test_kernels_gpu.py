@@ -191,3 +191,44 @@ def test_tc_up_conv_transpose_2x2_s2(pkg, shape):
     assert rel_l2(y.float().cpu().permute(0, 3, 1, 2), y_ref.detach()) < 6e-3
     assert rel_l2(dx.float().cpu().permute(0, 3, 1, 2), x.grad) < 6e-3
     assert rel_l2(dw.cpu(), w.grad) < 1e-4
+
+
+HALO_SHAPES = [  # B, Cin, Cout, H, W  -- 3x3 convs wide enough for the halo kernel (W >= 24)
+    (2, 32, 32, 40, 56),      # thin layer: 64-byte rows, weights resident in shared memory
+    (1, 64, 64, 48, 48),      # resident weights, 128-byte rows
+    (2, 128, 128, 24, 40),    # streamed weights, two pixel tiles per weight tile, 2 K chunks
+    (1, 32, 64, 33, 29),      # ragged in both directions
+    (3, 64, 32, 26, 70),
+    (1, 256, 256, 24, 24),    # two N tiles
+    (5, 64, 64, 24, 24),      # odd number of pixel tiles (last pair half empty)
+]
+
+
+@pytest.mark.parametrize("env", [{}, {"FU_TC_HALO1": "0"}, {"FU_TC_PAIR": "0"}, {"FU_TC_RESIDENT": "0"}])
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+def test_tc_halo_conv_fwd_dgrad(pkg, shape, env):
+    """Second-generation 3x3 kernel (one halo load per chunk, taps = row-shifted descriptor views, paired
+    pixel tiles, resident weights) and each of its fallback modes, against torch-CPU fp32."""
+    import os
+    B, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + 7)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g).bfloat16().float()
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        y, stats = run_conv(pkg, 1, 1, 0, x, w, b, None, 3, 1, 1, relu=1, want_stats=True)
+        dx = run_conv(pkg, 1, 1, 1, x, w, None, dy, 3, 1, 1)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    y_ref = torch.relu(F.conv2d(x, w, b, padding=1))
+    assert rel_l2(y, y_ref.bfloat16().float()) < 2e-3, rel_l2(y, y_ref)
+    assert rel_l2(stats[:Cout], y.double().sum(dim=(0, 2, 3))) < 1e-4
+    assert rel_l2(stats[Cout:], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
+    assert rel_l2(dx, torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=1)) < 6e-3
