@@ -143,6 +143,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// true in exactly one lane of a fully converged warp.  Code guarded by it is known by the compiler to run
+// in a single thread, so tcgen05.mma / cp.async.bulk.tensor (which take uniform registers) are emitted as
+// straight-line code instead of a per-active-lane ELECT loop (measured: ~30 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -160,6 +172,10 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_
   d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
   d |= layout << 61;
   return d;
+}
+// descriptor of the same tile family at another shared-memory address (< 256 KB, so no carry out of the field)
+__device__ __forceinline__ uint64_t umma_desc_at(uint64_t base_desc_no_addr, uint32_t smem_addr) {
+  return base_desc_no_addr + (uint64_t)(smem_addr >> 4);
 }
 // instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t n) {
@@ -207,6 +223,7 @@ struct TcConvParams {
 
 constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kTcMaxStages = 8;
+constexpr int kTc3Threads = 320;      // halo kernel: producer, MMA, 2 x 4 epilogue warps (one group per paired pixel tile)
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -265,8 +282,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (whole warp loops, one elected lane issues) -----
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int w0, h0, n0, nb;
@@ -275,21 +292,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = kit / cchunks, c0 = (kit - tap * cchunks) * p.KC;
           const int kh = tap / p.ksz, kw = tap - kh * p.ksz;
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
-          ptx::mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
-          if (p.a5) ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kw, w0, kh, h0);
-          else ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw - p.pad, h0 + kh - p.pad, n0);
-          ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), c0, tap, nb);
+          if (ptx::elect_one()) {
+            const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+            ptx::mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
+            if (p.a5) ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kw, w0, kh, h0);
+            else ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+            ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), c0, tap, nb);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (whole warp loops, one elected lane issues) -----
+    {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
+      const uint64_t dbase = umma_desc_kmajor(0, row_bytes);
       const int ksteps = p.KC / 16;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -298,17 +319,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kit = 0; kit < k_iters; ++kit) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
-          const uint32_t b_addr = a_addr + a_bytes;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint64_t ad = umma_desc_kmajor(a_addr + (uint32_t)j * 32u, row_bytes);
-            const uint64_t bd = umma_desc_kmajor(b_addr + (uint32_t)j * 32u, row_bytes);
-            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kit | j) != 0 ? 1u : 0u);
+          if (ptx::elect_one()) {
+            const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+            const uint64_t ad0 = umma_desc_at(dbase, a_addr), bd0 = umma_desc_at(dbase, a_addr + a_bytes);
+            for (int j = 0; j < ksteps; ++j)   // +32 B per K step = +2 in the descriptor's address field
+              ptx::umma_bf16(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, (kit | j) != 0 ? 1u : 0u);
+            ptx::umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
+            if (kit == k_iters - 1) ptx::umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
           }
-          ptx::umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
@@ -492,9 +513,10 @@ struct TcConv3Params {
   const bf16* t; int t_ld;
   const float* bn_a; const float* bn_b;
   double* stat;
+  long long* dbg;               // optional timeline buffer (FU_TC_DBG=1): [role][super][event] clock64 of CTA 0
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTc3Threads, 1)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const TcConv3Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -510,9 +532,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t b_off = a_off + (uint32_t)p.a_stages * a_stage_bytes;
   const uint32_t b_region = p.resident ? (uint32_t)(cchunks * 9) * b_bytes : (uint32_t)p.b_stages * b_bytes;
   const uint32_t staging_off = b_off + b_region;
-  const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;
-  const uint32_t stat_off = staging_off + staging_bytes;          // [4 warps][2][BN] floats
-  const uint32_t bar_off = stat_off + 4u * 2u * (uint32_t)p.BN * 4u;
+  const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;      // one per epilogue group
+  const uint32_t vec_off = staging_off + (uint32_t)p.npair * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
+  const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;    // [npair][2][BN] floats
+  const uint32_t bar_off = (stat_off + (uint32_t)p.npair * 2u * (uint32_t)p.BN * 4u + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(8 + s); };
@@ -531,17 +554,31 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1);
       ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1);
     }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(t_full(a), 1); ptx::mbar_init(t_empty(a), 128); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(t_full(a), 1); ptx::mbar_init(t_empty(a), 128u * (uint32_t)p.npair); }
     ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
   }
   if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  {
+    // per-channel epilogue vectors live in shared memory for the whole (persistent) CTA: the epilogue warps
+    // run one per scheduler, so a global/L1 load in their dependency chain is an exposed long-scoreboard stall
+    float* vec = reinterpret_cast<float*>(smem + vec_off);
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      vec[i] = p.bias ? p.bias[i] : 0.f;
+      vec[p.N + i] = p.bn_a ? p.bn_a[i] : 1.f;
+      vec[2 * p.N + i] = p.bn_a ? p.bn_b[i] : 0.f;
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *slot_ptr;
 
+#define FU_DBG(role, idx, ev)                                                                       \
+  do {                                                                                              \
+    if (p.dbg && blockIdx.x == 0 && (idx) < 24) p.dbg[((role) * 24 + (idx)) * 4 + (ev)] = clock64(); \
+  } while (0)
   const int tiles_img = p.tiles_w * p.tiles_h;
   const int m_tiles = tiles_img * p.B;
   const int supers_m = (m_tiles + p.npair - 1) / p.npair;
@@ -558,14 +595,15 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      if (p.resident) {
+    // ------------------------------ TMA producer (whole warp loops, one elected lane issues) -----
+    {
+      if (p.resident && ptx::elect_one()) {
         ptx::mbar_expect_tx(res_bar, (uint32_t)(cchunks * 9) * b_bytes);
         for (int c = 0; c < cchunks; ++c)
           for (int tap = 0; tap < 9; ++tap)
             ptx::tma_load_3d(smem_base + b_off + (uint32_t)(c * 9 + tap) * b_bytes, &tmB, res_bar, c * p.KC, tap, 0);
       }
+      __syncwarp();
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
       for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
         const int nt = st % p.n_tiles, sp = st / p.n_tiles;
@@ -573,24 +611,31 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int c = 0; c < cchunks; ++c) {
           for (int g = 0; g < groups; ++g) {
             ptx::mbar_wait(a_empty(as), aph ^ 1u);
-            int nvalid = 0;
-            for (int i = 0; i < p.npair; ++i) nvalid += (sp * p.npair + i) < m_tiles ? 1 : 0;
-            ptx::mbar_expect_tx(a_full(as), (uint32_t)nvalid * box_bytes);
-            for (int i = 0; i < p.npair; ++i) {
-              const int mt = sp * p.npair + i;
-              if (mt >= m_tiles) break;
-              int w0, h0, n;
-              decode_m(mt, w0, h0, n);
-              ptx::tma_load_4d(smem_base + a_off + (uint32_t)as * a_stage_bytes + (uint32_t)i * p.a_tile_bytes, &tmA,
-                               a_full(as), c * p.KC, w0 - 1 + (p.halo1 ? 0 : g), h0 - 1, n);
+            if (ptx::elect_one()) {
+              if (c == 0 && g == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
+              int nvalid = 0;
+              for (int i = 0; i < p.npair; ++i) nvalid += (sp * p.npair + i) < m_tiles ? 1 : 0;
+              ptx::mbar_expect_tx(a_full(as), (uint32_t)nvalid * box_bytes);
+              for (int i = 0; i < p.npair; ++i) {
+                const int mt = sp * p.npair + i;
+                if (mt >= m_tiles) break;
+                int w0, h0, n;
+                decode_m(mt, w0, h0, n);
+                ptx::tma_load_4d(smem_base + a_off + (uint32_t)as * a_stage_bytes + (uint32_t)i * p.a_tile_bytes, &tmA,
+                                 a_full(as), c * p.KC, w0 - 1 + (p.halo1 ? 0 : g), h0 - 1, n);
+              }
             }
+            __syncwarp();
             if (++as == p.a_stages) { as = 0; aph ^= 1u; }
             if (!p.resident) {
               for (int tt = 0; tt < taps_per_group; ++tt) {
                 const int tap = p.halo1 ? tt : tt * 3 + g;      // (kh = tt, kw = g) when one load per kw
                 ptx::mbar_wait(b_empty(bs), bph ^ 1u);
-                ptx::mbar_expect_tx(b_full(bs), b_bytes);
-                ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB, b_full(bs), c * p.KC, tap, nb);
+                if (ptx::elect_one()) {
+                  ptx::mbar_expect_tx(b_full(bs), b_bytes);
+                  ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB, b_full(bs), c * p.KC, tap, nb);
+                }
+                __syncwarp();
                 if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
               }
             }
@@ -600,203 +645,253 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // The whole warp runs the loop; one elected lane issues.  The issue path is the critical resource of
+    // this kernel (measured with the FU_TC_DBG timeline: ~100 SASS instructions per tap made every MMA cost
+    // 120-215 cycles instead of 16-64), so everything address-like is reduced to 64-bit descriptor adds
+    // prepared outside the tap loop and the K steps are unrolled at compile time.
+    {
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
+      const uint64_t dbase = umma_desc_kmajor(0, row_bytes);
       const int ksteps = p.KC / 16;
-      if (p.resident) { ptx::mbar_wait(res_bar, 0); ptx::tc_fence_after(); }
+      const int npair = p.npair, resident = p.resident, halo1 = p.halo1, a_stages = p.a_stages, b_stages = p.b_stages;
+      const uint32_t BNc = (uint32_t)p.BN;
+      const uint32_t a_tile16 = p.a_tile_bytes >> 4, b16 = b_bytes >> 4;
+      // row offset (in 16-byte units) of each tap's view into the halo tile
+      uint32_t rowoff16[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+        rowoff16[tap] = ((uint32_t)((tap / 3) * p.twb + (halo1 ? tap % 3 : 0)) * row_bytes) >> 4;
+      if (resident) { ptx::mbar_wait(res_bar, 0); ptx::tc_fence_after(); }
       for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
         const int sp = st / p.n_tiles;
+        const bool two = npair == 2 && (sp * 2 + 1) < m_tiles;
         ptx::mbar_wait(t_empty(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
-        bool first = true;
+        if (lane == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * npair) * BNc, d1 = d0 + BNc;
+        uint32_t accum = 0;                       // 0 only for the very first MMA into each accumulator
         for (int c = 0; c < cchunks; ++c) {
           for (int g = 0; g < groups; ++g) {
             ptx::mbar_wait(a_full(as), aph);
             ptx::tc_fence_after();
-            const uint32_t a_base = smem_base + a_off + (uint32_t)as * a_stage_bytes;
-            for (int tt = 0; tt < taps_per_group; ++tt) {
-              const int tap = p.halo1 ? tt : tt * 3 + g;
-              const int kh = tap / 3, kw = tap - kh * 3;
-              uint32_t b_addr;
-              if (p.resident) {
-                b_addr = smem_base + b_off + (uint32_t)(c * 9 + tap) * b_bytes;
-              } else {
+            if (lane == 0 && c == 0 && g == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
+            const uint64_t a_desc0 = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4);
+            const bool last_group = c == cchunks - 1 && g == groups - 1;
+            if (resident) {
+              // all 9 taps straight from the resident weight region: one elected section per A stage
+              if (ptx::elect_one()) {
+                const uint64_t b_desc0 = dbase + (uint64_t)((smem_base + b_off + (uint32_t)(c * 9) * b_bytes) >> 4);
+#pragma unroll
+                for (int tt = 0; tt < 9; ++tt) {
+                  if (!halo1 && (tt % 3) != g) continue;        // one A load per kw: only taps with kw == g
+                  const uint64_t ad = a_desc0 + rowoff16[tt], bd = b_desc0 + (uint64_t)(tt * b16);
+                  if (ksteps == 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                    }
+                  }
+                  accum = 1;
+                }
+                ptx::umma_commit(a_empty(as));
+                if (last_group) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
+              }
+              __syncwarp();
+              accum = 1;
+            } else {
+              for (int tt = 0; tt < taps_per_group; ++tt) {
+                const int tap = halo1 ? tt : tt * 3 + g;
                 ptx::mbar_wait(b_full(bs), bph);
                 ptx::tc_fence_after();
-                b_addr = smem_base + b_off + (uint32_t)bs * b_bytes;
-              }
-              const uint32_t rowoff = (uint32_t)(kh * p.twb + (p.halo1 ? kw : 0)) * row_bytes;
-              for (int i = 0; i < p.npair; ++i) {
-                if (sp * p.npair + i >= m_tiles) break;
-                const uint32_t d_tmem = tmem_base + (uint32_t)((acc * p.npair + i) * p.BN);
-                for (int j = 0; j < ksteps; ++j) {
-                  const uint64_t ad = umma_desc_kmajor(a_base + (uint32_t)i * p.a_tile_bytes + rowoff + (uint32_t)j * 32u, row_bytes);
-                  const uint64_t bd = umma_desc_kmajor(b_addr + (uint32_t)j * 32u, row_bytes);
-                  ptx::umma_bf16(d_tmem, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
+                if (ptx::elect_one()) {
+                  const uint64_t ad = a_desc0 + rowoff16[tap];
+                  const uint64_t bd = dbase + (uint64_t)((smem_base + b_off + (uint32_t)bs * b_bytes) >> 4);
+                  if (ksteps == 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                    }
+                  }
+                  ptx::umma_commit(b_empty(bs));
+                  if (tt == taps_per_group - 1) {
+                    ptx::umma_commit(a_empty(as));
+                    if (last_group) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
+                  }
                 }
-              }
-              first = false;
-              if (!p.resident) {
-                ptx::umma_commit(b_empty(bs));
-                if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+                __syncwarp();
+                accum = 1;
+                if (++bs == b_stages) { bs = 0; bph ^= 1u; }
               }
             }
-            ptx::umma_commit(a_empty(as));
-            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+            if (++as == a_stages) { as = 0; aph ^= 1u; }
           }
         }
-        ptx::umma_commit(t_full(acc));
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else {
-    // ------------------------------ epilogue ------------------------------
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
-    const uint32_t pitch = (uint32_t)p.CS * 2u;
-    const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
-    const uint32_t sub_bytes = 128u * pitch;
-    uint8_t* staging = smem + staging_off;
-    const uint32_t staging_addr = smem_base + staging_off;
-    float* wstat = reinterpret_cast<float*>(smem + stat_off) + q * 2 * p.BN;   // this warp's [2][BN]
-    float* allstat = reinterpret_cast<float*>(smem + stat_off);
-    if (p.stat) for (int i = lane; i < 2 * p.BN; i += 32) wstat[i] = 0.f;
-    int acc = 0; uint32_t acc_phase = 0;
-    const int hi = row / p.twb, wq = row - hi * p.twb;
-    const bool row_ok = wq < p.two && hi < p.th;
-    const int mr = hi * p.two + wq;                 // compacted staging row (valid rows only)
-    int s_nb = -1;
-    auto flush_stats = [&]() {
-      if (p.stat && s_nb >= 0) {
-        ptx::named_bar_sync(1, 128);
-        for (int i = et; i < 2 * p.BN; i += 128) {
-          const float v = allstat[i] + allstat[2 * p.BN + i] + allstat[4 * p.BN + i] + allstat[6 * p.BN + i];
-          const int which = i / p.BN, c = i - which * p.BN;
-          atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
+    // ------------------------------ epilogue: one group of 4 warps per pixel tile of the pair -----
+    const int grp = (warp - 2) >> 2;          // 0 / 1 = which pixel tile of the super tile
+    if (grp < p.npair) {
+      const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+      const int row = q * 32 + lane;
+      const int et = (threadIdx.x - 64) & 127;   // thread index within the group
+      const int bar_id = 1 + grp;
+      const uint32_t pitch = (uint32_t)p.CS * 2u;
+      const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
+      const uint32_t sub_bytes = 128u * pitch;
+      uint8_t* staging = smem + staging_off + (uint32_t)grp * staging_bytes;
+      const uint32_t staging_addr = smem_base + staging_off + (uint32_t)grp * staging_bytes;
+      const float* vec = reinterpret_cast<const float*>(smem + vec_off);
+      float* gstat = reinterpret_cast<float*>(smem + stat_off) + grp * 2 * p.BN;
+      int acc = 0; uint32_t acc_phase = 0;
+      const int hi = row / p.twb, wq = row - hi * p.twb;
+      const bool row_ok = wq < p.two && hi < p.th;
+      const int mr = hi * p.two + wq;               // compacted staging row (valid rows only)
+      const int rows_valid = p.th * p.two;
+      // statistics ownership: column pair cp, row group rg (BN/2 rows each)
+      const int cpairs = p.BN >> 1;
+      const int cp = et % cpairs, rg = et / cpairs;
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+      int s_nb = -1;
+      auto flush_stats = [&]() {
+        if (p.stat && s_nb >= 0) {
+          for (int i = et; i < 2 * p.BN; i += 128) gstat[i] = 0.f;
+          ptx::named_bar_sync(bar_id, 128);
+          atomicAdd(&gstat[2 * cp], s0); atomicAdd(&gstat[2 * cp + 1], s1);
+          atomicAdd(&gstat[p.BN + 2 * cp], q0); atomicAdd(&gstat[p.BN + 2 * cp + 1], q1);
+          s0 = s1 = q0 = q1 = 0.f;
+          ptx::named_bar_sync(bar_id, 128);
+          for (int i = et; i < 2 * p.BN; i += 128) {
+            const int which = i / p.BN, c = i - which * p.BN;
+            atomicAdd(p.stat + which * p.N + s_nb + c, (double)gstat[i]);
+          }
+          ptx::named_bar_sync(bar_id, 128);
         }
-        ptx::named_bar_sync(1, 128);
-        for (int i = lane; i < 2 * p.BN; i += 32) wstat[i] = 0.f;
-      }
-    };
-    for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
-      const int nt = st % p.n_tiles, sp = st / p.n_tiles;
-      const int nb = nt * p.BN;
-      if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
-      ptx::mbar_wait(t_full(acc), acc_phase);
-      ptx::tc_fence_after();
-      for (int i = 0; i < p.npair; ++i) {
-        const int mt = sp * p.npair + i;
-        if (mt >= m_tiles) break;
-        int w0, h0, n;
-        decode_m(mt, w0, h0, n);
-        const bool valid = row_ok && (w0 + wq) < p.W && (h0 + hi) < p.H;
-        const long long pix = ((long long)n * p.H + (h0 + hi)) * p.W + (w0 + wq);
-        const uint32_t t_base = tmem_base + (uint32_t)((acc * p.npair + i) * p.BN) + ((uint32_t)(q * 32) << 16);
-        for (int j = 0; j < p.BN / 32; ++j) {
-          uint32_t v[32];
-          ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
-          ptx::tmem_ld_wait();
-          const int c0 = nb + j * 32;
-          float f[32];
-#pragma unroll
-          for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
-          if (p.bias) {
+      };
+      for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
+        const int nt = st % p.n_tiles, sp = st / p.n_tiles;
+        const int nb = nt * p.BN;
+        const int mt = sp * p.npair + grp;
+        if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
+        if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
+        ptx::mbar_wait(t_full(acc), acc_phase);
+        ptx::tc_fence_after();
+        if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
+        if (mt < m_tiles) {
+          int w0, h0, n;
+          decode_m(mt, w0, h0, n);
+          const bool valid = row_ok && (w0 + wq) < p.W && (h0 + hi) < p.H;
+          const long long pix = ((long long)n * p.H + (h0 + hi)) * p.W + (w0 + wq);
+          const uint32_t t_base = tmem_base + (uint32_t)((acc * p.npair + grp) * p.BN) + ((uint32_t)(q * 32) << 16);
+          for (int j = 0; j < p.BN / 32; ++j) {
+            uint32_t v[32];
+            ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
+            ptx::tmem_ld_wait();
+            const int c0 = nb + j * 32;
+            float f[32];
 #pragma unroll
             for (int k = 0; k < 32; k += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + k);
-              f[k] += b4.x; f[k + 1] += b4.y; f[k + 2] += b4.z; f[k + 3] += b4.w;
+              const float4 b4 = *reinterpret_cast<const float4*>(vec + c0 + k);
+              f[k] = __uint_as_float(v[k]) + b4.x; f[k + 1] = __uint_as_float(v[k + 1]) + b4.y;
+              f[k + 2] = __uint_as_float(v[k + 2]) + b4.z; f[k + 3] = __uint_as_float(v[k + 3]) + b4.w;
             }
-          }
-          if (p.t && valid) {
-            const bf16* tp = p.t + pix * p.t_ld + c0;
+            if (p.t && valid) {
+              const bf16* tp = p.t + pix * p.t_ld + c0;
 #pragma unroll
-            for (int k = 0; k < 32; k += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(tp + k);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              for (int k = 0; k < 32; k += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(tp + k);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const float2 tf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k2]));
-                const int c = k + 2 * k2;
-                if (p.bn_a) {
-                  f[c] += p.bn_a[c0 + c] * tf.x + p.bn_b[c0 + c];
-                  f[c + 1] += p.bn_a[c0 + c + 1] * tf.y + p.bn_b[c0 + c + 1];
-                } else {
-                  f[c] += tf.x; f[c + 1] += tf.y;
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  const float2 tf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k2]));
+                  const int c = k + 2 * k2;
+                  f[c] += vec[p.N + c0 + c] * tf.x + vec[2 * p.N + c0 + c];
+                  f[c + 1] += vec[p.N + c0 + c + 1] * tf.y + vec[2 * p.N + c0 + c + 1];
                 }
               }
             }
-          }
-          if (p.relu) {
+            if (p.relu) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
-          }
-          uint32_t packed[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(valid ? f[2 * k] : 0.f, valid ? f[2 * k + 1] : 0.f);
-            packed[k] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          if (valid) {
-            const int colt = j * 32;
-            const int sub = colt / p.CS;
-            const uint32_t byte_in_row = (uint32_t)(colt % p.CS) * 2u;
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const uint32_t logical = (uint32_t)mr * pitch + byte_in_row + (uint32_t)g4 * 16u;
-              const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
-              *reinterpret_cast<uint4*>(staging + (uint32_t)sub * sub_bytes + phys) =
-                  make_uint4(packed[g4 * 4], packed[g4 * 4 + 1], packed[g4 * 4 + 2], packed[g4 * 4 + 3]);
+              for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
             }
-          }
-          if (p.stat) {
-            // column sums over the warp's 32 rows by a butterfly transpose-reduce (31 shuffles per quantity);
-            // lane l ends up with column l of this chunk.  Values are the bf16-rounded stored ones.
-            float a[32], b[32];
+            if (row_ok) {
+              // rows that fall outside the image are written as zeros so the statistics can scan the tile
+              const int colt = j * 32;
+              const int sub = colt / p.CS;
+              const uint32_t byte_in_row = (uint32_t)(colt % p.CS) * 2u;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[k]));
-              a[2 * k] = r2.x; a[2 * k + 1] = r2.y;
-              b[2 * k] = r2.x * r2.x; b[2 * k + 1] = r2.y * r2.y;
-            }
+              for (int g4 = 0; g4 < 4; ++g4) {
+                uint32_t pk[4];
 #pragma unroll
-            for (int off = 16, nn = 32; off >= 1; off >>= 1, nn >>= 1) {
-              const bool up = (lane & off) != 0;
-#pragma unroll
-              for (int k = 0; k < nn / 2; ++k) {
-                const float sa = up ? a[k] : a[k + nn / 2];
-                const float sb = up ? b[k] : b[k + nn / 2];
-                const float ra = __shfl_xor_sync(0xffffffffu, sa, off);
-                const float rb = __shfl_xor_sync(0xffffffffu, sb, off);
-                a[k] = (up ? a[k + nn / 2] : a[k]) + ra;
-                b[k] = (up ? b[k + nn / 2] : b[k]) + rb;
+                for (int k = 0; k < 4; ++k) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(valid ? f[g4 * 8 + 2 * k] : 0.f, valid ? f[g4 * 8 + 2 * k + 1] : 0.f);
+                  pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                const uint32_t logical = (uint32_t)mr * pitch + byte_in_row + (uint32_t)g4 * 16u;
+                const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
+                *reinterpret_cast<uint4*>(staging + (uint32_t)sub * sub_bytes + phys) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
-            wstat[j * 32 + lane] += a[0];
-            wstat[p.BN + j * 32 + lane] += b[0];
           }
         }
-        if (i == p.npair - 1 || mt + 1 >= m_tiles) {
-          // all accumulators of this TMEM stage drained
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(t_empty(acc));
+        // accumulator drained: hand the TMEM stage back to the MMA warp
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(t_empty(acc));
+        if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 2);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        if (mt < m_tiles) {
+          int w0, h0, n;
+          decode_m(mt, w0, h0, n);
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(bar_id, 128);
+          if (et == 0) {
+            for (int s2 = 0; s2 < p.BN / p.CS; ++s2)
+              ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s2 * sub_bytes, nb + s2 * p.CS, w0, h0, n);
+            ptx::tma_store_commit();
+          }
+          if (p.stat) {
+            // per-channel sum / sum of squares of the stored (bf16) tile: thread = (column pair, row group)
+            const int c = 2 * cp;
+            const int sub = c / p.CS;
+            const uint32_t bir = (uint32_t)(c % p.CS) * 2u;
+            const int r0 = rg * cpairs;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 4
+            for (int r = r0; r < r0 + cpairs; ++r) {
+              if (r < rows_valid) {
+                const uint32_t logical = (uint32_t)r * pitch + bir;
+                const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
+                const float2 x2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(staging + (uint32_t)sub * sub_bytes + phys));
+                a0 += x2.x; a1 += x2.y; b0 = fmaf(x2.x, x2.x, b0); b1 = fmaf(x2.y, x2.y, b1);
+              }
+            }
+            s0 += a0; s1 += a1; q0 += b0; q1 += b1;
+          }
+          if (et == 0) ptx::tma_store_wait_read();   // staging may be overwritten after this
+          ptx::named_bar_sync(bar_id, 128);
+          if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 3);
         }
-        ptx::fence_proxy_async_smem();
-        ptx::named_bar_sync(1, 128);
-        if (et == 0) {
-          for (int s = 0; s < p.BN / p.CS; ++s)
-            ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s * sub_bytes, nb + s * p.CS, w0, h0, n);
-          ptx::tma_store_commit();
-          ptx::tma_store_wait_read();
-        }
-        ptx::named_bar_sync(1, 128);
       }
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      flush_stats();
+      if (et == 0) ptx::tma_store_wait_all();
     }
-    flush_stats();
-    if (et == 0) ptx::tma_store_wait_all();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -870,14 +965,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t tmem_base = *slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        int pt = pt_begin + it;
-        const int w0 = (pt % p.tiles_w) * p.tw; pt /= p.tiles_w;
-        const int h0 = (pt % p.tiles_h) * p.th; pt /= p.tiles_h;
-        const int n0 = pt * p.tn;
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+    // whole warp loops, one elected lane issues the TMA loads
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      int pt = pt_begin + it;
+      const int w0 = (pt % p.tiles_w) * p.tw; pt /= p.tiles_w;
+      const int h0 = (pt % p.tiles_h) * p.th; pt /= p.tiles_h;
+      const int n0 = pt * p.tn;
+      ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (ptx::elect_one()) {
         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
         ptx::mbar_expect_tx(full_bar(stage), (uint32_t)nblk_a * kBox + b_bytes);
         for (int blk = 0; blk < nblk_a; ++blk)
@@ -890,30 +986,34 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
             else ptx::tma_load_4d(dst, &tmX, full_bar(stage), ci0 + blk * 64, w0 + kw - p.pad, h0 + kh - p.pad, n0);
           }
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N);
-      for (int it = 0; it < n_iters; ++it) {
-        ptx::mbar_wait(full_bar(stage), phase);
-        ptx::tc_fence_after();
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N);
+    const uint64_t dbase = umma_desc_mnmajor(0, kBox, 1024u);
+    for (int it = 0; it < n_iters; ++it) {
+      ptx::mbar_wait(full_bar(stage), phase);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
         const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
-        const uint32_t b_addr = a_addr + a_bytes;
+        const uint64_t ad0 = umma_desc_at(dbase, a_addr);
         for (int t = 0; t < p.taps_per_cta; ++t) {
-          for (int ks = 0; ks < 4; ++ks) {     // 64 pixels = 4 x K16; 16 pixel rows = 2048 B
-            const uint64_t ad = umma_desc_mnmajor(a_addr + (uint32_t)ks * 2048u, kBox, 1024u);
-            const uint64_t bd = umma_desc_mnmajor(b_addr + (uint32_t)(t * nblk_b) * kBox + (uint32_t)ks * 2048u, kBox, 1024u);
-            ptx::umma_bf16(tmem_base + (uint32_t)(t * p.N), ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
-          }
+          const uint64_t bd0 = umma_desc_at(dbase, a_addr + a_bytes + (uint32_t)(t * nblk_b) * kBox);
+          for (int ks = 0; ks < 4; ++ks)      // 64 pixels = 4 x K16; 16 pixel rows = 2048 B = +128 in the address field
+            ptx::umma_bf16(tmem_base + (uint32_t)(t * p.N), ad0 + (uint64_t)(128 * ks), bd0 + (uint64_t)(128 * ks), idesc,
+                           (it | ks) != 0 ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar(stage));
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        if (it == n_iters - 1) ptx::umma_commit(done_bar);
       }
-      ptx::umma_commit(done_bar);
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
+    if (n_iters == 0 && ptx::elect_one()) ptx::umma_commit(done_bar);
+    __syncwarp();
   } else if (n_iters > 0) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -1284,7 +1384,8 @@ inline int tc_env_int(const char* name, int dflt) {
 }
 
 inline bool tc_use_v2(const TcConv& t, int H, int W) {
-  return t.kind == 0 && t.k == 3 && W >= 24 && H >= 8 && tc_env_int("FU_TC_V2", 1) != 0;
+  // measured (tools/conv_time.py, B=32): 32->32@192 73 vs 214 us, 64->64@96 34 vs 61, 128->128@48 33 vs 34, 256->256@24 40 vs 32
+  return t.kind == 0 && t.k == 3 && W >= tc_env_int("FU_TC_V2_MINW", 48) && H >= 8 && tc_env_int("FU_TC_V2", 1) != 0;
 }
 
 inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
@@ -1329,8 +1430,8 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   p.a_tile_bytes = (unsigned)((rows * row_bytes + 1023) / 1024 * 1024);
   const size_t a_stage = (size_t)p.npair * p.a_tile_bytes;
   const size_t b_bytes = (size_t)p.BN * row_bytes;
-  const size_t staging = (size_t)128 * p.BN * 2;
-  const size_t fixed = 1024 + staging + (size_t)32 * p.BN + 8 * 40;
+  const size_t staging = (size_t)p.npair * 128 * p.BN * 2;
+  const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)p.npair * 8 * p.BN + 16 + 8 * 40;
   const size_t budget = 227 * 1024;
   const size_t wbytes = (size_t)9 * K * p.BN * 2;
   p.resident = (p.n_tiles == 1 && fixed + wbytes + 2 * a_stage <= budget && tc_env_int("FU_TC_RESIDENT", 1)) ? 1 : 0;
@@ -1385,7 +1486,27 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
     }
     attr_set = true;
   }
-  tc_conv3_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  static long long* dbg_buf = nullptr;
+  const bool dbg = tc_env_int("FU_TC_DBG", 0) != 0;
+  if (dbg) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 4 * 24 * 4 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 4 * 24 * 4 * sizeof(long long), stream);
+  }
+  c->p.dbg = dbg ? dbg_buf : nullptr;
+  tc_conv3_kernel<<<c->grid, kTc3Threads, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  if (dbg) {
+    long long h[4 * 24 * 4];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = h[0];
+    fprintf(stderr, "[tc_conv3 timeline, CTA 0, cycles rel. to first producer issue] twb=%d th=%d BN=%d KC=%d pair=%d resident=%d a_stages=%d b_stages=%d grid=%d\n",
+            c->p.twb, c->p.th, c->p.BN, c->p.KC, c->p.npair, c->p.resident, c->p.a_stages, c->p.b_stages, c->grid);
+    for (int i = 0; i < 12; ++i)
+      fprintf(stderr, "super %2d: prod %7lld | mma tmem_free %7lld a_full %7lld committed %7lld | epi0 start %7lld t_full %7lld drained %7lld stored %7lld | epi1 t_full %7lld stored %7lld\n",
+              i, h[(0 * 24 + i) * 4] - t0, h[(1 * 24 + i) * 4] - t0, h[(1 * 24 + i) * 4 + 1] - t0, h[(1 * 24 + i) * 4 + 2] - t0,
+              h[(2 * 24 + i) * 4] - t0, h[(2 * 24 + i) * 4 + 1] - t0, h[(2 * 24 + i) * 4 + 2] - t0, h[(2 * 24 + i) * 4 + 3] - t0,
+              h[(3 * 24 + i) * 4 + 1] - t0, h[(3 * 24 + i) * 4 + 3] - t0);
+  }
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
