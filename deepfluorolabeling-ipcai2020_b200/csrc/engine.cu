@@ -324,7 +324,7 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
     c.wp_dgrad = w.take<float>((size_t)taps_d * c.Cout * c.npad_dgrad);
     c.bsum = db.take<double>(c.Cout);
     c.small_cin = !c.transposed && (c.k == 3 || c.k == 1) && c.Cin <= 2 && (c.Cout % 8 == 0) && c.Cout <= 256 &&
-                  (c.Cout & (c.Cout - 1)) == 0;
+                  (c.Cout & (c.Cout - 1)) == 0 && c.Cout / 8 <= 32;
     if (c.Cout > maxc) maxc = c.Cout;
     if (c.Cin > maxc) maxc = c.Cin;
     tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision == FU_PRECISION_BF16, w, ws);
@@ -601,7 +601,7 @@ int run_wgrad(fu_engine* e, const WgradCall& c) {
 }
 
 inline dim3 red_grid(fu_engine* e, long long P, int C) {
-  const int cvecs = C / 4;
+  const int cvecs = C / (e->esz == 2 ? 8 : 4);     // Vec<T>::N channels per thread
   const int lanes = cvecs < 256 ? cvecs : 256;
   const int rows = 256 / lanes;
   long long gx = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);
@@ -649,7 +649,7 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     if (t) { a.t = t->p; a.t_ld = t->ld; a.bn_a = bn_a; a.bn_b = bn_b; }
     a.stat = stat;
     const long long total = (long long)B * H * W * (cw.Cout / 8);
-    const size_t smem = ((size_t)cw.k * cw.k * cw.Cin * cw.Cout + 3 * cw.Cout) * sizeof(float);
+    const size_t smem = ((size_t)cw.k * cw.k * cw.Cin * cw.Cout + 3 * cw.Cout + 16 * cw.Cout) * sizeof(float);
     auto kfn = conv_small_cin_kernel<T>;
     if (e->prof) e->prof_begin("conv_small_cin_kernel");
     kfn<<<grid1d(total, 256, e->num_sms), 256, smem, e->stream>>>(a);
@@ -686,7 +686,7 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
              reinterpret_cast<long long*>(e->tensors[b.i_nbt].data), 0.1f, 1e-5f, b.mean, b.invstd, b.a, b.b);
       if (i < nd - 1 || !blk.has_res) {
         View z = (i == nd - 1) ? out : blk.z[i];
-        LAUNCH(e, (bn_apply_kernel<T>), grid1d(P * (b.C / 4), 256, e->num_sms), 256,
+        LAUNCH(e, (bn_apply_kernel<T>), grid1d(P * (b.C / (int)Vec<T>::N), 256, e->num_sms), 256,
                reinterpret_cast<const T*>(r.p), r.ld, reinterpret_cast<T*>(z.p), z.ld, b.a, b.b, P, b.C);
         cur = z;
       } else {
@@ -1086,6 +1086,7 @@ int validate(const fu_config* c, std::string& why) {
   if (c->lands_block_depth != 0) return bad("lands_block_depth > 0 is not supported");
   if (c->depth < 1 || c->depth > 8) return bad("depth must be in [1,8]");
   if (c->wf < 2 || c->wf + c->depth - 1 > 12) return bad("wf must be >= 2 and 2^(wf+depth-1) <= 4096");
+  if (c->precision == FU_PRECISION_BF16 && c->wf < 3) return bad("throughput mode (bf16) needs wf >= 3 (16-byte channel vectors); use precision='fp32'");
   if (c->in_channels < 1 || c->in_channels > 64) return bad("in_channels must be in [1,64]");
   if (c->n_classes < 1 || c->n_classes > kMaxClasses) return bad("n_classes must be in [1,32]");
   if (c->num_lands < 0 || c->num_lands > 256) return bad("num_lands must be in [0,256]");

@@ -314,17 +314,23 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallCinArgs 
         cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], o);
       }
     }
-    const int lane = threadIdx.x & 31;
-    if (lane < groups || groups > 32) {
-      const int g = groups > 32 ? (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % groups) : lane;
+    // deterministic block reduction (fixed order over the 8 warps): float atomics here would perturb the
+    // BN statistics by ~1e-7 run to run, which bf16 rounding downstream amplifies
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    float* part = sm_s + 2 * p.Cout;            // [8 warps][2*Cout]
+    if (lane < groups) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sm_s[g * 8 + j], cs[j]);
-        atomicAdd(&sm_s[p.Cout + g * 8 + j], cq[j]);
+        part[wrp * 2 * p.Cout + lane * 8 + j] = cs[j];
+        part[wrp * 2 * p.Cout + p.Cout + lane * 8 + j] = cq[j];
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) atomicAdd(&p.stat[i], (double)sm_s[i]);
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) {
+      float v = 0.f;
+      for (int w2 = 0; w2 < 8; ++w2) v += part[w2 * 2 * p.Cout + i];
+      atomicAdd(&p.stat[i], (double)v);
+    }
   }
 }
 
@@ -820,30 +826,70 @@ __global__ void bn_finalize_kernel(const double* stat, long long P, int C, int t
   b_o[c] = beta[c] - mean * a;
 }
 
+// z = a[c]*r + b[c]   (BatchNorm apply with the folded scale / shift)
+template <typename T>
+__global__ void bn_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const float* a, const float* b,
+                                long long P, int C);
+
+// 16-byte vector access per storage type: 4 fp32 or 8 bf16 channels per thread
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const bf16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static __forceinline__ void store(bf16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 template <typename T>
 __global__ void bn_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const float* a, const float* b,
                                 long long P, int C) {
-  const int cv = C >> 2;
+  constexpr int V = Vec<T>::N;
+  const int cv = C / V;
   const long long total = P * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 4;
+    const int c = (int)(i % cv) * V;
     const long long pix = i / cv;
-    float4 v = ld4(r + pix * r_ld + c);
-    const float4 aa = *reinterpret_cast<const float4*>(a + c);
-    const float4 bb = *reinterpret_cast<const float4*>(b + c);
-    v.x = fmaf(aa.x, v.x, bb.x); v.y = fmaf(aa.y, v.y, bb.y);
-    v.z = fmaf(aa.z, v.z, bb.z); v.w = fmaf(aa.w, v.w, bb.w);
-    st4(z + pix * z_ld + c, v);
+    float v[V];
+    Vec<T>::load(r + pix * r_ld + c, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = fmaf(a[c + k], v[k], b[c + k]);
+    Vec<T>::store(z + pix * z_ld + c, v);
   }
 }
 
-// Shared thread mapping of the per-channel reductions: lanes = min(C/4, 256) channel
-// vectors across, 256/lanes pixel rows down; grid.y covers C/4 > 256.
+// Shared thread mapping of the per-channel reductions: lanes = min(C/VEC, 256) channel vectors across,
+// 256/lanes pixel rows down; grid.y covers C/VEC > 256.  (C and VEC are powers of two, C >= VEC.)
+template <int VEC>
 struct RedMap {
   int lanes, rows, cv, prow;
   __device__ RedMap(int C) {
-    const int cvecs = C >> 2;
+    const int cvecs = C / VEC;
     lanes = cvecs < 256 ? cvecs : 256;
     rows = 256 / lanes;
     cv = blockIdx.y * lanes + (threadIdx.x % lanes);
@@ -851,20 +897,23 @@ struct RedMap {
   }
 };
 
-__device__ __forceinline__ void block_channel_reduce(const RedMap& mp, float4 s, double* out, int C,
-                                                     float4* sm) {
-  sm[threadIdx.x] = s;
+// block-level sum over the pixel rows of each channel, then one fp64 atomic per channel per block
+template <int VEC>
+__device__ __forceinline__ void block_channel_reduce(const RedMap<VEC>& mp, const float* s, double* out, int C, float* sm) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sm[threadIdx.x * VEC + i] = s[i];
   __syncthreads();
-  if (mp.prow == 0 && mp.cv * 4 < C) {
-    float4 t = s;
+  if (mp.prow == 0 && mp.cv * VEC < C) {
+    float t[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = s[i];
     for (int r = 1; r < mp.rows; ++r) {
-      const float4 o = sm[r * mp.lanes + (threadIdx.x % mp.lanes)];
-      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      const float* o = sm + (r * mp.lanes + (threadIdx.x % mp.lanes)) * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t[i] += o[i];
     }
-    atomicAdd(out + mp.cv * 4 + 0, (double)t.x);
-    atomicAdd(out + mp.cv * 4 + 1, (double)t.y);
-    atomicAdd(out + mp.cv * 4 + 2, (double)t.z);
-    atomicAdd(out + mp.cv * 4 + 3, (double)t.w);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomicAdd(out + mp.cv * VEC + i, (double)t[i]);
   }
   __syncthreads();
 }
@@ -874,24 +923,38 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* d, int d_ld, const T* r, int r_ld,
                                                             const float* mean, const float* invstd,
                                                             long long P, int C, double* out) {
-  __shared__ float4 sm[256];
-  RedMap mp(C);
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  if (mp.cv * 4 < C) {
-    const int c = mp.cv * 4;
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
-    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
-    for (long long pix = (long long)blockIdx.x * mp.rows + mp.prow; pix < P;
-         pix += (long long)gridDim.x * mp.rows) {
-      const float4 dv = ld4(d + pix * d_ld + c);
-      const float4 rv = ld4(r + pix * r_ld + c);
-      s1.x += dv.x; s1.y += dv.y; s1.z += dv.z; s1.w += dv.w;
-      s2.x += dv.x * (rv.x - mu.x) * is.x; s2.y += dv.y * (rv.y - mu.y) * is.y;
-      s2.z += dv.z * (rv.z - mu.z) * is.z; s2.w += dv.w * (rv.w - mu.w) * is.w;
+  constexpr int V = Vec<T>::N;
+  __shared__ float sm[256 * V];
+  RedMap<V> mp(C);
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  if (mp.cv * V < C) {
+    const int c = mp.cv * V;
+    float mu[V], is[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { mu[i] = mean[c + i]; is[i] = invstd[c + i]; }
+    const long long step = (long long)gridDim.x * mp.rows;
+    long long pix = (long long)blockIdx.x * mp.rows + mp.prow;
+    for (; pix + step < P; pix += 2 * step) {        // two pixels in flight per thread
+      float d0[V], r0[V], d1[V], r1[V];
+      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
+      Vec<T>::load(d + (pix + step) * d_ld + c, d1); Vec<T>::load(r + (pix + step) * r_ld + c, r1);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s1[i] += d0[i] + d1[i];
+        s2[i] += d0[i] * (r0[i] - mu[i]) * is[i] + d1[i] * (r1[i] - mu[i]) * is[i];
+      }
+    }
+    for (; pix < P; pix += step) {
+      float d0[V], r0[V];
+      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s1[i] += d0[i]; s2[i] += d0[i] * (r0[i] - mu[i]) * is[i]; }
     }
   }
-  block_channel_reduce(mp, s1, out, C, sm);
-  block_channel_reduce(mp, s2, out + C, C, sm);
+  block_channel_reduce<V>(mp, s1, out, C, sm);
+  block_channel_reduce<V>(mp, s2, out + C, C, sm);
 }
 
 // bstat -> d(gamma), d(beta) [, d(res bias) = sum d], and the coefficients of the
@@ -917,56 +980,69 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* d, int d_ld, cons
                                                       const float* invstd, const float* ga,
                                                       const float* m1, const float* m2, long long P, int C,
                                                       double* out) {
-  __shared__ float4 sm[256];
-  RedMap mp(C);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (mp.cv * 4 < C) {
-    const int c = mp.cv * 4;
-    float4 mu = s, is = s, g = s, a1 = s, a2 = s;
-    if (has_bn) {
-      mu = *reinterpret_cast<const float4*>(mean + c);
-      is = *reinterpret_cast<const float4*>(invstd + c);
-      g = *reinterpret_cast<const float4*>(ga + c);
-      a1 = *reinterpret_cast<const float4*>(m1 + c);
-      a2 = *reinterpret_cast<const float4*>(m2 + c);
+  constexpr int V = Vec<T>::N;
+  __shared__ float sm[256 * V];
+  RedMap<V> mp(C);
+  float s[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = 0.f;
+  if (mp.cv * V < C) {
+    const int c = mp.cv * V;
+    float mu[V], is[V], g[V], a1[V], a2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      mu[i] = has_bn ? mean[c + i] : 0.f; is[i] = has_bn ? invstd[c + i] : 0.f;
+      g[i] = has_bn ? ga[c + i] : 1.f; a1[i] = has_bn ? m1[c + i] : 0.f; a2[i] = has_bn ? m2[c + i] : 0.f;
     }
-    for (long long pix = (long long)blockIdx.x * mp.rows + mp.prow; pix < P;
-         pix += (long long)gridDim.x * mp.rows) {
-      const float4 dv = ld4(d + pix * d_ld + c);
-      const float4 rv = ld4(r + pix * r_ld + c);
-      float4 o;
-      if (has_bn) {
-        o.x = rv.x > 0.f ? g.x * (dv.x - a1.x - (rv.x - mu.x) * is.x * a2.x) : 0.f;
-        o.y = rv.y > 0.f ? g.y * (dv.y - a1.y - (rv.y - mu.y) * is.y * a2.y) : 0.f;
-        o.z = rv.z > 0.f ? g.z * (dv.z - a1.z - (rv.z - mu.z) * is.z * a2.z) : 0.f;
-        o.w = rv.w > 0.f ? g.w * (dv.w - a1.w - (rv.w - mu.w) * is.w * a2.w) : 0.f;
-      } else {
-        o.x = rv.x > 0.f ? dv.x : 0.f; o.y = rv.y > 0.f ? dv.y : 0.f;
-        o.z = rv.z > 0.f ? dv.z : 0.f; o.w = rv.w > 0.f ? dv.w : 0.f;
+    const long long step = (long long)gridDim.x * mp.rows;
+    long long pix = (long long)blockIdx.x * mp.rows + mp.prow;
+    auto one = [&](const float* dv, const float* rv, T* dst) {
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        // (with has_bn == 0: g = 1, a1 = a2 = 0 -> o = d where r > 0)
+        o[i] = rv[i] > 0.f ? g[i] * (dv[i] - a1[i] - (rv[i] - mu[i]) * is[i] * a2[i]) : 0.f;
       }
-      T* dst = dy + pix * dy_ld + c;
-      st4(dst, o);
-      s.x += rnd(o.x, dst); s.y += rnd(o.y, dst); s.z += rnd(o.z, dst); s.w += rnd(o.w, dst);
+      Vec<T>::store(dst, o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += rnd(o[i], dst);
+    };
+    for (; pix + step < P; pix += 2 * step) {
+      float d0[V], r0[V], d1[V], r1[V];
+      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
+      Vec<T>::load(d + (pix + step) * d_ld + c, d1); Vec<T>::load(r + (pix + step) * r_ld + c, r1);
+      one(d0, r0, dy + pix * dy_ld + c);
+      one(d1, r1, dy + (pix + step) * dy_ld + c);
+    }
+    for (; pix < P; pix += step) {
+      float d0[V], r0[V];
+      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
+      one(d0, r0, dy + pix * dy_ld + c);
     }
   }
-  block_channel_reduce(mp, s, out, C, sm);
+  block_channel_reduce<V>(mp, s, out, C, sm);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* d, int d_ld, long long P, int C,
                                                           double* out) {
-  __shared__ float4 sm[256];
-  RedMap mp(C);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (mp.cv * 4 < C) {
-    const int c = mp.cv * 4;
+  constexpr int V = Vec<T>::N;
+  __shared__ float sm[256 * V];
+  RedMap<V> mp(C);
+  float s[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = 0.f;
+  if (mp.cv * V < C) {
+    const int c = mp.cv * V;
     for (long long pix = (long long)blockIdx.x * mp.rows + mp.prow; pix < P;
          pix += (long long)gridDim.x * mp.rows) {
-      const float4 dv = ld4(d + pix * d_ld + c);
-      s.x += dv.x; s.y += dv.y; s.z += dv.z; s.w += dv.w;
+      float dv[V];
+      Vec<T>::load(d + pix * d_ld + c, dv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += dv[i];
     }
   }
-  block_channel_reduce(mp, s, out, C, sm);
+  block_channel_reduce<V>(mp, s, out, C, sm);
 }
 
 __global__ void sum_to_float_kernel(const double* src, float* dst, int C) {

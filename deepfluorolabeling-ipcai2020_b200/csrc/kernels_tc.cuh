@@ -770,17 +770,24 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int cp = et % cpairs, rg = et / cpairs;
       float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
       int s_nb = -1;
+      // Deterministic flush: every (column pair, row group) thread parks its partial sums in the (idle)
+      // staging tile, then one thread per column adds the row groups in a fixed order.  Float atomics here
+      // would make BN statistics differ by ~1e-7 run to run, which bf16 rounding + the network amplify into
+      // visibly different gradients (tools/diag_repeat2.py).
       auto flush_stats = [&]() {
         if (p.stat && s_nb >= 0) {
-          for (int i = et; i < 2 * p.BN; i += 128) gstat[i] = 0.f;
+          float* park = reinterpret_cast<float*>(staging);        // [rgroups][2][BN] floats <= 128*BN*2 bytes
+          const int rgroups = 128 / cpairs;
           ptx::named_bar_sync(bar_id, 128);
-          atomicAdd(&gstat[2 * cp], s0); atomicAdd(&gstat[2 * cp + 1], s1);
-          atomicAdd(&gstat[p.BN + 2 * cp], q0); atomicAdd(&gstat[p.BN + 2 * cp + 1], q1);
+          park[(rg * 2 + 0) * p.BN + 2 * cp] = s0; park[(rg * 2 + 0) * p.BN + 2 * cp + 1] = s1;
+          park[(rg * 2 + 1) * p.BN + 2 * cp] = q0; park[(rg * 2 + 1) * p.BN + 2 * cp + 1] = q1;
           s0 = s1 = q0 = q1 = 0.f;
           ptx::named_bar_sync(bar_id, 128);
           for (int i = et; i < 2 * p.BN; i += 128) {
             const int which = i / p.BN, c = i - which * p.BN;
-            atomicAdd(p.stat + which * p.N + s_nb + c, (double)gstat[i]);
+            float v = 0.f;
+            for (int r = 0; r < rgroups; ++r) v += park[(r * 2 + which) * p.BN + c];
+            atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
           }
           ptx::named_bar_sync(bar_id, 128);
         }
@@ -1391,7 +1398,7 @@ inline bool tc_use_v2(const TcConv& t, int H, int W) {
 inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
   long long best = -1;
   twb = 16; th = 8;
-  for (int a = 8; a <= 130; a += (halo1 ? 1 : 8)) {
+  for (int a = 8; a <= 66; a += (halo1 ? 1 : 8)) {
     int b = 128 / a;
     if (b > H) b = H;
     if (b < 1) continue;
@@ -1538,11 +1545,12 @@ inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld
                            int accumulate, cudaStream_t stream, fu_counters* cnt) {
   if (tc_use_v2(t, H, W)) {
     TcConv::Cached3* c3 = tc_prepare3(t, 0, x, x_ld, y, y_ld, B, H, W);
-    if (!c3) return -1;
-    c3->p.bias = bias; c3->p.relu = relu; c3->p.stat = stat;
-    c3->p.t = reinterpret_cast<const bf16*>(tp); c3->p.t_ld = t_ld; c3->p.bn_a = bn_a; c3->p.bn_b = bn_b;
-    if (accumulate) { c3->p.t = reinterpret_cast<const bf16*>(y); c3->p.t_ld = y_ld; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr; }
-    return tc_launch3(c3, stream, cnt);
+    if (c3) {
+      c3->p.bias = bias; c3->p.relu = relu; c3->p.stat = stat;
+      c3->p.t = reinterpret_cast<const bf16*>(tp); c3->p.t_ld = t_ld; c3->p.bn_a = bn_a; c3->p.bn_b = bn_b;
+      if (accumulate) { c3->p.t = reinterpret_cast<const bf16*>(y); c3->p.t_ld = y_ld; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr; }
+      return tc_launch3(c3, stream, cnt);
+    }   // else: the halo configuration does not fit shared memory for this shape -> first-generation kernel
   }
   TcConv::Cached* c = tc_prepare(t, 0, x, x_ld, y, y_ld, B, H, W);
   if (!c) return -1;
@@ -1560,10 +1568,11 @@ inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_
                          cudaStream_t stream, fu_counters* cnt) {
   if (tc_use_v2(t, H, W)) {
     TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
-    if (!c3) return -1;
-    c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = nullptr; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
-    c3->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c3->p.t_ld = dx_ld;
-    return tc_launch3(c3, stream, cnt);
+    if (c3) {
+      c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = nullptr; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
+      c3->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c3->p.t_ld = dx_ld;
+      return tc_launch3(c3, stream, cnt);
+    }
   }
   TcConv::Cached* c = tc_prepare(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
   if (!c) return -1;

@@ -110,6 +110,8 @@ class UNet(nn.Module):
             precision = os.environ.get("FLUORO_UNET_PRECISION", "fp32")
         if precision not in _capi.PRECISION:
             raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision == "bf16" and wf < 3:
+            raise ValueError("throughput mode (bf16) needs wf >= 3 (16-byte channel vectors); use precision='fp32'")
         self.padding = padding
         self.pad_mode = pad_mode
         self.depth = depth

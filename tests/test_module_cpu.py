@@ -64,7 +64,7 @@ def test_default_init_is_rng_identical_to_reference(pkg):
 
 @pytest.mark.parametrize("kw", [dict(padding=False), dict(padding=True, pad_mode="circular"),
                                 dict(padding=True, up_mode="upsample"), dict(padding=True, lands_block_depth=1),
-                                dict(padding=True, precision="fp8")])
+                                dict(padding=True, precision="fp8"), dict(padding=True, precision="bf16", wf=2)])
 def test_unsupported_configs_are_rejected(pkg, kw):
     with pytest.raises(ValueError):
         pkg.UNet(**kw)
