@@ -1050,6 +1050,171 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+// ===========================================================================
+// weight gradient of the 3x3 convolutions, second generation (levels with W >= 32).
+// K tiles are single image-row segments of tw pixels.  The dY tile (A, M = out-channels) is loaded once per
+// stage and the X operand (B, N = in-channels) comes from ONE halo box of (tw+2) x nrows pixels; tap (kh,kw)
+// is that tile read from row (kh-kh0)*(tw+2)+kw on (a start-address shift of the MN-major descriptor: the
+// pixel rows are the K dimension, and a single image row never wraps, so no garbage enters the reduction).
+// Thin layers (Cin = 32) use 32-channel / 64-byte boxes so all nine taps (9 x 32 columns) fit one CTA's
+// TMEM; wider layers keep one filter row (3 taps) per CTA.
+// ===========================================================================
+struct TcWgrad3Params {
+  int B, H, W, Cin, Cout;
+  int tw, segs;                 // K pixels per stage (32/48/64), row segments per image row
+  int N, cb;                    // in-channel tile (32/64/128) and channels per B box (32 -> SW64, 64 -> SW128)
+  int tpg, groups;              // taps per CTA (9 or 3) and tap groups (1 or 3)
+  int co_tiles, ci_tiles, splits, stages;
+  unsigned b_stage_bytes;       // bytes of the B region of one stage
+  float* dw_acc;                // [9][Cout][Cin] fp32, zeroed by the caller
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const TcWgrad3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kABox = 64u * 128u;                   // room for 64 pixels x 64 channels
+  const uint32_t a_bytes = 2u * kABox;
+  const uint32_t brow = (uint32_t)p.cb * 2u;                // bytes per pixel row of a B box
+  const int nrows = p.tpg == 9 ? 3 : 1;                     // halo rows held per stage
+  const int nblk_b = p.N / p.cb;
+  const uint32_t b_box_bytes = ((uint32_t)((p.tw + 2) * nrows) * brow + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + p.b_stage_bytes;
+  const uint32_t bar_off = (uint32_t)p.stages * stage_bytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kTcMaxStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (uint32_t)(2 * kTcMaxStages);
+  const uint32_t slot_addr = bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 1);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * kTcMaxStages + 1));
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(p.tpg * p.N)) tmem_cols <<= 1;
+
+  int bid = blockIdx.x;
+  const int split = bid % p.splits; bid /= p.splits;
+  const int grp = bid % p.groups; bid /= p.groups;
+  const int ci_t = bid % p.ci_tiles;
+  const int co_t = bid / p.ci_tiles;
+  const int co0 = co_t * 128, ci0 = ci_t * p.N;
+  const int total_kt = p.B * p.H * p.segs;
+  const int per = (total_kt + p.splits - 1) / p.splits;
+  const int kt_begin = split * per;
+  const int kt_end = min(total_kt, kt_begin + per);
+  const int n_iters = max(kt_end - kt_begin, 0);
+  const int nblk_a = (p.Cout - co0 > 64) ? 2 : 1;
+  const int kh0 = p.tpg == 9 ? 0 : grp;                     // first filter row held by this CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmX);
+  }
+  if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t a_tx = (uint32_t)nblk_a * (uint32_t)p.tw * 128u;
+    const uint32_t b_tx = (uint32_t)nblk_b * (uint32_t)((p.tw + 2) * nrows) * brow;
+    for (int it = 0; it < n_iters; ++it) {
+      int kt = kt_begin + it;
+      const int w0 = (kt % p.segs) * p.tw; kt /= p.segs;
+      const int h = kt % p.H;
+      const int n = kt / p.H;
+      ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (ptx::elect_one()) {
+        const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+        ptx::mbar_expect_tx(full_bar(stage), a_tx + b_tx);
+        for (int blk = 0; blk < nblk_a; ++blk)
+          ptx::tma_load_4d(a_dst + (uint32_t)blk * kABox, &tmY, full_bar(stage), co0 + blk * 64, w0, h, n);
+        for (int blk = 0; blk < nblk_b; ++blk)
+          ptx::tma_load_4d(a_dst + a_bytes + (uint32_t)blk * b_box_bytes, &tmX, full_bar(stage), ci0 + blk * p.cb, w0 - 1,
+                           h - 1 + kh0, n);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N);
+    const uint64_t da = umma_desc_mnmajor(0, kABox, 1024u);                       // A: 64-channel SW128 blocks
+    uint64_t db;                                                                   // B: SW128 or SW64 blocks
+    {
+      uint64_t d = 0;
+      d |= (uint64_t)((b_box_bytes >> 4) & 0x3FFF) << 16;                          // LBO: next channel block
+      d |= (uint64_t)(((8u * brow) >> 4) & 0x3FFF) << 32;                          // SBO: next 8 pixel rows
+      d |= (uint64_t)1 << 46;
+      d |= (uint64_t)(p.cb == 64 ? 2 : 4) << 61;
+      db = d;
+    }
+    const int ksteps = p.tw / 16;
+    const int tpg = p.tpg, Nn = p.N;
+    const uint32_t step_a16 = (16u * 128u) >> 4, step_b16 = (16u * brow) >> 4;
+    uint32_t tapoff16[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int kh = tpg == 9 ? t / 3 : 0, kw = tpg == 9 ? t % 3 : t;
+      tapoff16[t] = ((uint32_t)(kh * (p.tw + 2) + kw) * brow) >> 4;
+    }
+    for (int it = 0; it < n_iters; ++it) {
+      ptx::mbar_wait(full_bar(stage), phase);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+        const uint64_t ad0 = da + (uint64_t)(a_addr >> 4);
+        const uint64_t bd0 = db + (uint64_t)((a_addr + a_bytes) >> 4);
+        const uint32_t accum = it != 0 ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if (t < tpg) {
+            const uint32_t d_t = tmem_base + (uint32_t)(t * Nn);
+            for (int ks = 0; ks < ksteps; ++ks)
+              ptx::umma_bf16(d_t, ad0 + (uint64_t)(ks * step_a16), bd0 + (uint64_t)(tapoff16[t] + ks * step_b16), idesc,
+                             accum | (uint32_t)ks);
+          }
+        }
+        ptx::umma_commit(empty_bar(stage));
+        if (it == n_iters - 1) ptx::umma_commit(done_bar);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (n_iters > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int co = co0 + row;
+    ptx::mbar_wait(done_bar, 0);
+    ptx::tc_fence_after();
+    for (int t = 0; t < p.tpg; ++t) {
+      const int tap = p.tpg == 9 ? t : grp * 3 + t;
+      for (int j = 0; j < p.N / 32; ++j) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + (uint32_t)(t * p.N + j * 32) + ((uint32_t)(q * 32) << 16), v);
+        ptx::tmem_ld_wait();
+        const int ci = ci0 + j * 32;
+        if (co < p.Cout && ci < p.Cin) {
+          float* dst = p.dw_acc + ((long long)tap * p.Cout + co) * p.Cin + ci;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + i),
+                      make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                  __uint_as_float(v[i + 3])));
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
 // [taps][Cout][Cin] fp32 accumulator -> torch layout (Cout,Cin,k,k)
 __global__ void tc_wgrad_unpack_kernel(const float* acc, float* dw, int Cout, int Cin, int taps) {
   const long long total = (long long)Cout * Cin * taps;
@@ -1183,6 +1348,11 @@ struct TcConv {
     CUtensorMap y, xm; TcWgradParams p; int grid; size_t smem;
   };
   std::vector<WCached> wcache;
+  struct W3Cached {
+    const void *x, *dy; int x_ld, dy_ld, B, H, W;
+    CUtensorMap y, xm; TcWgrad3Params p; int grid; size_t smem;
+  };
+  std::vector<W3Cached> w3cache;
   struct Cached3 {
     const void *x, *y; int x_ld, y_ld, B, H, W, dir;
     CUtensorMap a, b, c; TcConv3Params p; int grid; size_t smem;
@@ -1219,6 +1389,7 @@ inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool 
   t.cache.clear();
   t.cache3.clear();
   t.wcache.clear();
+  t.w3cache.clear();
 }
 
 inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* cnt) {
@@ -1719,9 +1890,90 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
   return 0;
 }
 
+// halo weight-gradient kernel (3x3, W >= 32)
+inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld, int B, int H, int W, float* dw,
+                     cudaStream_t stream, fu_counters* cnt) {
+  TcConv::W3Cached* c = nullptr;
+  for (auto& k : t.w3cache)
+    if (k.x == x && k.dy == dy && k.x_ld == x_ld && k.dy_ld == dy_ld && k.B == B && k.H == H && k.W == W) { c = &k; break; }
+  if (!c) {
+    TcConv::W3Cached n;
+    memset(&n, 0, sizeof(n));
+    n.x = x; n.dy = dy; n.x_ld = x_ld; n.dy_ld = dy_ld; n.B = B; n.H = H; n.W = W;
+    TcWgrad3Params& p = n.p;
+    p.B = B; p.H = H; p.W = W; p.Cin = t.Cin; p.Cout = t.Cout;
+    // K pixels per stage: the multiple of 16 in {64,48,32} that wastes the fewest pixels per row
+    int best_tw = 64; long long best_cost = -1;
+    for (int tw = 64; tw >= 32; tw -= 16) {
+      const long long cost = (long long)((W + tw - 1) / tw) * tw;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
+    }
+    p.tw = best_tw; p.segs = (W + p.tw - 1) / p.tw;
+    if (t.Cin <= 32) { p.N = 32; p.cb = 32; p.tpg = 9; p.groups = 1; }
+    else { p.N = t.Cin > 64 ? 128 : 64; p.cb = 64; p.tpg = 3; p.groups = 3; }
+    const int nrows = p.tpg == 9 ? 3 : 1;
+    const size_t b_box = ((size_t)(p.tw + 2) * nrows * p.cb * 2 + 1023) / 1024 * 1024;
+    p.b_stage_bytes = (unsigned)(b_box * (p.N / p.cb));
+    p.co_tiles = (t.Cout + 127) / 128; p.ci_tiles = (t.Cin + p.N - 1) / p.N;
+    const size_t stage_bytes = 2 * 8192 + p.b_stage_bytes;
+    const size_t fixed = 1024 + 8 * (2 * kTcMaxStages + 4);
+    int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+    if (stages > kTcMaxStages) stages = kTcMaxStages;
+    p.stages = stages;
+    n.smem = fixed + (size_t)stages * stage_bytes;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
+    const long long total_kt = (long long)B * H * p.segs;
+    long long splits = (2ll * sms + units - 1) / units;
+    const long long max_splits = (total_kt + 7) / 8;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const long long per = (total_kt + splits - 1) / splits;
+    splits = (total_kt + per - 1) / per;
+    p.splits = (int)splits;
+    n.grid = (int)(units * splits);
+    p.dw_acc = t.dw_acc;
+    {
+      long long dims[4] = {t.Cout, W, H, B};
+      long long str[4] = {1, dy_ld, (long long)W * dy_ld, (long long)H * W * dy_ld};
+      int box[4] = {64, p.tw, 1, 1};
+      if (tc_make_map(&n.y, dy, 4, dims, str, box, 128)) return -1;
+    }
+    {
+      long long dims[4] = {t.Cin, W, H, B};
+      long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
+      int box[4] = {p.cb, p.tw + 2, nrows, 1};
+      if (tc_make_map(&n.xm, x, 4, dims, str, box, p.cb * 2)) return -1;
+    }
+    t.w3cache.push_back(n);
+    c = &t.w3cache.back();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      tc_err() = "cudaFuncSetAttribute(max dynamic smem, wgrad3) failed";
+      return -1;
+    }
+    attr_set = true;
+  }
+  tc_wgrad3_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
+  const long long total = (long long)t.Cout * t.Cin * 9;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  tc_wgrad_unpack_kernel<<<(unsigned)g, 256, 0, stream>>>(t.dw_acc, dw, t.Cout, t.Cin, 9);
+  if (cnt) { cnt->kernel_launches += 2; cnt->tc_kernel_launches++; }
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
 // Conv2d 3x3 / 1x1: x, dy on the same (B,H,W) grid
 inline int tc_conv_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int dy_ld, int B, int H, int W, float* dw,
                          cudaStream_t stream, fu_counters* cnt) {
+  if (t.kind == 0 && t.k == 3 && W >= tc_env_int("FU_TC_W3_MINW", 32) && tc_env_int("FU_TC_W3", 1))
+    return tc_wgrad3(t, x, x_ld, dy, dy_ld, B, H, W, dw, stream, cnt);
   return tc_wgrad_common(t, dy, dy_ld, t.Cout, x, x_ld, t.Cin, 0, t.k, B, H, W, dw, stream, cnt);
 }
 // Conv2d 2x2/s2: x (B,H,W,Cin) fine, dy (B,H/2,W/2,Cout) coarse -> dw (Cout,Cin,2,2)

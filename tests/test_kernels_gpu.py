@@ -201,6 +201,8 @@ HALO_SHAPES = [  # B, Cin, Cout, H, W  -- 3x3 convs wide enough for the halo ker
     (3, 64, 32, 26, 70),
     (1, 256, 256, 24, 24),    # two N tiles
     (5, 64, 64, 24, 24),      # odd number of pixel tiles (last pair half empty)
+    (2, 32, 64, 20, 96),      # weight gradient: 48-pixel K tiles, nine taps per CTA (Cin = 32)
+    (1, 128, 64, 12, 192),    # weight gradient: 64-pixel K tiles, 128-channel B tiles
 ]
 
 
@@ -222,6 +224,7 @@ def test_tc_halo_conv_fwd_dgrad(pkg, shape, env):
     try:
         y, stats = run_conv(pkg, 1, 1, 0, x, w, b, None, 3, 1, 1, relu=1, want_stats=True)
         dx = run_conv(pkg, 1, 1, 1, x, w, None, dy, 3, 1, 1)
+        dw = run_conv(pkg, 1, 1, 2, x, w, None, dy, 3, 1, 1)       # halo weight-gradient kernel when W >= 32
     finally:
         for k, v in old.items():
             if v is None:
@@ -233,3 +236,4 @@ def test_tc_halo_conv_fwd_dgrad(pkg, shape, env):
     assert rel_l2(stats[:Cout], y.double().sum(dim=(0, 2, 3))) < 1e-4
     assert rel_l2(stats[Cout:], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
     assert rel_l2(dx, torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=1)) < 6e-3
+    assert rel_l2(dw, torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=1)) < 1e-4
