@@ -109,6 +109,8 @@ struct fu_engine {
   cudaStream_t stream = nullptr;
   int num_sms = 148;
   // optional per-launch CUDA-event profiling (fu_profile_enable)
+  struct DeferredSum { const double* src; float* dst; int n; };
+  std::vector<DeferredSum> deferred_sums;
   bool prof = false;
   struct ProfRec { std::string tag; const char* kern; cudaEvent_t a, b; double flops, bytes; };
   std::vector<ProfRec> prof_recs;
@@ -681,15 +683,22 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
     if (bn) {
       BNL& b = blk.bns[i];
       e->set_tag(0, 2.0 * P * b.C * e->esz, "bn_fwd %dx%d C%d", H, W, b.C);
-      LAUNCH(e, bn_finalize_kernel, (b.C + 127) / 128, 128, b.stat, P, b.C, training, tdata(e, b.i_gamma),
-             tdata(e, b.i_beta), tdata(e, b.i_rm), tdata(e, b.i_rv),
-             reinterpret_cast<long long*>(e->tensors[b.i_nbt].data), 0.1f, 1e-5f, b.mean, b.invstd, b.a, b.b);
       if (i < nd - 1 || !blk.has_res) {
+        // finalise + apply in one launch
         View z = (i == nd - 1) ? out : blk.z[i];
-        LAUNCH(e, (bn_apply_kernel<T>), grid1d(P * (b.C / (int)Vec<T>::N), 256, e->num_sms), 256,
-               reinterpret_cast<const T*>(r.p), r.ld, reinterpret_cast<T*>(z.p), z.ld, b.a, b.b, P, b.C);
+        BnFwdFin f;
+        f.stat = b.stat; f.gamma = tdata(e, b.i_gamma); f.beta = tdata(e, b.i_beta); f.rmean = tdata(e, b.i_rm);
+        f.rvar = tdata(e, b.i_rv); f.nbt = reinterpret_cast<long long*>(e->tensors[b.i_nbt].data);
+        f.mean_o = b.mean; f.invstd_o = b.invstd; f.a_o = b.a; f.b_o = b.b; f.training = training;
+        f.momentum = 0.1f; f.eps = 1e-5f;
+        LAUNCH(e, (bn_finalize_apply_kernel<T>), red_grid(e, P, b.C).x, 256, reinterpret_cast<const T*>(r.p), r.ld,
+               reinterpret_cast<T*>(z.p), z.ld, f, P, b.C);
         cur = z;
       } else {
+        // the last BN of a residual block is applied inside the residual conv's epilogue
+        LAUNCH(e, bn_finalize_kernel, (b.C + 127) / 128, 128, b.stat, P, b.C, training, tdata(e, b.i_gamma),
+               tdata(e, b.i_beta), tdata(e, b.i_rm), tdata(e, b.i_rv),
+               reinterpret_cast<long long*>(e->tensors[b.i_nbt].data), 0.1f, 1e-5f, b.mean, b.invstd, b.a, b.b);
         cur = r;
       }
     } else {
@@ -822,7 +831,26 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
 template <typename T>
 int channel_sum_to(fu_engine* e, const View& d, long long P, double* scratch, float* dst) {
   LAUNCH(e, (channel_sum_kernel<T>), red_grid(e, P, d.C), 256, reinterpret_cast<const T*>(d.p), d.ld, P, d.C, scratch);
-  LAUNCH(e, sum_to_float_kernel, (d.C + 127) / 128, 128, scratch, dst, d.C);
+  e->deferred_sums.push_back({scratch, dst, d.C});     // converted to fp32 by one launch at the end of backward
+  return FU_OK;
+}
+
+int flush_deferred_sums(fu_engine* e) {
+  size_t i = 0;
+  while (i < e->deferred_sums.size()) {
+    SumTable t;
+    t.count = 0;
+    int maxn = 1;
+    for (; i < e->deferred_sums.size() && t.count < SumTable::kMax; ++i) {
+      t.src[t.count] = e->deferred_sums[i].src; t.dst[t.count] = e->deferred_sums[i].dst;
+      t.n[t.count] = e->deferred_sums[i].n;
+      if (e->deferred_sums[i].n > maxn) maxn = e->deferred_sums[i].n;
+      ++t.count;
+    }
+    e->set_tag(0, 0, "bias_grads");
+    LAUNCH(e, sums_to_float_kernel, t.count, maxn < 256 ? 128 : 256, t);
+  }
+  e->deferred_sums.clear();
   return FU_OK;
 }
 
@@ -908,18 +936,21 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
       BNL& b = blk.bns[i];
       LAUNCH(e, (bn_bwd_reduce_kernel<T>), red_grid(e, P, b.C), 256, dp, d.ld, reinterpret_cast<const T*>(r.p),
              r.ld, b.mean, b.invstd, P, b.C, b.bstat);
-      float* g_extra = (i == nd - 1 && blk.has_res) ? gptr(e, flat, blk.res.b_idx) : nullptr;
-      LAUNCH(e, bn_bwd_finalize_kernel, (b.C + 127) / 128, 128, b.bstat, P, b.C, training, tdata(e, b.i_gamma),
-             b.invstd, gptr(e, flat, b.i_gamma), gptr(e, flat, b.i_beta), g_extra, b.ga, b.m1, b.m2);
+      BnBwdFin fin;
+      fin.bstat = b.bstat; fin.gamma = tdata(e, b.i_gamma); fin.g_gamma = gptr(e, flat, b.i_gamma);
+      fin.g_beta = gptr(e, flat, b.i_beta);
+      fin.g_extra = (i == nd - 1 && blk.has_res) ? gptr(e, flat, blk.res.b_idx) : nullptr;
+      fin.training = training;
       LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, b.C), 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
-             reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, 1, b.mean, b.invstd, b.ga, b.m1, b.m2, P, b.C,
-             cw.bsum);
+             reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, 1, b.mean, b.invstd, fin, P, b.C, cw.bsum);
     } else {
+      BnBwdFin fin;
+      memset(&fin, 0, sizeof(fin));
       LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, blk.C), 256, dp, d.ld,
              reinterpret_cast<const T*>(blk.r[i].p), blk.r[i].ld, reinterpret_cast<T*>(blk.dy[i].p),
-             blk.dy[i].ld, 0, nullptr, nullptr, nullptr, nullptr, nullptr, P, blk.C, cw.bsum);
+             blk.dy[i].ld, 0, nullptr, nullptr, fin, P, blk.C, cw.bsum);
     }
-    LAUNCH(e, sum_to_float_kernel, (blk.C + 127) / 128, 128, cw.bsum, gptr(e, flat, cw.b_idx), blk.C);
+    e->deferred_sums.push_back({cw.bsum, gptr(e, flat, cw.b_idx), blk.C});
     View conv_in = (i == 0) ? x_in : (bn ? blk.z[i - 1] : blk.r[i - 1]);
     if ((rc = conv_wgrad<T>(e, cw, conv_in, blk.dy[i], B, H, W, gptr(e, flat, cw.w_idx)))) return rc;
     if (i > 0) {
@@ -942,6 +973,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   const long long HW = (long long)H * W, P0 = (long long)B * HW;
   const int training = e->saved_training;
   int rc;
+  e->deferred_sums.clear();
   CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
   CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
   if (e->cfg.precision == FU_PRECISION_BF16 && e->wgrad_scr_bytes > 512)
@@ -1074,7 +1106,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
       }
     }
   }
-  return FU_OK;
+  return flush_deferred_sums(e);
 }
 
 int validate(const fu_config* c, std::string& why) {

@@ -830,6 +830,16 @@ __global__ void bn_finalize_kernel(const double* stat, long long P, int C, int t
 template <typename T>
 __global__ void bn_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const float* a, const float* b,
                                 long long P, int C);
+// BatchNorm forward finalise + apply in one launch: every thread derives mean / invstd / scale / shift of its
+// channels from stat = [sum x | sum x^2] (train) or the running statistics (eval); block 0 also publishes
+// mean / invstd (needed by the backward), and in training updates running_mean / running_var / num_batches_tracked.
+struct BnFwdFin {
+  const double* stat; const float* gamma; const float* beta; float* rmean; float* rvar; long long* nbt;
+  float* mean_o; float* invstd_o; float* a_o; float* b_o; int training; float momentum, eps;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const BnFwdFin f,
+                                                                long long P, int C);
 
 // 16-byte vector access per storage type: 4 fp32 or 8 bf16 channels per thread
 template <typename T> struct Vec;
@@ -880,6 +890,59 @@ __global__ void bn_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const floa
 #pragma unroll
     for (int k = 0; k < V; ++k) v[k] = fmaf(a[c + k], v[k], b[c + k]);
     Vec<T>::store(z + pix * z_ld + c, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const BnFwdFin f,
+                                                                long long P, int C) {
+  constexpr int V = Vec<T>::N;
+  const int cvecs = C / V;
+  const int lanes = cvecs < 256 ? cvecs : 256;
+  const int rows = 256 / lanes;
+  const int lane_c = threadIdx.x % lanes, prow = threadIdx.x / lanes;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && f.training && f.nbt) *f.nbt += 1;
+  for (int cv = lane_c; cv < cvecs; cv += lanes) {
+    const int c = cv * V;
+    float a[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float mean, var;
+      double unb = 0.0;
+      if (f.training) {
+        const double m = f.stat[c + i] / (double)P;
+        double v = f.stat[C + c + i] / (double)P - m * m;
+        if (v < 0.0) v = 0.0;
+        mean = (float)m; var = (float)v;
+        unb = P > 1 ? v * ((double)P / (double)(P - 1)) : v;
+      } else {
+        mean = f.rmean[c + i]; var = f.rvar[c + i];
+      }
+      const float invstd = rsqrtf(var + f.eps);
+      a[i] = f.gamma[c + i] * invstd;
+      b[i] = f.beta[c + i] - mean * a[i];
+      if (blockIdx.x == 0 && prow == 0) {
+        f.mean_o[c + i] = mean; f.invstd_o[c + i] = invstd; f.a_o[c + i] = a[i]; f.b_o[c + i] = b[i];
+      }
+    }
+    for (long long pix = (long long)blockIdx.x * rows + prow; pix < P; pix += (long long)gridDim.x * rows) {
+      float v[V];
+      Vec<T>::load(r + pix * r_ld + c, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = fmaf(a[i], v[i], b[i]);
+      Vec<T>::store(z + pix * z_ld + c, v);
+    }
+  }
+  // running statistics: after every block has read them (eval never writes; train never reads them above)
+  if (blockIdx.x == 0 && f.training) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double m = f.stat[c] / (double)P;
+      double v = f.stat[C + c] / (double)P - m * m;
+      if (v < 0.0) v = 0.0;
+      const double unb = P > 1 ? v * ((double)P / (double)(P - 1)) : v;
+      f.rmean[c] = (1.f - f.momentum) * f.rmean[c] + f.momentum * (float)m;
+      f.rvar[c] = (1.f - f.momentum) * f.rvar[c] + f.momentum * (float)unb;
+    }
   }
 }
 
@@ -973,12 +1036,17 @@ __global__ void bn_bwd_finalize_kernel(const double* bstat, long long P, int C, 
   m2[c] = training ? (float)(s2 / (double)P) : 0.f;
 }
 
-// dy = relu'(r) * (has_bn ? ga*(d - m1 - xhat*m2) : d); out[0:C] += sum dy  (= conv bias gradient)
+// dy = relu'(r) * (has_bn ? ga*(d - m1 - xhat*m2) : d); out[0:C] += sum dy  (= conv bias gradient).
+// With has_bn the kernel finalises the BN backward itself from bstat = [sum d | sum d*xhat] (written by
+// bn_bwd_reduce_kernel): ga = gamma*invstd, m1 = mean(d), m2 = mean(d*xhat) (0 in eval mode); block (0,y)
+// also stores d(gamma) = sum d*xhat, d(beta) = sum d [and d(res bias) = sum d].
+struct BnBwdFin {
+  const double* bstat; const float* gamma; float* g_gamma; float* g_beta; float* g_extra; int training;
+};
 template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const T* d, int d_ld, const T* r, int r_ld,
                                                       T* dy, int dy_ld, int has_bn, const float* mean,
-                                                      const float* invstd, const float* ga,
-                                                      const float* m1, const float* m2, long long P, int C,
+                                                      const float* invstd, const BnBwdFin fin, long long P, int C,
                                                       double* out) {
   constexpr int V = Vec<T>::N;
   __shared__ float sm[256 * V];
@@ -992,7 +1060,18 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* d, int d_ld, cons
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       mu[i] = has_bn ? mean[c + i] : 0.f; is[i] = has_bn ? invstd[c + i] : 0.f;
-      g[i] = has_bn ? ga[c + i] : 1.f; a1[i] = has_bn ? m1[c + i] : 0.f; a2[i] = has_bn ? m2[c + i] : 0.f;
+      g[i] = 1.f; a1[i] = 0.f; a2[i] = 0.f;
+      if (has_bn) {
+        const double s1 = fin.bstat[c + i], s2 = fin.bstat[C + c + i];
+        g[i] = fin.gamma[c + i] * is[i];
+        a1[i] = fin.training ? (float)(s1 / (double)P) : 0.f;
+        a2[i] = fin.training ? (float)(s2 / (double)P) : 0.f;
+        if (blockIdx.x == 0 && mp.prow == 0) {
+          fin.g_gamma[c + i] = (float)s2;
+          fin.g_beta[c + i] = (float)s1;
+          if (fin.g_extra) fin.g_extra[c + i] = (float)s1;
+        }
+      }
     }
     const long long step = (long long)gridDim.x * mp.rows;
     long long pix = (long long)blockIdx.x * mp.rows + mp.prow;
@@ -1043,6 +1122,17 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* d, int d_ld, 
     }
   }
   block_channel_reduce<V>(mp, s, out, C, sm);
+}
+
+// all bias-gradient accumulators of a backward pass -> fp32 gradients, one launch
+struct SumTable {
+  enum { kMax = 96 };
+  const double* src[kMax]; float* dst[kMax]; int n[kMax]; int count;
+};
+__global__ void sums_to_float_kernel(const SumTable t) {
+  const int e = blockIdx.x;
+  if (e >= t.count) return;
+  for (int i = threadIdx.x; i < t.n[e]; i += blockDim.x) t.dst[e][i] = (float)t.src[e][i];
 }
 
 __global__ void sum_to_float_kernel(const double* src, float* dst, int C) {

@@ -216,6 +216,7 @@ struct TcConvParams {
   double* stat;                 // optional [2N]: per-channel sum / sum of squares of the stored values
   // 2x2/stride-2 variants (Conv2d(C,C,2,2) and ConvTranspose2d(.,.,2,2), unet.py:93,240): the pixel grid
   // is (W, H = B*rows) with B = 1 (image rows merged; no padding so tiles may span images)
+  int nstaging;                 // staging tiles for the TMA store (2 = double buffered)
   int a5;                       // A operand gathered with stride 2: 5-D map (C,2,W,2,H), tap = (kh,kw)
   int c5;                       // output scattered (pixel shuffle): 5-D map (Cst,2,W,2,H), GEMM column = (a,b,co)
   int Cst;                      // channels of the scattered output tensor (N = 4*Cst)
@@ -239,7 +240,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t staging_off = (uint32_t)p.stages * stage_bytes;
   const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;
-  const uint32_t bar_off = staging_off + staging_bytes;
+  const int vlen = p.c5 ? p.Cst : p.N;                              // channels of the bias / bn vectors
+  const int nstg = p.nstaging;                                       // 1 or 2 staging tiles (double buffered stores)
+  const uint32_t vec_off = staging_off + (uint32_t)nstg * staging_bytes;   // bias | bn_a | bn_b, [3][vlen] floats
+  const uint32_t bar_off = (vec_off + 3u * (uint32_t)vlen * 4u + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kTcMaxStages + s); };
@@ -260,6 +264,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     ptx::tmem_alloc(slot_addr, tmem_cols);
     ptx::tmem_relinquish();
+  }
+  {
+    // per-channel epilogue vectors in shared memory (no global load in the epilogue's dependency chain)
+    float* vec = reinterpret_cast<float*>(smem + vec_off);
+    for (int i = threadIdx.x; i < vlen; i += blockDim.x) {
+      vec[i] = p.bias ? p.bias[i] : 0.f;
+      vec[vlen + i] = p.bn_a ? p.bn_a[i] : 1.f;
+      vec[2 * vlen + i] = p.bn_a ? p.bn_b[i] : 0.f;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -342,23 +355,34 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
     const uint32_t sub_bytes = 128u * pitch;
     uint8_t* staging = smem + staging_off;
-    const uint32_t staging_addr = smem_base + staging_off;
+    uint32_t staging_addr = smem_base + staging_off;
+    int sbuf = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const int rows_in_tile = p.tw * p.th * p.tn;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, ni = row / (p.tw * p.th);
-    float s_sum[2] = {0.f, 0.f}, s_sq[2] = {0.f, 0.f};
+    const float* vec = reinterpret_cast<const float*>(smem + vec_off);
+    // statistics ownership: column pair cp, row group rg (BN/2 rows each); deterministic flush (see tc_conv3_kernel)
+    const int cpairs = p.BN >> 1;
+    const int cp = et % cpairs, rg = et / cpairs;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
     int s_nb = -1;
     auto flush_stats = [&]() {
       if (p.stat && s_nb >= 0) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = et + u * 128;
-          if (c < p.BN) {
-            atomicAdd(p.stat + s_nb + c, (double)s_sum[u]);
-            atomicAdd(p.stat + p.N + s_nb + c, (double)s_sq[u]);
-          }
-          s_sum[u] = 0.f; s_sq[u] = 0.f;
+        float* park = reinterpret_cast<float*>(staging);
+        const int rgroups = 128 / cpairs;
+        if (et == 0) ptx::tma_store_wait_read();     // no store may still be reading the tile we park in
+        ptx::named_bar_sync(1, 128);
+        park[(rg * 2 + 0) * p.BN + 2 * cp] = s0; park[(rg * 2 + 0) * p.BN + 2 * cp + 1] = s1;
+        park[(rg * 2 + 1) * p.BN + 2 * cp] = q0; park[(rg * 2 + 1) * p.BN + 2 * cp + 1] = q1;
+        s0 = s1 = q0 = q1 = 0.f;
+        ptx::named_bar_sync(1, 128);
+        for (int i = et; i < 2 * p.BN; i += 128) {
+          const int which = i / p.BN, c = i - which * p.BN;
+          float v = 0.f;
+          for (int r = 0; r < rgroups; ++r) v += park[(r * 2 + which) * p.BN + c];
+          atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
         }
+        ptx::named_bar_sync(1, 128);
       }
     };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -375,6 +399,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         pix = ((long long)(h0 + hi) * 2 + sh_a) * (2 * p.W) + 2 * (w0 + wi) + sh_b;
       }
       if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
+      // the second epilogue operand (residual / accumulate) is fetched before waiting for the accumulator,
+      // so its global-memory latency hides behind the MMAs (BN <= 128: 16 x 16 B per thread)
+      if (nstg == 2) {
+        // double-buffered staging: only the store issued two tiles ago must have finished reading
+        staging = smem + staging_off + (uint32_t)sbuf * staging_bytes;
+        staging_addr = smem_base + staging_off + (uint32_t)sbuf * staging_bytes;
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        ptx::named_bar_sync(1, 128);
+        sbuf ^= 1;
+      }
+      uint4 tnext[4];
+      const bool t_on = p.t != nullptr && valid;
+      const uint4* tp4 = reinterpret_cast<const uint4*>(p.t + pix * p.t_ld + cb);
+      if (t_on) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tnext[i] = tp4[i];
+      }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
@@ -385,31 +426,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c0 = cb + j * 32;
         float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + i);
-            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-          }
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(vec + c0 + i);
+          f[i] = __uint_as_float(v[i]) + b4.x; f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+          f[i + 2] = __uint_as_float(v[i + 2]) + b4.z; f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
         }
-        if (p.t && valid) {
-          const bf16* tp = p.t + pix * p.t_ld + c0;
+        if (t_on) {
+          uint4 tcur[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tcur[i] = tnext[i];
+          if (j + 1 < p.BN / 32) {            // software pipeline: next chunk's operand is in flight during this one
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tnext[i] = tp4[(j + 1) * 4 + i];
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
-            const uint4 u = *reinterpret_cast<const uint4*>(tp + i);
+            const uint4 u = tcur[i / 8];
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int k2 = 0; k2 < 4; ++k2) {
-              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k2]);
-              const float2 tf = __bfloat1622float2(h2);
+              const float2 tf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k2]));
               const int c = i + 2 * k2;
-              if (p.bn_a) {
-                f[c] += p.bn_a[c0 + c] * tf.x + p.bn_b[c0 + c];
-                f[c + 1] += p.bn_a[c0 + c + 1] * tf.y + p.bn_b[c0 + c + 1];
-              } else {
-                f[c] += tf.x; f[c + 1] += tf.y;
-              }
+              f[c] += vec[vlen + c0 + c] * tf.x + vec[2 * vlen + c0 + c];
+              f[c + 1] += vec[vlen + c0 + c + 1] * tf.y + vec[2 * vlen + c0 + c + 1];
             }
           }
         }
@@ -454,27 +493,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tma_store_commit();
       }
       if (p.stat) {
-        // per-channel statistics of the stored (bf16-rounded) tile; invalid rows hold zeros
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = et + u * 128;
-          if (c < p.BN) {
-            const int sub = c / p.CS;
-            const uint32_t bir = (uint32_t)(c % p.CS) * 2u;
-            float a = 0.f, b = 0.f;
-            for (int r = 0; r < 128; ++r) {
-              const uint32_t logical = (uint32_t)r * pitch + bir;
-              const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
-              const float x = __bfloat162float(*reinterpret_cast<const bf16*>(staging + (uint32_t)sub * sub_bytes + phys));
-              a += x; b += x * x;
-            }
-            s_sum[u] += a; s_sq[u] += b;
-          }
+        // per-channel statistics of the stored (bf16-rounded) tile; invalid rows hold zeros.
+        // thread = (column pair, row group of BN/2 rows)
+        const int c = 2 * cp;
+        const int sub = c / p.CS;
+        const uint32_t bir = (uint32_t)(c % p.CS) * 2u;
+        const int r0 = rg * cpairs;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 4
+        for (int r = r0; r < r0 + cpairs; ++r) {
+          const uint32_t logical = (uint32_t)r * pitch + bir;
+          const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
+          const float2 x2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(staging + (uint32_t)sub * sub_bytes + phys));
+          a0 += x2.x; a1 += x2.y; b0 = fmaf(x2.x, x2.x, b0); b1 = fmaf(x2.y, x2.y, b1);
         }
+        s0 += a0; s1 += a1; q0 += b0; q1 += b1;
       }
-      if (et == 0) ptx::tma_store_wait_read();     // staging may be overwritten after this
-      ptx::named_bar_sync(1, 128);
+      if (nstg == 1) {
+        if (et == 0) ptx::tma_store_wait_read();     // staging may be overwritten after this
+        ptx::named_bar_sync(1, 128);
+      } else if (p.stat) {
+        ptx::named_bar_sync(1, 128);                 // statistics readers are done with this tile
+      }
     }
+    if (nstg == 2) { if (et == 0) ptx::tma_store_wait_read(); ptx::named_bar_sync(1, 128); }
     flush_stats();
     if (et == 0) ptx::tma_store_wait_all();
   }
@@ -1443,8 +1485,9 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_b = (B + p.tn - 1) / p.tn;
   p.n_tiles = N / p.BN;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
-  const size_t staging = (size_t)128 * p.BN * 2;
-  const size_t fixed = 1024 /*alignment slack*/ + staging + 8 * (2 * kTcMaxStages + 6);
+  p.nstaging = p.BN <= 64 ? 2 : 1;
+  const size_t staging = (size_t)p.nstaging * 128 * p.BN * 2;
+  const size_t fixed = 1024 /*alignment slack*/ + staging + (size_t)12 * N + 16 + 8 * (2 * kTcMaxStages + 6);
   const size_t budget = 227 * 1024;
   int stages = (int)((budget - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
@@ -1518,8 +1561,9 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   p.tiles_w = (Wg + p.tw - 1) / p.tw; p.tiles_h = (int)((Rg + p.th - 1) / p.th); p.tiles_b = 1;
   p.n_tiles = N / p.BN;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
-  const size_t staging = (size_t)128 * p.BN * 2;
-  const size_t fixed = 1024 + staging + 8 * (2 * kTcMaxStages + 6);
+  p.nstaging = p.BN <= 64 ? 2 : 1;
+  const size_t staging = (size_t)p.nstaging * 128 * p.BN * 2;
+  const size_t fixed = 1024 + staging + (size_t)12 * (gather ? N : Cst) + 16 + 8 * (2 * kTcMaxStages + 6);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   p.stages = stages;
