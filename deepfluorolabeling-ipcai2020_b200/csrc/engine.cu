@@ -165,6 +165,25 @@ struct fu_engine {
                        cudaGetErrorString(_ce), __FILE__, __LINE__);                        \
   } while (0)
 
+// same, with dynamic shared memory (> 48 KB is opted into once per kernel)
+#define LAUNCH_SMEM(e, kern, grid, block, smem, ...)                                        \
+  do {                                                                                      \
+    auto _kfn = kern;                                                                       \
+    static bool _attr = false;                                                              \
+    if (!_attr && (smem) > 48 * 1024) {                                                     \
+      cudaFuncSetAttribute(_kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
+      _attr = true;                                                                         \
+    }                                                                                       \
+    if ((e)->prof) (e)->prof_begin(#kern);                                                  \
+    _kfn<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);                            \
+    if ((e)->prof) (e)->prof_end();                                                         \
+    (e)->cnt.kernel_launches++;                                                             \
+    cudaError_t _ce = cudaPeekAtLastError();                                                \
+    if (_ce != cudaSuccess)                                                                 \
+      return (e)->fail(FU_ERR_CUDA, "launch %s failed: %s (%s:%d)", #kern,                  \
+                       cudaGetErrorString(_ce), __FILE__, __LINE__);                        \
+  } while (0)
+
 namespace {
 
 inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
@@ -650,6 +669,16 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     a.B = B; a.H = H; a.W = W; a.k = cw.k; a.pad = cw.k / 2; a.relu = relu;
     if (t) { a.t = t->p; a.t_ld = t->ld; a.bn_a = bn_a; a.bn_b = bn_b; }
     a.stat = stat;
+    if (cw.Cin == 1) {
+      // C_in = 1 fast path: persistent blocks, two per SM
+      const int TW = 256 / (cw.Cout / 8);
+      const long long tiles = (long long)((W + TW - 1) / TW) * ((H + kCin1TileH - 1) / kCin1TileH) * B;
+      const unsigned grid = (unsigned)std::min<long long>(tiles, 2ll * e->num_sms);
+      const size_t sm1 = cin1_smem_bytes(cw.k, cw.Cout, false);
+      if (cw.k == 3) LAUNCH_SMEM(e, (conv_cin1_kernel<T, 3>), grid, 256, sm1, a);
+      else LAUNCH_SMEM(e, (conv_cin1_kernel<T, 1>), grid, 256, sm1, a);
+      return FU_OK;
+    }
     const long long total = (long long)B * H * W * (cw.Cout / 8);
     const size_t smem = ((size_t)cw.k * cw.k * cw.Cin * cw.Cout + 3 * cw.Cout + 16 * cw.Cout) * sizeof(float);
     auto kfn = conv_small_cin_kernel<T>;
@@ -790,15 +819,15 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
   if (e->Cf == 32 && c.n_classes == 7 && (c.num_lands == 0 || (c.num_lands == 14 && e->lands.size() == 2 && e->lands[0].Cout == 21))) {
     // paper heads (7 classes, 39 -> 21 -> 14): one fused pass
     const long long P = (long long)B * HW;
+    const unsigned gridf = (unsigned)std::min<long long>((P + 255) / 256, (long long)e->num_sms * 4);   // 4 resident blocks/SM (126 regs)
     if (c.num_lands == 14)
-      LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 21, 14>), (unsigned)((P + 127) / 128), 128,
+      LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 21, 14>), gridf, 128,
              reinterpret_cast<const T*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx),
-             tdata(e, e->lands[1].w_idx), reinterpret_cast<T*>(lg.p), reinterpret_cast<T*>(pl.hmid[0].p),
-             pl.hmid[0].ld, seg, logits, heat, B, HW, c.do_soft_max);
+             tdata(e, e->lands[1].w_idx), reinterpret_cast<T*>(lg.p), seg, logits, heat, B, HW, c.do_soft_max);
     else
-      LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 1, 0>), (unsigned)((P + 127) / 128), 128,
+      LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 1, 0>), gridf, 128,
              reinterpret_cast<const T*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), (const float*)nullptr,
-             (const float*)nullptr, reinterpret_cast<T*>(lg.p), (T*)nullptr, 0, seg, logits, (float*)nullptr, B, HW,
+             (const float*)nullptr, reinterpret_cast<T*>(lg.p), seg, logits, (float*)nullptr, B, HW,
              c.do_soft_max);
     return FU_OK;
   }
@@ -898,6 +927,15 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
     memset(&a, 0, sizeof(a));
     a.x = x.p; a.x_ld = x.ld; a.Cin = cw.Cin; a.dy = dy.p; a.dy_ld = dy.ld; a.Cout = cw.Cout;
     a.B = B; a.H = H; a.W = W; a.k = cw.k; a.pad = cw.k / 2; a.dw = dw;
+    if (cw.Cin == 1) {
+      const int TW = 256 / (cw.Cout / 8);
+      const long long tiles = (long long)((W + TW - 1) / TW) * ((H + kCin1TileH - 1) / kCin1TileH) * B;
+      const unsigned grid = (unsigned)std::min<long long>(tiles, 2ll * e->num_sms);
+      const size_t sm1 = cin1_smem_bytes(cw.k, cw.Cout, true);
+      if (cw.k == 3) LAUNCH_SMEM(e, (wgrad_cin1_kernel<T, 3>), grid, 256, sm1, a);
+      else LAUNCH_SMEM(e, (wgrad_cin1_kernel<T, 1>), grid, 256, sm1, a);
+      return FU_OK;
+    }
     const int rows = 256 / (cw.Cout / 4);
     long long gx = ((long long)B * H * W + (long long)rows * 32 - 1) / ((long long)rows * 32);
     if (gx > (long long)e->num_sms * 8) gx = (long long)e->num_sms * 8;
@@ -989,15 +1027,15 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   if (fused_heads) {
     const size_t gbytes = ((size_t)(c.num_lands + c.n_classes) * (e->Cf + c.n_classes) + 64) * sizeof(float);
     CUDA_TRY(e, cudaMemsetAsync(e->heads_gacc, 0, gbytes, e->stream));
-    const unsigned gridh = (unsigned)std::min<long long>((P0 + 127) / 128, (long long)e->num_sms * 4);
+    const unsigned gridh = (unsigned)std::min<long long>((P0 + 255) / 256, (long long)e->num_sms * 2);   // 2 resident blocks/SM (255 regs)
     if (c.num_lands == 14) {
-      LAUNCH(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, reinterpret_cast<const T*>(feat.p), feat.ld,
+      LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, (heads_bwd_smem_bytes<32, 7, 21, 14>()), reinterpret_cast<const T*>(feat.p), feat.ld,
              tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,
              reinterpret_cast<T*>(d_feat.p), d_feat.ld, e->heads_gacc, B, HW, c.do_soft_max);
       LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
              gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
     } else {
-      LAUNCH(e, (heads_bwd_fused_kernel<T, 32, 7, 1, 0>), gridh, 128, reinterpret_cast<const T*>(feat.p), feat.ld,
+      LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 1, 0>), gridh, 128, (heads_bwd_smem_bytes<32, 7, 1, 0>()), reinterpret_cast<const T*>(feat.p), feat.ld,
              tdata(e, e->seg.w_idx), (const float*)nullptr, (const float*)nullptr, d_seg, (const float*)nullptr,
              reinterpret_cast<T*>(d_feat.p), d_feat.ld, e->heads_gacc, B, HW, c.do_soft_max);
       LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,

@@ -388,119 +388,411 @@ __global__ void __launch_bounds__(256) wgrad_small_cin_kernel(const SmallCinWgra
 }
 
 // --------------------------------------------------------------------------
-// Fused heads (unet.py:176-191): per pixel  logits = Wseg feat ; seg = softmax(logits) ;
-// heat = W2 (W1 [feat ; logits]).  One thread per pixel, weights in shared memory, one pass over the
-// feature map; seg / heat / (optional) logits are written as fp32 NCHW boundary tensors.
+// C_in = 1 fast path (every reference script: in_channels = 1, unet.py:41, train.py:313).  The generic
+// first-layer kernels above issue one scalar global load and two shared-memory weight loads per 8 FMAs and
+// run at 5-10 % of the HBM rate of their 32-channel operand.  Here a thread owns 8 output channels for the
+// whole kernel and keeps their K*K weights in registers, a block walks 4-row pixel tiles whose input halo is
+// staged once in shared memory, and lanes map to (pixel, channel group) with the group fastest so a warp's
+// 16-byte vectors form one contiguous 512-byte segment of the NHWC tensor.
 // --------------------------------------------------------------------------
-template <typename T, int CF, int NC, int NF, int NL>
-__global__ void __launch_bounds__(128) heads_fwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
-                                                              const float* w2, T* logits_nhwc, T* mid_nhwc, int mid_ld,
-                                                              float* seg, float* logits_out, float* heat, int B,
-                                                              long long HW, int do_softmax) {
-  __shared__ float s_wseg[NC * CF];
-  __shared__ float s_w1[NF * (CF + NC)];
-  __shared__ float s_w2[NL * NF > 0 ? NL * NF : 1];
-  __shared__ float s_mid[NL > 0 ? NF * 128 : 1];
-  for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
-  if (NL > 0) {
-    for (int i = threadIdx.x; i < NF * (CF + NC); i += blockDim.x) s_w1[i] = w1[i];
-    for (int i = threadIdx.x; i < NL * NF; i += blockDim.x) s_w2[i] = w2[i];
+template <typename T> struct Ld8;
+template <> struct Ld8<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Ld8<bf16> {
+  static __device__ __forceinline__ void ld(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+constexpr int kCin1TileH = 4;
+// dynamic shared memory of the two kernels below
+inline size_t cin1_smem_bytes(int K, int Cout, bool wgrad) {
+  const int groups = Cout >> 3, TW = 256 / groups, PAD = K / 2;
+  const size_t halo = (size_t)(TW + 2 * PAD) * (kCin1TileH + 2 * PAD);
+  return sizeof(float) * (halo + 8 + (wgrad ? (size_t)8 * K * K * Cout : (size_t)8 * 2 * Cout));
+}
+
+// stage the (zero padded) input halo of tile (n, h0, w0) in shared memory as floats
+template <typename T, int K>
+__device__ __forceinline__ void cin1_stage(const T* xp, int x_ld, float* sx, int n, int h0, int w0, int H, int W, int TW) {
+  constexpr int PAD = K / 2;
+  const int XW = TW + 2 * PAD, XH = kCin1TileH + 2 * PAD;
+  for (int i = threadIdx.x; i < XW * XH; i += blockDim.x) {
+    const int r = i / XW, c = i - r * XW;
+    const int ih = h0 + r - PAD, iw = w0 + c - PAD;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = ld1(xp + ((long long)(n * H + ih) * W + iw) * x_ld);
+    sx[i] = v;
+  }
+}
+
+// y = [relu](conv_K(x) + bias) [+ bn_a*t + bn_b], optional per-channel sum / sum of squares (SmallCinArgs, Cin == 1)
+template <typename T, int K>
+__global__ void __launch_bounds__(256, 2) conv_cin1_kernel(const SmallCinArgs p) {
+  constexpr int KK = K * K, PAD = K / 2, TH = kCin1TileH;
+  extern __shared__ __align__(16) float cin1_sm[];
+  const int groups = p.Cout >> 3, TW = 256 / groups;
+  const int XW = TW + 2 * PAD, XH = TH + 2 * PAD;
+  float* sx = cin1_sm;
+  float* part = cin1_sm + ((XW * XH + 7) & ~7);          // [8 warps][2*Cout]
+  const int g = threadIdx.x % groups, slot = threadIdx.x / groups;
+  float w[KK][8], bias[8], ba[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int co = g * 8 + j;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) w[t][j] = p.w[(long long)co * KK + t];
+    bias[j] = (p.bias ? p.bias[co] : 0.f) + (p.t ? p.bn_b[co] : 0.f);
+    ba[j] = p.t ? p.bn_a[co] : 0.f;
+  }
+  const T* xp = reinterpret_cast<const T*>(p.x);
+  const T* tp = reinterpret_cast<const T*>(p.t);
+  T* yp = reinterpret_cast<T*>(p.y);
+  float cs[8], cq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+  const int tiles_w = (p.W + TW - 1) / TW, tiles_h = (p.H + TH - 1) / TH;
+  const int total = tiles_w * tiles_h * p.B;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / (tiles_w * tiles_h), rem = tile - n * (tiles_w * tiles_h);
+    const int h0 = (rem / tiles_w) * TH, w0 = (rem % tiles_w) * TW;
+    __syncthreads();
+    cin1_stage<T, K>(xp, p.x_ld, sx, n, h0, w0, p.H, p.W, TW);
+    __syncthreads();
+    const int wc = w0 + slot;
+    if (wc < p.W) {
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {
+        const int h = h0 + r;
+        if (h < p.H) {
+          const long long pix = ((long long)n * p.H + h) * p.W + wc;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+#pragma unroll
+          for (int t = 0; t < KK; ++t) {
+            const float xv = sx[(r + t / K) * XW + slot + t % K];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, w[t][j], acc[j]);
+          }
+          if (p.t) {
+            float tv[8];
+            Ld8<T>::ld(tp + pix * p.t_ld + g * 8, tv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(ba[j], tv[j], acc[j]);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+          }
+          T* dst = yp + pix * p.y_ld + g * 8;
+          Ld8<T>::st(dst, acc);
+          if (p.stat) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float v = rnd(acc[j], dst); cs[j] += v; cq[j] = fmaf(v, v, cq[j]); }
+          }
+        }
+      }
+    }
+  }
+  if (p.stat) {
+    // lanes with equal (lane % groups) hold the same channels (groups is a power of two <= 32); the block
+    // reduction runs in a fixed order so the BN statistics are reproducible run to run
+    for (int o = groups; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
+        cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], o);
+      }
+    }
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane < groups) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        part[wrp * 2 * p.Cout + lane * 8 + j] = cs[j];
+        part[wrp * 2 * p.Cout + p.Cout + lane * 8 + j] = cq[j];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) {
+      float v = 0.f;
+      for (int w2 = 0; w2 < 8; ++w2) v += part[w2 * 2 * p.Cout + i];
+      atomicAdd(&p.stat[i], (double)v);
+    }
+  }
+}
+
+// dW(Cout,1,K,K) += sum_pixels x[p@tap] * dy[p, co]   (SmallCinWgradArgs, Cin == 1): reads dy once
+template <typename T, int K>
+__global__ void __launch_bounds__(256, 2) wgrad_cin1_kernel(const SmallCinWgradArgs p) {
+  constexpr int KK = K * K, PAD = K / 2, TH = kCin1TileH;
+  extern __shared__ __align__(16) float cin1_sm[];
+  const int groups = p.Cout >> 3, TW = 256 / groups;
+  const int XW = TW + 2 * PAD, XH = TH + 2 * PAD;
+  float* sx = cin1_sm;
+  float* part = cin1_sm + ((XW * XH + 7) & ~7);          // [8 warps][KK][Cout]
+  const int g = threadIdx.x % groups, slot = threadIdx.x / groups;
+  const T* xp = reinterpret_cast<const T*>(p.x);
+  const T* dyp = reinterpret_cast<const T*>(p.dy);
+  float acc[KK][8];
+#pragma unroll
+  for (int t = 0; t < KK; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const int tiles_w = (p.W + TW - 1) / TW, tiles_h = (p.H + TH - 1) / TH;
+  const int total = tiles_w * tiles_h * p.B;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / (tiles_w * tiles_h), rem = tile - n * (tiles_w * tiles_h);
+    const int h0 = (rem / tiles_w) * TH, w0 = (rem % tiles_w) * TW;
+    __syncthreads();
+    cin1_stage<T, K>(xp, p.x_ld, sx, n, h0, w0, p.H, p.W, TW);
+    __syncthreads();
+    const int wc = w0 + slot;
+    if (wc < p.W) {
+      float d[TH][8];
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {       // all of the tile's dy loads in flight before the FMAs
+        const int h = h0 + r;
+        if (h < p.H) {
+          Ld8<T>::ld(dyp + (((long long)n * p.H + h) * p.W + wc) * p.dy_ld + g * 8, d[r]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[r][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+          const float xv = sx[(r + t / K) * XW + slot + t % K];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv, d[r][j], acc[t][j]);
+        }
+      }
+    }
+  }
+  for (int o = groups; o < 32; o <<= 1) {
+#pragma unroll
+    for (int t = 0; t < KK; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] += __shfl_xor_sync(0xffffffffu, acc[t][j], o);
+  }
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane < groups) {
+#pragma unroll
+    for (int t = 0; t < KK; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[(wrp * KK + t) * p.Cout + lane * 8 + j] = acc[t][j];
   }
   __syncthreads();
-  const long long P = (long long)B * HW;
-  // one pixel per thread, no grid-stride loop: a loop would let the compiler hoist every
-  // (loop-invariant) shared-memory weight into registers (255 regs + spills, measured)
-  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (pix < P) {
-    const long long n = pix / HW, hw = pix - n * HW;
-    float f[CF];
+  for (int i = threadIdx.x; i < KK * p.Cout; i += blockDim.x) {
+    const int t = i / p.Cout, co = i - t * p.Cout;
+    float v = 0.f;
+    for (int w2 = 0; w2 < 8; ++w2) v += part[(w2 * KK + t) * p.Cout + co];
+    atomicAdd(p.dw + (long long)co * KK + t, v);
+  }
+}
+
+// --------------------------------------------------------------------------
+// Fused heads (unet.py:176-191): per pixel  logits = Wseg feat ; seg = softmax(logits) ;
+// heat = W2 (W1 [feat ; logits]) = W21 [feat ; logits] with W21 = W2 W1 folded once per block
+// (no non-linearity sits between the two 1x1 convs, unet.py:148-153).  One thread = TWO pixels so that every
+// 16-byte shared-memory weight load feeds 8 FMAs (the first version issued one LDS per FMA and was
+// LDS-bound at 0.25 ms; the op's HBM floor is ~30 us).  seg / heat / (optional) logits are written as fp32
+// NCHW boundary tensors; the logits also go, in the storage type, into the head's concat buffer.
+// --------------------------------------------------------------------------
+template <int CF, int NC, int NF, int NL>
+struct HeadsDims {
+  static constexpr int NCAT = CF + NC;
+  static constexpr int NCATP = (NCAT + 3) / 4 * 4;
+  static constexpr int NCP = (NC + 3) / 4 * 4;
+  static constexpr int NLp = NL > 0 ? NL : 1;
+};
+
+// W21[l][j] = sum_m W2[l][m] W1[m][j], rows padded with zeros to NCATP
+template <int CF, int NC, int NF, int NL>
+__device__ __forceinline__ void heads_fold_w21(const float* w1, const float* w2, float* s_w21) {
+  typedef HeadsDims<CF, NC, NF, NL> D;
+  if (NL > 0) {
+    for (int i = threadIdx.x; i < NL * D::NCATP; i += blockDim.x) {
+      const int l = i / D::NCATP, j = i - l * D::NCATP;
+      float a = 0.f;
+      if (j < D::NCAT)
+        for (int m = 0; m < NF; ++m) a = fmaf(w2[l * NF + m], w1[m * D::NCAT + j], a);
+      s_w21[i] = a;
+    }
+  }
+}
+
+// logits of two pixels from their feature vectors (4 independent FMA chains per pixel)
+template <int CF, int NC>
+__device__ __forceinline__ void heads_logits2(const float* q_wseg, const float (&f)[2][CF], float (&lg)[2][(NC + 3) / 4 * 4]) {
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
 #pragma unroll
     for (int c = 0; c < CF; c += 4) {
-      const float4 v = ld4(feat + pix * ld + c);
-      f[c] = v.x; f[c + 1] = v.y; f[c + 2] = v.z; f[c + 3] = v.w;
+      const float4 w = *reinterpret_cast<const float4*>(q_wseg + k * CF + c);
+      a0.x = fmaf(w.x, f[0][c], a0.x); a0.y = fmaf(w.y, f[0][c + 1], a0.y);
+      a0.z = fmaf(w.z, f[0][c + 2], a0.z); a0.w = fmaf(w.w, f[0][c + 3], a0.w);
+      a1.x = fmaf(w.x, f[1][c], a1.x); a1.y = fmaf(w.y, f[1][c + 1], a1.y);
+      a1.z = fmaf(w.z, f[1][c + 2], a1.z); a1.w = fmaf(w.w, f[1][c + 3], a1.w);
     }
-    float lg[NC];
+    lg[0][k] = (a0.x + a0.y) + (a0.z + a0.w);
+    lg[1][k] = (a1.x + a1.y) + (a1.z + a1.w);
+  }
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      float a = 0.f;
+  for (int k = NC; k < (NC + 3) / 4 * 4; ++k) { lg[0][k] = 0.f; lg[1][k] = 0.f; }
+}
+
+template <typename T, int CF, int NC, int NF, int NL>
+__global__ void __launch_bounds__(128) heads_fwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
+                                                              const float* w2, T* logits_nhwc, float* seg,
+                                                              float* logits_out, float* heat, int B, long long HW,
+                                                              int do_softmax) {
+  typedef HeadsDims<CF, NC, NF, NL> D;
+  static_assert(CF % 4 == 0, "feature channels must be a multiple of 4");
+  __shared__ __align__(16) float s_wseg[NC * CF];
+  __shared__ __align__(16) float s_w21[NL > 0 ? NL * D::NCATP : 4];
+  for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
+  heads_fold_w21<CF, NC, NF, NL>(w1, w2, s_w21);
+  __syncthreads();
+  const long long P = (long long)B * HW;
+  const long long nchunks = (P + 255) / 256;
+  for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    // z == 0, but opaque to the compiler: keeps it from hoisting the (loop-invariant) shared-memory weights
+    // out of the chunk loop into registers (255 registers + spills otherwise, measured)
+    const int z = (int)((unsigned long long)chunk >> 44);
+    const float* q_wseg = s_wseg + z;
+    const float* q_w21 = s_w21 + z;
+    long long pix[2], n[2], hw[2];
+    bool ok[2];
+    float f[2][CF];
 #pragma unroll
-      for (int c = 0; c < CF; ++c) a = fmaf(s_wseg[k * CF + c], f[c], a);
-      lg[k] = a;
+    for (int u = 0; u < 2; ++u) {
+      pix[u] = chunk * 256 + u * 128 + threadIdx.x;
+      ok[u] = pix[u] < P;
+      n[u] = ok[u] ? pix[u] / HW : 0;
+      hw[u] = ok[u] ? pix[u] - n[u] * HW : 0;
+#pragma unroll
+      for (int c = 0; c < CF; c += 4) {
+        const float4 v = ok[u] ? ld4(feat + pix[u] * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f[u][c] = v.x; f[u][c + 1] = v.y; f[u][c + 2] = v.z; f[u][c + 3] = v.w;
+      }
     }
-    if (logits_nhwc) {
+    float lg[2][D::NCP];
+    heads_logits2<CF, NC>(q_wseg, f, lg);
 #pragma unroll
-      for (int k = 0; k < NC; ++k) st1(logits_nhwc + pix * ld + k, lg[k]);
-    }
-    if (logits_out) {
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      if (logits_nhwc) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) logits_out[(n * NC + k) * HW + hw] = lg[k];
-    }
-    if (do_softmax) {
-      float mx = lg[0];
+        for (int k = 0; k < NC; ++k) st1(logits_nhwc + pix[u] * ld + k, lg[u][k]);
+      }
+      if (logits_out) {
 #pragma unroll
-      for (int k = 1; k < NC; ++k) mx = fmaxf(mx, lg[k]);
-      float pr[NC], ssum = 0.f;
+        for (int k = 0; k < NC; ++k) logits_out[(n[u] * NC + k) * HW + hw[u]] = lg[u][k];
+      }
+      if (do_softmax) {
+        float mx = lg[u][0];
 #pragma unroll
-      for (int k = 0; k < NC; ++k) { pr[k] = expf(lg[k] - mx); ssum += pr[k]; }
-      const float inv = 1.f / ssum;
+        for (int k = 1; k < NC; ++k) mx = fmaxf(mx, lg[u][k]);
+        float pr[NC], ssum = 0.f;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) seg[(n * NC + k) * HW + hw] = pr[k] * inv;
-    } else {
+        for (int k = 0; k < NC; ++k) { pr[k] = expf(lg[u][k] - mx); ssum += pr[k]; }
+        const float inv = 1.f / ssum;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) seg[(n * NC + k) * HW + hw] = lg[k];
+        for (int k = 0; k < NC; ++k) seg[(n[u] * NC + k) * HW + hw[u]] = pr[k] * inv;
+      } else {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) seg[(n[u] * NC + k) * HW + hw[u]] = lg[u][k];
+      }
     }
     if (NL > 0) {
-      // mid = W1 [feat ; logits] kept in shared memory (one column per thread) so the m / l loops can
-      // stay rolled: registers hold only the feature vector
-#pragma unroll 1
-      for (int m = 0; m < NF; ++m) {
-        float a = 0.f;
-#pragma unroll
-        for (int c = 0; c < CF; ++c) a = fmaf(s_w1[m * (CF + NC) + c], f[c], a);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) a = fmaf(s_w1[m * (CF + NC) + CF + k], lg[k], a);
-        s_mid[m * 128 + threadIdx.x] = a;
-        if (mid_nhwc) st1(mid_nhwc + pix * mid_ld + m, a);
-      }
-#pragma unroll 1
+#pragma unroll 2
       for (int l = 0; l < NL; ++l) {
-        float a = 0.f;
+        const float* wr = q_w21 + l * D::NCATP;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
 #pragma unroll
-        for (int m = 0; m < NF; ++m) a = fmaf(s_w2[l * NF + m], s_mid[m * 128 + threadIdx.x], a);
-        heat[(n * NL + l) * HW + hw] = a;
+        for (int c = 0; c < CF; c += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wr + c);
+          a0.x = fmaf(w.x, f[0][c], a0.x); a0.y = fmaf(w.y, f[0][c + 1], a0.y);
+          a0.z = fmaf(w.z, f[0][c + 2], a0.z); a0.w = fmaf(w.w, f[0][c + 3], a0.w);
+          a1.x = fmaf(w.x, f[1][c], a1.x); a1.y = fmaf(w.y, f[1][c + 1], a1.y);
+          a1.z = fmaf(w.z, f[1][c + 2], a1.z); a1.w = fmaf(w.w, f[1][c + 3], a1.w);
+        }
+#pragma unroll
+        for (int k = 0; k < D::NCP; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wr + CF + k);   // padded columns hold zeros
+          a0.x = fmaf(w.x, lg[0][k], a0.x); a0.y = fmaf(w.y, lg[0][k + 1], a0.y);
+          a0.z = fmaf(w.z, lg[0][k + 2], a0.z); a0.w = fmaf(w.w, lg[0][k + 3], a0.w);
+          a1.x = fmaf(w.x, lg[1][k], a1.x); a1.y = fmaf(w.y, lg[1][k + 1], a1.y);
+          a1.z = fmaf(w.z, lg[1][k + 2], a1.z); a1.w = fmaf(w.w, lg[1][k + 3], a1.w);
+        }
+        if (ok[0]) heat[(n[0] * NL + l) * HW + hw[0]] = (a0.x + a0.y) + (a0.z + a0.w);
+        if (ok[1]) heat[(n[1] * NL + l) * HW + hw[1]] = (a1.x + a1.y) + (a1.z + a1.w);
       }
     }
   }
 }
 
-// Fused heads backward.  Per pixel (one thread each): recompute logits/softmax from the features,
-//   dmid = W2^T dheat ; dcat = W1^T dmid ; dlg = dcat[CF:] + softmax'(dseg) ; dfeat = dcat[:CF] + Wseg^T dlg.
+// Fused heads backward.  Per pixel (one thread = two pixels): recompute logits/softmax from the features,
+//   dcat = W21^T dheat ; dlg = dcat[CF:] + softmax'(dseg) ; dfeat = dcat[:CF] + Wseg^T dlg.
 // Weight gradients: with cat = [feat ; logits] and mid = W1 cat,
 //   dW2 = sum dheat (x) mid = G1 W1^T ,  dW1 = sum dmid (x) cat = W2^T G1 ,  G1 = sum_pixels dheat (x) cat  (NL x (CF+NC))
 //   dWseg = Gseg = sum_pixels dlg (x) feat  (NC x CF)
-// so only G1 and Gseg (770 numbers for the paper heads) are reduced over pixels: per 128-pixel chunk the
+// so only G1 and Gseg (770 numbers for the paper heads) are reduced over pixels: per 256-pixel chunk the
 // per-pixel vectors go through shared memory and register-tiled outer products accumulate them; blocks are
 // persistent and add their partial G's to global memory once.  heads_bwd_finalize_kernel forms dW1, dW2.
+// Dynamic shared memory: heads_bwd_smem_bytes<...>().
+template <int CF, int NC, int NF, int NL>
+constexpr size_t heads_bwd_smem_bytes() {
+  typedef HeadsDims<CF, NC, NF, NL> D;
+  return sizeof(float) * ((size_t)(D::NLp + D::NCAT + NC) * 256 + NC * CF + (NL > 0 ? NL * D::NCATP : 4));
+}
+
 template <typename T, int CF, int NC, int NF, int NL>
 __global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
                                                               const float* w2, const float* d_seg, const float* d_heat,
                                                               T* d_feat, int d_ld, float* g_acc /*[NL*(CF+NC) + NC*CF]*/,
                                                               int B, long long HW, int do_softmax) {
-  constexpr int NCAT = CF + NC;
-  constexpr int NLp = NL > 0 ? NL : 1;
+  typedef HeadsDims<CF, NC, NF, NL> D;
+  constexpr int NCAT = D::NCAT, NCATP = D::NCATP, NLp = D::NLp;
   constexpr int ROWS = NLp + NCAT + NC;          // dheat rows, cat rows, dlg rows
   constexpr int TA = 2, TB = 3;                  // G1 register tile
   constexpr int NTA = (NLp + TA - 1) / TA, NTB = (NCAT + TB - 1) / TB;
   static_assert(NTA * NTB + CF <= 128, "outer-product tiles must fit one block");
-  __shared__ float s_wseg[NC * CF];
-  __shared__ float s_w1[NL > 0 ? NF * NCAT : 1];
-  __shared__ float s_w2[NL > 0 ? NL * NF : 1];
-  __shared__ __align__(16) float s_v[ROWS * 128];   // per-pixel vectors, one column per pixel
+  extern __shared__ __align__(16) float heads_smem[];
+  float* s_v = heads_smem;                       // [ROWS][256] per-pixel vectors, one column per pixel
+  float* s_wseg = s_v + ROWS * 256;              // [NC][CF]
+  float* s_w21 = s_wseg + NC * CF;               // [NL][NCATP]
   for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
-  if (NL > 0) {
-    for (int i = threadIdx.x; i < NF * NCAT; i += blockDim.x) s_w1[i] = w1[i];
-    for (int i = threadIdx.x; i < NL * NF; i += blockDim.x) s_w2[i] = w2[i];
-  }
+  heads_fold_w21<CF, NC, NF, NL>(w1, w2, s_w21);
   const int tid = threadIdx.x;
   // outer-product ownership
   const bool own_g1 = NL > 0 && tid < NTA * NTB;
@@ -515,96 +807,124 @@ __global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int
 #pragma unroll
   for (int k = 0; k < NC; ++k) gs[k] = 0.f;
   const long long P = (long long)B * HW;
-  const long long nchunks = (P + 127) / 128;
+  const long long nchunks = (P + 255) / 256;
   for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    __syncthreads();                              // previous chunk's outer products are done with s_v
-    const long long pix = chunk * 128 + tid;
-    float* col = s_v + tid;                       // row r of this pixel at col[r*128]
-    // z == 0, but opaque to the compiler: keeps it from hoisting all (loop-invariant) shared-memory
-    // weights out of the chunk loop into registers (255 registers + spills otherwise, measured)
-    const int z = (int)((unsigned long long)chunk >> 44);
+    __syncthreads();                              // weights ready / previous chunk's outer products done with s_v
+    const int z = (int)((unsigned long long)chunk >> 44);   // == 0, opaque (see heads_fwd_fused_kernel)
     const float* q_wseg = s_wseg + z;
-    const float* q_w1 = s_w1 + z;
-    const float* q_w2 = s_w2 + z;
-    if (pix < P) {
-      const long long n = pix / HW, hw = pix - n * HW;
-      float f[CF];
+    const float* q_w21 = s_w21 + z;
+    long long pix[2], n[2], hw[2];
+    bool ok[2];
+    float f[2][CF];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      pix[u] = chunk * 256 + u * 128 + tid;
+      ok[u] = pix[u] < P;
+      n[u] = ok[u] ? pix[u] / HW : 0;
+      hw[u] = ok[u] ? pix[u] - n[u] * HW : 0;
 #pragma unroll
       for (int c = 0; c < CF; c += 4) {
-        const float4 v = ld4(feat + pix * ld + c);
-        f[c] = v.x; f[c + 1] = v.y; f[c + 2] = v.z; f[c + 3] = v.w;
+        const float4 v = ok[u] ? ld4(feat + pix[u] * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f[u][c] = v.x; f[u][c + 1] = v.y; f[u][c + 2] = v.z; f[u][c + 3] = v.w;
       }
-      float lg[NC];
+    }
+    // upstream gradients (fp32 NCHW: consecutive threads read consecutive addresses)
+    float dh[2][NLp], dlg[2][D::NCP];
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        float a = 0.f;
+    for (int u = 0; u < 2; ++u) {
 #pragma unroll
-        for (int c = 0; c < CF; ++c) a = fmaf(q_wseg[k * CF + c], f[c], a);
-        lg[k] = a;
-      }
+      for (int l = 0; l < NLp; ++l) dh[u][l] = (NL > 0 && d_heat && ok[u]) ? d_heat[(n[u] * NL + l) * HW + hw[u]] : 0.f;
 #pragma unroll
-      for (int c = 0; c < CF; ++c) col[(NLp + c) * 128] = f[c];
+      for (int k = 0; k < D::NCP; ++k) dlg[u][k] = (k < NC && d_seg && ok[u]) ? d_seg[(n[u] * NC + k) * HW + hw[u]] : 0.f;
+    }
+    float lg[2][D::NCP];
+    heads_logits2<CF, NC>(q_wseg, f, lg);
 #pragma unroll
-      for (int k = 0; k < NC; ++k) col[(NLp + CF + k) * 128] = lg[k];
-      // dL/dlogits from the segmentation output
-      float dlg[NC];
+    for (int u = 0; u < 2; ++u) {
+      float* col = s_v + u * 128 + tid;           // row r of this pixel at col[r*256]
 #pragma unroll
-      for (int k = 0; k < NC; ++k) dlg[k] = d_seg ? d_seg[(n * NC + k) * HW + hw] : 0.f;
+      for (int l = 0; l < NLp; ++l) col[l * 256] = dh[u][l];
+#pragma unroll
+      for (int c = 0; c < CF; ++c) col[(NLp + c) * 256] = f[u][c];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) col[(NLp + CF + k) * 256] = lg[u][k];
       if (do_softmax && d_seg) {
-        float mx = lg[0];
+        float mx = lg[u][0];
 #pragma unroll
-        for (int k = 1; k < NC; ++k) mx = fmaxf(mx, lg[k]);
+        for (int k = 1; k < NC; ++k) mx = fmaxf(mx, lg[u][k]);
         float pr[NC], ssum = 0.f;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) { pr[k] = expf(lg[k] - mx); ssum += pr[k]; }
+        for (int k = 0; k < NC; ++k) { pr[k] = expf(lg[u][k] - mx); ssum += pr[k]; }
         const float inv = 1.f / ssum;
         float dot = 0.f;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) { pr[k] *= inv; dot = fmaf(pr[k], dlg[k], dot); }
+        for (int k = 0; k < NC; ++k) { pr[k] *= inv; dot = fmaf(pr[k], dlg[u][k], dot); }
 #pragma unroll
-        for (int k = 0; k < NC; ++k) dlg[k] = pr[k] * (dlg[k] - dot);
+        for (int k = 0; k < NC; ++k) dlg[u][k] = pr[k] * (dlg[u][k] - dot);
       }
-      float df[CF];
+    }
+    // dcat = W21^T dheat: f is dead from here on, its registers become dfeat
+    float (&df)[2][CF] = f;
 #pragma unroll
-      for (int c = 0; c < CF; ++c) df[c] = 0.f;
-      if (NL > 0) {
-        // dheat -> smem rows [0, NL); dmid[m] = sum_l W2[l][m] dheat[l]; dcat += W1[m][:] * dmid[m]
-#pragma unroll 1
-        for (int l = 0; l < NL; ++l) col[l * 128] = d_heat ? d_heat[(n * NL + l) * HW + hw] : 0.f;
-#pragma unroll 1
-        for (int m = 0; m < NF; ++m) {
-          float dm = 0.f;
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int l = 0; l < NL; ++l) dm = fmaf(q_w2[l * NF + m], col[l * 128], dm);
+      for (int c = 0; c < CF; ++c) df[u][c] = 0.f;
+    if (NL > 0) {
 #pragma unroll
-          for (int c = 0; c < CF; ++c) df[c] = fmaf(q_w1[m * NCAT + c], dm, df[c]);
+      for (int l = 0; l < NL; ++l) {
+        const float* wr = q_w21 + l * NCATP;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) dlg[k] = fmaf(q_w1[m * NCAT + CF + k], dm, dlg[k]);
+        for (int c = 0; c < CF; c += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wr + c);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            df[u][c] = fmaf(w.x, dh[u][l], df[u][c]); df[u][c + 1] = fmaf(w.y, dh[u][l], df[u][c + 1]);
+            df[u][c + 2] = fmaf(w.z, dh[u][l], df[u][c + 2]); df[u][c + 3] = fmaf(w.w, dh[u][l], df[u][c + 3]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < D::NCP; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wr + CF + k);   // padded columns hold zeros
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            dlg[u][k] = fmaf(w.x, dh[u][l], dlg[u][k]); dlg[u][k + 1] = fmaf(w.y, dh[u][l], dlg[u][k + 1]);
+            dlg[u][k + 2] = fmaf(w.z, dh[u][l], dlg[u][k + 2]); dlg[u][k + 3] = fmaf(w.w, dh[u][l], dlg[u][k + 3]);
+          }
         }
       }
+    }
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        col[(NLp + NCAT + k) * 128] = dlg[k];
+    for (int k = 0; k < NC; ++k) {
+      s_v[(NLp + NCAT + k) * 256 + tid] = dlg[0][k];
+      s_v[(NLp + NCAT + k) * 256 + 128 + tid] = dlg[1][k];
 #pragma unroll
-        for (int c = 0; c < CF; ++c) df[c] = fmaf(q_wseg[k * CF + c], dlg[k], df[c]);
+      for (int c = 0; c < CF; c += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(q_wseg + k * CF + c);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          df[u][c] = fmaf(w.x, dlg[u][k], df[u][c]); df[u][c + 1] = fmaf(w.y, dlg[u][k], df[u][c + 1]);
+          df[u][c + 2] = fmaf(w.z, dlg[u][k], df[u][c + 2]); df[u][c + 3] = fmaf(w.w, dlg[u][k], df[u][c + 3]);
+        }
       }
+    }
 #pragma unroll
-      for (int c = 0; c < CF; c += 4) st4(d_feat + pix * d_ld + c, make_float4(df[c], df[c + 1], df[c + 2], df[c + 3]));
-    } else {
-#pragma unroll 1
-      for (int r = 0; r < ROWS; ++r) col[r * 128] = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int c = 0; c < CF; c += 4)
+        st4(d_feat + pix[u] * d_ld + c, make_float4(df[u][c], df[u][c + 1], df[u][c + 2], df[u][c + 3]));
     }
     __syncthreads();
-    // outer products over the chunk's 128 pixels (float4 along the pixel axis)
+    // outer products over the chunk's 256 pixels (float4 along the pixel axis); out-of-range pixels hold zeros
     if (own_g1) {
 #pragma unroll 2
-      for (int p4 = 0; p4 < 32; ++p4) {
-        const int px = ((p4 + tid) & 31) * 4;     // staggered start: fewer bank conflicts between tiles
+      for (int p4 = 0; p4 < 64; ++p4) {
+        const int px = ((p4 + tid) & 63) * 4;     // staggered start: no bank conflicts between tiles
         float4 a[TA], b[TB];
 #pragma unroll
-        for (int i = 0; i < TA; ++i) a[i] = (ta + i < NL) ? *reinterpret_cast<const float4*>(s_v + (ta + i) * 128 + px) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < TA; ++i) a[i] = (ta + i < NL) ? *reinterpret_cast<const float4*>(s_v + (ta + i) * 256 + px) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < TB; ++j) b[j] = (tb + j < NCAT) ? *reinterpret_cast<const float4*>(s_v + (NLp + tb + j) * 128 + px) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < TB; ++j) b[j] = (tb + j < NCAT) ? *reinterpret_cast<const float4*>(s_v + (NLp + tb + j) * 256 + px) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < TA; ++i)
 #pragma unroll
@@ -614,12 +934,12 @@ __global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int
     }
     if (own_gs) {
 #pragma unroll 1
-      for (int p4 = 0; p4 < 32; ++p4) {
-        const int px = ((p4 + tid) & 31) * 4;
-        const float4 fv = *reinterpret_cast<const float4*>(s_v + (NLp + gs_c) * 128 + px);
+      for (int p4 = 0; p4 < 64; ++p4) {
+        const int px = ((p4 + tid) & 63) * 4;
+        const float4 fv = *reinterpret_cast<const float4*>(s_v + (NLp + gs_c) * 256 + px);
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
-          const float4 dv = *reinterpret_cast<const float4*>(s_v + (NLp + NCAT + k) * 128 + px);
+          const float4 dv = *reinterpret_cast<const float4*>(s_v + (NLp + NCAT + k) * 256 + px);
           gs[k] += dv.x * fv.x + dv.y * fv.y + dv.z * fv.z + dv.w * fv.w;
         }
       }

@@ -1100,6 +1100,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 // pixel rows are the K dimension, and a single image row never wraps, so no garbage enters the reduction).
 // Thin layers (Cin = 32) use 32-channel / 64-byte boxes so all nine taps (9 x 32 columns) fit one CTA's
 // TMEM; wider layers keep one filter row (3 taps) per CTA.
+// Tap stacking (N == cb, i.e. Cin <= 64): the kw = 0,1,2 views of a halo row differ by one pixel row
+// (= `brow` bytes) of the MN-major tile, so they are addressed as three consecutive N blocks of ONE operand
+// whose leading-dimension byte offset is `brow`: one MMA with N = 3*Cin replaces three with N = Cin.  The
+// accumulator columns come out as (kw, ci), exactly the per-tap layout the epilogue already reads.  The thin
+// layers are bound by MMA count (every MMA re-reads the 128-row dY operand from shared memory), so this
+// is a ~2x cut of their tensor-pipe time.
 // ===========================================================================
 struct TcWgrad3Params {
   int B, H, W, Cin, Cout;
@@ -1108,6 +1114,7 @@ struct TcWgrad3Params {
   int tpg, groups;              // taps per CTA (9 or 3) and tap groups (1 or 3)
   int co_tiles, ci_tiles, splits, stages;
   unsigned b_stage_bytes;       // bytes of the B region of one stage
+  int stack;                    // 1: the three kw taps of a filter row are ONE MMA with N = 3*N (see above)
   float* dw_acc;                // [9][Cout][Cin] fp32, zeroed by the caller
 };
 
@@ -1196,6 +1203,9 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       d |= (uint64_t)(p.cb == 64 ? 2 : 4) << 61;
       db = d;
     }
+    // stacked operand: N block b = the tile shifted by b pixel rows
+    const uint64_t dbs = (db & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((brow >> 4) & 0x3FFF) << 16);
+    const uint32_t idesc_s = umma_idesc_bf16_mn((uint32_t)(3 * p.N));
     const int ksteps = p.tw / 16;
     const int tpg = p.tpg, Nn = p.N;
     const uint32_t step_a16 = (16u * 128u) >> 4, step_b16 = (16u * brow) >> 4;
@@ -1212,14 +1222,27 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
         const uint64_t ad0 = da + (uint64_t)(a_addr >> 4);
         const uint64_t bd0 = db + (uint64_t)((a_addr + a_bytes) >> 4);
+        const uint64_t bd0s = dbs + (uint64_t)((a_addr + a_bytes) >> 4);
         const uint32_t accum = it != 0 ? 1u : 0u;
+        if (p.stack) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          if (t < tpg) {
-            const uint32_t d_t = tmem_base + (uint32_t)(t * Nn);
-            for (int ks = 0; ks < ksteps; ++ks)
-              ptx::umma_bf16(d_t, ad0 + (uint64_t)(ks * step_a16), bd0 + (uint64_t)(tapoff16[t] + ks * step_b16), idesc,
-                             accum | (uint32_t)ks);
+          for (int r = 0; r < 3; ++r) {
+            if (3 * r < tpg) {
+              const uint32_t d_t = tmem_base + (uint32_t)(3 * r * Nn);
+              for (int ks = 0; ks < ksteps; ++ks)
+                ptx::umma_bf16(d_t, ad0 + (uint64_t)(ks * step_a16), bd0s + (uint64_t)(tapoff16[3 * r] + ks * step_b16), idesc_s,
+                               accum | (uint32_t)ks);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if (t < tpg) {
+              const uint32_t d_t = tmem_base + (uint32_t)(t * Nn);
+              for (int ks = 0; ks < ksteps; ++ks)
+                ptx::umma_bf16(d_t, ad0 + (uint64_t)(ks * step_a16), bd0 + (uint64_t)(tapoff16[t] + ks * step_b16), idesc,
+                               accum | (uint32_t)ks);
+            }
           }
         }
         ptx::umma_commit(empty_bar(stage));
@@ -1958,6 +1981,7 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     const int nrows = p.tpg == 9 ? 3 : 1;
     const size_t b_box = ((size_t)(p.tw + 2) * nrows * p.cb * 2 + 1023) / 1024 * 1024;
     p.b_stage_bytes = (unsigned)(b_box * (p.N / p.cb));
+    p.stack = (p.N == p.cb && tc_env_int("FU_TC_W3_STACK", 1)) ? 1 : 0;
     p.co_tiles = (t.Cout + 127) / 128; p.ci_tiles = (t.Cin + p.N - 1) / p.N;
     const size_t stage_bytes = 2 * 8192 + p.b_stage_bytes;
     const size_t fixed = 1024 + 8 * (2 * kTcMaxStages + 4);
