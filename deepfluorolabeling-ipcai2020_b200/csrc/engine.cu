@@ -672,8 +672,8 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     if (cw.Cin == 1) {
       // C_in = 1 fast path: persistent blocks, two per SM
       const int TW = 256 / (cw.Cout / 8);
-      const long long tiles = (long long)((W + TW - 1) / TW) * ((H + kCin1TileH - 1) / kCin1TileH) * B;
-      const unsigned grid = (unsigned)std::min<long long>(tiles, 2ll * e->num_sms);
+      const long long tiles = (long long)((W + TW - 1) / TW) * ((H + cin1_tile_h(cw.k) - 1) / cin1_tile_h(cw.k)) * B;
+      const unsigned grid = (unsigned)std::min<long long>(tiles, 4ll * e->num_sms);
       const size_t sm1 = cin1_smem_bytes(cw.k, cw.Cout, false);
       if (cw.k == 3) LAUNCH_SMEM(e, (conv_cin1_kernel<T, 3>), grid, 256, sm1, a);
       else LAUNCH_SMEM(e, (conv_cin1_kernel<T, 1>), grid, 256, sm1, a);
@@ -929,8 +929,8 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
     a.B = B; a.H = H; a.W = W; a.k = cw.k; a.pad = cw.k / 2; a.dw = dw;
     if (cw.Cin == 1) {
       const int TW = 256 / (cw.Cout / 8);
-      const long long tiles = (long long)((W + TW - 1) / TW) * ((H + kCin1TileH - 1) / kCin1TileH) * B;
-      const unsigned grid = (unsigned)std::min<long long>(tiles, 2ll * e->num_sms);
+      const long long tiles = (long long)((W + TW - 1) / TW) * ((H + cin1_tile_h(cw.k) - 1) / cin1_tile_h(cw.k)) * B;
+      const unsigned grid = (unsigned)std::min<long long>(tiles, 4ll * e->num_sms);
       const size_t sm1 = cin1_smem_bytes(cw.k, cw.Cout, true);
       if (cw.k == 3) LAUNCH_SMEM(e, (wgrad_cin1_kernel<T, 3>), grid, 256, sm1, a);
       else LAUNCH_SMEM(e, (wgrad_cin1_kernel<T, 1>), grid, 256, sm1, a);
@@ -1027,7 +1027,8 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   if (fused_heads) {
     const size_t gbytes = ((size_t)(c.num_lands + c.n_classes) * (e->Cf + c.n_classes) + 64) * sizeof(float);
     CUDA_TRY(e, cudaMemsetAsync(e->heads_gacc, 0, gbytes, e->stream));
-    const unsigned gridh = (unsigned)std::min<long long>((P0 + 255) / 256, (long long)e->num_sms * 2);   // 2 resident blocks/SM (255 regs)
+    // resident blocks per SM: 3 with the landmark head (168 registers, 64.5 KB), 2 without (255 registers)
+    const unsigned gridh = (unsigned)std::min<long long>((P0 + 255) / 256, (long long)e->num_sms * (c.num_lands == 14 ? 3 : 2));
     if (c.num_lands == 14) {
       LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, (heads_bwd_smem_bytes<32, 7, 21, 14>()), reinterpret_cast<const T*>(feat.p), feat.ld,
              tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,

@@ -391,9 +391,9 @@ __global__ void __launch_bounds__(256) wgrad_small_cin_kernel(const SmallCinWgra
 // C_in = 1 fast path (every reference script: in_channels = 1, unet.py:41, train.py:313).  The generic
 // first-layer kernels above issue one scalar global load and two shared-memory weight loads per 8 FMAs and
 // run at 5-10 % of the HBM rate of their 32-channel operand.  Here a thread owns 8 output channels for the
-// whole kernel and keeps their K*K weights in registers, a block walks 4-row pixel tiles whose input halo is
-// staged once in shared memory, and lanes map to (pixel, channel group) with the group fastest so a warp's
-// 16-byte vectors form one contiguous 512-byte segment of the NHWC tensor.
+// whole kernel and keeps their K*K weights in registers, walks 4-row pixel columns whose input window sits in
+// registers, and lanes map to (pixel, channel group) with the group fastest so a warp's 16-byte vectors form
+// one contiguous 512-byte segment of the NHWC tensor.
 // --------------------------------------------------------------------------
 template <typename T> struct Ld8;
 template <> struct Ld8<float> {
@@ -427,37 +427,58 @@ template <> struct Ld8<bf16> {
   }
 };
 
-constexpr int kCin1TileH = 4;
-// dynamic shared memory of the two kernels below
+// rows per thread and loop trip
+__host__ __device__ constexpr int cin1_tile_h(int K) { return 4; }
+// dynamic shared memory of the two kernels below: block-reduction scratch + (3x3 only) the staged input halo
 inline size_t cin1_smem_bytes(int K, int Cout, bool wgrad) {
-  const int groups = Cout >> 3, TW = 256 / groups, PAD = K / 2;
-  const size_t halo = (size_t)(TW + 2 * PAD) * (kCin1TileH + 2 * PAD);
-  return sizeof(float) * (halo + 8 + (wgrad ? (size_t)8 * K * K * Cout : (size_t)8 * 2 * Cout));
+  const int TW = 256 / (Cout >> 3), PAD = K / 2;
+  const size_t halo = K == 3 ? (size_t)(((TW + 2 * PAD) * (cin1_tile_h(K) + 2 * PAD) + 7) & ~7) : 0;
+  return sizeof(float) * (halo + (wgrad ? (size_t)8 * K * K * Cout : (size_t)8 * 2 * Cout));
+}
+__device__ __forceinline__ float ldg1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldg1(const bf16* p) {
+  return __bfloat162float(__ushort_as_bfloat16(__ldg(reinterpret_cast<const unsigned short*>(p))));
 }
 
-// stage the (zero padded) input halo of tile (n, h0, w0) in shared memory as floats
+// The (TH+2*PAD) x K input window of a column of TH pixels, zero padded.  1x1: straight from global memory
+// (the single-channel input is tiny and L1/L2 resident), no barrier in the pixel loop.  3x3: the block's halo
+// tile is staged in shared memory first (18 scalar global loads per thread measured slower than the two
+// barriers per tile: 70 vs 53 us forward, 116 vs 80 us weight gradient at 32x192x192).
 template <typename T, int K>
-__device__ __forceinline__ void cin1_stage(const T* xp, int x_ld, float* sx, int n, int h0, int w0, int H, int W, int TW) {
-  constexpr int PAD = K / 2;
-  const int XW = TW + 2 * PAD, XH = kCin1TileH + 2 * PAD;
-  for (int i = threadIdx.x; i < XW * XH; i += blockDim.x) {
-    const int r = i / XW, c = i - r * XW;
-    const int ih = h0 + r - PAD, iw = w0 + c - PAD;
-    float v = 0.f;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = ld1(xp + ((long long)(n * H + ih) * W + iw) * x_ld);
-    sx[i] = v;
+__device__ __forceinline__ void cin1_window(const T* xp, int x_ld, float* sx, int n, int h0, int w0, int slot, int TW,
+                                            int H, int W, float (&xw)[cin1_tile_h(K) + 2 * (K / 2)][K]) {
+  constexpr int PAD = K / 2, XH = cin1_tile_h(K) + 2 * PAD;
+  if constexpr (K == 3) {
+    const int XW = TW + 2 * PAD;
+    __syncthreads();                                   // the previous tile's readers are done
+    for (int i = threadIdx.x; i < XW * XH; i += blockDim.x) {
+      const int r = i / XW, c = i - r * XW;
+      const int ih = h0 + r - PAD, iw = w0 + c - PAD;
+      sx[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? ldg1(xp + ((long long)(n * H + ih) * W + iw) * x_ld) : 0.f;
+    }
+    __syncthreads();                                   // (the window is read from sx at the point of use)
+  } else {
+    const int wc = w0 + slot;
+#pragma unroll
+    for (int r = 0; r < XH; ++r) {
+      const int ih = h0 + r - PAD;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const int iw = wc + c - PAD;
+        xw[r][c] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? ldg1(xp + ((long long)(n * H + ih) * W + iw) * x_ld) : 0.f;
+      }
+    }
   }
 }
 
 // y = [relu](conv_K(x) + bias) [+ bn_a*t + bn_b], optional per-channel sum / sum of squares (SmallCinArgs, Cin == 1)
 template <typename T, int K>
-__global__ void __launch_bounds__(256, 2) conv_cin1_kernel(const SmallCinArgs p) {
-  constexpr int KK = K * K, PAD = K / 2, TH = kCin1TileH;
+__global__ void __launch_bounds__(256, K == 1 ? 3 : 2) conv_cin1_kernel(const SmallCinArgs p) {
+  constexpr int KK = K * K, TH = cin1_tile_h(K);
   extern __shared__ __align__(16) float cin1_sm[];
   const int groups = p.Cout >> 3, TW = 256 / groups;
-  const int XW = TW + 2 * PAD, XH = TH + 2 * PAD;
-  float* sx = cin1_sm;
-  float* part = cin1_sm + ((XW * XH + 7) & ~7);          // [8 warps][2*Cout]
+  float* sx = cin1_sm;                                    // 3x3: [TH+2][TW+2] input halo
+  float* part = cin1_sm + (K == 3 ? (((TW + 2) * (TH + 2) + 7) & ~7) : 0);   // [8 warps][2*Cout]
   const int g = threadIdx.x % groups, slot = threadIdx.x / groups;
   float w[KK][8], bias[8], ba[8];
 #pragma unroll
@@ -479,41 +500,38 @@ __global__ void __launch_bounds__(256, 2) conv_cin1_kernel(const SmallCinArgs p)
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int n = tile / (tiles_w * tiles_h), rem = tile - n * (tiles_w * tiles_h);
     const int h0 = (rem / tiles_w) * TH, w0 = (rem % tiles_w) * TW;
-    __syncthreads();
-    cin1_stage<T, K>(xp, p.x_ld, sx, n, h0, w0, p.H, p.W, TW);
-    __syncthreads();
     const int wc = w0 + slot;
-    if (wc < p.W) {
+    float xw[TH + 2 * (K / 2)][K];
+    cin1_window<T, K>(xp, p.x_ld, sx, n, h0, w0, slot, TW, p.H, p.W, xw);
 #pragma unroll
-      for (int r = 0; r < TH; ++r) {
-        const int h = h0 + r;
-        if (h < p.H) {
-          const long long pix = ((long long)n * p.H + h) * p.W + wc;
-          float acc[8];
+    for (int r = 0; r < TH; ++r) {
+      const int h = h0 + r;
+      if (h < p.H && wc < p.W) {
+        const long long pix = ((long long)n * p.H + h) * p.W + wc;
+        float acc[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+        for (int j = 0; j < 8; ++j) acc[j] = bias[j];
 #pragma unroll
-          for (int t = 0; t < KK; ++t) {
-            const float xv = sx[(r + t / K) * XW + slot + t % K];
+        for (int t = 0; t < KK; ++t) {
+          const float xv = K == 3 ? sx[(r + t / K) * (TW + 2) + slot + t % K] : xw[r + t / K][t % K];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, w[t][j], acc[j]);
-          }
-          if (p.t) {
-            float tv[8];
-            Ld8<T>::ld(tp + pix * p.t_ld + g * 8, tv);
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, w[t][j], acc[j]);
+        }
+        if (p.t) {
+          float tv[8];
+          Ld8<T>::ld(tp + pix * p.t_ld + g * 8, tv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(ba[j], tv[j], acc[j]);
-          }
-          if (p.relu) {
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(ba[j], tv[j], acc[j]);
+        }
+        if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-          }
-          T* dst = yp + pix * p.y_ld + g * 8;
-          Ld8<T>::st(dst, acc);
-          if (p.stat) {
+          for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        T* dst = yp + pix * p.y_ld + g * 8;
+        Ld8<T>::st(dst, acc);
+        if (p.stat) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float v = rnd(acc[j], dst); cs[j] += v; cq[j] = fmaf(v, v, cq[j]); }
-          }
+          for (int j = 0; j < 8; ++j) { const float v = rnd(acc[j], dst); cs[j] += v; cq[j] = fmaf(v, v, cq[j]); }
         }
       }
     }
@@ -548,13 +566,12 @@ __global__ void __launch_bounds__(256, 2) conv_cin1_kernel(const SmallCinArgs p)
 
 // dW(Cout,1,K,K) += sum_pixels x[p@tap] * dy[p, co]   (SmallCinWgradArgs, Cin == 1): reads dy once
 template <typename T, int K>
-__global__ void __launch_bounds__(256, 2) wgrad_cin1_kernel(const SmallCinWgradArgs p) {
-  constexpr int KK = K * K, PAD = K / 2, TH = kCin1TileH;
+__global__ void __launch_bounds__(256, K == 1 ? 3 : 2) wgrad_cin1_kernel(const SmallCinWgradArgs p) {
+  constexpr int KK = K * K, TH = cin1_tile_h(K);
   extern __shared__ __align__(16) float cin1_sm[];
   const int groups = p.Cout >> 3, TW = 256 / groups;
-  const int XW = TW + 2 * PAD, XH = TH + 2 * PAD;
-  float* sx = cin1_sm;
-  float* part = cin1_sm + ((XW * XH + 7) & ~7);          // [8 warps][KK][Cout]
+  float* sx = cin1_sm;                                    // 3x3: [TH+2][TW+2] input halo
+  float* part = cin1_sm + (K == 3 ? (((TW + 2) * (TH + 2) + 7) & ~7) : 0);   // [8 warps][KK][Cout]
   const int g = threadIdx.x % groups, slot = threadIdx.x / groups;
   const T* xp = reinterpret_cast<const T*>(p.x);
   const T* dyp = reinterpret_cast<const T*>(p.dy);
@@ -568,30 +585,27 @@ __global__ void __launch_bounds__(256, 2) wgrad_cin1_kernel(const SmallCinWgradA
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int n = tile / (tiles_w * tiles_h), rem = tile - n * (tiles_w * tiles_h);
     const int h0 = (rem / tiles_w) * TH, w0 = (rem % tiles_w) * TW;
-    __syncthreads();
-    cin1_stage<T, K>(xp, p.x_ld, sx, n, h0, w0, p.H, p.W, TW);
-    __syncthreads();
     const int wc = w0 + slot;
-    if (wc < p.W) {
-      float d[TH][8];
+    float d[TH][8];
 #pragma unroll
-      for (int r = 0; r < TH; ++r) {       // all of the tile's dy loads in flight before the FMAs
-        const int h = h0 + r;
-        if (h < p.H) {
-          Ld8<T>::ld(dyp + (((long long)n * p.H + h) * p.W + wc) * p.dy_ld + g * 8, d[r]);
-        } else {
+    for (int r = 0; r < TH; ++r) {       // all of the tile's dy loads in flight before the barrier / the FMAs
+      const int h = h0 + r;
+      if (h < p.H && wc < p.W) {
+        Ld8<T>::ld(dyp + (((long long)n * p.H + h) * p.W + wc) * p.dy_ld + g * 8, d[r]);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d[r][j] = 0.f;
-        }
+        for (int j = 0; j < 8; ++j) d[r][j] = 0.f;
       }
+    }
+    float xw[TH + 2 * (K / 2)][K];
+    cin1_window<T, K>(xp, p.x_ld, sx, n, h0, w0, slot, TW, p.H, p.W, xw);
 #pragma unroll
-      for (int r = 0; r < TH; ++r) {
+    for (int r = 0; r < TH; ++r) {
 #pragma unroll
-        for (int t = 0; t < KK; ++t) {
-          const float xv = sx[(r + t / K) * XW + slot + t % K];
+      for (int t = 0; t < KK; ++t) {
+        const float xv = K == 3 ? sx[(r + t / K) * (TW + 2) + slot + t % K] : xw[r + t / K][t % K];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv, d[r][j], acc[t][j]);
-        }
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(xv, d[r][j], acc[t][j]);
       }
     }
   }
@@ -777,7 +791,7 @@ constexpr size_t heads_bwd_smem_bytes() {
 }
 
 template <typename T, int CF, int NC, int NF, int NL>
-__global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
+__global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
                                                               const float* w2, const float* d_seg, const float* d_heat,
                                                               T* d_feat, int d_ld, float* g_acc /*[NL*(CF+NC) + NC*CF]*/,
                                                               int B, long long HW, int do_softmax) {
@@ -829,11 +843,13 @@ __global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int
       }
     }
     // upstream gradients (fp32 NCHW: consecutive threads read consecutive addresses)
-    float dh[2][NLp], dlg[2][D::NCP];
+    // (dheat goes straight to its shared-memory rows and is read back per landmark below: 28 registers less)
+    float dlg[2][D::NCP];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
+      float* col = s_v + u * 128 + tid;
 #pragma unroll
-      for (int l = 0; l < NLp; ++l) dh[u][l] = (NL > 0 && d_heat && ok[u]) ? d_heat[(n[u] * NL + l) * HW + hw[u]] : 0.f;
+      for (int l = 0; l < NLp; ++l) col[l * 256] = (NL > 0 && d_heat && ok[u]) ? d_heat[(n[u] * NL + l) * HW + hw[u]] : 0.f;
 #pragma unroll
       for (int k = 0; k < D::NCP; ++k) dlg[u][k] = (k < NC && d_seg && ok[u]) ? d_seg[(n[u] * NC + k) * HW + hw[u]] : 0.f;
     }
@@ -842,8 +858,6 @@ __global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       float* col = s_v + u * 128 + tid;           // row r of this pixel at col[r*256]
-#pragma unroll
-      for (int l = 0; l < NLp; ++l) col[l * 256] = dh[u][l];
 #pragma unroll
       for (int c = 0; c < CF; ++c) col[(NLp + c) * 256] = f[u][c];
 #pragma unroll
@@ -873,13 +887,14 @@ __global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
         const float* wr = q_w21 + l * NCATP;
+        const float dh[2] = {s_v[l * 256 + tid], s_v[l * 256 + 128 + tid]};
 #pragma unroll
         for (int c = 0; c < CF; c += 4) {
           const float4 w = *reinterpret_cast<const float4*>(wr + c);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            df[u][c] = fmaf(w.x, dh[u][l], df[u][c]); df[u][c + 1] = fmaf(w.y, dh[u][l], df[u][c + 1]);
-            df[u][c + 2] = fmaf(w.z, dh[u][l], df[u][c + 2]); df[u][c + 3] = fmaf(w.w, dh[u][l], df[u][c + 3]);
+            df[u][c] = fmaf(w.x, dh[u], df[u][c]); df[u][c + 1] = fmaf(w.y, dh[u], df[u][c + 1]);
+            df[u][c + 2] = fmaf(w.z, dh[u], df[u][c + 2]); df[u][c + 3] = fmaf(w.w, dh[u], df[u][c + 3]);
           }
         }
 #pragma unroll
@@ -887,8 +902,8 @@ __global__ void __launch_bounds__(128) heads_bwd_fused_kernel(const T* feat, int
           const float4 w = *reinterpret_cast<const float4*>(wr + CF + k);   // padded columns hold zeros
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            dlg[u][k] = fmaf(w.x, dh[u][l], dlg[u][k]); dlg[u][k + 1] = fmaf(w.y, dh[u][l], dlg[u][k + 1]);
-            dlg[u][k + 2] = fmaf(w.z, dh[u][l], dlg[u][k + 2]); dlg[u][k + 3] = fmaf(w.w, dh[u][l], dlg[u][k + 3]);
+            dlg[u][k] = fmaf(w.x, dh[u], dlg[u][k]); dlg[u][k + 1] = fmaf(w.y, dh[u], dlg[u][k + 1]);
+            dlg[u][k + 2] = fmaf(w.z, dh[u], dlg[u][k + 2]); dlg[u][k + 3] = fmaf(w.w, dh[u], dlg[u][k + 3]);
           }
         }
       }

@@ -222,11 +222,16 @@ struct TcConvParams {
   int Cst;                      // channels of the scattered output tensor (N = 4*Cst)
 };
 
-constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (wgrad kernels; the conv kernel has 4*G epilogue warps)
 constexpr int kTcMaxStages = 8;
 constexpr int kTc3Threads = 320;      // halo kernel: producer, MMA, 2 x 4 epilogue warps (one group per paired pixel tile)
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// G = epilogue groups of 4 warps.  Tile i of a CTA (in its own order) is drained by group i % G from TMEM
+// stage i % (2G), so up to 2G accumulators are in flight.  The 1x1 / 2x2 layers have 4-16 MMAs per tile and
+// are bound by the epilogue's per-warp latency chain (TMEM load, second-operand fetch, convert, staging
+// store, TMA store, statistics): four groups cut their time ~3x; the deep 3x3 layers keep G = 1 or 2.
+template <int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -242,22 +247,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;
   const int vlen = p.c5 ? p.Cst : p.N;                              // channels of the bias / bn vectors
   const int nstg = p.nstaging;                                       // 1 or 2 staging tiles (double buffered stores)
-  const uint32_t vec_off = staging_off + (uint32_t)nstg * staging_bytes;   // bias | bn_a | bn_b, [3][vlen] floats
+  const uint32_t vec_off = staging_off + (uint32_t)(G * nstg) * staging_bytes;   // bias | bn_a | bn_b, [3][vlen] floats
   const uint32_t bar_off = (vec_off + 3u * (uint32_t)vlen * 4u + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kTcMaxStages + s); };
+  constexpr int NACC = 2 * G;             // TMEM accumulator stages
   auto tfull_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 2 + a); };
-  const uint32_t slot_addr = bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 4);
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * kTcMaxStages + 4));
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + NACC + a); };
+  const uint32_t slot_addr = bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 2 * NACC);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * kTcMaxStages + 2 * NACC));
 
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)p.BN) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(NACC * p.BN)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < NACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 128); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
   }
@@ -343,21 +349,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ------------------------------ epilogue (4 warps, 128 threads) ------------------------------
+    // ------------------------------ epilogue (G groups of 4 warps / 128 threads) ------------------------------
+    const int grp = (warp - 2) >> 2;        // which group; it drains tiles grp, grp + G, ... of this CTA
+    const int bar_id = 1 + grp;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;          // accumulator row = pixel slot of the tile
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = (threadIdx.x - 64) & 127;   // 0..127 within the group
     const uint32_t pitch = (uint32_t)p.CS * 2u;
     const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
     const uint32_t sub_bytes = 128u * pitch;
-    uint8_t* staging = smem + staging_off;
-    uint32_t staging_addr = smem_base + staging_off;
+    const uint32_t grp_staging_off = staging_off + (uint32_t)(grp * nstg) * staging_bytes;
+    uint8_t* staging = smem + grp_staging_off;
+    uint32_t staging_addr = smem_base + grp_staging_off;
     int sbuf = 0;
-    int acc = 0; uint32_t acc_phase = 0;
+    int acc = grp; uint32_t acc_phase = 0;
     const int rows_in_tile = p.tw * p.th * p.tn;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, ni = row / (p.tw * p.th);
     const float* vec = reinterpret_cast<const float*>(smem + vec_off);
@@ -371,21 +380,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* park = reinterpret_cast<float*>(staging);
         const int rgroups = 128 / cpairs;
         if (et == 0) ptx::tma_store_wait_read();     // no store may still be reading the tile we park in
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(bar_id, 128);
         park[(rg * 2 + 0) * p.BN + 2 * cp] = s0; park[(rg * 2 + 0) * p.BN + 2 * cp + 1] = s1;
         park[(rg * 2 + 1) * p.BN + 2 * cp] = q0; park[(rg * 2 + 1) * p.BN + 2 * cp + 1] = q1;
         s0 = s1 = q0 = q1 = 0.f;
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(bar_id, 128);
         for (int i = et; i < 2 * p.BN; i += 128) {
           const int which = i / p.BN, c = i - which * p.BN;
           float v = 0.f;
           for (int r = 0; r < rgroups; ++r) v += park[(r * 2 + which) * p.BN + c];
           atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
         }
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(bar_id, 128);
       }
     };
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < total_tiles; tile += G * (int)gridDim.x) {
       int w0, h0, n0, nb;
       decode(tile, w0, h0, n0, nb);
       const bool valid = row < rows_in_tile && (w0 + wi) < p.W && (h0 + hi) < p.H && (n0 + ni) < p.B;
@@ -403,10 +412,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // so its global-memory latency hides behind the MMAs (BN <= 128: 16 x 16 B per thread)
       if (nstg == 2) {
         // double-buffered staging: only the store issued two tiles ago must have finished reading
-        staging = smem + staging_off + (uint32_t)sbuf * staging_bytes;
-        staging_addr = smem_base + staging_off + (uint32_t)sbuf * staging_bytes;
+        staging = smem + grp_staging_off + (uint32_t)sbuf * staging_bytes;
+        staging_addr = smem_base + grp_staging_off + (uint32_t)sbuf * staging_bytes;
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(bar_id, 128);
         sbuf ^= 1;
       }
       uint4 tnext[4];
@@ -481,10 +490,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // accumulator drained: hand the TMEM stage back to the MMA warp
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty_bar(acc));
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      acc += G; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
       // staging tile complete -> TMA store
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(bar_id, 128);
       if (et == 0) {
         for (int s = 0; s < p.BN / p.CS; ++s) {
           if (p.c5) ptx::tma_store_5d(&tmC, staging_addr + (uint32_t)s * sub_bytes, cb + s * p.CS, sh_b, w0, sh_a, h0);
@@ -511,12 +520,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (nstg == 1) {
         if (et == 0) ptx::tma_store_wait_read();     // staging may be overwritten after this
-        ptx::named_bar_sync(1, 128);
+        ptx::named_bar_sync(bar_id, 128);
       } else if (p.stat) {
-        ptx::named_bar_sync(1, 128);                 // statistics readers are done with this tile
+        ptx::named_bar_sync(bar_id, 128);                 // statistics readers are done with this tile
       }
     }
-    if (nstg == 2) { if (et == 0) ptx::tma_store_wait_read(); ptx::named_bar_sync(1, 128); }
+    if (nstg == 2) { if (et == 0) ptx::tma_store_wait_read(); ptx::named_bar_sync(bar_id, 128); }
     flush_stats();
     if (et == 0) ptx::tma_store_wait_all();
   }
@@ -558,7 +567,12 @@ struct TcConv3Params {
   long long* dbg;               // optional timeline buffer (FU_TC_DBG=1): [role][super][event] clock64 of CTA 0
 };
 
-__global__ void __launch_bounds__(kTc3Threads, 1)
+// S = epilogue sets.  A set is one group of 4 warps per pixel tile of the pair; super tile i of a CTA is drained
+// by set i % S from TMEM stage i % (2S).  The thin layers (BN <= 64: 18-72 MMAs per tile) are bound by the
+// epilogue's per-warp latency chain, not by the tensor pipe (FU_TC_DBG timeline: ~3600 cycles per super tile of
+// which the MMAs take 2000), so they run two sets.
+template <int S>
+__global__ void __launch_bounds__(64 + 256 * S, 1)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const TcConv3Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -575,28 +589,29 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t b_region = p.resident ? (uint32_t)(cchunks * 9) * b_bytes : (uint32_t)p.b_stages * b_bytes;
   const uint32_t staging_off = b_off + b_region;
   const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;      // one per epilogue group
-  const uint32_t vec_off = staging_off + (uint32_t)p.npair * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
-  const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;    // [npair][2][BN] floats
-  const uint32_t bar_off = (stat_off + (uint32_t)p.npair * 2u * (uint32_t)p.BN * 4u + 7u) & ~7u;
+  constexpr int NACC = 2 * S;              // TMEM accumulator stages (each: npair tiles of BN columns)
+  const uint32_t vec_off = staging_off + (uint32_t)(S * p.npair) * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
+  const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;    // [S*npair][2][BN] floats
+  const uint32_t bar_off = (stat_off + (uint32_t)(S * p.npair) * 2u * (uint32_t)p.BN * 4u + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(8 + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(16 + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(24 + s); };
   auto t_full = [&](int a) { return bar_base + 8u * (uint32_t)(32 + a); };
-  auto t_empty = [&](int a) { return bar_base + 8u * (uint32_t)(34 + a); };
-  const uint32_t res_bar = bar_base + 8u * 36u;
-  const uint32_t slot_addr = bar_base + 8u * 37u;
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * 37u);
+  auto t_empty = [&](int a) { return bar_base + 8u * (uint32_t)(36 + a); };
+  const uint32_t res_bar = bar_base + 8u * 40u;
+  const uint32_t slot_addr = bar_base + 8u * 41u;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * 41u);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)(p.npair * p.BN)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(NACC * p.npair * p.BN)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 8; ++s) {
       ptx::mbar_init(a_full(s), 1); ptx::mbar_init(a_empty(s), 1);
       ptx::mbar_init(b_full(s), 1); ptx::mbar_init(b_empty(s), 1);
     }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(t_full(a), 1); ptx::mbar_init(t_empty(a), 128u * (uint32_t)p.npair); }
+    for (int a = 0; a < NACC; ++a) { ptx::mbar_init(t_full(a), 1); ptx::mbar_init(t_empty(a), 128u * (uint32_t)p.npair); }
     ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
@@ -784,25 +799,26 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (++as == a_stages) { as = 0; aph ^= 1u; }
           }
         }
-        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ------------------------------ epilogue: one group of 4 warps per pixel tile of the pair -----
-    const int grp = (warp - 2) >> 2;          // 0 / 1 = which pixel tile of the super tile
+    // ------------------------------ epilogue: S sets of one group of 4 warps per pixel tile of the pair -----
+    const int gi = (warp - 2) >> 2;           // group index 0 .. 2S-1
+    const int grp = gi & 1;                   // which pixel tile of the super tile
+    const int set = gi >> 1;                  // this set drains super tiles set, set + S, ... of the CTA
     if (grp < p.npair) {
       const int q = warp & 3;                 // TMEM lane quadrant this warp may access
       const int row = q * 32 + lane;
       const int et = (threadIdx.x - 64) & 127;   // thread index within the group
-      const int bar_id = 1 + grp;
+      const int bar_id = 1 + gi;
       const uint32_t pitch = (uint32_t)p.CS * 2u;
       const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
       const uint32_t sub_bytes = 128u * pitch;
-      uint8_t* staging = smem + staging_off + (uint32_t)grp * staging_bytes;
-      const uint32_t staging_addr = smem_base + staging_off + (uint32_t)grp * staging_bytes;
+      uint8_t* staging = smem + staging_off + (uint32_t)gi * staging_bytes;
+      const uint32_t staging_addr = smem_base + staging_off + (uint32_t)gi * staging_bytes;
       const float* vec = reinterpret_cast<const float*>(smem + vec_off);
-      float* gstat = reinterpret_cast<float*>(smem + stat_off) + grp * 2 * p.BN;
-      int acc = 0; uint32_t acc_phase = 0;
+      int acc = set; uint32_t acc_phase = 0;
       const int hi = row / p.twb, wq = row - hi * p.twb;
       const bool row_ok = wq < p.two && hi < p.th;
       const int mr = hi * p.two + wq;               // compacted staging row (valid rows only)
@@ -834,7 +850,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::named_bar_sync(bar_id, 128);
         }
       };
-      for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
+      for (int st = blockIdx.x + set * (int)gridDim.x; st < total_super; st += S * (int)gridDim.x) {
         const int nt = st % p.n_tiles, sp = st / p.n_tiles;
         const int nb = nt * p.BN;
         const int mt = sp * p.npair + grp;
@@ -904,7 +920,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ptx::tc_fence_before();
         ptx::mbar_arrive(t_empty(acc));
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 2);
-        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        acc += S; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         if (mt < m_tiles) {
           int w0, h0, n;
           decode_m(mt, w0, h0, n);
@@ -1420,12 +1436,12 @@ struct TcConv {
   std::vector<W3Cached> w3cache;
   struct Cached3 {
     const void *x, *y; int x_ld, y_ld, B, H, W, dir;
-    CUtensorMap a, b, c; TcConv3Params p; int grid; size_t smem;
+    CUtensorMap a, b, c; TcConv3Params p; int grid; size_t smem; int S;
   };
   std::vector<Cached3> cache3;
   struct Cached {
     const void *x, *y; int x_ld, y_ld, B, H, W, dir;   // H, W: spatial dims of the GEMM's pixel grid
-    CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem;
+    CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem; int G;
   };
   std::vector<Cached> cache;
 };
@@ -1484,6 +1500,21 @@ inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* 
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
+inline int tc_env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+// epilogue groups of the conv kernel: 4 for the thin, shallow tiles (few MMAs per tile: the epilogue is the
+// bottleneck), 2 up to 128 columns, 1 for 256-column tiles (TMEM holds 2G accumulators of BN columns)
+inline int tc_pick_groups(int BN, int k_iters, int ksteps) {
+  const int g_env = tc_env_int("FU_TC_EPI_GROUPS", 0);
+  int G = (BN <= 64 && k_iters * ksteps <= 48) ? 4 : (BN <= 128 ? 2 : 1);
+  if (g_env == 1 || g_env == 2 || g_env == 4) G = g_env;
+  while (2 * G * BN > 512) G >>= 1;
+  return G < 1 ? 1 : G;
+}
+
 inline bool tc_ptr_ok(const void* p, int ld) { return p && (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 8 == 0); }
 
 // Build (or fetch) the launch description: dir 0 = forward (A has Cin channels, N = Cout), dir 1 = data
@@ -1500,17 +1531,27 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   const int N = dir == 0 ? t.Cout : t.Cin;
   p.B = B; p.H = H; p.W = W; p.Cin = K; p.N = N; p.ksz = t.k; p.pad = t.k / 2;
   p.KC = (K % 64 == 0) ? 64 : 32;
-  int bn = tc_bn_max();
-  while (N % bn) bn >>= 1;
-  p.BN = bn;
-  p.CS = bn >= 64 ? 64 : 32;
   tc_pick_tile(B, H, W, p.tw, p.th, p.tn);
   p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_b = (B + p.tn - 1) / p.tn;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int bn = tc_bn_max();
+  while (N % bn) bn >>= 1;
+  // 128 x 256 tiles halve the shared-memory operand traffic per FLOP (an M=128, N=128 MMA reads 8 KB per
+  // 64 cycles = the full 128 B/clk of the SM; measured 707 -> 977 TFLOP/s at 256->256 @24x24), but only pay
+  // when they still fill the machine
+  if (getenv("FU_TC_BN_MAX") == nullptr && N % 256 == 0 &&
+      (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / 256) * 10 >= 9ll * sms)
+    bn = 256;
+  p.BN = bn;
+  p.CS = bn >= 64 ? 64 : 32;
   p.n_tiles = N / p.BN;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
   p.nstaging = p.BN <= 64 ? 2 : 1;
-  const size_t staging = (size_t)p.nstaging * 128 * p.BN * 2;
-  const size_t fixed = 1024 /*alignment slack*/ + staging + (size_t)12 * N + 16 + 8 * (2 * kTcMaxStages + 6);
+  c.G = tc_pick_groups(p.BN, t.k * t.k * (K / p.KC), p.KC / 16);
+  const size_t staging = (size_t)c.G * p.nstaging * 128 * p.BN * 2;
+  const size_t fixed = 1024 /*alignment slack*/ + staging + (size_t)12 * N + 16 + 8 * (2 * kTcMaxStages + 18);
   const size_t budget = 227 * 1024;
   int stages = (int)((budget - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
@@ -1518,9 +1559,6 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   p.stages = stages;
   c.smem = fixed + (size_t)stages * stage_bytes;
   const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   c.grid = (int)(total_tiles < sms ? total_tiles : sms);
   // A: activation (K channels, W, H, B)
   {
@@ -1585,8 +1623,9 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   p.n_tiles = N / p.BN;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
   p.nstaging = p.BN <= 64 ? 2 : 1;
-  const size_t staging = (size_t)p.nstaging * 128 * p.BN * 2;
-  const size_t fixed = 1024 + staging + (size_t)12 * (gather ? N : Cst) + 16 + 8 * (2 * kTcMaxStages + 6);
+  c.G = tc_pick_groups(p.BN, (gather ? 4 : 1) * (K / p.KC), p.KC / 16);
+  const size_t staging = (size_t)c.G * p.nstaging * 128 * p.BN * 2;
+  const size_t fixed = 1024 + staging + (size_t)12 * (gather ? N : Cst) + 16 + 8 * (2 * kTcMaxStages + 18);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   p.stages = stages;
@@ -1623,10 +1662,6 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
 // ---------------------------------------------------------------------------
 // halo kernel (tc_conv3_kernel) host side
 // ---------------------------------------------------------------------------
-inline int tc_env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s ? atoi(s) : dflt;
-}
 
 inline bool tc_use_v2(const TcConv& t, int H, int W) {
   // measured (tools/conv_time.py, B=32): 32->32@192 73 vs 214 us, 64->64@96 34 vs 61, 128->128@48 33 vs 34, 256->256@24 40 vs 32
@@ -1675,24 +1710,31 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   p.a_tile_bytes = (unsigned)((rows * row_bytes + 1023) / 1024 * 1024);
   const size_t a_stage = (size_t)p.npair * p.a_tile_bytes;
   const size_t b_bytes = (size_t)p.BN * row_bytes;
-  const size_t staging = (size_t)p.npair * 128 * p.BN * 2;
-  const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)p.npair * 8 * p.BN + 16 + 8 * 40;
   const size_t budget = 227 * 1024;
   const size_t wbytes = (size_t)9 * K * p.BN * 2;
-  p.resident = (p.n_tiles == 1 && fixed + wbytes + 2 * a_stage <= budget && tc_env_int("FU_TC_RESIDENT", 1)) ? 1 : 0;
-  if (p.resident) {
-    int as = (int)((budget - fixed - wbytes) / a_stage);
-    p.a_stages = as > 4 ? 4 : as;
-    p.b_stages = 1;
-    c.smem = fixed + wbytes + (size_t)p.a_stages * a_stage;
-  } else {
+  // two epilogue sets for the thin layers when everything (resident weights, >= 2 A stages) still fits
+  c.S = (p.BN <= 64 && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
+  for (;; c.S = 1) {
+    const size_t staging = (size_t)c.S * p.npair * 128 * p.BN * 2;
+    const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * 8 * p.BN + 16 + 8 * 48;
+    p.resident = (p.n_tiles == 1 && fixed + wbytes + 2 * a_stage <= budget && tc_env_int("FU_TC_RESIDENT", 1)) ? 1 : 0;
+    if (p.resident) {
+      int as = (int)((budget - fixed - wbytes) / a_stage);
+      p.a_stages = as > 4 ? 4 : as;
+      p.b_stages = 1;
+      c.smem = fixed + wbytes + (size_t)p.a_stages * a_stage;
+      break;
+    }
+    if (c.S == 2) continue;          // retry with one set before giving up residency
     p.a_stages = 2;
     if (fixed + 3 * a_stage + 6 * b_bytes <= budget) p.a_stages = 3;
+    if (fixed + (size_t)p.a_stages * a_stage + 2 * b_bytes > budget) { tc_err() = "halo tile does not fit shared memory"; return nullptr; }
     int bs = (int)((budget - fixed - (size_t)p.a_stages * a_stage) / b_bytes);
     if (bs > 8) bs = 8;
     if (bs < 2) { tc_err() = "halo tile does not fit shared memory"; return nullptr; }
     p.b_stages = bs;
     c.smem = fixed + (size_t)p.a_stages * a_stage + (size_t)bs * b_bytes;
+    break;
   }
   const long long m_tiles = (long long)p.tiles_w * p.tiles_h * B;
   const long long total_super = (m_tiles + p.npair - 1) / p.npair * p.n_tiles;
@@ -1725,7 +1767,8 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
 inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem, conv3) failed";
       return -1;
     }
@@ -1738,7 +1781,8 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
     cudaMemsetAsync(dbg_buf, 0, 4 * 24 * 4 * sizeof(long long), stream);
   }
   c->p.dbg = dbg ? dbg_buf : nullptr;
-  tc_conv3_kernel<<<c->grid, kTc3Threads, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 64 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  else tc_conv3_kernel<1><<<c->grid, 64 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->p);
   if (dbg) {
     long long h[4 * 24 * 4];
     cudaStreamSynchronize(stream);
@@ -1761,13 +1805,17 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
 inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem) failed";
       return -1;
     }
     attr_set = true;
   }
-  tc_conv_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  if (c->G == 4) tc_conv_kernel<4><<<c->grid, 64 + 128 * 4, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  else if (c->G == 2) tc_conv_kernel<2><<<c->grid, 64 + 128 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  else tc_conv_kernel<1><<<c->grid, 64 + 128, c->smem, stream>>>(c->a, c->b, c->c, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }

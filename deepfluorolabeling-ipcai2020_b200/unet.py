@@ -160,6 +160,7 @@ class UNet(nn.Module):
         self._handle_device = None
         self._schema = None
         self._bound_ptrs = None
+        self._state_cache = None
         self._generation = 0
         self._grad_numel = 0
         self._last_logits = None
@@ -216,14 +217,44 @@ class UNet(nn.Module):
         self._schema = schema
         self._grad_numel = int(L.fu_grad_numel(handle))
         self._bound_ptrs = None
+        self._state_cache = None
 
     def _state_tensors(self):
-        sd = dict(self.named_parameters())
-        sd.update(dict(self.named_buffers()))
-        return [sd[name] for name, *_ in self._schema]
+        """Parameters and buffers in engine-schema order.  Walking the module tree costs ~0.4 ms of Python per
+        call, which sits on the critical path of every step whose loss is read back (train.py:430), so the
+        list is cached; `_apply` (.to/.cuda) and `invalidate_cache()` drop it."""
+        if self._state_cache is None:
+            sd = dict(self.named_parameters())
+            sd.update(dict(self.named_buffers()))
+            tensors = [sd[name] for name, *_ in self._schema]
+            gp, params = [], []
+            for (name, shape, kind, _, off), t in zip(self._schema, tensors):
+                if kind == 0 and off >= 0:
+                    params.append(t)
+                    n = 1
+                    for d in shape:
+                        n *= d
+                    gp.append((name, shape, n, off))
+            self._state_cache = (tensors, params, gp, list(self.parameters()))
+        return self._state_cache[0]
+
+    def invalidate_cache(self):
+        """Call after replacing a Parameter/buffer OBJECT of the module by hand (in-place updates,
+        load_state_dict and .to() need nothing)."""
+        self._state_cache = None
+        self._bound_ptrs = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._state_cache = None
+        self._bound_ptrs = None
+        return out
 
     def _bind(self, device):
         tensors = self._state_tensors()
+        ptrs = [t.data_ptr() for t in tensors]
+        if ptrs == self._bound_ptrs:      # same storages as the last call: already validated and bound
+            return tensors
         ptrs = []
         for (name, _, _, dtype, _), t in zip(self._schema, tensors):
             want = torch.int64 if dtype == 1 else torch.float32
@@ -251,7 +282,7 @@ class UNet(nn.Module):
         heat = torch.empty((B, nl, H, W), device=x.device, dtype=torch.float32) if nl > 0 else None
         logits = torch.empty_like(seg) if self.keep_logits else None
         version = 0
-        for p in self.parameters():
+        for p in self._state_cache[3]:
             version += p._version
         stream = torch.cuda.current_stream(x.device).cuda_stream
         self._generation += 1
@@ -346,17 +377,7 @@ class UNet(nn.Module):
         x = x.contiguous()
         self._ensure_engine(x.device)
         self._bind(x.device)
-        sd = dict(self.named_parameters())
-        gp, params = [], []
-        for name, shape, kind, _, off in self._schema:
-            if kind == 0 and off >= 0:
-                p = sd[name]
-                params.append(p)
-                n = 1
-                for s in shape:
-                    n *= s
-                gp.append((name, shape, n, off))
-        self._grad_params = gp
+        params, self._grad_params = self._state_cache[1], self._state_cache[2]
         save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if save:
             return _UNetFunction.apply(self, True, x, *params)
