@@ -213,7 +213,8 @@ def run_ours(args):
     net.train()
     if world > 1:
         pkg.parallel.data_parallel(net)
-    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    # train.py:333-334's optimiser; fused=True is the same update in one multi-tensor kernel
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True, fused=True)
     crit = pkg.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
     B, S, T = args.batch, args.size, args.tile
     g = torch.Generator().manual_seed(100 + rank)

@@ -100,6 +100,11 @@ struct fu_engine {
   char* wgrad_scr = nullptr; size_t wgrad_scr_bytes = 0;   // tensor-core weight-gradient accumulators
   float *ones = nullptr, *zeros = nullptr;
   float* heads_gacc = nullptr;   // [NL*(CF+NC) + NC*CF] accumulators of the fused heads backward
+  // batched weight pack / weight-gradient unpack (kernels_tc.cuh): device job tables and what they hold
+  static constexpr int kJobCap = 512;
+  TcPackJob* pack_tbl = nullptr; TcUnpackJob* unpack_tbl = nullptr;
+  std::vector<TcPackJob> pack_uploaded; std::vector<TcUnpackJob> unpack_uploaded;
+  TcBatch batch;
   int64_t packed_version = -1;
   bool packed_once = false;
   Plan plan;
@@ -374,6 +379,8 @@ int alloc_persistent(fu_engine* e) {
   CUDA_TRY(e, cudaMalloc(&e->dscr_fwd, e->dscr_fwd_bytes));
   CUDA_TRY(e, cudaMalloc(&e->dscr_bwd, e->dscr_bwd_bytes));
   CUDA_TRY(e, cudaMemset(e->wmem, 0, e->wmem_bytes));
+  CUDA_TRY(e, cudaMalloc(&e->pack_tbl, fu_engine::kJobCap * sizeof(TcPackJob)));
+  CUDA_TRY(e, cudaMalloc(&e->unpack_tbl, fu_engine::kJobCap * sizeof(TcUnpackJob)));
   Bump w2, df2, db2, ws2;
   w2.base = e->wmem; df2.base = reinterpret_cast<char*>(e->dscr_fwd); db2.base = reinterpret_cast<char*>(e->dscr_bwd);
   ws2.base = e->wgrad_scr;
@@ -528,6 +535,8 @@ int pack_all(fu_engine* e, bool training) {
   int rc = FU_OK;
   const int last = e->cfg.depth - 1;
   int di = 0;
+  e->batch.pack.clear();
+  tc_batch() = &e->batch;        // tensor-core layers only register their job; one launch packs them all
   for (auto& c : e->downc) { if (di++ != last && rc == FU_OK) rc = pack_conv(e, c); }
   auto blk = [&](Block& b) {
     if (b.has_res && rc == FU_OK) rc = pack_conv(e, b.res);
@@ -538,7 +547,16 @@ int pack_all(fu_engine* e, bool training) {
   for (auto& b : e->dec) blk(b);
   if (rc == FU_OK) rc = pack_conv(e, e->seg);
   for (auto& c : e->lands) if (rc == FU_OK) rc = pack_conv(e, c);
+  tc_batch() = nullptr;
   (void)training;
+  if (rc == FU_OK && !e->batch.pack.empty()) {
+    e->set_tag(0, 0, "weight_pack");
+    if (e->prof) e->prof_begin("tc_pack_batched_kernel");
+    const int trc = tc_flush_jobs(e->batch.pack, e->pack_uploaded, e->pack_tbl, fu_engine::kJobCap, tc_pack_batched_kernel,
+                                  e->stream, &e->cnt);
+    if (e->prof) e->prof_end();
+    if (trc) return e->fail(FU_ERR_CUDA, "batched weight pack failed");
+  }
   return rc;
 }
 
@@ -1012,6 +1030,8 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   const int training = e->saved_training;
   int rc;
   e->deferred_sums.clear();
+  e->batch.unpack.clear();
+  struct SinkGuard { SinkGuard(TcBatch* b) { tc_batch() = b; } ~SinkGuard() { tc_batch() = nullptr; } } sink_guard(&e->batch);
   CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
   CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
   if (e->cfg.precision == FU_PRECISION_BF16 && e->wgrad_scr_bytes > 512)
@@ -1145,6 +1165,15 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
       }
     }
   }
+  if (!e->batch.unpack.empty()) {
+    // every tensor-core weight gradient of this step: [taps][M][N] accumulators -> torch layout, one launch
+    e->set_tag(0, 0, "wgrad_unpack");
+    if (e->prof) e->prof_begin("tc_unpack_batched_kernel");
+    const int trc = tc_flush_jobs(e->batch.unpack, e->unpack_uploaded, e->unpack_tbl, fu_engine::kJobCap,
+                                  tc_unpack_batched_kernel, e->stream, &e->cnt);
+    if (e->prof) e->prof_end();
+    if (trc) return e->fail(FU_ERR_CUDA, "batched weight-gradient unpack failed");
+  }
   return flush_deferred_sums(e);
 }
 
@@ -1219,6 +1248,8 @@ void fu_engine_destroy(fu_engine* e) {
   if (e->dscr_fwd) cudaFree(e->dscr_fwd);
   if (e->dscr_bwd) cudaFree(e->dscr_bwd);
   if (e->wgrad_scr) cudaFree(e->wgrad_scr);
+  if (e->pack_tbl) cudaFree(e->pack_tbl);
+  if (e->unpack_tbl) cudaFree(e->unpack_tbl);
   delete e;
 }
 

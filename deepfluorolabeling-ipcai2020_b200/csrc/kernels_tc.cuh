@@ -1296,17 +1296,12 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
 }
 
-// [taps][Cout][Cin] fp32 accumulator -> torch layout (Cout,Cin,k,k)
-__global__ void tc_wgrad_unpack_kernel(const float* acc, float* dw, int Cout, int Cin, int taps) {
-  const long long total = (long long)Cout * Cin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i % taps);
-    const long long r = i / taps;   // co*Cin + ci
-    dw[i] = acc[(long long)t * Cout * Cin + r];
-  }
-}
-
+// ---------------------------------------------------------------------------
+// Weight repacking, batched: ONE launch per step packs every tensor-core layer's fp32 torch weights into the
+// two bf16 GEMM layouts, and ONE launch at the end of backward turns every [taps][M][N] fp32 weight-gradient
+// accumulator into the torch layout.  (The per-layer versions were 92 launches and 0.64 ms per step, most of
+// it uncoalesced 2-byte scatter: the transposes now go through shared-memory tiles.)
+// ---------------------------------------------------------------------------
 // generic bf16 pack of a GEMM B matrix [N][T][K] from a torch-layout weight:
 //   dst[(n*T + t)*K + k] = src[tmap(t)*st + k*sk + (n / Ninner)*snh + (n % Ninner)*snl]
 struct TcPackArgs {
@@ -1314,34 +1309,140 @@ struct TcPackArgs {
   int N, T, K, Ninner, flip;
   long long st, sk, snh, snl;
 };
-__global__ void tc_pack_generic_kernel(const TcPackArgs p) {
-  const long long total = (long long)p.N * p.T * p.K;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % p.K);
-    const long long r = i / p.K;
-    const int t = (int)(r % p.T);
-    const int n = (int)(r / p.T);
-    const int tm = p.flip ? (p.T - 1 - t) : t;
-    const int nh = n / p.Ninner, nl = n - nh * p.Ninner;
-    p.dst[i] = __float2bfloat16_rn(p.src[tm * p.st + k * p.sk + nh * p.snh + nl * p.snl]);
+struct TcPackJob {
+  int kind;                     // 0: Conv2d 3x3 / 1x1 (tiled transposes); 1: generic (2x2 stride-2 layers)
+  int block0;                   // first block of this job in the batched grid
+  int nblocks;
+  // kind 0: fp32 torch weights (Cout,Cin,k,k) -> bf16 [Cout][tap][Cin] (forward) and [Cin][flip(tap)][Cout] (data gradient)
+  const float* w; bf16* fwd; bf16* dgrad; int Cout, Cin, taps;
+  TcPackArgs f, d;              // kind 1
+};
+struct TcUnpackJob {
+  const float* acc;             // [taps][M][N] fp32
+  float* dw;                    // torch layout (M, N, k, k)
+  int M, N, taps;
+  int block0, nblocks;
+};
+constexpr int kPackGenericPerBlock = 2048;
+
+template <typename Job>
+__device__ __forceinline__ int tc_find_job(const Job* jobs, int njobs, int* s_job) {
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {            // last job with block0 <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    *s_job = lo;
+  }
+  __syncthreads();
+  return *s_job;
+}
+
+__global__ void __launch_bounds__(256) tc_pack_batched_kernel(const TcPackJob* jobs, int njobs) {
+  __shared__ int s_job;
+  __shared__ float tile[32 * 289];      // [co][ci*taps + t], odd row stride: conflict-free row- and column-wise
+  const TcPackJob& J = jobs[tc_find_job(jobs, njobs, &s_job)];
+  const int lb = (int)blockIdx.x - J.block0;
+  if (J.kind == 0) {
+    const int taps = J.taps, tiles_ci = J.Cin / 32;
+    const int co0 = (lb / tiles_ci) * 32, ci0 = (lb % tiles_ci) * 32;
+    const int rowlen = 32 * taps;
+    for (int i = threadIdx.x; i < 32 * rowlen; i += 256) {
+      const int r = i / rowlen, c = i - r * rowlen;
+      tile[r * 289 + c] = J.w[((long long)(co0 + r) * J.Cin + ci0) * taps + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * rowlen; i += 256) {
+      const int ci = i & 31, t = (i >> 5) % taps, r = i / rowlen;
+      J.fwd[((long long)(co0 + r) * taps + t) * J.Cin + ci0 + ci] = __float2bfloat16_rn(tile[r * 289 + ci * taps + t]);
+    }
+    for (int i = threadIdx.x; i < 32 * rowlen; i += 256) {
+      const int r = i & 31, t = (i >> 5) % taps, ci = i / rowlen;
+      J.dgrad[((long long)(ci0 + ci) * taps + (taps - 1 - t)) * J.Cout + co0 + r] = __float2bfloat16_rn(tile[r * 289 + ci * taps + t]);
+    }
+  } else {
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const TcPackArgs& p = which ? J.d : J.f;
+      const long long total = (long long)p.N * p.T * p.K;
+      const long long i0 = (long long)lb * kPackGenericPerBlock;
+      for (long long i = i0 + threadIdx.x; i < i0 + kPackGenericPerBlock && i < total; i += 256) {
+        const int k = (int)(i % p.K);
+        const long long r = i / p.K;
+        const int t = (int)(r % p.T);
+        const int n = (int)(r / p.T);
+        const int tm = p.flip ? (p.T - 1 - t) : t;
+        const int nh = n / p.Ninner, nl = n - nh * p.Ninner;
+        p.dst[i] = __float2bfloat16_rn(p.src[tm * p.st + k * p.sk + nh * p.snh + nl * p.snl]);
+      }
+    }
   }
 }
 
-// fp32 torch weights (Cout,Cin,k,k) -> bf16 [Cout][tap][Cin] (forward) and [Cin][flip(tap)][Cout] (data gradient)
-__global__ void tc_pack_conv_kernel(const float* w, bf16* fwd, bf16* dgrad, int Cout, int Cin, int taps) {
-  const long long total = (long long)Cout * Cin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % Cin);
-    const long long r = i / Cin;
-    const int t = (int)(r % taps);
-    const int co = (int)(r / taps);
-    const float v = w[((long long)co * Cin + ci) * taps + t];
-    const bf16 h = __float2bfloat16_rn(v);
-    fwd[i] = h;                                                    // [co][t][ci]
-    dgrad[((long long)ci * taps + (taps - 1 - t)) * Cout + co] = h;  // [ci][flip t][co]
+// dw[(m*N + n)*taps + t] = acc[(t*M + m)*N + n]: tiles of 8 m x 32 n, reads and writes both contiguous
+__global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJob* jobs, int njobs) {
+  __shared__ int s_job;
+  __shared__ float tile[8][32 * 9 + 1];
+  const TcUnpackJob& J = jobs[tc_find_job(jobs, njobs, &s_job)];
+  const int lb = (int)blockIdx.x - J.block0;
+  const int taps = J.taps, tiles_n = J.N / 32;
+  const int m0 = (lb / tiles_n) * 8, n0 = (lb % tiles_n) * 32;
+  const int rowlen = 32 * taps;
+  for (int i = threadIdx.x; i < 8 * rowlen; i += 256) {
+    const int n = i & 31, t = (i >> 5) % taps, m = i / rowlen;
+    if (m0 + m < J.M) tile[m][n * taps + t] = J.acc[((long long)t * J.M + m0 + m) * J.N + n0 + n];
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * rowlen; i += 256) {
+    const int m = i / rowlen, c = i - m * rowlen;
+    if (m0 + m < J.M) J.dw[((long long)(m0 + m) * J.N + n0) * taps + c] = tile[m][c];
+  }
+}
+
+// Jobs are collected by the engine over a step (tc_batch() != nullptr) and flushed in one launch; without a
+// collector (kernel test hook) every job is flushed immediately through a one-entry table.
+struct TcBatch {
+  std::vector<TcPackJob> pack;
+  std::vector<TcUnpackJob> unpack;
+};
+inline TcBatch*& tc_batch() {
+  static thread_local TcBatch* b = nullptr;
+  return b;
+}
+// upload `jobs` when they differ from what the device table already holds, then launch
+template <typename Job, typename Kern>
+inline int tc_flush_jobs(std::vector<Job>& jobs, std::vector<Job>& uploaded, Job* dev_tbl, int dev_cap, Kern kern,
+                         cudaStream_t stream, fu_counters* cnt) {
+  if (jobs.empty()) return 0;
+  if ((int)jobs.size() > dev_cap) return -1;
+  int blocks = 0;
+  for (auto& j : jobs) { j.block0 = blocks; blocks += j.nblocks; }
+  if (uploaded.size() != jobs.size() || memcmp(uploaded.data(), jobs.data(), jobs.size() * sizeof(Job)) != 0) {
+    if (cudaMemcpyAsync(dev_tbl, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -1;
+    uploaded = jobs;
+  }
+  kern<<<blocks, 256, 0, stream>>>(dev_tbl, (int)jobs.size());
+  if (cnt) cnt->kernel_launches++;
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+template <typename Job, typename Kern>
+inline int tc_run_job_now(Job job, Kern kern, cudaStream_t stream, fu_counters* cnt) {
+  Job* d = nullptr;
+  if (cudaMalloc(&d, sizeof(Job)) != cudaSuccess) return -1;
+  std::vector<Job> jobs(1, job), up;
+  const int rc = tc_flush_jobs(jobs, up, d, 1, kern, stream, cnt);
+  cudaStreamSynchronize(stream);
+  cudaFree(d);
+  return rc;
+}
+inline int tc_unpack(const float* acc, float* dw, int M, int N, int taps, cudaStream_t stream, fu_counters* cnt) {
+  TcUnpackJob j;
+  memset(&j, 0, sizeof(j));
+  j.acc = acc; j.dw = dw; j.M = M; j.N = N; j.taps = taps;
+  j.nblocks = ((M + 7) / 8) * (N / 32);
+  if (tc_batch()) { tc_batch()->unpack.push_back(j); return 0; }
+  return tc_run_job_now(j, tc_unpack_batched_kernel, stream, cnt);
 }
 
 // ===========================================================================
@@ -1475,14 +1576,14 @@ inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool 
 
 inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* cnt) {
   if (!t.enabled) return 0;
-  const long long total = (long long)t.Cin * t.Cout * t.k * t.k;
-  long long g = (total + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
+  TcPackJob j;
+  memset(&j, 0, sizeof(j));
   if (t.kind == 0) {
-    tc_pack_conv_kernel<<<(unsigned)g, 256, 0, stream>>>(w, t.w_fwd, t.w_dgrad, t.Cout, t.Cin, t.k * t.k);
-    if (cnt) cnt->kernel_launches++;
+    j.kind = 0; j.w = w; j.fwd = t.w_fwd; j.dgrad = t.w_dgrad; j.Cout = t.Cout; j.Cin = t.Cin; j.taps = t.k * t.k;
+    j.nblocks = (t.Cout / 32) * (t.Cin / 32);
   } else {
-    TcPackArgs f, d;
+    TcPackArgs& f = j.f; TcPackArgs& d = j.d;
+    j.kind = 1;
     f.src = d.src = w; f.dst = t.w_fwd; d.dst = t.w_dgrad; f.flip = d.flip = 0;
     if (t.kind == 1) {
       // W[co][ci][ab].  fwd (gather conv): [N=Cout][T=4][K=Cin];  dgrad (scatter GEMM): [N=(ab,ci)][1][K=Cout]
@@ -1493,11 +1594,11 @@ inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* 
       f.N = 4 * t.Cout; f.T = 1; f.K = t.Cin; f.Ninner = t.Cout; f.st = 0; f.sk = (long long)t.Cout * 4; f.snh = 1; f.snl = 4;
       d.N = t.Cin; d.T = 4; d.K = t.Cout; d.Ninner = t.Cin; d.st = 1; d.sk = 4; d.snh = 0; d.snl = (long long)t.Cout * 4;
     }
-    tc_pack_generic_kernel<<<(unsigned)g, 256, 0, stream>>>(f);
-    tc_pack_generic_kernel<<<(unsigned)g, 256, 0, stream>>>(d);
-    if (cnt) cnt->kernel_launches += 2;
+    const long long total = (long long)t.Cin * t.Cout * 4;
+    j.nblocks = (int)((total + kPackGenericPerBlock - 1) / kPackGenericPerBlock);
   }
-  return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+  if (tc_batch()) { tc_batch()->pack.push_back(j); return 0; }
+  return tc_run_job_now(j, tc_pack_batched_kernel, stream, cnt);
 }
 
 inline int tc_env_int(const char* name, int dflt) {
@@ -1993,15 +2094,15 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     }
     attr_set = true;
   }
-  tc_wgrad_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
+  // 1x1 convolutions: [1][M][N] IS the torch layout, so the kernel accumulates straight into the (zeroed)
+  // gradient and nothing is unpacked
   const int taps = ksz * ksz;
-  const long long total = (long long)M * Nn * taps;
-  long long g = (total + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
-  tc_wgrad_unpack_kernel<<<(unsigned)g, 256, 0, stream>>>(t.dw_acc, dw, M, Nn, taps);
-  if (cnt) { cnt->kernel_launches += 2; cnt->tc_kernel_launches++; }
+  c->p.dw_acc = taps == 1 ? dw : t.dw_acc;
+  tc_wgrad_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
+  if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
+  if (taps > 1 && tc_unpack(t.dw_acc, dw, M, Nn, taps, stream, cnt)) { tc_err() = "weight-gradient unpack failed"; return -1; }
   return 0;
 }
 
@@ -2075,13 +2176,10 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     attr_set = true;
   }
   tc_wgrad3_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
-  const long long total = (long long)t.Cout * t.Cin * 9;
-  long long g = (total + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
-  tc_wgrad_unpack_kernel<<<(unsigned)g, 256, 0, stream>>>(t.dw_acc, dw, t.Cout, t.Cin, 9);
-  if (cnt) { cnt->kernel_launches += 2; cnt->tc_kernel_launches++; }
+  if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
+  if (tc_unpack(t.dw_acc, dw, t.Cout, t.Cin, 9, stream, cnt)) { tc_err() = "weight-gradient unpack failed"; return -1; }
   return 0;
 }
 
@@ -2127,6 +2225,7 @@ inline int tc_test_conv(int mode, int B, int H, int W, int Cin, int Cout, int k,
   int rc = 0;
   if (mode == 2) {
     cudaMemsetAsync(mem2, 0, dry2.off + 256, stream);
+    cudaMemsetAsync(dw, 0, (size_t)Cin * Cout * k * k * sizeof(float), stream);   // 1x1 layers accumulate in place
     if (plain) rc = tc_conv_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
     else if (down) rc = tc_down_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
     else rc = tc_up_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);

@@ -11,7 +11,7 @@ kw = dict(n_classes=7, depth=6, wf=5, batch_norm=True, padding=True, max_pool=Fa
 torch.manual_seed(0)
 net = pkg.UNet(precision="bf16", **kw).to(dev).train()
 crit = pkg.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
-opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True)
+opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True, fused=True)
 g = torch.Generator().manual_seed(1)
 x = torch.randn(B, 1, S, S, generator=g).to(dev)
 T = S - 12
