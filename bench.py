@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--torch-loss", action="store_true",
+                    help="use the PyTorch DiceAndHeatMapLoss2D on cropped views instead of the fused device loss")
     return ap.parse_args()
 
 
@@ -168,6 +170,9 @@ def config_dict(args, world):
                         f"{args.size}x{args.size}, train step = fwd + DiceAndHeatMapLoss2D + bwd + SGD(nesterov)",
             "per_gpu_batch": args.batch, "global_batch": args.batch * world, "net_input": args.size, "tile": args.tile,
             "parallelism": f"dp{world}", "precision": args.precision,
+            "loss": "torch DiceAndHeatMapLoss2D on cropped views" if getattr(args, "torch_loss", False)
+                    else "fused device DiceAndHeatMapLoss2D (crop folded in)",
+            "optimizer": "torch.optim.SGD(momentum 0.9, nesterov, wd 1e-4, fused=True)",
             "l2": "per-step working set (~1.5 GB of NHWC activations + 300 MB of weights/grads) >> 126 MB L2; no flush needed"}
 
 
@@ -215,7 +220,10 @@ def run_ours(args):
         pkg.parallel.data_parallel(net)
     # train.py:333-334's optimiser; fused=True is the same update in one multi-tensor kernel
     opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True, fused=True)
-    crit = pkg.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
+    # train.py:324's loss.  Default: the fused device version (same value and gradient, tests/test_loss_gpu.py),
+    # which folds the output crop of train.py:414-417 into its indexing.
+    fused_loss = not args.torch_loss
+    crit = (pkg.FusedDiceAndHeatMapLoss2D if fused_loss else pkg.DiceAndHeatMapLoss2D)(skip_bg=False, heatmap_wgt=0.5)
     B, S, T = args.batch, args.size, args.tile
     g = torch.Generator().manual_seed(100 + rank)
     n_host = 2
@@ -230,7 +238,10 @@ def run_ours(args):
     def train_step(x, mask, heat):
         opt.zero_grad(set_to_none=True)
         seg, hm = net(x)
-        loss = crit((pkg.center_crop(seg, mask.shape), pkg.center_crop(hm, heat.shape)), (mask, heat))
+        if fused_loss:
+            loss = crit((seg, hm), (mask, heat))
+        else:
+            loss = crit((pkg.center_crop(seg, mask.shape), pkg.center_crop(hm, heat.shape)), (mask, heat))
         loss.backward()
         opt.step()
         return loss
@@ -267,6 +278,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     c1 = net.engine_counters()
     launches = c1["kernel_launches"] - c0["kernel_launches"]
+    if fused_loss:
+        launches += 3 * args.steps       # loss_sums, loss_finalize, loss_backward (stateless entry points, not in the engine's counter)
     ms_step = ms / args.steps
     value = B * world / (ms_step * 1e-3)
 

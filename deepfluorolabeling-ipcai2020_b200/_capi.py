@@ -29,9 +29,21 @@ class FuCounters(C.Structure):
         "last_fwd_launches", "last_bwd_launches")]
 
 
+class FuLossDesc(C.Structure):
+    """include/fluoro_unet.h: fu_loss_desc"""
+    _fields_ = [("seg", C.c_void_p), ("seg_stride", C.c_int64 * 3),
+                ("mask", C.c_void_p), ("mask_stride", C.c_int64 * 3),
+                ("heat", C.c_void_p), ("heat_stride", C.c_int64 * 3),
+                ("heat_t", C.c_void_p), ("heat_t_stride", C.c_int64 * 3),
+                ("B", C.c_int32), ("n_classes", C.c_int32), ("num_lands", C.c_int32),
+                ("Ht", C.c_int32), ("Wt", C.c_int32), ("skip_bg", C.c_int32),
+                ("dice_wgt", C.c_float), ("heat_wgt", C.c_float)]
+
+
 EXPORTS = ["fu_engine_create", "fu_engine_destroy", "fu_last_error", "fu_num_tensors",
            "fu_tensor_get_info", "fu_grad_numel", "fu_bind_tensors", "fu_forward", "fu_backward",
-           "fu_get_counters", "fu_build_info", "fu_test_conv", "fu_profile_enable", "fu_profile_report", "fu_debug_copy"]
+           "fu_get_counters", "fu_build_info", "fu_test_conv", "fu_profile_enable", "fu_profile_report", "fu_debug_copy",
+           "fu_loss_workspace_doubles", "fu_loss_forward", "fu_loss_backward"]
 
 _lib = None
 
@@ -77,6 +89,12 @@ def lib():
     L.fu_build_info.restype = C.c_char_p
     L.fu_test_conv.argtypes = [i32] * 12 + [vp] * 8
     L.fu_test_conv.restype = i32
+    L.fu_loss_workspace_doubles.argtypes = [i32, i32, i32]
+    L.fu_loss_workspace_doubles.restype = i64
+    L.fu_loss_forward.argtypes = [C.POINTER(FuLossDesc), vp, vp, vp]
+    L.fu_loss_forward.restype = i32
+    L.fu_loss_backward.argtypes = [C.POINTER(FuLossDesc), vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    L.fu_loss_backward.restype = i32
     _lib = L
     return L
 

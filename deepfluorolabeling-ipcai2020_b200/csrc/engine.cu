@@ -16,6 +16,7 @@
 #include "../../include/fluoro_unet.h"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_loss.cuh"
 
 using namespace fu;
 
@@ -1415,6 +1416,65 @@ int64_t fu_profile_report(fu_engine* e, char* buf, int64_t cap) {
     buf[n] = 0;
   }
   return (int64_t)out.size() + 1;
+}
+
+// ---- fused loss (kernels_loss.cuh) ----
+static int loss_args(const fu_loss_desc* d, LossArgs& a) {
+  if (!d || !d->seg || !d->mask || d->B < 1 || d->n_classes < 1 || d->Ht < 1 || d->Wt < 1 || d->num_lands < 0) {
+    g_create_error = "fu_loss: bad descriptor";
+    return FU_ERR_ARG;
+  }
+  if ((d->heat == nullptr) != (d->num_lands == 0) || (d->heat && !d->heat_t)) {
+    g_create_error = "fu_loss: heat / heat_t / num_lands disagree";
+    return FU_ERR_ARG;
+  }
+  if ((long long)d->Ht * d->Wt < 2) { g_create_error = "fu_loss: ncc needs at least 2 pixels (ncc.py:14)"; return FU_ERR_ARG; }
+  memset(&a, 0, sizeof(a));
+  a.seg = d->seg; a.seg_sb = d->seg_stride[0]; a.seg_sc = d->seg_stride[1]; a.seg_sr = (int)d->seg_stride[2];
+  a.mask = d->mask; a.mask_sb = d->mask_stride[0]; a.mask_sc = d->mask_stride[1]; a.mask_sr = (int)d->mask_stride[2];
+  a.heat = d->heat; a.heat_sb = d->heat_stride[0]; a.heat_sc = d->heat_stride[1]; a.heat_sr = (int)d->heat_stride[2];
+  a.heat_t = d->heat_t; a.heat_t_sb = d->heat_t_stride[0]; a.heat_t_sc = d->heat_t_stride[1]; a.heat_t_sr = (int)d->heat_t_stride[2];
+  a.B = d->B; a.NC = d->n_classes; a.NL = d->num_lands; a.Ht = d->Ht; a.Wt = d->Wt;
+  a.skip_bg = d->skip_bg ? 1 : 0; a.dice_wgt = d->dice_wgt; a.heat_wgt = d->heat_wgt;
+  if (a.skip_bg && a.NC < 2) { g_create_error = "fu_loss: skip_bg needs at least 2 classes"; return FU_ERR_ARG; }
+  return FU_OK;
+}
+
+int64_t fu_loss_workspace_doubles(int B, int n_classes, int num_lands) {
+  return (int64_t)B * (3 * (int64_t)n_classes + 5 * (int64_t)num_lands);
+}
+
+int fu_loss_forward(const fu_loss_desc* d, double* sums, float* loss_out, void* stream) {
+  LossArgs a;
+  int rc = loss_args(d, a);
+  if (rc) return rc;
+  if (!sums || !loss_out) { g_create_error = "fu_loss_forward: null workspace / output"; return FU_ERR_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  a.sums = sums;
+  const size_t ws = (size_t)fu_loss_workspace_doubles(a.B, a.NC, a.NL) * sizeof(double);
+  if (cudaMemsetAsync(sums, 0, ws, st) != cudaSuccess) { g_create_error = "fu_loss_forward: memset failed"; return FU_ERR_CUDA; }
+  const dim3 grid((unsigned)((a.Ht * a.Wt + kLossChunk - 1) / kLossChunk), (unsigned)(a.B * (a.NC + a.NL)));
+  loss_sums_kernel<<<grid, 256, 0, st>>>(a);
+  loss_finalize_kernel<<<1, 256, 0, st>>>(a, loss_out);
+  cudaError_t ce = cudaPeekAtLastError();
+  if (ce != cudaSuccess) { g_create_error = std::string("fu_loss_forward: ") + cudaGetErrorString(ce); return FU_ERR_CUDA; }
+  return FU_OK;
+}
+
+int fu_loss_backward(const fu_loss_desc* d, const double* sums, const float* dloss, int H, int W, int r0, int c0,
+                     float* d_seg, float* d_heat, void* stream) {
+  LossBwdArgs q;
+  int rc = loss_args(d, q.a);
+  if (rc) return rc;
+  if (!sums || !dloss || !d_seg || (q.a.NL > 0 && !d_heat)) { g_create_error = "fu_loss_backward: null argument"; return FU_ERR_ARG; }
+  if (r0 < 0 || c0 < 0 || r0 + q.a.Ht > H || c0 + q.a.Wt > W) { g_create_error = "fu_loss_backward: window outside the output"; return FU_ERR_ARG; }
+  q.a.sums = const_cast<double*>(sums);
+  q.dloss = dloss; q.d_seg = d_seg; q.d_heat = d_heat; q.H = H; q.W = W; q.r0 = r0; q.c0 = c0;
+  const dim3 grid((unsigned)((H * W + kLossChunk - 1) / kLossChunk), (unsigned)(q.a.B * (q.a.NC + q.a.NL)));
+  loss_backward_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+  cudaError_t ce = cudaPeekAtLastError();
+  if (ce != cudaSuccess) { g_create_error = std::string("fu_loss_backward: ") + cudaGetErrorString(ce); return FU_ERR_CUDA; }
+  return FU_OK;
 }
 
 const char* fu_build_info(void) {

@@ -1,0 +1,188 @@
+// Fused training loss of the reference: DiceLoss2D / DiceAndHeatMapLoss2D
+// (dice.py:14-86) over ncc_2d (ncc.py:12-38), with the centre crop of the network outputs
+// (util.py:92-114, called at train.py:414-417) folded into the indexing.
+//
+// The PyTorch formulation makes ~25 elementwise / reduction passes over the (B,7+14,H,W) outputs and
+// their cropped views (0.9 ms of a 8.5 ms step at B=32, 192x192); here the forward is ONE pass that
+// reduces every (image, channel) plane to 3 (Dice) or 5 (NCC) fp64 sums, a one-block kernel turns the
+// sums into the scalar loss, and the backward is ONE pass that writes the full-size (uncropped)
+// gradients of both outputs, zeros outside the crop window, straight from the closed-form derivative.
+#pragma once
+#include "common.cuh"
+
+namespace fu {
+
+struct LossArgs {
+  const float* seg; long long seg_sb, seg_sc; int seg_sr;        // prediction strides: batch, channel, row (elements)
+  const float* mask; long long mask_sb, mask_sc; int mask_sr;
+  const float* heat; long long heat_sb, heat_sc; int heat_sr;    // heat == nullptr: Dice only
+  const float* heat_t; long long heat_t_sb, heat_t_sc; int heat_t_sr;
+  int B, NC, NL;
+  int Ht, Wt;                   // window (= target) size; prediction pointers already address the window origin
+  int skip_bg;
+  float dice_wgt, heat_wgt;
+  double* sums;                 // [B][NC*3 + NL*5]
+};
+
+constexpr int kLossChunk = 2048;     // window elements per block
+
+__device__ __forceinline__ double block_sum_double(double v, double* sm) {
+  // 256 threads: warp shuffle, then one value per warp through shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 8) t = sm[threadIdx.x];
+  if (w == 0) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;    // valid in thread 0
+}
+
+// grid: (chunks of the window, B*(NC+NL) planes)
+__global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
+  __shared__ double sm[8];
+  const int plane = blockIdx.y;
+  const int b = plane / (p.NC + p.NL), c = plane - b * (p.NC + p.NL);
+  const int n_win = p.Ht * p.Wt;
+  const int i0 = blockIdx.x * kLossChunk;
+  const int i1 = min(i0 + kLossChunk, n_win);
+  const int per = p.NC * 3 + p.NL * 5;
+  if (c < p.NC) {
+    const float* x = p.seg + b * p.seg_sb + c * p.seg_sc;
+    const float* t = p.mask + b * p.mask_sb + c * p.mask_sc;
+    double s_tp = 0.0, s_tt = 0.0, s_pp = 0.0;
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+      const int r = i / p.Wt, col = i - r * p.Wt;
+      const float xv = x[(long long)r * p.seg_sr + col], tv = t[(long long)r * p.mask_sr + col];
+      s_tp += (double)(tv * xv); s_tt += (double)(tv * tv); s_pp += (double)(xv * xv);
+    }
+    s_tp = block_sum_double(s_tp, sm); s_tt = block_sum_double(s_tt, sm); s_pp = block_sum_double(s_pp, sm);
+    if (threadIdx.x == 0) {
+      double* o = p.sums + (long long)b * per + c * 3;
+      atomicAdd(o, s_tp); atomicAdd(o + 1, s_tt); atomicAdd(o + 2, s_pp);
+    }
+  } else {
+    const int l = c - p.NC;
+    const float* x = p.heat + b * p.heat_sb + l * p.heat_sc;
+    const float* y = p.heat_t + b * p.heat_t_sb + l * p.heat_t_sc;
+    double sx = 0.0, sxx = 0.0, sy = 0.0, syy = 0.0, sxy = 0.0;
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+      const int r = i / p.Wt, col = i - r * p.Wt;
+      const double xv = x[(long long)r * p.heat_sr + col], yv = y[(long long)r * p.heat_t_sr + col];
+      sx += xv; sxx += xv * xv; sy += yv; syy += yv * yv; sxy += xv * yv;
+    }
+    sx = block_sum_double(sx, sm); sxx = block_sum_double(sxx, sm); sy = block_sum_double(sy, sm);
+    syy = block_sum_double(syy, sm); sxy = block_sum_double(sxy, sm);
+    if (threadIdx.x == 0) {
+      double* o = p.sums + (long long)b * per + p.NC * 3 + l * 5;
+      atomicAdd(o, sx); atomicAdd(o + 1, sxx); atomicAdd(o + 2, sy); atomicAdd(o + 3, syy); atomicAdd(o + 4, sxy);
+    }
+  }
+}
+
+// per-plane NCC pieces from the raw moments (ncc.py:12-38: sample standard deviations, 1e-8 in the denominator)
+struct NccTerms { double mx, my, sdx, sdy, sxy_c, den; };
+__device__ __forceinline__ NccTerms ncc_terms(const double* m, double N) {
+  NccTerms t;
+  t.mx = m[0] / N; t.my = m[2] / N;
+  const double vxx = fmax(m[1] - N * t.mx * t.mx, 0.0), vyy = fmax(m[3] - N * t.my * t.my, 0.0);
+  t.sdx = sqrt(vxx / (N - 1.0)); t.sdy = sqrt(vyy / (N - 1.0));
+  t.sxy_c = m[4] - N * t.mx * t.my;
+  t.den = N * t.sdx * t.sdy + 1.0e-8;
+  return t;
+}
+
+// one block: the scalar loss (dice.py:48-55, 74-86)
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const LossArgs p, float* loss_out) {
+  __shared__ double sm[8];
+  const int per = p.NC * 3 + p.NL * 5;
+  const int c_first = p.skip_bg ? 1 : 0;
+  const int n_cls = p.NC - c_first;
+  const double N = (double)p.Ht * p.Wt;
+  double dice = 0.0, ncc = 0.0;
+  for (int i = threadIdx.x; i < p.B * p.NC; i += 256) {
+    const int b = i / p.NC, c = i - b * p.NC;
+    if (c < c_first) continue;
+    const double* s = p.sums + (long long)b * per + c * 3;
+    dice += (-2.0 * s[0] + 1.0e-4) / (s[1] + s[2] + 1.0e-4);
+  }
+  for (int i = threadIdx.x; i < p.B * p.NL; i += 256) {
+    const int b = i / p.NL, l = i - b * p.NL;
+    const NccTerms t = ncc_terms(p.sums + (long long)b * per + p.NC * 3 + l * 5, N);
+    ncc += (t.sxy_c / t.den + 1.0) * -0.5;
+  }
+  dice = block_sum_double(dice, sm);
+  ncc = block_sum_double(ncc, sm);
+  if (threadIdx.x == 0) {
+    double loss = (double)p.dice_wgt * dice / ((double)n_cls * p.B);
+    if (p.NL > 0) loss += (double)p.heat_wgt * ncc / ((double)p.B * p.NL);
+    *loss_out = (float)loss;
+  }
+}
+
+struct LossBwdArgs {
+  LossArgs a;
+  const float* dloss;           // device scalar: upstream gradient of the loss
+  float* d_seg; float* d_heat;  // full-size contiguous (B,NC,H,W) / (B,NL,H,W) gradients
+  int H, W, r0, c0;             // full output size and window origin
+};
+
+// grid: (chunks of the FULL plane, B*(NC+NL) planes); zeros outside the window
+__global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q) {
+  const LossArgs& p = q.a;
+  const int plane = blockIdx.y;
+  const int b = plane / (p.NC + p.NL), c = plane - b * (p.NC + p.NL);
+  const int per = p.NC * 3 + p.NL * 5;
+  const int n_full = q.H * q.W;
+  const int i0 = blockIdx.x * kLossChunk;
+  const int i1 = min(i0 + kLossChunk, n_full);
+  const float up = *q.dloss;
+  if (c < p.NC) {
+    float* g = q.d_seg + ((long long)b * p.NC + c) * n_full;
+    const int c_first = p.skip_bg ? 1 : 0;
+    const double* s = p.sums + (long long)b * per + c * 3;
+    const double num = -2.0 * s[0] + 1.0e-4, den = s[1] + s[2] + 1.0e-4;
+    // d(num/den)/dp = (-2 t den - 2 p num) / den^2
+    const float k = c < c_first ? 0.f : (float)((double)up * p.dice_wgt / ((double)(p.NC - c_first) * p.B) / (den * den));
+    const float fden = (float)den, fnum = (float)num;
+    const float* x = p.seg + b * p.seg_sb + c * p.seg_sc;
+    const float* t = p.mask + b * p.mask_sb + c * p.mask_sc;
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+      const int r = i / q.W - q.r0, col = i % q.W - q.c0;
+      float v = 0.f;
+      if (r >= 0 && r < p.Ht && col >= 0 && col < p.Wt && k != 0.f) {
+        const float xv = x[(long long)r * p.seg_sr + col], tv = t[(long long)r * p.mask_sr + col];
+        v = k * (-2.f * tv * fden - 2.f * xv * fnum);
+      }
+      g[i] = v;
+    }
+  } else {
+    const int l = c - p.NC;
+    float* g = q.d_heat + ((long long)b * p.NL + l) * n_full;
+    const double N = (double)p.Ht * p.Wt;
+    const NccTerms t = ncc_terms(p.sums + (long long)b * per + p.NC * 3 + l * 5, N);
+    // ncc = Sxy / D, D = N sdx sdy + 1e-8:  d ncc / dx_i = (y_i - my)/D - Sxy N sdy (x_i - mx) / ((N-1) sdx D^2)
+    const double w = (double)up * p.heat_wgt * -0.5 / ((double)p.B * p.NL);
+    const float ka = (float)(w / t.den);
+    const float kb = t.sdx > 0.0 ? (float)(w * t.sxy_c * N * t.sdy / ((N - 1.0) * t.sdx * t.den * t.den)) : 0.f;
+    const float mx = (float)t.mx, my = (float)t.my;
+    const float* x = p.heat + b * p.heat_sb + l * p.heat_sc;
+    const float* y = p.heat_t + b * p.heat_t_sb + l * p.heat_t_sc;
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+      const int r = i / q.W - q.r0, col = i % q.W - q.c0;
+      float v = 0.f;
+      if (r >= 0 && r < p.Ht && col >= 0 && col < p.Wt) {
+        const float xv = x[(long long)r * p.heat_sr + col], yv = y[(long long)r * p.heat_t_sr + col];
+        v = ka * (yv - my) - kb * (xv - mx);
+      }
+      g[i] = v;
+    }
+  }
+}
+
+}  // namespace fu

@@ -2060,7 +2060,7 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
     const long long total_pt = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
-    long long splits = (2ll * sms + units - 1) / units;       // ~2 CTAs per SM in flight over the launch
+    long long splits = ((long long)tc_env_int("FU_TC_WGRAD_WAVES", 2) * sms + units - 1) / units;   // CTAs per SM over the launch
     const long long max_splits = (total_pt + 3) / 4;          // at least 4 pixel tiles per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -2143,7 +2143,7 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
     const long long total_kt = (long long)B * H * p.segs;
-    long long splits = (2ll * sms + units - 1) / units;
+    long long splits = ((long long)tc_env_int("FU_TC_WGRAD3_WAVES", 2) * sms + units - 1) / units;
     const long long max_splits = (total_kt + 7) / 8;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -149,6 +149,34 @@ int64_t fu_profile_report(fu_engine* e, char* buf, int64_t cap);
  * (B,C,H,W); with dst == NULL only the shape is returned.  Enqueued on the stream of the last call. */
 int fu_debug_copy(fu_engine* e, const char* name, float* dst, int64_t capacity, int32_t* shape4);
 
+/* ---- fused training loss -------------------------------------------------
+ * DiceLoss2D / DiceAndHeatMapLoss2D of dice.py:14-86 over ncc_2d (ncc.py:12-38), with the centre
+ * crop of the network outputs (util.py:92-114 as called at train.py:414-417) folded in: the
+ * prediction pointers address the first element of the crop WINDOW inside the full (B,C,H,W) output
+ * and the strides are those of the full tensor.  All tensors fp32, column stride 1.
+ *   loss = dice_wgt * mean_b( mean_c( (-2 sum(t p) + 1e-4) / (sum(t^2) + sum(p^2) + 1e-4) ) )
+ *        + heat_wgt * mean_{b,l}( -(ncc(heat, heat_t) + 1) / 2 )          [second term iff heat != NULL]
+ * DiceLoss2D (train.py:327) is heat == NULL, dice_wgt = 1.  Stateless: no engine handle. */
+typedef struct fu_loss_desc {
+  const float* seg;    int64_t seg_stride[3];     /* batch, channel, row strides in elements */
+  const float* mask;   int64_t mask_stride[3];    /* targets (B,n_classes,Ht,Wt) */
+  const float* heat;   int64_t heat_stride[3];    /* NULL: Dice only */
+  const float* heat_t; int64_t heat_t_stride[3];  /* (B,num_lands,Ht,Wt) */
+  int32_t B, n_classes, num_lands;                /* num_lands = 0 when heat == NULL */
+  int32_t Ht, Wt;                                 /* window size = target size */
+  int32_t skip_bg;                                /* dice.py:16: leave class 0 out of the Dice mean */
+  float dice_wgt, heat_wgt;                       /* dice.py:65-66: dice_wgt = 1 - heatmap_wgt */
+} fu_loss_desc;
+/* doubles of workspace both calls share: per image 3 sums per class + 5 per landmark */
+int64_t fu_loss_workspace_doubles(int B, int n_classes, int num_lands);
+/* sums (workspace) is zeroed and filled; loss_out is one device float. */
+int fu_loss_forward(const fu_loss_desc* d, double* sums, float* loss_out, void* stream);
+/* Gradients of the loss w.r.t. the FULL outputs: d_seg (B,n_classes,H,W), d_heat (B,num_lands,H,W;
+ * NULL iff heat == NULL), contiguous, zero outside the window whose origin is (r0,c0).  dloss is the
+ * upstream gradient (one device float).  `sums` is the workspace fu_loss_forward filled. */
+int fu_loss_backward(const fu_loss_desc* d, const double* sums, const float* dloss, int H, int W,
+                     int r0, int c0, float* d_seg, float* d_heat, void* stream);
+
 /* Build information: "sm_100a;tcgen05=1;..." */
 const char* fu_build_info(void);
 

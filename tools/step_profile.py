@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 kw = dict(n_classes=7, depth=6, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=14)
 torch.manual_seed(0)
 net = pkg.UNet(precision="bf16", **kw).to(dev).train()
-crit = pkg.DiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
+crit = pkg.FusedDiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
 opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, nesterov=True, fused=True)
 g = torch.Generator().manual_seed(1)
 x = torch.randn(B, 1, S, S, generator=g).to(dev)
@@ -21,7 +21,7 @@ heat = torch.rand(B, 14, T, T, generator=g).to(dev)
 def step():
     opt.zero_grad(set_to_none=True)
     seg, hm = net(x)
-    loss = crit((pkg.center_crop(seg, mask.shape), pkg.center_crop(hm, heat.shape)), (mask, heat))
+    loss = crit((seg, hm), (mask, heat))
     loss.backward()
     opt.step()
     return loss
