@@ -24,7 +24,7 @@ struct LossArgs {
   double* sums;                 // [B][NC*3 + NL*5]
 };
 
-constexpr int kLossChunk = 2048;     // window elements per block
+constexpr int kLossRows = 16;        // image rows per block: warp w takes rows w, w+8; lanes stride the columns
 
 __device__ __forceinline__ double block_sum_double(double v, double* sm) {
   // 256 threads: warp shuffle, then one value per warp through shared memory
@@ -43,23 +43,27 @@ __device__ __forceinline__ double block_sum_double(double v, double* sm) {
   return t;    // valid in thread 0
 }
 
-// grid: (chunks of the window, B*(NC+NL) planes)
+// grid: (row chunks of the window, B*(NC+NL) planes)
 __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
   __shared__ double sm[8];
   const int plane = blockIdx.y;
   const int b = plane / (p.NC + p.NL), c = plane - b * (p.NC + p.NL);
-  const int n_win = p.Ht * p.Wt;
-  const int i0 = blockIdx.x * kLossChunk;
-  const int i1 = min(i0 + kLossChunk, n_win);
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int r_begin = blockIdx.x * kLossRows, r_end = min(r_begin + kLossRows, p.Ht);
   const int per = p.NC * 3 + p.NL * 5;
   if (c < p.NC) {
     const float* x = p.seg + b * p.seg_sb + c * p.seg_sc;
     const float* t = p.mask + b * p.mask_sb + c * p.mask_sc;
     double s_tp = 0.0, s_tt = 0.0, s_pp = 0.0;
-    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-      const int r = i / p.Wt, col = i - r * p.Wt;
-      const float xv = x[(long long)r * p.seg_sr + col], tv = t[(long long)r * p.mask_sr + col];
-      s_tp += (double)(tv * xv); s_tt += (double)(tv * tv); s_pp += (double)(xv * xv);
+    for (int r = r_begin + wrp; r < r_end; r += 8) {
+      const float* xr = x + (long long)r * p.seg_sr;
+      const float* tr = t + (long long)r * p.mask_sr;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;              // <= 8 columns per lane and row: fp32 is exact enough here
+      for (int col = lane; col < p.Wt; col += 32) {
+        const float xv = xr[col], tv = tr[col];
+        a0 = fmaf(tv, xv, a0); a1 = fmaf(tv, tv, a1); a2 = fmaf(xv, xv, a2);
+      }
+      s_tp += (double)a0; s_tt += (double)a1; s_pp += (double)a2;
     }
     s_tp = block_sum_double(s_tp, sm); s_tt = block_sum_double(s_tt, sm); s_pp = block_sum_double(s_pp, sm);
     if (threadIdx.x == 0) {
@@ -71,10 +75,13 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
     const float* x = p.heat + b * p.heat_sb + l * p.heat_sc;
     const float* y = p.heat_t + b * p.heat_t_sb + l * p.heat_t_sc;
     double sx = 0.0, sxx = 0.0, sy = 0.0, syy = 0.0, sxy = 0.0;
-    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-      const int r = i / p.Wt, col = i - r * p.Wt;
-      const double xv = x[(long long)r * p.heat_sr + col], yv = y[(long long)r * p.heat_t_sr + col];
-      sx += xv; sxx += xv * xv; sy += yv; syy += yv * yv; sxy += xv * yv;
+    for (int r = r_begin + wrp; r < r_end; r += 8) {
+      const float* xr = x + (long long)r * p.heat_sr;
+      const float* yr = y + (long long)r * p.heat_t_sr;
+      for (int col = lane; col < p.Wt; col += 32) {
+        const double xv = xr[col], yv = yr[col];     // fp64 throughout: the variances below are differences of sums
+        sx += xv; sxx += xv * xv; sy += yv; syy += yv * yv; sxy += xv * yv;
+      }
     }
     sx = block_sum_double(sx, sm); sxx = block_sum_double(sxx, sm); sy = block_sum_double(sy, sm);
     syy = block_sum_double(syy, sm); sxy = block_sum_double(sxy, sm);
@@ -132,15 +139,15 @@ struct LossBwdArgs {
   int H, W, r0, c0;             // full output size and window origin
 };
 
-// grid: (chunks of the FULL plane, B*(NC+NL) planes); zeros outside the window
+// grid: (row chunks of the FULL plane, B*(NC+NL) planes); zeros outside the window
 __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q) {
   const LossArgs& p = q.a;
   const int plane = blockIdx.y;
   const int b = plane / (p.NC + p.NL), c = plane - b * (p.NC + p.NL);
   const int per = p.NC * 3 + p.NL * 5;
-  const int n_full = q.H * q.W;
-  const int i0 = blockIdx.x * kLossChunk;
-  const int i1 = min(i0 + kLossChunk, n_full);
+  const long long n_full = (long long)q.H * q.W;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int R_begin = blockIdx.x * kLossRows, R_end = min(R_begin + kLossRows, q.H);
   const float up = *q.dloss;
   if (c < p.NC) {
     float* g = q.d_seg + ((long long)b * p.NC + c) * n_full;
@@ -152,14 +159,17 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q)
     const float fden = (float)den, fnum = (float)num;
     const float* x = p.seg + b * p.seg_sb + c * p.seg_sc;
     const float* t = p.mask + b * p.mask_sb + c * p.mask_sc;
-    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-      const int r = i / q.W - q.r0, col = i % q.W - q.c0;
-      float v = 0.f;
-      if (r >= 0 && r < p.Ht && col >= 0 && col < p.Wt && k != 0.f) {
-        const float xv = x[(long long)r * p.seg_sr + col], tv = t[(long long)r * p.mask_sr + col];
-        v = k * (-2.f * tv * fden - 2.f * xv * fnum);
+    for (int R = R_begin + wrp; R < R_end; R += 8) {
+      const int r = R - q.r0;
+      const bool row_in = r >= 0 && r < p.Ht && k != 0.f;
+      const float* xr = x + (long long)r * p.seg_sr;
+      const float* tr = t + (long long)r * p.mask_sr;
+      for (int C = lane; C < q.W; C += 32) {
+        const int col = C - q.c0;
+        float v = 0.f;
+        if (row_in && col >= 0 && col < p.Wt) v = k * (-2.f * tr[col] * fden - 2.f * xr[col] * fnum);
+        g[(long long)R * q.W + C] = v;
       }
-      g[i] = v;
     }
   } else {
     const int l = c - p.NC;
@@ -173,14 +183,17 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q)
     const float mx = (float)t.mx, my = (float)t.my;
     const float* x = p.heat + b * p.heat_sb + l * p.heat_sc;
     const float* y = p.heat_t + b * p.heat_t_sb + l * p.heat_t_sc;
-    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
-      const int r = i / q.W - q.r0, col = i % q.W - q.c0;
-      float v = 0.f;
-      if (r >= 0 && r < p.Ht && col >= 0 && col < p.Wt) {
-        const float xv = x[(long long)r * p.heat_sr + col], yv = y[(long long)r * p.heat_t_sr + col];
-        v = ka * (yv - my) - kb * (xv - mx);
+    for (int R = R_begin + wrp; R < R_end; R += 8) {
+      const int r = R - q.r0;
+      const bool row_in = r >= 0 && r < p.Ht;
+      const float* xr = x + (long long)r * p.heat_sr;
+      const float* yr = y + (long long)r * p.heat_t_sr;
+      for (int C = lane; C < q.W; C += 32) {
+        const int col = C - q.c0;
+        float v = 0.f;
+        if (row_in && col >= 0 && col < p.Wt) v = ka * (yr[col] - my) - kb * (xr[col] - mx);
+        g[(long long)R * q.W + C] = v;
       }
-      g[i] = v;
     }
   }
 }

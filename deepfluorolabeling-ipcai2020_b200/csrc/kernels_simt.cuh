@@ -1177,9 +1177,15 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const T* r, int 
                                                                 long long P, int C);
 
 // 16-byte vector access per storage type: 4 fp32 or 8 bf16 channels per thread
+// 16-byte vectors of the two storage types.  `raw`/`unpack` split a load from its conversion so that several
+// loads can be in flight while costing 4 registers each.
+__device__ __forceinline__ uint4 ld_raw16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 template <typename T> struct Vec;
 template <> struct Vec<float> {
   static constexpr int N = 4;
+  __device__ static __forceinline__ void unpack(const uint4& u, float* v) {
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+  }
   __device__ static __forceinline__ void load(const float* p, float* v) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -1190,6 +1196,14 @@ template <> struct Vec<float> {
 };
 template <> struct Vec<bf16> {
   static constexpr int N = 8;
+  __device__ static __forceinline__ void unpack(const uint4& u, float* v) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
   __device__ static __forceinline__ void load(const bf16* p, float* v) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -1334,14 +1348,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* d, int d_ld
     for (int i = 0; i < V; ++i) { mu[i] = mean[c + i]; is[i] = invstd[c + i]; }
     const long long step = (long long)gridDim.x * mp.rows;
     long long pix = (long long)blockIdx.x * mp.rows + mp.prow;
-    for (; pix + step < P; pix += 2 * step) {        // two pixels in flight per thread
-      float d0[V], r0[V], d1[V], r1[V];
-      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
-      Vec<T>::load(d + (pix + step) * d_ld + c, d1); Vec<T>::load(r + (pix + step) * r_ld + c, r1);
+    for (; pix + 3 * step < P; pix += 4 * step) {    // four pixels (eight 16-byte loads) in flight per thread
+      uint4 dq[4], rq[4];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        s1[i] += d0[i] + d1[i];
-        s2[i] += d0[i] * (r0[i] - mu[i]) * is[i] + d1[i] * (r1[i] - mu[i]) * is[i];
+      for (int u = 0; u < 4; ++u) {
+        dq[u] = ld_raw16(d + (pix + u * step) * d_ld + c);
+        rq[u] = ld_raw16(r + (pix + u * step) * r_ld + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float d0[V], r0[V];
+        Vec<T>::unpack(dq[u], d0); Vec<T>::unpack(rq[u], r0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s1[i] += d0[i]; s2[i] += d0[i] * (r0[i] - mu[i]) * is[i]; }
       }
     }
     for (; pix < P; pix += step) {
@@ -1421,12 +1440,19 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* d, int d_ld, cons
 #pragma unroll
       for (int i = 0; i < V; ++i) s[i] += rnd(o[i], dst);
     };
-    for (; pix + step < P; pix += 2 * step) {
-      float d0[V], r0[V], d1[V], r1[V];
-      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
-      Vec<T>::load(d + (pix + step) * d_ld + c, d1); Vec<T>::load(r + (pix + step) * r_ld + c, r1);
-      one(d0, r0, dy + pix * dy_ld + c);
-      one(d1, r1, dy + (pix + step) * dy_ld + c);
+    for (; pix + 3 * step < P; pix += 4 * step) {    // four pixels (eight 16-byte loads) in flight per thread
+      uint4 dq[4], rq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dq[u] = ld_raw16(d + (pix + u * step) * d_ld + c);
+        rq[u] = ld_raw16(r + (pix + u * step) * r_ld + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float d0[V], r0[V];
+        Vec<T>::unpack(dq[u], d0); Vec<T>::unpack(rq[u], r0);
+        one(d0, r0, dy + (pix + u * step) * dy_ld + c);
+      }
     }
     for (; pix < P; pix += step) {
       float d0[V], r0[V];

@@ -1065,11 +1065,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       if (ptx::elect_one()) {
         const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
         const uint64_t ad0 = umma_desc_at(dbase, a_addr);
-        for (int t = 0; t < p.taps_per_cta; ++t) {
-          const uint64_t bd0 = umma_desc_at(dbase, a_addr + a_bytes + (uint32_t)(t * nblk_b) * kBox);
-          for (int ks = 0; ks < 4; ++ks)      // 64 pixels = 4 x K16; 16 pixel rows = 2048 B = +128 in the address field
+        // 64 pixels = 4 x K16; 16 pixel rows = 2048 B = +128 in the address field.  K step outermost so that
+        // consecutive MMAs accumulate into different taps' accumulators.
+        for (int ks = 0; ks < 4; ++ks) {
+          for (int t = 0; t < p.taps_per_cta; ++t) {
+            const uint64_t bd0 = umma_desc_at(dbase, a_addr + a_bytes + (uint32_t)(t * nblk_b) * kBox);
             ptx::umma_bf16(tmem_base + (uint32_t)(t * p.N), ad0 + (uint64_t)(128 * ks), bd0 + (uint64_t)(128 * ks), idesc,
                            (it | ks) != 0 ? 1u : 0u);
+          }
         }
         ptx::umma_commit(empty_bar(stage));
         if (it == n_iters - 1) ptx::umma_commit(done_bar);
@@ -1240,24 +1243,24 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const uint64_t bd0 = db + (uint64_t)((a_addr + a_bytes) >> 4);
         const uint64_t bd0s = dbs + (uint64_t)((a_addr + a_bytes) >> 4);
         const uint32_t accum = it != 0 ? 1u : 0u;
+        // K step outermost: consecutive MMAs go to DIFFERENT accumulators, so a dependent accumulation is
+        // never issued back to back
         if (p.stack) {
+          for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            if (3 * r < tpg) {
-              const uint32_t d_t = tmem_base + (uint32_t)(3 * r * Nn);
-              for (int ks = 0; ks < ksteps; ++ks)
-                ptx::umma_bf16(d_t, ad0 + (uint64_t)(ks * step_a16), bd0s + (uint64_t)(tapoff16[3 * r] + ks * step_b16), idesc_s,
-                               accum | (uint32_t)ks);
+            for (int r = 0; r < 3; ++r) {
+              if (3 * r < tpg)
+                ptx::umma_bf16(tmem_base + (uint32_t)(3 * r * Nn), ad0 + (uint64_t)(ks * step_a16),
+                               bd0s + (uint64_t)(tapoff16[3 * r] + ks * step_b16), idesc_s, accum | (uint32_t)ks);
             }
           }
         } else {
+          for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            if (t < tpg) {
-              const uint32_t d_t = tmem_base + (uint32_t)(t * Nn);
-              for (int ks = 0; ks < ksteps; ++ks)
-                ptx::umma_bf16(d_t, ad0 + (uint64_t)(ks * step_a16), bd0 + (uint64_t)(tapoff16[t] + ks * step_b16), idesc,
-                               accum | (uint32_t)ks);
+            for (int t = 0; t < 9; ++t) {
+              if (t < tpg)
+                ptx::umma_bf16(tmem_base + (uint32_t)(t * Nn), ad0 + (uint64_t)(ks * step_a16),
+                               bd0 + (uint64_t)(tapoff16[t] + ks * step_b16), idesc, accum | (uint32_t)ks);
             }
           }
         }
@@ -1339,28 +1342,39 @@ __device__ __forceinline__ int tc_find_job(const Job* jobs, int njobs, int* s_jo
   return *s_job;
 }
 
+// one 32 (co) x 32 (ci) x TAPS tile; the loops are warp = row, lane = column, so no division by a run-time value
+template <int TAPS>
+__device__ __forceinline__ void tc_pack_tile(const TcPackJob& J, int lb, float* tile) {
+  const int tiles_ci = J.Cin / 32;
+  const int co0 = (lb / tiles_ci) * 32, ci0 = (lb % tiles_ci) * 32;
+  constexpr int ROW = 32 * TAPS;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int r = wrp; r < 32; r += 8) {
+    const float* src = J.w + ((long long)(co0 + r) * J.Cin + ci0) * TAPS;
+#pragma unroll
+    for (int c = lane; c < ROW; c += 32) tile[r * 289 + c] = src[c];
+  }
+  __syncthreads();
+  for (int r = wrp; r < 32; r += 8) {           // forward: rows co, (t, ci) contiguous per co
+    bf16* dst = J.fwd + (long long)(co0 + r) * TAPS * J.Cin + ci0 + lane;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) dst[(long long)t * J.Cin] = __float2bfloat16_rn(tile[r * 289 + lane * TAPS + t]);
+  }
+  for (int ci = wrp; ci < 32; ci += 8) {        // data gradient: rows ci, (flipped t, co) contiguous per ci
+    bf16* dst = J.dgrad + (long long)(ci0 + ci) * TAPS * J.Cout + co0 + lane;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) dst[(long long)(TAPS - 1 - t) * J.Cout] = __float2bfloat16_rn(tile[lane * 289 + ci * TAPS + t]);
+  }
+}
+
 __global__ void __launch_bounds__(256) tc_pack_batched_kernel(const TcPackJob* jobs, int njobs) {
   __shared__ int s_job;
   __shared__ float tile[32 * 289];      // [co][ci*taps + t], odd row stride: conflict-free row- and column-wise
   const TcPackJob& J = jobs[tc_find_job(jobs, njobs, &s_job)];
   const int lb = (int)blockIdx.x - J.block0;
   if (J.kind == 0) {
-    const int taps = J.taps, tiles_ci = J.Cin / 32;
-    const int co0 = (lb / tiles_ci) * 32, ci0 = (lb % tiles_ci) * 32;
-    const int rowlen = 32 * taps;
-    for (int i = threadIdx.x; i < 32 * rowlen; i += 256) {
-      const int r = i / rowlen, c = i - r * rowlen;
-      tile[r * 289 + c] = J.w[((long long)(co0 + r) * J.Cin + ci0) * taps + c];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * rowlen; i += 256) {
-      const int ci = i & 31, t = (i >> 5) % taps, r = i / rowlen;
-      J.fwd[((long long)(co0 + r) * taps + t) * J.Cin + ci0 + ci] = __float2bfloat16_rn(tile[r * 289 + ci * taps + t]);
-    }
-    for (int i = threadIdx.x; i < 32 * rowlen; i += 256) {
-      const int r = i & 31, t = (i >> 5) % taps, ci = i / rowlen;
-      J.dgrad[((long long)(ci0 + ci) * taps + (taps - 1 - t)) * J.Cout + co0 + r] = __float2bfloat16_rn(tile[r * 289 + ci * taps + t]);
-    }
+    if (J.taps == 9) tc_pack_tile<9>(J, lb, tile);
+    else tc_pack_tile<1>(J, lb, tile);
   } else {
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
@@ -1388,15 +1402,15 @@ __global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJo
   const int lb = (int)blockIdx.x - J.block0;
   const int taps = J.taps, tiles_n = J.N / 32;
   const int m0 = (lb / tiles_n) * 8, n0 = (lb % tiles_n) * 32;
-  const int rowlen = 32 * taps;
-  for (int i = threadIdx.x; i < 8 * rowlen; i += 256) {
-    const int n = i & 31, t = (i >> 5) % taps, m = i / rowlen;
-    if (m0 + m < J.M) tile[m][n * taps + t] = J.acc[((long long)t * J.M + m0 + m) * J.N + n0 + n];
+  const int lane = threadIdx.x & 31, m = threadIdx.x >> 5;      // warp = one m row, lane = n column
+  if (m0 + m < J.M) {
+    const float* src = J.acc + ((long long)(m0 + m)) * J.N + n0 + lane;
+    for (int t = 0; t < taps; ++t) tile[m][lane * taps + t] = src[(long long)t * J.M * J.N];
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 8 * rowlen; i += 256) {
-    const int m = i / rowlen, c = i - m * rowlen;
-    if (m0 + m < J.M) J.dw[((long long)(m0 + m) * J.N + n0) * taps + c] = tile[m][c];
+  __syncwarp();
+  if (m0 + m < J.M) {
+    float* dst = J.dw + ((long long)(m0 + m) * J.N + n0) * taps;
+    for (int c = lane; c < 32 * taps; c += 32) dst[c] = tile[m][c];
   }
 }
 
@@ -1814,7 +1828,8 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   const size_t budget = 227 * 1024;
   const size_t wbytes = (size_t)9 * K * p.BN * 2;
   // two epilogue sets for the thin layers when everything (resident weights, >= 2 A stages) still fits
-  c.S = (p.BN <= 64 && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
+  // (measured: 32-column layers 75 -> 70 us, 32->64 dgrad @192 95 -> 77 us; 64->64 @96 35.5 -> 37 us: no gain at K >= 576)
+  c.S = (p.BN <= 64 && (long long)K * p.BN <= 64 * 32 && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
   for (;; c.S = 1) {
     const size_t staging = (size_t)c.S * p.npair * 128 * p.BN * 2;
     const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * 8 * p.BN + 16 + 8 * 48;
@@ -2060,7 +2075,7 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
     const long long total_pt = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
-    long long splits = ((long long)tc_env_int("FU_TC_WGRAD_WAVES", 2) * sms + units - 1) / units;   // CTAs per SM over the launch
+    long long splits = ((long long)tc_env_int("FU_TC_WGRAD_WAVES", 1) * sms + units - 1) / units;   // CTAs per SM over the launch
     const long long max_splits = (total_pt + 3) / 4;          // at least 4 pixel tiles per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

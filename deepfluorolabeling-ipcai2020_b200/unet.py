@@ -161,6 +161,7 @@ class UNet(nn.Module):
         self._schema = None
         self._bound_ptrs = None
         self._state_cache = None
+        self._pack_epoch = 0
         self._generation = 0
         self._grad_numel = 0
         self._last_logits = None
@@ -239,10 +240,12 @@ class UNet(nn.Module):
         return self._state_cache[0]
 
     def invalidate_cache(self):
-        """Call after replacing a Parameter/buffer OBJECT of the module by hand (in-place updates,
-        load_state_dict and .to() need nothing)."""
+        """Call after replacing a Parameter/buffer OBJECT of the module by hand, or after changing parameter
+        VALUES outside autograd's version tracking (e.g. a fused optimizer step that was not preceded by this
+        module's backward).  In-place updates, load_state_dict and .to() need nothing."""
         self._state_cache = None
         self._bound_ptrs = None
+        self._pack_epoch = (self._pack_epoch + 1) & 0x3FFFFFFF
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -281,9 +284,13 @@ class UNet(nn.Module):
         seg = torch.empty((B, nc, H, W), device=x.device, dtype=torch.float32)
         heat = torch.empty((B, nl, H, W), device=x.device, dtype=torch.float32) if nl > 0 else None
         logits = torch.empty_like(seg) if self.keep_logits else None
+        # weights_version: tensor version counters catch ordinary in-place updates (optimizer.step, copy_,
+        # load_state_dict); fused / foreach optimizers (torch.optim.SGD(fused=True)) update parameters WITHOUT
+        # bumping them, so every backward also advances an epoch: the forward after a backward always re-packs.
         version = 0
         for p in self._state_cache[3]:
             version += p._version
+        version = (version & 0xFFFFFFFF) | (self._pack_epoch << 32)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         self._generation += 1
         rc = L.fu_forward(self._handle, x.data_ptr(), B, H, W, int(self.training), int(save), version,
@@ -312,6 +319,7 @@ class UNet(nn.Module):
                            d_heat.data_ptr() if d_heat is not None else None, flat.data_ptr(), stream)
         if rc != 0:
             raise RuntimeError(f"fu_backward failed ({rc}): {_capi.last_error(self._handle)}")
+        self._pack_epoch = (self._pack_epoch + 1) & 0x3FFFFFFF   # an optimizer step usually follows
         if self.grad_hook is not None:
             self.grad_hook(flat)
         self.last_flat_grad = flat

@@ -290,6 +290,42 @@ def test_training_loop_reduces_loss_like_reference_loop(pkg):
     assert losses[-1] < losses[0] - 0.01, losses
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_optimizer_updates_reach_the_engine(pkg, precision):
+    """torch.optim.SGD(fused=True) changes parameters without bumping their version counters; the engine must
+    still re-pack its weight copies every step (it re-packs after every backward).  Same trajectory as the
+    ordinary optimiser, and as the fused device loss."""
+    dev = torch.device("cuda:0")
+    kw = dict(n_classes=7, depth=3, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=14)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 1, 32, 32, generator=g).to(dev)
+    tgt_seg = torch.nn.functional.one_hot(torch.randint(0, 7, (4, 28, 28), generator=g), 7).permute(0, 3, 1, 2).float().contiguous().to(dev)
+    tgt_heat = torch.rand(4, 14, 28, 28, generator=g).to(dev)
+    runs = {}
+    for name, fused, fused_loss in (("plain", False, False), ("fused_sgd", True, False), ("fused_both", True, True)):
+        torch.manual_seed(0)
+        net = pkg.UNet(precision=precision, **kw).to(dev)
+        opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4, fused=fused)
+        crit = (pkg.FusedDiceAndHeatMapLoss2D if fused_loss else pkg.DiceAndHeatMapLoss2D)(skip_bg=False, heatmap_wgt=0.5)
+        losses = []
+        for _ in range(6):
+            opt.zero_grad(set_to_none=True)
+            seg, heat = net(x)
+            if fused_loss:
+                loss = crit((seg, heat), (tgt_seg, tgt_heat))
+            else:
+                loss = crit((pkg.center_crop(seg, tgt_seg.shape), pkg.center_crop(heat, tgt_heat.shape)), (tgt_seg, tgt_heat))
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        runs[name] = losses
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    assert runs["plain"][-1] < runs["plain"][0] - 0.005, runs
+    for name in ("fused_sgd", "fused_both"):
+        for a, b in zip(runs[name], runs["plain"]):
+            assert abs(a - b) < tol, runs
+
+
 def test_tensor_core_path_agrees_with_cuda_core_path(pkg):
     """Throughput mode twice on the same weights/inputs: tcgen05 kernels vs the CUDA-core bf16
     kernels (FU_TC_DISABLE=1).  Same storage precision, so they must agree tightly; this isolates

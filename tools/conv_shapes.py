@@ -1,0 +1,39 @@
+"""Run a list of tensor-core conv layer shapes through the kernel test hook in ONE process (for ncu captures
+and for CUDA-event timing without paying the interpreter start-up per shape).
+usage: conv_shapes.py [--time] "B Cin Cout H W k mode" ...      (mode 0 fwd, 1 dgrad, 2 wgrad)"""
+import ctypes, importlib, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("deepfluorolabeling-ipcai2020_b200")
+L = pkg._capi.lib(); dev = torch.device("cuda:0")
+args = sys.argv[1:]
+timed = False
+if args and args[0] == "--time":
+    timed = True; args = args[1:]
+p = lambda t: ctypes.c_void_p(t.data_ptr())
+for spec in args:
+    B, Cin, Cout, H, W, k, mode = [int(a) for a in spec.split()]
+    x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5)
+    b = torch.randn(Cout, device=dev)
+    dy = torch.randn(B, H, W, Cout, device=dev).bfloat16()
+    y = torch.empty(B, H, W, Cout if mode == 0 else Cin, device=dev, dtype=torch.bfloat16)
+    dw = torch.empty_like(w)
+    def run():
+        rc = L.fu_test_conv(1, 1, mode, B, H, W, Cin, Cout, k, 1, k // 2, 1, p(x), p(w), p(b), p(y), p(dy), p(dw), None, None)
+        assert rc == 0, pkg._capi.last_error(None)
+    run()
+    if timed:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5): run()
+            torch.cuda.synchronize()
+        for e in prof.key_averages():
+            if "tc_" in e.key and "batched" not in e.key:
+                fl = 2.0 * B * H * W * Cin * Cout * k * k
+                us = e.device_time_total / e.count
+                print("%-26s %-30s %8.1f us %7.1f TFLOP/s" % (spec, e.key[:30], us, fl / us / 1e6), flush=True)
+    else:
+        run()
+torch.cuda.synchronize()
+print("done")
