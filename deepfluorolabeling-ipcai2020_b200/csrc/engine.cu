@@ -104,6 +104,7 @@ struct fu_engine {
   // batched weight pack / weight-gradient unpack (kernels_tc.cuh): device job tables and what they hold
   static constexpr int kJobCap = 512;
   TcPackJob* pack_tbl = nullptr; TcUnpackJob* unpack_tbl = nullptr;
+  TcPackJob* pack_pin = nullptr; TcUnpackJob* unpack_pin = nullptr;      // page-locked staging copies
   std::vector<TcPackJob> pack_uploaded; std::vector<TcUnpackJob> unpack_uploaded;
   TcBatch batch;
   int64_t packed_version = -1;
@@ -382,6 +383,8 @@ int alloc_persistent(fu_engine* e) {
   CUDA_TRY(e, cudaMemset(e->wmem, 0, e->wmem_bytes));
   CUDA_TRY(e, cudaMalloc(&e->pack_tbl, fu_engine::kJobCap * sizeof(TcPackJob)));
   CUDA_TRY(e, cudaMalloc(&e->unpack_tbl, fu_engine::kJobCap * sizeof(TcUnpackJob)));
+  CUDA_TRY(e, cudaMallocHost(&e->pack_pin, fu_engine::kJobCap * sizeof(TcPackJob)));
+  CUDA_TRY(e, cudaMallocHost(&e->unpack_pin, fu_engine::kJobCap * sizeof(TcUnpackJob)));
   Bump w2, df2, db2, ws2;
   w2.base = e->wmem; df2.base = reinterpret_cast<char*>(e->dscr_fwd); db2.base = reinterpret_cast<char*>(e->dscr_bwd);
   ws2.base = e->wgrad_scr;
@@ -554,7 +557,7 @@ int pack_all(fu_engine* e, bool training) {
     e->set_tag(0, 0, "weight_pack");
     if (e->prof) e->prof_begin("tc_pack_batched_kernel");
     const int trc = tc_flush_jobs(e->batch.pack, e->pack_uploaded, e->pack_tbl, fu_engine::kJobCap, tc_pack_batched_kernel,
-                                  e->stream, &e->cnt);
+                                  e->stream, &e->cnt, e->pack_pin);
     if (e->prof) e->prof_end();
     if (trc) return e->fail(FU_ERR_CUDA, "batched weight pack failed");
   }
@@ -1171,7 +1174,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     e->set_tag(0, 0, "wgrad_unpack");
     if (e->prof) e->prof_begin("tc_unpack_batched_kernel");
     const int trc = tc_flush_jobs(e->batch.unpack, e->unpack_uploaded, e->unpack_tbl, fu_engine::kJobCap,
-                                  tc_unpack_batched_kernel, e->stream, &e->cnt);
+                                  tc_unpack_batched_kernel, e->stream, &e->cnt, e->unpack_pin);
     if (e->prof) e->prof_end();
     if (trc) return e->fail(FU_ERR_CUDA, "batched weight-gradient unpack failed");
   }
@@ -1251,6 +1254,8 @@ void fu_engine_destroy(fu_engine* e) {
   if (e->wgrad_scr) cudaFree(e->wgrad_scr);
   if (e->pack_tbl) cudaFree(e->pack_tbl);
   if (e->unpack_tbl) cudaFree(e->unpack_tbl);
+  if (e->pack_pin) cudaFreeHost(e->pack_pin);
+  if (e->unpack_pin) cudaFreeHost(e->unpack_pin);
   delete e;
 }
 

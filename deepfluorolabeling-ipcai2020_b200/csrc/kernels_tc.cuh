@@ -1424,16 +1424,29 @@ inline TcBatch*& tc_batch() {
   static thread_local TcBatch* b = nullptr;
   return b;
 }
-// upload `jobs` when they differ from what the device table already holds, then launch
+// upload `jobs` when they differ from what the device table already holds, then launch.  `pinned` (optional,
+// dev_cap entries of page-locked host memory) is the staging copy the upload reads: a copy from pageable memory
+// cannot be captured into a CUDA graph, and a captured copy re-reads its host source at every replay.
 template <typename Job, typename Kern>
 inline int tc_flush_jobs(std::vector<Job>& jobs, std::vector<Job>& uploaded, Job* dev_tbl, int dev_cap, Kern kern,
-                         cudaStream_t stream, fu_counters* cnt) {
+                         cudaStream_t stream, fu_counters* cnt, Job* pinned = nullptr) {
   if (jobs.empty()) return 0;
   if ((int)jobs.size() > dev_cap) return -1;
   int blocks = 0;
   for (auto& j : jobs) { j.block0 = blocks; blocks += j.nblocks; }
   if (uploaded.size() != jobs.size() || memcmp(uploaded.data(), jobs.data(), jobs.size() * sizeof(Job)) != 0) {
-    if (cudaMemcpyAsync(dev_tbl, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -1;
+    const void* src = jobs.data();
+    if (pinned) {
+      // an earlier upload may still be reading the staging copy (eager mode; tables change only when a tensor
+      // address changes, so this wait is rare).  While capturing nothing from eager mode is in flight on this
+      // stream and synchronising would invalidate the capture.
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
+      if (cap == cudaStreamCaptureStatusNone && cudaStreamSynchronize(stream) != cudaSuccess) return -1;
+      memcpy(pinned, jobs.data(), jobs.size() * sizeof(Job));
+      src = pinned;
+    }
+    if (cudaMemcpyAsync(dev_tbl, src, jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -1;
     uploaded = jobs;
   }
   kern<<<blocks, 256, 0, stream>>>(dev_tbl, (int)jobs.size());
@@ -1618,6 +1631,22 @@ inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* 
 inline int tc_env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
+}
+
+// Split-K factor of the weight-gradient kernels.  One CTA is resident per SM, so CTAs = units x splits should
+// fill whole waves: among 1..4 target waves (starting at `first`) take the one with the best last-wave fill,
+// split counts rounded DOWN (rounding up made 3 units x 99 splits = 297 CTAs = three waves on 148 SMs).
+inline long long tc_pick_splits(long long units, long long max_splits, int sms, int first) {
+  long long best = 1; double best_eff = -1.0;
+  for (int w = first; w <= 4; ++w) {
+    long long sp = (long long)w * sms / units;
+    if (sp > max_splits) sp = max_splits;
+    if (sp < 1) sp = 1;
+    const long long ctas = units * sp;
+    const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = sp; }
+  }
+  return best;
 }
 
 // epilogue groups of the conv kernel: 4 for the thin, shallow tiles (few MMAs per tile: the epilogue is the
@@ -2075,10 +2104,8 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
     const long long total_pt = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
-    long long splits = ((long long)tc_env_int("FU_TC_WGRAD_WAVES", 1) * sms + units - 1) / units;   // CTAs per SM over the launch
     const long long max_splits = (total_pt + 3) / 4;          // at least 4 pixel tiles per CTA
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    long long splits = tc_pick_splits(units, max_splits, sms, tc_env_int("FU_TC_WGRAD_WAVES", 1));
     const long long per = (total_pt + splits - 1) / splits;
     splits = (total_pt + per - 1) / per;
     p.splits = (int)splits;
@@ -2158,10 +2185,8 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
     const long long total_kt = (long long)B * H * p.segs;
-    long long splits = ((long long)tc_env_int("FU_TC_WGRAD3_WAVES", 2) * sms + units - 1) / units;
     const long long max_splits = (total_kt + 7) / 8;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    long long splits = tc_pick_splits(units, max_splits, sms, tc_env_int("FU_TC_WGRAD3_WAVES", 2));
     const long long per = (total_kt + splits - 1) / splits;
     splits = (total_kt + per - 1) / per;
     p.splits = (int)splits;
