@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every step eagerly instead of replaying a captured CUDA graph (N=1 only uses graphs)")
     ap.add_argument("--torch-loss", action="store_true",
                     help="use the PyTorch DiceAndHeatMapLoss2D on cropped views instead of the fused device loss")
     return ap.parse_args()
@@ -173,6 +175,7 @@ def config_dict(args, world):
             "loss": "torch DiceAndHeatMapLoss2D on cropped views" if getattr(args, "torch_loss", False)
                     else "fused device DiceAndHeatMapLoss2D (crop folded in)",
             "optimizer": "torch.optim.SGD(momentum 0.9, nesterov, wd 1e-4, fused=True)",
+            "launch": "one CUDA-graph replay per step (GraphedStep)" if getattr(args, "graphed", False) else "eager launches",
             "l2": "per-step working set (~1.5 GB of NHWC activations + 300 MB of weights/grads) >> 126 MB L2; no flush needed"}
 
 
@@ -267,17 +270,34 @@ def run_ours(args):
         barrier()
         return ms
 
+    # ---- one step = one CUDA-graph replay (pkg.GraphedStep) when single-process; eager otherwise ----
+    step_call, graphed, launches_per_step = train_step, False, None
+    if world == 1 and not args.no_graph:
+        for _ in range(2):
+            train_step(*resident)
+        ca = net.engine_counters()["kernel_launches"]
+        train_step(*resident)
+        launches_per_step = net.engine_counters()["kernel_launches"] - ca     # the captured step launches the same kernels
+        try:
+            gstep = pkg.GraphedStep(train_step, resident, warmup=2)
+            step_call, graphed = gstep, True
+        except Exception as ex:        # stay correct, say so in the output
+            print(f"bench: CUDA-graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+
     # ---- device-resident inputs: `value` ----
     for _ in range(args.warmup):
-        train_step(*resident)
+        step_call(*resident)
     c0 = net.engine_counters()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(lambda i: train_step(*resident), args.steps)
+    ms = timed(lambda i: step_call(*resident), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     c1 = net.engine_counters()
     launches = c1["kernel_launches"] - c0["kernel_launches"]
+    if graphed:
+        launches = launches_per_step * args.steps      # replayed kernels do not pass through the engine's host counters
     if fused_loss:
         launches += 3 * args.steps       # loss_sums, loss_finalize, loss_backward (stateless entry points, not in the engine's counter)
     ms_step = ms / args.steps
@@ -303,7 +323,7 @@ def run_ours(args):
             prefetch(0)
         prefetch(i + 1)                      # the next step's inputs travel while this step computes
         torch.cuda.current_stream().wait_event(ready[s])
-        loss = train_step(*slots[s])
+        loss = step_call(*slots[s])
         freed[s].record(torch.cuda.current_stream())
         return loss.item()                   # device -> host read of the step's result, every step
 
@@ -341,6 +361,7 @@ def run_ours(args):
         breakdown = {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         breakdown["_engine_total_ms"] = round(tot, 4)
 
+    args.graphed = graphed
     line = None
     if rank == 0:
         line = {"metric": "images/sec fwd+bwd U-Net (1x180x180, 7+14 heads)", "value": value, "unit": "images/s",

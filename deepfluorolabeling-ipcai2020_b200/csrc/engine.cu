@@ -556,8 +556,8 @@ int pack_all(fu_engine* e, bool training) {
   if (rc == FU_OK && !e->batch.pack.empty()) {
     e->set_tag(0, 0, "weight_pack");
     if (e->prof) e->prof_begin("tc_pack_batched_kernel");
-    const int trc = tc_flush_jobs(e->batch.pack, e->pack_uploaded, e->pack_tbl, fu_engine::kJobCap, tc_pack_batched_kernel,
-                                  e->stream, &e->cnt, e->pack_pin);
+    const int trc = tc_flush_jobs(e->batch.pack, e->pack_uploaded, e->pack_tbl, fu_engine::kJobCap,
+                                  tc_pack_launcher(e->stream), e->stream, &e->cnt, e->pack_pin);
     if (e->prof) e->prof_end();
     if (trc) return e->fail(FU_ERR_CUDA, "batched weight pack failed");
   }
@@ -647,7 +647,13 @@ inline dim3 red_grid(fu_engine* e, long long P, int C) {
   const int cvecs = C / (e->esz == 2 ? 8 : 4);     // Vec<T>::N channels per thread
   const int lanes = cvecs < 256 ? cvecs : 256;
   const int rows = 256 / lanes;
-  long long gx = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);
+  // pixel rows per block: 16 x `rows` on the big levels; on the small ones (6x6 ... 24x24) fewer, so that the
+  // launch still has ~4 blocks per SM -- with one block per SM a 5 MB tensor took 12 us (memory-level parallelism
+  // of 16 KB per SM), the same as a 19 MB one
+  long long per = P / ((long long)rows * 4 * e->num_sms);
+  if (per > 16) per = 16;
+  if (per < 1) per = 1;
+  long long gx = (P + (long long)rows * per - 1) / ((long long)rows * per);
   const long long cap = (long long)e->num_sms * 8;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -1035,6 +1041,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   int rc;
   e->deferred_sums.clear();
   e->batch.unpack.clear();
+  e->batch.flat = flat;
   struct SinkGuard { SinkGuard(TcBatch* b) { tc_batch() = b; } ~SinkGuard() { tc_batch() = nullptr; } } sink_guard(&e->batch);
   CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
   CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
@@ -1174,7 +1181,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     e->set_tag(0, 0, "wgrad_unpack");
     if (e->prof) e->prof_begin("tc_unpack_batched_kernel");
     const int trc = tc_flush_jobs(e->batch.unpack, e->unpack_uploaded, e->unpack_tbl, fu_engine::kJobCap,
-                                  tc_unpack_batched_kernel, e->stream, &e->cnt, e->unpack_pin);
+                                  tc_unpack_launcher(e->stream, flat), e->stream, &e->cnt, e->unpack_pin);
     if (e->prof) e->prof_end();
     if (trc) return e->fail(FU_ERR_CUDA, "batched weight-gradient unpack failed");
   }

@@ -750,12 +750,15 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                       ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                       if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                     }
-                  } else {
+                  } else if (ksteps == 2) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                       if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                     }
+                  } else {
+                    ptx::umma_bf16(d0, ad, bd, idesc, accum);
+                    if (two) ptx::umma_bf16(d1, ad + a_tile16, bd, idesc, accum);
                   }
                   accum = 1;
                 }
@@ -778,12 +781,15 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                       ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                       if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                     }
-                  } else {
+                  } else if (ksteps == 2) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                       if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
                     }
+                  } else {
+                    ptx::umma_bf16(d0, ad, bd, idesc, accum);
+                    if (two) ptx::umma_bf16(d1, ad + a_tile16, bd, idesc, accum);
                   }
                   ptx::umma_commit(b_empty(bs));
                   if (tt == taps_per_group - 1) {
@@ -1322,7 +1328,9 @@ struct TcPackJob {
 };
 struct TcUnpackJob {
   const float* acc;             // [taps][M][N] fp32
-  float* dw;                    // torch layout (M, N, k, k)
+  long long dw_off;             // torch layout (M, N, k, k) at base + dw_off floats; the base (the step's flat gradient
+                                // buffer) is a launch argument, so the table does not change when PyTorch hands the
+                                // engine a different buffer
   int M, N, taps;
   int block0, nblocks;
 };
@@ -1395,7 +1403,7 @@ __global__ void __launch_bounds__(256) tc_pack_batched_kernel(const TcPackJob* j
 }
 
 // dw[(m*N + n)*taps + t] = acc[(t*M + m)*N + n]: tiles of 8 m x 32 n, reads and writes both contiguous
-__global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJob* jobs, int njobs) {
+__global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJob* jobs, int njobs, float* base) {
   __shared__ int s_job;
   __shared__ float tile[8][32 * 9 + 1];
   const TcUnpackJob& J = jobs[tc_find_job(jobs, njobs, &s_job)];
@@ -1409,7 +1417,7 @@ __global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJo
   }
   __syncwarp();
   if (m0 + m < J.M) {
-    float* dst = J.dw + ((long long)(m0 + m) * J.N + n0) * taps;
+    float* dst = base + J.dw_off + ((long long)(m0 + m) * J.N + n0) * taps;
     for (int c = lane; c < 32 * taps; c += 32) dst[c] = tile[m][c];
   }
 }
@@ -1419,6 +1427,7 @@ __global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJo
 struct TcBatch {
   std::vector<TcPackJob> pack;
   std::vector<TcUnpackJob> unpack;
+  float* flat = nullptr;        // base of the gradient buffer the unpack offsets are relative to
 };
 inline TcBatch*& tc_batch() {
   static thread_local TcBatch* b = nullptr;
@@ -1427,8 +1436,8 @@ inline TcBatch*& tc_batch() {
 // upload `jobs` when they differ from what the device table already holds, then launch.  `pinned` (optional,
 // dev_cap entries of page-locked host memory) is the staging copy the upload reads: a copy from pageable memory
 // cannot be captured into a CUDA graph, and a captured copy re-reads its host source at every replay.
-template <typename Job, typename Kern>
-inline int tc_flush_jobs(std::vector<Job>& jobs, std::vector<Job>& uploaded, Job* dev_tbl, int dev_cap, Kern kern,
+template <typename Job, typename Launch>
+inline int tc_flush_jobs(std::vector<Job>& jobs, std::vector<Job>& uploaded, Job* dev_tbl, int dev_cap, Launch launch,
                          cudaStream_t stream, fu_counters* cnt, Job* pinned = nullptr) {
   if (jobs.empty()) return 0;
   if ((int)jobs.size() > dev_cap) return -1;
@@ -1449,16 +1458,22 @@ inline int tc_flush_jobs(std::vector<Job>& jobs, std::vector<Job>& uploaded, Job
     if (cudaMemcpyAsync(dev_tbl, src, jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -1;
     uploaded = jobs;
   }
-  kern<<<blocks, 256, 0, stream>>>(dev_tbl, (int)jobs.size());
+  launch(blocks, dev_tbl, (int)jobs.size());
   if (cnt) cnt->kernel_launches++;
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
-template <typename Job, typename Kern>
-inline int tc_run_job_now(Job job, Kern kern, cudaStream_t stream, fu_counters* cnt) {
+inline auto tc_pack_launcher(cudaStream_t stream) {
+  return [stream](int blocks, const TcPackJob* tbl, int n) { tc_pack_batched_kernel<<<blocks, 256, 0, stream>>>(tbl, n); };
+}
+inline auto tc_unpack_launcher(cudaStream_t stream, float* base) {
+  return [stream, base](int blocks, const TcUnpackJob* tbl, int n) { tc_unpack_batched_kernel<<<blocks, 256, 0, stream>>>(tbl, n, base); };
+}
+template <typename Job, typename Launch>
+inline int tc_run_job_now(Job job, Launch launch, cudaStream_t stream, fu_counters* cnt) {
   Job* d = nullptr;
   if (cudaMalloc(&d, sizeof(Job)) != cudaSuccess) return -1;
   std::vector<Job> jobs(1, job), up;
-  const int rc = tc_flush_jobs(jobs, up, d, 1, kern, stream, cnt);
+  const int rc = tc_flush_jobs(jobs, up, d, 1, launch, stream, cnt);
   cudaStreamSynchronize(stream);
   cudaFree(d);
   return rc;
@@ -1466,10 +1481,11 @@ inline int tc_run_job_now(Job job, Kern kern, cudaStream_t stream, fu_counters* 
 inline int tc_unpack(const float* acc, float* dw, int M, int N, int taps, cudaStream_t stream, fu_counters* cnt) {
   TcUnpackJob j;
   memset(&j, 0, sizeof(j));
-  j.acc = acc; j.dw = dw; j.M = M; j.N = N; j.taps = taps;
+  j.acc = acc; j.M = M; j.N = N; j.taps = taps;
   j.nblocks = ((M + 7) / 8) * (N / 32);
-  if (tc_batch()) { tc_batch()->unpack.push_back(j); return 0; }
-  return tc_run_job_now(j, tc_unpack_batched_kernel, stream, cnt);
+  if (tc_batch()) { j.dw_off = dw - tc_batch()->flat; tc_batch()->unpack.push_back(j); return 0; }
+  j.dw_off = 0;
+  return tc_run_job_now(j, tc_unpack_launcher(stream, dw), stream, cnt);
 }
 
 // ===========================================================================
@@ -1625,7 +1641,7 @@ inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* 
     j.nblocks = (int)((total + kPackGenericPerBlock - 1) / kPackGenericPerBlock);
   }
   if (tc_batch()) { tc_batch()->pack.push_back(j); return 0; }
-  return tc_run_job_now(j, tc_pack_batched_kernel, stream, cnt);
+  return tc_run_job_now(j, tc_pack_launcher(stream), stream, cnt);
 }
 
 inline int tc_env_int(const char* name, int dflt) {
@@ -1675,6 +1691,7 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   const int N = dir == 0 ? t.Cout : t.Cin;
   p.B = B; p.H = H; p.W = W; p.Cin = K; p.N = N; p.ksz = t.k; p.pad = t.k / 2;
   p.KC = (K % 64 == 0) ? 64 : 32;
+  { const int kc = tc_env_int("FU_TC_KC", 0); if ((kc == 16 || kc == 32 || kc == 64) && K % kc == 0) p.KC = kc; }
   tc_pick_tile(B, H, W, p.tw, p.th, p.tn);
   p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_b = (B + p.tn - 1) / p.tn;
   int dev = 0, sms = 148;
@@ -1839,6 +1856,7 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   const int N = dir == 0 ? t.Cout : t.Cin;
   p.B = B; p.H = H; p.W = W; p.K = K; p.N = N;
   p.KC = (K % 64 == 0) ? 64 : 32;
+  { const int kc = tc_env_int("FU_TC_KC", 0); if ((kc == 16 || kc == 32 || kc == 64) && K % kc == 0) p.KC = kc; }
   int bn = 128;
   while (N % bn) bn >>= 1;
   p.BN = bn; p.CS = bn >= 64 ? 64 : 32;

@@ -1,0 +1,56 @@
+"""CUDA-graph replay of a whole training step.
+
+The reference's loop (train.py:395-430) reads the loss back every step (`loss.item()`), so the host cannot run
+ahead of the device: the ~215 kernel launches of one step, plus the Python around them, are re-issued from an
+idle pipeline every time.  `GraphedStep` captures ONE step -- zero_grad, UNet forward, loss, backward (incl. the
+engine's weight re-pack and gradient unpack), optimizer.step -- into a CUDA graph and replays it per batch, so a
+step costs one launch.  Streams and graphs instead of a tracing compiler: nothing is re-written, the captured
+kernels are exactly the ones the eager path launches.
+
+Requirements (checked or documented, never silently worked around):
+  * fixed input shapes (the reference trains on fixed-size tiles, dataset.py:26-40);
+  * `step_fn` must not synchronise or read device values on the host (return the loss tensor, read it outside);
+  * optimisers whose step is capture-safe (torch.optim.SGD, also fused=True; Adam needs capturable=True);
+  * single process: the NCCL gradient all-reduce of `parallel.data_parallel` is left to eager mode.
+"""
+import torch
+
+
+class GraphedStep:
+    def __init__(self, step_fn, example_inputs, warmup=3):
+        """step_fn(*inputs) -> loss tensor (or tuple of tensors); example_inputs: CUDA tensors of the step's shapes."""
+        if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
+            raise ValueError("GraphedStep: example_inputs must be CUDA tensors")
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            raise RuntimeError("GraphedStep is single-process; run the data-parallel loop in eager mode")
+        self.step_fn = step_fn
+        self.static_in = [torch.empty_like(t) for t in example_inputs]
+        for d, s in zip(self.static_in, example_inputs):
+            d.copy_(s)
+        dev = example_inputs[0].device
+        # warm-up on a side stream: lazy allocations (engine arena, tensor maps, job tables, optimizer state)
+        # must all have happened before the capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                step_fn(*self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = step_fn(*self.static_in)
+        torch.cuda.synchronize(dev)
+
+    def __call__(self, *inputs):
+        """Copies `inputs` into the graph's static buffers (device-to-device, on the current stream), replays the
+        step and returns the static output tensor(s); their values are overwritten by the next call."""
+        if len(inputs) != len(self.static_in):
+            raise ValueError("GraphedStep: wrong number of inputs")
+        for d, s in zip(self.static_in, inputs):
+            if s.shape != d.shape or s.dtype != d.dtype:
+                raise ValueError(f"GraphedStep: input {tuple(s.shape)}/{s.dtype} does not match the captured {tuple(d.shape)}/{d.dtype}")
+            if s.data_ptr() != d.data_ptr():
+                d.copy_(s, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

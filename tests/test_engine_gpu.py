@@ -326,6 +326,52 @@ def test_fused_optimizer_updates_reach_the_engine(pkg, precision):
             assert abs(a - b) < tol, runs
 
 
+def test_graphed_step_replays_the_eager_step(pkg):
+    """pkg.GraphedStep (one CUDA-graph replay per training step) must follow the eager loop's loss trajectory,
+    with new input values reaching the captured step through its static buffers."""
+    dev = torch.device("cuda:0")
+    kw = dict(n_classes=7, depth=3, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=14)
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for _ in range(3):
+        x = torch.randn(4, 1, 32, 32, generator=g).to(dev)
+        ts = torch.nn.functional.one_hot(torch.randint(0, 7, (4, 28, 28), generator=g), 7).permute(0, 3, 1, 2).float().contiguous().to(dev)
+        th = torch.rand(4, 14, 28, 28, generator=g).to(dev)
+        batches.append((x, ts, th))
+    runs = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        net = pkg.UNet(precision="bf16", **kw).to(dev)
+        opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=1e-4, fused=True)
+        crit = pkg.FusedDiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
+
+        def step(x, ts, th):
+            opt.zero_grad(set_to_none=True)
+            seg, heat = net(x)
+            loss = crit((seg, heat), (ts, th))
+            loss.backward()
+            opt.step()
+            return loss
+        losses = []
+        warm = 2
+        if mode == "graph":
+            call = pkg.GraphedStep(step, batches[0], warmup=warm)      # `warm` eager steps run here; capturing executes nothing
+        else:
+            for _ in range(warm):
+                step(*batches[0])
+            call = step
+        for i in range(9):
+            losses.append(float(call(*batches[i % 3]).detach()))
+        runs[mode] = losses
+        rm = dict(net.named_buffers())["down_path.0.block.2.running_mean"].clone()
+        runs[mode + "_rm"] = rm
+    for a, b in zip(runs["graph"], runs["eager"]):
+        assert abs(a - b) < 2e-2, runs
+    assert runs["eager"][-1] < runs["eager"][0], runs
+    # BN running statistics are updated by the replayed kernels too
+    assert float((runs["graph_rm"] - runs["eager_rm"]).abs().max()) < 2e-2 * float(runs["eager_rm"].abs().max() + 1e-3)
+
+
 def test_tensor_core_path_agrees_with_cuda_core_path(pkg):
     """Throughput mode twice on the same weights/inputs: tcgen05 kernels vs the CUDA-core bf16
     kernels (FU_TC_DISABLE=1).  Same storage precision, so they must agree tightly; this isolates
