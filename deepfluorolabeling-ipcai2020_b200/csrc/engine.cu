@@ -647,13 +647,10 @@ inline dim3 red_grid(fu_engine* e, long long P, int C) {
   const int cvecs = C / (e->esz == 2 ? 8 : 4);     // Vec<T>::N channels per thread
   const int lanes = cvecs < 256 ? cvecs : 256;
   const int rows = 256 / lanes;
-  // pixel rows per block: 16 x `rows` on the big levels; on the small ones (6x6 ... 24x24) fewer, so that the
-  // launch still has ~4 blocks per SM -- with one block per SM a 5 MB tensor took 12 us (memory-level parallelism
-  // of 16 KB per SM), the same as a 19 MB one
-  long long per = P / ((long long)rows * 4 * e->num_sms);
-  if (per > 16) per = 16;
-  if (per < 1) per = 1;
-  long long gx = (P + (long long)rows * per - 1) / ((long long)rows * per);
+  // 16 x `rows` pixel rows per block.  (Smaller chunks on the 6x6 ... 24x24 levels, to get more than one block
+  // per SM, were measured 1.6x SLOWER: every block ends in one fp64 atomic per channel, and at 512-1024 channels
+  // those atomics, not the loads, bound the kernel.)
+  long long gx = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);
   const long long cap = (long long)e->num_sms * 8;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
