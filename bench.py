@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
-                    help="launch every step eagerly instead of replaying a captured CUDA graph (N=1 only uses graphs)")
+                    help="launch every step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--torch-loss", action="store_true",
                     help="use the PyTorch DiceAndHeatMapLoss2D on cropped views instead of the fused device loss")
     return ap.parse_args()
@@ -272,18 +272,23 @@ def run_ours(args):
 
     # ---- one step = one CUDA-graph replay (pkg.GraphedStep) when single-process; eager otherwise ----
     step_call, graphed, launches_per_step = train_step, False, None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         for _ in range(2):
             train_step(*resident)
         ca = net.engine_counters()["kernel_launches"]
         train_step(*resident)
         launches_per_step = net.engine_counters()["kernel_launches"] - ca     # the captured step launches the same kernels
         try:
-            gstep = pkg.GraphedStep(train_step, resident, warmup=2)
+            gstep = pkg.GraphedStep(train_step, resident, warmup=2, allow_distributed=world > 1)
             step_call, graphed = gstep, True
         except Exception as ex:        # stay correct, say so in the output
             print(f"bench: CUDA-graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
             torch.cuda.synchronize()
+        if world > 1:                  # all ranks replay, or none does
+            ok = torch.tensor([1.0 if graphed else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) < 1.0:
+                step_call, graphed = train_step, False
 
     # ---- device-resident inputs: `value` ----
     for _ in range(args.warmup):
@@ -382,6 +387,13 @@ def run_ours(args):
                                               f"port of unet.py on torch-CPU, {threads} threads, {cms:.0f} ms/step"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if graphed:
+            # a live CUDA graph that contains NCCL kernels makes communicator teardown hang (observed: the JSON
+            # line was out, then destroy_process_group never returned): leave together and skip the teardown
+            sys.stdout.flush()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -647,9 +647,10 @@ inline dim3 red_grid(fu_engine* e, long long P, int C) {
   const int cvecs = C / (e->esz == 2 ? 8 : 4);     // Vec<T>::N channels per thread
   const int lanes = cvecs < 256 ? cvecs : 256;
   const int rows = 256 / lanes;
-  // 16 x `rows` pixel rows per block.  (Smaller chunks on the 6x6 ... 24x24 levels, to get more than one block
-  // per SM, were measured 1.6x SLOWER: every block ends in one fp64 atomic per channel, and at 512-1024 channels
-  // those atomics, not the loads, bound the kernel.)
+  // 16 x `rows` pixel rows per block.  Two attempts to get more blocks in flight on the small, wide levels
+  // (6x6 ... 24x24, where these kernels are latency bound at 12-16 us) were measured and dropped: smaller chunks
+  // made every kernel end in 4-32x more fp64 atomics (1.6x slower overall), and reducing across 8-block clusters
+  // through distributed shared memory first made the big levels pay for cluster scheduling (act_bwd 0.54 -> 0.97 ms).
   long long gx = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);
   const long long cap = (long long)e->num_sms * 8;
   if (gx > cap) gx = cap;

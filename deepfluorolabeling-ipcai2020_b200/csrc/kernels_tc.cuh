@@ -97,6 +97,13 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// shared -> global bulk reduction (fp32 add) of `bytes` contiguous bytes (16-byte aligned, multiple of 16)
+__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(ssrc), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -976,6 +983,41 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // channels) = MN-major for the MMA.  One CTA owns one (co tile, ci tile, filter row) and a range of pixel
 // tiles (split-K); the 3 taps of the filter row share the dY tile and accumulate in 3 TMEM regions.
 // ===========================================================================
+// Epilogue of the weight-gradient kernels: thread = accumulator row (out-channel) `co`.  For every tap the row leaves
+// TMEM through a private shared-memory row buffer (the operand stages are free once the last MMA has retired) and
+// is added to the global [tap][co][ci] accumulator by ONE bulk reduction (`cp.reduce.async.bulk ... add.f32`, up to
+// 512 B) instead of N/4 16-byte `red.global` instructions: the split-K epilogues cost 0.37 ms of a 7.5 ms step
+// (FU_TC_WGRAD_NOEPI diagnostic) and most of that was issue and L2-atomic traffic.  Rows are private to their
+// thread, so the only ordering needed is the thread's own proxy fence and bulk-group waits (double buffered).
+__device__ __forceinline__ void tc_wgrad_epilogue(uint32_t tmem_base, uint32_t smem_base, uint32_t avail_bytes, int N, int ntaps,
+                                                  int tap0, int tap_stride, int co, int Cout, int ci0, int Cin, int row,
+                                                  int q, float* dw_acc, int skip) {
+  const uint32_t pitch = (uint32_t)N * 4u + 16u;            // +16 B: 8 consecutive rows cover all 32 banks
+  const int nbuf = avail_bytes >= 2u * 128u * pitch ? 2 : 1;
+  const int ncols = min(N, Cin - ci0);                      // valid in-channels of this tile
+  const bool live = co < Cout && ncols > 0 && !skip;
+  for (int t = 0; t < ntaps; ++t) {
+    const uint32_t soff = (uint32_t)(row * nbuf + (t % nbuf)) * pitch;
+    if (t >= nbuf) { if (nbuf == 2) ptx::tma_store_wait_read1(); else ptx::tma_store_wait_read(); }
+    for (int j = 0; j < N / 32; ++j) {
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_base + (uint32_t)(t * N + j * 32) + ((uint32_t)(q * 32) << 16), v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + soff + (uint32_t)(j * 32 + i) * 4u),
+                     "r"(v[i]), "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3]) : "memory");
+    }
+    if (live) {
+      ptx::fence_proxy_async_smem();
+      const int tap = tap0 + t * tap_stride;
+      ptx::bulk_reduce_add_f32(dw_acc + ((long long)tap * Cout + co) * Cin + ci0, smem_base + soff, (uint32_t)ncols * 4u);
+    }
+    ptx::tma_store_commit();
+  }
+  ptx::tma_store_wait_all();       // every reduction has completed before the CTA (and its smem) goes away
+}
+
 struct TcWgradParams {
   int B, H, W, Cin, Cout;
   int ksz, pad, taps_per_cta, groups;
@@ -984,6 +1026,7 @@ struct TcWgradParams {
   int tiles_w, tiles_h, tiles_b;
   int co_tiles, ci_tiles, splits, stages;
   float* dw_acc;                // [taps][Cout][Cin] fp32, zeroed by the caller
+  int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1): drop the accumulators instead of adding them
   int b5;                       // B operand gathered with stride 2 (5-D map), taps = 2x2, pixel grid (W, H), B = 1
 };
 
@@ -1091,26 +1134,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   } else if (n_iters > 0) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int co = co0 + row;
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
-    for (int t = 0; t < p.taps_per_cta; ++t) {
-      const int tap = p.ksz > 1 ? p.ksz * grp + t : 0;
-      for (int j = 0; j < p.N / 32; ++j) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + (uint32_t)(t * p.N + j * 32) + ((uint32_t)(q * 32) << 16), v);
-        ptx::tmem_ld_wait();
-        const int ci = ci0 + j * 32;
-        if (co < p.Cout && ci < p.Cin) {
-          float* dst = p.dw_acc + ((long long)tap * p.Cout + co) * p.Cin + ci;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            atomicAdd(reinterpret_cast<float4*>(dst + i),
-                      make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                  __uint_as_float(v[i + 3])));
-        }
-      }
-    }
+    tc_wgrad_epilogue(tmem_base, smem_base, (uint32_t)p.stages * stage_bytes, p.N, p.taps_per_cta,
+                      p.ksz > 1 ? p.ksz * grp : 0, 1, co0 + row, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -1140,6 +1167,7 @@ struct TcWgrad3Params {
   int co_tiles, ci_tiles, splits, stages;
   unsigned b_stage_bytes;       // bytes of the B region of one stage
   int stack;                    // 1: the three kw taps of a filter row are ONE MMA with N = 3*N (see above)
+  int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1)
   float* dw_acc;                // [9][Cout][Cin] fp32, zeroed by the caller
 };
 
@@ -1279,26 +1307,10 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   } else if (n_iters > 0) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int co = co0 + row;
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
-    for (int t = 0; t < p.tpg; ++t) {
-      const int tap = p.tpg == 9 ? t : grp * 3 + t;
-      for (int j = 0; j < p.N / 32; ++j) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_base + (uint32_t)(t * p.N + j * 32) + ((uint32_t)(q * 32) << 16), v);
-        ptx::tmem_ld_wait();
-        const int ci = ci0 + j * 32;
-        if (co < p.Cout && ci < p.Cin) {
-          float* dst = p.dw_acc + ((long long)tap * p.Cout + co) * p.Cin + ci;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            atomicAdd(reinterpret_cast<float4*>(dst + i),
-                      make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                  __uint_as_float(v[i + 3])));
-        }
-      }
-    }
+    tc_wgrad_epilogue(tmem_base, smem_base, (uint32_t)p.stages * stage_bytes, p.N, p.tpg, p.tpg == 9 ? 0 : grp * 3, 1,
+                      co0 + row, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -2129,6 +2141,7 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     p.splits = (int)splits;
     n.grid = (int)(units * splits);
     p.dw_acc = t.dw_acc;
+    p.skip_epi = tc_env_int("FU_TC_WGRAD_NOEPI", 0);
     {
       long long dims[4] = {M, p.W, p.H, p.B};
       long long str[4] = {1, a_ld, (long long)p.W * a_ld, (long long)p.H * p.W * a_ld};
@@ -2204,12 +2217,13 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
     const long long total_kt = (long long)B * H * p.segs;
     const long long max_splits = (total_kt + 7) / 8;
-    long long splits = tc_pick_splits(units, max_splits, sms, tc_env_int("FU_TC_WGRAD3_WAVES", 2));
+    long long splits = tc_pick_splits(units, max_splits, sms, tc_env_int("FU_TC_WGRAD3_WAVES", 1));
     const long long per = (total_kt + splits - 1) / splits;
     splits = (total_kt + per - 1) / per;
     p.splits = (int)splits;
     n.grid = (int)(units * splits);
     p.dw_acc = t.dw_acc;
+    p.skip_epi = tc_env_int("FU_TC_WGRAD_NOEPI", 0);
     {
       long long dims[4] = {t.Cout, W, H, B};
       long long str[4] = {1, dy_ld, (long long)W * dy_ld, (long long)H * W * dy_ld};

@@ -11,18 +11,23 @@ Requirements (checked or documented, never silently worked around):
   * fixed input shapes (the reference trains on fixed-size tiles, dataset.py:26-40);
   * `step_fn` must not synchronise or read device values on the host (return the loss tensor, read it outside);
   * optimisers whose step is capture-safe (torch.optim.SGD, also fused=True; Adam needs capturable=True);
-  * single process: the NCCL gradient all-reduce of `parallel.data_parallel` is left to eager mode.
+  * under torch.distributed the NCCL gradient all-reduce of `parallel.data_parallel` is captured too
+    (allow_distributed=True): every rank has to capture and replay in lock step.
 """
 import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn, example_inputs, warmup=3):
-        """step_fn(*inputs) -> loss tensor (or tuple of tensors); example_inputs: CUDA tensors of the step's shapes."""
+    def __init__(self, step_fn, example_inputs, warmup=3, allow_distributed=False):
+        """step_fn(*inputs) -> loss tensor (or tuple of tensors); example_inputs: CUDA tensors of the step's shapes.
+        allow_distributed: also capture under torch.distributed (the NCCL gradient all-reduce of
+        parallel.data_parallel becomes a node of the graph; every rank must capture and replay in lock step)."""
         if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
             raise ValueError("GraphedStep: example_inputs must be CUDA tensors")
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            raise RuntimeError("GraphedStep is single-process; run the data-parallel loop in eager mode")
+        if (not allow_distributed and torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1):
+            raise RuntimeError("GraphedStep: pass allow_distributed=True to capture the data-parallel step "
+                               "(all ranks must then capture and replay together)")
         self.step_fn = step_fn
         self.static_in = [torch.empty_like(t) for t in example_inputs]
         for d, s in zip(self.static_in, example_inputs):
