@@ -62,6 +62,7 @@ struct Block {
   ConvW res;
   std::vector<ConvW> convs;
   std::vector<BNL> bns;
+  double* dstat = nullptr;      // [2*Cin]: per-channel sums of the block's input gradient (from the last dgrad's epilogue)
   // plan-dependent
   std::vector<View> r, z, dy, dz;
 };
@@ -357,6 +358,8 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
     if (c.Cin > maxc) maxc = c.Cin;
     tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision == FU_PRECISION_BF16, w, ws);
   });
+  for (auto& b : e->enc) b.dstat = db.take<double>(2 * (size_t)b.Cin);
+  for (auto& b : e->dec) b.dstat = db.take<double>(2 * (size_t)b.Cin);
   for_each_bn(e, [&](BNL& b) {
     b.stat = df.take<double>(2 * b.C);
     b.bstat = db.take<double>(2 * b.C);
@@ -910,8 +913,10 @@ int flush_deferred_sums(fu_engine* e) {
 }
 
 // gradient of a stride-1 conv (3x3/pad1 or 1x1) w.r.t. its input
+// stat / stat_done: see tc_conv_dgrad; *stat_done is set when the (tensor-core) kernel produced the sums
 template <typename T>
-int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, int H, int W, int accumulate) {
+int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, int H, int W, int accumulate,
+               double* stat = nullptr, bool* stat_done = nullptr) {
   {
     const double M = (double)B * H * W;
     e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (dx.C + dy.C)) * e->esz + 2.0 * cw.Cin * cw.Cout * cw.k * cw.k,
@@ -919,10 +924,11 @@ int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, i
   }
   if (tc_dgrad_eligible(cw.tc, dy.p, dy.ld, dx.p, dx.ld)) {
     if (e->prof) e->prof_begin("tc_conv_kernel");
-    const int trc = tc_conv_dgrad(cw.tc, dy.p, dy.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt);
+    const int trc = tc_conv_dgrad(cw.tc, dy.p, dy.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt, stat);
     if (e->prof) e->prof_end();
     if (trc)
       return e->fail(FU_ERR_CUDA, "tensor-core dgrad launch failed: %s", tc_last_error());
+    if (stat && stat_done) *stat_done = true;
     return FU_OK;
   }
   ConvCall c;
@@ -979,9 +985,10 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
   return run_wgrad<T>(e, c);
 }
 
+// in_sums (optional): set when blk.dstat received the per-channel sums of *d_in from the last data-gradient kernel
 template <typename T>
 int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, const View* d_in, int B, int H,
-                   int W, int training, float* flat) {
+                   int W, int training, float* flat, bool* in_sums = nullptr) {
   const int nd = (int)blk.convs.size();
   const bool bn = !blk.bns.empty();
   const long long P = (long long)B * H * W;
@@ -1021,8 +1028,11 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
       if ((rc = conv_dgrad<T>(e, cw, blk.dy[i], blk.dz[i], B, H, W, 0))) return rc;
       d = blk.dz[i];
     } else if (d_in) {
-      if ((rc = conv_dgrad<T>(e, cw, blk.dy[0], *d_in, B, H, W, 0))) return rc;
-      if (blk.has_res && (rc = conv_dgrad<T>(e, blk.res, g, *d_in, B, H, W, 1))) return rc;
+      // the LAST writer of *d_in also sums it per channel: that is the bias gradient of the up / downsample conv
+      // whose output this block consumed (no separate pass over the tensor)
+      double* st = in_sums ? blk.dstat : nullptr;
+      if ((rc = conv_dgrad<T>(e, cw, blk.dy[0], *d_in, B, H, W, 0, blk.has_res ? nullptr : st, in_sums))) return rc;
+      if (blk.has_res && (rc = conv_dgrad<T>(e, blk.res, g, *d_in, B, H, W, 1, st, in_sums))) return rc;
     }
   }
   return FU_OK;
@@ -1100,13 +1110,15 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   for (int j = D - 2; j >= 0; --j) {
     const int l = D - 2 - j;
     const int h = H >> l, w = W >> l;
-    if ((rc = block_backward<T>(e, e->dec[j], pl.cat[l], g, &pl.d_cat[l], B, h, w, training, flat))) return rc;
+    bool in_sums = false;
+    if ((rc = block_backward<T>(e, e->dec[j], pl.cat[l], g, &pl.d_cat[l], B, h, w, training, flat, &in_sums))) return rc;
     ConvW& up = e->upc[j];
     View d_up = slice(pl.d_cat[l], 0, e->chans[l], esz);
     View u = (l == D - 2) ? pl.bott : pl.decout[l + 1];
     View d_u = (l == D - 2) ? pl.d_bott : pl.d_decout[l + 1];
     e->set_tag(4.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_bwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
-    if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
+    if (in_sums) e->deferred_sums.push_back({e->dec[j].dstat, gptr(e, flat, up.b_idx), e->chans[l]});   // channels [0,C) of d_cat
+    else if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
     if (tc_up_eligible(up.tc, u.p, u.ld, d_up.p, d_up.ld)) {
       if (e->prof) e->prof_begin("tc_wgrad_kernel");
       int trc = tc_up_wgrad(up.tc, u.p, u.ld, d_up.p, d_up.ld, B, h / 2, w / 2, gptr(e, flat, up.w_idx), e->stream, &e->cnt);
@@ -1137,7 +1149,9 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     const int h = H >> l, w = W >> l;
     View gl = (D == 1) ? g : (l == D - 1 ? g : slice(pl.d_cat[l], e->chans[l], e->chans[l], esz));
     View x_in = (l == 0) ? pl.xin : pl.down[l];
-    if ((rc = block_backward<T>(e, e->enc[l], x_in, gl, l == 0 ? nullptr : &pl.d_down[l], B, h, w, training, flat)))
+    bool in_sums = false;
+    if ((rc = block_backward<T>(e, e->enc[l], x_in, gl, l == 0 ? nullptr : &pl.d_down[l], B, h, w, training, flat,
+                                (l > 0 && !c.max_pool) ? &in_sums : nullptr)))
       return rc;
     if (l > 0) {
       View src = slice(pl.cat[l - 1], e->chans[l - 1], e->chans[l - 1], esz);     // encoder output of level l-1
@@ -1149,7 +1163,8 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
                pl.d_down[l].ld, reinterpret_cast<T*>(d_src.p), d_src.ld, B, h, w, src.C, 1);
       } else {
         ConvW& cw = e->downc[l - 1];
-        if ((rc = channel_sum_to<T>(e, pl.d_down[l], (long long)B * h * w, cw.bsum, gptr(e, flat, cw.b_idx)))) return rc;
+        if (in_sums) e->deferred_sums.push_back({e->enc[l].dstat, gptr(e, flat, cw.b_idx), cw.Cout});
+        else if ((rc = channel_sum_to<T>(e, pl.d_down[l], (long long)B * h * w, cw.bsum, gptr(e, flat, cw.b_idx)))) return rc;
         if (tc_down_eligible(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld)) {
           if (e->prof) e->prof_begin("tc_wgrad_kernel");
           int trc = tc_down_wgrad(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld, B, 2 * h, 2 * w,

@@ -201,8 +201,8 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32
   return d;
 }
 // bf16 x bf16 -> fp32, both operands MN-major (K = pixels is the strided dimension), M = 128, N = n
-__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(uint32_t n, uint32_t m = 128u) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // ===========================================================================
@@ -989,13 +989,21 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // 512 B) instead of N/4 16-byte `red.global` instructions: the split-K epilogues cost 0.37 ms of a 7.5 ms step
 // (FU_TC_WGRAD_NOEPI diagnostic) and most of that was issue and L2-atomic traffic.  Rows are private to their
 // thread, so the only ordering needed is the thread's own proxy fence and bulk-group waits (double buffered).
+// m64 != 0: the MMAs ran with M = 64 (layers with <= 64 out-channels; an M = 128 tile would be half or three quarters
+// padding).  `m64` selects how accumulator row r maps to a TMEM lane: 2 (what the hardware does, tools/m64_probe.py):
+// lane (r % 16) + 32 * (r / 16), i.e. 16 lanes of each warp's quadrant; 1 (wrong, kept for the probe): lane r.
+// Measured gain is small (93 -> 78 us at 32->32 @192x192): these layers are not bound by tensor-pipe time.
 __device__ __forceinline__ void tc_wgrad_epilogue(uint32_t tmem_base, uint32_t smem_base, uint32_t avail_bytes, int N, int ntaps,
-                                                  int tap0, int tap_stride, int co, int Cout, int ci0, int Cin, int row,
-                                                  int q, float* dw_acc, int skip) {
+                                                  int tap0, int tap_stride, int co0, int Cout, int ci0, int Cin, int row,
+                                                  int q, float* dw_acc, int skip, int m64) {
   const uint32_t pitch = (uint32_t)N * 4u + 16u;            // +16 B: 8 consecutive rows cover all 32 banks
   const int nbuf = avail_bytes >= 2u * 128u * pitch ? 2 : 1;
   const int ncols = min(N, Cin - ci0);                      // valid in-channels of this tile
-  const bool live = co < Cout && ncols > 0 && !skip;
+  int acc_row = row;                                        // accumulator row held by this thread's TMEM lane
+  if (m64 == 1) acc_row = row < 64 ? row : -1;
+  else if (m64 == 2) acc_row = (row & 31) < 16 ? (row >> 5) * 16 + (row & 15) : -1;
+  const int co = co0 + acc_row;
+  const bool live = acc_row >= 0 && co < Cout && ncols > 0 && !skip;
   for (int t = 0; t < ntaps; ++t) {
     const uint32_t soff = (uint32_t)(row * nbuf + (t % nbuf)) * pitch;
     if (t >= nbuf) { if (nbuf == 2) ptx::tma_store_wait_read1(); else ptx::tma_store_wait_read(); }
@@ -1027,6 +1035,7 @@ struct TcWgradParams {
   int co_tiles, ci_tiles, splits, stages;
   float* dw_acc;                // [taps][Cout][Cin] fp32, zeroed by the caller
   int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1): drop the accumulators instead of adding them
+  int m64;                      // 0: M = 128 MMAs; 1/2: M = 64 (out-channels <= 64), value = TMEM row layout (see epilogue)
   int b5;                       // B operand gathered with stride 2 (5-D map), taps = 2x2, pixel grid (W, H), B = 1
 };
 
@@ -1106,7 +1115,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     }
   } else if (warp == 1) {
     int stage = 0; uint32_t phase = 0;
-    const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N);
+    const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N, p.m64 ? 64u : 128u);
     const uint64_t dbase = umma_desc_mnmajor(0, kBox, 1024u);
     for (int it = 0; it < n_iters; ++it) {
       ptx::mbar_wait(full_bar(stage), phase);
@@ -1137,7 +1146,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
     tc_wgrad_epilogue(tmem_base, smem_base, (uint32_t)p.stages * stage_bytes, p.N, p.taps_per_cta,
-                      p.ksz > 1 ? p.ksz * grp : 0, 1, co0 + row, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi);
+                      p.ksz > 1 ? p.ksz * grp : 0, 1, co0, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi, p.m64);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -1168,6 +1177,7 @@ struct TcWgrad3Params {
   unsigned b_stage_bytes;       // bytes of the B region of one stage
   int stack;                    // 1: the three kw taps of a filter row are ONE MMA with N = 3*N (see above)
   int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1)
+  int m64;                      // see TcWgradParams
   float* dw_acc;                // [9][Cout][Cin] fp32, zeroed by the caller
 };
 
@@ -1245,7 +1255,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     }
   } else if (warp == 1) {
     int stage = 0; uint32_t phase = 0;
-    const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N);
+    const uint32_t idesc = umma_idesc_bf16_mn((uint32_t)p.N, p.m64 ? 64u : 128u);
     const uint64_t da = umma_desc_mnmajor(0, kABox, 1024u);                       // A: 64-channel SW128 blocks
     uint64_t db;                                                                   // B: SW128 or SW64 blocks
     {
@@ -1258,7 +1268,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     }
     // stacked operand: N block b = the tile shifted by b pixel rows
     const uint64_t dbs = (db & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((brow >> 4) & 0x3FFF) << 16);
-    const uint32_t idesc_s = umma_idesc_bf16_mn((uint32_t)(3 * p.N));
+    const uint32_t idesc_s = umma_idesc_bf16_mn((uint32_t)(3 * p.N), p.m64 ? 64u : 128u);
     const int ksteps = p.tw / 16;
     const int tpg = p.tpg, Nn = p.N;
     const uint32_t step_a16 = (16u * 128u) >> 4, step_b16 = (16u * brow) >> 4;
@@ -1310,7 +1320,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
     tc_wgrad_epilogue(tmem_base, smem_base, (uint32_t)p.stages * stage_bytes, p.N, p.tpg, p.tpg == 9 ? 0 : grp * 3, 1,
-                      co0 + row, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi);
+                      co0, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi, p.m64);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -2025,19 +2035,21 @@ inline bool tc_dgrad_eligible(const TcConv& t, const void* dy, int dy_ld, const 
   return t.enabled && tc_ptr_ok(dy, dy_ld) && tc_ptr_ok(dx, dx_ld);
 }
 
+// stat (optional, [2*Cin] doubles, zeroed by the caller): per-channel sum / sum of squares of the STORED dx, i.e.
+// of the final value when accumulate = 1 -- the bias gradient of the layer that produced dx's forward twin
 inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
-                         cudaStream_t stream, fu_counters* cnt) {
+                         cudaStream_t stream, fu_counters* cnt, double* stat = nullptr) {
   if (tc_use_v2(t, H, W)) {
     TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
     if (c3) {
-      c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = nullptr; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
+      c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = stat; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
       c3->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c3->p.t_ld = dx_ld;
       return tc_launch3(c3, stream, cnt);
     }
   }
   TcConv::Cached* c = tc_prepare(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
   if (!c) return -1;
-  c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  c->p.bias = nullptr; c->p.relu = 0; c->p.stat = stat; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
   c->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c->p.t_ld = dx_ld;
   return tc_launch(c, stream, cnt);
 }
@@ -2142,6 +2154,7 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     n.grid = (int)(units * splits);
     p.dw_acc = t.dw_acc;
     p.skip_epi = tc_env_int("FU_TC_WGRAD_NOEPI", 0);
+    p.m64 = M <= 64 ? tc_env_int("FU_TC_M64", 2) : 0;
     {
       long long dims[4] = {M, p.W, p.H, p.B};
       long long str[4] = {1, a_ld, (long long)p.W * a_ld, (long long)p.H * p.W * a_ld};
@@ -2224,6 +2237,7 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     n.grid = (int)(units * splits);
     p.dw_acc = t.dw_acc;
     p.skip_epi = tc_env_int("FU_TC_WGRAD_NOEPI", 0);
+    p.m64 = t.Cout <= 64 ? tc_env_int("FU_TC_M64", 2) : 0;
     {
       long long dims[4] = {t.Cout, W, H, B};
       long long str[4] = {1, dy_ld, (long long)W * dy_ld, (long long)H * W * dy_ld};
