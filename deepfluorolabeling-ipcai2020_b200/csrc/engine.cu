@@ -1031,8 +1031,26 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
       // the LAST writer of *d_in also sums it per channel: that is the bias gradient of the up / downsample conv
       // whose output this block consumed (no separate pass over the tensor)
       double* st = in_sums ? blk.dstat : nullptr;
-      if ((rc = conv_dgrad<T>(e, cw, blk.dy[0], *d_in, B, H, W, 0, blk.has_res ? nullptr : st, in_sums))) return rc;
-      if (blk.has_res && (rc = conv_dgrad<T>(e, blk.res, g, *d_in, B, H, W, 1, st, in_sums))) return rc;
+      bool fused = false;
+      if (blk.has_res && tc_dgrad_eligible(cw.tc, blk.dy[0].p, blk.dy[0].ld, d_in->p, d_in->ld) &&
+          tc_dgrad_can_fuse_res(cw.tc, blk.res.tc, H, W, g.p, g.ld)) {
+        // d_in = conv3x3^T(dy_0) + conv1x1^T(g) in ONE launch: the shortcut's data gradient rides along as extra,
+        // centre-tap-only K chunks (no write + read-modify-write of d_in, one launch less)
+        const double M = (double)B * H * W;
+        e->set_tag(2.0 * M * cw.Cin * cw.Cout * 10.0, (M * (d_in->C + 2.0 * blk.C)) * e->esz, "conv3_dgrad %dx%d %d->%d",
+                   H, W, cw.Cout, cw.Cin);
+        if (e->prof) e->prof_begin("tc_conv_kernel");
+        const int trc = tc_conv_dgrad(cw.tc, blk.dy[0].p, blk.dy[0].ld, d_in->p, d_in->ld, B, H, W, 0, e->stream, &e->cnt,
+                                      st, &blk.res.tc, g.p, g.ld);
+        if (e->prof) e->prof_end();
+        if (trc == 0) { fused = true; if (st && in_sums) *in_sums = true; }
+        else if (trc != -2) return e->fail(FU_ERR_CUDA, "fused residual dgrad launch failed: %s", tc_last_error());
+        else if (e->prof) { cudaEventDestroy(e->prof_recs.back().a); cudaEventDestroy(e->prof_recs.back().b); e->prof_recs.pop_back(); }
+      }
+      if (!fused) {
+        if ((rc = conv_dgrad<T>(e, cw, blk.dy[0], *d_in, B, H, W, 0, blk.has_res ? nullptr : st, in_sums))) return rc;
+        if (blk.has_res && (rc = conv_dgrad<T>(e, blk.res, g, *d_in, B, H, W, 1, st, in_sums))) return rc;
+      }
     }
   }
   return FU_OK;

@@ -564,6 +564,9 @@ struct TcConv3Params {
   int halo1;                    // 1: one halo load per chunk (kw by row shift); 0: one load per (chunk, kw)
   int npair;                    // pixel tiles per weight tile (1 or 2)
   int resident;                 // weights resident in shared memory (n_tiles == 1)
+  int res;                      // 1: a second source (tmA2 / tmB2) is accumulated as one more, centre-tap-only, set of K chunks:
+                                //    dX = conv3x3^T(dY) + conv1x1^T(G), the data gradients of a residual block's first 3x3 conv and
+                                //    of its 1x1 shortcut (unet.py:229-231) in ONE pass over dX instead of a write + read-modify-write
   int a_stages, b_stages;
   unsigned a_tile_bytes;        // one halo tile, rounded up to 1024 B
   int relu;
@@ -581,7 +584,8 @@ struct TcConv3Params {
 template <int S>
 __global__ void __launch_bounds__(64 + 256 * S, 1)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const TcConv3Params p) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB2, const TcConv3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
@@ -593,7 +597,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t a_stage_bytes = (uint32_t)p.npair * p.a_tile_bytes;
   const uint32_t a_off = 0;
   const uint32_t b_off = a_off + (uint32_t)p.a_stages * a_stage_bytes;
-  const uint32_t b_region = p.resident ? (uint32_t)(cchunks * 9) * b_bytes : (uint32_t)p.b_stages * b_bytes;
+  const int wtiles = cchunks * 9 + (p.res ? cchunks : 0);          // resident weight tiles: 9 taps (+ the 1x1) per chunk
+  const uint32_t b_region = p.resident ? (uint32_t)wtiles * b_bytes : (uint32_t)p.b_stages * b_bytes;
   const uint32_t staging_off = b_off + b_region;
   const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;      // one per epilogue group
   constexpr int NACC = 2 * S;              // TMEM accumulator stages (each: npair tiles of BN columns)
@@ -622,6 +627,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
+    if (p.res) { ptx::prefetch_tmap(&tmA2); ptx::prefetch_tmap(&tmB2); }
   }
   if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
   {
@@ -662,10 +668,13 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------ TMA producer (whole warp loops, one elected lane issues) -----
     {
       if (p.resident && ptx::elect_one()) {
-        ptx::mbar_expect_tx(res_bar, (uint32_t)(cchunks * 9) * b_bytes);
+        ptx::mbar_expect_tx(res_bar, (uint32_t)wtiles * b_bytes);
         for (int c = 0; c < cchunks; ++c)
           for (int tap = 0; tap < 9; ++tap)
             ptx::tma_load_3d(smem_base + b_off + (uint32_t)(c * 9 + tap) * b_bytes, &tmB, res_bar, c * p.KC, tap, 0);
+        if (p.res)
+          for (int c = 0; c < cchunks; ++c)
+            ptx::tma_load_3d(smem_base + b_off + (uint32_t)(cchunks * 9 + c) * b_bytes, &tmB2, res_bar, c * p.KC, 0, 0);
       }
       __syncwarp();
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
@@ -702,6 +711,36 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 __syncwarp();
                 if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
               }
+            }
+          }
+        }
+        if (p.res) {
+          // second source: the same halo boxes of G (only the centre view is used), one weight tile per chunk
+          for (int c = 0; c < cchunks; ++c) {
+            ptx::mbar_wait(a_empty(as), aph ^ 1u);
+            if (ptx::elect_one()) {
+              int nvalid = 0;
+              for (int i = 0; i < p.npair; ++i) nvalid += (sp * p.npair + i) < m_tiles ? 1 : 0;
+              ptx::mbar_expect_tx(a_full(as), (uint32_t)nvalid * box_bytes);
+              for (int i = 0; i < p.npair; ++i) {
+                const int mt = sp * p.npair + i;
+                if (mt >= m_tiles) break;
+                int w0, h0, n;
+                decode_m(mt, w0, h0, n);
+                ptx::tma_load_4d(smem_base + a_off + (uint32_t)as * a_stage_bytes + (uint32_t)i * p.a_tile_bytes, &tmA2,
+                                 a_full(as), c * p.KC, w0 - 1, h0 - 1, n);
+              }
+            }
+            __syncwarp();
+            if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+            if (!p.resident) {
+              ptx::mbar_wait(b_empty(bs), bph ^ 1u);
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(b_full(bs), b_bytes);
+                ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB2, b_full(bs), c * p.KC, 0, nb);
+              }
+              __syncwarp();
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
             }
           }
         }
@@ -742,7 +781,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::tc_fence_after();
             if (lane == 0 && c == 0 && g == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
             const uint64_t a_desc0 = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4);
-            const bool last_group = c == cchunks - 1 && g == groups - 1;
+            const bool last_group = c == cchunks - 1 && g == groups - 1 && !p.res;
             if (resident) {
               // all 9 taps straight from the resident weight region: one elected section per A stage
               if (ptx::elect_one()) {
@@ -809,6 +848,32 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (++bs == b_stages) { bs = 0; bph ^= 1u; }
               }
             }
+            if (++as == a_stages) { as = 0; aph ^= 1u; }
+          }
+        }
+        if (p.res) {
+          // + conv1x1^T(G): centre view of G's halo tile times the shortcut's weights, one K chunk at a time
+          for (int c = 0; c < cchunks; ++c) {
+            ptx::mbar_wait(a_full(as), aph);
+            ptx::tc_fence_after();
+            if (!resident) { ptx::mbar_wait(b_full(bs), bph); ptx::tc_fence_after(); }
+            if (ptx::elect_one()) {
+              const uint64_t ad = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4) +
+                                  (uint64_t)((uint32_t)((p.twb + 1) * row_bytes) >> 4);      // view (kh,kw) = (1,1)
+              const uint32_t b_addr = resident ? smem_base + b_off + (uint32_t)(cchunks * 9 + c) * b_bytes
+                                               : smem_base + b_off + (uint32_t)bs * b_bytes;
+              const uint64_t bd = dbase + (uint64_t)(b_addr >> 4);
+              for (int j = 0; j < ksteps; ++j) {
+                ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+                if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
+              }
+              if (!resident) ptx::umma_commit(b_empty(bs));
+              ptx::umma_commit(a_empty(as));
+              if (c == cchunks - 1) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
+            }
+            __syncwarp();
+            accum = 1;
+            if (!resident) { if (++bs == b_stages) { bs = 0; bph ^= 1u; } }
             if (++as == a_stages) { as = 0; aph ^= 1u; }
           }
         }
@@ -1601,8 +1666,8 @@ struct TcConv {
   };
   std::vector<W3Cached> w3cache;
   struct Cached3 {
-    const void *x, *y; int x_ld, y_ld, B, H, W, dir;
-    CUtensorMap a, b, c; TcConv3Params p; int grid; size_t smem; int S;
+    const void *x, *y, *x2; int x_ld, y_ld, x2_ld, B, H, W, dir;     // x2: second source of the fused residual dgrad (or null)
+    CUtensorMap a, b, c, a2, b2; TcConv3Params p; int grid; size_t smem; int S;
   };
   std::vector<Cached3> cache3;
   struct Cached {
@@ -1866,13 +1931,16 @@ inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
   }
 }
 
-inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W) {
+// res / x2: (dir 1 only) the block's 1x1 shortcut and the gradient G of the block output: dX = conv3x3^T(x) + conv1x1^T(x2)
+inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W,
+                                     const TcConv* res = nullptr, const void* x2 = nullptr, int x2_ld = 0) {
   for (auto& c : t.cache3)
-    if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == H && c.W == W && c.dir == dir)
+    if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == H && c.W == W && c.dir == dir &&
+        c.x2 == x2 && c.x2_ld == x2_ld)
       return &c;
   TcConv::Cached3 c;
   memset(&c, 0, sizeof(c));
-  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = H; c.W = W; c.dir = dir;
+  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = H; c.W = W; c.dir = dir; c.x2 = x2; c.x2_ld = x2_ld;
   TcConv3Params& p = c.p;
   const int K = dir == 0 ? t.Cin : t.Cout;
   const int N = dir == 0 ? t.Cout : t.Cin;
@@ -1895,7 +1963,8 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   const size_t a_stage = (size_t)p.npair * p.a_tile_bytes;
   const size_t b_bytes = (size_t)p.BN * row_bytes;
   const size_t budget = 227 * 1024;
-  const size_t wbytes = (size_t)9 * K * p.BN * 2;
+  p.res = (res && x2) ? 1 : 0;
+  const size_t wbytes = (size_t)(9 + p.res) * K * p.BN * 2;
   // two epilogue sets for the thin layers when everything (resident weights, >= 2 A stages) still fits
   // (measured: 32-column layers 75 -> 70 us, 32->64 dgrad @192 95 -> 77 us; 64->64 @96 35.5 -> 37 us: no gain at K >= 576)
   c.S = (p.BN <= 64 && (long long)K * p.BN <= 64 * 32 && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
@@ -1945,6 +2014,17 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     int box[4] = {p.CS, p.two, p.th, 1};
     if (tc_make_map(&c.c, y, 4, dims, str, box, p.CS * 2)) return nullptr;
   }
+  c.a2 = c.a; c.b2 = c.b;
+  if (p.res) {
+    long long dims[4] = {K, W, H, B};
+    long long str[4] = {1, x2_ld, (long long)W * x2_ld, (long long)H * W * x2_ld};
+    int box[4] = {p.KC, p.twb, p.th + 2, 1};
+    if (tc_make_map(&c.a2, x2, 4, dims, str, box, p.KC * 2)) return nullptr;
+    long long wd[3] = {K, 1, N};
+    long long ws[3] = {1, K, (long long)K};
+    int wb[3] = {p.KC, 1, p.BN};
+    if (tc_make_map(&c.b2, res->w_dgrad, 3, wd, ws, wb, p.KC * 2)) return nullptr;      // [Cin][1][Cout] of the 1x1
+  }
   t.cache3.push_back(c);
   return &t.cache3.back();
 }
@@ -1966,8 +2046,8 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
     cudaMemsetAsync(dbg_buf, 0, 4 * 24 * 4 * sizeof(long long), stream);
   }
   c->p.dbg = dbg ? dbg_buf : nullptr;
-  if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 64 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->p);
-  else tc_conv3_kernel<1><<<c->grid, 64 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 64 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else tc_conv3_kernel<1><<<c->grid, 64 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
   if (dbg) {
     long long h[4 * 24 * 4];
     cudaStreamSynchronize(stream);
@@ -2037,16 +2117,24 @@ inline bool tc_dgrad_eligible(const TcConv& t, const void* dy, int dy_ld, const 
 
 // stat (optional, [2*Cin] doubles, zeroed by the caller): per-channel sum / sum of squares of the STORED dx, i.e.
 // of the final value when accumulate = 1 -- the bias gradient of the layer that produced dx's forward twin
+// res / g: fuse the data gradient of the block's 1x1 shortcut (dX += conv1x1^T(g)) into this launch; only the halo
+// kernel can (tc_dgrad_can_fuse_res)
+inline bool tc_dgrad_can_fuse_res(const TcConv& t, const TcConv& res, int H, int W, const void* g, int g_ld) {
+  return tc_use_v2(t, H, W) && res.enabled && res.kind == 0 && res.k == 1 && res.Cin == t.Cin && res.Cout == t.Cout &&
+         tc_ptr_ok(g, g_ld) && tc_env_int("FU_TC_FUSE_RES", 1) != 0;
+}
 inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
-                         cudaStream_t stream, fu_counters* cnt, double* stat = nullptr) {
+                         cudaStream_t stream, fu_counters* cnt, double* stat = nullptr, const TcConv* res = nullptr,
+                         const void* g = nullptr, int g_ld = 0) {
   if (tc_use_v2(t, H, W)) {
-    TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
+    TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W, res, g, g_ld);
     if (c3) {
       c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = stat; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
       c3->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c3->p.t_ld = dx_ld;
       return tc_launch3(c3, stream, cnt);
     }
   }
+  if (res) return -2;          // not fusable here (no halo configuration): the caller runs the two kernels
   TcConv::Cached* c = tc_prepare(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
   if (!c) return -1;
   c->p.bias = nullptr; c->p.relu = 0; c->p.stat = stat; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
