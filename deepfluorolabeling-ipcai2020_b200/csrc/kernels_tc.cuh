@@ -1398,20 +1398,19 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 // accumulator into the torch layout.  (The per-layer versions were 92 launches and 0.64 ms per step, most of
 // it uncoalesced 2-byte scatter: the transposes now go through shared-memory tiles.)
 // ---------------------------------------------------------------------------
-// generic bf16 pack of a GEMM B matrix [N][T][K] from a torch-layout weight:
-//   dst[(n*T + t)*K + k] = src[tmap(t)*st + k*sk + (n / Ninner)*snh + (n % Ninner)*snl]
-struct TcPackArgs {
-  const float* src; bf16* dst;
-  int N, T, K, Ninner, flip;
-  long long st, sk, snh, snl;
-};
+// One pack job = one fp32 torch weight viewed as [R][Cc][taps] (rows, columns, taps; taps fastest) and its two bf16 GEMM
+// layouts, both written through 32 x 32 x taps shared-memory tiles:
+//   out1[r*a1 + t*b1 + c]          -- for fixed (r, t) the columns are contiguous  ("row-major" output)
+//   out2[base2 + c*a2 + t*b2 + r]  -- for fixed (c, t) the rows are contiguous     ("transposed" output)
+// Conv2d 3x3/1x1 (R=Cout, Cc=Cin): out1 = forward [Cout][tap][Cin], out2 = data gradient [Cin][flip(tap)][Cout].
+// Conv2d 2x2/s2  (R=Cout, Cc=Cin): out1 = forward (gather conv) [Cout][ab][Cin], out2 = data gradient (scatter GEMM) [(ab,ci)][Cout].
+// ConvT  2x2/s2  (R=Cin, Cc=Cout): out1 = data gradient (gather conv over dY) [Cin][ab][Cout], out2 = forward (scatter GEMM) [(ab,co)][Cin].
 struct TcPackJob {
-  int kind;                     // 0: Conv2d 3x3 / 1x1 (tiled transposes); 1: generic (2x2 stride-2 layers)
   int block0;                   // first block of this job in the batched grid
   int nblocks;
-  // kind 0: fp32 torch weights (Cout,Cin,k,k) -> bf16 [Cout][tap][Cin] (forward) and [Cin][flip(tap)][Cout] (data gradient)
-  const float* w; bf16* fwd; bf16* dgrad; int Cout, Cin, taps;
-  TcPackArgs f, d;              // kind 1
+  const float* w; bf16* out1; bf16* out2;
+  int R, Cc, taps;
+  long long a1, b1, a2, b2, base2;
 };
 struct TcUnpackJob {
   const float* acc;             // [taps][M][N] fp32
@@ -1421,72 +1420,51 @@ struct TcUnpackJob {
   int M, N, taps;
   int block0, nblocks;
 };
-constexpr int kPackGenericPerBlock = 2048;
-
 template <typename Job>
 __device__ __forceinline__ int tc_find_job(const Job* jobs, int njobs, int* s_job) {
-  if (threadIdx.x == 0) {
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) {            // last job with block0 <= blockIdx.x
-      const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    *s_job = lo;
-  }
+  // last job with block0 <= blockIdx.x: every thread tests one job (one round trip to the table instead of the
+  // six dependent ones of a single-thread binary search at the start of every block)
+  if (threadIdx.x == 0) *s_job = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < njobs; i += blockDim.x)
+    if (jobs[i].block0 <= (int)blockIdx.x && (i + 1 == njobs || jobs[i + 1].block0 > (int)blockIdx.x)) *s_job = i;
   __syncthreads();
   return *s_job;
 }
 
-// one 32 (co) x 32 (ci) x TAPS tile; the loops are warp = row, lane = column, so no division by a run-time value
+// one 32 (rows) x 32 (columns) x TAPS tile; the loops are warp = row, lane = column, so no division by a run-time value
 template <int TAPS>
 __device__ __forceinline__ void tc_pack_tile(const TcPackJob& J, int lb, float* tile) {
-  const int tiles_ci = J.Cin / 32;
-  const int co0 = (lb / tiles_ci) * 32, ci0 = (lb % tiles_ci) * 32;
+  const int tiles_c = J.Cc / 32;
+  const int r0 = (lb / tiles_c) * 32, c0 = (lb % tiles_c) * 32;
   constexpr int ROW = 32 * TAPS;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   for (int r = wrp; r < 32; r += 8) {
-    const float* src = J.w + ((long long)(co0 + r) * J.Cin + ci0) * TAPS;
+    const float* src = J.w + ((long long)(r0 + r) * J.Cc + c0) * TAPS;
 #pragma unroll
     for (int c = lane; c < ROW; c += 32) tile[r * 289 + c] = src[c];
   }
   __syncthreads();
-  for (int r = wrp; r < 32; r += 8) {           // forward: rows co, (t, ci) contiguous per co
-    bf16* dst = J.fwd + (long long)(co0 + r) * TAPS * J.Cin + ci0 + lane;
+  for (int r = wrp; r < 32; r += 8) {           // out1: (t, c) per row, c contiguous
+    bf16* dst = J.out1 + (long long)(r0 + r) * J.a1 + c0 + lane;
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) dst[(long long)t * J.Cin] = __float2bfloat16_rn(tile[r * 289 + lane * TAPS + t]);
+    for (int t = 0; t < TAPS; ++t) dst[(long long)t * J.b1] = __float2bfloat16_rn(tile[r * 289 + lane * TAPS + t]);
   }
-  for (int ci = wrp; ci < 32; ci += 8) {        // data gradient: rows ci, (flipped t, co) contiguous per ci
-    bf16* dst = J.dgrad + (long long)(ci0 + ci) * TAPS * J.Cout + co0 + lane;
+  for (int c = wrp; c < 32; c += 8) {           // out2: (t, r) per column, r contiguous
+    bf16* dst = J.out2 + J.base2 + (long long)(c0 + c) * J.a2 + r0 + lane;
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) dst[(long long)(TAPS - 1 - t) * J.Cout] = __float2bfloat16_rn(tile[lane * 289 + ci * TAPS + t]);
+    for (int t = 0; t < TAPS; ++t) dst[(long long)t * J.b2] = __float2bfloat16_rn(tile[lane * 289 + c * TAPS + t]);
   }
 }
 
 __global__ void __launch_bounds__(256) tc_pack_batched_kernel(const TcPackJob* jobs, int njobs) {
   __shared__ int s_job;
-  __shared__ float tile[32 * 289];      // [co][ci*taps + t], odd row stride: conflict-free row- and column-wise
+  __shared__ float tile[32 * 289];      // [r][c*taps + t], odd row stride: conflict-free row- and column-wise
   const TcPackJob& J = jobs[tc_find_job(jobs, njobs, &s_job)];
   const int lb = (int)blockIdx.x - J.block0;
-  if (J.kind == 0) {
-    if (J.taps == 9) tc_pack_tile<9>(J, lb, tile);
-    else tc_pack_tile<1>(J, lb, tile);
-  } else {
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      const TcPackArgs& p = which ? J.d : J.f;
-      const long long total = (long long)p.N * p.T * p.K;
-      const long long i0 = (long long)lb * kPackGenericPerBlock;
-      for (long long i = i0 + threadIdx.x; i < i0 + kPackGenericPerBlock && i < total; i += 256) {
-        const int k = (int)(i % p.K);
-        const long long r = i / p.K;
-        const int t = (int)(r % p.T);
-        const int n = (int)(r / p.T);
-        const int tm = p.flip ? (p.T - 1 - t) : t;
-        const int nh = n / p.Ninner, nl = n - nh * p.Ninner;
-        p.dst[i] = __float2bfloat16_rn(p.src[tm * p.st + k * p.sk + nh * p.snh + nl * p.snl]);
-      }
-    }
-  }
+  if (J.taps == 9) tc_pack_tile<9>(J, lb, tile);
+  else if (J.taps == 4) tc_pack_tile<4>(J, lb, tile);
+  else tc_pack_tile<1>(J, lb, tile);
 }
 
 // dw[(m*N + n)*taps + t] = acc[(t*M + m)*N + n]: tiles of 8 m x 32 n, reads and writes both contiguous
@@ -1708,25 +1686,23 @@ inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* 
   if (!t.enabled) return 0;
   TcPackJob j;
   memset(&j, 0, sizeof(j));
-  if (t.kind == 0) {
-    j.kind = 0; j.w = w; j.fwd = t.w_fwd; j.dgrad = t.w_dgrad; j.Cout = t.Cout; j.Cin = t.Cin; j.taps = t.k * t.k;
-    j.nblocks = (t.Cout / 32) * (t.Cin / 32);
-  } else {
-    TcPackArgs& f = j.f; TcPackArgs& d = j.d;
-    j.kind = 1;
-    f.src = d.src = w; f.dst = t.w_fwd; d.dst = t.w_dgrad; f.flip = d.flip = 0;
-    if (t.kind == 1) {
-      // W[co][ci][ab].  fwd (gather conv): [N=Cout][T=4][K=Cin];  dgrad (scatter GEMM): [N=(ab,ci)][1][K=Cout]
-      f.N = t.Cout; f.T = 4; f.K = t.Cin; f.Ninner = t.Cout; f.st = 1; f.sk = 4; f.snh = 0; f.snl = (long long)t.Cin * 4;
-      d.N = 4 * t.Cin; d.T = 1; d.K = t.Cout; d.Ninner = t.Cin; d.st = 0; d.sk = (long long)t.Cin * 4; d.snh = 1; d.snl = 4;
-    } else {
-      // W[ci][co][ab].  fwd (scatter GEMM): [N=(ab,co)][1][K=Cin];  dgrad (gather conv over dY): [N=Cin][T=4][K=Cout]
-      f.N = 4 * t.Cout; f.T = 1; f.K = t.Cin; f.Ninner = t.Cout; f.st = 0; f.sk = (long long)t.Cout * 4; f.snh = 1; f.snl = 4;
-      d.N = t.Cin; d.T = 4; d.K = t.Cout; d.Ninner = t.Cin; d.st = 1; d.sk = 4; d.snh = 0; d.snl = (long long)t.Cout * 4;
-    }
-    const long long total = (long long)t.Cin * t.Cout * 4;
-    j.nblocks = (int)((total + kPackGenericPerBlock - 1) / kPackGenericPerBlock);
+  j.w = w;
+  const long long Ci = t.Cin, Co = t.Cout;
+  if (t.kind == 0) {            // W[co][ci][tap]
+    const int taps = t.k * t.k;
+    j.R = t.Cout; j.Cc = t.Cin; j.taps = taps;
+    j.out1 = t.w_fwd; j.a1 = taps * Ci; j.b1 = Ci;                                   // [co][tap][ci]
+    j.out2 = t.w_dgrad; j.a2 = taps * Co; j.b2 = -Co; j.base2 = (taps - 1) * Co;     // [ci][flip tap][co]
+  } else if (t.kind == 1) {     // W[co][ci][ab]
+    j.R = t.Cout; j.Cc = t.Cin; j.taps = 4;
+    j.out1 = t.w_fwd; j.a1 = 4 * Ci; j.b1 = Ci;                                      // gather conv: [co][ab][ci]
+    j.out2 = t.w_dgrad; j.a2 = Co; j.b2 = Ci * Co; j.base2 = 0;                      // scatter GEMM: [(ab,ci)][co]
+  } else {                      // W[ci][co][ab]
+    j.R = t.Cin; j.Cc = t.Cout; j.taps = 4;
+    j.out1 = t.w_dgrad; j.a1 = 4 * Co; j.b1 = Co;                                    // gather conv over dY: [ci][ab][co]
+    j.out2 = t.w_fwd; j.a2 = Ci; j.b2 = Co * Ci; j.base2 = 0;                        // scatter GEMM: [(ab,co)][ci]
   }
+  j.nblocks = (j.R / 32) * (j.Cc / 32);
   if (tc_batch()) { tc_batch()->pack.push_back(j); return 0; }
   return tc_run_job_now(j, tc_pack_launcher(stream), stream, cnt);
 }
