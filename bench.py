@@ -359,8 +359,21 @@ def run_ours(args):
         conv_fl = sum(v["flops"] for k, v in fam.items() if k.startswith("conv3_"))
         peak, _, how = peaks()
         ach = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        # DRAM bytes per step of the tensor-core conv kernels from the committed ncu launch list of this workload
+        # (tools/ncu_traffic.py; cold-cache per launch, and a superset of the family: it includes the 1x1 / 2x2 layers)
+        traffic, traffic_note = None, "no ncu summary committed"
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic_final.json")
+        if S == 192 and B == 32 and os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic = tj["tensor_core_conv_kernels_per_step"]["dram_bytes"]
+                traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per step over tc_conv*/tc_wgrad* launches "
+                                "(profiles/r01_ncu_launches_final.csv; ncu flushes caches per launch; includes the 1x1/2x2 layers)")
+            except Exception:
+                pass
         roof = {"bound": "tensor", "kernel": "3x3 conv family (fwd + dgrad + wgrad, 22 layers x 3)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": how, "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms_per_step": conv_ms}
         tot = sum(v["ms"] for v in fam.values())
         breakdown = {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}

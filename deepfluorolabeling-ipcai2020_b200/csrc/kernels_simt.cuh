@@ -1274,7 +1274,22 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const T* r, int 
         f.mean_o[c + i] = mean; f.invstd_o[c + i] = invstd; f.a_o[c + i] = a[i]; f.b_o[c + i] = b[i];
       }
     }
-    for (long long pix = (long long)blockIdx.x * rows + prow; pix < P; pix += (long long)gridDim.x * rows) {
+    const long long step = (long long)gridDim.x * rows;
+    long long pix = (long long)blockIdx.x * rows + prow;
+    for (; pix + 3 * step < P; pix += 4 * step) {      // four 16-byte loads in flight per thread
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = ld_raw16(r + (pix + u * step) * r_ld + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[V];
+        Vec<T>::unpack(q[u], v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = fmaf(a[i], v[i], b[i]);
+        Vec<T>::store(z + (pix + u * step) * z_ld + c, v);
+      }
+    }
+    for (; pix < P; pix += step) {
       float v[V];
       Vec<T>::load(r + pix * r_ld + c, v);
 #pragma unroll

@@ -1768,6 +1768,11 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   if (getenv("FU_TC_BN_MAX") == nullptr && N % 256 == 0 &&
       (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / 256) * 10 >= 9ll * sms)
     bn = 256;
+  // ... and the other way round on the smallest levels (6x6: 9 pixel tiles): narrower N tiles until at least ~60 % of
+  // the SMs have one (72 CTAs of 128 columns leave half the machine idle; 144 of 64 columns re-read A twice as often
+  // but finish sooner)
+  if (getenv("FU_TC_BN_MAX") == nullptr)
+    while (bn > 32 && (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / bn) * 10 < 6ll * sms) bn >>= 1;
   p.BN = bn;
   p.CS = bn >= 64 ? 64 : 32;
   p.n_tiles = N / p.BN;
