@@ -343,8 +343,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
         for (int kit = 0; kit < k_iters; ++kit) {
+          // (no tcgen05.fence here: the operands were written by TMA, whose completion the mbarrier itself orders
+          //  before this thread's MMAs; the fence is only needed after waits on barriers that OTHER THREADS'
+          //  tcgen05.ld signalled, i.e. the accumulator hand-back above)
           ptx::mbar_wait(full_bar(stage), phase);
-          ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
             const uint64_t ad0 = umma_desc_at(dbase, a_addr), bd0 = umma_desc_at(dbase, a_addr + a_bytes);
@@ -778,7 +780,6 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int c = 0; c < cchunks; ++c) {
           for (int g = 0; g < groups; ++g) {
             ptx::mbar_wait(a_full(as), aph);
-            ptx::tc_fence_after();
             if (lane == 0 && c == 0 && g == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
             const uint64_t a_desc0 = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4);
             const bool last_group = c == cchunks - 1 && g == groups - 1 && !p.res;
@@ -817,7 +818,6 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int tt = 0; tt < taps_per_group; ++tt) {
                 const int tap = halo1 ? tt : tt * 3 + g;
                 ptx::mbar_wait(b_full(bs), bph);
-                ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                   const uint64_t ad = a_desc0 + rowoff16[tap];
                   const uint64_t bd = dbase + (uint64_t)((smem_base + b_off + (uint32_t)bs * b_bytes) >> 4);
@@ -855,8 +855,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // + conv1x1^T(G): centre view of G's halo tile times the shortcut's weights, one K chunk at a time
           for (int c = 0; c < cchunks; ++c) {
             ptx::mbar_wait(a_full(as), aph);
-            ptx::tc_fence_after();
-            if (!resident) { ptx::mbar_wait(b_full(bs), bph); ptx::tc_fence_after(); }
+            if (!resident) ptx::mbar_wait(b_full(bs), bph);
             if (ptx::elect_one()) {
               const uint64_t ad = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4) +
                                   (uint64_t)((uint32_t)((p.twb + 1) * row_bytes) >> 4);      // view (kh,kw) = (1,1)
@@ -1184,7 +1183,6 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     const uint64_t dbase = umma_desc_mnmajor(0, kBox, 1024u);
     for (int it = 0; it < n_iters; ++it) {
       ptx::mbar_wait(full_bar(stage), phase);
-      ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
         const uint64_t ad0 = umma_desc_at(dbase, a_addr);
@@ -1345,7 +1343,6 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     }
     for (int it = 0; it < n_iters; ++it) {
       ptx::mbar_wait(full_bar(stage), phase);
-      ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
         const uint64_t ad0 = da + (uint64_t)(a_addr >> 4);

@@ -12,15 +12,19 @@ if args and args[0] == "--time":
     timed = True; args = args[1:]
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 for spec in args:
-    B, Cin, Cout, H, W, k, mode = [int(a) for a in spec.split()]
+    f = [int(a) for a in spec.split()]
+    B, Cin, Cout, H, W, k, mode = f[:7]
+    stride = f[7] if len(f) > 7 else 1          # 2: Conv2d(k=2,s=2) on x (B,H,W,Cin); -2: ConvTranspose2d(k=2,s=2)
+    Ho, Wo = (H // 2, W // 2) if stride == 2 else ((2 * H, 2 * W) if stride == -2 else (H, W))
     x = torch.randn(B, H, W, Cin, device=dev).bfloat16()
-    w = (torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5)
+    w = (torch.randn(*((Cin, Cout, k, k) if stride == -2 else (Cout, Cin, k, k)), device=dev) / (Cin * k * k) ** 0.5)
     b = torch.randn(Cout, device=dev)
-    dy = torch.randn(B, H, W, Cout, device=dev).bfloat16()
-    y = torch.empty(B, H, W, Cout if mode == 0 else Cin, device=dev, dtype=torch.bfloat16)
+    dy = torch.randn(B, Ho, Wo, Cout, device=dev).bfloat16()
+    y = torch.empty(*((B, Ho, Wo, Cout) if mode == 0 else (B, H, W, Cin)), device=dev, dtype=torch.bfloat16)
     dw = torch.empty_like(w)
+    pad = k // 2 if stride == 1 else 0
     def run():
-        rc = L.fu_test_conv(1, 1, mode, B, H, W, Cin, Cout, k, 1, k // 2, 1, p(x), p(w), p(b), p(y), p(dy), p(dw), None, None)
+        rc = L.fu_test_conv(1, 1, mode, B, H, W, Cin, Cout, k, stride, pad, 1 if stride == 1 else 0, p(x), p(w), p(b), p(y), p(dy), p(dw), None, None)
         assert rc == 0, pkg._capi.last_error(None)
     run()
     if timed:
@@ -30,7 +34,7 @@ for spec in args:
             torch.cuda.synchronize()
         for e in prof.key_averages():
             if "tc_" in e.key and "batched" not in e.key:
-                fl = 2.0 * B * H * W * Cin * Cout * k * k
+                fl = 2.0 * B * (H * W if stride != 2 else Ho * Wo) * Cin * Cout * k * k
                 us = e.device_time_total / e.count
                 print("%-26s %-30s %8.1f us %7.1f TFLOP/s" % (spec, e.key[:30], us, fl / us / 1e6), flush=True)
     else:
