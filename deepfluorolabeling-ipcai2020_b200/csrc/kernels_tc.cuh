@@ -408,14 +408,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode(tile, w0, h0, n0, nb);
       const bool valid = row < rows_in_tile && (w0 + wi) < p.W && (h0 + hi) < p.H && (n0 + ni) < p.B;
       long long pix = ((long long)(n0 + ni) * p.H + (h0 + hi)) * p.W + (w0 + wi);
-      int cb = nb;            // channel base of this N tile in the bias / t / output tensors
-      int sh_a = 0, sh_b = 0;
-      if (p.c5) {
-        const int ab = nb / p.Cst;
-        cb = nb - ab * p.Cst;
-        sh_a = ab >> 1; sh_b = ab & 1;
-        pix = ((long long)(h0 + hi) * 2 + sh_a) * (2 * p.W) + 2 * (w0 + wi) + sh_b;
-      }
+      // Scattered (pixel-shuffle) output: GEMM column = (a,b,co).  An N tile may span several (a,b) blocks (BN a
+      // multiple of Cst: the A tile is then loaded once for all four sub-pixels), so the channel base and the
+      // output pixel are functions of the 32-column chunk, not of the tile.
+      auto chunk_cb = [&](int col) { return p.c5 ? col % p.Cst : col; };     // channel base in bias / t / output
+      auto chunk_pix = [&](int col) {
+        if (!p.c5) return pix;
+        const int ab = col / p.Cst;
+        return ((long long)(h0 + hi) * 2 + (ab >> 1)) * (2 * p.W) + 2 * (w0 + wi) + (ab & 1);
+      };
       if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
       // the second epilogue operand (residual / accumulate) is fetched before waiting for the accumulator,
       // so its global-memory latency hides behind the MMAs (BN <= 128: 16 x 16 B per thread)
@@ -429,8 +430,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       uint4 tnext[4];
       const bool t_on = p.t != nullptr && valid;
-      const uint4* tp4 = reinterpret_cast<const uint4*>(p.t + pix * p.t_ld + cb);
       if (t_on) {
+        const uint4* tp4 = reinterpret_cast<const uint4*>(p.t + chunk_pix(nb) * p.t_ld + chunk_cb(nb));
 #pragma unroll
         for (int i = 0; i < 4; ++i) tnext[i] = tp4[i];
       }
@@ -441,7 +442,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
         ptx::tmem_ld_wait();
-        const int c0 = cb + j * 32;
+        const int c0 = chunk_cb(nb + j * 32);
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -454,8 +455,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 4; ++i) tcur[i] = tnext[i];
           if (j + 1 < p.BN / 32) {            // software pipeline: next chunk's operand is in flight during this one
+            const int ncol = nb + (j + 1) * 32;
+            const uint4* tp4 = reinterpret_cast<const uint4*>(p.t + chunk_pix(ncol) * p.t_ld + chunk_cb(ncol));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tnext[i] = tp4[(j + 1) * 4 + i];
+            for (int i = 0; i < 4; ++i) tnext[i] = tp4[i];
           }
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
@@ -505,7 +508,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::named_bar_sync(bar_id, 128);
       if (et == 0) {
         for (int s = 0; s < p.BN / p.CS; ++s) {
-          if (p.c5) ptx::tma_store_5d(&tmC, staging_addr + (uint32_t)s * sub_bytes, cb + s * p.CS, sh_b, w0, sh_a, h0);
+          if (p.c5) {
+            const int col = nb + s * p.CS, ab = col / p.Cst;
+            ptx::tma_store_5d(&tmC, staging_addr + (uint32_t)s * sub_bytes, col - ab * p.Cst, ab & 1, w0, ab >> 1, h0);
+          }
           else ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s * sub_bytes, nb + s * p.CS, w0, h0, n0);
         }
         ptx::tma_store_commit();
@@ -1825,7 +1831,7 @@ inline int tc_make_s2_map(CUtensorMap* m, const void* base, int C, int ld, int W
 //                  gather = 0: y(2Wg,2Rg) scattered from x(Wg,Rg)               (ConvT forward, Conv2d k2s2 dgrad)
 // (Wg, Hg) is the COARSE grid; Rg = B*Hg merged rows.  K / N are the GEMM depth / columns.
 inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16* wmat, int K, int N, int Cst,
-                                      const void* x, int x_ld, void* y, int y_ld, int B, int Hg, int Wg) {
+                                      const void* x, int x_ld, void* y, int y_ld, int B, int Hg, int Wg, int merge = 1) {
   for (auto& c : t.cache)
     if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == Hg && c.W == Wg && c.dir == dir)
       return &c;
@@ -1839,10 +1845,20 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   p.a5 = gather ? 1 : 0; p.c5 = gather ? 0 : 1; p.Cst = Cst;
   p.KC = (K % 64 == 0) ? 64 : 32;
   int bn = tc_bn_max();
-  const int ncol = gather ? N : Cst;      // an N tile must not straddle two (a,b) blocks
-  while (ncol % bn) bn >>= 1;
-  p.BN = bn;
-  p.CS = bn >= 64 ? 64 : 32;
+  if (gather) {
+    while (N % bn) bn >>= 1;
+    p.BN = bn;
+    p.CS = bn >= 64 ? 64 : 32;
+  } else {
+    // scatter: N = 4*Cst columns (a,b,co).  One N tile covers as many whole (a,b) blocks as fit 128 columns, so the
+    // A tile is read once for all of them; a store box (CS channels) never straddles two blocks.
+    while (Cst % bn) bn >>= 1;                                   // bn <= Cst, divides it
+    p.CS = bn >= 64 ? 64 : 32;
+    // (not when the epilogue also reads the old output, i.e. the accumulating downsample data gradient: there the
+    //  wider tile's per-chunk second-operand fetches cost more than the A re-reads save -- measured in the step)
+    if (merge && tc_env_int("FU_TC_SCATTER_MERGE", 1)) while (bn * 2 <= 128 && N % (bn * 2) == 0) bn *= 2;
+    p.BN = bn;
+  }
   tc_pick_tile(1, (int)Rg, Wg, p.tw, p.th, p.tn);
   p.tn = 1;
   p.tiles_w = (Wg + p.tw - 1) / p.tw; p.tiles_h = (int)((Rg + p.th - 1) / p.th); p.tiles_b = 1;
@@ -2134,7 +2150,8 @@ inline int tc_down_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld
 // dx (B,H,W,Cin) (+)= scatter of dy (B,H/2,W/2,Cout)
 inline int tc_down_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
                          cudaStream_t stream, fu_counters* cnt) {
-  TcConv::Cached* c = tc_prepare_s2(t, 1, 0, t.w_dgrad, t.Cout, 4 * t.Cin, t.Cin, dy, dy_ld, dx, dx_ld, B, H / 2, W / 2);
+  TcConv::Cached* c = tc_prepare_s2(t, 1, 0, t.w_dgrad, t.Cout, 4 * t.Cin, t.Cin, dy, dy_ld, dx, dx_ld, B, H / 2, W / 2,
+                                    accumulate ? 0 : 1);
   if (!c) return -1;
   c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
   c->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c->p.t_ld = dx_ld;
