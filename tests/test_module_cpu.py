@@ -111,3 +111,20 @@ def test_losses_match_reference_formulas(pkg):
     b = O.dice_and_heatmap_loss(seg, heat, tgt_seg, tgt_heat, skip_bg=False, heatmap_wgt=0.5)
     assert abs(float(a) - float(b)) < 1e-6
     assert abs(float(pkg.DiceLoss2D(skip_bg=True)(seg, tgt_seg)) - float(O.dice_loss(seg, tgt_seg, True))) < 1e-6
+
+
+def test_fused_loss_and_graphed_step_refuse_cpu_tensors(pkg):
+    """The device-only helpers fail loudly instead of falling back to a CPU path."""
+    seg = torch.rand(1, 7, 8, 8)
+    with pytest.raises(RuntimeError):
+        pkg.FusedDiceLoss2D()(seg, seg)
+    with pytest.raises(RuntimeError):
+        pkg.FusedDiceAndHeatMapLoss2D()((seg, seg), (seg, seg))
+    with pytest.raises(ValueError):
+        pkg.GraphedStep(lambda x: x, (seg,))
+
+
+def test_fused_loss_descriptor_matches_header(pkg):
+    """ctypes mirror of fu_loss_desc: 4 x (pointer + 3 int64 strides) + 6 int32 + 2 float, no hidden padding."""
+    import ctypes as C
+    assert C.sizeof(pkg._capi.FuLossDesc) == 4 * (8 + 24) + 6 * 4 + 2 * 4
