@@ -115,6 +115,14 @@ struct fu_engine {
   int saved_training = 0;
   fu_counters cnt;
   cudaStream_t stream = nullptr;
+  // Second stream of the backward pass: weight gradients only produce dW, nothing downstream in the step reads them
+  // before the final unpack, so they run beside the dgrad -> BN-backward chain (HBM-bound, small shared memory) instead
+  // of in line with it.  Fork = event on the caller's stream, join = event before the unpack; inside a CUDA-graph
+  // capture this becomes a parallel branch of the graph.  FU_STREAMS=1 keeps everything on the caller's stream.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_used = false;
+  int use_side = 1;
   int num_sms = 148;
   // optional per-launch CUDA-event profiling (fu_profile_enable)
   struct DeferredSum { const double* src; float* dst; int n; };
@@ -193,6 +201,27 @@ struct fu_engine {
   } while (0)
 
 namespace {
+
+// launches issued while a SideScope is alive go to the engine's side stream, ordered after everything enqueued on the
+// caller's stream so far (no-op when profiling, or with FU_STREAMS=1)
+struct SideScope {
+  fu_engine* e; cudaStream_t saved; bool active;
+  explicit SideScope(fu_engine* e_) : e(e_), saved(e_->stream), active(e_->use_side && !e_->prof && e_->side != nullptr) {
+    if (active) {
+      cudaEventRecord(e->ev_fork, saved);
+      cudaStreamWaitEvent(e->side, e->ev_fork, 0);
+      e->stream = e->side;
+      e->side_used = true;
+    }
+  }
+  ~SideScope() { if (active) e->stream = saved; }
+};
+inline void side_join(fu_engine* e) {
+  if (!e->side_used) return;
+  cudaEventRecord(e->ev_join, e->side);
+  cudaStreamWaitEvent(e->stream, e->ev_join, 0);
+  e->side_used = false;
+}
 
 inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -386,6 +415,15 @@ int alloc_persistent(fu_engine* e) {
   CUDA_TRY(e, cudaMemset(e->wmem, 0, e->wmem_bytes));
   CUDA_TRY(e, cudaMalloc(&e->pack_tbl, fu_engine::kJobCap * sizeof(TcPackJob)));
   CUDA_TRY(e, cudaMalloc(&e->unpack_tbl, fu_engine::kJobCap * sizeof(TcUnpackJob)));
+  {
+    const char* s = getenv("FU_STREAMS");
+    e->use_side = (s && atoi(s) == 1) ? 0 : 1;
+    if (e->use_side) {
+      CUDA_TRY(e, cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+      CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    }
+  }
   CUDA_TRY(e, cudaMallocHost(&e->pack_pin, fu_engine::kJobCap * sizeof(TcPackJob)));
   CUDA_TRY(e, cudaMallocHost(&e->unpack_pin, fu_engine::kJobCap * sizeof(TcUnpackJob)));
   Bump w2, df2, db2, ws2;
@@ -994,7 +1032,10 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
   const long long P = (long long)B * H * W;
   int rc;
   if (blk.has_res) {
-    if ((rc = conv_wgrad<T>(e, blk.res, x_in, g, B, H, W, gptr(e, flat, blk.res.w_idx)))) return rc;
+    {
+      SideScope side(e);
+      if ((rc = conv_wgrad<T>(e, blk.res, x_in, g, B, H, W, gptr(e, flat, blk.res.w_idx)))) return rc;
+    }
     if (!bn && (rc = channel_sum_to<T>(e, g, P, blk.res.bsum, gptr(e, flat, blk.res.b_idx)))) return rc;
   }
   View d = g;
@@ -1023,7 +1064,10 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
     }
     e->deferred_sums.push_back({cw.bsum, gptr(e, flat, cw.b_idx), blk.C});
     View conv_in = (i == 0) ? x_in : (bn ? blk.z[i - 1] : blk.r[i - 1]);
-    if ((rc = conv_wgrad<T>(e, cw, conv_in, blk.dy[i], B, H, W, gptr(e, flat, cw.w_idx)))) return rc;
+    {
+      SideScope side(e);
+      if ((rc = conv_wgrad<T>(e, cw, conv_in, blk.dy[i], B, H, W, gptr(e, flat, cw.w_idx)))) return rc;
+    }
     if (i > 0) {
       if ((rc = conv_dgrad<T>(e, cw, blk.dy[i], blk.dz[i], B, H, W, 0))) return rc;
       d = blk.dz[i];
@@ -1139,7 +1183,11 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     else if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
     if (tc_up_eligible(up.tc, u.p, u.ld, d_up.p, d_up.ld)) {
       if (e->prof) e->prof_begin("tc_wgrad_kernel");
-      int trc = tc_up_wgrad(up.tc, u.p, u.ld, d_up.p, d_up.ld, B, h / 2, w / 2, gptr(e, flat, up.w_idx), e->stream, &e->cnt);
+      int trc;
+      {
+        SideScope side(e);
+        trc = tc_up_wgrad(up.tc, u.p, u.ld, d_up.p, d_up.ld, B, h / 2, w / 2, gptr(e, flat, up.w_idx), e->stream, &e->cnt);
+      }
       if (e->prof) { e->prof_end(); e->prof_begin("tc_conv_kernel"); }
       if (!trc) trc = tc_up_dgrad(up.tc, d_up.p, d_up.ld, d_u.p, d_u.ld, B, h / 2, w / 2, e->stream, &e->cnt);
       if (e->prof) e->prof_end();
@@ -1185,8 +1233,12 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
         else if ((rc = channel_sum_to<T>(e, pl.d_down[l], (long long)B * h * w, cw.bsum, gptr(e, flat, cw.b_idx)))) return rc;
         if (tc_down_eligible(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld)) {
           if (e->prof) e->prof_begin("tc_wgrad_kernel");
-          int trc = tc_down_wgrad(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld, B, 2 * h, 2 * w,
-                                  gptr(e, flat, cw.w_idx), e->stream, &e->cnt);
+          int trc;
+          {
+            SideScope side(e);
+            trc = tc_down_wgrad(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld, B, 2 * h, 2 * w,
+                                gptr(e, flat, cw.w_idx), e->stream, &e->cnt);
+          }
           if (e->prof) { e->prof_end(); e->prof_begin("tc_conv_kernel"); }
           if (!trc) trc = tc_down_dgrad(cw.tc, pl.d_down[l].p, pl.d_down[l].ld, d_src.p, d_src.ld, B, 2 * h, 2 * w, 1,
                                         e->stream, &e->cnt);
@@ -1207,6 +1259,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
       }
     }
   }
+  side_join(e);                  // every weight gradient has been accumulated before anything reads it
   if (!e->batch.unpack.empty()) {
     // every tensor-core weight gradient of this step: [taps][M][N] accumulators -> torch layout, one launch
     e->set_tag(0, 0, "wgrad_unpack");
@@ -1292,6 +1345,9 @@ void fu_engine_destroy(fu_engine* e) {
   if (e->wgrad_scr) cudaFree(e->wgrad_scr);
   if (e->pack_tbl) cudaFree(e->pack_tbl);
   if (e->unpack_tbl) cudaFree(e->unpack_tbl);
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->pack_pin) cudaFreeHost(e->pack_pin);
   if (e->unpack_pin) cudaFreeHost(e->unpack_pin);
   delete e;
@@ -1363,6 +1419,7 @@ int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* fl
   int rc;
   if (e->cfg.precision == FU_PRECISION_BF16) rc = backward_t<bf16>(e, d_seg, d_heat, flat_grads);
   else rc = backward_t<float>(e, d_seg, d_heat, flat_grads);
+  side_join(e);                  // (already joined on the normal path; an error return may have left work on the side stream)
   if (rc) return rc;
   e->cnt.backward_calls++;
   e->cnt.last_bwd_launches = e->cnt.kernel_launches - l0;

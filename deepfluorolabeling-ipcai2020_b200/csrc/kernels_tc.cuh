@@ -227,6 +227,8 @@ struct TcConvParams {
   int a5;                       // A operand gathered with stride 2: 5-D map (C,2,W,2,H), tap = (kh,kw)
   int c5;                       // output scattered (pixel shuffle): 5-D map (Cst,2,W,2,H), GEMM column = (a,b,co)
   int Cst;                      // channels of the scattered output tensor (N = 4*Cst)
+  int cst_shift;                // log2(Cst): channel counts are powers of two (unet.py:86: 2**(wf+i)), so the per-chunk
+                                // (a,b) block / channel split is a shift and a mask
 };
 
 constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (wgrad kernels; the conv kernel has 4*G epilogue warps)
@@ -411,11 +413,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // Scattered (pixel-shuffle) output: GEMM column = (a,b,co).  An N tile may span several (a,b) blocks (BN a
       // multiple of Cst: the A tile is then loaded once for all four sub-pixels), so the channel base and the
       // output pixel are functions of the 32-column chunk, not of the tile.
-      auto chunk_cb = [&](int col) { return p.c5 ? col % p.Cst : col; };     // channel base in bias / t / output
+      const long long pix_c5 = (long long)(h0 + hi) * 2 * (2 * p.W) + 2 * (w0 + wi);   // sub-pixel (0,0) of this row's pixel
+      auto chunk_cb = [&](int col) { return p.c5 ? (col & (p.Cst - 1)) : col; };     // channel base in bias / t / output
       auto chunk_pix = [&](int col) {
         if (!p.c5) return pix;
-        const int ab = col / p.Cst;
-        return ((long long)(h0 + hi) * 2 + (ab >> 1)) * (2 * p.W) + 2 * (w0 + wi) + (ab & 1);
+        const int ab = col >> p.cst_shift;
+        return pix_c5 + (long long)(ab >> 1) * (2 * p.W) + (ab & 1);
       };
       if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
       // the second epilogue operand (residual / accumulate) is fetched before waiting for the accumulator,
@@ -509,8 +512,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (et == 0) {
         for (int s = 0; s < p.BN / p.CS; ++s) {
           if (p.c5) {
-            const int col = nb + s * p.CS, ab = col / p.Cst;
-            ptx::tma_store_5d(&tmC, staging_addr + (uint32_t)s * sub_bytes, col - ab * p.Cst, ab & 1, w0, ab >> 1, h0);
+            const int col = nb + s * p.CS, ab = col >> p.cst_shift;
+            ptx::tma_store_5d(&tmC, staging_addr + (uint32_t)s * sub_bytes, col & (p.Cst - 1), ab & 1, w0, ab >> 1, h0);
           }
           else ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s * sub_bytes, nb + s * p.CS, w0, h0, n0);
         }
@@ -1843,6 +1846,10 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   p.B = 1; p.H = (int)Rg; p.W = Wg; p.Cin = K; p.N = N;
   p.ksz = gather ? 2 : 1; p.pad = 0;
   p.a5 = gather ? 1 : 0; p.c5 = gather ? 0 : 1; p.Cst = Cst;
+  if (!gather) {
+    if (Cst <= 0 || (Cst & (Cst - 1)) != 0) { tc_err() = "scatter layer: channel count must be a power of two"; return nullptr; }
+    for (p.cst_shift = 0; (1 << p.cst_shift) < Cst; ++p.cst_shift) {}
+  }
   p.KC = (K % 64 == 0) ? 64 : 32;
   int bn = tc_bn_max();
   if (gather) {
