@@ -106,8 +106,10 @@ struct fu_engine {
   static constexpr int kJobCap = 512;
   TcPackJob* pack_tbl = nullptr; TcUnpackJob* unpack_tbl = nullptr;
   TcPackJob* pack_pin = nullptr; TcUnpackJob* unpack_pin = nullptr;      // page-locked staging copies
-  std::vector<TcPackJob> pack_uploaded; std::vector<TcUnpackJob> unpack_uploaded;
+  std::vector<TcPackJob> pack_uploaded, pack_uploaded2; std::vector<TcUnpackJob> unpack_uploaded, unpack_uploaded2;
   TcBatch batch;
+  TcBatch batch_deep;            // pack jobs of the layers first used at level >= split_level(): packed on the side stream
+  int split_level() const { return cfg.depth / 2 > 1 ? cfg.depth / 2 : 1; }
   int64_t packed_version = -1;
   bool packed_once = false;
   Plan plan;
@@ -580,24 +582,41 @@ int pack_all(fu_engine* e, bool training) {
   int rc = FU_OK;
   const int last = e->cfg.depth - 1;
   int di = 0;
+  // Tensor-core layers only register their job; one launch packs a whole list.  Two lists: the layers the forward
+  // needs first (encoder levels below split_level(): a few hundred KB of weights) are packed in line, everything else
+  // (97 % of the bytes: deep encoder levels, the whole decoder, the heads) on the side stream while the shallow
+  // encoder levels run; forward_t joins before the first deep layer.
+  const int Ls = e->split_level();
   e->batch.pack.clear();
-  tc_batch() = &e->batch;        // tensor-core layers only register their job; one launch packs them all
-  for (auto& c : e->downc) { if (di++ != last && rc == FU_OK) rc = pack_conv(e, c); }
+  e->batch_deep.pack.clear();
+  auto sink = [&](bool deep) { tc_batch() = deep ? &e->batch_deep : &e->batch; };
+  for (auto& c : e->downc) { const int i = di++; sink(i >= Ls); if (i != last && rc == FU_OK) rc = pack_conv(e, c); }
   auto blk = [&](Block& b) {
     if (b.has_res && rc == FU_OK) rc = pack_conv(e, b.res);
     for (auto& c : b.convs) if (rc == FU_OK) rc = pack_conv(e, c);
   };
-  for (auto& b : e->enc) blk(b);
+  for (int l = 0; l < (int)e->enc.size(); ++l) { sink(l >= Ls); blk(e->enc[l]); }
+  sink(true);
   for (auto& c : e->upc) if (rc == FU_OK) rc = pack_conv(e, c);
   for (auto& b : e->dec) blk(b);
   if (rc == FU_OK) rc = pack_conv(e, e->seg);
   for (auto& c : e->lands) if (rc == FU_OK) rc = pack_conv(e, c);
   tc_batch() = nullptr;
   (void)training;
-  if (rc == FU_OK && !e->batch.pack.empty()) {
-    e->set_tag(0, 0, "weight_pack");
+  if (rc != FU_OK) return rc;
+  e->set_tag(0, 0, "weight_pack");
+  if (!e->batch_deep.pack.empty()) {
+    SideScope side(e);
     if (e->prof) e->prof_begin("tc_pack_batched_kernel");
-    const int trc = tc_flush_jobs(e->batch.pack, e->pack_uploaded, e->pack_tbl, fu_engine::kJobCap,
+    const int trc = tc_flush_jobs(e->batch_deep.pack, e->pack_uploaded2, e->pack_tbl + fu_engine::kJobCap / 2,
+                                  fu_engine::kJobCap / 2, tc_pack_launcher(e->stream), e->stream, &e->cnt,
+                                  e->pack_pin + fu_engine::kJobCap / 2);
+    if (e->prof) e->prof_end();
+    if (trc) return e->fail(FU_ERR_CUDA, "batched weight pack failed");
+  }
+  if (!e->batch.pack.empty()) {
+    if (e->prof) e->prof_begin("tc_pack_batched_kernel");
+    const int trc = tc_flush_jobs(e->batch.pack, e->pack_uploaded, e->pack_tbl, fu_engine::kJobCap / 2,
                                   tc_pack_launcher(e->stream), e->stream, &e->cnt, e->pack_pin);
     if (e->prof) e->prof_end();
     if (trc) return e->fail(FU_ERR_CUDA, "batched weight pack failed");
@@ -828,6 +847,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
   for (int l = 0; l < D; ++l) {
     const int h = H >> l, w = W >> l;
     View outv = (D == 1) ? pl.decout[0] : (l < D - 1 ? slice(pl.cat[l], e->chans[l], e->chans[l], esz) : pl.bott);
+    if (l == e->split_level()) side_join(e);        // the deep layers' weight packs (side stream) are needed from here on
     if ((rc = block_forward<T>(e, e->enc[l], cur, outv, B, h, w, training))) return rc;
     if (l < D - 1) {
       View dn = pl.down[l + 1];
@@ -857,6 +877,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
       cur = outv;
     }
   }
+  side_join(e);                                     // (no-op unless the network is shallower than the split level)
   for (int j = 0; j < D - 1; ++j) {
     const int l = D - 2 - j;
     const int h = H >> l, w = W >> l;
@@ -928,6 +949,21 @@ template <typename T>
 int channel_sum_to(fu_engine* e, const View& d, long long P, double* scratch, float* dst) {
   LAUNCH(e, (channel_sum_kernel<T>), red_grid(e, P, d.C), 256, reinterpret_cast<const T*>(d.p), d.ld, P, d.C, scratch);
   e->deferred_sums.push_back({scratch, dst, d.C});     // converted to fp32 by one launch at the end of backward
+  return FU_OK;
+}
+
+// [taps][M][N] accumulators of the tensor-core weight gradients registered so far -> torch layout, one launch.
+// part 0 = the mid-backward flush (device table half 0), part 1 = the final one.
+int flush_unpack(fu_engine* e, float* flat, int part) {
+  if (e->batch.unpack.empty()) return FU_OK;
+  const int half = fu_engine::kJobCap / 2;
+  e->set_tag(0, 0, "wgrad_unpack");
+  if (e->prof) e->prof_begin("tc_unpack_batched_kernel");
+  const int trc = tc_flush_jobs(e->batch.unpack, part ? e->unpack_uploaded2 : e->unpack_uploaded, e->unpack_tbl + part * half,
+                                half, tc_unpack_launcher(e->stream, flat), e->stream, &e->cnt, e->unpack_pin + part * half);
+  if (e->prof) e->prof_end();
+  e->batch.unpack.clear();
+  if (trc) return e->fail(FU_ERR_CUDA, "batched weight-gradient unpack failed");
   return FU_OK;
 }
 
@@ -1215,6 +1251,12 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     const int h = H >> l, w = W >> l;
     View gl = (D == 1) ? g : (l == D - 1 ? g : slice(pl.d_cat[l], e->chans[l], e->chans[l], esz));
     View x_in = (l == 0) ? pl.xin : pl.down[l];
+    if (l == e->split_level() - 1) {
+      // every layer at the deep levels (and the whole decoder) has its weight gradient on the side stream by now: 97 %
+      // of the parameters.  Their unpack goes out behind them on that stream, beside the shallow encoder levels.
+      SideScope side(e);
+      if ((rc = flush_unpack(e, flat, 0))) return rc;
+    }
     bool in_sums = false;
     if ((rc = block_backward<T>(e, e->enc[l], x_in, gl, l == 0 ? nullptr : &pl.d_down[l], B, h, w, training, flat,
                                 (l > 0 && !c.max_pool) ? &in_sums : nullptr)))
@@ -1260,15 +1302,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     }
   }
   side_join(e);                  // every weight gradient has been accumulated before anything reads it
-  if (!e->batch.unpack.empty()) {
-    // every tensor-core weight gradient of this step: [taps][M][N] accumulators -> torch layout, one launch
-    e->set_tag(0, 0, "wgrad_unpack");
-    if (e->prof) e->prof_begin("tc_unpack_batched_kernel");
-    const int trc = tc_flush_jobs(e->batch.unpack, e->unpack_uploaded, e->unpack_tbl, fu_engine::kJobCap,
-                                  tc_unpack_launcher(e->stream, flat), e->stream, &e->cnt, e->unpack_pin);
-    if (e->prof) e->prof_end();
-    if (trc) return e->fail(FU_ERR_CUDA, "batched weight-gradient unpack failed");
-  }
+  if ((rc = flush_unpack(e, flat, 1))) return rc;     // the shallow layers' gradients (the deep ones went out mid-way)
   return flush_deferred_sums(e);
 }
 
@@ -1393,13 +1427,14 @@ int fu_forward(fu_engine* e, const float* x, int B, int H, int W, int training, 
   int rc = ensure_plan(e, B, H, W);
   if (rc) return rc;
   if (!e->packed_once || e->packed_version != weights_version) {
-    if ((rc = pack_all(e, training != 0))) return rc;
+    if ((rc = pack_all(e, training != 0))) { side_join(e); return rc; }
     e->packed_once = true;
     e->packed_version = weights_version;
   }
   e->saved = false;
   if (e->cfg.precision == FU_PRECISION_BF16) rc = forward_t<bf16>(e, x, B, H, W, training, seg, logits, heat);
   else rc = forward_t<float>(e, x, B, H, W, training, seg, logits, heat);
+  side_join(e);
   if (rc) return rc;
   e->saved = save != 0;
   e->saved_training = training;
