@@ -1968,7 +1968,9 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   const size_t wbytes = (size_t)(9 + p.res) * K * p.BN * 2;
   // two epilogue sets for the thin layers when everything (resident weights, >= 2 A stages) still fits
   // (measured: 32-column layers 75 -> 70 us, 32->64 dgrad @192 95 -> 77 us; 64->64 @96 35.5 -> 37 us: no gain at K >= 576)
-  c.S = (p.BN <= 64 && (long long)K * p.BN <= 64 * 32 && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
+  // The forward launches (dir 0) also compute the BN statistics in their epilogue, which roughly doubles its cost
+  // (64->64 @96x96: 35 us without, 56 us with statistics): there two sets pay at every thin shape that fits.
+  c.S = (p.BN <= 64 && (dir == 0 || (long long)K * p.BN <= 64 * 32) && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
   for (;; c.S = 1) {
     const size_t staging = (size_t)c.S * p.npair * 128 * p.BN * 2;
     const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * 8 * p.BN + 16 + 8 * 48;
