@@ -28,7 +28,9 @@ with open(out_csv, "w") as f:
     f.write("id,kernel,grid,block,time_us,dram_read_bytes,dram_write_bytes\n")
     for i, L in launch.items():
         f.write(f"{i},{short(L['kernel'])},\"{L['grid']}\",\"{L['block']}\",{L.get('us', 0):.2f},{int(L.get('rd', 0))},{int(L.get('wr', 0))}\n")
-steps = sum(1 for L in launch.values() if "tc_unpack_batched" in L["kernel"]) or 1
+# training steps in the capture = launches of a kernel that runs exactly once per step
+steps = (sum(1 for L in launch.values() if "nchw_to_nhwc_kernel" in L["kernel"]) or
+         sum(1 for L in launch.values() if "heads_bwd_fused_kernel" in L["kernel"]) or 1)
 agg = collections.OrderedDict()
 for L in launch.values():
     a = agg.setdefault(short(L["kernel"]), {"launches": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
