@@ -730,7 +730,7 @@ float* gptr(fu_engine* e, float* flat, int idx) {
 // ---------------------------------------------------------------------------
 template <typename T>
 int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, int H, int W, int relu,
-                 double* stat, const View* t, const float* bn_a, const float* bn_b) {
+                 double* stat, const View* t, const float* bn_a, const float* bn_b, const TcBnFin* fin = nullptr) {
   // 3x3/pad1 or 1x1 convolution, stride 1
   {
     const double M = (double)B * H * W;
@@ -740,7 +740,7 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
   if (tc_conv_eligible(cw.tc, x.p, x.ld, y.p, y.ld, t ? t->p : nullptr, t ? t->ld : 0)) {
     if (e->prof) e->prof_begin("tc_conv_kernel");
     int rc = tc_conv_forward(cw.tc, x.p, x.ld, y.p, y.ld, B, H, W, tdata(e, cw.b_idx), relu, stat,
-                             t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt);
+                             t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt, fin);
     if (e->prof) e->prof_end();
     if (rc) return e->fail(FU_ERR_CUDA, "tensor-core conv launch failed: %s", tc_last_error());
     return FU_OK;
@@ -791,6 +791,9 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
   const long long P = (long long)B * H * W;
   View cur = x_in;
   int rc;
+  TcBnFin res_fin;
+  memset(&res_fin, 0, sizeof(res_fin));
+  bool use_res_fin = false;
   for (int i = 0; i < nd; ++i) {
     View r = blk.r[i];   // (aliases `out` when the block ends in a bare ReLU, see carve_plan)
     double* stat = (bn && training) ? blk.bns[i].stat : nullptr;
@@ -810,10 +813,20 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
                reinterpret_cast<T*>(z.p), z.ld, f, P, b.C);
         cur = z;
       } else {
-        // the last BN of a residual block is applied inside the residual conv's epilogue
-        LAUNCH(e, bn_finalize_kernel, (b.C + 127) / 128, 128, b.stat, P, b.C, training, tdata(e, b.i_gamma),
-               tdata(e, b.i_beta), tdata(e, b.i_rm), tdata(e, b.i_rv),
-               reinterpret_cast<long long*>(e->tensors[b.i_nbt].data), 0.1f, 1e-5f, b.mean, b.invstd, b.a, b.b);
+        // the last BN of a residual block is applied inside the residual conv's epilogue; on the tensor-core path it
+        // is also finalised there (res_fin), otherwise by a one-block kernel
+        if (tc_conv_eligible(blk.res.tc, x_in.p, x_in.ld, out.p, out.ld, r.p, r.ld)) {
+          res_fin.stat = b.stat; res_fin.P = P; res_fin.training = training;
+          res_fin.gamma = tdata(e, b.i_gamma); res_fin.beta = tdata(e, b.i_beta);
+          res_fin.rmean = tdata(e, b.i_rm); res_fin.rvar = tdata(e, b.i_rv);
+          res_fin.nbt = reinterpret_cast<long long*>(e->tensors[b.i_nbt].data);
+          res_fin.momentum = 0.1f; res_fin.eps = 1e-5f; res_fin.mean_o = b.mean; res_fin.invstd_o = b.invstd;
+          use_res_fin = true;
+        } else {
+          LAUNCH(e, bn_finalize_kernel, (b.C + 127) / 128, 128, b.stat, P, b.C, training, tdata(e, b.i_gamma),
+                 tdata(e, b.i_beta), tdata(e, b.i_rm), tdata(e, b.i_rv),
+                 reinterpret_cast<long long*>(e->tensors[b.i_nbt].data), 0.1f, 1e-5f, b.mean, b.invstd, b.a, b.b);
+        }
         cur = r;
       }
     } else {
@@ -825,7 +838,7 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
     const View& t = blk.r[nd - 1];
     const float* a = bn ? blk.bns[nd - 1].a : e->ones;
     const float* b = bn ? blk.bns[nd - 1].b : e->zeros;
-    if ((rc = conv_forward<T>(e, blk.res, x_in, out, B, H, W, 0, nullptr, &t, a, b))) return rc;
+    if ((rc = conv_forward<T>(e, blk.res, x_in, out, B, H, W, 0, nullptr, &t, a, b, use_res_fin ? &res_fin : nullptr))) return rc;
   }
   return FU_OK;
 }

@@ -208,6 +208,19 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(uint32_t n, uint32_t m = 
 // ===========================================================================
 // the convolution kernel (forward and data gradient; 3x3/pad 1 and 1x1)
 // ===========================================================================
+// BatchNorm finalisation folded into the prologue of the kernel that applies it (the residual 1x1 conv, whose epilogue
+// computes BN2(r2) + conv1x1(x)): every CTA turns the fp64 batch sums into the folded scale / shift it needs, CTA 0
+// also stores mean / invstd for the backward pass and updates the running statistics (nn.BatchNorm2d, unet.py:222).
+struct TcBnFin {
+  const double* stat;           // [2C] sum, sum of squares (null: not used, bn_a / bn_b are given)
+  long long P;
+  int training;
+  const float* gamma; const float* beta;
+  float* rmean; float* rvar; long long* nbt;
+  float momentum, eps;
+  float* mean_o; float* invstd_o;
+};
+
 struct TcConvParams {
   int B, H, W;
   int Cin, N;
@@ -226,6 +239,7 @@ struct TcConvParams {
   int nstaging;                 // staging tiles for the TMA store (2 = double buffered)
   int a5;                       // A operand gathered with stride 2: 5-D map (C,2,W,2,H), tap = (kh,kw)
   int c5;                       // output scattered (pixel shuffle): 5-D map (Cst,2,W,2,H), GEMM column = (a,b,co)
+  TcBnFin fin;                  // fin.stat != null: bn_a / bn_b are computed here instead of being read
   int Cst;                      // channels of the scattered output tensor (N = 4*Cst)
   int cst_shift;                // log2(Cst): channel counts are powers of two (unet.py:86: 2**(wf+i)), so the per-chunk
                                 // (a,b) block / channel split is a shift and a mask
@@ -283,10 +297,40 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   {
     // per-channel epilogue vectors in shared memory (no global load in the epilogue's dependency chain)
     float* vec = reinterpret_cast<float*>(smem + vec_off);
-    for (int i = threadIdx.x; i < vlen; i += blockDim.x) {
-      vec[i] = p.bias ? p.bias[i] : 0.f;
-      vec[vlen + i] = p.bn_a ? p.bn_a[i] : 1.f;
-      vec[2 * vlen + i] = p.bn_a ? p.bn_b[i] : 0.f;
+    if (p.fin.stat) {
+      const TcBnFin& f = p.fin;
+      if (blockIdx.x == 0 && threadIdx.x == 0 && f.training && f.nbt) *f.nbt += 1;
+      for (int i = threadIdx.x; i < vlen; i += blockDim.x) {
+        float mean, var;
+        double unb = 0.0;
+        if (f.training) {
+          const double m = f.stat[i] / (double)f.P;
+          double v = f.stat[vlen + i] / (double)f.P - m * m;
+          if (v < 0.0) v = 0.0;
+          mean = (float)m; var = (float)v;
+          unb = f.P > 1 ? v * ((double)f.P / (double)(f.P - 1)) : v;
+        } else {
+          mean = f.rmean[i]; var = f.rvar[i];
+        }
+        const float invstd = rsqrtf(var + f.eps);
+        const float a = f.gamma[i] * invstd;
+        vec[i] = p.bias ? p.bias[i] : 0.f;
+        vec[vlen + i] = a;
+        vec[2 * vlen + i] = f.beta[i] - mean * a;
+        if (blockIdx.x == 0) {
+          f.mean_o[i] = mean; f.invstd_o[i] = invstd;
+          if (f.training) {      // (train mode never reads the running statistics, eval mode never writes them)
+            f.rmean[i] = (1.f - f.momentum) * f.rmean[i] + f.momentum * mean;
+            f.rvar[i] = (1.f - f.momentum) * f.rvar[i] + f.momentum * (float)unb;
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < vlen; i += blockDim.x) {
+        vec[i] = p.bias ? p.bias[i] : 0.f;
+        vec[vlen + i] = p.bn_a ? p.bn_a[i] : 1.f;
+        vec[2 * vlen + i] = p.bn_a ? p.bn_b[i] : 0.f;
+      }
     }
   }
   ptx::tc_fence_before();
@@ -2094,9 +2138,12 @@ inline bool tc_conv_eligible(const TcConv& t, const void* x, int x_ld, const voi
   return t.enabled && tc_ptr_ok(x, x_ld) && tc_ptr_ok(y, y_ld) && (!tp || tc_ptr_ok(tp, t_ld));
 }
 
+// fin (optional, 1x1 / first-generation kernel only): finalise the BatchNorm whose folded scale / shift the epilogue applies
+// to `tp` inside this launch (see TcBnFin) instead of reading bn_a / bn_b
 inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, const float* bias,
                            int relu, double* stat, const void* tp, int t_ld, const float* bn_a, const float* bn_b,
-                           int accumulate, cudaStream_t stream, fu_counters* cnt) {
+                           int accumulate, cudaStream_t stream, fu_counters* cnt, const TcBnFin* fin = nullptr) {
+  if (fin && tc_use_v2(t, H, W)) { tc_err() = "BN finalisation can only ride on the 1x1 kernel"; return -1; }
   if (tc_use_v2(t, H, W)) {
     TcConv::Cached3* c3 = tc_prepare3(t, 0, x, x_ld, y, y_ld, B, H, W);
     if (c3) {
@@ -2111,6 +2158,7 @@ inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld
   c->p.bias = bias; c->p.relu = relu; c->p.stat = stat;
   c->p.t = reinterpret_cast<const bf16*>(tp); c->p.t_ld = t_ld; c->p.bn_a = bn_a; c->p.bn_b = bn_b;
   if (accumulate) { c->p.t = reinterpret_cast<const bf16*>(y); c->p.t_ld = y_ld; c->p.bn_a = nullptr; c->p.bn_b = nullptr; }
+  if (fin) c->p.fin = *fin; else memset(&c->p.fin, 0, sizeof(c->p.fin));
   return tc_launch(c, stream, cnt);
 }
 
