@@ -17,6 +17,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_loss.cuh"
+#include "kernels_io.cuh"
 
 using namespace fu;
 
@@ -1631,4 +1632,5 @@ const char* fu_build_info(void) {
 
 }  // extern "C"
 
+#include "io_api.inl"
 #include "test_hooks.inl"

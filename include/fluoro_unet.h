@@ -177,6 +177,47 @@ int fu_loss_forward(const fu_loss_desc* d, double* sums, float* loss_out, void* 
 int fu_loss_backward(const fu_loss_desc* d, const double* sums, const float* dloss, int H, int W,
                      int r0, int c0, float* d_seg, float* d_heat, void* stream);
 
+/* ---- callers either side of the path ---------------------------------------
+ * Sample preparation before the network and inference post-processing after it, as device kernels
+ * on the tensors the reference's host code holds (fp32 NCHW, u1 labels).  Stateless (no engine
+ * handle); errors through fu_last_error(NULL); everything is enqueued on `stream`, no host sync. */
+
+/* dataset.py:287-293 (RandomDataAugDataSet.__getitem__): reflect-pad every tile by `pad` pixels per
+ * side (numpy.pad mode 'reflect'; calc_pad_amount, dataset.py:26-40, gives pad) and, when `normalize`,
+ * z-score it with the mean and UNBIASED standard deviation of the padded tile.
+ *   tiles (B,h,w) fp32 -> out (B,1,h+2*pad,w+2*pad) fp32;  sums: 2*B doubles of workspace. */
+int fu_prep_tiles(const float* tiles, int B, int h, int w, int pad, int normalize, double* sums, float* out,
+                  void* stream);
+
+/* dataset.py:295-325: Gaussian heat-map targets exp(-((X-x)^2+(Y-y)^2)/(2 sigma^2)) / (2 pi sigma^2)
+ * (sigma 2.5 in the reference), a zero plane for a landmark whose x or y is +-inf (outside the view,
+ * dataset.py:316).   lands (B,2,num_lands) fp32, row 0 = column (x), row 1 = row (y) -> out (B,num_lands,H,W). */
+int fu_heatmap_targets(const float* lands, int B, int num_lands, int H, int W, float sigma, float* out, void* stream);
+
+/* util.py:293-377 (seg_dataset_ensemble), the arithmetic between the networks' forward calls and the
+ * HDF5 write: centre-crop window (r0,c0,h,w) of every network's outputs (util.py:339,347), class
+ * probabilities summed in list order and divided by n_nets, arg-max over classes (first maximum wins)
+ * -> labels u1 (B,h,w); heat-maps min-max normalised per (network, image) (util.py:348-351), summed
+ * and divided by n_nets -> avg_heat (B,num_lands,h,w).
+ *   seg / heat: HOST arrays of n_nets (<= 16) DEVICE pointers to (B,n_classes,H,W) / (B,num_lands,H,W);
+ *   heat, avg_heat, workspace NULL iff num_lands == 0; workspace: fu_ensemble_workspace_words() uint32. */
+int64_t fu_ensemble_workspace_words(int n_nets, int B);
+int fu_ensemble_combine(const float* const* seg, const float* const* heat, int n_nets, int B, int n_classes,
+                        int num_lands, int H, int W, int r0, int c0, int h, int w, uint32_t* workspace,
+                        uint8_t* labels, float* avg_heat, void* stream);
+
+/* est_lands_csv.py:87-134 (rule_3): per (projection, landmark) the arg-max pixel of the heat-map,
+ * restricted to pixels whose label in `segs` equals seg_labels[landmark] when segs != NULL and the
+ * label is >= 0 (est_lands_csv.py:54-71 holds the label table); kept only if the NCC (ncc.py:12-38) of
+ * the tmpl_dim x tmpl_dim Gaussian template (util.py:36-48; 25 and sigma 2.5 in the reference) with the
+ * window of the reflect-padded heat-map centred there is >= min_ncc (0.9).
+ *   heats (P,num_lands,h,w) fp32 device; segs (P,h,w) u1 device or NULL; seg_labels HOST array of
+ *   num_lands (<= 64) ints or NULL;  out_rc (P,num_lands,2) int32 row,col, (-1,-1) = not found
+ *   (est_lands_csv.py:126-128);  out_ncc optional (P,num_lands) scores. */
+int fu_extract_landmarks(const float* heats, const uint8_t* segs, const int32_t* seg_labels, int P, int num_lands,
+                         int h, int w, int tmpl_dim, float sigma, float min_ncc, int32_t* out_rc, float* out_ncc,
+                         void* stream);
+
 /* Build information: "sm_100a;tcgen05=1;..." */
 const char* fu_build_info(void);
 
