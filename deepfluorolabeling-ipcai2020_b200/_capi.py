@@ -43,7 +43,9 @@ class FuLossDesc(C.Structure):
 EXPORTS = ["fu_engine_create", "fu_engine_destroy", "fu_last_error", "fu_num_tensors",
            "fu_tensor_get_info", "fu_grad_numel", "fu_bind_tensors", "fu_forward", "fu_backward",
            "fu_get_counters", "fu_build_info", "fu_test_conv", "fu_profile_enable", "fu_profile_report", "fu_debug_copy",
-           "fu_loss_workspace_doubles", "fu_loss_forward", "fu_loss_backward"]
+           "fu_loss_workspace_doubles", "fu_loss_forward", "fu_loss_backward",
+           "fu_prep_tiles", "fu_heatmap_targets", "fu_ensemble_workspace_words", "fu_ensemble_combine",
+           "fu_extract_landmarks"]
 
 _lib = None
 
@@ -95,6 +97,17 @@ def lib():
     L.fu_loss_forward.restype = i32
     L.fu_loss_backward.argtypes = [C.POINTER(FuLossDesc), vp, vp, i32, i32, i32, i32, vp, vp, vp]
     L.fu_loss_backward.restype = i32
+    f32 = C.c_float
+    L.fu_prep_tiles.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.fu_prep_tiles.restype = i32
+    L.fu_heatmap_targets.argtypes = [vp, i32, i32, i32, i32, f32, vp, vp]
+    L.fu_heatmap_targets.restype = i32
+    L.fu_ensemble_workspace_words.argtypes = [i32, i32]
+    L.fu_ensemble_workspace_words.restype = i64
+    L.fu_ensemble_combine.argtypes = [C.POINTER(vp), C.POINTER(vp)] + [i32] * 10 + [vp, vp, vp, vp]
+    L.fu_ensemble_combine.restype = i32
+    L.fu_extract_landmarks.argtypes = [vp, vp, C.POINTER(C.c_int32), i32, i32, i32, i32, i32, f32, f32, vp, vp, vp]
+    L.fu_extract_landmarks.restype = i32
     _lib = L
     return L
 

@@ -128,3 +128,32 @@ def test_fused_loss_descriptor_matches_header(pkg):
     """ctypes mirror of fu_loss_desc: 4 x (pointer + 3 int64 strides) + 6 int32 + 2 float, no hidden padding."""
     import ctypes as C
     assert C.sizeof(pkg._capi.FuLossDesc) == 4 * (8 + 24) + 6 * 4 + 2 * 4
+
+
+def test_prepost_helpers_refuse_cpu_tensors_and_validate_arguments(pkg):
+    """prepost.py has no CPU path; the C ABI rejects bad shapes before touching the device."""
+    import ctypes as C
+    pp = pkg.prepost
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pp.prep_tiles(torch.zeros(2, 8, 8), pad_img_dim=12)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pp.heatmap_targets(torch.zeros(2, 2, 3), (8, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pp.ensemble_combine([torch.zeros(1, 2, 8, 8)], None, (8, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pp.extract_landmarks(torch.zeros(1, 2, 30, 30))
+    assert pp.calc_pad_amount(192, 180) == 6 and pp.calc_pad_amount(32, 21) == 6       # dataset.py:26-40
+    assert pp.SEG_LABELS_FOR_LANDS["FH-l"] == 5 and pp.SEG_LABELS_FOR_LANDS["ASIS-r"] == 2 and len(pp.SEG_LABELS_FOR_LANDS) == 18
+    L = pkg._capi.lib()
+    one = C.c_void_p(8)   # any non-null address: validation fails before it is used
+    assert L.fu_prep_tiles(one, 1, 8, 8, 8, 0, None, one, None) == -2 and "pad < tile" in pkg._capi.last_error(None)
+    assert L.fu_prep_tiles(one, 1, 8, 8, 2, 1, None, one, None) == -6                   # normalise without workspace
+    assert L.fu_heatmap_targets(one, 1, 14, 8, 8, 0.0, one, None) == -6                 # sigma must be positive
+    assert L.fu_ensemble_workspace_words(3, 32) == 192
+    ptrs = (C.c_void_p * 17)(*([8] * 17))
+    assert L.fu_ensemble_combine(ptrs, None, 17, 1, 7, 0, 8, 8, 0, 0, 8, 8, None, one, None, None) == -6
+    assert "at most 16" in pkg._capi.last_error(None)
+    assert L.fu_ensemble_combine(ptrs, None, 2, 1, 7, 0, 8, 8, 1, 0, 8, 8, None, one, None, None) == -6   # window outside
+    assert L.fu_extract_landmarks(one, None, None, 1, 14, 30, 30, 24, 2.5, 0.9, one, None, None) == -6    # even template
+    assert L.fu_extract_landmarks(one, None, None, 1, 14, 12, 30, 25, 2.5, 0.9, one, None, None) == -2    # 12 >= h
+    assert L.fu_extract_landmarks(one, None, None, 1, 65, 30, 30, 25, 2.5, 0.9, one, None, None) == -6    # > 64 landmarks
