@@ -2,6 +2,19 @@
 // side of the path"; kernels in kernels_io.cuh).  Stateless: no engine handle; errors go to fu_last_error(NULL).
 namespace {
 
+void launch_ens_combine(const EnsArgs& a, dim3 grid, cudaStream_t st) {
+  switch (a.n_nets) {
+    case 1: ens_combine_kernel<1><<<grid, 256, 0, st>>>(a); break;
+    case 2: ens_combine_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: ens_combine_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    case 4: ens_combine_kernel<4><<<grid, 256, 0, st>>>(a); break;
+    case 5: ens_combine_kernel<5><<<grid, 256, 0, st>>>(a); break;
+    case 6: ens_combine_kernel<6><<<grid, 256, 0, st>>>(a); break;
+    case 8: ens_combine_kernel<8><<<grid, 256, 0, st>>>(a); break;
+    default: ens_combine_kernel<0><<<grid, 256, 0, st>>>(a); break;
+  }
+}
+
 int io_fail(int rc, const std::string& msg) { g_create_error = msg; return rc; }
 
 int io_launch_check(const char* who) {
@@ -31,16 +44,20 @@ int fu_prep_tiles(const float* tiles, int B, int h, int w, int pad, int normaliz
   a.src = tiles; a.out = out; a.sums = sums; a.B = B; a.h = h; a.w = w; a.pad = pad;
   a.Hp = h + 2 * pad; a.Wp = w + 2 * pad; a.normalize = normalize ? 1 : 0;
   const long long n = (long long)a.Hp * a.Wp;
-  if (n < 2 || n > 0x7fffffffLL) return io_fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_prep_tiles: tile size");
+  if (n < 2 || n > 0x7ff00000LL) return io_fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_prep_tiles: tile size");
   if (B > 65535) return io_fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_prep_tiles: at most 65535 tiles per call");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a.normalize) {
     if (cudaMemsetAsync(sums, 0, (size_t)B * 2 * sizeof(double), st) != cudaSuccess)
       return io_fail(FU_ERR_CUDA, "fu_prep_tiles: memset failed");
-    const unsigned gx = (unsigned)std::min<long long>((n + 256 * 8 - 1) / (256 * 8), 128);
+    // enough blocks to fill the machine (~16 per SM over all tiles), each with at least 8 pixels per thread
+    const long long want = std::max<long long>(1, (16LL * 148 + B - 1) / B);
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(std::min<long long>((n + 256 * 8 - 1) / (256 * 8), want), 128));
     prep_stats_kernel<<<dim3(gx, (unsigned)B), 256, 0, st>>>(a);
   }
-  prep_apply_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)B), 256, 0, st>>>(a);
+  a.vec = ((a.Wp & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+  const long long groups = (long long)a.Hp * ((a.Wp + 3) / 4);
+  prep_apply_kernel<<<dim3((unsigned)((groups + 255) / 256), (unsigned)B), 256, 0, st>>>(a);
   return io_launch_check("fu_prep_tiles");
 }
 
@@ -52,9 +69,16 @@ int fu_heatmap_targets(const float* lands, int B, int num_lands, int H, int W, f
   HeatArgs a;
   a.lands = lands; a.out = out; a.B = B; a.L = num_lands; a.H = H; a.W = W;
   gauss_consts(sigma, &a.neg2ss, &a.norm);
+  a.far_r2 = -a.neg2ss * 105.0f;
+  a.R = (int)ceilf(sqrtf(a.far_r2)) + 1;
   const long long n = (long long)H * W;
-  heatmap_targets_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)(B * num_lands)), 256, 0,
-                           reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(out, 0, (size_t)B * num_lands * n * sizeof(float), st) != cudaSuccess)
+    return io_fail(FU_ERR_CUDA, "fu_heatmap_targets: memset failed");
+  const long long box = (long long)(2 * a.R + 2) * (2 * a.R + 2);
+  // a few fat blocks per plane: the per-block prologue (landmark load, box origin) is amortised over ~6 pixels a thread
+  const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((std::min(box, n) + 256 * 6 - 1) / (256 * 6), 64));
+  heatmap_targets_kernel<<<dim3(gx, (unsigned)(B * num_lands)), 256, 0, st>>>(a);
   return io_launch_check("fu_heatmap_targets");
 }
 
@@ -70,7 +94,6 @@ int fu_ensemble_combine(const float* const* seg, const float* const* heat, int n
   if (r0 < 0 || c0 < 0 || r0 + h > H || c0 + w > W) return io_fail(FU_ERR_ARG, "fu_ensemble_combine: window outside the output");
   if ((num_lands > 0) != (heat != nullptr) || (num_lands > 0) != (avg_heat != nullptr) || (num_lands > 0 && !workspace))
     return io_fail(FU_ERR_ARG, "fu_ensemble_combine: heat / avg_heat / workspace / num_lands disagree");
-  if ((long long)n_nets * B > 65535) return io_fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_ensemble_combine: n_nets*B <= 65535");
   EnsArgs a;
   memset(&a, 0, sizeof(a));
   for (int n = 0; n < n_nets; ++n) {
@@ -82,16 +105,29 @@ int fu_ensemble_combine(const float* const* seg, const float* const* heat, int n
   a.r0 = r0; a.c0 = c0; a.h = h; a.w = w; a.labels = labels; a.avg_heat = avg_heat;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long hw = (long long)h * w;
-  if (num_lands > 0) {
-    const int nb = n_nets * B;
-    a.mn = workspace; a.mx = workspace + nb;
-    if (cudaMemsetAsync(a.mn, 0xff, (size_t)nb * 4, st) != cudaSuccess || cudaMemsetAsync(a.mx, 0, (size_t)nb * 4, st) != cudaSuccess)
-      return io_fail(FU_ERR_CUDA, "fu_ensemble_combine: memset failed");
-    const long long tot = hw * num_lands;
-    const unsigned gx = (unsigned)std::min<long long>((tot + 256 * 8 - 1) / (256 * 8), 128);
-    ens_minmax_kernel<<<dim3(gx, (unsigned)nb), 256, 0, st>>>(a);
+  const unsigned gx_c = (unsigned)((hw + 256 * kEnsPix - 1) / (256 * kEnsPix));
+  if (num_lands == 0) {
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+      a.b0 = b0; a.nb = std::min(B - b0, 65535);
+      launch_ens_combine(a, dim3(gx_c, (unsigned)a.nb, 1), st);
+    }
+    return io_launch_check("fu_ensemble_combine");
   }
-  ens_combine_kernel<<<dim3((unsigned)((hw + 255) / 256), (unsigned)B), 256, 0, st>>>(a);
+  const int nbt = n_nets * B;
+  a.mn = workspace; a.mx = workspace + nbt;
+  if (cudaMemsetAsync(a.mn, 0xff, (size_t)nbt * 4, st) != cudaSuccess || cudaMemsetAsync(a.mx, 0, (size_t)nbt * 4, st) != cudaSuccess)
+    return io_fail(FU_ERR_CUDA, "fu_ensemble_combine: memset failed");
+  // images per chunk: all networks' heat-maps of a chunk stay within ~48 MB so the second pass hits L2
+  const long long per_img = (long long)n_nets * num_lands * H * W * 4;
+  const int chunk = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(B, 65535 / n_nets),
+                                                                    (48LL << 20) / std::max<long long>(per_img, 1)));
+  const long long row_groups = ((long long)num_lands * h + 7) / 8;   // a block pass covers 8 rows
+  const unsigned gx_m = (unsigned)std::max<long long>(1, std::min<long long>((row_groups + 3) / 4, 64));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    a.b0 = b0; a.nb = std::min(B - b0, chunk);
+    ens_minmax_kernel<<<dim3(gx_m, (unsigned)(n_nets * a.nb)), 256, 0, st>>>(a);
+    launch_ens_combine(a, dim3(gx_c, (unsigned)a.nb, (unsigned)(num_lands + 1)), st);
+  }
   return io_launch_check("fu_ensemble_combine");
 }
 
@@ -112,6 +148,8 @@ int fu_extract_landmarks(const float* heats, const uint8_t* segs, const int32_t*
   for (int l = 0; l < num_lands; ++l) a.label[l] = seg_labels ? seg_labels[l] : -1;
   a.P = P; a.L = num_lands; a.h = h; a.w = w; a.D = tmpl_dim; a.min_ncc = min_ncc;
   gauss_consts(sigma, &a.neg2ss, &a.norm);
+  a.vec = (((long long)h * w & 3) == 0 && (reinterpret_cast<uintptr_t>(heats) & 15) == 0 &&
+           (!segs || (reinterpret_cast<uintptr_t>(segs) & 3) == 0)) ? 1 : 0;
   extract_landmarks_kernel<<<(unsigned)((long long)P * num_lands), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return io_launch_check("fu_extract_landmarks");
 }

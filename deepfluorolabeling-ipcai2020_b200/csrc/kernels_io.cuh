@@ -57,6 +57,7 @@ struct PrepArgs {
   float* out;        // (B,Hp,Wp)
   double* sums;      // (B,2): sum, sum of squares over the padded tile
   int B, h, w, pad, Hp, Wp, normalize;
+  int vec;           // out 16-byte aligned and Wp % 4 == 0: float4 stores
 };
 
 __global__ void __launch_bounds__(256) prep_stats_kernel(PrepArgs a) {
@@ -65,11 +66,20 @@ __global__ void __launch_bounds__(256) prep_stats_kernel(PrepArgs a) {
   const float* s = a.src + (size_t)b * a.h * a.w;
   const int n = a.Hp * a.Wp;
   double acc = 0.0, acc2 = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int y = i / a.Wp, x = i - y * a.Wp;
-    const double v = (double)s[(size_t)reflect_idx(y - a.pad, a.h) * a.w + reflect_idx(x - a.pad, a.w)];
-    acc += v;
-    acc2 += v * v;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // four independent loads in flight before the fp64 adds
+      const int j = i + k * stride;
+      const int y = j / a.Wp, x = j - y * a.Wp;
+      v[k] = j < n ? s[(size_t)reflect_idx(y - a.pad, a.h) * a.w + reflect_idx(x - a.pad, a.w)] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc += (double)v[k];
+      acc2 += (double)v[k] * (double)v[k];
+    }
   }
   acc = block_sum_d(acc, sh);
   acc2 = block_sum_d(acc2, sh);
@@ -79,20 +89,39 @@ __global__ void __launch_bounds__(256) prep_stats_kernel(PrepArgs a) {
   }
 }
 
+// One thread = 4 consecutive pixels of a padded row (Wp4 = ceil(Wp/4) groups per row); the tile's mean / std are
+// finalised once per block.  16-byte stores when the padded row length is a multiple of 4.
 __global__ void __launch_bounds__(256) prep_apply_kernel(PrepArgs a) {
+  __shared__ float s_mean, s_std;
   const int b = blockIdx.y;
   const int n = a.Hp * a.Wp;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int y = i / a.Wp, x = i - y * a.Wp;
-  float v = a.src[(size_t)b * a.h * a.w + (size_t)reflect_idx(y - a.pad, a.h) * a.w + reflect_idx(x - a.pad, a.w)];
-  if (a.normalize) {
+  if (a.normalize && threadIdx.x == 0) {
     const double s = a.sums[2 * b], ss = a.sums[2 * b + 1];
     const double mean = s / n;
-    const double var = fmax(ss - s * mean, 0.0) / (double)(n - 1);
-    v = __fdiv_rn(__fsub_rn(v, (float)mean), (float)sqrt(var));
+    s_mean = (float)mean;
+    s_std = (float)sqrt(fmax(ss - s * mean, 0.0) / (double)(n - 1));
   }
-  a.out[(size_t)b * n + i] = v;
+  __syncthreads();
+  const int Wp4 = (a.Wp + 3) >> 2;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.Hp * Wp4) return;
+  const int y = g / Wp4, x0 = (g - y * Wp4) << 2;
+  const float* row = a.src + (size_t)b * a.h * a.w + (size_t)reflect_idx(y - a.pad, a.h) * a.w;
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x0 + k;
+    v[k] = x < a.Wp ? row[reflect_idx(x - a.pad, a.w)] : 0.f;
+    if (a.normalize) v[k] = __fdiv_rn(__fsub_rn(v[k], s_mean), s_std);
+  }
+  float* dst = a.out + (size_t)b * n + (size_t)y * a.Wp + x0;
+  if (a.vec) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (x0 + k < a.Wp) dst[k] = v[k];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -105,22 +134,42 @@ struct HeatArgs {
   int B, L, H, W;
   float neg2ss;   // sigma * sigma * -2
   float norm;     // 2 * pi * sigma * sigma
+  float far_r2;   // beyond this squared distance exp() is exactly 0 in fp32 (argument < -105)
+  int R;          // ceil(sqrt(far_r2)) + 1: half side of the box that holds every non-zero pixel
 };
 
+__device__ __forceinline__ float gauss_px(float x, float y, float mx, float my, float neg2ss, float norm, float far_r2) {
+  const float dx = __fsub_rn(x, mx), dy = __fsub_rn(y, my);
+  const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  if (!(r2 <= far_r2)) return r2 != r2 ? r2 : 0.f;   // underflows to +0 (also below the smallest denormal); NaN stays NaN
+  return __fdiv_rn(expf(__fdiv_rn(r2, neg2ss)), norm);
+}
+
+// The planes are zero-filled by a memset (write-bound, no instructions per pixel); this kernel then visits only the
+// (2R+2)^2 bounding box of each landmark's support disc (R = ceil(sqrt(far_r2)), 37 pixels for sigma 2.5): outside
+// it the fp32 value of the reference expression is exactly +0.  grid = (box blocks, B*L); a NaN coordinate
+// makes the whole plane NaN in the reference, so such a plane is swept completely.
 __global__ void __launch_bounds__(256) heatmap_targets_kernel(HeatArgs a) {
   const int bl = blockIdx.y;
   const int b = bl / a.L, l = bl - b * a.L;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.H * a.W) return;
   const float mx = a.lands[((size_t)b * 2 + 0) * a.L + l], my = a.lands[((size_t)b * 2 + 1) * a.L + l];
-  float v = 0.f;
-  if (!isinf(mx) && !isinf(my)) {
-    const int y = i / a.W, x = i - y * a.W;
-    const float dx = __fsub_rn((float)x, mx), dy = __fsub_rn((float)y, my);
-    const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    v = __fdiv_rn(expf(__fdiv_rn(r2, a.neg2ss)), a.norm);
+  if (isinf(mx) || isinf(my)) return;  // dataset.py:316: plane stays zero
+  float* dst = a.out + (size_t)bl * a.H * a.W;
+  if (mx != mx || my != my) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.H * a.W; i += gridDim.x * blockDim.x) dst[i] = CUDART_NAN_F;
+    return;
   }
-  a.out[(size_t)bl * a.H * a.W + i] = v;
+  const int side = 2 * a.R + 2;
+  // box origin; coordinates far outside the image give an empty intersection (clamped before the int conversion)
+  const int x0 = (int)floorf(fminf(fmaxf(mx, -1.0e6f), 1.0e6f)) - a.R;
+  const int y0 = (int)floorf(fminf(fmaxf(my, -1.0e6f), 1.0e6f)) - a.R;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < side * side; i += gridDim.x * blockDim.x) {
+    const int by = i / side, bx = i - by * side;
+    const int y = y0 + by, x = x0 + bx;
+    if (y < 0 || y >= a.H || x < 0 || x >= a.W) continue;
+    const float v = gauss_px((float)x, (float)y, mx, my, a.neg2ss, a.norm, a.far_r2);
+    if (v != 0.f) dst[(size_t)y * a.W + x] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -131,25 +180,40 @@ struct EnsArgs {
   const float* seg[kMaxNets];
   const float* heat[kMaxNets];
   int n_nets, B, C, L, H, W, r0, c0, h, w;
+  int b0, nb;       // this launch covers images [b0, b0 + nb)
   uint32_t* mn;     // (n_nets*B) ordered-uint minima
   uint32_t* mx;     // (n_nets*B) ordered-uint maxima
   uint8_t* labels;  // (B,h,w)
   float* avg_heat;  // (B,L,h,w)
 };
 
+// The host launches min-max + combine per CHUNK of images whose heat-maps (all networks) fit in a fraction of the
+// 126 MB L2, so the combine pass re-reads them from L2 instead of HBM (the min / max of a whole (network, image)
+// tensor must be known before its first pixel can be normalised: two passes are inherent).
+// 256 threads = 4 rows x 64 columns of the crop window; one integer division per row, none per pixel.
 __global__ void __launch_bounds__(256) ens_minmax_kernel(EnsArgs a) {
   __shared__ float s_mn[8], s_mx[8];
-  const int nb = blockIdx.y;
-  const int n = nb / a.B, b = nb - n * a.B;
+  const int n = blockIdx.y / a.nb, b = a.b0 + (blockIdx.y - n * a.nb);
   const float* src = a.heat[n] + (size_t)b * a.L * a.H * a.W;
-  const int hw = a.h * a.w, tot = a.L * hw;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int rows = a.L * a.h;
   float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
-    const int l = i / hw, r = i - l * hw;
-    const int y = r / a.w, x = r - y * a.w;
-    const float v = src[((size_t)l * a.H + a.r0 + y) * a.W + a.c0 + x];
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
+  for (int row = blockIdx.x * 8 + ty; row < rows; row += gridDim.x * 8) {
+    const int row2 = min(row + 4, rows - 1);  // second row of the pair (a repeat of a valid row at the end)
+    const int l = row / a.h, y = row - l * a.h, l2 = row2 / a.h, y2 = row2 - l2 * a.h;
+    const float* p = src + ((size_t)l * a.H + a.r0 + y) * a.W + a.c0;
+    const float* p2 = src + ((size_t)l2 * a.H + a.r0 + y2) * a.W + a.c0;
+    for (int x = tx; x < a.w; x += 256) {  // eight independent loads in flight
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = x + 64 * k < a.w ? x + 64 * k : x;
+        v[k] = p[xx];
+        v[4 + k] = p2[xx];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { mn = fminf(mn, v[k]); mx = fmaxf(mx, v[k]); }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -161,42 +225,105 @@ __global__ void __launch_bounds__(256) ens_minmax_kernel(EnsArgs a) {
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { mn = fminf(mn, s_mn[k]); mx = fmaxf(mx, s_mx[k]); }
-    atomicMin(&a.mn[nb], f2ord(mn));
-    atomicMax(&a.mx[nb], f2ord(mx));
+    atomicMin(&a.mn[n * a.B + b], f2ord(mn));
+    atomicMax(&a.mx[n * a.B + b], f2ord(mx));
   }
 }
 
+// grid = (pixel blocks, images of the chunk, L + 1): z < L normalises and averages heat-map plane z, z == L does the
+// class average + arg-max.  NN > 0: network count known at compile time, so the NN loads of a pixel are issued
+// together; NN == 0: any count up to kMaxNets.  The sums run over the networks in list order, as util.py:341-356.
+constexpr int kEnsPix = 4;  // pixels per thread in ens_combine (strided by the block size: coalesced, 4*NN loads in flight)
+template <int NN>
 __global__ void __launch_bounds__(256) ens_combine_kernel(EnsArgs a) {
-  const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int hw = a.h * a.w;
-  if (i >= hw) return;
-  const int y = i / a.w, x = i - y * a.w;
-  const size_t pix = (size_t)(a.r0 + y) * a.W + a.c0 + x;
-  const float fn = (float)a.n_nets;
-  // avg_masks = sum over nets in list order, / num_nets, torch.max(dim=1): the first maximum wins
-  float best = 0.f;
-  int arg = 0;
-  for (int c = 0; c < a.C; ++c) {
-    const size_t off = ((size_t)b * a.C + c) * a.H * a.W + pix;
-    float acc = a.seg[0][off];
-    for (int n = 1; n < a.n_nets; ++n) acc = __fadd_rn(acc, a.seg[n][off]);
-    acc = __fdiv_rn(acc, fn);
-    if (c == 0 || acc > best) { best = acc; arg = c; }
+  __shared__ float s_lo[kMaxNets], s_den[kMaxNets];
+  const int b = a.b0 + blockIdx.y;
+  const int nn = NN > 0 ? NN : a.n_nets;
+  const bool heat_plane = (int)blockIdx.z < a.L;
+  if (heat_plane && threadIdx.x < nn) {
+    const float lo = ord2f(a.mn[threadIdx.x * a.B + b]), hi = ord2f(a.mx[threadIdx.x * a.B + b]);
+    s_lo[threadIdx.x] = lo;
+    s_den[threadIdx.x] = __fsub_rn(hi, lo);   // util.py:351
   }
-  a.labels[(size_t)b * hw + i] = (uint8_t)arg;
-  if (a.avg_heat) {
-    for (int l = 0; l < a.L; ++l) {
-      const size_t off = ((size_t)b * a.L + l) * a.H * a.W + pix;
-      float acc = 0.f;
-      for (int n = 0; n < a.n_nets; ++n) {
-        const float lo = ord2f(a.mn[n * a.B + b]), hi = ord2f(a.mx[n * a.B + b]);
-        const float v = __fdiv_rn(__fsub_rn(a.heat[n][off], lo), __fsub_rn(hi, lo));
-        acc = n == 0 ? v : __fadd_rn(acc, v);
+  __syncthreads();
+  const int hw = a.h * a.w;
+  const size_t plane = (size_t)a.H * a.W;
+  const float fn = (float)nn;
+  constexpr int U = NN > 0 ? NN : 1;
+  int idx[kEnsPix];
+  size_t pix[kEnsPix];
+#pragma unroll
+  for (int k = 0; k < kEnsPix; ++k) {
+    idx[k] = (blockIdx.x * kEnsPix + k) * blockDim.x + threadIdx.x;
+    const int i = min(idx[k], hw - 1);  // out-of-range lanes read a valid pixel and skip the store
+    const int y = i / a.w, x = i - y * a.w;
+    pix[k] = (size_t)(a.r0 + y) * a.W + a.c0 + x;
+  }
+  if (heat_plane) {
+    const int l = blockIdx.z;
+    const size_t base = ((size_t)b * a.L + l) * plane;
+    float acc[kEnsPix];
+    if (NN > 0) {
+      float v[kEnsPix][U];
+#pragma unroll
+      for (int k = 0; k < kEnsPix; ++k)
+#pragma unroll
+        for (int n = 0; n < U; ++n) v[k][n] = a.heat[n][base + pix[k]];
+#pragma unroll
+      for (int k = 0; k < kEnsPix; ++k) {
+        acc[k] = __fdiv_rn(__fsub_rn(v[k][0], s_lo[0]), s_den[0]);
+#pragma unroll
+        for (int n = 1; n < U; ++n) acc[k] = __fadd_rn(acc[k], __fdiv_rn(__fsub_rn(v[k][n], s_lo[n]), s_den[n]));
       }
-      a.avg_heat[((size_t)b * a.L + l) * hw + i] = __fdiv_rn(acc, fn);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kEnsPix; ++k) {
+        acc[k] = __fdiv_rn(__fsub_rn(a.heat[0][base + pix[k]], s_lo[0]), s_den[0]);
+        for (int n = 1; n < nn; ++n)
+          acc[k] = __fadd_rn(acc[k], __fdiv_rn(__fsub_rn(a.heat[n][base + pix[k]], s_lo[n]), s_den[n]));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kEnsPix; ++k)
+      if (idx[k] < hw) a.avg_heat[((size_t)b * a.L + l) * hw + idx[k]] = __fdiv_rn(acc[k], fn);
+    return;
+  }
+  // avg_masks = sum over nets in list order, / num_nets, torch.max(dim=1): the first maximum wins
+  float best[kEnsPix];
+  int arg[kEnsPix];
+#pragma unroll
+  for (int k = 0; k < kEnsPix; ++k) { best[k] = 0.f; arg[k] = 0; }
+  for (int c = 0; c < a.C; ++c) {
+    const size_t base = ((size_t)b * a.C + c) * plane;
+    float acc[kEnsPix];
+    if (NN > 0) {
+      float v[kEnsPix][U];
+#pragma unroll
+      for (int k = 0; k < kEnsPix; ++k)
+#pragma unroll
+        for (int n = 0; n < U; ++n) v[k][n] = a.seg[n][base + pix[k]];
+#pragma unroll
+      for (int k = 0; k < kEnsPix; ++k) {
+        acc[k] = v[k][0];
+#pragma unroll
+        for (int n = 1; n < U; ++n) acc[k] = __fadd_rn(acc[k], v[k][n]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kEnsPix; ++k) {
+        acc[k] = a.seg[0][base + pix[k]];
+        for (int n = 1; n < nn; ++n) acc[k] = __fadd_rn(acc[k], a.seg[n][base + pix[k]]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kEnsPix; ++k) {
+      const float m = __fdiv_rn(acc[k], fn);
+      if (c == 0 || m > best[k]) { best[k] = m; arg[k] = c; }
     }
   }
+#pragma unroll
+  for (int k = 0; k < kEnsPix; ++k)
+    if (idx[k] < hw) a.labels[(size_t)b * hw + idx[k]] = (uint8_t)arg[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -212,6 +339,7 @@ struct LandArgs {
   int32_t* out;         // (P,L,2): row, col
   float* ncc_out;       // (P,L) or nullptr; NaN when the masked arg-max found nothing
   int P, L, h, w, D;
+  int vec;              // heat-map planes 16-byte aligned, seg planes 4-byte aligned, h*w % 4 == 0
   float neg2ss, norm, min_ncc;
 };
 
@@ -229,10 +357,31 @@ __global__ void __launch_bounds__(256) extract_landmarks_kernel(LandArgs a) {
   const uint8_t* seg = masked ? a.segs + (size_t)p * hw : nullptr;
   float best = -CUDART_INF_F;
   int arg = INT_MAX;
-  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-    float v = heat[i];
-    if (masked && (int)seg[i] != label) v = -CUDART_INF_F;
-    if (v > best) { best = v; arg = i; }
+  if (a.vec) {  // planes are 16-byte (heat) / 4-byte (seg) aligned and a multiple of 4 pixels: 4 pixels per load
+    const float4* h4 = reinterpret_cast<const float4*>(heat);
+    const uchar4* s4 = reinterpret_cast<const uchar4*>(seg);
+#pragma unroll 4
+    for (int q = threadIdx.x; q < (hw >> 2); q += blockDim.x) {
+      float4 v = h4[q];
+      if (masked) {
+        const uchar4 m = s4[q];
+        if ((int)m.x != label) v.x = -CUDART_INF_F;
+        if ((int)m.y != label) v.y = -CUDART_INF_F;
+        if ((int)m.z != label) v.z = -CUDART_INF_F;
+        if ((int)m.w != label) v.w = -CUDART_INF_F;
+      }
+      const int i = q << 2;   // ascending index order within the thread: strict > keeps the first maximum
+      if (v.x > best) { best = v.x; arg = i; }
+      if (v.y > best) { best = v.y; arg = i + 1; }
+      if (v.z > best) { best = v.z; arg = i + 2; }
+      if (v.w > best) { best = v.w; arg = i + 3; }
+    }
+  } else {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+      float v = heat[i];
+      if (masked && (int)seg[i] != label) v = -CUDART_INF_F;
+      if (v > best) { best = v; arg = i; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

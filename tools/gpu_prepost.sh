@@ -4,6 +4,4 @@ mkdir -p gpurun_out/prepost
 (timeout 240 python -m pytest tests/test_prepost_gpu.py -m gpu -q 2>&1 | tail -40) > gpurun_out/prepost/pytest_prepost.log
 (timeout 120 python tools/prepost_time.py 256 3 2>&1 | tail -8) > gpurun_out/prepost/time_b256.log
 (timeout 120 python tools/prepost_time.py 32 3 2>&1 | tail -8) > gpurun_out/prepost/time_b32.log
-(timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -6) > gpurun_out/prepost/smoke.log
-(timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv -k regex:"prep_|heatmap_targets|ens_|extract_landmarks" -c 40 --log-file gpurun_out/prepost/ncu_prepost.csv python tools/prepost_time.py 256 3 > gpurun_out/prepost/ncu.log 2>&1)
-cat gpurun_out/prepost/pytest_prepost.log gpurun_out/prepost/time_b256.log gpurun_out/prepost/time_b32.log gpurun_out/prepost/smoke.log
+(timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv -k regex:"prep_|heatmap_targets|ens_|extract_landmarks" -c 120 --log-file gpurun_out/prepost/ncu_prepost.csv python tools/prepost_time.py 256 3 > gpurun_out/prepost/ncu.log 2>&1)
