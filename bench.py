@@ -47,6 +47,10 @@ def parse():
                     help="launch every step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--torch-loss", action="store_true",
                     help="use the PyTorch DiceAndHeatMapLoss2D on cropped views instead of the fused device loss")
+    ap.add_argument("--seg-only", action="store_true",
+                    help="num_lands=0 network with DiceLoss2D (train.py:327; BASELINE configs[2]: --batch 8 --size 736 --tile 718)")
+    ap.add_argument("--heatmap-wgt", type=float, default=0.5,
+                    help="train.py --heat-coeff (BASELINE configs[4] uses 1.0: --batch 2 --size 1440 --tile 1436)")
     ap.add_argument("--device-prep", action="store_true",
                     help="also time an end-to-end step whose host inputs are the RAW tiles, landmark coordinates and u1 label "
                          "maps: reflect pad + z-score and the Gaussian heat-map targets run on the device (prepost.py, "
@@ -171,9 +175,15 @@ def cpu_reference_run(torch, steps, warmup, batch, size, tile, threads):
 
 
 def config_dict(args, world):
-    return {"workload": f"paper dual-head U-Net (depth 6, wf 5, BN, learned 2x2/s2 downsample, res 1x1; 7-class seg + "
-                        f"14 heat-maps), {args.batch} tiles/GPU of 1x{args.tile}x{args.tile} reflect-padded to "
-                        f"{args.size}x{args.size}, train step = fwd + DiceAndHeatMapLoss2D + bwd + SGD(nesterov)",
+    if getattr(args, "seg_only", False):
+        heads, loss_name = "7-class seg only, num_lands=0", "DiceLoss2D"
+    else:
+        heads, loss_name = "7-class seg + 14 heat-maps", "DiceAndHeatMapLoss2D"
+        if getattr(args, "heatmap_wgt", 0.5) != 0.5:
+            loss_name += f"(heatmap_wgt={args.heatmap_wgt})"
+    return {"workload": f"paper dual-head U-Net (depth 6, wf 5, BN, learned 2x2/s2 downsample, res 1x1; {heads}), "
+                        f"{args.batch} tiles/GPU of 1x{args.tile}x{args.tile} reflect-padded to "
+                        f"{args.size}x{args.size}, train step = fwd + {loss_name} + bwd + SGD(nesterov)",
             "per_gpu_batch": args.batch, "global_batch": args.batch * world, "net_input": args.size, "tile": args.tile,
             "parallelism": f"dp{world}", "precision": args.precision,
             "loss": "torch DiceAndHeatMapLoss2D on cropped views" if getattr(args, "torch_loss", False)
@@ -221,7 +231,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
-    net = pkg.UNet(precision=args.precision, **PAPER).to(dev)
+    if args.seg_only and args.device_prep:
+        raise SystemExit("bench.py: --device-prep times the dual-head sample preparation; drop --seg-only")
+    net_cfg = dict(PAPER, num_lands=0) if args.seg_only else PAPER
+    net = pkg.UNet(precision=args.precision, **net_cfg).to(dev)
     net.train()
     if world > 1:
         pkg.parallel.data_parallel(net)
@@ -230,7 +243,10 @@ def run_ours(args):
     # train.py:324's loss.  Default: the fused device version (same value and gradient, tests/test_loss_gpu.py),
     # which folds the output crop of train.py:414-417 into its indexing.
     fused_loss = not args.torch_loss
-    crit = (pkg.FusedDiceAndHeatMapLoss2D if fused_loss else pkg.DiceAndHeatMapLoss2D)(skip_bg=False, heatmap_wgt=0.5)
+    if args.seg_only:
+        crit = (pkg.FusedDiceLoss2D if fused_loss else pkg.DiceLoss2D)(skip_bg=False)                     # train.py:327
+    else:
+        crit = (pkg.FusedDiceAndHeatMapLoss2D if fused_loss else pkg.DiceAndHeatMapLoss2D)(skip_bg=False, heatmap_wgt=args.heatmap_wgt)
     B, S, T = args.batch, args.size, args.tile
     g = torch.Generator().manual_seed(100 + rank)
     n_host = 2
@@ -238,12 +254,18 @@ def run_ours(args):
     for _ in range(n_host):
         x = torch.randn(B, 1, S, S, generator=g)
         mask, heat = make_targets(B, T, 7, 14, g, torch)
-        host.append(tuple(t.pin_memory() for t in (x, mask, heat)))
+        host.append(tuple(t.pin_memory() for t in ((x, mask) if args.seg_only else (x, mask, heat))))
     resident = tuple(t.to(dev) for t in host[0])
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
 
-    def train_step(x, mask, heat):
+    def train_step(x, mask, heat=None):
         opt.zero_grad(set_to_none=True)
+        if args.seg_only:
+            seg = net(x)
+            loss = crit(seg, mask) if fused_loss else crit(pkg.center_crop(seg, mask.shape), mask)
+            loss.backward()
+            opt.step()
+            return loss
         seg, hm = net(x)
         if fused_loss:
             loss = crit((seg, hm), (mask, heat))
