@@ -106,6 +106,19 @@ def test_prep_and_heat_targets_match_oracle(pp, B, h, dim, L, seed):
     np.testing.assert_allclose(heat.cpu().numpy(), IO.heatmap_targets(lands, h, h + 3).numpy(), **HEAT_TOL)
 
 
+def test_heat_targets_special_coordinates(pp):
+    """NaN coordinates poison the whole plane in the reference expression, +-inf gives a zero plane (dataset.py:316), finite
+    coordinates far outside the view underflow to zero, peaks just outside the border still leak in."""
+    lands = torch.tensor([[[float("nan"), 5.0, 1.0e30, -3.5, 20.25, float("-inf")],
+                           [7.0, float("nan"), 4.0, 10.0, 33.75, 2.0]]])
+    got = pp.heatmap_targets(lands.to(DEV), (30, 34)).cpu()
+    want = IO.heatmap_targets(lands, 30, 34)
+    assert bool(got[0, 0].isnan().all()) and bool(got[0, 1].isnan().all())
+    assert float(got[0, 2].abs().max()) == 0.0 and float(got[0, 5].abs().max()) == 0.0
+    assert float(got[0, 3].max()) > 0 and float(got[0, 4].max()) > 0
+    np.testing.assert_allclose(got.numpy(), want.numpy(), **HEAT_TOL)
+
+
 @pytest.mark.parametrize("n,B,C,L,H,h,seed", [(1, 3, 7, 14, 24, 24, 0), (4, 2, 5, 3, 33, 20, 1), (16, 1, 2, 1, 16, 9, 2),
                                                   (4, 7, 7, 14, 192, 180, 3)])   # the last one spans two L2 chunks
 def test_ensemble_matches_oracle(pp, n, B, C, L, H, h, seed):
