@@ -1,4 +1,4 @@
-# GPU check of the sample-prep / post-processing kernels: their parity tests, timings, smoke, then the rest of the GPU suite.
+# GPU check of the sample-prep / post-processing kernels: parity tests, CUDA-event timings, ncu launch list (time + DRAM bytes).
 set -x
 mkdir -p gpurun_out/prepost
 (timeout 240 python -m pytest tests/test_prepost_gpu.py -m gpu -q 2>&1 | tail -40) > gpurun_out/prepost/pytest_prepost.log
