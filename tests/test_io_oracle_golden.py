@@ -64,3 +64,33 @@ def test_extract_landmarks_matches_est_lands_csv(gold, tag):
     assert 0 < found.sum() < found.size                                    # both outcomes are pinned
     s = scores.numpy()
     assert np.all(np.isnan(s) | (np.abs(s - 0.9) > 1e-3))                  # no score sits on the threshold
+
+
+# ---- size-independent properties of the restatement itself (the same ones the GPU tests demand of the kernels) ----
+
+def test_oracle_properties_prep_and_round_trip():
+    g = torch.Generator().manual_seed(21)
+    tiles = torch.rand(3, 26, 26, generator=g) * 5000
+    x = IO.prep_tiles(tiles.numpy(), IO.calc_pad_amount(32, 26))
+    assert x.shape == (3, 1, 32, 32)
+    assert float(x.mean(dim=(1, 2, 3)).abs().max()) < 1e-5 and float((x.std(dim=(1, 2, 3)) - 1).abs().max()) < 1e-5
+    p = 3
+    assert torch.equal(x[:, :, p - 2, :], x[:, :, p + 2, :]) and torch.equal(x[:, :, :, 31 - p + 1], x[:, :, :, 31 - p - 1])
+    lands = torch.stack([torch.randint(13, 35, (3, 4), generator=g), torch.randint(13, 35, (3, 4), generator=g)], 1).float()
+    heat = IO.heatmap_targets(lands, 48, 48)
+    assert float((heat.sum(dim=(2, 3)) - 1).abs().max()) < 1e-3            # unit-mass Gaussians inside the view
+    rc, ncc = IO.extract_landmarks(heat)
+    assert torch.equal(rc, torch.stack([lands[:, 1], lands[:, 0]], dim=-1).long())
+    assert float((ncc - 624.0 / 625.0).abs().max()) < 1e-5                 # ncc.py:38: unbiased sd under an N-fold sum
+
+
+def test_oracle_properties_ensemble():
+    g = torch.Generator().manual_seed(22)
+    seg = torch.softmax(torch.randn(2, 5, 12, 12, generator=g), 1)
+    heat = torch.randn(2, 3, 12, 12, generator=g)
+    l1, a1 = IO.ensemble_combine([seg], [heat], (10, 10))
+    l3, a3 = IO.ensemble_combine([seg, seg, seg], [heat, heat * 7 - 2, heat * 0.01], (10, 10))
+    assert torch.equal(l1, l3)                                             # identical members: the same labels
+    np.testing.assert_allclose(a3.numpy(), a1.numpy(), rtol=0, atol=2e-6)  # min-max normalisation removes scale and offset
+    assert torch.equal(l1.long(), IO._crop(seg, (10, 10)).argmax(dim=1))
+    assert float(a1.amin()) == 0.0 and float(a1.amax()) == 1.0
