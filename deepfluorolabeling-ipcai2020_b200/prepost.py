@@ -72,6 +72,9 @@ def heatmap_targets(lands, shape, sigma=2.5):
         raise ValueError("heatmap_targets: lands must be (B,2,L) (dataset.py:59)")
     B, _, L = lands.shape
     H, W = int(shape[-2]), int(shape[-1])
+    if L > 0 and B * L > 65535:     # one launch covers at most 65535 planes: split the batch
+        step = max(1, 65535 // L)
+        return torch.cat([heatmap_targets(lands[i:i + step], shape, sigma) for i in range(0, B, step)])
     out = torch.empty(B, L, H, W, device=lands.device, dtype=torch.float32)
     with torch.cuda.device(lands.device):
         _check(_capi.lib().fu_heatmap_targets(lands.data_ptr(), B, L, H, W, float(sigma), out.data_ptr(), _stream(lands)),
