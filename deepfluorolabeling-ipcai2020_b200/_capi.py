@@ -8,7 +8,8 @@ LIB_PATH = os.path.join(HERE, "libfluorounet.so")
 FU_OK = 0
 FU_ERR_INVALID_CONFIG = -1
 FU_ERR_UNSUPPORTED_SHAPE = -2
-PRECISION = {"fp32": 0, "bf16": 1}
+# include/fluoro_unet.h FU_PRECISION_*: "parity_tc" = fp32 storage with split-bf16 x3 tensor-core contractions
+PRECISION = {"fp32": 0, "bf16": 1, "parity_tc": 2}
 
 
 class FuConfig(C.Structure):

@@ -29,6 +29,8 @@ struct View {
   char* p = nullptr;  // address of channel 0 of this view
   int C = 0;          // channels in the view
   int ld = 0;         // pixel stride, in elements
+  char* sp = nullptr; // parity_tc mode: channel 0 of the hi half of this view's split-bf16 twin (kernels_tc.cuh:
+                      // split_f32_kernel); twin pixel stride 2*ld bf16 elements, lo half ld elements after the hi half
 };
 
 struct TensorSlot {
@@ -73,6 +75,7 @@ struct Plan {
   bool valid = false;
   char* arena = nullptr;
   size_t arena_bytes = 0;
+  char* twin = nullptr;         // parity_tc mode: second arena of the same size holding the split-bf16 twins
   View xin;
   std::vector<View> cat, d_cat, down, d_down, decout, d_decout;
   View bott, d_bott, hcat, d_hcat, dheat;
@@ -127,6 +130,11 @@ struct fu_engine {
   bool side_used = false;
   int use_side = 1;
   int num_sms = 148;
+  bool split = false;            // parity_tc: fp32 storage, tensor-core layers read split-bf16 twins (three MMA passes)
+  // twins that are up to date: (view address, channels).  Forward activations stay valid until the next forward;
+  // gradient tensors are produced once per backward.
+  std::vector<std::pair<const void*, int>> fresh_fwd, fresh_bwd;
+  bool in_backward = false;
   // optional per-launch CUDA-event profiling (fu_profile_enable)
   struct DeferredSum { const double* src; float* dst; int n; };
   std::vector<DeferredSum> deferred_sums;
@@ -233,6 +241,7 @@ inline View slice(const View& v, int c0, int C, int esz) {
   o.p = v.p + (size_t)c0 * esz;
   o.C = C;
   o.ld = v.ld;
+  o.sp = v.sp ? v.sp + (size_t)c0 * 2 : nullptr;
   return o;
 }
 inline unsigned grid1d(long long total, int block, int sms) {
@@ -388,7 +397,7 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
                   (c.Cout & (c.Cout - 1)) == 0 && c.Cout / 8 <= 32;
     if (c.Cout > maxc) maxc = c.Cout;
     if (c.Cin > maxc) maxc = c.Cin;
-    tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision == FU_PRECISION_BF16, w, ws);
+    tc_carve(c.tc, c.Cin, c.Cout, c.k, c.transposed, e->cfg.precision != FU_PRECISION_FP32, w, ws, e->split);
   });
   for (auto& b : e->enc) b.dstat = db.take<double>(2 * (size_t)b.Cin);
   for (auto& b : e->dec) b.dstat = db.take<double>(2 * (size_t)b.Cin);
@@ -444,11 +453,13 @@ int alloc_persistent(fu_engine* e) {
 // ---------------------------------------------------------------------------
 // plan: activation arena for (B,H,W)
 // ---------------------------------------------------------------------------
-View take_view(Bump& b, long long pixels, int C, int ld, int esz) {
+View take_view(Bump& b, long long pixels, int C, int ld, int esz, const Plan* pl = nullptr) {
   View v;
   v.p = b.take<char>((size_t)pixels * ld * esz);
   v.C = C;
   v.ld = ld;
+  // the twin of a buffer sits at the same offset of the twin arena (same bytes per pixel: 2 x ld bf16 = ld fp32)
+  if (pl && pl->twin && v.p) v.sp = pl->twin + (v.p - pl->arena);
   return v;
 }
 
@@ -457,27 +468,27 @@ void carve_plan(fu_engine* e, Plan& pl, Bump& b, int B, int H, int W) {
   const int esz = e->esz;
   const int D = c.depth;
   auto pix = [&](int lvl) { return (long long)B * (H >> lvl) * (W >> lvl); };
-  pl.xin = take_view(b, pix(0), c.in_channels, c.in_channels, esz);
+  pl.xin = take_view(b, pix(0), c.in_channels, c.in_channels, esz, &pl);
   pl.cat.assign(D, View()); pl.d_cat.assign(D, View());
   pl.down.assign(D, View()); pl.d_down.assign(D, View());
   pl.decout.assign(D, View()); pl.d_decout.assign(D, View());
-  pl.hcat = take_view(b, pix(0), e->Cpad, e->Cpad, esz);
-  pl.d_hcat = take_view(b, pix(0), e->Cpad, e->Cpad, esz);
+  pl.hcat = take_view(b, pix(0), e->Cpad, e->Cpad, esz, &pl);
+  pl.d_hcat = take_view(b, pix(0), e->Cpad, e->Cpad, esz, &pl);
   for (int l = 0; l < D - 1; ++l) {
-    pl.cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz);
-    pl.d_cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz);
+    pl.cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz, &pl);
+    pl.d_cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz, &pl);
   }
   for (int l = 1; l < D; ++l) {
-    pl.down[l] = take_view(b, pix(l), e->chans[l - 1], e->chans[l - 1], esz);
-    pl.d_down[l] = take_view(b, pix(l), e->chans[l - 1], e->chans[l - 1], esz);
+    pl.down[l] = take_view(b, pix(l), e->chans[l - 1], e->chans[l - 1], esz, &pl);
+    pl.d_down[l] = take_view(b, pix(l), e->chans[l - 1], e->chans[l - 1], esz, &pl);
   }
   if (D > 1) {
-    pl.bott = take_view(b, pix(D - 1), e->chans[D - 1], e->chans[D - 1], esz);
-    pl.d_bott = take_view(b, pix(D - 1), e->chans[D - 1], e->chans[D - 1], esz);
+    pl.bott = take_view(b, pix(D - 1), e->chans[D - 1], e->chans[D - 1], esz, &pl);
+    pl.d_bott = take_view(b, pix(D - 1), e->chans[D - 1], e->chans[D - 1], esz, &pl);
   }
   for (int l = 1; l < D - 1; ++l) {
-    pl.decout[l] = take_view(b, pix(l), e->chans[l], e->chans[l], esz);
-    pl.d_decout[l] = take_view(b, pix(l), e->chans[l], e->chans[l], esz);
+    pl.decout[l] = take_view(b, pix(l), e->chans[l], e->chans[l], esz, &pl);
+    pl.d_decout[l] = take_view(b, pix(l), e->chans[l], e->chans[l], esz, &pl);
   }
   // the last block of the network writes its output straight into the head's concat buffer
   pl.decout[0] = slice(pl.hcat, 0, e->Cf, esz);
@@ -487,10 +498,10 @@ void carve_plan(fu_engine* e, Plan& pl, Bump& b, int B, int H, int W) {
     blk.r.assign(nd, View()); blk.z.assign(nd, View()); blk.dy.assign(nd, View()); blk.dz.assign(nd, View());
     for (int i = 0; i < nd; ++i) {
       if (i == nd - 1 && blk.bns.empty() && !blk.has_res) blk.r[i] = outv;  // ReLU output IS the block output
-      else blk.r[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
-      if (!blk.bns.empty() && i < nd - 1) blk.z[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
-      blk.dy[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
-      if (i > 0) blk.dz[i] = take_view(b, pix(lvl), blk.C, blk.C, esz);
+      else blk.r[i] = take_view(b, pix(lvl), blk.C, blk.C, esz, &pl);
+      if (!blk.bns.empty() && i < nd - 1) blk.z[i] = take_view(b, pix(lvl), blk.C, blk.C, esz, &pl);
+      blk.dy[i] = take_view(b, pix(lvl), blk.C, blk.C, esz, &pl);
+      if (i > 0) blk.dz[i] = take_view(b, pix(lvl), blk.C, blk.C, esz, &pl);
     }
   };
   for (int l = 0; l < D; ++l)
@@ -499,10 +510,10 @@ void carve_plan(fu_engine* e, Plan& pl, Bump& b, int B, int H, int W) {
   pl.hmid.clear(); pl.d_hmid.clear();
   for (size_t k = 0; k + 1 < e->lands.size(); ++k) {
     const int n = e->lands[k].Cout;
-    pl.hmid.push_back(take_view(b, pix(0), n, pad_to(n, 8), esz));
-    pl.d_hmid.push_back(take_view(b, pix(0), n, pad_to(n, 8), esz));
+    pl.hmid.push_back(take_view(b, pix(0), n, pad_to(n, 8), esz, &pl));
+    pl.d_hmid.push_back(take_view(b, pix(0), n, pad_to(n, 8), esz, &pl));
   }
-  if (c.num_lands > 0) pl.dheat = take_view(b, pix(0), c.num_lands, pad_to(c.num_lands, 8), esz);
+  if (c.num_lands > 0) pl.dheat = take_view(b, pix(0), c.num_lands, pad_to(c.num_lands, 8), esz, &pl);
 }
 
 int ensure_plan(fu_engine* e, int B, int H, int W) {
@@ -523,15 +534,18 @@ int ensure_plan(fu_engine* e, int B, int H, int W) {
     if (pl.arena) {
       CUDA_TRY(e, cudaStreamSynchronize(e->stream));
       CUDA_TRY(e, cudaFree(pl.arena));
-      pl.arena = nullptr;
+      if (pl.twin) CUDA_TRY(e, cudaFree(pl.twin));
+      pl.arena = nullptr; pl.twin = nullptr;
       pl.arena_bytes = 0;
     }
     CUDA_TRY(e, cudaMalloc(&pl.arena, need));
+    if (e->split) CUDA_TRY(e, cudaMalloc(&pl.twin, need));
     pl.arena_bytes = need;
   }
   Bump real;
   real.base = pl.arena;
   carve_plan(e, pl, real, B, H, W);
+  e->fresh_fwd.clear(); e->fresh_bwd.clear();
   pl.B = B; pl.H = H; pl.W = W;
   pl.valid = true;
   e->saved = false;
@@ -720,6 +734,31 @@ inline dim3 red_grid(fu_engine* e, long long P, int C) {
 }
 
 float* tdata(fu_engine* e, int idx) { return idx < 0 ? nullptr : reinterpret_cast<float*>(e->tensors[idx].data); }
+
+// ---------------------------------------------------------------------------
+// parity_tc mode: MMA operands are read from split-bf16 twins of the fp32 tensors
+// ---------------------------------------------------------------------------
+struct Opnd { const void* p; int ld; };
+// operand descriptor of a view as the tensor-core kernels take it: the view itself, or its twin (hi half, twin stride)
+inline Opnd opnd(const fu_engine* e, const View& v) {
+  return e->split ? Opnd{v.sp, 2 * v.ld} : Opnd{v.p, v.ld};
+}
+// make the twin of `v` (P pixels) current on the engine's CURRENT stream.  Call it on the main stream before forking
+// work that reads the twin to the side stream.
+int ensure_split(fu_engine* e, const View& v, long long P) {
+  if (!e->split || !v.sp || (v.C % 4) || (v.ld % 4)) return FU_OK;
+  const std::pair<const void*, int> key(v.p, v.C);
+  for (auto& k : e->fresh_fwd) if (k == key) return FU_OK;
+  for (auto& k : e->fresh_bwd) if (k == key) return FU_OK;
+  e->set_tag(0, 8.0 * P * v.C, "split_twin");
+  if (e->prof) e->prof_begin("split_f32_kernel");
+  const int rc = tc_split(reinterpret_cast<const float*>(v.p), v.ld, v.C, reinterpret_cast<bf16*>(v.sp), 2 * v.ld, v.ld, P,
+                          e->num_sms, e->stream, &e->cnt);
+  if (e->prof) e->prof_end();
+  if (rc) return e->fail(FU_ERR_CUDA, "split_f32_kernel launch failed");
+  (e->in_backward ? e->fresh_bwd : e->fresh_fwd).push_back(key);
+  return FU_OK;
+}
 float* gptr(fu_engine* e, float* flat, int idx) {
   if (idx < 0) return nullptr;
   const int64_t off = e->tensors[idx].info.grad_offset;
@@ -738,9 +777,11 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (x.C + y.C)) * e->esz + 2.0 * cw.Cin * cw.Cout * cw.k * cw.k,
                "conv%d_fwd %dx%d %d->%d", cw.k, H, W, cw.Cin, cw.Cout);
   }
-  if (tc_conv_eligible(cw.tc, x.p, x.ld, y.p, y.ld, t ? t->p : nullptr, t ? t->ld : 0)) {
+  const Opnd xo = opnd(e, x);
+  if (tc_conv_eligible(cw.tc, xo.p, xo.ld, y.p, y.ld, t ? t->p : nullptr, t ? t->ld : 0)) {
+    { const int src = ensure_split(e, x, (long long)B * H * W); if (src) return src; }
     if (e->prof) e->prof_begin("tc_conv_kernel");
-    int rc = tc_conv_forward(cw.tc, x.p, x.ld, y.p, y.ld, B, H, W, tdata(e, cw.b_idx), relu, stat,
+    int rc = tc_conv_forward(cw.tc, xo.p, xo.ld, y.p, y.ld, B, H, W, tdata(e, cw.b_idx), relu, stat,
                              t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt, fin);
     if (e->prof) e->prof_end();
     if (rc) return e->fail(FU_ERR_CUDA, "tensor-core conv launch failed: %s", tc_last_error());
@@ -816,7 +857,7 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
       } else {
         // the last BN of a residual block is applied inside the residual conv's epilogue; on the tensor-core path it
         // is also finalised there (res_fin), otherwise by a one-block kernel
-        if (tc_conv_eligible(blk.res.tc, x_in.p, x_in.ld, out.p, out.ld, r.p, r.ld)) {
+        if (tc_conv_eligible(blk.res.tc, opnd(e, x_in).p, opnd(e, x_in).ld, out.p, out.ld, r.p, r.ld)) {
           res_fin.stat = b.stat; res_fin.P = P; res_fin.training = training;
           res_fin.gamma = tdata(e, b.i_gamma); res_fin.beta = tdata(e, b.i_beta);
           res_fin.rmean = tdata(e, b.i_rm); res_fin.rvar = tdata(e, b.i_rv);
@@ -872,9 +913,11 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
                w / 2, outv.C);
       } else {
         ConvW& cw = e->downc[l];
-        if (tc_down_eligible(cw.tc, outv.p, outv.ld, dn.p, dn.ld)) {
+        const Opnd oo = opnd(e, outv);
+        if (tc_down_eligible(cw.tc, oo.p, oo.ld, dn.p, dn.ld)) {
+          if ((rc = ensure_split(e, outv, (long long)B * h * w))) return rc;
           if (e->prof) e->prof_begin("tc_conv_kernel");
-          const int trc = tc_down_forward(cw.tc, outv.p, outv.ld, dn.p, dn.ld, B, h, w, tdata(e, cw.b_idx), e->stream, &e->cnt);
+          const int trc = tc_down_forward(cw.tc, oo.p, oo.ld, dn.p, dn.ld, B, h, w, tdata(e, cw.b_idx), e->stream, &e->cnt);
           if (e->prof) e->prof_end();
           if (trc)
             return e->fail(FU_ERR_CUDA, "tensor-core downsample launch failed: %s", tc_last_error());
@@ -898,9 +941,11 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     ConvW& up = e->upc[j];
     View upv = slice(pl.cat[l], 0, e->chans[l], esz);
     e->set_tag(2.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_fwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
-    if (tc_up_eligible(up.tc, cur.p, cur.ld, upv.p, upv.ld)) {
+    const Opnd co = opnd(e, cur);
+    if (tc_up_eligible(up.tc, co.p, co.ld, upv.p, upv.ld)) {
+      if ((rc = ensure_split(e, cur, (long long)B * (h / 2) * (w / 2)))) return rc;
       if (e->prof) e->prof_begin("tc_conv_kernel");
-      const int trc = tc_up_forward(up.tc, cur.p, cur.ld, upv.p, upv.ld, B, h / 2, w / 2, tdata(e, up.b_idx), e->stream, &e->cnt);
+      const int trc = tc_up_forward(up.tc, co.p, co.ld, upv.p, upv.ld, B, h / 2, w / 2, tdata(e, up.b_idx), e->stream, &e->cnt);
       if (e->prof) e->prof_end();
       if (trc)
         return e->fail(FU_ERR_CUDA, "tensor-core upconv launch failed: %s", tc_last_error());
@@ -1010,9 +1055,11 @@ int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, i
     e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (dx.C + dy.C)) * e->esz + 2.0 * cw.Cin * cw.Cout * cw.k * cw.k,
                "conv%d_dgrad %dx%d %d->%d", cw.k, H, W, cw.Cout, cw.Cin);
   }
-  if (tc_dgrad_eligible(cw.tc, dy.p, dy.ld, dx.p, dx.ld)) {
+  const Opnd dyo = opnd(e, dy);
+  if (tc_dgrad_eligible(cw.tc, dyo.p, dyo.ld, dx.p, dx.ld)) {
+    { const int src = ensure_split(e, dy, (long long)B * H * W); if (src) return src; }
     if (e->prof) e->prof_begin("tc_conv_kernel");
-    const int trc = tc_conv_dgrad(cw.tc, dy.p, dy.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt, stat);
+    const int trc = tc_conv_dgrad(cw.tc, dyo.p, dyo.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt, stat);
     if (e->prof) e->prof_end();
     if (trc)
       return e->fail(FU_ERR_CUDA, "tensor-core dgrad launch failed: %s", tc_last_error());
@@ -1034,9 +1081,12 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
     e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (x.C + dy.C)) * e->esz + 4.0 * cw.Cin * cw.Cout * cw.k * cw.k,
                "conv%d_wgrad %dx%d %d->%d", cw.k, H, W, cw.Cin, cw.Cout);
   }
-  if (tc_wgrad_eligible(cw.tc, x.p, x.ld, dy.p, dy.ld)) {
+  const Opnd xo = opnd(e, x), dyo = opnd(e, dy);
+  if (tc_wgrad_eligible(cw.tc, xo.p, xo.ld, dyo.p, dyo.ld)) {
+    // (twins are made on the main stream by the caller before this runs on the side stream: see prep_wgrad)
+    { int src = ensure_split(e, x, (long long)B * H * W); if (!src) src = ensure_split(e, dy, (long long)B * H * W); if (src) return src; }
     if (e->prof) e->prof_begin("tc_wgrad_kernel");
-    const int trc = tc_conv_wgrad(cw.tc, x.p, x.ld, dy.p, dy.ld, B, H, W, dw, e->stream, &e->cnt);
+    const int trc = tc_conv_wgrad(cw.tc, xo.p, xo.ld, dyo.p, dyo.ld, B, H, W, dw, e->stream, &e->cnt);
     if (e->prof) e->prof_end();
     if (trc)
       return e->fail(FU_ERR_CUDA, "tensor-core wgrad launch failed: %s", tc_last_error());
@@ -1082,6 +1132,8 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
   const long long P = (long long)B * H * W;
   int rc;
   if (blk.has_res) {
+    // parity_tc: twins are written on the main stream BEFORE the weight gradient is forked to the side stream
+    if (blk.res.tc.enabled && ((rc = ensure_split(e, x_in, P)) || (rc = ensure_split(e, g, P)))) return rc;
     {
       SideScope side(e);
       if ((rc = conv_wgrad<T>(e, blk.res, x_in, g, B, H, W, gptr(e, flat, blk.res.w_idx)))) return rc;
@@ -1114,6 +1166,7 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
     }
     e->deferred_sums.push_back({cw.bsum, gptr(e, flat, cw.b_idx), blk.C});
     View conv_in = (i == 0) ? x_in : (bn ? blk.z[i - 1] : blk.r[i - 1]);
+    if (cw.tc.enabled && ((rc = ensure_split(e, conv_in, P)) || (rc = ensure_split(e, blk.dy[i], P)))) return rc;
     {
       SideScope side(e);
       if ((rc = conv_wgrad<T>(e, cw, conv_in, blk.dy[i], B, H, W, gptr(e, flat, cw.w_idx)))) return rc;
@@ -1126,16 +1179,18 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
       // whose output this block consumed (no separate pass over the tensor)
       double* st = in_sums ? blk.dstat : nullptr;
       bool fused = false;
-      if (blk.has_res && tc_dgrad_eligible(cw.tc, blk.dy[0].p, blk.dy[0].ld, d_in->p, d_in->ld) &&
-          tc_dgrad_can_fuse_res(cw.tc, blk.res.tc, H, W, g.p, g.ld)) {
+      const Opnd dy0 = opnd(e, blk.dy[0]), go = opnd(e, g);
+      if (blk.has_res && tc_dgrad_eligible(cw.tc, dy0.p, dy0.ld, d_in->p, d_in->ld) &&
+          tc_dgrad_can_fuse_res(cw.tc, blk.res.tc, H, W, go.p, go.ld)) {
+        if ((rc = ensure_split(e, blk.dy[0], P)) || (rc = ensure_split(e, g, P))) return rc;
         // d_in = conv3x3^T(dy_0) + conv1x1^T(g) in ONE launch: the shortcut's data gradient rides along as extra,
         // centre-tap-only K chunks (no write + read-modify-write of d_in, one launch less)
         const double M = (double)B * H * W;
         e->set_tag(2.0 * M * cw.Cin * cw.Cout * 10.0, (M * (d_in->C + 2.0 * blk.C)) * e->esz, "conv3_dgrad %dx%d %d->%d",
                    H, W, cw.Cout, cw.Cin);
         if (e->prof) e->prof_begin("tc_conv_kernel");
-        const int trc = tc_conv_dgrad(cw.tc, blk.dy[0].p, blk.dy[0].ld, d_in->p, d_in->ld, B, H, W, 0, e->stream, &e->cnt,
-                                      st, &blk.res.tc, g.p, g.ld);
+        const int trc = tc_conv_dgrad(cw.tc, dy0.p, dy0.ld, d_in->p, d_in->ld, B, H, W, 0, e->stream, &e->cnt,
+                                      st, &blk.res.tc, go.p, go.ld);
         if (e->prof) e->prof_end();
         if (trc == 0) { fused = true; if (st && in_sums) *in_sums = true; }
         else if (trc != -2) return e->fail(FU_ERR_CUDA, "fused residual dgrad launch failed: %s", tc_last_error());
@@ -1165,7 +1220,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   struct SinkGuard { SinkGuard(TcBatch* b) { tc_batch() = b; } ~SinkGuard() { tc_batch() = nullptr; } } sink_guard(&e->batch);
   CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
   CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
-  if (e->cfg.precision == FU_PRECISION_BF16 && e->wgrad_scr_bytes > 512)
+  if (e->cfg.precision != FU_PRECISION_FP32 && e->wgrad_scr_bytes > 512)
     CUDA_TRY(e, cudaMemsetAsync(e->wgrad_scr, 0, e->wgrad_scr_bytes, e->stream));
   // ---- heads ----
   e->set_tag(0, 0, "heads_bwd");
@@ -1231,15 +1286,17 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     e->set_tag(4.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_bwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
     if (in_sums) e->deferred_sums.push_back({e->dec[j].dstat, gptr(e, flat, up.b_idx), e->chans[l]});   // channels [0,C) of d_cat
     else if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
-    if (tc_up_eligible(up.tc, u.p, u.ld, d_up.p, d_up.ld)) {
+    const Opnd uo = opnd(e, u), dupo = opnd(e, d_up);
+    if (tc_up_eligible(up.tc, uo.p, uo.ld, d_u.p, d_u.ld) && tc_ptr_ok(dupo.p, dupo.ld)) {
+      if ((rc = ensure_split(e, u, (long long)B * (h / 2) * (w / 2))) || (rc = ensure_split(e, d_up, (long long)B * h * w))) return rc;
       if (e->prof) e->prof_begin("tc_wgrad_kernel");
       int trc;
       {
         SideScope side(e);
-        trc = tc_up_wgrad(up.tc, u.p, u.ld, d_up.p, d_up.ld, B, h / 2, w / 2, gptr(e, flat, up.w_idx), e->stream, &e->cnt);
+        trc = tc_up_wgrad(up.tc, uo.p, uo.ld, dupo.p, dupo.ld, B, h / 2, w / 2, gptr(e, flat, up.w_idx), e->stream, &e->cnt);
       }
       if (e->prof) { e->prof_end(); e->prof_begin("tc_conv_kernel"); }
-      if (!trc) trc = tc_up_dgrad(up.tc, d_up.p, d_up.ld, d_u.p, d_u.ld, B, h / 2, w / 2, e->stream, &e->cnt);
+      if (!trc) trc = tc_up_dgrad(up.tc, dupo.p, dupo.ld, d_u.p, d_u.ld, B, h / 2, w / 2, e->stream, &e->cnt);
       if (e->prof) e->prof_end();
       if (trc) return e->fail(FU_ERR_CUDA, "tensor-core upconv backward failed: %s", tc_last_error());
       g = d_u;
@@ -1287,16 +1344,18 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
         ConvW& cw = e->downc[l - 1];
         if (in_sums) e->deferred_sums.push_back({e->enc[l].dstat, gptr(e, flat, cw.b_idx), cw.Cout});
         else if ((rc = channel_sum_to<T>(e, pl.d_down[l], (long long)B * h * w, cw.bsum, gptr(e, flat, cw.b_idx)))) return rc;
-        if (tc_down_eligible(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld)) {
+        const Opnd so = opnd(e, src), ddo = opnd(e, pl.d_down[l]);
+        if (tc_down_eligible(cw.tc, so.p, so.ld, d_src.p, d_src.ld) && tc_ptr_ok(ddo.p, ddo.ld)) {
+          if ((rc = ensure_split(e, src, 4ll * B * h * w)) || (rc = ensure_split(e, pl.d_down[l], (long long)B * h * w))) return rc;
           if (e->prof) e->prof_begin("tc_wgrad_kernel");
           int trc;
           {
             SideScope side(e);
-            trc = tc_down_wgrad(cw.tc, src.p, src.ld, pl.d_down[l].p, pl.d_down[l].ld, B, 2 * h, 2 * w,
+            trc = tc_down_wgrad(cw.tc, so.p, so.ld, ddo.p, ddo.ld, B, 2 * h, 2 * w,
                                 gptr(e, flat, cw.w_idx), e->stream, &e->cnt);
           }
           if (e->prof) { e->prof_end(); e->prof_begin("tc_conv_kernel"); }
-          if (!trc) trc = tc_down_dgrad(cw.tc, pl.d_down[l].p, pl.d_down[l].ld, d_src.p, d_src.ld, B, 2 * h, 2 * w, 1,
+          if (!trc) trc = tc_down_dgrad(cw.tc, ddo.p, ddo.ld, d_src.p, d_src.ld, B, 2 * h, 2 * w, 1,
                                         e->stream, &e->cnt);
           if (e->prof) e->prof_end();
           if (trc) return e->fail(FU_ERR_CUDA, "tensor-core downsample backward failed: %s", tc_last_error());
@@ -1335,7 +1394,8 @@ int validate(const fu_config* c, std::string& why) {
   if (c->num_lands < 0 || c->num_lands > 256) return bad("num_lands must be in [0,256]");
   if (c->block_depth < 1 || c->block_depth > 8) return bad("block_depth must be in [1,8]");
   if (c->num_lands > 0 && (c->lands_num_1x1 < 1 || c->lands_num_1x1 > 8)) return bad("lands_num_1x1 must be in [1,8]");
-  if (c->precision != FU_PRECISION_FP32 && c->precision != FU_PRECISION_BF16) return bad("precision must be FU_PRECISION_FP32 or FU_PRECISION_BF16");
+  if (c->precision != FU_PRECISION_FP32 && c->precision != FU_PRECISION_BF16 && c->precision != FU_PRECISION_FP32_TC)
+    return bad("precision must be FU_PRECISION_FP32, FU_PRECISION_BF16 or FU_PRECISION_FP32_TC");
   (void)buf;
   return FU_OK;
 }
@@ -1372,6 +1432,7 @@ int fu_engine_create(const fu_config* cfg, int device, fu_engine** out) {
   e->cfg = *cfg;
   e->device = device;
   e->esz = cfg->precision == FU_PRECISION_BF16 ? 2 : 4;
+  e->split = cfg->precision == FU_PRECISION_FP32_TC;
   e->num_sms = prop.multiProcessorCount;
   memset(&e->cnt, 0, sizeof(e->cnt));
   cudaSetDevice(device);
@@ -1387,6 +1448,7 @@ void fu_engine_destroy(fu_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   if (e->plan.arena) cudaFree(e->plan.arena);
+  if (e->plan.twin) cudaFree(e->plan.twin);
   if (e->wmem) cudaFree(e->wmem);
   if (e->dscr_fwd) cudaFree(e->dscr_fwd);
   if (e->dscr_bwd) cudaFree(e->dscr_bwd);
@@ -1446,6 +1508,7 @@ int fu_forward(fu_engine* e, const float* x, int B, int H, int W, int training, 
     e->packed_version = weights_version;
   }
   e->saved = false;
+  e->fresh_fwd.clear(); e->fresh_bwd.clear(); e->in_backward = false;
   if (e->cfg.precision == FU_PRECISION_BF16) rc = forward_t<bf16>(e, x, B, H, W, training, seg, logits, heat);
   else rc = forward_t<float>(e, x, B, H, W, training, seg, logits, heat);
   side_join(e);
@@ -1466,8 +1529,10 @@ int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* fl
   e->stream = reinterpret_cast<cudaStream_t>(stream);
   const int64_t l0 = e->cnt.kernel_launches;
   int rc;
+  e->fresh_bwd.clear(); e->in_backward = true;
   if (e->cfg.precision == FU_PRECISION_BF16) rc = backward_t<bf16>(e, d_seg, d_heat, flat_grads);
   else rc = backward_t<float>(e, d_seg, d_heat, flat_grads);
+  e->in_backward = false;
   side_join(e);                  // (already joined on the normal path; an error return may have left work on the side stream)
   if (rc) return rc;
   e->cnt.backward_calls++;

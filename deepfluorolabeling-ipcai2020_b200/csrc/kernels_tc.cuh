@@ -243,6 +243,13 @@ struct TcConvParams {
   int Cst;                      // channels of the scattered output tensor (N = 4*Cst)
   int cst_shift;                // log2(Cst): channel counts are powers of two (unet.py:86: 2**(wf+i)), so the per-chunk
                                 // (a,b) block / channel split is a shift and a mask
+  // split-bf16 x3 parity mode (kernel template F32 = true): fp32 values travel as bf16 pairs hi = bf16(v),
+  // lo = bf16(v - hi); the K loop runs three passes per channel chunk, (A_hi, W_hi), (A_hi, W_lo), (A_lo, W_hi),
+  // into the same fp32 accumulator (the dropped lo*lo term is ~2^-16 relative).  The A map spans the operand's
+  // split twin, whose lo half sits `a_lo` channels after the hi half; the weight map's K dimension is [hi | lo]
+  // with lo at `b_lo`.  Output and second epilogue operand are fp32.
+  int a_lo, b_lo;
+  const float* tf;              // (F32) second epilogue operand, fp32 NHWC with pixel stride t_ld
 };
 
 constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (wgrad kernels; the conv kernel has 4*G epilogue warps)
@@ -253,7 +260,7 @@ constexpr int kTc3Threads = 320;      // halo kernel: producer, MMA, 2 x 4 epilo
 // stage i % (2G), so up to 2G accumulators are in flight.  The 1x1 / 2x2 layers have 4-16 MMAs per tile and
 // are bound by the epilogue's per-warp latency chain (TMEM load, second-operand fetch, convert, staging
 // store, TMA store, statistics): four groups cut their time ~3x; the deep 3x3 layers keep G = 1 or 2.
-template <int G>
+template <int G, bool F32 = false>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcConvParams p) {
@@ -267,11 +274,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t staging_off = (uint32_t)p.stages * stage_bytes;
-  const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;
+  // F32: one 128-row x 32-column fp32 chunk (16 KB) per staging tile, always double buffered
+  const uint32_t staging_bytes = F32 ? 16384u : 128u * (uint32_t)p.BN * 2u;
   const int vlen = p.c5 ? p.Cst : p.N;                              // channels of the bias / bn vectors
-  const int nstg = p.nstaging;                                       // 1 or 2 staging tiles (double buffered stores)
+  const int nstg = F32 ? 2 : p.nstaging;                             // 1 or 2 staging tiles (double buffered stores)
   const uint32_t vec_off = staging_off + (uint32_t)(G * nstg) * staging_bytes;   // bias | bn_a | bn_b, [3][vlen] floats
-  const uint32_t bar_off = (vec_off + 3u * (uint32_t)vlen * 4u + 7u) & ~7u;
+  const uint32_t park_off = vec_off + 3u * (uint32_t)vlen * 4u;     // (F32) statistics partials [G][4][2][BN] floats
+  const uint32_t bar_off = (park_off + (F32 ? (uint32_t)(G * 8 * p.BN) * 4u : 0u) + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kTcMaxStages + s); };
@@ -332,6 +341,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         vec[2 * vlen + i] = p.bn_a ? p.bn_b[i] : 0.f;
       }
     }
+    if (F32) {
+      float* park = reinterpret_cast<float*>(smem + park_off);
+      for (int i = threadIdx.x; i < G * 8 * p.BN; i += blockDim.x) park[i] = 0.f;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -341,7 +354,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
   const int total_tiles = tiles_m * p.n_tiles;
   const int cchunks = p.Cin / p.KC;
-  const int k_iters = p.ksz * p.ksz * cchunks;
+  const int vchunks = F32 ? 3 * cchunks : cchunks;          // split mode: three passes per real channel chunk
+  const int k_iters = p.ksz * p.ksz * vchunks;
   const uint32_t a_tx = (uint32_t)(p.tw * p.th * p.tn) * row_bytes;
 
   auto decode = [&](int tile, int& w0, int& h0, int& n0, int& nb) {
@@ -361,7 +375,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int w0, h0, n0, nb;
         decode(tile, w0, h0, n0, nb);
         for (int kit = 0; kit < k_iters; ++kit) {
-          const int tap = kit / cchunks, c0 = (kit - tap * cchunks) * p.KC;
+          const int tap = kit / vchunks, vc = kit - tap * vchunks;
+          int c0 = vc * p.KC, cb0 = c0;
+          if (F32) {                       // pass 0: (hi, W_hi), pass 1: (hi, W_lo), pass 2: (lo, W_hi)
+            const int pass = vc / cchunks;
+            c0 = (vc - pass * cchunks) * p.KC;
+            cb0 = c0 + (pass == 1 ? p.b_lo : 0);
+            c0 += pass == 2 ? p.a_lo : 0;
+          }
           const int kh = tap / p.ksz, kw = tap - kh * p.ksz;
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           if (ptx::elect_one()) {
@@ -369,7 +390,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
             if (p.a5) ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kw, w0, kh, h0);
             else ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw - p.pad, h0 + kh - p.pad, n0);
-            ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), c0, tap, nb);
+            ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), cb0, tap, nb);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -464,6 +485,98 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ab = col >> p.cst_shift;
         return pix_c5 + (long long)(ab >> 1) * (2 * p.W) + (ab & 1);
       };
+      if constexpr (F32) {
+        // ---- fp32 output (parity mode): 32-column chunks through a double-buffered 16 KB staging tile ----
+        float* park = reinterpret_cast<float*>(smem + park_off) + grp * 8 * p.BN;     // [4 row groups][2][BN]
+        if (p.stat && nb != s_nb) {
+          if (s_nb >= 0) {
+            ptx::named_bar_sync(bar_id, 128);
+            for (int i = et; i < 2 * p.BN; i += 128) {
+              const int which = i / p.BN, c = i - which * p.BN;
+              float v = 0.f;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) { v += park[(r * 2 + which) * p.BN + c]; park[(r * 2 + which) * p.BN + c] = 0.f; }
+              atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
+            }
+            ptx::named_bar_sync(bar_id, 128);
+          }
+          s_nb = nb;
+        }
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_base = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
+        const bool t_on = p.tf != nullptr && valid;
+        for (int j = 0; j < p.BN / 32; ++j) {
+          uint32_t v[32];
+          ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
+          ptx::tmem_ld_wait();
+          const int col = nb + j * 32;
+          const int c0 = chunk_cb(col);
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(vec + c0 + i);
+            f[i] = __uint_as_float(v[i]) + b4.x; f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z; f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+          }
+          if (t_on) {
+            const float4* tp4 = reinterpret_cast<const float4*>(p.tf + chunk_pix(col) * p.t_ld + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t4 = tp4[i];
+              const int c = 4 * i;
+              f[c] += vec[vlen + c0 + c] * t4.x + vec[2 * vlen + c0 + c];
+              f[c + 1] += vec[vlen + c0 + c + 1] * t4.y + vec[2 * vlen + c0 + c + 1];
+              f[c + 2] += vec[vlen + c0 + c + 2] * t4.z + vec[2 * vlen + c0 + c + 2];
+              f[c + 3] += vec[vlen + c0 + c + 3] * t4.w + vec[2 * vlen + c0 + c + 3];
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = 0.f;
+          }
+          uint8_t* stg = smem + grp_staging_off + (uint32_t)sbuf * staging_bytes;
+          const uint32_t stg_addr = smem_base + grp_staging_off + (uint32_t)sbuf * staging_bytes;
+          if (et == 0) ptx::tma_store_wait_read1();       // the store issued two chunks ago has finished reading this tile
+          ptx::named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(stg + (uint32_t)row * 128u + (uint32_t)((g ^ (row & 7)) << 4)) =
+                make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(bar_id, 128);
+          if (et == 0) {
+            if (p.c5) {
+              const int ab = col >> p.cst_shift;
+              ptx::tma_store_5d(&tmC, stg_addr, col & (p.Cst - 1), ab & 1, w0, ab >> 1, h0);
+            } else {
+              ptx::tma_store_4d(&tmC, stg_addr, col, w0, h0, n0);
+            }
+            ptx::tma_store_commit();
+          }
+          if (p.stat) {
+            // column c of this chunk over 32 rows (rows outside the image hold zeros)
+            const int c = et & 31, rgp = et >> 5;
+            float a0 = 0.f, b0 = 0.f;
+#pragma unroll 8
+            for (int r = rgp * 32; r < rgp * 32 + 32; ++r) {
+              const float x = *reinterpret_cast<const float*>(stg + (uint32_t)r * 128u + (uint32_t)((((c >> 2) ^ (r & 7)) << 4) + (c & 3) * 4));
+              a0 += x; b0 = fmaf(x, x, b0);
+            }
+            park[(rgp * 2 + 0) * p.BN + j * 32 + c] += a0;
+            park[(rgp * 2 + 1) * p.BN + j * 32 + c] += b0;
+          }
+          sbuf ^= 1;
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(tempty_bar(acc));
+        acc += G; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
+        continue;
+      }
       if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
       // the second epilogue operand (residual / accumulate) is fetched before waiting for the accumulator,
       // so its global-memory latency hides behind the MMAs (BN <= 128: 16 x 16 B per thread)
@@ -588,7 +701,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (nstg == 2) { if (et == 0) ptx::tma_store_wait_read(); ptx::named_bar_sync(bar_id, 128); }
-    flush_stats();
+    if constexpr (F32) {
+      if (p.stat && s_nb >= 0) {
+        float* park = reinterpret_cast<float*>(smem + park_off) + grp * 8 * p.BN;
+        for (int i = et; i < 2 * p.BN; i += 128) {
+          const int which = i / p.BN, c = i - which * p.BN;
+          float v = 0.f;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) v += park[(r * 2 + which) * p.BN + c];
+          atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
+        }
+      }
+    } else {
+      flush_stats();
+    }
     if (et == 0) ptx::tma_store_wait_all();
   }
   ptx::tc_fence_before();
@@ -630,13 +756,17 @@ struct TcConv3Params {
   const float* bn_a; const float* bn_b;
   double* stat;
   long long* dbg;               // optional timeline buffer (FU_TC_DBG=1): [role][super][event] clock64 of CTA 0
+  // split-bf16 x3 parity mode (template F32 = true, see TcConvParams): lo-half offsets of the A / weight maps of
+  // both sources, fp32 second epilogue operand
+  int a_lo, b_lo, a2_lo, b2_lo;
+  const float* tf;
 };
 
 // S = epilogue sets.  A set is one group of 4 warps per pixel tile of the pair; super tile i of a CTA is drained
 // by set i % S from TMEM stage i % (2S).  The thin layers (BN <= 64: 18-72 MMAs per tile) are bound by the
 // epilogue's per-warp latency chain, not by the tensor pipe (FU_TC_DBG timeline: ~3600 cycles per super tile of
 // which the MMAs take 2000), so they run two sets.
-template <int S>
+template <int S, bool F32 = false>
 __global__ void __launch_bounds__(64 + 256 * S, 1)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
@@ -648,18 +778,25 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)p.KC * 2u;
   const uint32_t b_bytes = (uint32_t)p.BN * row_bytes;
-  const int cchunks = p.K / p.KC;
+  const int rchunks = p.K / p.KC;                                  // real channel chunks
+  // split mode: virtual chunk v = pass * rchunks + c; pass 0: (A_hi, W_hi), 1: (A_hi, W_lo), 2: (A_lo, W_hi)
+  const int cchunks = F32 ? 3 * rchunks : rchunks;
+  const int wchunks = F32 ? 2 * rchunks : rchunks;                 // distinct weight chunks (hi | lo)
+  auto a_coord = [&](int v, int lo) { return F32 ? (v % rchunks) * p.KC + (v / rchunks == 2 ? lo : 0) : v * p.KC; };
+  auto w_index = [&](int v) { return F32 ? (v / rchunks == 1 ? rchunks + v % rchunks : v % rchunks) : v; };
+  auto w_coord = [&](int wi, int lo) { return F32 ? (wi % rchunks) * p.KC + (wi >= rchunks ? lo : 0) : wi * p.KC; };
   const uint32_t a_stage_bytes = (uint32_t)p.npair * p.a_tile_bytes;
   const uint32_t a_off = 0;
   const uint32_t b_off = a_off + (uint32_t)p.a_stages * a_stage_bytes;
-  const int wtiles = cchunks * 9 + (p.res ? cchunks : 0);          // resident weight tiles: 9 taps (+ the 1x1) per chunk
+  const int wtiles = wchunks * 9 + (p.res ? wchunks : 0);          // resident weight tiles: 9 taps (+ the 1x1) per chunk
   const uint32_t b_region = p.resident ? (uint32_t)wtiles * b_bytes : (uint32_t)p.b_stages * b_bytes;
   const uint32_t staging_off = b_off + b_region;
-  const uint32_t staging_bytes = 128u * (uint32_t)p.BN * 2u;      // one per epilogue group
+  // F32: 128 rows x 32 fp32 columns (16 KB), two per epilogue group
+  const uint32_t staging_bytes = F32 ? 32768u : 128u * (uint32_t)p.BN * 2u;      // one per epilogue group
   constexpr int NACC = 2 * S;              // TMEM accumulator stages (each: npair tiles of BN columns)
   const uint32_t vec_off = staging_off + (uint32_t)(S * p.npair) * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
-  const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;    // [S*npair][2][BN] floats
-  const uint32_t bar_off = (stat_off + (uint32_t)(S * p.npair) * 2u * (uint32_t)p.BN * 4u + 7u) & ~7u;
+  const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;    // (F32) statistics partials [S*npair][4][2][BN] floats
+  const uint32_t bar_off = (stat_off + (uint32_t)(S * p.npair) * (F32 ? 8u : 2u) * (uint32_t)p.BN * 4u + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(8 + s); };
@@ -694,6 +831,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       vec[p.N + i] = p.bn_a ? p.bn_a[i] : 1.f;
       vec[2 * p.N + i] = p.bn_a ? p.bn_b[i] : 0.f;
     }
+    if (F32) {
+      float* park = reinterpret_cast<float*>(smem + stat_off);
+      for (int i = threadIdx.x; i < S * p.npair * 8 * p.BN; i += blockDim.x) park[i] = 0.f;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -724,12 +865,12 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     {
       if (p.resident && ptx::elect_one()) {
         ptx::mbar_expect_tx(res_bar, (uint32_t)wtiles * b_bytes);
-        for (int c = 0; c < cchunks; ++c)
+        for (int c = 0; c < wchunks; ++c)
           for (int tap = 0; tap < 9; ++tap)
-            ptx::tma_load_3d(smem_base + b_off + (uint32_t)(c * 9 + tap) * b_bytes, &tmB, res_bar, c * p.KC, tap, 0);
+            ptx::tma_load_3d(smem_base + b_off + (uint32_t)(c * 9 + tap) * b_bytes, &tmB, res_bar, w_coord(c, p.b_lo), tap, 0);
         if (p.res)
-          for (int c = 0; c < cchunks; ++c)
-            ptx::tma_load_3d(smem_base + b_off + (uint32_t)(cchunks * 9 + c) * b_bytes, &tmB2, res_bar, c * p.KC, 0, 0);
+          for (int c = 0; c < wchunks; ++c)
+            ptx::tma_load_3d(smem_base + b_off + (uint32_t)(wchunks * 9 + c) * b_bytes, &tmB2, res_bar, w_coord(c, p.b2_lo), 0, 0);
       }
       __syncwarp();
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
@@ -750,7 +891,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 int w0, h0, n;
                 decode_m(mt, w0, h0, n);
                 ptx::tma_load_4d(smem_base + a_off + (uint32_t)as * a_stage_bytes + (uint32_t)i * p.a_tile_bytes, &tmA,
-                                 a_full(as), c * p.KC, w0 - 1 + (p.halo1 ? 0 : g), h0 - 1, n);
+                                 a_full(as), a_coord(c, p.a_lo), w0 - 1 + (p.halo1 ? 0 : g), h0 - 1, n);
               }
             }
             __syncwarp();
@@ -761,7 +902,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 ptx::mbar_wait(b_empty(bs), bph ^ 1u);
                 if (ptx::elect_one()) {
                   ptx::mbar_expect_tx(b_full(bs), b_bytes);
-                  ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB, b_full(bs), c * p.KC, tap, nb);
+                  ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB, b_full(bs), w_coord(w_index(c), p.b_lo), tap, nb);
                 }
                 __syncwarp();
                 if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
@@ -783,7 +924,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 int w0, h0, n;
                 decode_m(mt, w0, h0, n);
                 ptx::tma_load_4d(smem_base + a_off + (uint32_t)as * a_stage_bytes + (uint32_t)i * p.a_tile_bytes, &tmA2,
-                                 a_full(as), c * p.KC, w0 - 1, h0 - 1, n);
+                                 a_full(as), a_coord(c, p.a2_lo), w0 - 1, h0 - 1, n);
               }
             }
             __syncwarp();
@@ -792,7 +933,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               ptx::mbar_wait(b_empty(bs), bph ^ 1u);
               if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(b_full(bs), b_bytes);
-                ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB2, b_full(bs), c * p.KC, 0, nb);
+                ptx::tma_load_3d(smem_base + b_off + (uint32_t)bs * b_bytes, &tmB2, b_full(bs), w_coord(w_index(c), p.b2_lo), 0, nb);
               }
               __syncwarp();
               if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
@@ -839,7 +980,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (resident) {
               // all 9 taps straight from the resident weight region: one elected section per A stage
               if (ptx::elect_one()) {
-                const uint64_t b_desc0 = dbase + (uint64_t)((smem_base + b_off + (uint32_t)(c * 9) * b_bytes) >> 4);
+                const uint64_t b_desc0 = dbase + (uint64_t)((smem_base + b_off + (uint32_t)(w_index(c) * 9) * b_bytes) >> 4);
 #pragma unroll
                 for (int tt = 0; tt < 9; ++tt) {
                   if (!halo1 && (tt % 3) != g) continue;        // one A load per kw: only taps with kw == g
@@ -912,7 +1053,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (ptx::elect_one()) {
               const uint64_t ad = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4) +
                                   (uint64_t)((uint32_t)((p.twb + 1) * row_bytes) >> 4);      // view (kh,kw) = (1,1)
-              const uint32_t b_addr = resident ? smem_base + b_off + (uint32_t)(cchunks * 9 + c) * b_bytes
+              const uint32_t b_addr = resident ? smem_base + b_off + (uint32_t)(wchunks * 9 + w_index(c)) * b_bytes
                                                : smem_base + b_off + (uint32_t)bs * b_bytes;
               const uint64_t bd = dbase + (uint64_t)(b_addr >> 4);
               for (int j = 0; j < ksteps; ++j) {
@@ -984,6 +1125,97 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int nt = st % p.n_tiles, sp = st / p.n_tiles;
         const int nb = nt * p.BN;
         const int mt = sp * p.npair + grp;
+        if constexpr (F32) {
+          // ---- fp32 output (parity mode): 32-column chunks through two 16 KB staging tiles ----
+          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * 8 * p.BN;      // [4 row groups][2][BN]
+          if (p.stat && nb != s_nb) {
+            if (s_nb >= 0) {
+              ptx::named_bar_sync(bar_id, 128);
+              for (int i = et; i < 2 * p.BN; i += 128) {
+                const int which = i / p.BN, c = i - which * p.BN;
+                float v = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { v += park[(r * 2 + which) * p.BN + c]; park[(r * 2 + which) * p.BN + c] = 0.f; }
+                atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
+              }
+              ptx::named_bar_sync(bar_id, 128);
+            }
+            s_nb = nb;
+          }
+          ptx::mbar_wait(t_full(acc), acc_phase);
+          ptx::tc_fence_after();
+          if (mt < m_tiles) {
+            int w0, h0, n;
+            decode_m(mt, w0, h0, n);
+            const bool valid = row_ok && (w0 + wq) < p.W && (h0 + hi) < p.H;
+            const long long pix = ((long long)n * p.H + (h0 + hi)) * p.W + (w0 + wq);
+            const uint32_t t_base = tmem_base + (uint32_t)((acc * p.npair + grp) * p.BN) + ((uint32_t)(q * 32) << 16);
+            for (int j = 0; j < p.BN / 32; ++j) {
+              uint32_t v[32];
+              ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
+              ptx::tmem_ld_wait();
+              const int c0 = nb + j * 32;
+              float f[32];
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(vec + c0 + k);
+                f[k] = __uint_as_float(v[k]) + b4.x; f[k + 1] = __uint_as_float(v[k + 1]) + b4.y;
+                f[k + 2] = __uint_as_float(v[k + 2]) + b4.z; f[k + 3] = __uint_as_float(v[k + 3]) + b4.w;
+              }
+              if (p.tf && valid) {
+                const float4* tp4 = reinterpret_cast<const float4*>(p.tf + pix * p.t_ld + c0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float4 t4 = tp4[k];
+                  const int c = 4 * k;
+                  f[c] += vec[p.N + c0 + c] * t4.x + vec[2 * p.N + c0 + c];
+                  f[c + 1] += vec[p.N + c0 + c + 1] * t4.y + vec[2 * p.N + c0 + c + 1];
+                  f[c + 2] += vec[p.N + c0 + c + 2] * t4.z + vec[2 * p.N + c0 + c + 2];
+                  f[c + 3] += vec[p.N + c0 + c + 3] * t4.w + vec[2 * p.N + c0 + c + 3];
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
+              }
+              uint8_t* stg = staging + (uint32_t)(j & 1) * 16384u;
+              if (et == 0) ptx::tma_store_wait_read1();
+              ptx::named_bar_sync(bar_id, 128);
+              if (row_ok) {
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4)
+                  *reinterpret_cast<float4*>(stg + (uint32_t)mr * 128u + (uint32_t)((g4 ^ (mr & 7)) << 4)) =
+                      valid ? make_float4(f[4 * g4], f[4 * g4 + 1], f[4 * g4 + 2], f[4 * g4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              ptx::fence_proxy_async_smem();
+              ptx::named_bar_sync(bar_id, 128);
+              if (et == 0) {
+                ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)(j & 1) * 16384u, c0, w0, h0, n);
+                ptx::tma_store_commit();
+              }
+              if (p.stat) {
+                const int c = et & 31, rgp = et >> 5;
+                float a0 = 0.f, b0 = 0.f;
+#pragma unroll 8
+                for (int r = rgp * 32; r < rgp * 32 + 32; ++r) {
+                  if (r < rows_valid) {
+                    const float x = *reinterpret_cast<const float*>(stg + (uint32_t)r * 128u + (uint32_t)((((c >> 2) ^ (r & 7)) << 4) + (c & 3) * 4));
+                    a0 += x; b0 = fmaf(x, x, b0);
+                  }
+                }
+                park[(rgp * 2 + 0) * p.BN + j * 32 + c] += a0;
+                park[(rgp * 2 + 1) * p.BN + j * 32 + c] += b0;
+              }
+            }
+            // an odd chunk count would leave the buffer parity out of step with `j & 1`; BN is 32, 64 or 128 and a single
+            // chunk (BN = 32) always uses buffer 0: drain before the next tile reuses it
+            if (p.BN == 32) { if (et == 0) ptx::tma_store_wait_read(); ptx::named_bar_sync(bar_id, 128); }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(t_empty(acc));
+          acc += S; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
+          continue;
+        }
         if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
         ptx::mbar_wait(t_full(acc), acc_phase);
@@ -1084,7 +1316,21 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 3);
         }
       }
-      flush_stats();
+      if constexpr (F32) {
+        if (p.stat && s_nb >= 0) {
+          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * 8 * p.BN;
+          ptx::named_bar_sync(bar_id, 128);
+          for (int i = et; i < 2 * p.BN; i += 128) {
+            const int which = i / p.BN, c = i - which * p.BN;
+            float v = 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v += park[(r * 2 + which) * p.BN + c];
+            atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
+          }
+        }
+      } else {
+        flush_stats();
+      }
       if (et == 0) ptx::tma_store_wait_all();
     }
   }
@@ -1154,6 +1400,9 @@ struct TcWgradParams {
   int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1): drop the accumulators instead of adding them
   int m64;                      // 0: M = 128 MMAs; 1/2: M = 64 (out-channels <= 64), value = TMEM row layout (see epilogue)
   int b5;                       // B operand gathered with stride 2 (5-D map), taps = 2x2, pixel grid (W, H), B = 1
+  // split-bf16 x3 parity mode: every pixel tile is visited three times, (dY_hi, X_hi), (dY_hi, X_lo), (dY_lo, X_hi);
+  // y_lo / x_lo are the channel offsets of the lo halves in the two (twin) maps
+  int split, y_lo, x_lo;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -1189,7 +1438,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const int per = (total_pt + p.splits - 1) / p.splits;
   const int pt_begin = split * per;
   const int pt_end = min(total_pt, pt_begin + per);
-  const int n_iters = max(pt_end - pt_begin, 0);
+  const int npass = p.split ? 3 : 1;
+  const int n_iters = max(pt_end - pt_begin, 0) * npass;
   const int nblk_a = (p.Cout - co0 > 64) ? 2 : 1;
 
   if (threadIdx.x == 0) {
@@ -1208,7 +1458,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     // whole warp loops, one elected lane issues the TMA loads
     int stage = 0; uint32_t phase = 0;
     for (int it = 0; it < n_iters; ++it) {
-      int pt = pt_begin + it;
+      int pt = pt_begin + it / npass;
+      const int pass = it % npass;
+      const int yoff = co0 + (pass == 2 ? p.y_lo : 0), xoff = ci0 + (pass == 1 ? p.x_lo : 0);
       const int w0 = (pt % p.tiles_w) * p.tw; pt /= p.tiles_w;
       const int h0 = (pt % p.tiles_h) * p.th; pt /= p.tiles_h;
       const int n0 = pt * p.tn;
@@ -1217,13 +1469,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
         ptx::mbar_expect_tx(full_bar(stage), (uint32_t)nblk_a * kBox + b_bytes);
         for (int blk = 0; blk < nblk_a; ++blk)
-          ptx::tma_load_4d(a_dst + (uint32_t)blk * kBox, &tmY, full_bar(stage), co0 + blk * 64, w0, h0, n0);
+          ptx::tma_load_4d(a_dst + (uint32_t)blk * kBox, &tmY, full_bar(stage), yoff + blk * 64, w0, h0, n0);
         for (int t = 0; t < p.taps_per_cta; ++t) {
           const int kh = p.ksz > 1 ? grp : 0, kw = p.ksz > 1 ? t : 0;
           for (int blk = 0; blk < nblk_b; ++blk) {
             const uint32_t dst = a_dst + a_bytes + (uint32_t)(t * nblk_b + blk) * kBox;
-            if (p.b5) ptx::tma_load_5d(dst, &tmX, full_bar(stage), ci0 + blk * 64, kw, w0, kh, h0);
-            else ptx::tma_load_4d(dst, &tmX, full_bar(stage), ci0 + blk * 64, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+            if (p.b5) ptx::tma_load_5d(dst, &tmX, full_bar(stage), xoff + blk * 64, kw, w0, kh, h0);
+            else ptx::tma_load_4d(dst, &tmX, full_bar(stage), xoff + blk * 64, w0 + kw - p.pad, h0 + kh - p.pad, n0);
           }
         }
       }
@@ -1295,6 +1547,7 @@ struct TcWgrad3Params {
   int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1)
   int m64;                      // see TcWgradParams
   float* dw_acc;                // [9][Cout][Cin] fp32, zeroed by the caller
+  int split, y_lo, x_lo;        // see TcWgradParams
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -1331,7 +1584,8 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   const int per = (total_kt + p.splits - 1) / p.splits;
   const int kt_begin = split * per;
   const int kt_end = min(total_kt, kt_begin + per);
-  const int n_iters = max(kt_end - kt_begin, 0);
+  const int npass = p.split ? 3 : 1;
+  const int n_iters = max(kt_end - kt_begin, 0) * npass;
   const int nblk_a = (p.Cout - co0 > 64) ? 2 : 1;
   const int kh0 = p.tpg == 9 ? 0 : grp;                     // first filter row held by this CTA
 
@@ -1352,7 +1606,9 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const uint32_t a_tx = (uint32_t)nblk_a * (uint32_t)p.tw * 128u;
     const uint32_t b_tx = (uint32_t)nblk_b * (uint32_t)((p.tw + 2) * nrows) * brow;
     for (int it = 0; it < n_iters; ++it) {
-      int kt = kt_begin + it;
+      int kt = kt_begin + it / npass;
+      const int pass = it % npass;
+      const int yoff = co0 + (pass == 2 ? p.y_lo : 0), xoff = ci0 + (pass == 1 ? p.x_lo : 0);
       const int w0 = (kt % p.segs) * p.tw; kt /= p.segs;
       const int h = kt % p.H;
       const int n = kt / p.H;
@@ -1361,9 +1617,9 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
         ptx::mbar_expect_tx(full_bar(stage), a_tx + b_tx);
         for (int blk = 0; blk < nblk_a; ++blk)
-          ptx::tma_load_4d(a_dst + (uint32_t)blk * kABox, &tmY, full_bar(stage), co0 + blk * 64, w0, h, n);
+          ptx::tma_load_4d(a_dst + (uint32_t)blk * kABox, &tmY, full_bar(stage), yoff + blk * 64, w0, h, n);
         for (int blk = 0; blk < nblk_b; ++blk)
-          ptx::tma_load_4d(a_dst + a_bytes + (uint32_t)blk * b_box_bytes, &tmX, full_bar(stage), ci0 + blk * p.cb, w0 - 1,
+          ptx::tma_load_4d(a_dst + a_bytes + (uint32_t)blk * b_box_bytes, &tmX, full_bar(stage), xoff + blk * p.cb, w0 - 1,
                            h - 1 + kh0, n);
       }
       __syncwarp();
@@ -1443,6 +1699,42 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------
+// Split-bf16 twin of an fp32 NHWC tensor (parity mode): hi = bf16(v) at dst[pix*dld + c], lo = bf16(v - hi) at
+// dst[pix*dld + dlo + c].  The twin of a buffer with fp32 pixel stride ld has dld = 2*ld and dlo = ld, i.e. it
+// occupies the same bytes per pixel, and a channel slice of the buffer maps to the same slice of either half.
+// hi + lo carries 16 mantissa bits of v; the three products hi*hi' + hi*lo' + lo*hi' of two split operands are
+// exact in the tensor core's fp32 accumulation, so a GEMM over twins differs from the fp32 one by ~2^-16 per term.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ src, int ld, int C, bf16* __restrict__ dst,
+                                                        int dld, int dlo, long long P) {
+  const int cv = C >> 2;                       // 4-channel vectors per pixel
+  const long long total = P * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c = (int)(i - pix * cv) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + pix * ld + c);
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    uint2 hh, ll;
+    hh.x = *reinterpret_cast<const uint32_t*>(&h0); hh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ll.x = *reinterpret_cast<const uint32_t*>(&l0); ll.y = *reinterpret_cast<const uint32_t*>(&l1);
+    bf16* d = dst + pix * dld + c;
+    *reinterpret_cast<uint2*>(d) = hh;
+    *reinterpret_cast<uint2*>(d + dlo) = ll;
+  }
+}
+inline int tc_split(const float* src, int ld, int C, bf16* dst, int dld, int dlo, long long P, int sms, cudaStream_t stream,
+                    fu_counters* cnt) {
+  long long blocks = (P * (C / 4) + 255) / 256;
+  if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+  if (blocks < 1) blocks = 1;
+  split_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, ld, C, dst, dld, dlo, P);
+  if (cnt) cnt->kernel_launches++;
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------
 // Weight repacking, batched: ONE launch per step packs every tensor-core layer's fp32 torch weights into the
 // two bf16 GEMM layouts, and ONE launch at the end of backward turns every [taps][M][N] fp32 weight-gradient
 // accumulator into the torch layout.  (The per-layer versions were 92 launches and 0.64 ms per step, most of
@@ -1461,6 +1753,8 @@ struct TcPackJob {
   const float* w; bf16* out1; bf16* out2;
   int R, Cc, taps;
   long long a1, b1, a2, b2, base2;
+  long long lo1, lo2;           // split-bf16 parity mode (0: off): the residual bf16(w - hi) is written lo1 / lo2 elements
+                                // after the hi value (the GEMM K dimension of both layouts is [hi | lo])
 };
 struct TcUnpackJob {
   const float* acc;             // [taps][M][N] fp32
@@ -1498,12 +1792,22 @@ __device__ __forceinline__ void tc_pack_tile(const TcPackJob& J, int lb, float* 
   for (int r = wrp; r < 32; r += 8) {           // out1: (t, c) per row, c contiguous
     bf16* dst = J.out1 + (long long)(r0 + r) * J.a1 + c0 + lane;
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) dst[(long long)t * J.b1] = __float2bfloat16_rn(tile[r * 289 + lane * TAPS + t]);
+    for (int t = 0; t < TAPS; ++t) {
+      const float v = tile[r * 289 + lane * TAPS + t];
+      const bf16 h = __float2bfloat16_rn(v);
+      dst[(long long)t * J.b1] = h;
+      if (J.lo1) dst[(long long)t * J.b1 + J.lo1] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
   }
   for (int c = wrp; c < 32; c += 8) {           // out2: (t, r) per column, r contiguous
     bf16* dst = J.out2 + J.base2 + (long long)(c0 + c) * J.a2 + r0 + lane;
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) dst[(long long)t * J.b2] = __float2bfloat16_rn(tile[lane * 289 + c * TAPS + t]);
+    for (int t = 0; t < TAPS; ++t) {
+      const float v = tile[lane * 289 + c * TAPS + t];
+      const bf16 h = __float2bfloat16_rn(v);
+      dst[(long long)t * J.b2] = h;
+      if (J.lo2) dst[(long long)t * J.b2 + J.lo2] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
   }
 }
 
@@ -1635,7 +1939,7 @@ inline CUtensorMapSwizzle tc_swizzle_for(int inner_bytes) {
 
 // bf16 tensor map over up to 4 dims; dims[0] is the contiguous (channel) dim, strides in elements
 inline int tc_make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
-                       const int* box, int inner_bytes) {
+                       const int* box, int inner_bytes, bool f32 = false) {
   PFN_encodeTiled fn = tc_encode_fn();
   if (!fn) { tc_err() = "cuTensorMapEncodeTiled entry point not available"; return -1; }
   cuuint64_t gdim[5], gstr[5];
@@ -1644,9 +1948,9 @@ inline int tc_make_map(CUtensorMap* m, const void* base, int rank, const long lo
     gdim[i] = (cuuint64_t)dims[i];
     bx[i] = (cuuint32_t)box[i];
     es[i] = 1;
-    if (i > 0) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 2ull;
+    if (i > 0) gstr[i - 1] = (cuuint64_t)strides_elems[i] * (f32 ? 4ull : 2ull);
   }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle_for(inner_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1678,6 +1982,8 @@ inline void tc_pick_tile(int B, int H, int W, int& tw, int& th, int& tn) {
 
 struct TcConv {
   bool enabled = false;
+  bool split = false;        // split-bf16 x3 parity mode: fp32 tensors, operands read from their [hi | lo] bf16 twins
+                             // (pointer = hi half, pixel stride = 2 * fp32 stride, lo half = stride / 2 elements on)
   int Cin = 0, Cout = 0, k = 0;
   int kind = 0;              // 0: Conv2d 3x3/1x1 stride 1; 1: Conv2d 2x2 stride 2; 2: ConvTranspose2d 2x2 stride 2
   bf16* w_fwd = nullptr;     // [Cout][taps][Cin]
@@ -1695,12 +2001,12 @@ struct TcConv {
   std::vector<W3Cached> w3cache;
   struct Cached3 {
     const void *x, *y, *x2; int x_ld, y_ld, x2_ld, B, H, W, dir;     // x2: second source of the fused residual dgrad (or null)
-    CUtensorMap a, b, c, a2, b2; TcConv3Params p; int grid; size_t smem; int S;
+    CUtensorMap a, b, c, a2, b2; TcConv3Params p; int grid; size_t smem; int S; int f32;
   };
   std::vector<Cached3> cache3;
   struct Cached {
     const void *x, *y; int x_ld, y_ld, B, H, W, dir;   // H, W: spatial dims of the GEMM's pixel grid
-    CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem; int G;
+    CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem; int G; int f32;
   };
   std::vector<Cached> cache;
 };
@@ -1715,16 +2021,16 @@ inline int tc_bn_max() {
   return v;
 }
 
-inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool enabled, Bump& w, Bump& ws) {
-  t.Cin = Cin; t.Cout = Cout; t.k = k;
+inline void tc_carve(TcConv& t, int Cin, int Cout, int k, bool transposed, bool enabled, Bump& w, Bump& ws, bool split = false) {
+  t.Cin = Cin; t.Cout = Cout; t.k = k; t.split = split;
   t.kind = transposed ? 2 : (k == 2 ? 1 : 0);
   t.enabled = enabled && (k == 3 || k == 1 || k == 2) && (Cin % 32 == 0) && (Cout % 32 == 0) &&
               getenv("FU_TC_DISABLE") == nullptr;
   if (t.kind != 0 && getenv("FU_TC_NO_UPDOWN") != nullptr) t.enabled = false;
   if (!t.enabled) return;
   const size_t n = (size_t)Cin * Cout * k * k;
-  t.w_fwd = w.take<bf16>(n);
-  t.w_dgrad = w.take<bf16>(n);
+  t.w_fwd = w.take<bf16>(split ? 2 * n : n);
+  t.w_dgrad = w.take<bf16>(split ? 2 * n : n);
   t.dw_acc = ws.take<float>(n);
   t.cache.clear();
   t.cache3.clear();
@@ -1737,20 +2043,25 @@ inline int tc_pack(TcConv& t, const float* w, cudaStream_t stream, fu_counters* 
   TcPackJob j;
   memset(&j, 0, sizeof(j));
   j.w = w;
-  const long long Ci = t.Cin, Co = t.Cout;
+  // K widths of the two GEMMs: doubled to [hi | lo] in split mode
+  const long long s = t.split ? 2 : 1;
+  const long long Ci = t.Cin * s, Co = t.Cout * s;
   if (t.kind == 0) {            // W[co][ci][tap]
     const int taps = t.k * t.k;
     j.R = t.Cout; j.Cc = t.Cin; j.taps = taps;
     j.out1 = t.w_fwd; j.a1 = taps * Ci; j.b1 = Ci;                                   // [co][tap][ci]
     j.out2 = t.w_dgrad; j.a2 = taps * Co; j.b2 = -Co; j.base2 = (taps - 1) * Co;     // [ci][flip tap][co]
+    if (t.split) { j.lo1 = t.Cin; j.lo2 = t.Cout; }
   } else if (t.kind == 1) {     // W[co][ci][ab]
     j.R = t.Cout; j.Cc = t.Cin; j.taps = 4;
     j.out1 = t.w_fwd; j.a1 = 4 * Ci; j.b1 = Ci;                                      // gather conv: [co][ab][ci]
-    j.out2 = t.w_dgrad; j.a2 = Co; j.b2 = Ci * Co; j.base2 = 0;                      // scatter GEMM: [(ab,ci)][co]
+    j.out2 = t.w_dgrad; j.a2 = Co; j.b2 = (long long)t.Cin * Co; j.base2 = 0;        // scatter GEMM: [(ab,ci)][co]
+    if (t.split) { j.lo1 = t.Cin; j.lo2 = t.Cout; }
   } else {                      // W[ci][co][ab]
     j.R = t.Cin; j.Cc = t.Cout; j.taps = 4;
     j.out1 = t.w_dgrad; j.a1 = 4 * Co; j.b1 = Co;                                    // gather conv over dY: [ci][ab][co]
-    j.out2 = t.w_fwd; j.a2 = Ci; j.b2 = Co * Ci; j.base2 = 0;                        // scatter GEMM: [(ab,co)][ci]
+    j.out2 = t.w_fwd; j.a2 = Ci; j.b2 = (long long)t.Cout * Ci; j.base2 = 0;         // scatter GEMM: [(ab,co)][ci]
+    if (t.split) { j.lo1 = t.Cout; j.lo2 = t.Cin; }
   }
   j.nblocks = (j.R / 32) * (j.Cc / 32);
   if (tc_batch()) { tc_batch()->pack.push_back(j); return 0; }
@@ -1789,6 +2100,15 @@ inline int tc_pick_groups(int BN, int k_iters, int ksteps) {
 }
 
 inline bool tc_ptr_ok(const void* p, int ld) { return p && (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 8 == 0); }
+// fp32 tensor (output / second epilogue operand of the split mode)
+inline bool tc_ptr_ok_f32(const void* p, int ld) { return p && (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0); }
+// set the second epilogue operand of a launch description for either storage mode
+template <typename P>
+inline void tc_set_t(const TcConv& t, P& p, const void* tp, int t_ld) {
+  p.t = t.split ? nullptr : reinterpret_cast<const bf16*>(tp);
+  p.tf = t.split ? reinterpret_cast<const float*>(tp) : nullptr;
+  p.t_ld = t_ld;
+}
 
 // Build (or fetch) the launch description: dir 0 = forward (A has Cin channels, N = Cout), dir 1 = data
 // gradient (A has Cout channels, N = Cin).
@@ -1798,7 +2118,7 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
       return &c;
   TcConv::Cached c;
   memset(&c, 0, sizeof(c));
-  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = H; c.W = W; c.dir = dir;
+  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = H; c.W = W; c.dir = dir; c.f32 = t.split ? 1 : 0;
   TcConvParams& p = c.p;
   const int K = dir == 0 ? t.Cin : t.Cout;
   const int N = dir == 0 ? t.Cout : t.Cin;
@@ -1824,14 +2144,16 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   if (getenv("FU_TC_BN_MAX") == nullptr)
     while (bn > 32 && (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / bn) * 10 < 6ll * sms) bn >>= 1;
   p.BN = bn;
-  p.CS = bn >= 64 ? 64 : 32;
+  p.CS = (bn >= 64 && !t.split) ? 64 : 32;
   p.n_tiles = N / p.BN;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
   p.nstaging = p.BN <= 64 ? 2 : 1;
-  c.G = tc_pick_groups(p.BN, t.k * t.k * (K / p.KC), p.KC / 16);
-  const size_t staging = (size_t)c.G * p.nstaging * 128 * p.BN * 2;
+  c.G = tc_pick_groups(p.BN, t.k * t.k * (K / p.KC) * (t.split ? 3 : 1), p.KC / 16);
+  if (t.split && c.G > 2) c.G = 2;
+  const size_t staging = t.split ? (size_t)c.G * 2 * 16384 + (size_t)c.G * 8 * p.BN * 4 : (size_t)c.G * p.nstaging * 128 * p.BN * 2;
   const size_t fixed = 1024 /*alignment slack*/ + staging + (size_t)12 * N + 16 + 8 * (2 * kTcMaxStages + 18);
   const size_t budget = 227 * 1024;
+  p.a_lo = t.split ? x_ld / 2 : 0; p.b_lo = t.split ? K : 0;
   int stages = (int)((budget - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   if (stages < 2) { tc_err() = "tile does not fit shared memory"; return nullptr; }
@@ -1839,27 +2161,28 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   c.smem = fixed + (size_t)stages * stage_bytes;
   const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   c.grid = (int)(total_tiles < sms ? total_tiles : sms);
-  // A: activation (K channels, W, H, B)
+  // A: activation (K channels, W, H, B); split mode: the twin's [hi | lo] halves are one channel range
   {
-    long long dims[4] = {K, W, H, B};
+    long long dims[4] = {K + p.a_lo, W, H, B};
     long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
     int box[4] = {p.KC, p.tw, p.th, p.tn};
     if (tc_make_map(&c.a, x, 4, dims, str, box, p.KC * 2)) return nullptr;
   }
-  // B: weights [N][taps][K]
+  // B: weights [N][taps][K]  (split: [N][taps][hi K | lo K])
   {
     const int taps = t.k * t.k;
-    long long dims[3] = {K, taps, N};
-    long long str[3] = {1, K, (long long)taps * K};
+    const long long Kw = t.split ? 2 * K : K;
+    long long dims[3] = {Kw, taps, N};
+    long long str[3] = {1, Kw, (long long)taps * Kw};
     int box[3] = {p.KC, 1, p.BN};
     if (tc_make_map(&c.b, dir == 0 ? t.w_fwd : t.w_dgrad, 3, dims, str, box, p.KC * 2)) return nullptr;
   }
-  // C: output (N channels, W, H, B)
+  // C: output (N channels, W, H, B), bf16 or (split) fp32
   {
     long long dims[4] = {N, W, H, B};
     long long str[4] = {1, y_ld, (long long)W * y_ld, (long long)H * W * y_ld};
     int box[4] = {p.CS, p.tw, p.th, p.tn};
-    if (tc_make_map(&c.c, y, 4, dims, str, box, p.CS * 2)) return nullptr;
+    if (tc_make_map(&c.c, y, 4, dims, str, box, t.split ? 128 : p.CS * 2, t.split)) return nullptr;
   }
   t.cache.push_back(c);
   return &t.cache.back();
@@ -1867,11 +2190,12 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
 
 // 5-D view of an NHWC tensor (B, 2*Hg, 2*Wg, C) as (C, 2, Wg, 2, B*Hg): element (c, b, j, a, r) is
 // pixel (row 2*(r % Hg) + a of image r / Hg, column 2j + b).  Rows of consecutive images are contiguous.
-inline int tc_make_s2_map(CUtensorMap* m, const void* base, int C, int ld, int Wg, long long Rg, int box_c, int tw, int th) {
+inline int tc_make_s2_map(CUtensorMap* m, const void* base, int C, int ld, int Wg, long long Rg, int box_c, int tw, int th,
+                          bool f32 = false) {
   long long dims[5] = {C, 2, Wg, 2, Rg};
   long long str[5] = {1, ld, 2ll * ld, 2ll * Wg * ld, 4ll * Wg * ld};
   int box[5] = {box_c, 1, tw, 1, th};
-  return tc_make_map(m, base, 5, dims, str, box, box_c * 2);
+  return tc_make_map(m, base, 5, dims, str, box, box_c * (f32 ? 4 : 2), f32);
 }
 
 // Strided layers.  gather = 1: y(Wg,Rg) = sum over the 2x2 taps of x(2Wg,2Rg)  (Conv2d k2s2 forward, ConvT dgrad)
@@ -1884,7 +2208,7 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
       return &c;
   TcConv::Cached c;
   memset(&c, 0, sizeof(c));
-  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = Hg; c.W = Wg; c.dir = dir;
+  c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = Hg; c.W = Wg; c.dir = dir; c.f32 = t.split ? 1 : 0;
   TcConvParams& p = c.p;
   const long long Rg = (long long)B * Hg;
   p.B = 1; p.H = (int)Rg; p.W = Wg; p.Cin = K; p.N = N;
@@ -1896,15 +2220,16 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   }
   p.KC = (K % 64 == 0) ? 64 : 32;
   int bn = tc_bn_max();
+  p.a_lo = t.split ? x_ld / 2 : 0; p.b_lo = t.split ? K : 0;
   if (gather) {
     while (N % bn) bn >>= 1;
     p.BN = bn;
-    p.CS = bn >= 64 ? 64 : 32;
+    p.CS = (bn >= 64 && !t.split) ? 64 : 32;
   } else {
     // scatter: N = 4*Cst columns (a,b,co).  One N tile covers as many whole (a,b) blocks as fit 128 columns, so the
     // A tile is read once for all of them; a store box (CS channels) never straddles two blocks.
     while (Cst % bn) bn >>= 1;                                   // bn <= Cst, divides it
-    p.CS = bn >= 64 ? 64 : 32;
+    p.CS = (bn >= 64 && !t.split) ? 64 : 32;
     // (not when the epilogue also reads the old output, i.e. the accumulating downsample data gradient: there the
     //  wider tile's per-chunk second-operand fetches cost more than the A re-reads save -- measured in the step)
     if (merge && tc_env_int("FU_TC_SCATTER_MERGE", 1)) while (bn * 2 <= 128 && N % (bn * 2) == 0) bn *= 2;
@@ -1916,8 +2241,9 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   p.n_tiles = N / p.BN;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
   p.nstaging = p.BN <= 64 ? 2 : 1;
-  c.G = tc_pick_groups(p.BN, (gather ? 4 : 1) * (K / p.KC), p.KC / 16);
-  const size_t staging = (size_t)c.G * p.nstaging * 128 * p.BN * 2;
+  c.G = tc_pick_groups(p.BN, (gather ? 4 : 1) * (K / p.KC) * (t.split ? 3 : 1), p.KC / 16);
+  if (t.split && c.G > 2) c.G = 2;
+  const size_t staging = t.split ? (size_t)c.G * 2 * 16384 + (size_t)c.G * 8 * p.BN * 4 : (size_t)c.G * p.nstaging * 128 * p.BN * 2;
   const size_t fixed = 1024 + staging + (size_t)12 * (gather ? N : Cst) + 16 + 8 * (2 * kTcMaxStages + 18);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
@@ -1929,22 +2255,23 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   c.grid = (int)(total_tiles < sms ? total_tiles : sms);
   if (gather) {
-    if (tc_make_s2_map(&c.a, x, K, x_ld, Wg, Rg, p.KC, p.tw, p.th)) return nullptr;
+    if (tc_make_s2_map(&c.a, x, K + p.a_lo, x_ld, Wg, Rg, p.KC, p.tw, p.th)) return nullptr;
     long long dims[4] = {N, Wg, Rg, 1};
     long long str[4] = {1, y_ld, (long long)Wg * y_ld, Rg * Wg * y_ld};
     int box[4] = {p.CS, p.tw, p.th, 1};
-    if (tc_make_map(&c.c, y, 4, dims, str, box, p.CS * 2)) return nullptr;
+    if (tc_make_map(&c.c, y, 4, dims, str, box, t.split ? 128 : p.CS * 2, t.split)) return nullptr;
   } else {
-    long long dims[4] = {K, Wg, Rg, 1};
+    long long dims[4] = {K + p.a_lo, Wg, Rg, 1};
     long long str[4] = {1, x_ld, (long long)Wg * x_ld, Rg * Wg * x_ld};
     int box[4] = {p.KC, p.tw, p.th, 1};
     if (tc_make_map(&c.a, x, 4, dims, str, box, p.KC * 2)) return nullptr;
-    if (tc_make_s2_map(&c.c, y, Cst, y_ld, Wg, Rg, p.CS, p.tw, p.th)) return nullptr;
+    if (tc_make_s2_map(&c.c, y, Cst, y_ld, Wg, Rg, p.CS, p.tw, p.th, t.split)) return nullptr;
   }
   {
     const int taps = gather ? 4 : 1;
-    long long dims[3] = {K, taps, N};
-    long long str[3] = {1, K, (long long)taps * K};
+    const long long Kw = t.split ? 2 * K : K;
+    long long dims[3] = {Kw, taps, N};
+    long long str[3] = {1, Kw, (long long)taps * Kw};
     int box[3] = {p.KC, 1, p.BN};
     if (tc_make_map(&c.b, wmat, 3, dims, str, box, p.KC * 2)) return nullptr;
   }
@@ -1986,6 +2313,7 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   TcConv::Cached3 c;
   memset(&c, 0, sizeof(c));
   c.x = x; c.y = y; c.x_ld = x_ld; c.y_ld = y_ld; c.B = B; c.H = H; c.W = W; c.dir = dir; c.x2 = x2; c.x2_ld = x2_ld;
+  c.f32 = t.split ? 1 : 0;
   TcConv3Params& p = c.p;
   const int K = dir == 0 ? t.Cin : t.Cout;
   const int N = dir == 0 ? t.Cout : t.Cin;
@@ -1994,8 +2322,10 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   { const int kc = tc_env_int("FU_TC_KC", 0); if ((kc == 16 || kc == 32 || kc == 64) && K % kc == 0) p.KC = kc; }
   int bn = 128;
   while (N % bn) bn >>= 1;
-  p.BN = bn; p.CS = bn >= 64 ? 64 : 32;
+  p.BN = bn; p.CS = (bn >= 64 && !t.split) ? 64 : 32;
   p.n_tiles = N / bn;
+  p.a_lo = t.split ? x_ld / 2 : 0; p.b_lo = t.split ? K : 0;
+  p.a2_lo = t.split ? x2_ld / 2 : 0; p.b2_lo = p.b_lo;
   p.halo1 = tc_env_int("FU_TC_HALO1", 1) ? 1 : 0;
   p.npair = tc_env_int("FU_TC_PAIR", 1) ? 2 : 1;
   tc_pick_halo_tile(H, W, p.halo1 != 0, p.twb, p.th);
@@ -2009,15 +2339,16 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   const size_t b_bytes = (size_t)p.BN * row_bytes;
   const size_t budget = 227 * 1024;
   p.res = (res && x2) ? 1 : 0;
-  const size_t wbytes = (size_t)(9 + p.res) * K * p.BN * 2;
+  const size_t wbytes = (size_t)(9 + p.res) * K * p.BN * 2 * (t.split ? 2 : 1);
   // two epilogue sets for the thin layers when everything (resident weights, >= 2 A stages) still fits
   // (measured: 32-column layers 75 -> 70 us, 32->64 dgrad @192 95 -> 77 us; 64->64 @96 35.5 -> 37 us: no gain at K >= 576)
   // The forward launches (dir 0) also compute the BN statistics in their epilogue, which roughly doubles its cost
   // (64->64 @96x96: 35 us without, 56 us with statistics): there two sets pay at every thin shape that fits.
   c.S = (p.BN <= 64 && (dir == 0 || (long long)K * p.BN <= 64 * 32) && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
+  if (t.split) c.S = 1;            // fp32 staging: 32 KB per epilogue group
   for (;; c.S = 1) {
-    const size_t staging = (size_t)c.S * p.npair * 128 * p.BN * 2;
-    const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * 8 * p.BN + 16 + 8 * 48;
+    const size_t staging = t.split ? (size_t)c.S * p.npair * 32768 : (size_t)c.S * p.npair * 128 * p.BN * 2;
+    const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * (t.split ? 32 : 8) * p.BN + 16 + 8 * 48;
     p.resident = (p.n_tiles == 1 && fixed + wbytes + 2 * a_stage <= budget && tc_env_int("FU_TC_RESIDENT", 1)) ? 1 : 0;
     if (p.resident) {
       int as = (int)((budget - fixed - wbytes) / a_stage);
@@ -2043,15 +2374,16 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   c.grid = (int)(total_super < sms ? total_super : sms);
+  const long long Kw = t.split ? 2 * K : K;       // K width of the weight layouts ([hi | lo] in split mode)
   {
-    long long dims[4] = {K, W, H, B};
+    long long dims[4] = {K + p.a_lo, W, H, B};
     long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
     int box[4] = {p.KC, p.twb, p.th + 2, 1};
     if (tc_make_map(&c.a, x, 4, dims, str, box, p.KC * 2)) return nullptr;
   }
   {
-    long long dims[3] = {K, 9, N};
-    long long str[3] = {1, K, 9ll * K};
+    long long dims[3] = {Kw, 9, N};
+    long long str[3] = {1, Kw, 9ll * Kw};
     int box[3] = {p.KC, 1, p.BN};
     if (tc_make_map(&c.b, dir == 0 ? t.w_fwd : t.w_dgrad, 3, dims, str, box, p.KC * 2)) return nullptr;
   }
@@ -2059,16 +2391,16 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     long long dims[4] = {N, W, H, B};
     long long str[4] = {1, y_ld, (long long)W * y_ld, (long long)H * W * y_ld};
     int box[4] = {p.CS, p.two, p.th, 1};
-    if (tc_make_map(&c.c, y, 4, dims, str, box, p.CS * 2)) return nullptr;
+    if (tc_make_map(&c.c, y, 4, dims, str, box, t.split ? 128 : p.CS * 2, t.split)) return nullptr;
   }
   c.a2 = c.a; c.b2 = c.b;
   if (p.res) {
-    long long dims[4] = {K, W, H, B};
+    long long dims[4] = {K + p.a2_lo, W, H, B};
     long long str[4] = {1, x2_ld, (long long)W * x2_ld, (long long)H * W * x2_ld};
     int box[4] = {p.KC, p.twb, p.th + 2, 1};
     if (tc_make_map(&c.a2, x2, 4, dims, str, box, p.KC * 2)) return nullptr;
-    long long wd[3] = {K, 1, N};
-    long long ws[3] = {1, K, (long long)K};
+    long long wd[3] = {Kw, 1, N};
+    long long ws[3] = {1, Kw, Kw};
     int wb[3] = {p.KC, 1, p.BN};
     if (tc_make_map(&c.b2, res->w_dgrad, 3, wd, ws, wb, p.KC * 2)) return nullptr;      // [Cin][1][Cout] of the 1x1
   }
@@ -2080,6 +2412,7 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem, conv3) failed";
       return -1;
@@ -2093,7 +2426,8 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
     cudaMemsetAsync(dbg_buf, 0, 4 * 24 * 4 * sizeof(long long), stream);
   }
   c->p.dbg = dbg ? dbg_buf : nullptr;
-  if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 64 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
+  if (c->f32) tc_conv3_kernel<1, true><<<c->grid, 64 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 64 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
   else tc_conv3_kernel<1><<<c->grid, 64 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
   if (dbg) {
     long long h[4 * 24 * 4];
@@ -2118,6 +2452,8 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem) failed";
@@ -2125,7 +2461,9 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
     }
     attr_set = true;
   }
-  if (c->G == 4) tc_conv_kernel<4><<<c->grid, 64 + 128 * 4, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  if (c->f32 && c->G == 2) tc_conv_kernel<2, true><<<c->grid, 64 + 128 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  else if (c->f32) tc_conv_kernel<1, true><<<c->grid, 64 + 128, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  else if (c->G == 4) tc_conv_kernel<4><<<c->grid, 64 + 128 * 4, c->smem, stream>>>(c->a, c->b, c->c, c->p);
   else if (c->G == 2) tc_conv_kernel<2><<<c->grid, 64 + 128 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->p);
   else tc_conv_kernel<1><<<c->grid, 64 + 128, c->smem, stream>>>(c->a, c->b, c->c, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
@@ -2134,7 +2472,9 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
   return 0;
 }
 
+// (split mode: x / x_ld describe the operand's bf16 twin, y and tp are fp32 tensors)
 inline bool tc_conv_eligible(const TcConv& t, const void* x, int x_ld, const void* y, int y_ld, const void* tp, int t_ld) {
+  if (t.split) return t.enabled && tc_ptr_ok(x, x_ld) && tc_ptr_ok_f32(y, y_ld) && (!tp || tc_ptr_ok_f32(tp, t_ld));
   return t.enabled && tc_ptr_ok(x, x_ld) && tc_ptr_ok(y, y_ld) && (!tp || tc_ptr_ok(tp, t_ld));
 }
 
@@ -2148,22 +2488,22 @@ inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld
     TcConv::Cached3* c3 = tc_prepare3(t, 0, x, x_ld, y, y_ld, B, H, W);
     if (c3) {
       c3->p.bias = bias; c3->p.relu = relu; c3->p.stat = stat;
-      c3->p.t = reinterpret_cast<const bf16*>(tp); c3->p.t_ld = t_ld; c3->p.bn_a = bn_a; c3->p.bn_b = bn_b;
-      if (accumulate) { c3->p.t = reinterpret_cast<const bf16*>(y); c3->p.t_ld = y_ld; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr; }
+      tc_set_t(t, c3->p, tp, t_ld); c3->p.bn_a = bn_a; c3->p.bn_b = bn_b;
+      if (accumulate) { tc_set_t(t, c3->p, y, y_ld); c3->p.bn_a = nullptr; c3->p.bn_b = nullptr; }
       return tc_launch3(c3, stream, cnt);
     }   // else: the halo configuration does not fit shared memory for this shape -> first-generation kernel
   }
   TcConv::Cached* c = tc_prepare(t, 0, x, x_ld, y, y_ld, B, H, W);
   if (!c) return -1;
   c->p.bias = bias; c->p.relu = relu; c->p.stat = stat;
-  c->p.t = reinterpret_cast<const bf16*>(tp); c->p.t_ld = t_ld; c->p.bn_a = bn_a; c->p.bn_b = bn_b;
-  if (accumulate) { c->p.t = reinterpret_cast<const bf16*>(y); c->p.t_ld = y_ld; c->p.bn_a = nullptr; c->p.bn_b = nullptr; }
+  tc_set_t(t, c->p, tp, t_ld); c->p.bn_a = bn_a; c->p.bn_b = bn_b;
+  if (accumulate) { tc_set_t(t, c->p, y, y_ld); c->p.bn_a = nullptr; c->p.bn_b = nullptr; }
   if (fin) c->p.fin = *fin; else memset(&c->p.fin, 0, sizeof(c->p.fin));
   return tc_launch(c, stream, cnt);
 }
 
 inline bool tc_dgrad_eligible(const TcConv& t, const void* dy, int dy_ld, const void* dx, int dx_ld) {
-  return t.enabled && tc_ptr_ok(dy, dy_ld) && tc_ptr_ok(dx, dx_ld);
+  return t.enabled && tc_ptr_ok(dy, dy_ld) && (t.split ? tc_ptr_ok_f32(dx, dx_ld) : tc_ptr_ok(dx, dx_ld));
 }
 
 // stat (optional, [2*Cin] doubles, zeroed by the caller): per-channel sum / sum of squares of the STORED dx, i.e.
@@ -2172,7 +2512,7 @@ inline bool tc_dgrad_eligible(const TcConv& t, const void* dy, int dy_ld, const 
 // kernel can (tc_dgrad_can_fuse_res)
 inline bool tc_dgrad_can_fuse_res(const TcConv& t, const TcConv& res, int H, int W, const void* g, int g_ld) {
   return tc_use_v2(t, H, W) && res.enabled && res.kind == 0 && res.k == 1 && res.Cin == t.Cin && res.Cout == t.Cout &&
-         tc_ptr_ok(g, g_ld) && tc_env_int("FU_TC_FUSE_RES", 1) != 0;
+         res.split == t.split && tc_ptr_ok(g, g_ld) && tc_env_int("FU_TC_FUSE_RES", 1) != 0;
 }
 inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
                          cudaStream_t stream, fu_counters* cnt, double* stat = nullptr, const TcConv* res = nullptr,
@@ -2181,7 +2521,7 @@ inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_
     TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W, res, g, g_ld);
     if (c3) {
       c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = stat; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
-      c3->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c3->p.t_ld = dx_ld;
+      tc_set_t(t, c3->p, accumulate ? dx : nullptr, dx_ld);
       return tc_launch3(c3, stream, cnt);
     }
   }
@@ -2189,19 +2529,20 @@ inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_
   TcConv::Cached* c = tc_prepare(t, 1, dy, dy_ld, dx, dx_ld, B, H, W);
   if (!c) return -1;
   c->p.bias = nullptr; c->p.relu = 0; c->p.stat = stat; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
-  c->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c->p.t_ld = dx_ld;
+  tc_set_t(t, c->p, accumulate ? dx : nullptr, dx_ld);
   return tc_launch(c, stream, cnt);
 }
 
 // ---- Conv2d(C,C,2,stride 2) (unet.py:93) : x (B,H,W,Cin) -> y (B,H/2,W/2,Cout) ----
 inline bool tc_down_eligible(const TcConv& t, const void* x, int x_ld, const void* y, int y_ld) {
+  if (t.split) return t.enabled && t.kind == 1 && tc_ptr_ok(x, x_ld) && tc_ptr_ok_f32(y, y_ld);
   return t.enabled && t.kind == 1 && tc_ptr_ok(x, x_ld) && tc_ptr_ok(y, y_ld);
 }
 inline int tc_down_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, const float* bias,
                            cudaStream_t stream, fu_counters* cnt) {
   TcConv::Cached* c = tc_prepare_s2(t, 0, 1, t.w_fwd, t.Cin, t.Cout, 0, x, x_ld, y, y_ld, B, H / 2, W / 2);
   if (!c) return -1;
-  c->p.bias = bias; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  c->p.bias = bias; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.tf = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
   return tc_launch(c, stream, cnt);
 }
 // dx (B,H,W,Cin) (+)= scatter of dy (B,H/2,W/2,Cout)
@@ -2211,18 +2552,19 @@ inline int tc_down_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_
                                     accumulate ? 0 : 1);
   if (!c) return -1;
   c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
-  c->p.t = accumulate ? reinterpret_cast<const bf16*>(dx) : nullptr; c->p.t_ld = dx_ld;
+  tc_set_t(t, c->p, accumulate ? dx : nullptr, dx_ld);
   return tc_launch(c, stream, cnt);
 }
 // ---- ConvTranspose2d(Cin,Cout,2,stride 2) (unet.py:240) : x (B,h,w,Cin) -> y (B,2h,2w,Cout) ----
 inline bool tc_up_eligible(const TcConv& t, const void* x, int x_ld, const void* y, int y_ld) {
+  if (t.split) return t.enabled && t.kind == 2 && tc_ptr_ok(x, x_ld) && tc_ptr_ok_f32(y, y_ld);
   return t.enabled && t.kind == 2 && tc_ptr_ok(x, x_ld) && tc_ptr_ok(y, y_ld);
 }
 inline int tc_up_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int h, int w, const float* bias,
                          cudaStream_t stream, fu_counters* cnt) {
   TcConv::Cached* c = tc_prepare_s2(t, 0, 0, t.w_fwd, t.Cin, 4 * t.Cout, t.Cout, x, x_ld, y, y_ld, B, h, w);
   if (!c) return -1;
-  c->p.bias = bias; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  c->p.bias = bias; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.tf = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
   return tc_launch(c, stream, cnt);
 }
 // dx (B,h,w,Cin) = gather of dy (B,2h,2w,Cout)
@@ -2230,7 +2572,7 @@ inline int tc_up_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld
                        fu_counters* cnt) {
   TcConv::Cached* c = tc_prepare_s2(t, 1, 1, t.w_dgrad, t.Cout, t.Cin, 0, dy, dy_ld, dx, dx_ld, B, h, w);
   if (!c) return -1;
-  c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
+  c->p.bias = nullptr; c->p.relu = 0; c->p.stat = nullptr; c->p.t = nullptr; c->p.tf = nullptr; c->p.bn_a = nullptr; c->p.bn_b = nullptr;
   return tc_launch(c, stream, cnt);
 }
 
@@ -2295,16 +2637,17 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     p.dw_acc = t.dw_acc;
     p.skip_epi = tc_env_int("FU_TC_WGRAD_NOEPI", 0);
     p.m64 = M <= 64 ? tc_env_int("FU_TC_M64", 2) : 0;
+    p.split = t.split ? 1 : 0; p.y_lo = t.split ? a_ld / 2 : 0; p.x_lo = t.split ? b_ld / 2 : 0;
     {
-      long long dims[4] = {M, p.W, p.H, p.B};
+      long long dims[4] = {M + p.y_lo, p.W, p.H, p.B};
       long long str[4] = {1, a_ld, (long long)p.W * a_ld, (long long)p.H * p.W * a_ld};
       int box[4] = {64, p.tw, p.th, p.tn};
       if (tc_make_map(&n.y, a, 4, dims, str, box, 128)) return -1;
     }
     if (s2) {
-      if (tc_make_s2_map(&n.xm, b, Nn, b_ld, W, Rg, 64, p.tw, p.th)) return -1;
+      if (tc_make_s2_map(&n.xm, b, Nn + p.x_lo, b_ld, W, Rg, 64, p.tw, p.th)) return -1;
     } else {
-      long long dims[4] = {Nn, W, H, B};
+      long long dims[4] = {Nn + p.x_lo, W, H, B};
       long long str[4] = {1, b_ld, (long long)W * b_ld, (long long)H * W * b_ld};
       int box[4] = {64, p.tw, p.th, p.tn};
       if (tc_make_map(&n.xm, b, 4, dims, str, box, 128)) return -1;
@@ -2378,14 +2721,15 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     p.dw_acc = t.dw_acc;
     p.skip_epi = tc_env_int("FU_TC_WGRAD_NOEPI", 0);
     p.m64 = t.Cout <= 64 ? tc_env_int("FU_TC_M64", 2) : 0;
+    p.split = t.split ? 1 : 0; p.y_lo = t.split ? dy_ld / 2 : 0; p.x_lo = t.split ? x_ld / 2 : 0;
     {
-      long long dims[4] = {t.Cout, W, H, B};
+      long long dims[4] = {t.Cout + p.y_lo, W, H, B};
       long long str[4] = {1, dy_ld, (long long)W * dy_ld, (long long)H * W * dy_ld};
       int box[4] = {64, p.tw, 1, 1};
       if (tc_make_map(&n.y, dy, 4, dims, str, box, 128)) return -1;
     }
     {
-      long long dims[4] = {t.Cin, W, H, B};
+      long long dims[4] = {t.Cin + p.x_lo, W, H, B};
       long long str[4] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld};
       int box[4] = {p.cb, p.tw + 2, nrows, 1};
       if (tc_make_map(&n.xm, x, 4, dims, str, box, p.cb * 2)) return -1;
@@ -2428,9 +2772,10 @@ inline int tc_up_wgrad(TcConv& t, const void* x, int x_ld, const void* dy, int d
 }
 
 // kernel-level test hook (fu_test_conv, impl = 1): bf16 NHWC tensors, fp32 torch-layout weights
+// split != 0: parity mode -- x / dy / y_or_dx are fp32 NHWC, the operands go through their bf16 twins
 inline int tc_test_conv(int mode, int B, int H, int W, int Cin, int Cout, int k, int stride, int pad, int relu,
                         const void* x, const float* w, const float* bias, void* y_or_dx, const void* dy, float* dw,
-                        double* stats, cudaStream_t stream, fu_counters* cnt) {
+                        double* stats, cudaStream_t stream, fu_counters* cnt, int split = 0) {
   // k=3/1, stride 1: Conv2d.  k=2, stride 2: Conv2d(Cin,Cout,2,2) on x (B,H,W,Cin).  k=2, stride -2:
   // ConvTranspose2d(Cin,Cout,2,2) on x (B,H,W,Cin) -> (B,2H,2W,Cout), w in its (Cin,Cout,2,2) layout.
   const bool plain = (k == 1 || k == 3) && stride == 1 && pad == k / 2;
@@ -2440,36 +2785,58 @@ inline int tc_test_conv(int mode, int B, int H, int W, int Cin, int Cout, int k,
   TcConv t;
   char *mem = nullptr, *mem2 = nullptr;
   Bump dry, dry2;
-  tc_carve(t, Cin, Cout, k, up, true, dry, dry2);
+  tc_carve(t, Cin, Cout, k, up, true, dry, dry2, split != 0);
   if (!t.enabled) { tc_err() = "tc_test_conv: shape not eligible (channels must be multiples of 32)"; return -1; }
   if (cudaMalloc(&mem, dry.off + 256) != cudaSuccess || cudaMalloc(&mem2, dry2.off + 256) != cudaSuccess) {
     tc_err() = "cudaMalloc failed";
     return -1;
   }
   Bump real, real2; real.base = mem; real2.base = mem2;
-  tc_carve(t, Cin, Cout, k, up, true, real, real2);
+  tc_carve(t, Cin, Cout, k, up, true, real, real2, split != 0);
   int rc = 0;
+  // operand descriptors: the tensors themselves, or (split) their twins
+  bf16 *xt = nullptr, *dyt = nullptr;
+  int x_ld = Cin, dy_ld = Cout;
+  if (split) {
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    // pixel counts of the two operands: x lives on (B,H,W); dy on (B,H,W) (plain), (B,H/2,W/2) (down) or (B,2H,2W) (up)
+    const long long Px = (long long)B * H * W;
+    const long long Pdy = plain ? Px : (down ? (long long)B * (H / 2) * (W / 2) : 4 * Px);
+    if (x && mode != 1) {
+      if (cudaMalloc(&xt, (size_t)Px * Cin * 4) != cudaSuccess) { tc_err() = "cudaMalloc failed"; return -1; }
+      tc_split(reinterpret_cast<const float*>(x), Cin, Cin, xt, 2 * Cin, Cin, Px, sms, stream, cnt);
+      x = xt; x_ld = 2 * Cin;
+    }
+    if (dy && mode != 0) {
+      if (cudaMalloc(&dyt, (size_t)Pdy * Cout * 4) != cudaSuccess) { tc_err() = "cudaMalloc failed"; return -1; }
+      tc_split(reinterpret_cast<const float*>(dy), Cout, Cout, dyt, 2 * Cout, Cout, Pdy, sms, stream, cnt);
+      dy = dyt; dy_ld = 2 * Cout;
+    }
+  }
   if (mode == 2) {
     cudaMemsetAsync(mem2, 0, dry2.off + 256, stream);
     cudaMemsetAsync(dw, 0, (size_t)Cin * Cout * k * k * sizeof(float), stream);   // 1x1 layers accumulate in place
-    if (plain) rc = tc_conv_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
-    else if (down) rc = tc_down_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
-    else rc = tc_up_wgrad(t, x, Cin, dy, Cout, B, H, W, dw, stream, cnt);
+    if (plain) rc = tc_conv_wgrad(t, x, x_ld, dy, dy_ld, B, H, W, dw, stream, cnt);
+    else if (down) rc = tc_down_wgrad(t, x, x_ld, dy, dy_ld, B, H, W, dw, stream, cnt);
+    else rc = tc_up_wgrad(t, x, x_ld, dy, dy_ld, B, H, W, dw, stream, cnt);
   } else {
     rc = tc_pack(t, w, stream, cnt);
     if (!rc && mode == 0) {
-      if (plain) rc = tc_conv_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, relu, stats, nullptr, 0, nullptr, nullptr, 0, stream, cnt);
-      else if (down) rc = tc_down_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, stream, cnt);
-      else rc = tc_up_forward(t, x, Cin, y_or_dx, Cout, B, H, W, bias, stream, cnt);
+      if (plain) rc = tc_conv_forward(t, x, x_ld, y_or_dx, Cout, B, H, W, bias, relu, stats, nullptr, 0, nullptr, nullptr, 0, stream, cnt);
+      else if (down) rc = tc_down_forward(t, x, x_ld, y_or_dx, Cout, B, H, W, bias, stream, cnt);
+      else rc = tc_up_forward(t, x, x_ld, y_or_dx, Cout, B, H, W, bias, stream, cnt);
     } else if (!rc) {
-      if (plain) rc = tc_conv_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, 0, stream, cnt);
-      else if (down) rc = tc_down_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, 0, stream, cnt);
-      else rc = tc_up_dgrad(t, dy, Cout, y_or_dx, Cin, B, H, W, stream, cnt);
+      if (plain) rc = tc_conv_dgrad(t, dy, dy_ld, y_or_dx, Cin, B, H, W, 0, stream, cnt);
+      else if (down) rc = tc_down_dgrad(t, dy, dy_ld, y_or_dx, Cin, B, H, W, 0, stream, cnt);
+      else rc = tc_up_dgrad(t, dy, dy_ld, y_or_dx, Cin, B, H, W, stream, cnt);
     }
   }
   cudaError_t e = cudaStreamSynchronize(stream);
   cudaFree(mem);
   cudaFree(mem2);
+  if (xt) cudaFree(xt);
+  if (dyt) cudaFree(dyt);
   if (!rc && e != cudaSuccess) { tc_err() = std::string("tc_test_conv: ") + cudaGetErrorString(e); return -1; }
   return rc;
 }

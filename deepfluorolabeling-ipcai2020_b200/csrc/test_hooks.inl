@@ -66,8 +66,9 @@ extern "C" int fu_test_conv(int precision, int impl, int mode, int B, int H, int
     else
       rc = test_conv_simt<float>(&e, mode, B, H, W, Cin, Cout, ksize, stride, pad, relu, x, w, bias, y_or_dx, dy, dw, stats);
   } else {
+    // impl 1: bf16 tensors; impl 2: fp32 tensors through the split-bf16 x3 parity path (FU_PRECISION_FP32_TC)
     rc = tc_test_conv(mode, B, H, W, Cin, Cout, ksize, stride, pad, relu, x, w, bias, y_or_dx, dy, dw, stats,
-                      e.stream, &e.cnt);
+                      e.stream, &e.cnt, impl == 2 ? 1 : 0);
     if (rc) e.err = tc_last_error();
   }
   if (rc) g_create_error = e.err;

@@ -85,8 +85,10 @@ class UNet(nn.Module):
                  do_res=True, block_depth=2, lands_block_depth=0, lands_num_1x1=2,
                  do_soft_max=True, precision=None):
         """Same arguments as the reference (unet.py:41-45) plus ``precision``:
-        ``'fp32'`` (parity mode, default) or ``'bf16'`` (throughput mode).  The
-        default can be overridden with the environment variable FLUORO_UNET_PRECISION."""
+        ``'fp32'`` (parity mode on the CUDA cores, default), ``'parity_tc'`` (parity mode on the tensor cores:
+        fp32 storage, every contraction as three split-bf16 tcgen05 passes, ~1e-5 from the reference) or
+        ``'bf16'`` (throughput mode).  The default can be overridden with the environment variable
+        FLUORO_UNET_PRECISION."""
         super().__init__()
         if up_mode not in ('upconv', 'upsample'):
             raise ValueError("up_mode must be 'upconv' or 'upsample'")
@@ -109,7 +111,7 @@ class UNet(nn.Module):
         if precision is None:
             precision = os.environ.get("FLUORO_UNET_PRECISION", "fp32")
         if precision not in _capi.PRECISION:
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+            raise ValueError("precision must be 'fp32', 'parity_tc' or 'bf16'")
         if precision == "bf16" and wf < 3:
             raise ValueError("throughput mode (bf16) needs wf >= 3 (16-byte channel vectors); use precision='fp32'")
         self.padding = padding

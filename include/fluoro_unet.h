@@ -41,6 +41,10 @@ extern "C" {
 
 #define FU_PRECISION_FP32 0  /* parity mode: fp32 storage + fp32 FMA, matches unet.py to ~1e-5 */
 #define FU_PRECISION_BF16 1  /* throughput mode: bf16 NHWC storage, tcgen05 bf16 MMA, fp32 accumulate */
+#define FU_PRECISION_FP32_TC 2 /* parity mode on the tensor cores: fp32 NHWC storage; every MMA operand is read from a
+                                  split-bf16 twin (hi = bf16(v), lo = bf16(v - hi)) and each contraction runs the three
+                                  passes hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (~2^-16 per product);
+                                  matches unet.py to ~1e-5 like FU_PRECISION_FP32, at tensor-core speed */
 
 #define FU_KIND_PARAM 0
 #define FU_KIND_BUFFER 1
@@ -227,7 +231,8 @@ const char* fu_build_info(void);
  *   mode 0: forward 3x3/1x1/2x2s2 conv   y = conv(x, w) + bias [+relu]
  *   mode 1: data gradient                dx = conv^T(dy, w)
  *   mode 2: weight gradient              dw = x (*) dy
- * `impl` 0 = fp32/bf16 CUDA-core path, 1 = tcgen05 path (bf16 only).
+ * `impl` 0 = fp32/bf16 CUDA-core path, 1 = tcgen05 path (bf16 tensors), 2 = tcgen05 split-bf16 x3 parity path
+ * (fp32 tensors, FU_PRECISION_FP32_TC).
  * Tensors: x (B,H,W,Cin), y/dy (B,Ho,Wo,Cout) in the engine precision's storage
  * type (fp32 or bf16 bits); w, bias, dw fp32 in the torch layout (Cout,Cin,k,k). */
 int fu_test_conv(int precision, int impl, int mode, int B, int H, int W, int Cin, int Cout,

@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 # Gradients are judged per tensor in parity mode; in throughput mode per tensor only for the
 # well-conditioned ones (conv weights) and globally (flat gradient), because bias/BN gradients in a
 # conv->ReLU->BN stack are sums with heavy cancellation whose bf16 noise is large relative to their norm.
+# parity_tc (fp32 storage, split-bf16 x3 tcgen05 contractions): held to the same bounds as the CUDA-core parity mode.
 TOL = {"fp32": dict(out=5e-5, grad=1e-3, stats=1e-4, flat=1e-4),
+       "parity_tc": dict(out=5e-5, grad=1e-3, stats=1e-4, flat=1e-4),
        "bf16": dict(out=3e-2, grad=None, stats=3e-2, flat=3e-1)}
 REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
 
@@ -93,11 +95,11 @@ def _run_case(pkg, name, precision):
     flat_ref = torch.cat([ref_g[n].flatten() for n in names])
     errs["flat_grad"] = rel_l2(flat, flat_ref)
     errs["mask_flips"] = count_relu_mask_flips(net, golden_state(rec), O.UNetConfig(**meta["kwargs"]), rec["x"],
-                                               meta["training"]) if precision == "fp32" else -1
+                                               meta["training"]) if precision != "bf16" else -1
     return meta, errs, gerrs, serrs
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "parity_tc", "bf16"])
 @pytest.mark.parametrize("name", SMALL_CASES)
 def test_golden_case(pkg, name, precision):
     if precision == "bf16" and load_golden(name)[0]["kwargs"]["wf"] < 3:
@@ -135,10 +137,12 @@ def _paper_net(pkg, precision, meta):
     return net, sd, cfg
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "parity_tc", "bf16"])
 def test_paper_config_eval_192_matches_reference(pkg, precision):
     """BASELINE.json config 1: single-image eval forward, logits/probs/heat-maps within 1e-3 rel
-    of the reference PyTorch-CPU forward (parity mode).  Throughput mode is reported."""
+    of the reference PyTorch-CPU forward, in both parity modes: CUDA cores (fp32) and tensor cores
+    (parity_tc: every conv except the C_in = 1 first layer and the 7/14-channel heads is a tcgen05 kernel).
+    Throughput mode is reported."""
     meta, rec = load_golden("paper_eval_192")
     net, sd, cfg = _paper_net(pkg, precision, meta)
     dev = torch.device("cuda:0")
@@ -151,16 +155,22 @@ def test_paper_config_eval_192_matches_reference(pkg, precision):
          "seg": rel_l2(seg.cpu()[:, :, ::4, ::4], rec["seg_s4"]),
          "heat": rel_l2(heat.cpu()[:, :, ::4, ::4], rec["heat_s4"]),
          "heat_vs_fp64": rel_l2(heat.cpu()[:, :, ::4, ::4], rec["heat64_s4"])}
-    _report(test="paper_eval_192", precision=precision, **e)
-    tol = 1e-3 if precision == "fp32" else 5e-2
+    cnt = net.engine_counters()
+    _report(test="paper_eval_192", precision=precision, tc_kernel_launches=cnt["tc_kernel_launches"], **e)
+    tol = 1e-3 if precision != "bf16" else 5e-2
     assert e["logits"] < tol and e["seg"] < tol and e["heat"] < tol, e
+    if precision == "fp32":
+        assert cnt["tc_kernel_launches"] == 0
+    else:
+        assert cnt["tc_kernel_launches"] >= 38, cnt       # 21 3x3 + 11 1x1 + 5 down + 5 up convs on tcgen05
     assert seg.shape == (1, 7, 192, 192) and heat.shape == (1, 14, 192, 192)
 
 
-def test_paper_config_train_step_matches_oracle(pkg):
+@pytest.mark.parametrize("precision", ["fp32", "parity_tc"])
+def test_paper_config_train_step_matches_oracle(pkg, precision):
     """fwd+bwd of the paper network, B=2 at 96x96 (oracle finishes in seconds), every gradient."""
     meta, _ = load_golden("paper_eval_192")
-    net, sd, cfg = _paper_net(pkg, "fp32", meta)
+    net, sd, cfg = _paper_net(pkg, precision, meta)
     dev = torch.device("cuda:0")
     net.to(dev).train()
     g = torch.Generator().manual_seed(5)
@@ -198,8 +208,10 @@ def test_paper_config_train_step_matches_oracle(pkg):
     f = torch.cat([dict(net.named_parameters())[n].grad.cpu().flatten().double() for n in names])
     fr = torch.cat([rg64[n].flatten() for n in names])
     cos = float(torch.dot(f, fr) / (f.norm() * fr.norm()))
-    _report(test="paper_train_96", worst_grad=worst, flat_cosine=cos)
+    _report(test="paper_train_96", precision=precision, worst_grad=worst, flat_cosine=cos,
+            tc_kernel_launches=net.engine_counters()["tc_kernel_launches"])
     assert cos > 0.9999, cos
+    assert (net.engine_counters()["tc_kernel_launches"] > 100) == (precision == "parity_tc")
 
 
 def test_per_layer_forward_activations_match_oracle(pkg):

@@ -237,3 +237,104 @@ def test_tc_halo_conv_fwd_dgrad(pkg, shape, env):
     assert rel_l2(stats[Cout:], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-4
     assert rel_l2(dx, torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=1)) < 6e-3
     assert rel_l2(dw, torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=1)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parity mode on the tensor cores (FU_PRECISION_FP32_TC, fu_test_conv impl = 2): fp32 NHWC tensors, operands read
+# from split-bf16 twins, three MMA passes per contraction.  Inputs are NOT bf16-representable here; the result
+# must match torch-CPU fp32 to ~1e-5 (the dropped lo*lo products are ~2^-16 relative).
+# ---------------------------------------------------------------------------------------------------------------
+SPLIT_TOL = 3e-5
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_split_tc_conv_fwd_dgrad_wgrad(pkg, shape):
+    B, Cin, Cout, H, W, k = shape
+    pad = k // 2
+    g = torch.Generator().manual_seed(sum(shape) + 11)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    y_ref = torch.relu(F.conv2d(x, w, b, padding=pad))
+    y, stats = run_conv(pkg, 0, 2, 0, x, w, b, None, k, 1, pad, relu=1, want_stats=True)
+    assert rel_l2(y, y_ref) < SPLIT_TOL, rel_l2(y, y_ref)
+    assert rel_l2(stats[:Cout], y.double().sum(dim=(0, 2, 3))) < 1e-5
+    assert rel_l2(stats[Cout:], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-5
+    dx = run_conv(pkg, 0, 2, 1, x, w, None, dy, k, 1, pad)
+    assert rel_l2(dx, torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=pad)) < SPLIT_TOL
+    dw = run_conv(pkg, 0, 2, 2, x, w, None, dy, k, 1, pad)
+    assert rel_l2(dw, torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=pad)) < SPLIT_TOL
+
+
+@pytest.mark.parametrize("env", [{}, {"FU_TC_HALO1": "0"}, {"FU_TC_PAIR": "0"}, {"FU_TC_RESIDENT": "0"}])
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+def test_split_tc_halo_conv(pkg, shape, env):
+    import os
+    B, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) + 13)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    env = dict(env, FU_TC_V2_MINW="24")
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        y, stats = run_conv(pkg, 0, 2, 0, x, w, b, None, 3, 1, 1, relu=1, want_stats=True)
+        dx = run_conv(pkg, 0, 2, 1, x, w, None, dy, 3, 1, 1)
+        dw = run_conv(pkg, 0, 2, 2, x, w, None, dy, 3, 1, 1)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    y_ref = torch.relu(F.conv2d(x, w, b, padding=1))
+    assert rel_l2(y, y_ref) < SPLIT_TOL, rel_l2(y, y_ref)
+    assert rel_l2(stats[:Cout], y.double().sum(dim=(0, 2, 3))) < 1e-5
+    assert rel_l2(stats[Cout:], (y.double() ** 2).sum(dim=(0, 2, 3))) < 1e-5
+    assert rel_l2(dx, torch.nn.grad.conv2d_input(x.shape, w, dy, stride=1, padding=1)) < SPLIT_TOL
+    assert rel_l2(dw, torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=1, padding=1)) < SPLIT_TOL
+
+
+@pytest.mark.parametrize("shape", S2_SHAPES)
+def test_split_tc_down_and_up_2x2_s2(pkg, shape):
+    """Conv2d(C,C,2,2) and ConvTranspose2d(.,.,2,2) (unet.py:93,240) through the split path."""
+    B, Cin, Cout, H, W = shape
+    L, dev = pkg._capi.lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(sum(shape) + 17)
+    f32 = torch.float32
+    # ---- down ----
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 2, 2, generator=g) / (Cin * 4) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, H // 2, W // 2, generator=g)
+    xg, wg, bg, dyg = _nhwc(x, f32, dev), w.to(dev), b.to(dev), _nhwc(dy, f32, dev)
+    y = torch.empty(B, H // 2, W // 2, Cout, device=dev)
+    dx = torch.empty(B, H, W, Cin, device=dev)
+    dw = torch.empty_like(wg)
+    for mode, out in ((0, y), (1, dx), (2, None)):
+        rc = L.fu_test_conv(0, 2, mode, B, H, W, Cin, Cout, 2, 2, 0, 0, _p(xg), _p(wg), _p(bg), _p(out), _p(dyg), _p(dw), None, None)
+        assert rc == 0, pkg._capi.last_error(None)
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu().permute(0, 3, 1, 2), F.conv2d(x, w, b, stride=2)) < SPLIT_TOL
+    assert rel_l2(dx.cpu().permute(0, 3, 1, 2), torch.nn.grad.conv2d_input(x.shape, w, dy, stride=2)) < SPLIT_TOL
+    assert rel_l2(dw.cpu(), torch.nn.grad.conv2d_weight(x, w.shape, dy, stride=2)) < SPLIT_TOL
+    # ---- up ----
+    x = torch.randn(B, Cin, H, W, generator=g).requires_grad_(True)
+    w = (torch.randn(Cin, Cout, 2, 2, generator=g) / Cin ** 0.5).requires_grad_(True)
+    dy = torch.randn(B, Cout, 2 * H, 2 * W, generator=g)
+    y_ref = F.conv_transpose2d(x, w, b, stride=2)
+    y_ref.backward(dy)
+    xg, wg, dyg = _nhwc(x.detach(), f32, dev), w.detach().to(dev), _nhwc(dy, f32, dev)
+    y = torch.empty(B, 2 * H, 2 * W, Cout, device=dev)
+    dx = torch.empty(B, H, W, Cin, device=dev)
+    dw = torch.empty_like(wg)
+    for mode, out in ((0, y), (1, dx), (2, None)):
+        rc = L.fu_test_conv(0, 2, mode, B, H, W, Cin, Cout, 2, -2, 0, 0, _p(xg), _p(wg), _p(bg), _p(out), _p(dyg), _p(dw), None, None)
+        assert rc == 0, pkg._capi.last_error(None)
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu().permute(0, 3, 1, 2), y_ref.detach()) < SPLIT_TOL
+    assert rel_l2(dx.cpu().permute(0, 3, 1, 2), x.grad) < SPLIT_TOL
+    assert rel_l2(dw.cpu(), w.grad) < SPLIT_TOL
