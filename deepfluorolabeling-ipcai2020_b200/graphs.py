@@ -18,10 +18,15 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, step_fn, example_inputs, warmup=3, allow_distributed=False):
+    def __init__(self, step_fn, example_inputs, warmup=3, allow_distributed=False, modules=()):
         """step_fn(*inputs) -> loss tensor (or tuple of tensors); example_inputs: CUDA tensors of the step's shapes.
         allow_distributed: also capture under torch.distributed (the NCCL gradient all-reduce of
-        parallel.data_parallel becomes a node of the graph; every rank must capture and replay in lock step)."""
+        parallel.data_parallel becomes a node of the graph; every rank must capture and replay in lock step).
+        modules: the UNet modules the step trains.  A replay changes their parameters on the device without running
+        any Python, so neither the tensors' version counters nor the modules' pack epochs move; every replay
+        therefore tells them (`UNet.mark_weights_changed`) so that the next EAGER forward -- e.g. the per-epoch
+        validation of train.py:446-454 -- re-packs the engine's weight copies instead of using the ones the last
+        replayed step packed before its optimizer update."""
         if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
             raise ValueError("GraphedStep: example_inputs must be CUDA tensors")
         if (not allow_distributed and torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -29,6 +34,7 @@ class GraphedStep:
             raise RuntimeError("GraphedStep: pass allow_distributed=True to capture the data-parallel step "
                                "(all ranks must then capture and replay together)")
         self.step_fn = step_fn
+        self.modules = [m for m in modules if hasattr(m, "mark_weights_changed")]
         self.static_in = [torch.empty_like(t) for t in example_inputs]
         for d, s in zip(self.static_in, example_inputs):
             d.copy_(s)
@@ -58,4 +64,6 @@ class GraphedStep:
             if s.data_ptr() != d.data_ptr():
                 d.copy_(s, non_blocking=True)
         self.graph.replay()
+        for m in self.modules:
+            m.mark_weights_changed()
         return self.static_out

@@ -30,6 +30,8 @@ def broadcast_state(net, src=0, group=None):
         return
     for t in list(net.parameters()) + list(net.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+    if hasattr(net, "mark_weights_changed"):
+        net.mark_weights_changed()          # `.data` writes do not bump version counters
 
 
 def sync_buffers(net, src=0, group=None):

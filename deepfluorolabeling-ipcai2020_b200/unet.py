@@ -249,6 +249,11 @@ class UNet(nn.Module):
         self._bound_ptrs = None
         self._pack_epoch = (self._pack_epoch + 1) & 0x3FFFFFFF
 
+    def mark_weights_changed(self):
+        """Parameter VALUES changed outside autograd's version tracking (a CUDA-graph replay of a training step, a
+        `.data` write such as dist.broadcast(p.data)): the next forward re-packs the engine's weight copies."""
+        self._pack_epoch = (self._pack_epoch + 1) & 0x3FFFFFFF
+
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self._state_cache = None

@@ -483,3 +483,52 @@ def test_full_size_configs_properties(pkg, cfg):
     for n, p in net.named_parameters():
         if p.grad is not None and p.dim() > 1:
             assert rel_l2(p.grad.cpu(), 2 * g1[n].cpu()) < 2e-2, n           # (4) linear in the upstream gradient
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_eager_forward_after_graph_replays_uses_the_updated_weights(pkg, precision):
+    """A CUDA-graph replay of a training step updates the parameters on the device without running any Python, so no
+    version counter moves.  The per-epoch validation of train.py:446-454 (an eager eval forward between replays) must
+    still see the weights of the LAST replayed step: replay, eval, replay, eval against the same sequence run eagerly."""
+    dev = torch.device("cuda:0")
+    kw = dict(n_classes=7, depth=3, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=14)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(4, 1, 32, 32, generator=g).to(dev)
+    ts = torch.nn.functional.one_hot(torch.randint(0, 7, (4, 28, 28), generator=g), 7).permute(0, 3, 1, 2).float().contiguous().to(dev)
+    th = torch.rand(4, 14, 28, 28, generator=g).to(dev)
+    xv = torch.randn(2, 1, 32, 32, generator=g).to(dev)
+    vals = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        net = pkg.UNet(precision=precision, **kw).to(dev)
+        opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, nesterov=True, fused=True)
+        crit = pkg.FusedDiceAndHeatMapLoss2D(skip_bg=False, heatmap_wgt=0.5)
+
+        def step(x, ts, th):
+            opt.zero_grad(set_to_none=True)
+            seg, heat = net(x)
+            loss = crit((seg, heat), (ts, th))
+            loss.backward()
+            opt.step()
+            return loss
+        if mode == "graph":
+            call = pkg.GraphedStep(step, (x, ts, th), warmup=2, modules=[net])
+        else:
+            for _ in range(2):
+                step(x, ts, th)
+            call = step
+        outs = []
+        for _ in range(3):
+            for _ in range(2):
+                call(x, ts, th)
+            net.eval()
+            with torch.no_grad():
+                seg, heat = net(xv)
+            outs.append((seg.clone(), heat.clone()))
+            net.train()
+        vals[mode] = outs
+    tol = 1e-4 if precision == "fp32" else 3e-2
+    for (se, he), (sg, hg) in zip(vals["eager"], vals["graph"]):
+        assert rel_l2(sg.cpu(), se.cpu()) < tol and rel_l2(hg.cpu(), he.cpu()) < tol
+    # the validation outputs must actually move between epochs (otherwise the check above proves nothing)
+    assert rel_l2(vals["graph"][2][1].cpu(), vals["graph"][0][1].cpu()) > 0.1

@@ -109,3 +109,39 @@ def test_losses_match_reference_dice_and_ncc():
         assert abs(float(l_d) - float(t["l_dice"])) < 1e-6
         assert rel_l2(seg.grad, t["d_seg"]) < 1e-5
         assert rel_l2(heat.grad, t["d_heat"]) < 1e-5
+
+
+def test_oracle_training_step_matches_reference_at_the_benchmarked_size():
+    """BASELINE.json configs[1]: the oracle's explicit forward + hand-derived backward on 32 tiles at 192x192 against
+    the real reference's training step (tests/golden/make_golden_large.py): outputs, loss and every parameter
+    gradient.  Pins the checker at the size the bench runs."""
+    import importlib.util
+    import os
+    from conftest import GOLDEN, load_pkg
+    spec = importlib.util.spec_from_file_location("make_golden_large", os.path.join(GOLDEN, "make_golden_large.py"))
+    mgl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgl)
+    meta, rec = load_golden("large_paper_b32_192")
+    case = meta["case"]
+    torch.manual_seed(meta["init_seed"])
+    net = load_pkg().UNet(**case["kwargs"])           # parameter container: same init stream as the reference
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = O.UNetConfig(**case["kwargs"])
+    x, mask, heat_t = mgl.make_inputs(case, seed=meta["input_seed"])
+    out = O.forward(sd, cfg, x, training=True, want_tape=True)
+    st = case["out_stride"]
+    assert rel_l2(out["seg"][:, :, ::st, ::st], rec["seg_s"]) < 1e-4
+    assert rel_l2(out["heat"][:, :, ::st, ::st], rec["heat_s"]) < 1e-4
+    loss, d_seg, d_heat = O.loss_and_output_grads(out, cfg, mask, heat_t, heatmap_wgt=case["heatmap_wgt"])
+    assert abs(float(loss) - float(rec["loss"])) < 1e-5
+    grads = O.backward(sd, cfg, out["tape"], d_seg, d_heat)
+    for n, stride in meta["grad_strides"].items():
+        # two fp32 CPU computations in different summation orders, judged against the reference's fp64 run: the oracle
+        # may be as far from that truth as the fp32 reference is (its `floor`), within a small factor
+        smp = grads[n].flatten()[::stride]
+        e = rel_l2(smp, rec["grad_sample64/" + n])
+        floor = rel_l2(rec["grad_sample/" + n], rec["grad_sample64/" + n])
+        assert e < max(1e-3 if grads[n].dim() > 1 else 1e-2, 6 * floor), (n, e, floor)
+    for k, v in rec.items():
+        if k.startswith("state_after/"):
+            assert rel_l2(out["new_stats"][k[len("state_after/"):]], v) < 1e-4, k
