@@ -57,15 +57,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.  The report lives out of
+// line: inlined at every wait site it put ~12 instructions of printf set-up into each hot loop (instruction-cache
+// footprint is what limits the single MMA-issuing warp, see tc_mma_taps_resident).
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("fluoro_unet: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+         (int)threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("fluoro_unet: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout(bar, parity);
   }
 }
 
@@ -130,6 +133,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same with both descriptors given as (shared high word, 32-bit low word).  The start-address field of a
+// shared-memory descriptor is bits 0-13 of the low word (16-byte units, < 256 KB: it never carries), so all per-tap /
+// per-K-step descriptor arithmetic is ONE 32-bit add instead of a 64-bit add + uniform-register shuffling: the thin
+// layers (N = 32/64: 16-32 tensor cycles per MMA) were bound by the ~20 SASS instructions the issuing thread spent
+// per MMA (ncu source page, profiles/r02_ncu_thin_conv_before.txt), not by the tensor pipe.
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
@@ -205,6 +224,41 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(uint32_t n, uint32_t m = 
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// KS K-steps of one filter tap into the accumulators of a pixel-tile pair (32 bytes = +2 in the address field per step)
+template <int KS>
+__device__ __forceinline__ void tc_mma_tap(uint32_t d0, uint32_t d1, bool two, uint32_t a_lo, uint32_t a2_lo, uint32_t b_lo,
+                                           uint32_t hi, uint32_t idesc, uint32_t accum) {
+#pragma unroll
+  for (int j = 0; j < KS; ++j) {
+    ptx::umma_bf16_lo(d0, a_lo + 2u * j, b_lo + 2u * j, hi, idesc, j == 0 ? accum : 1u);
+    if (two) ptx::umma_bf16_lo(d1, a2_lo + 2u * j, b_lo + 2u * j, hi, idesc, j == 0 ? accum : 1u);
+  }
+}
+// All taps of one halo tile against the resident weights of its channel chunk.  Deliberately ROLLED loops: the
+// issuing warp shares its instruction caches with the epilogue warps, and the fully unrolled version of this
+// sequence (9 taps x KS steps x 2 tiles, ~5-10 KB of SASS per super tile) was evicted between super tiles -- 48 % of
+// the issuing warp's stall samples were "no instruction" (ncu source page, profiles/r02_ncu_thin_conv_before.txt).
+// g < 0: all nine taps; otherwise the three taps with kw == g (one-load-per-kw mode).  Offsets in 16-byte units.
+__device__ __forceinline__ void tc_mma_taps_resident(int ksteps, uint32_t d0, uint32_t d1, bool two, uint32_t a_lo0,
+                                                     uint32_t a_tile16, uint32_t b_lo0, uint32_t b16, uint32_t kh16,
+                                                     uint32_t kw16, int g, uint32_t hi, uint32_t idesc, uint32_t accum) {
+  uint32_t a_row = a_lo0;
+  uint32_t b_lo = g < 0 ? b_lo0 : b_lo0 + (uint32_t)g * b16;
+  const int nkw = g < 0 ? 3 : 1;
+  const uint32_t b_step = g < 0 ? b16 : 3u * b16;
+#pragma unroll 1
+  for (int kh = 0; kh < 3; ++kh, a_row += kh16) {
+    uint32_t a_lo = a_row;
+#pragma unroll 1
+    for (int kw = 0; kw < nkw; ++kw, a_lo += kw16, b_lo += b_step) {
+      if (ksteps == 4) tc_mma_tap<4>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, hi, idesc, accum);
+      else if (ksteps == 2) tc_mma_tap<2>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, hi, idesc, accum);
+      else tc_mma_tap<1>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, hi, idesc, accum);
+      accum = 1u;
+    }
+  }
+}
+
 // ===========================================================================
 // the convolution kernel (forward and data gradient; 3x3/pad 1 and 1x1)
 // ===========================================================================
@@ -270,6 +324,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + (smem_base - raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Warp roles.  The epilogue warps come FIRST and the TMA producer / MMA issuer LAST: the SM sub-partition schedulers
+  // prefer the highest warp id among eligible warps, and the single MMA-issuing thread is the critical path of the
+  // thin layers -- as warp 1 it was starved by the (instruction-heavy) epilogue warps sharing its scheduler (ncu:
+  // ~1000 idle tensor-pipe cycles between tiles, profiles/r02_ncu_thin_conv_before.txt).
+  constexpr int prod_warp = 4 * G, mma_warp = 4 * G + 1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2u;
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -299,7 +358,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
   }
-  if (warp == 1) {
+  if (warp == mma_warp) {
     ptx::tmem_alloc(slot_addr, tmem_cols);
     ptx::tmem_relinquish();
   }
@@ -367,7 +426,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     n0 = mt * p.tn;
   };
 
-  if (warp == 0) {
+  if (warp == prod_warp) {
     // ------------------------------ TMA producer (whole warp loops, one elected lane issues) -----
     {
       int stage = 0; uint32_t phase = 0;
@@ -397,14 +456,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == mma_warp) {
     // ------------------------------ MMA issuer (whole warp loops, one elected lane issues) -----
     {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
       const uint64_t dbase = umma_desc_kmajor(0, row_bytes);
+      const uint32_t dhi = (uint32_t)(dbase >> 32), dlo = (uint32_t)dbase;
       const int ksteps = p.KC / 16;
+      const uint32_t a16 = a_bytes >> 4;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
@@ -415,10 +476,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           //  tcgen05.ld signalled, i.e. the accumulator hand-back above)
           ptx::mbar_wait(full_bar(stage), phase);
           if (ptx::elect_one()) {
-            const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
-            const uint64_t ad0 = umma_desc_at(dbase, a_addr), bd0 = umma_desc_at(dbase, a_addr + a_bytes);
-            for (int j = 0; j < ksteps; ++j)   // +32 B per K step = +2 in the descriptor's address field
-              ptx::umma_bf16(d_tmem, ad0 + (uint64_t)(2 * j), bd0 + (uint64_t)(2 * j), idesc, (kit | j) != 0 ? 1u : 0u);
+            // +32 B per K step = +2 in the address field of the descriptors' low words (see umma_bf16_lo)
+            const uint32_t a_lo = dlo + ((smem_base + (uint32_t)stage * stage_bytes) >> 4);
+            const uint32_t first = kit != 0 ? 1u : 0u;
+            if (ksteps == 4) tc_mma_tap<4>(d_tmem, 0u, false, a_lo, 0u, a_lo + a16, dhi, idesc, first);
+            else if (ksteps == 2) tc_mma_tap<2>(d_tmem, 0u, false, a_lo, 0u, a_lo + a16, dhi, idesc, first);
+            else tc_mma_tap<1>(d_tmem, 0u, false, a_lo, 0u, a_lo + a16, dhi, idesc, first);
             ptx::umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
             if (kit == k_iters - 1) ptx::umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
           }
@@ -430,11 +493,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------ epilogue (G groups of 4 warps / 128 threads) ------------------------------
-    const int grp = (warp - 2) >> 2;        // which group; it drains tiles grp, grp + G, ... of this CTA
+    const int grp = warp >> 2;        // which group; it drains tiles grp, grp + G, ... of this CTA
     const int bar_id = 1 + grp;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;          // accumulator row = pixel slot of the tile
-    const int et = (threadIdx.x - 64) & 127;   // 0..127 within the group
+    const int et = threadIdx.x & 127;   // 0..127 within the group
     const uint32_t pitch = (uint32_t)p.CS * 2u;
     const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
     const uint32_t sub_bytes = 128u * pitch;
@@ -719,7 +782,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == mma_warp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -737,6 +800,44 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //  * two pixel tiles share every weight tile (2 accumulators per TMEM stage);
 //  * for thin layers (all taps fit in shared memory) the weights are loaded once per CTA and stay resident.
 // ===========================================================================
+// Per-channel sum / sum of squares of a bf16 staging tile: 128 rows x (nsub sub-boxes of CS channels), rows of PITCH =
+// 2*CS bytes swizzled the way the TMA store expects.  Warp `q` scans rows [32q, 32q + 32) of every sub-box; one load
+// instruction of the warp covers 128 consecutive bytes (one 128-byte row, or two 64-byte rows), so it is bank-conflict
+// free, and the swizzle term of load i is a compile-time constant (i & 7 resp. i & 3): 8 instructions per load instead
+// of the 28 of a generic address computation -- this loop was 36 % of all instructions the thin forward layers executed
+// (ncu source page, profiles/r02_ncu_thin_conv_before.txt).  The lane keeps one column pair per sub-box:
+// acc[sub] = {sum even ch, sum odd ch, sum of squares even, odd}.  Rows that are never written must hold zeros.
+__host__ __device__ inline uint32_t tc3_park_floats(int BN, int CS) {
+  const uint32_t a = 8u * (uint32_t)BN, b = 512u * (uint32_t)(BN / CS);
+  return a > b ? a : b;
+}
+template <int PITCH>
+__device__ __forceinline__ void tc_stats_scan(const uint8_t* tile, uint32_t sub_bytes, int nsub, int q, int lane,
+                                              float (&acc)[4][4]) {
+  constexpr int RPL = 128 / PITCH;               // rows per load instruction
+  constexpr int CPW = PITCH / 4;                 // column pairs per row
+  constexpr uint32_t SMASK = PITCH == 128 ? 7u : 3u;
+  const uint32_t base = (uint32_t)(32 * q + lane / CPW) * PITCH + (uint32_t)(lane % CPW) * 4u;
+  // (eight loads per trip = one swizzle period; not unrolled further: code size, see tc_mma_taps_resident)
+#pragma unroll
+  for (int sub = 0; sub < 4; ++sub) {
+    if (sub < nsub) {
+      const uint8_t* tp = tile + (uint32_t)sub * sub_bytes;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32 / RPL; i0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = (base ^ (((uint32_t)k & SMASK) << 4)) + (uint32_t)(i0 + k) * 128u;
+          const float2 x2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tp + off));
+          a0 += x2.x; a1 += x2.y; b0 = fmaf(x2.x, x2.x, b0); b1 = fmaf(x2.y, x2.y, b1);
+        }
+      }
+      acc[sub][0] += a0; acc[sub][1] += a1; acc[sub][2] += b0; acc[sub][3] += b1;
+    }
+  }
+}
+
 struct TcConv3Params {
   int B, H, W, K, N;
   int KC, BN, CS;
@@ -760,6 +861,11 @@ struct TcConv3Params {
   // both sources, fp32 second epilogue operand
   int a_lo, b_lo, a2_lo, b2_lo;
   const float* tf;
+  int dual;                     // 1: two MMA-issuing warps take alternate super tiles.  Only when an issuer that runs one
+                                // super tile ahead can never be a whole ring round ahead of the other (mbarrier parity
+                                // waits cannot tell round r from round r - 2): resident weights and a_stages >= 2 x the A
+                                // slots of one super tile
+  int nstg;                     // bf16 staging tiles per epilogue group (2: the TMA store of tile i drains under tile i + 1)
 };
 
 // S = epilogue sets.  A set is one group of 4 warps per pixel tile of the pair; super tile i of a CTA is drained
@@ -767,7 +873,7 @@ struct TcConv3Params {
 // epilogue's per-warp latency chain, not by the tensor pipe (FU_TC_DBG timeline: ~3600 cycles per super tile of
 // which the MMAs take 2000), so they run two sets.
 template <int S, bool F32 = false>
-__global__ void __launch_bounds__(64 + 256 * S, 1)
+__global__ void __launch_bounds__(96 + 256 * S, 1)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB2, const TcConv3Params p) {
@@ -776,6 +882,11 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Warp roles.  The epilogue warps come FIRST and the TMA producer / MMA issuer LAST: the SM sub-partition schedulers
+  // prefer the highest warp id among eligible warps, and the single MMA-issuing thread is the critical path of the
+  // thin layers -- as warp 1 it was starved by the (instruction-heavy) epilogue warps sharing its scheduler (ncu:
+  // ~1000 idle tensor-pipe cycles between tiles, profiles/r02_ncu_thin_conv_before.txt).
+  constexpr int prod_warp = 8 * S, mma_warp = 8 * S + 1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2u;
   const uint32_t b_bytes = (uint32_t)p.BN * row_bytes;
   const int rchunks = p.K / p.KC;                                  // real channel chunks
@@ -791,12 +902,17 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int wtiles = wchunks * 9 + (p.res ? wchunks : 0);          // resident weight tiles: 9 taps (+ the 1x1) per chunk
   const uint32_t b_region = p.resident ? (uint32_t)wtiles * b_bytes : (uint32_t)p.b_stages * b_bytes;
   const uint32_t staging_off = b_off + b_region;
+  // bf16: 128 x BN tile, double buffered when BN <= 64 (the TMA store of tile i drains while tile i + 1 is converted);
   // F32: 128 rows x 32 fp32 columns (16 KB), two per epilogue group
-  const uint32_t staging_bytes = F32 ? 32768u : 128u * (uint32_t)p.BN * 2u;      // one per epilogue group
+  const uint32_t tile_bytes = 128u * (uint32_t)p.BN * 2u;
+  const int nstg = p.nstg;
+  const uint32_t staging_bytes = F32 ? 32768u : (uint32_t)nstg * tile_bytes;      // per epilogue group
   constexpr int NACC = 2 * S;              // TMEM accumulator stages (each: npair tiles of BN columns)
   const uint32_t vec_off = staging_off + (uint32_t)(S * p.npair) * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
-  const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;    // (F32) statistics partials [S*npair][4][2][BN] floats
-  const uint32_t bar_off = (stat_off + (uint32_t)(S * p.npair) * (F32 ? 8u : 2u) * (uint32_t)p.BN * 4u + 7u) & ~7u;
+  // statistics partials per epilogue group (tc3_park_floats): F32 [4][2][BN] floats; bf16 one float4 per (thread, sub-box)
+  const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;
+  const uint32_t park_floats = tc3_park_floats(p.BN, p.CS);
+  const uint32_t bar_off = (stat_off + (uint32_t)(S * p.npair) * park_floats * 4u + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(8 + s); };
@@ -821,7 +937,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
     if (p.res) { ptx::prefetch_tmap(&tmA2); ptx::prefetch_tmap(&tmB2); }
   }
-  if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  if (warp == mma_warp) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
   {
     // per-channel epilogue vectors live in shared memory for the whole (persistent) CTA: the epilogue warps
     // run one per scheduler, so a global/L1 load in their dependency chain is an exposed long-scoreboard stall
@@ -833,7 +949,12 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     if (F32) {
       float* park = reinterpret_cast<float*>(smem + stat_off);
-      for (int i = threadIdx.x; i < S * p.npair * 8 * p.BN; i += blockDim.x) park[i] = 0.f;
+      for (int i = threadIdx.x; i < S * p.npair * (int)park_floats; i += blockDim.x) park[i] = 0.f;
+    } else if (p.stat) {
+      // rows of the staging tiles that no valid pixel maps to are never written: they must read as zeros in the
+      // statistics scan
+      uint4* z = reinterpret_cast<uint4*>(smem + staging_off);
+      for (int i = threadIdx.x; i < (int)((uint32_t)(S * p.npair) * staging_bytes / 16u); i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   ptx::tc_fence_before();
@@ -860,7 +981,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     w0 = (r % p.tiles_w) * p.two;
   };
 
-  if (warp == 0) {
+  if (warp == prod_warp) {
     // ------------------------------ TMA producer (whole warp loops, one elected lane issues) -----
     {
       if (p.resident && ptx::elect_one()) {
@@ -942,13 +1063,16 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    // The whole warp runs the loop; one elected lane issues.  The issue path is the critical resource of
-    // this kernel (measured with the FU_TC_DBG timeline: ~100 SASS instructions per tap made every MMA cost
-    // 120-215 cycles instead of 16-64), so everything address-like is reduced to 64-bit descriptor adds
-    // prepared outside the tap loop and the K steps are unrolled at compile time.
+  } else if (warp >= mma_warp) {
+    // ------------------------------ MMA issuers (two warps, alternating super tiles) ------------------------------
+    // The whole warp runs the loop; one elected lane issues.  Between two super tiles an issuer spends ~2000 cycles in
+    // serial barrier round trips (accumulator free -> fence -> operands landed -> ... -> commit; each already-complete
+    // mbarrier wait costs 300-500 cycles through the busy shared-memory pipe) while the tensor pipe, whose queue holds
+    // only ~4 MMAs, runs dry: FU_TC_DBG timeline of 32->32 @192x192: 1750 cycles of MMAs per 4050-cycle super tile.
+    // Two issuers take alternate super tiles (each tracks the rings of the tiles it skips), so one issuer's round trips
+    // overlap the other's MMAs; the MMAs of consecutive super tiles go to different accumulators and are independent.
     {
+      const int mw = warp - mma_warp;               // issuer 0 / 1
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
@@ -957,16 +1081,27 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int npair = p.npair, resident = p.resident, halo1 = p.halo1, a_stages = p.a_stages, b_stages = p.b_stages;
       const uint32_t BNc = (uint32_t)p.BN;
       const uint32_t a_tile16 = p.a_tile_bytes >> 4, b16 = b_bytes >> 4;
-      // row offset (in 16-byte units) of each tap's view into the halo tile
-      uint32_t rowoff16[9];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap)
-        rowoff16[tap] = ((uint32_t)((tap / 3) * p.twb + (halo1 ? tap % 3 : 0)) * row_bytes) >> 4;
+      // offset (in 16-byte units) of a tap's view into the halo tile: kh image rows + kw pixels
+      const uint32_t kh16 = ((uint32_t)p.twb * row_bytes) >> 4, kw16 = halo1 ? (row_bytes >> 4) : 0u;
+      const uint32_t dhi = (uint32_t)(dbase >> 32), dlo = (uint32_t)dbase;      // descriptor words shared by every tile
       if (resident) { ptx::mbar_wait(res_bar, 0); ptx::tc_fence_after(); }
-      for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
+      // ring slots one super tile consumes (the same for every super tile)
+      const int a_per_tile = cchunks * groups + (p.res ? cchunks : 0);
+      const int b_per_tile = resident ? 0 : cchunks * groups * taps_per_group + (p.res ? cchunks : 0);
+      int it = 0;
+      for (int st = blockIdx.x; st < total_super; st += gridDim.x, ++it) {
+        if (!p.dual) { if (mw) break; }
+        else if ((it & 1) != mw) {                  // the other issuer's super tile: step over its ring slots
+          as += a_per_tile; while (as >= a_stages) { as -= a_stages; aph ^= 1u; }
+          bs += b_per_tile; while (bs >= b_stages) { bs -= b_stages; bph ^= 1u; }
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
         const int sp = st / p.n_tiles;
         const bool two = npair == 2 && (sp * 2 + 1) < m_tiles;
+        if (lane == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 3);     // (dbg) arrived at the accumulator wait
         ptx::mbar_wait(t_empty(acc), acc_phase ^ 1u);
+        if (lane == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 1);     // (dbg) accumulator free, before the fence
         ptx::tc_fence_after();
         if (lane == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
         const uint32_t d0 = tmem_base + (uint32_t)(acc * npair) * BNc, d1 = d0 + BNc;
@@ -975,34 +1110,15 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int g = 0; g < groups; ++g) {
             ptx::mbar_wait(a_full(as), aph);
             if (lane == 0 && c == 0 && g == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
-            const uint64_t a_desc0 = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4);
+            const uint32_t a_lo0 = dlo + ((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4);
             const bool last_group = c == cchunks - 1 && g == groups - 1 && !p.res;
             if (resident) {
               // all 9 taps straight from the resident weight region: one elected section per A stage
               if (ptx::elect_one()) {
-                const uint64_t b_desc0 = dbase + (uint64_t)((smem_base + b_off + (uint32_t)(w_index(c) * 9) * b_bytes) >> 4);
-#pragma unroll
-                for (int tt = 0; tt < 9; ++tt) {
-                  if (!halo1 && (tt % 3) != g) continue;        // one A load per kw: only taps with kw == g
-                  const uint64_t ad = a_desc0 + rowoff16[tt], bd = b_desc0 + (uint64_t)(tt * b16);
-                  if (ksteps == 4) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                    }
-                  } else if (ksteps == 2) {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                    }
-                  } else {
-                    ptx::umma_bf16(d0, ad, bd, idesc, accum);
-                    if (two) ptx::umma_bf16(d1, ad + a_tile16, bd, idesc, accum);
-                  }
-                  accum = 1;
-                }
+                if (c == 0 && g == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 2);   // (dbg) first MMA about to issue
+                const uint32_t b_lo0 = dlo + ((smem_base + b_off + (uint32_t)(w_index(c) * 9) * b_bytes) >> 4);
+                // (halo1: all nine taps; otherwise one A load per kw and only the taps with kw == g)
+                tc_mma_taps_resident(ksteps, d0, d1, two, a_lo0, a_tile16, b_lo0, b16, kh16, kw16, halo1 ? -1 : g, dhi, idesc, accum);
                 ptx::umma_commit(a_empty(as));
                 if (last_group) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
               }
@@ -1013,24 +1129,12 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int tap = halo1 ? tt : tt * 3 + g;
                 ptx::mbar_wait(b_full(bs), bph);
                 if (ptx::elect_one()) {
-                  const uint64_t ad = a_desc0 + rowoff16[tap];
-                  const uint64_t bd = dbase + (uint64_t)((smem_base + b_off + (uint32_t)bs * b_bytes) >> 4);
-                  if (ksteps == 4) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                    }
-                  } else if (ksteps == 2) {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                      ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                      if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                    }
-                  } else {
-                    ptx::umma_bf16(d0, ad, bd, idesc, accum);
-                    if (two) ptx::umma_bf16(d1, ad + a_tile16, bd, idesc, accum);
-                  }
+                  const uint32_t kh = (uint32_t)tap / 3u, kw = (uint32_t)tap - 3u * kh;
+                  const uint32_t a_lo = a_lo0 + kh * kh16 + kw * kw16;
+                  const uint32_t b_lo = dlo + ((smem_base + b_off + (uint32_t)bs * b_bytes) >> 4);
+                  if (ksteps == 4) tc_mma_tap<4>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
+                  else if (ksteps == 2) tc_mma_tap<2>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
+                  else tc_mma_tap<1>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
                   ptx::umma_commit(b_empty(bs));
                   if (tt == taps_per_group - 1) {
                     ptx::umma_commit(a_empty(as));
@@ -1051,15 +1155,14 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_wait(a_full(as), aph);
             if (!resident) ptx::mbar_wait(b_full(bs), bph);
             if (ptx::elect_one()) {
-              const uint64_t ad = dbase + (uint64_t)((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4) +
-                                  (uint64_t)((uint32_t)((p.twb + 1) * row_bytes) >> 4);      // view (kh,kw) = (1,1)
+              const uint32_t a_lo = dlo + ((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4) +
+                                    (((uint32_t)(p.twb + 1) * row_bytes) >> 4);               // view (kh,kw) = (1,1)
               const uint32_t b_addr = resident ? smem_base + b_off + (uint32_t)(wchunks * 9 + w_index(c)) * b_bytes
                                                : smem_base + b_off + (uint32_t)bs * b_bytes;
-              const uint64_t bd = dbase + (uint64_t)(b_addr >> 4);
-              for (int j = 0; j < ksteps; ++j) {
-                ptx::umma_bf16(d0, ad + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-                if (two) ptx::umma_bf16(d1, ad + a_tile16 + 2 * j, bd + 2 * j, idesc, accum | (uint32_t)j);
-              }
+              const uint32_t b_lo = dlo + (b_addr >> 4);
+              if (ksteps == 4) tc_mma_tap<4>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
+              else if (ksteps == 2) tc_mma_tap<2>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
+              else tc_mma_tap<1>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
               if (!resident) ptx::umma_commit(b_empty(bs));
               ptx::umma_commit(a_empty(as));
               if (c == cchunks - 1) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
@@ -1075,13 +1178,13 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ------------------------------ epilogue: S sets of one group of 4 warps per pixel tile of the pair -----
-    const int gi = (warp - 2) >> 2;           // group index 0 .. 2S-1
+    const int gi = warp >> 2;           // group index 0 .. 2S-1
     const int grp = gi & 1;                   // which pixel tile of the super tile
     const int set = gi >> 1;                  // this set drains super tiles set, set + S, ... of the CTA
     if (grp < p.npair) {
       const int q = warp & 3;                 // TMEM lane quadrant this warp may access
       const int row = q * 32 + lane;
-      const int et = (threadIdx.x - 64) & 127;   // thread index within the group
+      const int et = threadIdx.x & 127;   // thread index within the group
       const int bar_id = 1 + gi;
       const uint32_t pitch = (uint32_t)p.CS * 2u;
       const uint32_t swz_mask = pitch == 128 ? 7u : (pitch == 64 ? 3u : 1u);
@@ -1094,28 +1197,37 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool row_ok = wq < p.two && hi < p.th;
       const int mr = hi * p.two + wq;               // compacted staging row (valid rows only)
       const int rows_valid = p.th * p.two;
-      // statistics ownership: column pair cp, row group rg (BN/2 rows each)
-      const int cpairs = p.BN >> 1;
-      const int cp = et % cpairs, rg = et / cpairs;
-      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+      // statistics: this lane's column pair of every sub-box over the rows its warp scans (tc_stats_scan)
+      const int nsub = p.BN / p.CS;
+      float sacc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f; }
       int s_nb = -1;
-      // Deterministic flush: every (column pair, row group) thread parks its partial sums in the (idle)
-      // staging tile, then one thread per column adds the row groups in a fixed order.  Float atomics here
-      // would make BN statistics differ by ~1e-7 run to run, which bf16 rounding + the network amplify into
-      // visibly different gradients (tools/diag_repeat2.py).
+      int sbuf = 0;                                 // staging buffer of the next tile (bf16, BN <= 64: double buffered)
+      // Deterministic flush: every thread parks its partial sums, then one thread per (statistic, channel) adds the
+      // partials of the 4 warps (and, for 64-byte rows, of the two lanes that share a column pair) in a fixed order.
+      // Float atomics here would make BN statistics differ by ~1e-7 run to run, which bf16 rounding + the network
+      // amplify into visibly different gradients (tools/diag_repeat2.py).
       auto flush_stats = [&]() {
         if (p.stat && s_nb >= 0) {
-          float* park = reinterpret_cast<float*>(staging);        // [rgroups][2][BN] floats <= 128*BN*2 bytes
-          const int rgroups = 128 / cpairs;
+          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * (int)park_floats;   // [128 threads][nsub][4]
           ptx::named_bar_sync(bar_id, 128);
-          park[(rg * 2 + 0) * p.BN + 2 * cp] = s0; park[(rg * 2 + 0) * p.BN + 2 * cp + 1] = s1;
-          park[(rg * 2 + 1) * p.BN + 2 * cp] = q0; park[(rg * 2 + 1) * p.BN + 2 * cp + 1] = q1;
-          s0 = s1 = q0 = q1 = 0.f;
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub)
+            if (sub < nsub) {
+              *reinterpret_cast<float4*>(park + (et * nsub + sub) * 4) = make_float4(sacc[sub][0], sacc[sub][1], sacc[sub][2], sacc[sub][3]);
+              sacc[sub][0] = sacc[sub][1] = sacc[sub][2] = sacc[sub][3] = 0.f;
+            }
           ptx::named_bar_sync(bar_id, 128);
+          const int cpw = p.CS / 2, rpl = 64 / p.CS;          // column pairs per row, rows per load (see tc_stats_scan)
           for (int i = et; i < 2 * p.BN; i += 128) {
             const int which = i / p.BN, c = i - which * p.BN;
+            const int sub = c / p.CS, cc = c - sub * p.CS;
+            const int comp = (cc & 1) + 2 * which;
             float v = 0.f;
-            for (int r = 0; r < rgroups; ++r) v += park[(r * 2 + which) * p.BN + c];
+            for (int w = 0; w < 4; ++w)
+              for (int ro = 0; ro < rpl; ++ro)
+                v += park[((w * 32 + ro * cpw + (cc >> 1)) * nsub + sub) * 4 + comp];
             atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
           }
           ptx::named_bar_sync(bar_id, 128);
@@ -1127,7 +1239,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int mt = sp * p.npair + grp;
         if constexpr (F32) {
           // ---- fp32 output (parity mode): 32-column chunks through two 16 KB staging tiles ----
-          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * 8 * p.BN;      // [4 row groups][2][BN]
+          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * (int)park_floats;      // [4 row groups][2][BN]
           if (p.stat && nb != s_nb) {
             if (s_nb >= 0) {
               ptx::named_bar_sync(bar_id, 128);
@@ -1218,6 +1330,14 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
+        uint8_t* stg = staging + (uint32_t)sbuf * tile_bytes;
+        const uint32_t stg_addr = staging_addr + (uint32_t)sbuf * tile_bytes;
+        if (nstg == 2 && mt < m_tiles) {
+          // double-buffered staging: only the store issued two tiles ago must have finished reading this buffer
+          if (et == 0) ptx::tma_store_wait_read1();
+          ptx::named_bar_sync(bar_id, 128);
+          sbuf ^= 1;
+        }
         ptx::mbar_wait(t_full(acc), acc_phase);
         ptx::tc_fence_after();
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
@@ -1273,7 +1393,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 const uint32_t logical = (uint32_t)mr * pitch + byte_in_row + (uint32_t)g4 * 16u;
                 const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
-                *reinterpret_cast<uint4*>(staging + (uint32_t)sub * sub_bytes + phys) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(stg + (uint32_t)sub * sub_bytes + phys) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
@@ -1290,35 +1410,24 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::named_bar_sync(bar_id, 128);
           if (et == 0) {
             for (int s2 = 0; s2 < p.BN / p.CS; ++s2)
-              ptx::tma_store_4d(&tmC, staging_addr + (uint32_t)s2 * sub_bytes, nb + s2 * p.CS, w0, h0, n);
+              ptx::tma_store_4d(&tmC, stg_addr + (uint32_t)s2 * sub_bytes, nb + s2 * p.CS, w0, h0, n);
             ptx::tma_store_commit();
           }
           if (p.stat) {
-            // per-channel sum / sum of squares of the stored (bf16) tile: thread = (column pair, row group)
-            const int c = 2 * cp;
-            const int sub = c / p.CS;
-            const uint32_t bir = (uint32_t)(c % p.CS) * 2u;
-            const int r0 = rg * cpairs;
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll 4
-            for (int r = r0; r < r0 + cpairs; ++r) {
-              if (r < rows_valid) {
-                const uint32_t logical = (uint32_t)r * pitch + bir;
-                const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
-                const float2 x2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(staging + (uint32_t)sub * sub_bytes + phys));
-                a0 += x2.x; a1 += x2.y; b0 = fmaf(x2.x, x2.x, b0); b1 = fmaf(x2.y, x2.y, b1);
-              }
-            }
-            s0 += a0; s1 += a1; q0 += b0; q1 += b1;
+            // per-channel sum / sum of squares of the stored (bf16) tile; rows no pixel maps to hold zeros
+            if (pitch == 128) tc_stats_scan<128>(stg, sub_bytes, nsub, q, lane, sacc);
+            else tc_stats_scan<64>(stg, sub_bytes, nsub, q, lane, sacc);
           }
-          if (et == 0) ptx::tma_store_wait_read();   // staging may be overwritten after this
-          ptx::named_bar_sync(bar_id, 128);
+          if (nstg == 1) {
+            if (et == 0) ptx::tma_store_wait_read();   // staging may be overwritten after this
+            ptx::named_bar_sync(bar_id, 128);
+          }
           if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 3);
         }
       }
       if constexpr (F32) {
         if (p.stat && s_nb >= 0) {
-          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * 8 * p.BN;
+          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * (int)park_floats;
           ptx::named_bar_sync(bar_id, 128);
           for (int i = et; i < 2 * p.BN; i += 128) {
             const int which = i / p.BN, c = i - which * p.BN;
@@ -1336,7 +1445,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
+  if (warp == mma_warp) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ===========================================================================
@@ -2346,9 +2455,15 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   // (64->64 @96x96: 35 us without, 56 us with statistics): there two sets pay at every thin shape that fits.
   c.S = (p.BN <= 64 && (dir == 0 || (long long)K * p.BN <= 64 * 32) && p.npair == 2 && tc_env_int("FU_TC_EPI_SETS", 2) >= 2) ? 2 : 1;
   if (t.split) c.S = 1;            // fp32 staging: 32 KB per epilogue group
-  for (;; c.S = 1) {
-    const size_t staging = t.split ? (size_t)c.S * p.npair * 32768 : (size_t)c.S * p.npair * 128 * p.BN * 2;
-    const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * (t.split ? 32 : 8) * p.BN + 16 + 8 * 48;
+  // preference order when shared memory is short: (2 sets, 2 staging tiles) -> (2 sets, 1) -> (1 set, 2) -> (1 set, 1)
+  p.nstg = (p.BN <= 64 && !t.split && tc_env_int("FU_TC_STAGING2", 1)) ? 2 : 1;
+  const int want_S = c.S, want_nstg = p.nstg;
+  for (int attempt = 0;; ++attempt) {
+    if (attempt == 1) { if (want_S == 2 && want_nstg == 2) { c.S = 2; p.nstg = 1; } else continue; }
+    if (attempt == 2) { if (want_S == 2) { c.S = 1; p.nstg = want_nstg; } else continue; }
+    if (attempt == 3) { c.S = 1; p.nstg = 1; }
+    const size_t staging = t.split ? (size_t)c.S * p.npair * 32768 : (size_t)c.S * p.npair * 128 * p.BN * 2 * p.nstg;
+    const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * tc3_park_floats(p.BN, p.CS) * 4 + 16 + 8 * 48;
     p.resident = (p.n_tiles == 1 && fixed + wbytes + 2 * a_stage <= budget && tc_env_int("FU_TC_RESIDENT", 1)) ? 1 : 0;
     if (p.resident) {
       int as = (int)((budget - fixed - wbytes) / a_stage);
@@ -2357,7 +2472,7 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
       c.smem = fixed + wbytes + (size_t)p.a_stages * a_stage;
       break;
     }
-    if (c.S == 2) continue;          // retry with one set before giving up residency
+    if (attempt < 3) continue;       // retry with less epilogue staging before giving up residency
     p.a_stages = 2;
     if (fixed + 3 * a_stage + 6 * b_bytes <= budget) p.a_stages = 3;
     if (fixed + (size_t)p.a_stages * a_stage + 2 * b_bytes > budget) { tc_err() = "halo tile does not fit shared memory"; return nullptr; }
@@ -2374,6 +2489,11 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   c.grid = (int)(total_super < sms ? total_super : sms);
+  {
+    const int vchunks = (K / p.KC) * (t.split ? 3 : 1);
+    const int a_per_tile = vchunks * (p.halo1 ? 1 : 3) + (p.res ? vchunks : 0);
+    p.dual = (p.resident && p.a_stages >= 2 * a_per_tile && tc_env_int("FU_TC_DUAL", 1)) ? 1 : 0;
+  }
   const long long Kw = t.split ? 2 * K : K;       // K width of the weight layouts ([hi | lo] in split mode)
   {
     long long dims[4] = {K + p.a_lo, W, H, B};
@@ -2426,9 +2546,9 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
     cudaMemsetAsync(dbg_buf, 0, 4 * 24 * 4 * sizeof(long long), stream);
   }
   c->p.dbg = dbg ? dbg_buf : nullptr;
-  if (c->f32) tc_conv3_kernel<1, true><<<c->grid, 64 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
-  else if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 64 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
-  else tc_conv3_kernel<1><<<c->grid, 64 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
+  if (c->f32) tc_conv3_kernel<1, true><<<c->grid, 96 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 96 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else tc_conv3_kernel<1><<<c->grid, 96 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
   if (dbg) {
     long long h[4 * 24 * 4];
     cudaStreamSynchronize(stream);
@@ -2437,8 +2557,9 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
     fprintf(stderr, "[tc_conv3 timeline, CTA 0, cycles rel. to first producer issue] twb=%d th=%d BN=%d KC=%d pair=%d resident=%d a_stages=%d b_stages=%d grid=%d\n",
             c->p.twb, c->p.th, c->p.BN, c->p.KC, c->p.npair, c->p.resident, c->p.a_stages, c->p.b_stages, c->grid);
     for (int i = 0; i < 12; ++i)
-      fprintf(stderr, "super %2d: prod %7lld | mma tmem_free %7lld a_full %7lld committed %7lld | epi0 start %7lld t_full %7lld drained %7lld stored %7lld | epi1 t_full %7lld stored %7lld\n",
-              i, h[(0 * 24 + i) * 4] - t0, h[(1 * 24 + i) * 4] - t0, h[(1 * 24 + i) * 4 + 1] - t0, h[(1 * 24 + i) * 4 + 2] - t0,
+      fprintf(stderr, "super %2d: prod %7lld | mma at_wait %7lld acc_free %7lld fenced %7lld a_full %7lld first_mma %7lld committed %7lld | epi0 start %7lld t_full %7lld drained %7lld stored %7lld | epi1 t_full %7lld stored %7lld\n",
+              i, h[(0 * 24 + i) * 4] - t0, h[(0 * 24 + i) * 4 + 3] - t0, h[(0 * 24 + i) * 4 + 1] - t0, h[(1 * 24 + i) * 4] - t0,
+              h[(1 * 24 + i) * 4 + 1] - t0, h[(0 * 24 + i) * 4 + 2] - t0, h[(1 * 24 + i) * 4 + 2] - t0,
               h[(2 * 24 + i) * 4] - t0, h[(2 * 24 + i) * 4 + 1] - t0, h[(2 * 24 + i) * 4 + 2] - t0, h[(2 * 24 + i) * 4 + 3] - t0,
               h[(3 * 24 + i) * 4 + 1] - t0, h[(3 * 24 + i) * 4 + 3] - t0);
   }

@@ -527,7 +527,9 @@ def test_eager_forward_after_graph_replays_uses_the_updated_weights(pkg, precisi
             outs.append((seg.clone(), heat.clone()))
             net.train()
         vals[mode] = outs
-    tol = 1e-4 if precision == "fp32" else 3e-2
+    # (six SGD steps at lr 0.1: the two runs differ by the order of the split-K / statistics atomics; weights that are one
+    #  optimizer step old would differ by ~1e-1)
+    tol = 2e-3 if precision == "fp32" else 3e-2
     for (se, he), (sg, hg) in zip(vals["eager"], vals["graph"]):
         assert rel_l2(sg.cpu(), se.cpu()) < tol and rel_l2(hg.cpu(), he.cpu()) < tol
     # the validation outputs must actually move between epochs (otherwise the check above proves nothing)

@@ -87,13 +87,13 @@ def test_training_step_matches_the_reference_at_full_size(pkg, name, precision):
         nrm = float(p.grad.double().norm()) / (float(rec["grad_norm/" + n][0]) + 1e-300)
         # error against the fp64 truth; floor = the fp32 reference's own distance to it
         per[n] = (rel_l2(smp, ref64), _cos(smp, ref64), nrm, p.dim(), rel_l2(ref, ref64))
-        norms[n] = (float(ref64.double().norm()), float(smp.double().norm()))
+        norms[n] = (float(ref64.double().norm()), float(smp.double().norm()), float(ref.double().norm()))
     # gradients that vanish identically (dual_b2_1440: with heatmap_wgt = 1 the loss is the NCC, which is invariant to
     # the per-channel constants the last block's biases add, so their gradient is pure rounding noise in every
-    # implementation) are held to an absolute bound instead of a relative one
+    # implementation) are held to an absolute bound instead of a relative one: ten times the fp32 reference's own noise
     med = sorted(v[0] for v in norms.values())[len(norms) // 2]
     for n in [k for k, v in norms.items() if v[0] < 1e-6 * med]:
-        assert norms[n][1] < (1e-2 if precision == "bf16" else 1e-4) * med, (n, norms[n], med)
+        assert norms[n][1] < 10 * norms[n][2] + 1e-4 * med, (n, norms[n], med)
         del per[n]
     worst = sorted(per.items(), key=lambda kv: -kv[1][0])[:5]
     cnt = net.engine_counters()
