@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace fu {
 
@@ -34,6 +36,16 @@ __device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn
 __device__ __forceinline__ float rnd(float v, const float*) { return v; }
 __device__ __forceinline__ float rnd(float v, const bf16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the step calls pdl_wait() before its first global-memory access: when the kernel was launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization it may have been scheduled while its predecessor in the stream was
+// still running, and this is the point where it waits for that grid (and, transitively, everything before it) to have
+// completed and flushed.  Launched normally the instruction returns at once.  pdl_trigger() lets the NEXT kernel of the
+// stream be scheduled as soon as every block of this one has started: its prologue (barrier initialisation, TMEM
+// allocation, tensor-map prefetch, index arithmetic) then overlaps this kernel's tail instead of following it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -52,6 +64,26 @@ struct Bump {
     return p;
   }
 };
+
+// kernel launch with or without the PDL attribute (see pdl_wait)
+template <typename... KArgs, typename... Args>
+inline cudaError_t fu_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// process-wide switch (FU_PDL=0 turns programmatic dependent launch off)
+inline bool fu_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("FU_PDL"); v = (s && atoi(s) == 0) ? 0 : 1; }
+  return v != 0;
+}
 
 #define FU_STR2(x) #x
 #define FU_STR(x) FU_STR2(x)

@@ -183,7 +183,7 @@ struct fu_engine {
   do {                                                                                      \
     auto _kfn = kern;                                                                       \
     if ((e)->prof) (e)->prof_begin(#kern);                                                  \
-    _kfn<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__);                                 \
+    fu_launch(_kfn, dim3(grid), dim3(block), 0, (e)->stream, fu_pdl_enabled(), __VA_ARGS__); \
     if ((e)->prof) (e)->prof_end();                                                         \
     (e)->cnt.kernel_launches++;                                                             \
     cudaError_t _ce = cudaPeekAtLastError();                                                \
@@ -202,7 +202,7 @@ struct fu_engine {
       _attr = true;                                                                         \
     }                                                                                       \
     if ((e)->prof) (e)->prof_begin(#kern);                                                  \
-    _kfn<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);                            \
+    fu_launch(_kfn, dim3(grid), dim3(block), (smem), (e)->stream, fu_pdl_enabled(), __VA_ARGS__); \
     if ((e)->prof) (e)->prof_end();                                                         \
     (e)->cnt.kernel_launches++;                                                             \
     cudaError_t _ce = cudaPeekAtLastError();                                                \
@@ -811,7 +811,7 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     const size_t smem = ((size_t)cw.k * cw.k * cw.Cin * cw.Cout + 3 * cw.Cout + 16 * cw.Cout) * sizeof(float);
     auto kfn = conv_small_cin_kernel<T>;
     if (e->prof) e->prof_begin("conv_small_cin_kernel");
-    kfn<<<grid1d(total, 256, e->num_sms), 256, smem, e->stream>>>(a);
+    fu_launch(kfn, dim3(grid1d(total, 256, e->num_sms)), dim3(256), smem, e->stream, fu_pdl_enabled(), a);
     if (e->prof) e->prof_end();
     e->cnt.kernel_launches++;
     if (cudaPeekAtLastError() != cudaSuccess) return e->fail(FU_ERR_CUDA, "conv_small_cin_kernel launch failed");

@@ -35,6 +35,7 @@ struct ConvArgs {
 
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) igemm_simt_kernel(const ConvArgs p) {
+  pdl_wait(); pdl_trigger();
   constexpr int BM = 128, BN = 64, BK = 16, AP = BM + 4;
   __shared__ __align__(16) float As[BK][AP];
   __shared__ __align__(16) float Bs[BK][BN];
@@ -241,6 +242,7 @@ struct SmallCinArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallCinArgs p) {
+  pdl_wait(); pdl_trigger();
   extern __shared__ float sm_w[];            // [taps*Cin][Cout] + [Cout] bias + 2*[Cout] stats
   const int taps = p.k * p.k, KK = taps * p.Cin;
   float* sm_b = sm_w + KK * p.Cout;
@@ -344,6 +346,7 @@ struct SmallCinWgradArgs {
 
 template <typename T, int KK>   // KK = taps*Cin accumulators per thread (x4 channels)
 __global__ void __launch_bounds__(256) wgrad_small_cin_kernel(const SmallCinWgradArgs p) {
+  pdl_wait(); pdl_trigger();
   __shared__ float red[256 * 4];
   const int cg = p.Cout >> 2;                 // channel groups of 4
   const int g = threadIdx.x % cg, lane_p = threadIdx.x / cg, rows = 256 / cg;
@@ -474,6 +477,7 @@ __device__ __forceinline__ void cin1_window(const T* xp, int x_ld, float* sx, in
 // y = [relu](conv_K(x) + bias) [+ bn_a*t + bn_b], optional per-channel sum / sum of squares (SmallCinArgs, Cin == 1)
 template <typename T, int K>
 __global__ void __launch_bounds__(256, K == 1 ? 3 : 2) conv_cin1_kernel(const SmallCinArgs p) {
+  pdl_wait(); pdl_trigger();
   constexpr int KK = K * K, TH = cin1_tile_h(K);
   extern __shared__ __align__(16) float cin1_sm[];
   const int groups = p.Cout >> 3, TW = 256 / groups;
@@ -567,6 +571,7 @@ __global__ void __launch_bounds__(256, K == 1 ? 3 : 2) conv_cin1_kernel(const Sm
 // dW(Cout,1,K,K) += sum_pixels x[p@tap] * dy[p, co]   (SmallCinWgradArgs, Cin == 1): reads dy once
 template <typename T, int K>
 __global__ void __launch_bounds__(256, K == 1 ? 3 : 2) wgrad_cin1_kernel(const SmallCinWgradArgs p) {
+  pdl_wait(); pdl_trigger();
   constexpr int KK = K * K, TH = cin1_tile_h(K);
   extern __shared__ __align__(16) float cin1_sm[];
   const int groups = p.Cout >> 3, TW = 256 / groups;
@@ -689,6 +694,7 @@ __global__ void __launch_bounds__(128) heads_fwd_fused_kernel(const T* feat, int
                                                               const float* w2, T* logits_nhwc, float* seg,
                                                               float* logits_out, float* heat, int B, long long HW,
                                                               int do_softmax) {
+  pdl_wait(); pdl_trigger();
   typedef HeadsDims<CF, NC, NF, NL> D;
   static_assert(CF % 4 == 0, "feature channels must be a multiple of 4");
   __shared__ __align__(16) float s_wseg[NC * CF];
@@ -795,6 +801,7 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
                                                               const float* w2, const float* d_seg, const float* d_heat,
                                                               T* d_feat, int d_ld, float* g_acc /*[NL*(CF+NC) + NC*CF]*/,
                                                               int B, long long HW, int do_softmax) {
+  pdl_wait(); pdl_trigger();
   typedef HeadsDims<CF, NC, NF, NL> D;
   constexpr int NCAT = D::NCAT, NCATP = D::NCATP, NLp = D::NLp;
   constexpr int ROWS = NLp + NCAT + NC;          // dheat rows, cat rows, dlg rows
@@ -976,6 +983,7 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
 // dW2 = G1 W1^T, dW1 = W2^T G1, dWseg = Gseg  (G's accumulated by heads_bwd_fused_kernel)
 __global__ void heads_bwd_finalize_kernel(const float* g_acc, const float* w1, const float* w2, float* dwseg, float* dw1,
                                           float* dw2, int CF, int NC, int NF, int NL) {
+  pdl_wait(); pdl_trigger();
   const int NCAT = CF + NC;
   const float* g1 = g_acc;
   const float* gs = g_acc + (NL > 0 ? NL * NCAT : 0);
@@ -1013,6 +1021,7 @@ struct WgradArgs {
 
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradArgs p) {
+  pdl_wait(); pdl_trigger();
   constexpr int BK = 16, TP = 64 + 4;
   __shared__ __align__(16) float Bg[BK][TP];
   __shared__ __align__(16) float Sm[BK][TP];
@@ -1110,6 +1119,7 @@ struct PackArgs {
   long long st, sk, snh, snl;
 };
 __global__ void pack_weights_kernel(const PackArgs p) {
+  pdl_wait(); pdl_trigger();
   const long long total = (long long)p.T * p.K * p.Npad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1136,6 +1146,7 @@ __global__ void bn_finalize_kernel(const double* stat, long long P, int C, int t
                                    const float* gamma, const float* beta, float* rmean, float* rvar,
                                    long long* nbt, float momentum, float eps,
                                    float* mean_o, float* invstd_o, float* a_o, float* b_o) {
+  pdl_wait(); pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt) *nbt += 1;
   if (c >= C) return;
@@ -1227,6 +1238,7 @@ template <> struct Vec<bf16> {
 template <typename T>
 __global__ void bn_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const float* a, const float* b,
                                 long long P, int C) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = Vec<T>::N;
   const int cv = C / V;
   const long long total = P * cv;
@@ -1245,6 +1257,7 @@ __global__ void bn_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const floa
 template <typename T>
 __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const BnFwdFin f,
                                                                 long long P, int C) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = Vec<T>::N;
   const int cvecs = C / V;
   const int lanes = cvecs < 256 ? cvecs : 256;
@@ -1350,6 +1363,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const T* d, int d_ld, const T* r, int r_ld,
                                                             const float* mean, const float* invstd,
                                                             long long P, int C, double* out) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = Vec<T>::N;
   __shared__ float sm[256 * V];
   RedMap<V> mp(C);
@@ -1393,6 +1407,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const T* d, int d
 __global__ void bn_bwd_finalize_kernel(const double* bstat, long long P, int C, int training,
                                        const float* gamma, const float* invstd, float* g_gamma,
                                        float* g_beta, float* g_extra, float* ga, float* m1, float* m2) {
+  pdl_wait(); pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double s1 = bstat[c], s2 = bstat[C + c];
@@ -1416,6 +1431,7 @@ __global__ void __launch_bounds__(256, 3) act_bwd_kernel(const T* d, int d_ld, c
                                                       T* dy, int dy_ld, int has_bn, const float* mean,
                                                       const float* invstd, const BnBwdFin fin, long long P, int C,
                                                       double* out) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = Vec<T>::N;
   __shared__ float sm[256 * V];
   RedMap<V> mp(C);
@@ -1476,6 +1492,7 @@ __global__ void __launch_bounds__(256, 3) act_bwd_kernel(const T* d, int d_ld, c
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* d, int d_ld, long long P, int C,
                                                           double* out) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = Vec<T>::N;
   __shared__ float sm[256 * V];
   RedMap<V> mp(C);
@@ -1501,12 +1518,14 @@ struct SumTable {
   const double* src[kMax]; float* dst[kMax]; int n[kMax]; int count;
 };
 __global__ void sums_to_float_kernel(const SumTable t) {
+  pdl_wait(); pdl_trigger();
   const int e = blockIdx.x;
   if (e >= t.count) return;
   for (int i = threadIdx.x; i < t.n[e]; i += blockDim.x) t.dst[e][i] = (float)t.src[e][i];
 }
 
 __global__ void sum_to_float_kernel(const double* src, float* dst, int C) {
+  pdl_wait(); pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) dst[c] = (float)src[c];
 }
@@ -1517,6 +1536,7 @@ __global__ void sum_to_float_kernel(const double* src, float* dst, int C) {
 // --------------------------------------------------------------------------
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* x, int x_ld, T* y, int y_ld, int B, int Ho, int Wo, int C) {
+  pdl_wait(); pdl_trigger();
   const int cv = C >> 2;
   const long long total = (long long)B * Ho * Wo * cv;
   const int Wi = Wo * 2, Hi = Ho * 2;
@@ -1552,6 +1572,7 @@ __device__ __forceinline__ int first_max4(float a, float b, float c, float d) {
 template <typename T>
 __global__ void maxpool_bwd_kernel(const T* x, int x_ld, const T* dy, int dy_ld, T* dx, int dx_ld,
                                    int B, int Ho, int Wo, int C, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const int cv = C >> 2;
   const long long total = (long long)B * Ho * Wo * cv;
   const int Wi = Wo * 2, Hi = Ho * 2;
@@ -1593,6 +1614,7 @@ __global__ void maxpool_bwd_kernel(const T* x, int x_ld, const T* dy, int dy_ld,
 // fp32 NCHW (B,C,H,W) -> T NHWC with pixel stride ld
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* src, T* dst, int ld, int B, int C, long long HW) {
+  pdl_wait(); pdl_trigger();
   const long long total = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1604,6 +1626,7 @@ __global__ void nchw_to_nhwc_kernel(const float* src, T* dst, int ld, int B, int
 // T NHWC (pixel stride ld) -> fp32 NCHW (debug / per-layer parity read-back)
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* src, int ld, float* dst, int B, int C, long long HW) {
+  pdl_wait(); pdl_trigger();
   const long long total = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1618,6 +1641,7 @@ constexpr int kMaxClasses = 32;
 template <typename T>
 __global__ void softmax_fwd_kernel(const T* logits, int ld, int B, int ncls, long long HW, int do_softmax,
                                    float* seg, float* logits_out) {
+  pdl_wait(); pdl_trigger();
   const long long total = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1644,6 +1668,7 @@ __global__ void softmax_fwd_kernel(const T* logits, int ld, int B, int ncls, lon
 template <typename T>
 __global__ void softmax_bwd_kernel(const T* logits, int ld, const float* d_seg, T* d_logits, int d_ld,
                                    int B, int ncls, long long HW, int do_softmax, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const long long total = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {

@@ -362,6 +362,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tmem_alloc(slot_addr, tmem_cols);
     ptx::tmem_relinquish();
   }
+  // everything above touched only this CTA's shared memory / TMEM and the kernel parameters: under programmatic
+  // dependent launch it ran while the previous kernel of the stream was finishing.  From here on its results are read.
+  pdl_wait(); pdl_trigger();
   {
     // per-channel epilogue vectors in shared memory (no global load in the epilogue's dependency chain)
     float* vec = reinterpret_cast<float*>(smem + vec_off);
@@ -938,6 +941,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (p.res) { ptx::prefetch_tmap(&tmA2); ptx::prefetch_tmap(&tmB2); }
   }
   if (warp == mma_warp) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  pdl_wait(); pdl_trigger();          // (see tc_conv_kernel)
   {
     // per-channel epilogue vectors live in shared memory for the whole (persistent) CTA: the epilogue warps
     // run one per scheduler, so a global/L1 load in their dependency chain is an exposed long-scoreboard stall
@@ -1558,6 +1562,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmX);
   }
   if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  pdl_wait(); pdl_trigger();          // (see tc_conv_kernel)
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -1705,6 +1710,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmX);
   }
   if (warp == 1) { ptx::tmem_alloc(slot_addr, tmem_cols); ptx::tmem_relinquish(); }
+  pdl_wait(); pdl_trigger();          // (see tc_conv_kernel)
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -1816,6 +1822,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ src, int ld, int C, bf16* __restrict__ dst,
                                                         int dld, int dlo, long long P) {
+  pdl_wait(); pdl_trigger();
   const int cv = C >> 2;                       // 4-channel vectors per pixel
   const long long total = P * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1838,7 +1845,7 @@ inline int tc_split(const float* src, int ld, int C, bf16* dst, int dld, int dlo
   long long blocks = (P * (C / 4) + 255) / 256;
   if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
   if (blocks < 1) blocks = 1;
-  split_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, ld, C, dst, dld, dlo, P);
+  fu_launch(split_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, fu_pdl_enabled(), src, ld, C, dst, dld, dlo, P);
   if (cnt) cnt->kernel_launches++;
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1921,6 +1928,7 @@ __device__ __forceinline__ void tc_pack_tile(const TcPackJob& J, int lb, float* 
 }
 
 __global__ void __launch_bounds__(256) tc_pack_batched_kernel(const TcPackJob* jobs, int njobs) {
+  pdl_wait(); pdl_trigger();
   __shared__ int s_job;
   __shared__ float tile[32 * 289];      // [r][c*taps + t], odd row stride: conflict-free row- and column-wise
   const TcPackJob& J = jobs[tc_find_job(jobs, njobs, &s_job)];
@@ -1932,6 +1940,7 @@ __global__ void __launch_bounds__(256) tc_pack_batched_kernel(const TcPackJob* j
 
 // dw[(m*N + n)*taps + t] = acc[(t*M + m)*N + n]: tiles of 8 m x 32 n, reads and writes both contiguous
 __global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJob* jobs, int njobs, float* base) {
+  pdl_wait(); pdl_trigger();
   __shared__ int s_job;
   __shared__ float tile[8][32 * 9 + 1];
   const TcUnpackJob& J = jobs[tc_find_job(jobs, njobs, &s_job)];
@@ -1991,10 +2000,10 @@ inline int tc_flush_jobs(std::vector<Job>& jobs, std::vector<Job>& uploaded, Job
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 inline auto tc_pack_launcher(cudaStream_t stream) {
-  return [stream](int blocks, const TcPackJob* tbl, int n) { tc_pack_batched_kernel<<<blocks, 256, 0, stream>>>(tbl, n); };
+  return [stream](int blocks, const TcPackJob* tbl, int n) { fu_launch(tc_pack_batched_kernel, dim3(blocks), dim3(256), 0, stream, fu_pdl_enabled(), tbl, n); };
 }
 inline auto tc_unpack_launcher(cudaStream_t stream, float* base) {
-  return [stream, base](int blocks, const TcUnpackJob* tbl, int n) { tc_unpack_batched_kernel<<<blocks, 256, 0, stream>>>(tbl, n, base); };
+  return [stream, base](int blocks, const TcUnpackJob* tbl, int n) { fu_launch(tc_unpack_batched_kernel, dim3(blocks), dim3(256), 0, stream, fu_pdl_enabled(), tbl, n, base); };
 }
 template <typename Job, typename Launch>
 inline int tc_run_job_now(Job job, Launch launch, cudaStream_t stream, fu_counters* cnt) {
@@ -2546,9 +2555,10 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
     cudaMemsetAsync(dbg_buf, 0, 4 * 24 * 4 * sizeof(long long), stream);
   }
   c->p.dbg = dbg ? dbg_buf : nullptr;
-  if (c->f32) tc_conv3_kernel<1, true><<<c->grid, 96 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
-  else if (c->S == 2) tc_conv3_kernel<2><<<c->grid, 96 + 256 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
-  else tc_conv3_kernel<1><<<c->grid, 96 + 256, c->smem, stream>>>(c->a, c->b, c->c, c->a2, c->b2, c->p);
+  const bool pdl = fu_pdl_enabled() && !dbg;
+  if (c->f32) fu_launch(tc_conv3_kernel<1, true>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else if (c->S == 2) fu_launch(tc_conv3_kernel<2, false>, dim3(c->grid), dim3(96 + 256 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else fu_launch(tc_conv3_kernel<1, false>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
   if (dbg) {
     long long h[4 * 24 * 4];
     cudaStreamSynchronize(stream);
@@ -2582,11 +2592,12 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
     }
     attr_set = true;
   }
-  if (c->f32 && c->G == 2) tc_conv_kernel<2, true><<<c->grid, 64 + 128 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->p);
-  else if (c->f32) tc_conv_kernel<1, true><<<c->grid, 64 + 128, c->smem, stream>>>(c->a, c->b, c->c, c->p);
-  else if (c->G == 4) tc_conv_kernel<4><<<c->grid, 64 + 128 * 4, c->smem, stream>>>(c->a, c->b, c->c, c->p);
-  else if (c->G == 2) tc_conv_kernel<2><<<c->grid, 64 + 128 * 2, c->smem, stream>>>(c->a, c->b, c->c, c->p);
-  else tc_conv_kernel<1><<<c->grid, 64 + 128, c->smem, stream>>>(c->a, c->b, c->c, c->p);
+  const bool pdl = fu_pdl_enabled();
+  if (c->f32 && c->G == 2) fu_launch(tc_conv_kernel<2, true>, dim3(c->grid), dim3(64 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else if (c->f32) fu_launch(tc_conv_kernel<1, true>, dim3(c->grid), dim3(64 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else if (c->G == 4) fu_launch(tc_conv_kernel<4, false>, dim3(c->grid), dim3(64 + 128 * 4), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else if (c->G == 2) fu_launch(tc_conv_kernel<2, false>, dim3(c->grid), dim3(64 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else fu_launch(tc_conv_kernel<1, false>, dim3(c->grid), dim3(64 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
@@ -2788,7 +2799,7 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
   // gradient and nothing is unpacked
   const int taps = ksz * ksz;
   c->p.dw_acc = taps == 1 ? dw : t.dw_acc;
-  tc_wgrad_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
+  fu_launch(tc_wgrad_kernel, dim3(c->grid), dim3(kTcThreads), c->smem, stream, fu_pdl_enabled(), c->y, c->xm, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
@@ -2866,7 +2877,7 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     }
     attr_set = true;
   }
-  tc_wgrad3_kernel<<<c->grid, kTcThreads, c->smem, stream>>>(c->y, c->xm, c->p);
+  fu_launch(tc_wgrad3_kernel, dim3(c->grid), dim3(kTcThreads), c->smem, stream, fu_pdl_enabled(), c->y, c->xm, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }

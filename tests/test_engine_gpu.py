@@ -527,10 +527,14 @@ def test_eager_forward_after_graph_replays_uses_the_updated_weights(pkg, precisi
             outs.append((seg.clone(), heat.clone()))
             net.train()
         vals[mode] = outs
-    # (six SGD steps at lr 0.1: the two runs differ by the order of the split-K / statistics atomics; weights that are one
-    #  optimizer step old would differ by ~1e-1)
-    tol = 2e-3 if precision == "fp32" else 3e-2
-    for (se, he), (sg, hg) in zip(vals["eager"], vals["graph"]):
-        assert rel_l2(sg.cpu(), se.cpu()) < tol and rel_l2(hg.cpu(), he.cpu()) < tol
-    # the validation outputs must actually move between epochs (otherwise the check above proves nothing)
+    # Criterion: packed weights that are ONE optimizer step old (of the two steps per "epoch" here) would put the graph
+    # run's validation output about half an epoch's movement away from the eager run's.  The two runs legitimately differ
+    # by the order of the split-K / statistics atomics amplified over six SGD steps at lr 0.1 (measured ~4e-3), so the
+    # bound is relative to how far the validation output moves between consecutive epochs of the eager run.
+    for k in range(1, 3):
+        move = rel_l2(vals["eager"][k][1].cpu(), vals["eager"][k - 1][1].cpu())
+        assert move > 0.02, move                                 # the check below must have something to detect
+        for which in (0, 1):
+            d = rel_l2(vals["graph"][k][which].cpu(), vals["eager"][k][which].cpu())
+            assert d < 0.1 * move, (k, which, d, move)
     assert rel_l2(vals["graph"][2][1].cpu(), vals["graph"][0][1].cpu()) > 0.1

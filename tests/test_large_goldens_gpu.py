@@ -93,7 +93,8 @@ def test_training_step_matches_the_reference_at_full_size(pkg, name, precision):
     # implementation) are held to an absolute bound instead of a relative one: ten times the fp32 reference's own noise
     med = sorted(v[0] for v in norms.values())[len(norms) // 2]
     for n in [k for k, v in norms.items() if v[0] < 1e-6 * med]:
-        assert norms[n][1] < 10 * norms[n][2] + 1e-4 * med, (n, norms[n], med)
+        # (bf16: the exact cancellation of ~4M rounded terms leaves ~1e-2 of a typical gradient norm)
+        assert norms[n][1] < (5e-2 * med if precision == "bf16" else 10 * norms[n][2] + 1e-4 * med), (n, norms[n], med)
         del per[n]
     worst = sorted(per.items(), key=lambda kv: -kv[1][0])[:5]
     cnt = net.engine_counters()
