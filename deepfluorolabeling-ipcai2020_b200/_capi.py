@@ -41,8 +41,12 @@ class FuLossDesc(C.Structure):
                 ("dice_wgt", C.c_float), ("heat_wgt", C.c_float)]
 
 
+# include/fluoro_unet.h: fu_bucket_callback(user, bucket, offset, numel)
+BUCKET_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int64, C.c_int64)
+
 EXPORTS = ["fu_engine_create", "fu_engine_destroy", "fu_last_error", "fu_num_tensors",
            "fu_tensor_get_info", "fu_grad_numel", "fu_bind_tensors", "fu_forward", "fu_backward",
+           "fu_set_bucket_callback", "fu_early_grad_numel",
            "fu_get_counters", "fu_build_info", "fu_test_conv", "fu_profile_enable", "fu_profile_report", "fu_debug_copy",
            "fu_loss_workspace_doubles", "fu_loss_forward", "fu_loss_backward",
            "fu_prep_tiles", "fu_heatmap_targets", "fu_ensemble_workspace_words", "fu_ensemble_combine",
@@ -80,6 +84,10 @@ def lib():
     L.fu_forward.restype = i32
     L.fu_backward.argtypes = [vp, vp, vp, vp, vp]
     L.fu_backward.restype = i32
+    L.fu_set_bucket_callback.argtypes = [vp, BUCKET_CALLBACK, vp, vp]
+    L.fu_set_bucket_callback.restype = i32
+    L.fu_early_grad_numel.argtypes = [vp]
+    L.fu_early_grad_numel.restype = i64
     L.fu_get_counters.argtypes = [vp, C.POINTER(FuCounters)]
     L.fu_get_counters.restype = i32
     L.fu_profile_enable.argtypes = [vp, i32]

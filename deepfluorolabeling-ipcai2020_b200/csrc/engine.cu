@@ -37,6 +37,7 @@ struct TensorSlot {
   fu_tensor_info info;
   void* data = nullptr;
   int64_t numel = 0;
+  bool late = false;   // gradient produced after the mid-backward point (shallow encoder levels): second all-reduce bucket
 };
 
 struct ConvW {
@@ -130,6 +131,16 @@ struct fu_engine {
   bool side_used = false;
   int use_side = 1;
   int num_sms = 148;
+  // Gradient buckets (data parallelism, fu_set_bucket_callback): flat[0, early_numel) holds every gradient that is
+  // final once the backward pass has left encoder level split_level() -- heads, the whole decoder, the deep encoder
+  // levels: 97 % of the parameters of the paper network -- so their all-reduce can run beside the shallow encoder
+  // levels' backward (the most expensive 40 % of the pass); the rest forms the tail bucket.
+  int64_t early_numel = 0;
+  fu_bucket_callback bucket_cb = nullptr;
+  void* bucket_user = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_mid_main = nullptr, ev_mid_side = nullptr;
+  bool creating_late = false;
   bool split = false;            // parity_tc: fp32 storage, tensor-core layers read split-bf16 twins (three MMA passes)
   // twins that are up to date: (view address, channels).  Forward activations stay valid until the next forward;
   // gradient tensors are produced once per backward.
@@ -269,11 +280,8 @@ int add_tensor(fu_engine* e, const std::string& name, std::vector<int64_t> shape
   s.numel = n;
   s.info.kind = kind;
   s.info.dtype = dtype;
-  s.info.grad_offset = -1;
-  if (has_grad) {
-    s.info.grad_offset = e->grad_numel;
-    e->grad_numel += (n + 3) / 4 * 4;  // keep every gradient 16-byte aligned
-  }
+  s.info.grad_offset = has_grad ? 0 : -1;   // offsets are assigned by assign_grad_offsets (early bucket first)
+  s.late = e->creating_late;
   e->tensors.push_back(s);
   return (int)e->tensors.size() - 1;
 }
@@ -318,16 +326,23 @@ int build_schema(fu_engine* e) {
   const fu_config& c = e->cfg;
   e->chans.clear();
   for (int i = 0; i < c.depth; ++i) e->chans.push_back(1 << (c.wf + i));
+  // "late" tensors: their gradients are written after backward_t's mid point (encoder levels below split_level() and
+  // the downsample convs feeding those levels' gradients back: downc[i] is processed at the end of level i + 1)
+  const int Ls = e->split_level();
   if (!c.max_pool)
-    for (int i = 0; i < c.depth; ++i)
+    for (int i = 0; i < c.depth; ++i) {
+      e->creating_late = i + 1 < Ls;
       e->downc.push_back(make_conv(e, "downsample_convs." + std::to_string(i), e->chans[i], e->chans[i], 2,
                                    true, false, i != c.depth - 1));
+    }
   int prev = c.in_channels;
   e->enc.resize(c.depth);
   for (int i = 0; i < c.depth; ++i) {
+    e->creating_late = i < Ls;
     make_block(e, e->enc[i], "down_path." + std::to_string(i), prev, e->chans[i]);
     prev = e->chans[i];
   }
+  e->creating_late = false;
   e->dec.resize(c.depth - 1);
   for (int j = 0; j < c.depth - 1; ++j) {
     const int lvl = c.depth - 2 - j;
@@ -347,6 +362,16 @@ int build_schema(fu_engine* e) {
     }
   }
   e->Cpad = pad_to(e->Cf + c.n_classes, 8);
+  // flat gradient layout: early bucket first, each gradient 16-byte aligned
+  e->grad_numel = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (auto& t : e->tensors)
+      if (t.info.grad_offset >= 0 && t.late == (pass == 1)) {
+        t.info.grad_offset = e->grad_numel;
+        e->grad_numel += (t.numel + 3) / 4 * 4;
+      }
+    if (pass == 0) e->early_numel = e->grad_numel;
+  }
   return FU_OK;
 }
 
@@ -1325,8 +1350,22 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     if (l == e->split_level() - 1) {
       // every layer at the deep levels (and the whole decoder) has its weight gradient on the side stream by now: 97 %
       // of the parameters.  Their unpack goes out behind them on that stream, beside the shallow encoder levels.
-      SideScope side(e);
-      if ((rc = flush_unpack(e, flat, 0))) return rc;
+      {
+        SideScope side(e);
+        if ((rc = flush_unpack(e, flat, 0))) return rc;
+      }
+      if (e->bucket_cb && e->early_numel > 0) {
+        // the early gradient bucket is final once the bias sums gathered so far are written (main stream) and the
+        // unpack above has run (side stream): hand it to the caller's all-reduce on the communication stream
+        if ((rc = flush_deferred_sums(e))) return rc;
+        CUDA_TRY(e, cudaEventRecord(e->ev_mid_main, e->stream));
+        CUDA_TRY(e, cudaStreamWaitEvent(e->comm_stream, e->ev_mid_main, 0));
+        if (e->side_used) {
+          CUDA_TRY(e, cudaEventRecord(e->ev_mid_side, e->side));
+          CUDA_TRY(e, cudaStreamWaitEvent(e->comm_stream, e->ev_mid_side, 0));
+        }
+        e->bucket_cb(e->bucket_user, 0, 0, e->early_numel);
+      }
     }
     bool in_sums = false;
     if ((rc = block_backward<T>(e, e->enc[l], x_in, gl, l == 0 ? nullptr : &pl.d_down[l], B, h, w, training, flat,
@@ -1458,6 +1497,8 @@ void fu_engine_destroy(fu_engine* e) {
   if (e->side) cudaStreamDestroy(e->side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->ev_mid_main) cudaEventDestroy(e->ev_mid_main);
+  if (e->ev_mid_side) cudaEventDestroy(e->ev_mid_side);
   if (e->pack_pin) cudaFreeHost(e->pack_pin);
   if (e->unpack_pin) cudaFreeHost(e->unpack_pin);
   delete e;
@@ -1539,6 +1580,20 @@ int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* fl
   e->cnt.last_bwd_launches = e->cnt.kernel_launches - l0;
   return FU_OK;
 }
+
+int fu_set_bucket_callback(fu_engine* e, fu_bucket_callback cb, void* user, void* comm_stream) {
+  if (!e) return FU_ERR_ARG;
+  if (cb && !comm_stream) return e->fail(FU_ERR_ARG, "fu_set_bucket_callback: a communication stream is required");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (cb && !e->ev_mid_main) {
+    CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_mid_main, cudaEventDisableTiming));
+    CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_mid_side, cudaEventDisableTiming));
+  }
+  e->bucket_cb = cb; e->bucket_user = user; e->comm_stream = reinterpret_cast<cudaStream_t>(comm_stream);
+  return FU_OK;
+}
+
+int64_t fu_early_grad_numel(const fu_engine* e) { return e ? e->early_numel : FU_ERR_ARG; }
 
 int fu_get_counters(const fu_engine* e, fu_counters* out) {
   if (!e || !out) return FU_ERR_ARG;

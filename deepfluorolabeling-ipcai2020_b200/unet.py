@@ -169,6 +169,12 @@ class UNet(nn.Module):
         self._last_logits = None
         self.keep_logits = False      # when True, forward also stores seg_x (unet.py:176) in .last_logits
         self.grad_hook = None         # callable(flat_fp32_grads) run before gradients are handed to autograd
+        # callable(flat, offset, numel) run MID-backward, on `bucket_stream`, as soon as flat[offset:offset+numel] (the
+        # early gradient bucket: heads, decoder, deep encoder levels) is final; see parallel.data_parallel(overlap=True)
+        self.grad_bucket_hook = None
+        self.bucket_stream = None
+        self._bucket_cb = None        # keeps the ctypes trampoline alive
+        self._bucket_cb_key = None
 
     # ------------------------------------------------------------------
     # engine plumbing
@@ -221,6 +227,7 @@ class UNet(nn.Module):
         self._grad_numel = int(L.fu_grad_numel(handle))
         self._bound_ptrs = None
         self._state_cache = None
+        self._bucket_cb_key = None
 
     def _state_tensors(self):
         """Parameters and buffers in engine-schema order.  Walking the module tree costs ~0.4 ms of Python per
@@ -322,6 +329,7 @@ class UNet(nn.Module):
             return g.contiguous().float()
         d_seg, d_heat = prep(d_seg), prep(d_heat)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        self._install_bucket_callback(flat)
         rc = L.fu_backward(self._handle, d_seg.data_ptr() if d_seg is not None else None,
                            d_heat.data_ptr() if d_heat is not None else None, flat.data_ptr(), stream)
         if rc != 0:
@@ -334,6 +342,35 @@ class UNet(nn.Module):
         for name, shape, numel, off in self._grad_params:
             grads.append(flat[off:off + numel].view(shape))
         return grads
+
+    def _install_bucket_callback(self, flat):
+        """Register (or remove) the engine's mid-backward callback for the early gradient bucket."""
+        L = _capi.lib()
+        key = (self.grad_bucket_hook, self.bucket_stream)
+        self._cur_flat = flat
+        if key == self._bucket_cb_key:
+            return
+        if self.grad_bucket_hook is None:
+            L.fu_set_bucket_callback(self._handle, _capi.BUCKET_CALLBACK(), None, None)
+            self._bucket_cb = None
+        else:
+            if self.bucket_stream is None:
+                raise RuntimeError("grad_bucket_hook needs bucket_stream (a torch.cuda.Stream)")
+            hook, comm = self.grad_bucket_hook, self.bucket_stream
+
+            def tramp(_user, _bucket, offset, numel):
+                with torch.cuda.stream(comm):
+                    hook(self._cur_flat, int(offset), int(numel))
+            self._bucket_cb = _capi.BUCKET_CALLBACK(tramp)
+            rc = L.fu_set_bucket_callback(self._handle, self._bucket_cb, None, comm.cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"fu_set_bucket_callback failed ({rc}): {_capi.last_error(self._handle)}")
+        self._bucket_cb_key = key
+
+    @property
+    def early_grad_numel(self):
+        """Elements of the flat gradient buffer that form the early bucket (include/fluoro_unet.h)."""
+        return int(_capi.lib().fu_early_grad_numel(self._handle)) if self._handle is not None else 0
 
     @property
     def last_logits(self):

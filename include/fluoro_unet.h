@@ -137,6 +137,18 @@ int fu_forward(fu_engine* e, const float* x, int B, int H, int W, int training, 
 int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* flat_grads,
                 void* stream);
 
+/* Data parallelism (no reference counterpart: util.py:28-29 hard-wires one GPU).  The flat gradient buffer
+ * is laid out so that elements [0, fu_early_grad_numel) are FINAL once the backward pass has left the deep encoder
+ * levels -- heads, decoder, deep encoder: 97 % of the paper network's parameters.  With a callback registered,
+ * fu_backward calls cb(user, 0, 0, fu_early_grad_numel) at that point, after making `comm_stream` wait (events, no
+ * host synchronisation) for everything that produced those elements; the caller enqueues its all-reduce of
+ * flat_grads[offset, offset + numel) on comm_stream, where it overlaps the rest of the backward pass, reduces the
+ * remaining tail [fu_early_grad_numel, fu_grad_numel) after fu_backward returns, and makes its own stream wait for
+ * comm_stream before the optimizer step.  cb == NULL removes the callback. */
+typedef void (*fu_bucket_callback)(void* user, int bucket, int64_t offset, int64_t numel);
+int fu_set_bucket_callback(fu_engine* e, fu_bucket_callback cb, void* user, void* comm_stream);
+int64_t fu_early_grad_numel(const fu_engine* e);
+
 int fu_get_counters(const fu_engine* e, fu_counters* out);
 
 /* Per-launch CUDA-event profiling (the reference's only tracing is time.time(), train.py:377,
