@@ -25,6 +25,14 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// the C entry points make the engine's device current for their own launches and put the caller's device back on
+// return (PyTorch tracks the current device itself; changing it behind its back breaks its next allocation)
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct View {
   char* p = nullptr;  // address of channel 0 of this view
   int C = 0;          // channels in the view
@@ -207,10 +215,11 @@ struct fu_engine {
 #define LAUNCH_SMEM(e, kern, grid, block, smem, ...)                                        \
   do {                                                                                      \
     auto _kfn = kern;                                                                       \
-    static bool _attr = false;                                                              \
-    if (!_attr && (smem) > 48 * 1024) {                                                     \
-      cudaFuncSetAttribute(_kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
-      _attr = true;                                                                         \
+    static bool _attr[64] = {};                                                             \
+    if (tc_attr_needed(_attr)) {     /* per device; opted in to the largest size any launch may ask for */ \
+      cudaFuncAttributes _fa;                                                               \
+      int _stat = cudaFuncGetAttributes(&_fa, _kfn) == cudaSuccess ? (int)_fa.sharedSizeBytes : 0; \
+      cudaFuncSetAttribute(_kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - _stat); \
     }                                                                                       \
     if ((e)->prof) (e)->prof_begin(#kern);                                                  \
     fu_launch(_kfn, dim3(grid), dim3(block), (smem), (e)->stream, fu_pdl_enabled(), __VA_ARGS__); \
@@ -1474,7 +1483,7 @@ int fu_engine_create(const fu_config* cfg, int device, fu_engine** out) {
   e->split = cfg->precision == FU_PRECISION_FP32_TC;
   e->num_sms = prop.multiProcessorCount;
   memset(&e->cnt, 0, sizeof(e->cnt));
-  cudaSetDevice(device);
+  DeviceScope dev_scope(device);
   build_schema(e);
   rc = alloc_persistent(e);
   if (rc) { g_create_error = e->err; delete e; return rc; }
@@ -1484,7 +1493,7 @@ int fu_engine_create(const fu_config* cfg, int device, fu_engine** out) {
 
 void fu_engine_destroy(fu_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  DeviceScope dev_scope(e->device);
   cudaDeviceSynchronize();
   if (e->plan.arena) cudaFree(e->plan.arena);
   if (e->plan.twin) cudaFree(e->plan.twin);
@@ -1538,7 +1547,7 @@ int fu_forward(fu_engine* e, const float* x, int B, int H, int W, int training, 
   if (!e->bound) return e->fail(FU_ERR_NOT_BOUND, "fu_forward before fu_bind_tensors");
   if (!x || !seg) return e->fail(FU_ERR_ARG, "fu_forward: x and seg must be non-null");
   if (e->cfg.num_lands > 0 && !heat) return e->fail(FU_ERR_ARG, "fu_forward: heat must be non-null when num_lands > 0");
-  CUDA_TRY(e, cudaSetDevice(e->device));
+  DeviceScope dev_scope(e->device);
   e->stream = reinterpret_cast<cudaStream_t>(stream);
   const int64_t l0 = e->cnt.kernel_launches;
   int rc = ensure_plan(e, B, H, W);
@@ -1566,7 +1575,7 @@ int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* fl
   if (!e->saved) return e->fail(FU_ERR_STATE, "fu_backward without a saved forward (call fu_forward with save=1 first)");
   if (!flat_grads) return e->fail(FU_ERR_ARG, "fu_backward: flat_grads must be non-null");
   if (!aligned(flat_grads, 16)) return e->fail(FU_ERR_ARG, "fu_backward: flat_grads must be 16-byte aligned");
-  CUDA_TRY(e, cudaSetDevice(e->device));
+  DeviceScope dev_scope(e->device);
   e->stream = reinterpret_cast<cudaStream_t>(stream);
   const int64_t l0 = e->cnt.kernel_launches;
   int rc;
@@ -1584,7 +1593,7 @@ int fu_backward(fu_engine* e, const float* d_seg, const float* d_heat, float* fl
 int fu_set_bucket_callback(fu_engine* e, fu_bucket_callback cb, void* user, void* comm_stream) {
   if (!e) return FU_ERR_ARG;
   if (cb && !comm_stream) return e->fail(FU_ERR_ARG, "fu_set_bucket_callback: a communication stream is required");
-  CUDA_TRY(e, cudaSetDevice(e->device));
+  DeviceScope dev_scope(e->device);
   if (cb && !e->ev_mid_main) {
     CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_mid_main, cudaEventDisableTiming));
     CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_mid_side, cudaEventDisableTiming));
@@ -1656,7 +1665,7 @@ int fu_profile_enable(fu_engine* e, int on) {
 
 int64_t fu_profile_report(fu_engine* e, char* buf, int64_t cap) {
   if (!e) return FU_ERR_ARG;
-  cudaSetDevice(e->device);
+  DeviceScope dev_scope(e->device);
   if (!e->prof_recs.empty()) cudaEventSynchronize(e->prof_recs.back().b);
   struct Agg { std::string tag, kern; int n; double ms, flops, bytes; };
   std::vector<Agg> aggs;

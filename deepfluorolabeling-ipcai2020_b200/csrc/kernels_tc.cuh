@@ -2028,6 +2028,17 @@ inline int tc_unpack(const float* acc, float* dw, int M, int N, int taps, cudaSt
 // ===========================================================================
 // host side
 // ===========================================================================
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a flag per (call site, device), so an
+// engine created on a second GPU of the same process also gets the opt-in
+inline bool tc_attr_needed(bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 inline std::string& tc_err() {
   static thread_local std::string s;
   return s;
@@ -2538,15 +2549,14 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
 }
 
 inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[64] = {};
+  if (tc_attr_needed(attr_done)) {
     if (cudaFuncSetAttribute(tc_conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem, conv3) failed";
       return -1;
     }
-    attr_set = true;
   }
   static long long* dbg_buf = nullptr;
   const bool dbg = tc_env_int("FU_TC_DBG", 0) != 0;
@@ -2580,8 +2590,8 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
 }
 
 inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[64] = {};
+  if (tc_attr_needed(attr_done)) {
     if (cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
@@ -2590,7 +2600,6 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem) failed";
       return -1;
     }
-    attr_set = true;
   }
   const bool pdl = fu_pdl_enabled();
   if (c->f32 && c->G == 2) fu_launch(tc_conv_kernel<2, true>, dim3(c->grid), dim3(64 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
@@ -2787,13 +2796,12 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     t.wcache.push_back(n);
     c = &t.wcache.back();
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[64] = {};
+  if (tc_attr_needed(attr_done)) {
     if (cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem, wgrad) failed";
       return -1;
     }
-    attr_set = true;
   }
   // 1x1 convolutions: [1][M][N] IS the torch layout, so the kernel accumulates straight into the (zeroed)
   // gradient and nothing is unpacked
@@ -2869,13 +2877,12 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     t.w3cache.push_back(n);
     c = &t.w3cache.back();
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_done[64] = {};
+  if (tc_attr_needed(attr_done)) {
     if (cudaFuncSetAttribute(tc_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem, wgrad3) failed";
       return -1;
     }
-    attr_set = true;
   }
   fu_launch(tc_wgrad3_kernel, dim3(c->grid), dim3(kTcThreads), c->smem, stream, fu_pdl_enabled(), c->y, c->xm, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }

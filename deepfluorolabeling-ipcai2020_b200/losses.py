@@ -108,7 +108,8 @@ class _FusedLossFn(torch.autograd.Function):
         sums = torch.empty(int(L.fu_loss_workspace_doubles(B, NC, NL)), device=seg.device, dtype=torch.float64)
         loss = torch.empty((), device=seg.device, dtype=torch.float32)
         stream = torch.cuda.current_stream(seg.device).cuda_stream
-        rc = L.fu_loss_forward(C.byref(d), sums.data_ptr(), loss.data_ptr(), stream)
+        with torch.cuda.device(seg.device):       # the loss kernels launch on the current device
+            rc = L.fu_loss_forward(C.byref(d), sums.data_ptr(), loss.data_ptr(), stream)
         if rc != 0:
             raise RuntimeError(f"fu_loss_forward failed ({rc}): {_capi.last_error(None)}")
         ctx.desc, ctx.geom = d, (H, W, r0, c0, NL)
@@ -126,8 +127,9 @@ class _FusedLossFn(torch.autograd.Function):
         d_heat = torch.empty_like(heat_full) if NL > 0 else None
         dloss = dloss.contiguous().float()
         stream = torch.cuda.current_stream(seg_full.device).cuda_stream
-        rc = L.fu_loss_backward(C.byref(ctx.desc), sums.data_ptr(), dloss.data_ptr(), H, W, r0, c0, d_seg.data_ptr(),
-                                d_heat.data_ptr() if d_heat is not None else None, stream)
+        with torch.cuda.device(seg_full.device):
+            rc = L.fu_loss_backward(C.byref(ctx.desc), sums.data_ptr(), dloss.data_ptr(), H, W, r0, c0, d_seg.data_ptr(),
+                                    d_heat.data_ptr() if d_heat is not None else None, stream)
         if rc != 0:
             raise RuntimeError(f"fu_loss_backward failed ({rc}): {_capi.last_error(None)}")
         return d_seg, d_heat, None, None, None, None, None

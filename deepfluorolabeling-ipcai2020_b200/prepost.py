@@ -72,6 +72,8 @@ def heatmap_targets(lands, shape, sigma=2.5):
         raise ValueError("heatmap_targets: lands must be (B,2,L) (dataset.py:59)")
     B, _, L = lands.shape
     H, W = int(shape[-2]), int(shape[-1])
+    if L > 65535:
+        raise ValueError("heatmap_targets: at most 65535 landmarks per sample (one launch covers 65535 planes)")
     if L > 0 and B * L > 65535:     # one launch covers at most 65535 planes: split the batch
         step = max(1, 65535 // L)
         return torch.cat([heatmap_targets(lands[i:i + step], shape, sigma) for i in range(0, B, step)])

@@ -307,6 +307,7 @@ class UNet(nn.Module):
         version = (version & 0xFFFFFFFF) | (self._pack_epoch << 32)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         self._generation += 1
+        # (the C entry points make the engine's device current for their launches and restore the caller's)
         rc = L.fu_forward(self._handle, x.data_ptr(), B, H, W, int(self.training), int(save), version,
                           seg.data_ptr(), logits.data_ptr() if logits is not None else None,
                           heat.data_ptr() if heat is not None else None, stream)
@@ -426,6 +427,9 @@ class UNet(nn.Module):
             raise ValueError(f"expected {self._cfg['in_channels']} input channels, got {x.shape[1]}")
         if x.dtype != torch.float32:
             raise TypeError("UNet.forward expects a float32 input (as the reference's dataset produces)")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("UNet.forward: the engine does not produce a gradient for the INPUT (the reference never asks "
+                               "for one: train.py:395-407 feeds data tensors); detach the input")
         x = x.contiguous()
         self._ensure_engine(x.device)
         self._bind(x.device)

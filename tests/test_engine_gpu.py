@@ -265,6 +265,9 @@ def test_module_semantics_on_gpu(pkg):
     # unsupported shape is rejected, not padded silently
     with pytest.raises(ValueError):
         net(torch.randn(1, 1, 9, 8, device=dev))
+    # an input that asks for a gradient is refused (the engine produces parameter gradients only), not silently ignored
+    with pytest.raises(RuntimeError, match="INPUT"):
+        net(torch.randn(2, 1, 8, 8, device=dev, requires_grad=True))
     # a stale backward is refused
     o1 = net(x)
     net(x)

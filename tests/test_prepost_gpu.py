@@ -221,3 +221,9 @@ def test_seg_dataset_ensemble_runs_the_engine_networks(pp):
                                          [torch.cat([o[1] for o in per_net]).cpu() for per_net in outs], (20, 20))
     assert torch.equal(labels.cpu(), want_l)
     np.testing.assert_allclose(heats.cpu().numpy(), want_h.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_heatmap_targets_rejects_more_landmarks_than_one_launch_covers(pkg):
+    """65536 landmarks per sample cannot be split over launches by batch: rejected loudly (used to recurse forever)."""
+    with pytest.raises(ValueError, match="65535"):
+        pkg.prepost.heatmap_targets(torch.zeros(1, 2, 65536, device="cuda:0"), (8, 8))

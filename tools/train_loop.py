@@ -263,8 +263,10 @@ def bench_train_loop(args, torch_mod, dist, pkg, dev, rank, world, local, config
     t0 = time.perf_counter()
     losses = [one() for _ in range(args.steps)]
     loop.sched.step()
+    ck0 = time.perf_counter()
     if rank == 0:                                   # the epoch's checkpoint (train.py:517-520), inside the timed region
         save_net(os.path.join(ckpt_dir, "checkpoint.pt"), 1, loop.net, loop.opt, loop.sched, torch_mod.tensor(losses[-1]), loop.cfg)
+    ckpt_ms = (time.perf_counter() - ck0) * 1e3
     e1.record()
     torch_mod.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
@@ -297,6 +299,7 @@ def bench_train_loop(args, torch_mod, dist, pkg, dev, rank, world, local, config
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": int(h2d or 0), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_step},
+            "checkpoint_ms": ckpt_ms, "images_per_s_without_checkpoint": args.batch * world * args.steps / max(1e-9, (ms - ckpt_ms) * 1e-3),
             "gpu_launches": int(launches), "loss_first_last": [losses[0], losses[-1]], "host_wall_ms_per_step": wall / args.steps,
             "build": pkg._capi.lib().fu_build_info().decode()}
 
