@@ -223,7 +223,7 @@ def test_seg_dataset_ensemble_runs_the_engine_networks(pp):
     np.testing.assert_allclose(heats.cpu().numpy(), want_h.numpy(), rtol=1e-5, atol=1e-6)
 
 
-def test_heatmap_targets_rejects_more_landmarks_than_one_launch_covers(pkg):
+def test_heatmap_targets_rejects_more_landmarks_than_one_launch_covers(pp):
     """65536 landmarks per sample cannot be split over launches by batch: rejected loudly (used to recurse forever)."""
     with pytest.raises(ValueError, match="65535"):
-        pkg.prepost.heatmap_targets(torch.zeros(1, 2, 65536, device="cuda:0"), (8, 8))
+        pp.heatmap_targets(torch.zeros(1, 2, 65536, device="cuda:0"), (8, 8))
