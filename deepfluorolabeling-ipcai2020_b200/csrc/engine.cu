@@ -155,7 +155,7 @@ struct fu_engine {
   std::vector<std::pair<const void*, int>> fresh_fwd, fresh_bwd;
   bool in_backward = false;
   // optional per-launch CUDA-event profiling (fu_profile_enable)
-  struct DeferredSum { const double* src; float* dst; int n; };
+  struct DeferredSum { const double* src; float* dst; int n; int copies; };
   std::vector<DeferredSum> deferred_sums;
   bool prof = false;
   struct ProfRec { std::string tag; const char* kern; cudaEvent_t a, b; double flops, bytes; };
@@ -426,7 +426,7 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
     c.wp_fwd = w.take<float>((size_t)taps_f * k_f * c.npad_fwd);
     const int taps_d = c.transposed ? 4 : (c.k == 2 ? 1 : c.k * c.k);
     c.wp_dgrad = w.take<float>((size_t)taps_d * c.Cout * c.npad_dgrad);
-    c.bsum = db.take<double>(c.Cout);
+    c.bsum = db.take<double>((size_t)kRedCopies * c.Cout);      // kRedCopies copies (kernels_simt.cuh)
     c.small_cin = !c.transposed && (c.k == 3 || c.k == 1) && c.Cin <= 2 && (c.Cout % 8 == 0) && c.Cout <= 256 &&
                   (c.Cout & (c.Cout - 1)) == 0 && c.Cout / 8 <= 32;
     if (c.Cout > maxc) maxc = c.Cout;
@@ -437,7 +437,7 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
   for (auto& b : e->dec) b.dstat = db.take<double>(2 * (size_t)b.Cin);
   for_each_bn(e, [&](BNL& b) {
     b.stat = df.take<double>(2 * b.C);
-    b.bstat = db.take<double>(2 * b.C);
+    b.bstat = db.take<double>((size_t)kRedCopies * 2 * b.C);
     b.mean = w.take<float>(b.C); b.invstd = w.take<float>(b.C);
     b.a = w.take<float>(b.C); b.b = w.take<float>(b.C);
     b.ga = w.take<float>(b.C); b.m1 = w.take<float>(b.C); b.m2 = w.take<float>(b.C);
@@ -760,7 +760,13 @@ inline dim3 red_grid(fu_engine* e, long long P, int C) {
   // (6x6 ... 24x24, where these kernels are latency bound at 12-16 us) were measured and dropped: smaller chunks
   // made every kernel end in 4-32x more fp64 atomics (1.6x slower overall), and reducing across 8-block clusters
   // through distributed shared memory first made the big levels pay for cluster scheduling (act_bwd 0.54 -> 0.97 ms).
-  long long gx = (P + (long long)rows * 16 - 1) / ((long long)rows * 16);
+  // pixel rows per thread: 16 on the big levels; fewer (down to 4) on the small ones so that at least ~4 blocks per SM
+  // are in flight -- with the per-channel atomics spread over kRedCopies copies more blocks no longer mean a longer
+  // serial atomic chain per address
+  long long per = 16;
+  static const int per_min = tc_env_int("FU_RED_PER_MIN", 16);   // (finer grids measured slower: 5.99 -> 6.13 ms per step)
+  while (per > per_min && (P + rows * per - 1) / (rows * per) < (long long)e->num_sms * 4) per >>= 1;
+  long long gx = (P + (long long)rows * per - 1) / ((long long)rows * per);
   const long long cap = (long long)e->num_sms * 8;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -1041,7 +1047,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
 template <typename T>
 int channel_sum_to(fu_engine* e, const View& d, long long P, double* scratch, float* dst) {
   LAUNCH(e, (channel_sum_kernel<T>), red_grid(e, P, d.C), 256, reinterpret_cast<const T*>(d.p), d.ld, P, d.C, scratch);
-  e->deferred_sums.push_back({scratch, dst, d.C});     // converted to fp32 by one launch at the end of backward
+  e->deferred_sums.push_back({scratch, dst, d.C, kRedCopies});     // converted to fp32 by one launch at the end of backward
   return FU_OK;
 }
 
@@ -1068,7 +1074,7 @@ int flush_deferred_sums(fu_engine* e) {
     int maxn = 1;
     for (; i < e->deferred_sums.size() && t.count < SumTable::kMax; ++i) {
       t.src[t.count] = e->deferred_sums[i].src; t.dst[t.count] = e->deferred_sums[i].dst;
-      t.n[t.count] = e->deferred_sums[i].n;
+      t.n[t.count] = e->deferred_sums[i].n; t.copies[t.count] = e->deferred_sums[i].copies;
       if (e->deferred_sums[i].n > maxn) maxn = e->deferred_sums[i].n;
       ++t.count;
     }
@@ -1198,7 +1204,7 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
              reinterpret_cast<const T*>(blk.r[i].p), blk.r[i].ld, reinterpret_cast<T*>(blk.dy[i].p),
              blk.dy[i].ld, 0, nullptr, nullptr, fin, P, blk.C, cw.bsum);
     }
-    e->deferred_sums.push_back({cw.bsum, gptr(e, flat, cw.b_idx), blk.C});
+    e->deferred_sums.push_back({cw.bsum, gptr(e, flat, cw.b_idx), blk.C, kRedCopies});
     View conv_in = (i == 0) ? x_in : (bn ? blk.z[i - 1] : blk.r[i - 1]);
     if (cw.tc.enabled && ((rc = ensure_split(e, conv_in, P)) || (rc = ensure_split(e, blk.dy[i], P)))) return rc;
     {
@@ -1318,7 +1324,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     View u = (l == D - 2) ? pl.bott : pl.decout[l + 1];
     View d_u = (l == D - 2) ? pl.d_bott : pl.d_decout[l + 1];
     e->set_tag(4.0 * B * (h / 2) * (w / 2) * 4.0 * up.Cin * up.Cout, 0, "up_bwd %dx%d %d->%d", h, w, up.Cin, up.Cout);
-    if (in_sums) e->deferred_sums.push_back({e->dec[j].dstat, gptr(e, flat, up.b_idx), e->chans[l]});   // channels [0,C) of d_cat
+    if (in_sums) e->deferred_sums.push_back({e->dec[j].dstat, gptr(e, flat, up.b_idx), e->chans[l], 1});   // channels [0,C) of d_cat
     else if ((rc = channel_sum_to<T>(e, d_up, (long long)B * h * w, up.bsum, gptr(e, flat, up.b_idx)))) return rc;
     const Opnd uo = opnd(e, u), dupo = opnd(e, d_up);
     if (tc_up_eligible(up.tc, uo.p, uo.ld, d_u.p, d_u.ld) && tc_ptr_ok(dupo.p, dupo.ld)) {
@@ -1390,7 +1396,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
                pl.d_down[l].ld, reinterpret_cast<T*>(d_src.p), d_src.ld, B, h, w, src.C, 1);
       } else {
         ConvW& cw = e->downc[l - 1];
-        if (in_sums) e->deferred_sums.push_back({e->enc[l].dstat, gptr(e, flat, cw.b_idx), cw.Cout});
+        if (in_sums) e->deferred_sums.push_back({e->enc[l].dstat, gptr(e, flat, cw.b_idx), cw.Cout, 1});
         else if ((rc = channel_sum_to<T>(e, pl.d_down[l], (long long)B * h * w, cw.bsum, gptr(e, flat, cw.b_idx)))) return rc;
         const Opnd so = opnd(e, src), ddo = opnd(e, pl.d_down[l]);
         if (tc_down_eligible(cw.tc, so.p, so.ld, d_src.p, d_src.ld) && tc_ptr_ok(ddo.p, ddo.ld)) {

@@ -1337,7 +1337,19 @@ struct RedMap {
   }
 };
 
-// block-level sum over the pixel rows of each channel, then one fp64 atomic per channel per block
+// Per-channel reduction targets are kept in kRedCopies copies, `stride` doubles apart: block b adds into copy
+// b % kRedCopies and the consumer sums the copies.  With ONE copy every block's atomics on a channel hit the same
+// address and serialise in L2 -- 1152 blocks x 64 addresses made that the tail of every reduction kernel (ncu: 12-16 us
+// floors on 2-10 MB tensors, 2 TB/s at 96x96); eight copies cut the chain per address eightfold.
+constexpr int kRedCopies = 8;
+__device__ __forceinline__ double red_sum_copies(const double* p, int stride) {
+  double v = 0.0;
+#pragma unroll
+  for (int k = 0; k < kRedCopies; ++k) v += p[(size_t)k * stride];
+  return v;
+}
+
+// block-level sum over the pixel rows of each channel, then one fp64 atomic per channel per block (into the block's copy)
 template <int VEC>
 __device__ __forceinline__ void block_channel_reduce(const RedMap<VEC>& mp, const float* s, double* out, int C, float* sm) {
 #pragma unroll
@@ -1357,6 +1369,8 @@ __device__ __forceinline__ void block_channel_reduce(const RedMap<VEC>& mp, cons
   }
   __syncthreads();
 }
+// copy of a [n]-double target this block adds into (copies are `stride` doubles apart)
+__device__ __forceinline__ double* red_copy(double* base, int stride) { return base + (size_t)(blockIdx.x % kRedCopies) * stride; }
 
 // out[0:C] += sum d ; out[C:2C] += sum d * xhat, xhat = (r - mean) * invstd
 template <typename T>
@@ -1398,8 +1412,9 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const T* d, int d
 #pragma unroll
     for (int i = 0; i < V; ++i) s2[i] *= invstd[c + i];
   }
-  block_channel_reduce<V>(mp, s1, out, C, sm);
-  block_channel_reduce<V>(mp, s2, out + C, C, sm);
+  double* oc = red_copy(out, 2 * C);
+  block_channel_reduce<V>(mp, s1, oc, C, sm);
+  block_channel_reduce<V>(mp, s2, oc + C, C, sm);
 }
 
 // bstat -> d(gamma), d(beta) [, d(res bias) = sum d], and the coefficients of the
@@ -1433,34 +1448,44 @@ __global__ void __launch_bounds__(256, 3) act_bwd_kernel(const T* d, int d_ld, c
                                                       double* out) {
   pdl_wait(); pdl_trigger();
   constexpr int V = Vec<T>::N;
-  __shared__ float sm[256 * V];
+  __shared__ float sm[3 * 256 * V];      // [3][lanes*V] constants, then the [256*V] reduction scratch
   RedMap<V> mp(C);
   float s[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) s[i] = 0.f;
-  if (mp.cv * V < C) {
-    const int c = mp.cv * V;
-    // dy = A*d + Bc*r + Cc where r > 0:  A = gamma*invstd, Bc = -A*invstd*m2, Cc = -A*m1 + A*invstd*m2*mean
-    // (m1 = mean(d), m2 = mean(d*xhat)); without BN: A = 1, Bc = Cc = 0.  Three constants per channel.
-    float A[V], Bc[V], Cc[V];
+  // dy = A*d + Bc*r + Cc where r > 0:  A = gamma*invstd, Bc = -A*invstd*m2, Cc = -A*m1 + A*invstd*m2*mean
+  // (m1 = mean(d), m2 = mean(d*xhat)); without BN: A = 1, Bc = Cc = 0.  Three constants per channel, computed once
+  // per block by the pixel-row-0 threads (they sum the kRedCopies copies of the statistics) and shared.
+  const bool active = mp.cv * V < C;
+  const int c = mp.cv * V;
+  float A[V], Bc[V], Cc[V];
+  {
+    float* sk = sm;                                  // [3][lanes*V] (sm is reused by the reduction at the end)
+    const int nl = mp.lanes * V, li = (threadIdx.x % mp.lanes) * V;
+    if (has_bn && active && mp.prow == 0) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      A[i] = 1.f; Bc[i] = 0.f; Cc[i] = 0.f;
-      if (has_bn) {
+      for (int i = 0; i < V; ++i) {
         const float mu = mean[c + i], is = invstd[c + i];
-        const double s1 = fin.bstat[c + i], s2 = fin.bstat[C + c + i];
+        const double s1 = red_sum_copies(fin.bstat + c + i, 2 * C), s2 = red_sum_copies(fin.bstat + C + c + i, 2 * C);
         const float a1 = fin.training ? (float)(s1 / (double)P) : 0.f;
         const float a2 = fin.training ? (float)(s2 / (double)P) : 0.f;
-        A[i] = fin.gamma[c + i] * is;
-        Bc[i] = -A[i] * is * a2;
-        Cc[i] = -A[i] * a1 - Bc[i] * mu;
-        if (blockIdx.x == 0 && mp.prow == 0) {
+        const float a = fin.gamma[c + i] * is, b = -a * is * a2;
+        sk[li + i] = a; sk[nl + li + i] = b; sk[2 * nl + li + i] = -a * a1 - b * mu;
+        if (blockIdx.x == 0) {
           fin.g_gamma[c + i] = (float)s2;
           fin.g_beta[c + i] = (float)s1;
           if (fin.g_extra) fin.g_extra[c + i] = (float)s1;
         }
       }
     }
+    if (has_bn) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      A[i] = has_bn ? sk[li + i] : 1.f; Bc[i] = has_bn ? sk[nl + li + i] : 0.f; Cc[i] = has_bn ? sk[2 * nl + li + i] : 0.f;
+    }
+    if (has_bn) __syncthreads();                     // sm is written again by block_channel_reduce
+  }
+  if (active) {
     const long long step = (long long)gridDim.x * mp.rows;
     long long pix = (long long)blockIdx.x * mp.rows + mp.prow;
     auto one = [&](const float* dv, const float* rv, T* dst) {
@@ -1486,7 +1511,7 @@ __global__ void __launch_bounds__(256, 3) act_bwd_kernel(const T* d, int d_ld, c
       one(d0, r0, dy + pix * dy_ld + c);
     }
   }
-  block_channel_reduce<V>(mp, s, out, C, sm);
+  block_channel_reduce<V>(mp, s, red_copy(out, C), C, sm);
 }
 
 template <typename T>
@@ -1509,19 +1534,23 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* d, int d_ld, 
       for (int i = 0; i < V; ++i) s[i] += dv[i];
     }
   }
-  block_channel_reduce<V>(mp, s, out, C, sm);
+  block_channel_reduce<V>(mp, s, red_copy(out, C), C, sm);
 }
 
 // all bias-gradient accumulators of a backward pass -> fp32 gradients, one launch
 struct SumTable {
   enum { kMax = 96 };
-  const double* src[kMax]; float* dst[kMax]; int n[kMax]; int count;
+  const double* src[kMax]; float* dst[kMax]; int n[kMax]; int copies[kMax]; int count;   // copies: 1 or kRedCopies (n doubles apart)
 };
 __global__ void sums_to_float_kernel(const SumTable t) {
   pdl_wait(); pdl_trigger();
   const int e = blockIdx.x;
   if (e >= t.count) return;
-  for (int i = threadIdx.x; i < t.n[e]; i += blockDim.x) t.dst[e][i] = (float)t.src[e][i];
+  for (int i = threadIdx.x; i < t.n[e]; i += blockDim.x) {
+    double v = 0.0;
+    for (int k = 0; k < t.copies[e]; ++k) v += t.src[e][(size_t)k * t.n[e] + i];
+    t.dst[e][i] = (float)v;
+  }
 }
 
 __global__ void sum_to_float_kernel(const double* src, float* dst, int C) {

@@ -304,6 +304,8 @@ struct TcConvParams {
   // with lo at `b_lo`.  Output and second epilogue operand are fp32.
   int a_lo, b_lo;
   const float* tf;              // (F32) second epilogue operand, fp32 NHWC with pixel stride t_ld
+  int dual;                     // two MMA-issuing warps on alternate tiles (stages >= 2 x the K iterations of a tile, so
+                                // that an issuer one tile ahead is never a whole ring round ahead; see TcConv3Params)
 };
 
 constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (wgrad kernels; the conv kernel has 4*G epilogue warps)
@@ -315,7 +317,7 @@ constexpr int kTc3Threads = 320;      // halo kernel: producer, MMA, 2 x 4 epilo
 // are bound by the epilogue's per-warp latency chain (TMEM load, second-operand fetch, convert, staging
 // store, TMA store, statistics): four groups cut their time ~3x; the deep 3x3 layers keep G = 1 or 2.
 template <int G, bool F32 = false>
-__global__ void __launch_bounds__(64 + 128 * G, 1)
+__global__ void __launch_bounds__(96 + 128 * G, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -459,17 +461,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == mma_warp) {
-    // ------------------------------ MMA issuer (whole warp loops, one elected lane issues) -----
+  } else if (warp >= mma_warp) {
+    // ------------------------------ MMA issuers (whole warp loops, one elected lane issues) -----
+    // Two issuers on alternate tiles when p.dual (see tc_conv3_kernel): the 1x1 / 2x2 layers have 1-8 MMAs per tile,
+    // so a single issuer spends most of a tile in barrier round trips.
     {
+      const int mw = warp - mma_warp;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      int it = 0;
       const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
       const uint64_t dbase = umma_desc_kmajor(0, row_bytes);
       const uint32_t dhi = (uint32_t)(dbase >> 32), dlo = (uint32_t)dbase;
       const int ksteps = p.KC / 16;
       const uint32_t a16 = a_bytes >> 4;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if (!p.dual) { if (mw) break; }
+        else if ((it & 1) != mw) {                  // the other issuer's tile: step over its ring slots
+          stage += k_iters; while (stage >= p.stages) { stage -= p.stages; phase ^= 1u; }
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
@@ -2602,11 +2614,15 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
     }
   }
   const bool pdl = fu_pdl_enabled();
-  if (c->f32 && c->G == 2) fu_launch(tc_conv_kernel<2, true>, dim3(c->grid), dim3(64 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else if (c->f32) fu_launch(tc_conv_kernel<1, true>, dim3(c->grid), dim3(64 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else if (c->G == 4) fu_launch(tc_conv_kernel<4, false>, dim3(c->grid), dim3(64 + 128 * 4), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else if (c->G == 2) fu_launch(tc_conv_kernel<2, false>, dim3(c->grid), dim3(64 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else fu_launch(tc_conv_kernel<1, false>, dim3(c->grid), dim3(64 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  {
+    const int k_iters = c->p.ksz * c->p.ksz * (c->p.Cin / c->p.KC) * (c->f32 ? 3 : 1);
+    c->p.dual = (c->p.stages >= 2 * k_iters && tc_env_int("FU_TC_DUAL", 1)) ? 1 : 0;
+  }
+  if (c->f32 && c->G == 2) fu_launch(tc_conv_kernel<2, true>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else if (c->f32) fu_launch(tc_conv_kernel<1, true>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else if (c->G == 4) fu_launch(tc_conv_kernel<4, false>, dim3(c->grid), dim3(96 + 128 * 4), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else if (c->G == 2) fu_launch(tc_conv_kernel<2, false>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  else fu_launch(tc_conv_kernel<1, false>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }

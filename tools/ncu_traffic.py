@@ -17,17 +17,22 @@ for r in rows[hi + 1:]:
     name = r[col["Metric Name"]]
     if name.startswith("gpu__time_duration"):
         L["us"] = v / 1e3 if unit.startswith("ns") or unit == "nsecond" else (v if unit.startswith("us") else v * 1e3)
-    elif "read" in name:
+    elif name.startswith("dram__bytes_read"):
         L["rd"] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-    elif "write" in name:
+    elif name.startswith("dram__bytes_write"):
         L["wr"] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    elif name.startswith("sm__pipe_tensor_cycles_active"):
+        L["tensor"] = v
+    elif name.startswith("smsp__issue_active"):
+        L["issue"] = v
 def short(k):
     k = re.sub(r"\(.*", "", k).replace("void ", "").replace("fu::", "")
     return re.sub(r"<__nv_bfloat16(, )?", "<", k)
 with open(out_csv, "w") as f:
-    f.write("id,kernel,grid,block,time_us,dram_read_bytes,dram_write_bytes\n")
+    f.write("id,kernel,grid,block,time_us,dram_read_bytes,dram_write_bytes,tensor_pipe_pct,issue_active_pct\n")
     for i, L in launch.items():
-        f.write(f"{i},{short(L['kernel'])},\"{L['grid']}\",\"{L['block']}\",{L.get('us', 0):.2f},{int(L.get('rd', 0))},{int(L.get('wr', 0))}\n")
+        f.write(f"{i},\"{short(L['kernel'])}\",\"{L['grid']}\",\"{L['block']}\",{L.get('us', 0):.2f},{int(L.get('rd', 0))},{int(L.get('wr', 0))},"
+                f"{L.get('tensor', 0):.1f},{L.get('issue', 0):.1f}\n")
 # training steps in the capture = launches of a kernel that runs exactly once per step
 steps = (sum(1 for L in launch.values() if "nchw_to_nhwc_kernel" in L["kernel"]) or
          sum(1 for L in launch.values() if "heads_bwd_fused_kernel" in L["kernel"]) or 1)
