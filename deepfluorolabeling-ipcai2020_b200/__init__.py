@@ -11,9 +11,9 @@ from .util import center_crop  # noqa: F401
 from . import parallel  # noqa: F401
 from .losses import (DiceLoss2D, DiceAndHeatMapLoss2D, ncc_2d,  # noqa: F401
                      FusedDiceLoss2D, FusedDiceAndHeatMapLoss2D)
-from .graphs import GraphedStep  # noqa: F401
+from .graphs import GraphedStep, GraphedForward  # noqa: F401
 from . import prepost  # noqa: F401
 from .build import build as build_library  # noqa: F401
 
 __all__ = ["UNet", "UNetConvBlock", "UNetUpBlock", "center_crop", "parallel", "build_library",
-           "DiceLoss2D", "DiceAndHeatMapLoss2D", "ncc_2d", "FusedDiceLoss2D", "FusedDiceAndHeatMapLoss2D", "GraphedStep", "prepost"]
+           "DiceLoss2D", "DiceAndHeatMapLoss2D", "ncc_2d", "FusedDiceLoss2D", "FusedDiceAndHeatMapLoss2D", "GraphedStep", "GraphedForward", "prepost"]

@@ -810,7 +810,8 @@ float* gptr(fu_engine* e, float* flat, int idx) {
 // ---------------------------------------------------------------------------
 template <typename T>
 int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, int H, int W, int relu,
-                 double* stat, const View* t, const float* bn_a, const float* bn_b, const TcBnFin* fin = nullptr) {
+                 double* stat, const View* t, const float* bn_a, const float* bn_b, const TcBnFin* fin = nullptr,
+                 int post = 0) {
   // 3x3/pad1 or 1x1 convolution, stride 1
   {
     const double M = (double)B * H * W;
@@ -822,12 +823,13 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     { const int src = ensure_split(e, x, (long long)B * H * W); if (src) return src; }
     if (e->prof) e->prof_begin("tc_conv_kernel");
     int rc = tc_conv_forward(cw.tc, xo.p, xo.ld, y.p, y.ld, B, H, W, tdata(e, cw.b_idx), relu, stat,
-                             t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt, fin);
+                             t ? t->p : nullptr, t ? t->ld : 0, bn_a, bn_b, 0, e->stream, &e->cnt, fin, post);
     if (e->prof) e->prof_end();
     if (rc) return e->fail(FU_ERR_CUDA, "tensor-core conv launch failed: %s", tc_last_error());
     return FU_OK;
   }
   if (cw.tc.enabled) return e->fail(FU_ERR_STATE, "tensor-core layer with a misaligned view (internal error)");
+  if (post) return e->fail(FU_ERR_STATE, "post-ReLU BatchNorm folding is a tensor-core epilogue feature (internal error)");
   const size_t va = 4 * sizeof(T);
   if (cw.small_cin && (y.ld % 4 == 0) && aligned(y.p, va) && (!t || ((t->ld % 4 == 0) && aligned(t->p, va)))) {
     SmallCinArgs a;
@@ -867,7 +869,8 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
 }
 
 template <typename T>
-int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, int B, int H, int W, int training) {
+int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, int B, int H, int W, int training,
+                  bool eval_fast = false) {
   const int nd = (int)blk.convs.size();
   const bool bn = !blk.bns.empty();
   const long long P = (long long)B * H * W;
@@ -879,6 +882,19 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
   for (int i = 0; i < nd; ++i) {
     View r = blk.r[i];   // (aliases `out` when the block ends in a bare ReLU, see carve_plan)
     double* stat = (bn && training) ? blk.bns[i].stat : nullptr;
+    if (eval_fast && bn && (i < nd - 1 || !blk.has_res)) {
+      // Inference fast path (no gradient will be asked for): the BatchNorm's folded running-statistics scale / shift
+      // (bn_eval_coeffs_kernel, once per forward) ride in the convolution's epilogue, z = a * relu(conv) + b; the
+      // post-ReLU tensor r is never written and the separate normalisation pass (one read + one write of the tensor) is
+      // gone.  Only for tensor-core layers; the C_in = 1 first layer keeps the two-pass form.
+      View z = (i == nd - 1) ? out : blk.z[i];
+      const Opnd xo = opnd(e, cur);
+      if (tc_conv_eligible(blk.convs[i].tc, xo.p, xo.ld, z.p, z.ld, nullptr, 0)) {
+        if ((rc = conv_forward<T>(e, blk.convs[i], cur, z, B, H, W, 1, nullptr, nullptr, blk.bns[i].a, blk.bns[i].b, nullptr, 1))) return rc;
+        cur = z;
+        continue;
+      }
+    }
     if ((rc = conv_forward<T>(e, blk.convs[i], cur, r, B, H, W, 1, stat, nullptr, nullptr, nullptr))) return rc;
     if (bn) {
       BNL& b = blk.bns[i];
@@ -927,13 +943,29 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
 
 template <typename T>
 int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, float* seg, float* logits,
-              float* heat) {
+              float* heat, bool eval_fast = false) {
   const fu_config& c = e->cfg;
   Plan& pl = e->plan;
   const int D = c.depth;
   const int esz = e->esz;
   int rc;
   if (training && c.batch_norm) CUDA_TRY(e, cudaMemsetAsync(e->dscr_fwd, 0, e->dscr_fwd_bytes, e->stream));
+  if (eval_fast && c.batch_norm) {
+    BnEvalTable t;
+    t.count = 0; t.eps = 1e-5f;
+    bool fits = true;
+    for_each_bn(e, [&](BNL& b) {
+      if (t.count >= BnEvalTable::kMax) { fits = false; return; }
+      const int k = t.count++;
+      t.gamma[k] = tdata(e, b.i_gamma); t.beta[k] = tdata(e, b.i_beta); t.rmean[k] = tdata(e, b.i_rm); t.rvar[k] = tdata(e, b.i_rv);
+      t.a[k] = b.a; t.b[k] = b.b; t.mean_o[k] = b.mean; t.invstd_o[k] = b.invstd; t.C[k] = b.C;
+    });
+    if (!fits) eval_fast = false;
+    else {
+      e->set_tag(0, 0, "bn_eval_coeffs");
+      LAUNCH(e, bn_eval_coeffs_kernel, t.count, 256, t);
+    }
+  }
   const long long HW = (long long)H * W;
   e->set_tag(0, 0, "input_cast");
   LAUNCH(e, (nchw_to_nhwc_kernel<T>), grid1d((long long)B * HW, 256, e->num_sms), 256, x,
@@ -943,7 +975,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     const int h = H >> l, w = W >> l;
     View outv = (D == 1) ? pl.decout[0] : (l < D - 1 ? slice(pl.cat[l], e->chans[l], e->chans[l], esz) : pl.bott);
     if (l == e->split_level()) side_join(e);        // the deep layers' weight packs (side stream) are needed from here on
-    if ((rc = block_forward<T>(e, e->enc[l], cur, outv, B, h, w, training))) return rc;
+    if ((rc = block_forward<T>(e, e->enc[l], cur, outv, B, h, w, training, eval_fast))) return rc;
     if (l < D - 1) {
       View dn = pl.down[l + 1];
       e->set_tag(2.0 * B * (h / 2) * (w / 2) * 4.0 * outv.C * outv.C, 0, "down_fwd %dx%d C%d", h, w, outv.C);
@@ -996,7 +1028,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
       cc.bias_mod = up.Cout; cc.KH = 1; cc.stride = 1; cc.pad = 0; cc.shuffle = 1;
       if ((rc = run_igemm<T>(e, cc))) return rc;
     }
-    if ((rc = block_forward<T>(e, e->dec[j], pl.cat[l], pl.decout[l], B, h, w, training))) return rc;
+    if ((rc = block_forward<T>(e, e->dec[j], pl.cat[l], pl.decout[l], B, h, w, training, eval_fast))) return rc;
     cur = pl.decout[l];
   }
   // ---- heads (unet.py:176-191) ----
@@ -1565,8 +1597,11 @@ int fu_forward(fu_engine* e, const float* x, int B, int H, int W, int training, 
   }
   e->saved = false;
   e->fresh_fwd.clear(); e->fresh_bwd.clear(); e->in_backward = false;
-  if (e->cfg.precision == FU_PRECISION_BF16) rc = forward_t<bf16>(e, x, B, H, W, training, seg, logits, heat);
-  else rc = forward_t<float>(e, x, B, H, W, training, seg, logits, heat);
+  // inference fast path: eval-mode statistics and no backward will follow (FU_EVAL_FAST=0 keeps the two-pass form)
+  static const bool eval_fast_on = tc_env_int("FU_EVAL_FAST", 1) != 0;
+  const bool eval_fast = eval_fast_on && !training && !save && e->cfg.precision != FU_PRECISION_FP32;
+  if (e->cfg.precision == FU_PRECISION_BF16) rc = forward_t<bf16>(e, x, B, H, W, training, seg, logits, heat, eval_fast);
+  else rc = forward_t<float>(e, x, B, H, W, training, seg, logits, heat, eval_fast);
   side_join(e);
   if (rc) return rc;
   e->saved = save != 0;

@@ -1187,6 +1187,27 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const T* r, int r_ld, T* z, int z_ld, const BnFwdFin f,
                                                                 long long P, int C);
 
+// Eval mode: the folded scale / shift of EVERY BatchNorm layer of the network from its running statistics, one block per
+// layer (nn.BatchNorm2d in eval(), unet.py:214-215,221-222): a = gamma / sqrt(running_var + eps), b = beta - mean * a.
+// They are known before the convolutions run, so the tensor-core epilogues apply them right behind the ReLU.
+struct BnEvalTable {
+  enum { kMax = 48 };
+  const float* gamma[kMax]; const float* beta[kMax]; const float* rmean[kMax]; const float* rvar[kMax];
+  float* a[kMax]; float* b[kMax]; float* mean_o[kMax]; float* invstd_o[kMax];
+  int C[kMax]; int count; float eps;
+};
+__global__ void bn_eval_coeffs_kernel(const BnEvalTable t) {
+  pdl_wait(); pdl_trigger();
+  const int e = blockIdx.x;
+  if (e >= t.count) return;
+  for (int i = threadIdx.x; i < t.C[e]; i += blockDim.x) {
+    const float mean = t.rmean[e][i], invstd = rsqrtf(t.rvar[e][i] + t.eps);
+    const float a = t.gamma[e][i] * invstd;
+    t.a[e][i] = a; t.b[e][i] = t.beta[e][i] - mean * a;
+    t.mean_o[e][i] = mean; t.invstd_o[e][i] = invstd;
+  }
+}
+
 // 16-byte vector access per storage type: 4 fp32 or 8 bf16 channels per thread
 // 16-byte vectors of the two storage types.  `raw`/`unpack` split a load from its conversion so that several
 // loads can be in flight while costing 4 registers each.

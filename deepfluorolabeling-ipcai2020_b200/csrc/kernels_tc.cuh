@@ -304,6 +304,8 @@ struct TcConvParams {
   // with lo at `b_lo`.  Output and second epilogue operand are fp32.
   int a_lo, b_lo;
   const float* tf;              // (F32) second epilogue operand, fp32 NHWC with pixel stride t_ld
+  int post;                     // 1: bn_a / bn_b are applied AFTER the ReLU (out = bn_a * relu(acc + bias) + bn_b, no `t`):
+                                // eval-mode BatchNorm folded into the producing convolution
   int dual;                     // two MMA-issuing warps on alternate tiles (stages >= 2 x the K iterations of a tile, so
                                 // that an issuer one tile ahead is never a whole ring round ahead; see TcConv3Params)
 };
@@ -613,6 +615,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
+          if (p.post) {          // eval-mode BatchNorm behind the ReLU: z = a * relu(conv) + b (unet.py:213-215)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaf(vec[vlen + c0 + i], f[i], vec[2 * vlen + c0 + i]);
+          }
           if (!valid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = 0.f;
@@ -714,6 +720,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.relu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.post) {            // eval-mode BatchNorm behind the ReLU: z = a * relu(conv) + b (unet.py:213-215)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaf(vec[vlen + c0 + i], f[i], vec[2 * vlen + c0 + i]);
         }
         if (!valid) {
 #pragma unroll
@@ -876,6 +886,7 @@ struct TcConv3Params {
   // both sources, fp32 second epilogue operand
   int a_lo, b_lo, a2_lo, b2_lo;
   const float* tf;
+  int post;                     // see TcConvParams
   int dual;                     // 1: two MMA-issuing warps take alternate super tiles.  Only when an issuer that runs one
                                 // super tile ahead can never be a whole ring round ahead of the other (mbarrier parity
                                 // waits cannot tell round r from round r - 2): resident weights and a_stages >= 2 x the A
@@ -1306,6 +1317,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
               }
+              if (p.post) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) f[k] = fmaf(vec[p.N + c0 + k], f[k], vec[2 * p.N + c0 + k]);
+              }
               uint8_t* stg = staging + (uint32_t)(j & 1) * 16384u;
               if (et == 0) ptx::tma_store_wait_read1();
               ptx::named_bar_sync(bar_id, 128);
@@ -1393,6 +1408,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (p.relu) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
+            }
+            if (p.post) {        // eval-mode BatchNorm behind the ReLU: z = a * relu(conv) + b (unet.py:213-215)
+#pragma unroll
+              for (int k = 0; k < 32; ++k) f[k] = fmaf(vec[p.N + c0 + k], f[k], vec[2 * p.N + c0 + k]);
             }
             if (row_ok) {
               // rows that fall outside the image are written as zeros so the statistics can scan the tile
@@ -2639,13 +2658,13 @@ inline bool tc_conv_eligible(const TcConv& t, const void* x, int x_ld, const voi
 // to `tp` inside this launch (see TcBnFin) instead of reading bn_a / bn_b
 inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W, const float* bias,
                            int relu, double* stat, const void* tp, int t_ld, const float* bn_a, const float* bn_b,
-                           int accumulate, cudaStream_t stream, fu_counters* cnt, const TcBnFin* fin = nullptr) {
+                           int accumulate, cudaStream_t stream, fu_counters* cnt, const TcBnFin* fin = nullptr, int post = 0) {
   if (fin && tc_use_v2(t, H, W)) { tc_err() = "BN finalisation can only ride on the 1x1 kernel"; return -1; }
   if (tc_use_v2(t, H, W)) {
     TcConv::Cached3* c3 = tc_prepare3(t, 0, x, x_ld, y, y_ld, B, H, W);
     if (c3) {
       c3->p.bias = bias; c3->p.relu = relu; c3->p.stat = stat;
-      tc_set_t(t, c3->p, tp, t_ld); c3->p.bn_a = bn_a; c3->p.bn_b = bn_b;
+      tc_set_t(t, c3->p, tp, t_ld); c3->p.bn_a = bn_a; c3->p.bn_b = bn_b; c3->p.post = post;
       if (accumulate) { tc_set_t(t, c3->p, y, y_ld); c3->p.bn_a = nullptr; c3->p.bn_b = nullptr; }
       return tc_launch3(c3, stream, cnt);
     }   // else: the halo configuration does not fit shared memory for this shape -> first-generation kernel
@@ -2653,7 +2672,7 @@ inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld
   TcConv::Cached* c = tc_prepare(t, 0, x, x_ld, y, y_ld, B, H, W);
   if (!c) return -1;
   c->p.bias = bias; c->p.relu = relu; c->p.stat = stat;
-  tc_set_t(t, c->p, tp, t_ld); c->p.bn_a = bn_a; c->p.bn_b = bn_b;
+  tc_set_t(t, c->p, tp, t_ld); c->p.bn_a = bn_a; c->p.bn_b = bn_b; c->p.post = post;
   if (accumulate) { tc_set_t(t, c->p, y, y_ld); c->p.bn_a = nullptr; c->p.bn_b = nullptr; }
   if (fin) c->p.fin = *fin; else memset(&c->p.fin, 0, sizeof(c->p.fin));
   return tc_launch(c, stream, cnt);

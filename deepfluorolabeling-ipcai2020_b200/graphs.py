@@ -67,3 +67,46 @@ class GraphedStep:
         for m in self.modules:
             m.mark_weights_changed()
         return self.static_out
+
+
+class GraphedForward:
+    """CUDA-graph replay of the inference forward of one or several networks on a fixed input shape.
+
+    The ensemble loop of util.py:321-366 runs every network on every image batch; eagerly that is ~60 kernel launches
+    per network per batch issued from Python through ctypes, and the host cannot keep three B200-sized forward passes
+    fed.  Capturing the eval-mode, no-grad forwards of all `nets` on one static input -- the networks run back to back
+    inside ONE graph, programmatic dependent launches included -- makes a batch one launch.  The networks must be in
+    eval() mode and their weights frozen: the engine packs its weight copies when it sees a new parameter version, which a
+    replay cannot do, so re-create the object after load_state_dict / optimizer steps."""
+
+    def __init__(self, nets, example_x, warmup=2):
+        if not isinstance(example_x, torch.Tensor) or not example_x.is_cuda:
+            raise ValueError("GraphedForward: example_x must be a CUDA tensor")
+        nets = list(nets)
+        if not nets or any(n.training for n in nets):
+            raise ValueError("GraphedForward: pass networks in eval() mode")
+        self.nets = nets
+        self.static_x = example_x.clone()
+        dev = example_x.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                for n in nets:
+                    n(self.static_x)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = [n(self.static_x) for n in nets]
+        torch.cuda.synchronize(dev)
+
+    def __call__(self, x):
+        """Returns the list of the networks' outputs (static tensors, overwritten by the next call)."""
+        if x.shape != self.static_x.shape or x.dtype != self.static_x.dtype:
+            raise ValueError(f"GraphedForward: input {tuple(x.shape)}/{x.dtype} does not match the captured "
+                             f"{tuple(self.static_x.shape)}/{self.static_x.dtype}")
+        if x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
