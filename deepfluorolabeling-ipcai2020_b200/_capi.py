@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfluorounet.so")
+LIB_PATH = os.environ.get("FLUORO_UNET_LIB") or os.path.join(HERE, "libfluorounet.so")   # (override: A/B builds of the same sources)
 
 FU_OK = 0
 FU_ERR_INVALID_CONFIG = -1

@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB + ".tmp", os.path.join(CSRC, "engine.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("FU_NVCC_EXTRA", "").split() + ["-o", LIB + ".tmp", os.path.join(CSRC, "engine.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -46,6 +46,24 @@ __device__ __forceinline__ float rnd(float v, const bf16*) { return __bfloat162f
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- division by a launch-time constant ----
+// q = n / d for 0 <= n < 2^31 as multiply-high + add + shift (3 instructions; a 32-bit integer division compiles to
+// ~25).  The persistent convolution kernels decode a tile index with up to six divisions per tile in every epilogue
+// warp: ~150 of the ~800 warp instructions per tile the thin layers executed (ncu source page, round 2).
+// d >= 1; s = ceil(log2 d); m = floor(2^32 (2^s - d) / d) + 1  (Granlund-Montgomery round-up variant).
+struct FastDiv {
+  uint32_t d, m, s;
+  __host__ __device__ FastDiv() : d(1), m(1), s(0) {}
+  __host__ explicit FastDiv(int dd) {
+    d = dd < 1 ? 1u : (uint32_t)dd;
+    s = 0;
+    while ((1ull << s) < d) ++s;
+    m = (uint32_t)((((1ull << s) - d) << 32) / d) + 1u;
+  }
+  __device__ __forceinline__ int div(int n) const { return (int)((__umulhi(m, (uint32_t)n) + (uint32_t)n) >> s); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * (int)d; }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

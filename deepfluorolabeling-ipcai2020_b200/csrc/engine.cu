@@ -115,6 +115,8 @@ struct fu_engine {
   char* wgrad_scr = nullptr; size_t wgrad_scr_bytes = 0;   // tensor-core weight-gradient accumulators
   float *ones = nullptr, *zeros = nullptr;
   float* heads_gacc = nullptr;   // [NL*(CF+NC) + NC*CF] accumulators of the fused heads backward
+  unsigned* coop_bar = nullptr;  // {arrival count, generation} of the grid barrier in bn_act_bwd_coop_kernel (self-resetting)
+  int coop_blocks_per_sm = -1;   // resident blocks per SM of that kernel (occupancy query, once); 0 = do not use it
   // batched weight pack / weight-gradient unpack (kernels_tc.cuh): device job tables and what they hold
   static constexpr int kJobCap = 512;
   TcPackJob* pack_tbl = nullptr; TcUnpackJob* unpack_tbl = nullptr;
@@ -445,6 +447,7 @@ void carve_persistent(fu_engine* e, Bump& w, Bump& df, Bump& db, Bump& ws) {
   e->ones = w.take<float>(maxc);
   e->zeros = w.take<float>(maxc);
   e->heads_gacc = w.take<float>((size_t)(e->cfg.num_lands + e->cfg.n_classes) * (e->Cf + e->cfg.n_classes) + 64);
+  e->coop_bar = reinterpret_cast<unsigned*>(w.take<float>(4));     // (wmem is zeroed once at allocation)
 }
 
 int alloc_persistent(fu_engine* e) {
@@ -752,25 +755,24 @@ int run_wgrad(fu_engine* e, const WgradCall& c) {
   return FU_OK;
 }
 
-inline dim3 red_grid(fu_engine* e, long long P, int C) {
+inline dim3 red_grid(fu_engine* e, long long P, int C, int max_lanes = kRedLanes) {
   const int cvecs = C / (e->esz == 2 ? 8 : 4);     // Vec<T>::N channels per thread
-  const int lanes = cvecs < 256 ? cvecs : 256;
+  const int lanes = cvecs < max_lanes ? cvecs : max_lanes;
   const int rows = 256 / lanes;
-  // 16 x `rows` pixel rows per block.  Two attempts to get more blocks in flight on the small, wide levels
-  // (6x6 ... 24x24, where these kernels are latency bound at 12-16 us) were measured and dropped: smaller chunks
-  // made every kernel end in 4-32x more fp64 atomics (1.6x slower overall), and reducing across 8-block clusters
-  // through distributed shared memory first made the big levels pay for cluster scheduling (act_bwd 0.54 -> 0.97 ms).
-  // pixel rows per thread: 16 on the big levels; fewer (down to 4) on the small ones so that at least ~4 blocks per SM
-  // are in flight -- with the per-channel atomics spread over kRedCopies copies more blocks no longer mean a longer
-  // serial atomic chain per address
+  // 16 x `rows` pixel rows per block on the big levels; fewer (down to 2) on the small, wide ones until ~1.5 blocks per
+  // SM exist.  A block covers at most kRedLanes channel vectors (grid.y = channel groups), so more blocks no longer
+  // mean proportionally more fp64 atomics: round 1 had blocks spanning all C channels, where finer grids were 1.6x
+  // slower, and an 8-block cluster / DSMEM pre-reduction made the big levels pay for cluster scheduling.
   long long per = 16;
-  static const int per_min = tc_env_int("FU_RED_PER_MIN", 16);   // (finer grids measured slower: 5.99 -> 6.13 ms per step)
-  while (per > per_min && (P + rows * per - 1) / (rows * per) < (long long)e->num_sms * 4) per >>= 1;
+  static const int per_env = tc_env_int("FU_RED_PER_MIN", 2);
+  const int per_min = max_lanes == kRedLanes ? per_env : 16;      // (the forward apply kernel keeps its round-1 grid)
+  const unsigned gy = (unsigned)((cvecs + lanes - 1) / lanes);
+  while (per > per_min && (P + rows * per - 1) / (rows * per) * gy < (long long)e->num_sms * 3 / 2) per >>= 1;
   long long gx = (P + (long long)rows * per - 1) / ((long long)rows * per);
-  const long long cap = (long long)e->num_sms * 8;
+  const long long cap = std::max<long long>((long long)e->num_sms * 8 / gy, 1);
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  return dim3((unsigned)gx, (unsigned)((cvecs + lanes - 1) / lanes));
+  return dim3((unsigned)gx, gy);
 }
 
 float* tdata(fu_engine* e, int idx) { return idx < 0 ? nullptr : reinterpret_cast<float*>(e->tensors[idx].data); }
@@ -907,7 +909,7 @@ int block_forward(fu_engine* e, Block& blk, const View& x_in, const View& out, i
         f.rvar = tdata(e, b.i_rv); f.nbt = reinterpret_cast<long long*>(e->tensors[b.i_nbt].data);
         f.mean_o = b.mean; f.invstd_o = b.invstd; f.a_o = b.a; f.b_o = b.b; f.training = training;
         f.momentum = 0.1f; f.eps = 1e-5f;
-        LAUNCH(e, (bn_finalize_apply_kernel<T>), red_grid(e, P, b.C).x, 256, reinterpret_cast<const T*>(r.p), r.ld,
+        LAUNCH(e, (bn_finalize_apply_kernel<T>), red_grid(e, P, b.C, 256).x, 256, reinterpret_cast<const T*>(r.p), r.ld,
                reinterpret_cast<T*>(z.p), z.ld, f, P, b.C);
         cur = z;
       } else {
@@ -1220,15 +1222,33 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
     e->set_tag(0, 5.0 * P * blk.C * e->esz, "act_bwd %dx%d C%d", H, W, blk.C);
     if (bn) {
       BNL& b = blk.bns[i];
-      LAUNCH(e, (bn_bwd_reduce_kernel<T>), red_grid(e, P, b.C), 256, dp, d.ld, reinterpret_cast<const T*>(r.p),
-             r.ld, b.mean, b.invstd, P, b.C, b.bstat);
       BnBwdFin fin;
       fin.bstat = b.bstat; fin.gamma = tdata(e, b.i_gamma); fin.g_gamma = gptr(e, flat, b.i_gamma);
       fin.g_beta = gptr(e, flat, b.i_beta);
       fin.g_extra = (i == nd - 1 && blk.has_res) ? gptr(e, flat, blk.res.b_idx) : nullptr;
       fin.training = training;
-      LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, b.C), 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
-             reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, 1, b.mean, b.invstd, fin, P, b.C, cw.bsum);
+      // one launch (reduce | grid barrier | apply) whenever the whole grid can be resident; two launches otherwise
+      dim3 rg = red_grid(e, P, b.C);
+      if (e->coop_blocks_per_sm < 0) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_act_bwd_coop_kernel<T>, 256, 0) != cudaSuccess) occ = 0;
+        const int cap_env = tc_env_int("FU_BN_COOP_OCC", 8);
+        e->coop_blocks_per_sm = occ < cap_env ? occ : cap_env;
+      }
+      // FU_BN_COOP: 0 never, 1 always, 2 (default) tensors of <= FU_BN_COOP_MB megabytes
+      static const int coop_mode = tc_env_int("FU_BN_COOP", 2), coop_mb = tc_env_int("FU_BN_COOP_MB", 12);
+      const bool coop_want = coop_mode == 1 || (coop_mode == 2 && (double)P * b.C * e->esz <= coop_mb * 1048576.0);
+      const long long coop_cap = (long long)e->coop_blocks_per_sm * e->num_sms / rg.y;
+      if (coop_want && coop_cap >= 1) {
+        if ((long long)rg.x > coop_cap) rg.x = (unsigned)coop_cap;
+        LAUNCH(e, (bn_act_bwd_coop_kernel<T>), rg, 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
+               reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, b.mean, b.invstd, fin, b.bstat, P, b.C, cw.bsum, e->coop_bar);
+      } else {
+        LAUNCH(e, (bn_bwd_reduce_kernel<T>), rg, 256, dp, d.ld, reinterpret_cast<const T*>(r.p),
+               r.ld, b.mean, b.invstd, P, b.C, b.bstat);
+        LAUNCH(e, (act_bwd_kernel<T>), rg, 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
+               reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, 1, b.mean, b.invstd, fin, P, b.C, cw.bsum);
+      }
     } else {
       BnBwdFin fin;
       memset(&fin, 0, sizeof(fin));

@@ -1344,14 +1344,18 @@ __global__ void __launch_bounds__(256) bn_finalize_apply_kernel(const T* r, int 
   }
 }
 
-// Shared thread mapping of the per-channel reductions: lanes = min(C/VEC, 256) channel vectors across,
-// 256/lanes pixel rows down; grid.y covers C/VEC > 256.  (C and VEC are powers of two, C >= VEC.)
+// Shared thread mapping of the per-channel reductions: lanes = min(C/VEC, kRedLanes) channel vectors across,
+// 256/lanes pixel rows down; grid.y covers the channel groups beyond kRedLanes vectors.  (C and VEC are powers of two,
+// C >= VEC.)  A block spans at most 8 vectors = one 128-byte line of channels: every block ends in one fp64 atomic
+// per channel it covers, and with blocks that spanned all C channels the 512 / 1024-channel levels issued ~0.5 M
+// atomics per kernel on 2-5 MB tensors (25-30 us per BatchNorm backward at 12x12 where the data moves in 3 us).
+constexpr int kRedLanes = 8;
 template <int VEC>
 struct RedMap {
   int lanes, rows, cv, prow;
   __device__ RedMap(int C) {
     const int cvecs = C / VEC;
-    lanes = cvecs < 256 ? cvecs : 256;
+    lanes = cvecs < kRedLanes ? cvecs : kRedLanes;
     rows = 256 / lanes;
     cv = blockIdx.y * lanes + (threadIdx.x % lanes);
     prow = threadIdx.x / lanes;
@@ -1506,9 +1510,9 @@ __global__ void __launch_bounds__(256, 3) act_bwd_kernel(const T* d, int d_ld, c
     }
     if (has_bn) __syncthreads();                     // sm is written again by block_channel_reduce
   }
-  if (active) {
-    const long long step = (long long)gridDim.x * mp.rows;
-    long long pix = (long long)blockIdx.x * mp.rows + mp.prow;
+  const long long step = (long long)gridDim.x * mp.rows;
+  const long long pix0 = (long long)blockIdx.x * mp.rows + mp.prow;
+  if (active && pix0 < P) {
     auto one = [&](const float* dv, const float* rv, T* dst) {
       float o[V];
 #pragma unroll
@@ -1519,17 +1523,156 @@ __global__ void __launch_bounds__(256, 3) act_bwd_kernel(const T* d, int d_ld, c
 #pragma unroll
       for (int i = 0; i < V; ++i) s[i] += rnd(o[i], dst);
     };
-    for (; pix + step < P; pix += 2 * step) {
+    // pixels pix0 + k*step, k < n, walked from the LAST to the first: bn_bwd_reduce_kernel (same grid, ascending
+    // order) has just read this tensor pair, and what it read last is what the L2 still holds
+    const long long n = (P - pix0 + step - 1) / step;
+    long long k = n - 1;
+    for (; k >= 1; k -= 2) {
+      const long long pa = pix0 + k * step, pb = pa - step;
       float d0[V], r0[V], d1[V], r1[V];
-      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
-      Vec<T>::load(d + (pix + step) * d_ld + c, d1); Vec<T>::load(r + (pix + step) * r_ld + c, r1);
-      one(d0, r0, dy + pix * dy_ld + c);
-      one(d1, r1, dy + (pix + step) * dy_ld + c);
+      Vec<T>::load(d + pa * d_ld + c, d0); Vec<T>::load(r + pa * r_ld + c, r0);
+      Vec<T>::load(d + pb * d_ld + c, d1); Vec<T>::load(r + pb * r_ld + c, r1);
+      one(d0, r0, dy + pa * dy_ld + c);
+      one(d1, r1, dy + pb * dy_ld + c);
     }
-    for (; pix < P; pix += step) {
+    if (k == 0) {
       float d0[V], r0[V];
-      Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
-      one(d0, r0, dy + pix * dy_ld + c);
+      Vec<T>::load(d + pix0 * d_ld + c, d0); Vec<T>::load(r + pix0 * r_ld + c, r0);
+      one(d0, r0, dy + pix0 * dy_ld + c);
+    }
+  }
+  block_channel_reduce<V>(mp, s, red_copy(out, C), C, sm);
+}
+
+// Grid-wide barrier for kernels whose whole grid is resident (the launcher sizes the grid from the occupancy query).
+// bar[0] = arrival count, bar[1] = generation; the last block to arrive resets the count and bumps the generation, so
+// the same two words serve every launch of a stream (and every replay of a captured graph) without a host-side reset.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* genp = bar + 1;
+    const unsigned gen = *genp;
+    __threadfence();                                  // this block's atomics / stores before its arrival
+    if (atomicAdd(bar, 1u) == nblocks - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*genp == gen) __nanosleep(40);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// BatchNorm backward + ReLU backward in ONE launch (bn_bwd_reduce_kernel + act_bwd_kernel with a grid barrier between
+// them): phase 1 adds [sum d | sum d*xhat] into bstat, phase 2 finalises the coefficients from it and writes dy,
+// walking the pixels in the OPPOSITE order so that what phase 1 read last (and the L2 still holds) is read first.
+// Two launches per BatchNorm cost 12-17 us each on the 24x24 ... 6x6 levels (2-10 MB tensors, latency bound), and on
+// the large levels the second pass found nothing of the first in L2.  The grid must be co-resident.
+template <typename T>
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_coop_kernel(const T* d, int d_ld, const T* r, int r_ld,
+                                                              T* dy, int dy_ld, const float* mean, const float* invstd,
+                                                              const BnBwdFin fin, double* bstat, long long P, int C,
+                                                              double* out, unsigned* bar) {
+  pdl_wait(); pdl_trigger();
+  constexpr int V = Vec<T>::N;
+  __shared__ float sm[3 * 256 * V];
+  RedMap<V> mp(C);
+  const bool active = mp.cv * V < C;
+  const int c = mp.cv * V;
+  const long long step = (long long)gridDim.x * mp.rows;
+  const long long pix0 = (long long)blockIdx.x * mp.rows + mp.prow;
+  {
+    float s1[V], s2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    if (active) {
+      float mu[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) mu[i] = mean[c + i];
+      long long pix = pix0;
+      for (; pix + step < P; pix += 2 * step) {
+        float d0[V], r0[V], d1[V], r1[V];
+        Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
+        Vec<T>::load(d + (pix + step) * d_ld + c, d1); Vec<T>::load(r + (pix + step) * r_ld + c, r1);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          s1[i] += d0[i] + d1[i];
+          s2[i] = fmaf(d0[i], r0[i] - mu[i], fmaf(d1[i], r1[i] - mu[i], s2[i]));
+        }
+      }
+      for (; pix < P; pix += step) {
+        float d0[V], r0[V];
+        Vec<T>::load(d + pix * d_ld + c, d0); Vec<T>::load(r + pix * r_ld + c, r0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s1[i] += d0[i]; s2[i] = fmaf(d0[i], r0[i] - mu[i], s2[i]); }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) s2[i] *= invstd[c + i];
+    }
+    double* oc = red_copy(bstat, 2 * C);
+    block_channel_reduce<V>(mp, s1, oc, C, sm);
+    block_channel_reduce<V>(mp, s2, oc + C, C, sm);
+  }
+  grid_barrier(bar, gridDim.x * gridDim.y);
+  float s[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = 0.f;
+  float A[V], Bc[V], Cc[V];
+  {
+    // (see act_bwd_kernel) dy = A*d + Bc*r + Cc where r > 0
+    float* sk = sm;
+    const int nl = mp.lanes * V, li = (threadIdx.x % mp.lanes) * V;
+    if (active && mp.prow == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float mu = mean[c + i], is = invstd[c + i];
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < kRedCopies; ++k) {        // written by other SMs' atomics: read at the L2
+          t1 += __ldcg(bstat + (size_t)k * 2 * C + c + i);
+          t2 += __ldcg(bstat + (size_t)k * 2 * C + C + c + i);
+        }
+        const float a1 = fin.training ? (float)(t1 / (double)P) : 0.f;
+        const float a2 = fin.training ? (float)(t2 / (double)P) : 0.f;
+        const float a = fin.gamma[c + i] * is, b = -a * is * a2;
+        sk[li + i] = a; sk[nl + li + i] = b; sk[2 * nl + li + i] = -a * a1 - b * mu;
+        if (blockIdx.x == 0) {
+          fin.g_gamma[c + i] = (float)t2;
+          fin.g_beta[c + i] = (float)t1;
+          if (fin.g_extra) fin.g_extra[c + i] = (float)t1;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) { A[i] = sk[li + i]; Bc[i] = sk[nl + li + i]; Cc[i] = sk[2 * nl + li + i]; }
+    __syncthreads();
+  }
+  if (active && pix0 < P) {
+    auto one = [&](const float* dv, const float* rv, T* dst) {
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = rv[i] > 0.f ? fmaf(A[i], dv[i], fmaf(Bc[i], rv[i], Cc[i])) : 0.f;
+      Vec<T>::store(dst, o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += rnd(o[i], dst);
+    };
+    const long long n = (P - pix0 + step - 1) / step;          // pixels of this thread: pix0 + k*step, k < n
+    long long k = n - 1;
+    for (; k >= 1; k -= 2) {
+      const long long pa = pix0 + k * step, pb = pa - step;
+      float d0[V], r0[V], d1[V], r1[V];
+      Vec<T>::load(d + pa * d_ld + c, d0); Vec<T>::load(r + pa * r_ld + c, r0);
+      Vec<T>::load(d + pb * d_ld + c, d1); Vec<T>::load(r + pb * r_ld + c, r1);
+      one(d0, r0, dy + pa * dy_ld + c);
+      one(d1, r1, dy + pb * dy_ld + c);
+    }
+    if (k == 0) {
+      float d0[V], r0[V];
+      Vec<T>::load(d + pix0 * d_ld + c, d0); Vec<T>::load(r + pix0 * r_ld + c, r0);
+      one(d0, r0, dy + pix0 * dy_ld + c);
     }
   }
   block_channel_reduce<V>(mp, s, red_copy(out, C), C, sm);

@@ -24,8 +24,30 @@
 #include "common.cuh"
 
 #define FU_TC_BUILD "1"
+// packed fp32x2 epilogue arithmetic (FADD2 / FFMA2): measured on the B200 and left off -- the thin 3x3 layers do not
+// change (32->32 @192x192 forward 63.6 vs 64.0 us) and the 1x1 layers with a second epilogue operand get slower
+// (64->32 @192x192: 98.7 -> 113 us), see gpurun A/B in DESIGN.md section 5
+#ifndef FU_EPI_PACKED
+#define FU_EPI_PACKED 0
+#endif
 
 namespace fu {
+
+// packed fp32 pairs (FADD2 / FFMA2, sm_100): one issue slot for two lanes of an elementwise epilogue op
+__device__ __forceinline__ float2 fu_add2(float2 a, float2 b) {
+#if FU_EPI_PACKED
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float2 fu_fma2(float2 a, float2 b, float2 c) {
+#if FU_EPI_PACKED
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
 
 // ===========================================================================
 // PTX wrappers
@@ -308,6 +330,8 @@ struct TcConvParams {
                                 // eval-mode BatchNorm folded into the producing convolution
   int dual;                     // two MMA-issuing warps on alternate tiles (stages >= 2 x the K iterations of a tile, so
                                 // that an issuer one tile ahead is never a whole ring round ahead; see TcConv3Params)
+  FastDiv fd_ntiles, fd_tw, fd_th;     // tile decode: divisions by n_tiles, tiles_w, tiles_h
+  int cs_shift;                 // log2(CS)
 };
 
 constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (wgrad kernels; the conv kernel has 4*G epilogue warps)
@@ -425,11 +449,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_tx = (uint32_t)(p.tw * p.th * p.tn) * row_bytes;
 
   auto decode = [&](int tile, int& w0, int& h0, int& n0, int& nb) {
-    const int nt = tile % p.n_tiles;
-    int mt = tile / p.n_tiles;
+    int nt, mt, r;
+    p.fd_ntiles.divmod(tile, mt, nt);
     nb = nt * p.BN;
-    w0 = (mt % p.tiles_w) * p.tw; mt /= p.tiles_w;
-    h0 = (mt % p.tiles_h) * p.th; mt /= p.tiles_h;
+    p.fd_tw.divmod(mt, mt, r); w0 = r * p.tw;
+    p.fd_th.divmod(mt, mt, r); h0 = r * p.th;
     n0 = mt * p.tn;
   };
 
@@ -682,6 +706,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
+      // (packed fp32 adds / FMAs and the ReLU on the packed bf16 pairs: see tc_conv3_kernel)
+      const bool relu_packed = p.relu && !p.post;
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
       for (int j = 0; j < p.BN / 32; ++j) {
         uint32_t v[32];
         ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
@@ -691,8 +718,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(vec + c0 + i);
-          f[i] = __uint_as_float(v[i]) + b4.x; f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-          f[i + 2] = __uint_as_float(v[i + 2]) + b4.z; f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+          const float2 r0 = fu_add2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(b4.x, b4.y));
+          const float2 r1 = fu_add2(make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), make_float2(b4.z, b4.w));
+          f[i] = r0.x; f[i + 1] = r0.y; f[i + 2] = r1.x; f[i + 3] = r1.y;
         }
         if (t_on) {
           uint4 tcur[4];
@@ -717,34 +745,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
         if (p.post) {            // eval-mode BatchNorm behind the ReLU: z = a * relu(conv) + b (unet.py:213-215)
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = fmaf(vec[vlen + c0 + i], f[i], vec[2 * vlen + c0 + i]);
         }
-        if (!valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = 0.f;
-        }
-        // 32 channels -> 4 x 16-byte stores into the swizzled staging tile
+        // 32 channels -> 4 x 16-byte stores into the swizzled staging tile (rows outside the image: zeros)
         const int colt = j * 32;                 // column within the BN tile
-        const int sub = colt / p.CS;             // store box this chunk belongs to
-        const uint32_t byte_in_row = (uint32_t)(colt % p.CS) * 2u;
+        const int sub = colt >> p.cs_shift;      // store box this chunk belongs to
+        const uint32_t row_off = (uint32_t)row * pitch + (uint32_t)(colt & (p.CS - 1)) * 2u;
+        uint8_t* dst = staging + (uint32_t)sub * sub_bytes;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-          o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-          const uint32_t logical = (uint32_t)row * pitch + byte_in_row + (uint32_t)g * 16u;
+          uint32_t pk[4];
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g * 8 + 2 * k], f[g * 8 + 2 * k + 1]);
+              if (relu_packed) h2 = __hmax2(h2, zero2);
+              pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          } else {
+            pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+          }
+          const uint32_t logical = row_off + (uint32_t)g * 16u;
           const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
-          *reinterpret_cast<uint4*>(staging + (uint32_t)sub * sub_bytes + phys) = o;
+          *reinterpret_cast<uint4*>(dst + phys) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
@@ -848,17 +877,17 @@ __device__ __forceinline__ void tc_stats_scan(const uint8_t* tile, uint32_t sub_
   for (int sub = 0; sub < 4; ++sub) {
     if (sub < nsub) {
       const uint8_t* tp = tile + (uint32_t)sub * sub_bytes;
-      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+      float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int i0 = 0; i0 < 32 / RPL; i0 += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t off = (base ^ (((uint32_t)k & SMASK) << 4)) + (uint32_t)(i0 + k) * 128u;
           const float2 x2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tp + off));
-          a0 += x2.x; a1 += x2.y; b0 = fmaf(x2.x, x2.x, b0); b1 = fmaf(x2.y, x2.y, b1);
+          a = fu_add2(a, x2); b = fu_fma2(x2, x2, b);          // packed fp32: two instructions per column pair
         }
       }
-      acc[sub][0] += a0; acc[sub][1] += a1; acc[sub][2] += b0; acc[sub][3] += b1;
+      acc[sub][0] += a.x; acc[sub][1] += a.y; acc[sub][2] += b.x; acc[sub][3] += b.y;
     }
   }
 }
@@ -892,6 +921,8 @@ struct TcConv3Params {
                                 // waits cannot tell round r from round r - 2): resident weights and a_stages >= 2 x the A
                                 // slots of one super tile
   int nstg;                     // bf16 staging tiles per epilogue group (2: the TMA store of tile i drains under tile i + 1)
+  FastDiv fd_ntiles, fd_timg, fd_tw;   // divisions by n_tiles, tiles_w * tiles_h, tiles_w (tile decode, every role, every tile)
+  int cs_shift;                 // log2(CS)
 };
 
 // S = epilogue sets.  A set is one group of 4 warps per pixel tile of the pair; super tile i of a CTA is drained
@@ -1002,10 +1033,11 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t box_bytes = (uint32_t)(p.twb * (p.th + 2)) * row_bytes;
 
   auto decode_m = [&](int mt, int& w0, int& h0, int& n) {
-    n = mt / tiles_img;
-    const int r = mt - n * tiles_img;
-    h0 = (r / p.tiles_w) * p.th;
-    w0 = (r % p.tiles_w) * p.two;
+    int r, hq, wq;
+    p.fd_timg.divmod(mt, n, r);
+    p.fd_tw.divmod(r, hq, wq);
+    h0 = hq * p.th;
+    w0 = wq * p.two;
   };
 
   if (warp == prod_warp) {
@@ -1023,7 +1055,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
       for (int st = blockIdx.x; st < total_super; st += gridDim.x) {
-        const int nt = st % p.n_tiles, sp = st / p.n_tiles;
+        int nt, sp;
+        p.fd_ntiles.divmod(st, sp, nt);
         const int nb = nt * p.BN;
         for (int c = 0; c < cchunks; ++c) {
           for (int g = 0; g < groups; ++g) {
@@ -1124,7 +1157,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
           continue;
         }
-        const int sp = st / p.n_tiles;
+        const int sp = p.fd_ntiles.div(st);
         const bool two = npair == 2 && (sp * 2 + 1) < m_tiles;
         if (lane == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 3);     // (dbg) arrived at the accumulator wait
         ptx::mbar_wait(t_empty(acc), acc_phase ^ 1u);
@@ -1261,7 +1294,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       };
       for (int st = blockIdx.x + set * (int)gridDim.x; st < total_super; st += S * (int)gridDim.x) {
-        const int nt = st % p.n_tiles, sp = st / p.n_tiles;
+        int nt, sp;
+        p.fd_ntiles.divmod(st, sp, nt);
         const int nb = nt * p.BN;
         const int mt = sp * p.npair + grp;
         if constexpr (F32) {
@@ -1369,15 +1403,19 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::named_bar_sync(bar_id, 128);
           sbuf ^= 1;
         }
+        // (tile coordinates before the accumulator wait: the index arithmetic hides behind the MMAs)
+        int w0 = 0, h0 = 0, n = 0;
+        if (mt < m_tiles) decode_m(mt, w0, h0, n);
+        const bool valid = row_ok && (w0 + wq) < p.W && (h0 + hi) < p.H;
         ptx::mbar_wait(t_full(acc), acc_phase);
         ptx::tc_fence_after();
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
         if (mt < m_tiles) {
-          int w0, h0, n;
-          decode_m(mt, w0, h0, n);
-          const bool valid = row_ok && (w0 + wq) < p.W && (h0 + hi) < p.H;
           const long long pix = ((long long)n * p.H + (h0 + hi)) * p.W + (w0 + wq);
           const uint32_t t_base = tmem_base + (uint32_t)((acc * p.npair + grp) * p.BN) + ((uint32_t)(q * 32) << 16);
+          // ReLU without a BatchNorm behind it is applied to the packed bf16 pairs (16 instead of 32 instructions per
+          // chunk; rounding is monotonic and keeps zero, so relu(bf16(x)) == bf16(relu(x)))
+          const bool relu_packed = p.relu && !p.post;
           for (int j = 0; j < p.BN / 32; ++j) {
             uint32_t v[32];
             ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
@@ -1385,10 +1423,11 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int c0 = nb + j * 32;
             float f[32];
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) {
+            for (int k = 0; k < 32; k += 4) {      // bias: two packed fp32 adds per four channels
               const float4 b4 = *reinterpret_cast<const float4*>(vec + c0 + k);
-              f[k] = __uint_as_float(v[k]) + b4.x; f[k + 1] = __uint_as_float(v[k + 1]) + b4.y;
-              f[k + 2] = __uint_as_float(v[k + 2]) + b4.z; f[k + 3] = __uint_as_float(v[k + 3]) + b4.w;
+              const float2 r0 = fu_add2(make_float2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), make_float2(b4.x, b4.y));
+              const float2 r1 = fu_add2(make_float2(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])), make_float2(b4.z, b4.w));
+              f[k] = r0.x; f[k + 1] = r0.y; f[k + 2] = r1.x; f[k + 3] = r1.y;
             }
             if (p.t && valid) {
               const bf16* tp = p.t + pix * p.t_ld + c0;
@@ -1405,30 +1444,38 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
               }
             }
-            if (p.relu) {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
-            }
             if (p.post) {        // eval-mode BatchNorm behind the ReLU: z = a * relu(conv) + b (unet.py:213-215)
+              if (p.relu) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
+              }
 #pragma unroll
               for (int k = 0; k < 32; ++k) f[k] = fmaf(vec[p.N + c0 + k], f[k], vec[2 * p.N + c0 + k]);
             }
             if (row_ok) {
               // rows that fall outside the image are written as zeros so the statistics can scan the tile
               const int colt = j * 32;
-              const int sub = colt / p.CS;
-              const uint32_t byte_in_row = (uint32_t)(colt % p.CS) * 2u;
+              const int sub = colt >> p.cs_shift;
+              const uint32_t byte_in_row = (uint32_t)(colt & (p.CS - 1)) * 2u;
+              const uint32_t row_off = (uint32_t)mr * pitch + byte_in_row;
+              uint8_t* dst = stg + (uint32_t)sub * sub_bytes;
+              const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
               for (int g4 = 0; g4 < 4; ++g4) {
                 uint32_t pk[4];
+                if (valid) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(valid ? f[g4 * 8 + 2 * k] : 0.f, valid ? f[g4 * 8 + 2 * k + 1] : 0.f);
-                  pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+                  for (int k = 0; k < 4; ++k) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 2 * k], f[g4 * 8 + 2 * k + 1]);
+                    if (relu_packed) h2 = __hmax2(h2, zero2);
+                    pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+                  }
+                } else {
+                  pk[0] = pk[1] = pk[2] = pk[3] = 0u;
                 }
-                const uint32_t logical = (uint32_t)mr * pitch + byte_in_row + (uint32_t)g4 * 16u;
+                const uint32_t logical = row_off + (uint32_t)g4 * 16u;
                 const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
-                *reinterpret_cast<uint4*>(stg + (uint32_t)sub * sub_bytes + phys) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(dst + phys) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
@@ -1439,8 +1486,6 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 2);
         acc += S; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         if (mt < m_tiles) {
-          int w0, h0, n;
-          decode_m(mt, w0, h0, n);
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
           if (et == 0) {
@@ -2306,6 +2351,8 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   p.BN = bn;
   p.CS = (bn >= 64 && !t.split) ? 64 : 32;
   p.n_tiles = N / p.BN;
+  p.fd_ntiles = FastDiv(p.n_tiles); p.fd_tw = FastDiv(p.tiles_w); p.fd_th = FastDiv(p.tiles_h);
+  p.cs_shift = p.CS == 64 ? 6 : 5;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
   p.nstaging = p.BN <= 64 ? 2 : 1;
   c.G = tc_pick_groups(p.BN, t.k * t.k * (K / p.KC) * (t.split ? 3 : 1), p.KC / 16);
@@ -2399,6 +2446,8 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   p.tn = 1;
   p.tiles_w = (Wg + p.tw - 1) / p.tw; p.tiles_h = (int)((Rg + p.th - 1) / p.th); p.tiles_b = 1;
   p.n_tiles = N / p.BN;
+  p.fd_ntiles = FastDiv(p.n_tiles); p.fd_tw = FastDiv(p.tiles_w); p.fd_th = FastDiv(p.tiles_h);
+  p.cs_shift = p.CS == 64 ? 6 : 5;
   const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
   p.nstaging = p.BN <= 64 ? 2 : 1;
   c.G = tc_pick_groups(p.BN, (gather ? 4 : 1) * (K / p.KC) * (t.split ? 3 : 1), p.KC / 16);
@@ -2491,6 +2540,8 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   tc_pick_halo_tile(H, W, p.halo1 != 0, p.twb, p.th);
   p.two = p.twb - 2;
   p.tiles_w = (W + p.two - 1) / p.two; p.tiles_h = (H + p.th - 1) / p.th;
+  p.fd_ntiles = FastDiv(p.n_tiles); p.fd_timg = FastDiv(p.tiles_w * p.tiles_h); p.fd_tw = FastDiv(p.tiles_w);
+  p.cs_shift = p.CS == 64 ? 6 : 5;
   const size_t row_bytes = (size_t)p.KC * 2;
   size_t rows = (size_t)(p.th + 2) * p.twb + 2;
   if (rows < (size_t)(2 * p.twb + 2 + 128)) rows = (size_t)(2 * p.twb + 2 + 128);

@@ -23,8 +23,10 @@ for spec in args:
     y = torch.empty(*((B, Ho, Wo, Cout) if mode == 0 else (B, H, W, Cin)), device=dev, dtype=torch.bfloat16)
     dw = torch.empty_like(w)
     pad = k // 2 if stride == 1 else 0
+    # CONV_STATS=1: forward launches also accumulate the BatchNorm statistics in their epilogue (as in a training step)
+    st = torch.zeros(2 * Cout, device=dev, dtype=torch.float64) if (os.environ.get("CONV_STATS") == "1" and mode == 0) else None
     def run():
-        rc = L.fu_test_conv(1, 1, mode, B, H, W, Cin, Cout, k, stride, pad, 1 if stride == 1 else 0, p(x), p(w), p(b), p(y), p(dy), p(dw), None, None)
+        rc = L.fu_test_conv(1, 1, mode, B, H, W, Cin, Cout, k, stride, pad, 1 if stride == 1 else 0, p(x), p(w), p(b), p(y), p(dy), p(dw), p(st) if st is not None else None, None)
         assert rc == 0, pkg._capi.last_error(None)
     run()
     if timed:
