@@ -261,9 +261,11 @@ __device__ __forceinline__ void tc_mma_tap(uint32_t d0, uint32_t d1, bool two, u
 // sequence (9 taps x KS steps x 2 tiles, ~5-10 KB of SASS per super tile) was evicted between super tiles -- 48 % of
 // the issuing warp's stall samples were "no instruction" (ncu source page, profiles/r02_ncu_thin_conv_before.txt).
 // g < 0: all nine taps; otherwise the three taps with kw == g (one-load-per-kw mode).  Offsets in 16-byte units.
+// baton != 0: mbarrier to arrive on when the last filter row starts (hands the tensor pipe to the other issuer, below).
 __device__ __forceinline__ void tc_mma_taps_resident(int ksteps, uint32_t d0, uint32_t d1, bool two, uint32_t a_lo0,
                                                      uint32_t a_tile16, uint32_t b_lo0, uint32_t b16, uint32_t kh16,
-                                                     uint32_t kw16, int g, uint32_t hi, uint32_t idesc, uint32_t accum) {
+                                                     uint32_t kw16, int g, uint32_t hi, uint32_t idesc, uint32_t accum,
+                                                     uint32_t baton = 0u, int baton_kh = 2) {
   uint32_t a_row = a_lo0;
   uint32_t b_lo = g < 0 ? b_lo0 : b_lo0 + (uint32_t)g * b16;
   const int nkw = g < 0 ? 3 : 1;
@@ -271,6 +273,7 @@ __device__ __forceinline__ void tc_mma_taps_resident(int ksteps, uint32_t d0, ui
 #pragma unroll 1
   for (int kh = 0; kh < 3; ++kh, a_row += kh16) {
     uint32_t a_lo = a_row;
+    if (kh == baton_kh && baton) ptx::mbar_arrive(baton);
 #pragma unroll 1
     for (int kw = 0; kw < nkw; ++kw, a_lo += kw16, b_lo += b_step) {
       if (ksteps == 4) tc_mma_tap<4>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, hi, idesc, accum);
@@ -279,6 +282,7 @@ __device__ __forceinline__ void tc_mma_taps_resident(int ksteps, uint32_t d0, ui
       accum = 1u;
     }
   }
+  if (baton_kh >= 3 && baton) ptx::mbar_arrive(baton);
 }
 
 // ===========================================================================
@@ -351,7 +355,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - raw);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role-local scalars can live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // Warp roles.  The epilogue warps come FIRST and the TMA producer / MMA issuer LAST: the SM sub-partition schedulers
   // prefer the highest warp id among eligible warps, and the single MMA-issuing thread is the critical path of the
   // thin layers -- as warp 1 it was starved by the (instruction-heavy) epilogue warps sharing its scheduler (ncu:
@@ -923,6 +928,7 @@ struct TcConv3Params {
   int nstg;                     // bf16 staging tiles per epilogue group (2: the TMA store of tile i drains under tile i + 1)
   FastDiv fd_ntiles, fd_timg, fd_tw;   // divisions by n_tiles, tiles_w * tiles_h, tiles_w (tile decode, every role, every tile)
   int cs_shift;                 // log2(CS)
+  int baton_kh;                 // filter row (0..2) of a super tile's last section at which the issuer passes the baton
 };
 
 // S = epilogue sets.  A set is one group of 4 warps per pixel tile of the pair; super tile i of a CTA is drained
@@ -938,7 +944,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role-local scalars can live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // Warp roles.  The epilogue warps come FIRST and the TMA producer / MMA issuer LAST: the SM sub-partition schedulers
   // prefer the highest warp id among eligible warps, and the single MMA-issuing thread is the critical path of the
   // thin layers -- as warp 1 it was starved by the (instruction-heavy) epilogue warps sharing its scheduler (ncu:
@@ -978,6 +985,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto t_full = [&](int a) { return bar_base + 8u * (uint32_t)(32 + a); };
   auto t_empty = [&](int a) { return bar_base + 8u * (uint32_t)(36 + a); };
   const uint32_t res_bar = bar_base + 8u * 40u;
+  auto baton_bar = [&](int x) { return bar_base + 8u * (uint32_t)(42 + x); };
   const uint32_t slot_addr = bar_base + 8u * 41u;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * 41u);
   uint32_t tmem_cols = 32;
@@ -990,6 +998,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < NACC; ++a) { ptx::mbar_init(t_full(a), 1); ptx::mbar_init(t_empty(a), 128u * (uint32_t)p.npair); }
     ptx::mbar_init(res_bar, 1);
+    ptx::mbar_init(baton_bar(0), 1); ptx::mbar_init(baton_bar(1), 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
     if (p.res) { ptx::prefetch_tmap(&tmA2); ptx::prefetch_tmap(&tmB2); }
@@ -1131,8 +1140,16 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // only ~4 MMAs, runs dry: FU_TC_DBG timeline of 32->32 @192x192: 1750 cycles of MMAs per 4050-cycle super tile.
     // Two issuers take alternate super tiles (each tracks the rings of the tiles it skips), so one issuer's round trips
     // overlap the other's MMAs; the MMAs of consecutive super tiles go to different accumulators and are independent.
+    // Left to themselves the two issuers fall into lock step (both issue into the one tensor pipe at the same time, both
+    // finish together, both epilogue sets wake together, and both issuers then crawl through their ~1200-4000 cycle
+    // control path while the pipe idles: FU_TC_DBG timeline of 32->32 @192x192, round 2: MMA phase 3000 cycles, then
+    // 3900 idle).  p.dual == 2: a baton (two mbarriers) makes them alternate strictly -- an issuer does its waits for
+    // super tile i + 1 while the other issues tile i, starts only when the other has reached its last filter row, and
+    // the epilogue sets are de-phased with them.
     {
       const int mw = warp - mma_warp;               // issuer 0 / 1
+      const bool use_baton = p.dual == 2;
+      uint32_t bat_phase = 0; bool bat_first = mw == 0;
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
@@ -1170,6 +1187,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int g = 0; g < groups; ++g) {
             ptx::mbar_wait(a_full(as), aph);
             if (lane == 0 && c == 0 && g == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
+            if (use_baton && c == 0 && g == 0) {          // my turn at the tensor pipe (issuer 0 opens)
+              if (!bat_first) { ptx::mbar_wait(baton_bar(mw), bat_phase); bat_phase ^= 1u; }
+              bat_first = false;
+            }
             const uint32_t a_lo0 = dlo + ((smem_base + a_off + (uint32_t)as * a_stage_bytes) >> 4);
             const bool last_group = c == cchunks - 1 && g == groups - 1 && !p.res;
             if (resident) {
@@ -1178,7 +1199,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (c == 0 && g == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 2);   // (dbg) first MMA about to issue
                 const uint32_t b_lo0 = dlo + ((smem_base + b_off + (uint32_t)(w_index(c) * 9) * b_bytes) >> 4);
                 // (halo1: all nine taps; otherwise one A load per kw and only the taps with kw == g)
-                tc_mma_taps_resident(ksteps, d0, d1, two, a_lo0, a_tile16, b_lo0, b16, kh16, kw16, halo1 ? -1 : g, dhi, idesc, accum);
+                tc_mma_taps_resident(ksteps, d0, d1, two, a_lo0, a_tile16, b_lo0, b16, kh16, kw16, halo1 ? -1 : g, dhi, idesc, accum,
+                                     (use_baton && last_group) ? baton_bar(mw ^ 1) : 0u, p.baton_kh);
                 ptx::umma_commit(a_empty(as));
                 if (last_group) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
               }
@@ -1220,6 +1242,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const uint32_t b_addr = resident ? smem_base + b_off + (uint32_t)(wchunks * 9 + w_index(c)) * b_bytes
                                                : smem_base + b_off + (uint32_t)bs * b_bytes;
               const uint32_t b_lo = dlo + (b_addr >> 4);
+              if (use_baton && c == cchunks - 1) ptx::mbar_arrive(baton_bar(mw ^ 1));     // last section of this super tile
               if (ksteps == 4) tc_mma_tap<4>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
               else if (ksteps == 2) tc_mma_tap<2>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
               else tc_mma_tap<1>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
@@ -1600,7 +1623,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role-local scalars can live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr uint32_t kBox = 64u * 128u;                 // 64 pixels x 64 channels bf16
   const int nblk_b = p.N / 64;
   const uint32_t a_bytes = 2u * kBox;
@@ -1746,7 +1770,8 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role-local scalars can live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr uint32_t kABox = 64u * 128u;                   // room for 64 pixels x 64 channels
   const uint32_t a_bytes = 2u * kABox;
   const uint32_t brow = (uint32_t)p.cb * 2u;                // bytes per pixel row of a B box
@@ -2595,6 +2620,8 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     const int vchunks = (K / p.KC) * (t.split ? 3 : 1);
     const int a_per_tile = vchunks * (p.halo1 ? 1 : 3) + (p.res ? vchunks : 0);
     p.dual = (p.resident && p.a_stages >= 2 * a_per_tile && tc_env_int("FU_TC_DUAL", 1)) ? 1 : 0;
+    if (p.dual && tc_env_int("FU_TC_BATON", 1)) p.dual = 2;
+    p.baton_kh = tc_env_int("FU_TC_BATON_KH", 2);   // measured (32->32 @192x192 dgrad): row 0: 55.0, 1: 50.3, 2: 47.6 us; no baton 56.4
   }
   const long long Kw = t.split ? 2 * K : K;       // K width of the weight layouts ([hi | lo] in split mode)
   {
