@@ -336,7 +336,13 @@ struct TcConvParams {
                                 // that an issuer one tile ahead is never a whole ring round ahead; see TcConv3Params)
   FastDiv fd_ntiles, fd_tw, fd_th;     // tile decode: divisions by n_tiles, tiles_w, tiles_h
   int cs_shift;                 // log2(CS)
+  int t_smem;                   // 1: the second epilogue operand `t` is brought into shared memory by the TMA producer
+                                // (map tmT, two tiles per epilogue group, laid out like the staging tile) instead of being
+                                // loaded from global memory by the epilogue threads: with 1-8 MMAs per tile the accumulator
+                                // is ready at once and the threads' own loads put a full memory latency into every tile
+                                // (ncu, residual 1x1 64->32 @192x192: 59 % of the stall samples long-scoreboard, 3.8 TB/s)
 };
+constexpr int kTcTBufs = 2;           // `t` tiles per epilogue group
 
 constexpr int kTcThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (wgrad kernels; the conv kernel has 4*G epilogue warps)
 constexpr int kTcMaxStages = 8;
@@ -349,7 +355,7 @@ constexpr int kTc3Threads = 320;      // halo kernel: producer, MMA, 2 x 4 epilo
 template <int G, bool F32 = false>
 __global__ void __launch_bounds__(96 + 128 * G, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const TcConvParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmT, const TcConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
@@ -370,7 +376,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t staging_bytes = F32 ? 16384u : 128u * (uint32_t)p.BN * 2u;
   const int vlen = p.c5 ? p.Cst : p.N;                              // channels of the bias / bn vectors
   const int nstg = F32 ? 2 : p.nstaging;                             // 1 or 2 staging tiles (double buffered stores)
-  const uint32_t vec_off = staging_off + (uint32_t)(G * nstg) * staging_bytes;   // bias | bn_a | bn_b, [3][vlen] floats
+  const uint32_t tbuf_off = staging_off + (uint32_t)(G * nstg) * staging_bytes;  // `t` tiles [G][kTcTBufs] (t_smem)
+  const uint32_t vec_off = tbuf_off + (p.t_smem ? (uint32_t)(G * kTcTBufs) * staging_bytes : 0u);   // bias | bn_a | bn_b, [3][vlen] floats
   const uint32_t park_off = vec_off + 3u * (uint32_t)vlen * 4u;     // (F32) statistics partials [G][4][2][BN] floats
   const uint32_t bar_off = (park_off + (F32 ? (uint32_t)(G * 8 * p.BN) * 4u : 0u) + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
@@ -381,6 +388,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + NACC + a); };
   const uint32_t slot_addr = bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 2 * NACC);
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * (2 * kTcMaxStages + 2 * NACC));
+  // `t` tile barriers: index g * kTcTBufs + b
+  auto tt_full = [&](int i) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 2 * NACC + 1 + i); };
+  auto tt_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 * kTcMaxStages + 2 * NACC + 1 + G * kTcTBufs + i); };
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(NACC * p.BN)) tmem_cols <<= 1;
@@ -388,6 +398,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 128); }
+    for (int i = 0; i < G * kTcTBufs; ++i) { ptx::mbar_init(tt_full(i), 1); ptx::mbar_init(tt_empty(i), 128); }
+    if (p.t_smem) ptx::prefetch_tmap(&tmT);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
   }
@@ -466,9 +478,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ TMA producer (whole warp loops, one elected lane issues) -----
     {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0;
+      const uint32_t t_sub_bytes = 128u * (uint32_t)p.CS * 2u;
+      const uint32_t t_tx = (uint32_t)(p.tw * p.th * p.tn) * (uint32_t)p.BN * 2u;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         int w0, h0, n0, nb;
         decode(tile, w0, h0, n0, nb);
+        if (p.t_smem) {
+          // the tile's second epilogue operand, for the group that will drain it (tile i of the CTA -> group i % G,
+          // buffer (i / G) % kTcTBufs of that group)
+          const int g = it % G, u = it / G, b = u % kTcTBufs, bi = g * kTcTBufs + b;
+          ptx::mbar_wait(tt_empty(bi), (((uint32_t)(u / kTcTBufs)) & 1u) ^ 1u);
+          if (ptx::elect_one()) {
+            const uint32_t dst = smem_base + tbuf_off + (uint32_t)bi * staging_bytes;
+            ptx::mbar_expect_tx(tt_full(bi), t_tx);
+            for (int s2 = 0; s2 < p.BN / p.CS; ++s2) {
+              if (p.c5) {
+                const int col = nb + s2 * p.CS, ab = col >> p.cst_shift;
+                ptx::tma_load_5d(dst + (uint32_t)s2 * t_sub_bytes, &tmT, tt_full(bi), col & (p.Cst - 1), ab & 1, w0, ab >> 1, h0);
+              } else {
+                ptx::tma_load_4d(dst + (uint32_t)s2 * t_sub_bytes, &tmT, tt_full(bi), nb + s2 * p.CS, w0, h0, n0);
+              }
+            }
+          }
+          __syncwarp();
+        }
         for (int kit = 0; kit < k_iters; ++kit) {
           const int tap = kit / vchunks, vc = kit - tap * vchunks;
           int c0 = vc * p.KC, cb0 = c0;
@@ -552,6 +586,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t staging_addr = smem_base + grp_staging_off;
     int sbuf = 0;
     int acc = grp; uint32_t acc_phase = 0;
+    int tb = 0; uint32_t tph = 0;           // `t` tile ring of this group (t_smem)
     const int rows_in_tile = p.tw * p.th * p.tn;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, ni = row / (p.tw * p.th);
     const float* vec = reinterpret_cast<const float*>(smem + vec_off);
@@ -702,7 +737,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         sbuf ^= 1;
       }
       uint4 tnext[4];
-      const bool t_on = p.t != nullptr && valid;
+      const bool t_sm = p.t_smem != 0;
+      // (the G = 4 instantiation runs at the 96-register limit: there `t` only ever comes through shared memory --
+      //  the launcher falls back to G = 2 otherwise -- and the register-resident global-load pipeline below is not compiled)
+      const bool t_on = G < 4 && p.t != nullptr && valid && !t_sm;
+      const uint8_t* tbuf = smem + tbuf_off + (uint32_t)(grp * kTcTBufs + tb) * staging_bytes;
+      if (t_sm) ptx::mbar_wait(tt_full(grp * kTcTBufs + tb), tph);
       if (t_on) {
         const uint4* tp4 = reinterpret_cast<const uint4*>(p.t + chunk_pix(nb) * p.t_ld + chunk_cb(nb));
 #pragma unroll
@@ -750,6 +790,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        // 32 channels <-> 4 x 16 bytes of the swizzled staging tile (rows outside the image: zeros)
+        const int colt = j * 32;                 // column within the BN tile
+        const int sub = colt >> p.cs_shift;      // store box this chunk belongs to
+        const uint32_t row_off = (uint32_t)row * pitch + (uint32_t)(colt & (p.CS - 1)) * 2u;
+        if (t_sm) {
+          // second operand from its shared-memory tile (same layout as the staging tile): f += a * t + b
+          const uint8_t* src = tbuf + (uint32_t)sub * sub_bytes;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t logical = row_off + (uint32_t)g * 16u;
+            const uint32_t phys = logical ^ (((logical >> 7) & swz_mask) << 4);
+            const uint4 u = *reinterpret_cast<const uint4*>(src + phys);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float2 tf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k2]));
+              const int c = g * 8 + 2 * k2;
+              f[c] += vec[vlen + c0 + c] * tf.x + vec[2 * vlen + c0 + c];
+              f[c + 1] += vec[vlen + c0 + c + 1] * tf.y + vec[2 * vlen + c0 + c + 1];
+            }
+          }
+        }
         if (p.post) {            // eval-mode BatchNorm behind the ReLU: z = a * relu(conv) + b (unet.py:213-215)
           if (p.relu) {
 #pragma unroll
@@ -758,10 +820,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = fmaf(vec[vlen + c0 + i], f[i], vec[2 * vlen + c0 + i]);
         }
-        // 32 channels -> 4 x 16-byte stores into the swizzled staging tile (rows outside the image: zeros)
-        const int colt = j * 32;                 // column within the BN tile
-        const int sub = colt >> p.cs_shift;      // store box this chunk belongs to
-        const uint32_t row_off = (uint32_t)row * pitch + (uint32_t)(colt & (p.CS - 1)) * 2u;
         uint8_t* dst = staging + (uint32_t)sub * sub_bytes;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -785,6 +843,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty_bar(acc));
       acc += G; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
+      if (t_sm) {                     // `t` tile consumed: the producer may refill it (tile i + kTcTBufs * G)
+        ptx::mbar_arrive(tt_empty(grp * kTcTBufs + tb));
+        if (++tb == kTcTBufs) { tb = 0; tph ^= 1u; }
+      }
       // staging tile complete -> TMA store
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(bar_id, 128);
@@ -2237,6 +2299,8 @@ struct TcConv {
   struct Cached {
     const void *x, *y; int x_ld, y_ld, B, H, W, dir;   // H, W: spatial dims of the GEMM's pixel grid
     CUtensorMap a, b, c; TcConvParams p; int grid; size_t smem; int G; int f32;
+    // second-epilogue-operand map (t_smem), built at launch for the tensor the launch names
+    CUtensorMap tm_t; const void* tm_t_ptr; int tm_t_ld; size_t smem_base_bytes; int stages_base;
   };
   std::vector<Cached> cache;
 };
@@ -2383,7 +2447,7 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   c.G = tc_pick_groups(p.BN, t.k * t.k * (K / p.KC) * (t.split ? 3 : 1), p.KC / 16);
   if (t.split && c.G > 2) c.G = 2;
   const size_t staging = t.split ? (size_t)c.G * 2 * 16384 + (size_t)c.G * 8 * p.BN * 4 : (size_t)c.G * p.nstaging * 128 * p.BN * 2;
-  const size_t fixed = 1024 /*alignment slack*/ + staging + (size_t)12 * N + 16 + 8 * (2 * kTcMaxStages + 18);
+  const size_t fixed = 1024 /*alignment slack*/ + staging + (size_t)12 * N + 16 + 8 * (2 * kTcMaxStages + 18 + 16);
   const size_t budget = 227 * 1024;
   p.a_lo = t.split ? x_ld / 2 : 0; p.b_lo = t.split ? K : 0;
   int stages = (int)((budget - fixed) / stage_bytes);
@@ -2478,7 +2542,7 @@ inline TcConv::Cached* tc_prepare_s2(TcConv& t, int dir, int gather, const bf16*
   c.G = tc_pick_groups(p.BN, (gather ? 4 : 1) * (K / p.KC) * (t.split ? 3 : 1), p.KC / 16);
   if (t.split && c.G > 2) c.G = 2;
   const size_t staging = t.split ? (size_t)c.G * 2 * 16384 + (size_t)c.G * 8 * p.BN * 4 : (size_t)c.G * p.nstaging * 128 * p.BN * 2;
-  const size_t fixed = 1024 + staging + (size_t)12 * (gather ? N : Cst) + 16 + 8 * (2 * kTcMaxStages + 18);
+  const size_t fixed = 1024 + staging + (size_t)12 * (gather ? N : Cst) + 16 + 8 * (2 * kTcMaxStages + 18 + 16);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   p.stages = stages;
@@ -2711,15 +2775,41 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
     }
   }
   const bool pdl = fu_pdl_enabled();
+  // second epilogue operand through shared memory (bf16 storage, thin tiles): two `t` tiles per epilogue group are
+  // carved from the operand stages; the map is the output's own (accumulate) or one of the same geometry over `t`
+  if (c->stages_base == 0) { c->stages_base = c->p.stages; c->smem_base_bytes = c->smem; }
+  c->p.t_smem = 0; c->p.stages = c->stages_base; c->smem = c->smem_base_bytes;
+  if (c->p.t && !c->f32 && c->p.BN <= 64 && tc_env_int("FU_TC_T_SMEM", 1)) {
+    const size_t stage_bytes = (size_t)(128 + c->p.BN) * c->p.KC * 2;
+    const size_t tbytes = (size_t)c->G * kTcTBufs * 128 * c->p.BN * 2;
+    const int st = (int)(((size_t)c->stages_base * stage_bytes - tbytes) / stage_bytes);
+    bool ok = (size_t)c->stages_base * stage_bytes > tbytes && st >= 2;
+    if (ok && c->p.t == reinterpret_cast<const bf16*>(c->y) && c->p.t_ld == c->y_ld) {
+      c->tm_t = c->c;                                   // accumulate: the old output is read through the store map
+    } else if (ok && !c->p.c5) {
+      if (c->tm_t_ptr != c->p.t || c->tm_t_ld != c->p.t_ld) {
+        long long dims[4] = {c->p.N, c->p.W, c->p.H, c->p.B};
+        long long str[4] = {1, c->p.t_ld, (long long)c->p.W * c->p.t_ld, (long long)c->p.H * c->p.W * c->p.t_ld};
+        int box[4] = {c->p.CS, c->p.tw, c->p.th, c->p.tn};
+        if (tc_make_map(&c->tm_t, c->p.t, 4, dims, str, box, c->p.CS * 2)) return -1;
+        c->tm_t_ptr = c->p.t; c->tm_t_ld = c->p.t_ld;
+      }
+    } else {
+      ok = false;
+    }
+    if (ok) { c->p.t_smem = 1; c->p.stages = st; c->smem = c->smem_base_bytes - (size_t)(c->stages_base - st) * stage_bytes + tbytes; }
+  }
+  if (!c->p.t_smem) c->tm_t = c->c;
+  const int G_run = (c->G == 4 && c->p.t && !c->p.t_smem) ? 2 : c->G;     // (G = 4 has no global-load path for `t`)
   {
     const int k_iters = c->p.ksz * c->p.ksz * (c->p.Cin / c->p.KC) * (c->f32 ? 3 : 1);
     c->p.dual = (c->p.stages >= 2 * k_iters && tc_env_int("FU_TC_DUAL", 1)) ? 1 : 0;
   }
-  if (c->f32 && c->G == 2) fu_launch(tc_conv_kernel<2, true>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else if (c->f32) fu_launch(tc_conv_kernel<1, true>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else if (c->G == 4) fu_launch(tc_conv_kernel<4, false>, dim3(c->grid), dim3(96 + 128 * 4), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else if (c->G == 2) fu_launch(tc_conv_kernel<2, false>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
-  else fu_launch(tc_conv_kernel<1, false>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->p);
+  if (c->f32 && c->G == 2) fu_launch(tc_conv_kernel<2, true>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
+  else if (c->f32) fu_launch(tc_conv_kernel<1, true>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
+  else if (G_run == 4) fu_launch(tc_conv_kernel<4, false>, dim3(c->grid), dim3(96 + 128 * 4), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
+  else if (G_run == 2) fu_launch(tc_conv_kernel<2, false>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
+  else fu_launch(tc_conv_kernel<1, false>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
   if (cnt) { cnt->kernel_launches++; cnt->tc_kernel_launches++; }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { tc_err() = cudaGetErrorString(e); return -1; }
