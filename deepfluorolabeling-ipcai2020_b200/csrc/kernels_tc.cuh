@@ -2782,8 +2782,10 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
   if (c->p.t && !c->f32 && c->p.BN <= 64 && tc_env_int("FU_TC_T_SMEM", 1)) {
     const size_t stage_bytes = (size_t)(128 + c->p.BN) * c->p.KC * 2;
     const size_t tbytes = (size_t)c->G * kTcTBufs * 128 * c->p.BN * 2;
-    const int st = (int)(((size_t)c->stages_base * stage_bytes - tbytes) / stage_bytes);
-    bool ok = (size_t)c->stages_base * stage_bytes > tbytes && st >= 2;
+    const size_t fixed = c->smem_base_bytes - (size_t)c->stages_base * stage_bytes;
+    int st = fixed + tbytes < (size_t)227 * 1024 ? (int)(((size_t)227 * 1024 - fixed - tbytes) / stage_bytes) : 0;
+    if (st > c->stages_base) st = c->stages_base;
+    bool ok = st >= 2;
     if (ok && c->p.t == reinterpret_cast<const bf16*>(c->y) && c->p.t_ld == c->y_ld) {
       c->tm_t = c->c;                                   // accumulate: the old output is read through the store map
     } else if (ok && !c->p.c5) {
@@ -2797,7 +2799,7 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
     } else {
       ok = false;
     }
-    if (ok) { c->p.t_smem = 1; c->p.stages = st; c->smem = c->smem_base_bytes - (size_t)(c->stages_base - st) * stage_bytes + tbytes; }
+    if (ok) { c->p.t_smem = 1; c->p.stages = st; c->smem = fixed + tbytes + (size_t)st * stage_bytes; }
   }
   if (!c->p.t_smem) c->tm_t = c->c;
   const int G_run = (c->G == 4 && c->p.t && !c->p.t_smem) ? 2 : c->G;     // (G = 4 has no global-load path for `t`)
