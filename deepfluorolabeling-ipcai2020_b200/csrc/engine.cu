@@ -1235,8 +1235,11 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
         const int cap_env = tc_env_int("FU_BN_COOP_OCC", 8);
         e->coop_blocks_per_sm = occ < cap_env ? occ : cap_env;
       }
-      // FU_BN_COOP: 0 never, 1 always, 2 (default) tensors of <= FU_BN_COOP_MB megabytes
-      static const int coop_mode = tc_env_int("FU_BN_COOP", 2), coop_mb = tc_env_int("FU_BN_COOP_MB", 12);
+      // FU_BN_COOP: 0 (default) never, 1 always, 2 tensors of <= FU_BN_COOP_MB megabytes.  Measured in the graph-replayed
+      // step (B=32 @192x192): 5.94 ms with two launches, 6.04 with mode 2, 6.12 with mode 1 -- the cooperative grid cannot
+      // pass its barrier until every block is resident, and the persistent weight-gradient kernels on the side stream hold
+      // SMs for 50-150 us at a time; per launch the fused kernel is no faster either (22 vs 12.6 + 10.7 us at 12x12).
+      static const int coop_mode = tc_env_int("FU_BN_COOP", 0), coop_mb = tc_env_int("FU_BN_COOP_MB", 12);
       const bool coop_want = coop_mode == 1 || (coop_mode == 2 && (double)P * b.C * e->esz <= coop_mb * 1048576.0);
       const long long coop_cap = (long long)e->coop_blocks_per_sm * e->num_sms / rg.y;
       if (coop_want && coop_cap >= 1) {
