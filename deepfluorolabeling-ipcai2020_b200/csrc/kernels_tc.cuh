@@ -1639,6 +1639,11 @@ __device__ __forceinline__ void tc_wgrad_epilogue(uint32_t tmem_base, uint32_t s
   int acc_row = row;                                        // accumulator row held by this thread's TMEM lane
   if (m64 == 1) acc_row = row < 64 ? row : -1;
   else if (m64 == 2) acc_row = (row & 31) < 16 ? (row >> 5) * 16 + (row & 15) : -1;
+  else if (m64 == 3) {
+    // filter rows stacked along M (tc_wgrad3_kernel, mstack): accumulator row = (2 - kh) * 32 + co, columns (kw, ci)
+    acc_row = row < 96 ? (row & 31) : -1;
+    tap0 = (2 - (row >> 5)) * 3;
+  }
   const int co = co0 + acc_row;
   const bool live = acc_row >= 0 && co < Cout && ncols > 0 && !skip;
   for (int t = 0; t < ntaps; ++t) {
@@ -1820,6 +1825,13 @@ struct TcWgrad3Params {
   int co_tiles, ci_tiles, splits, stages;
   unsigned b_stage_bytes;       // bytes of the B region of one stage
   int stack;                    // 1: the three kw taps of a filter row are ONE MMA with N = 3*N (see above)
+  int mstack;                   // 1 (Cout <= 32, with stack): the three FILTER ROWS are stacked along M as well.  A K tile is the
+                                //    row segment (h, w0..w0+tw) of X row h+1 against dY rows h, h+1, h+2 loaded as three
+                                //    32-channel (SWIZZLE_64B) blocks one leading-dimension offset apart: accumulator rows
+                                //    [32 s, 32 s + 32) hold sum dY[h+s] (x) X[h+1] = filter row kh = 2 - s, so ONE M = 128 MMA
+                                //    per 16 pixels replaces three M = 64 ones (which run at half rate with half their rows
+                                //    unused: the tensor pipe was 54 % busy doing 25 % useful work, profiles/r02_ncu_thin_wgrad3.txt).
+                                //    Row bands run over h = -2 .. H-1; TMA zero-fills the rows outside the image.
   int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1)
   int m64;                      // see TcWgradParams
   float* dw_acc;                // [9][Cout][Cin] fp32, zeroed by the caller
@@ -1857,14 +1869,15 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   const int ci_t = bid % p.ci_tiles;
   const int co_t = bid / p.ci_tiles;
   const int co0 = co_t * 128, ci0 = ci_t * p.N;
-  const int total_kt = p.B * p.H * p.segs;
+  const int Hk = p.mstack ? p.H + 2 : p.H;                    // row bands per image
+  const int total_kt = p.B * Hk * p.segs;
   const int per = (total_kt + p.splits - 1) / p.splits;
   const int kt_begin = split * per;
   const int kt_end = min(total_kt, kt_begin + per);
   const int npass = p.split ? 3 : 1;
   const int n_iters = max(kt_end - kt_begin, 0) * npass;
   const int nblk_a = (p.Cout - co0 > 64) ? 2 : 1;
-  const int kh0 = p.tpg == 9 ? 0 : grp;                     // first filter row held by this CTA
+  const int kh0 = p.mstack ? 2 : (p.tpg == 9 ? 0 : grp);    // first filter row held by this CTA (mstack: X row h + 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
@@ -1881,19 +1894,30 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 
   if (warp == 0) {
     int stage = 0; uint32_t phase = 0;
-    const uint32_t a_tx = (uint32_t)nblk_a * (uint32_t)p.tw * 128u;
+    const uint32_t a_tx = p.mstack ? 3u * (uint32_t)p.tw * 64u : (uint32_t)nblk_a * (uint32_t)p.tw * 128u;
     const uint32_t b_tx = (uint32_t)nblk_b * (uint32_t)((p.tw + 2) * nrows) * brow;
+    // (segment, row band, image) of the K tile, advanced incrementally: three integer divisions per stage were most of
+    //  what this warp executed, and with 2-4 MMAs per stage the producer's issue rate bounds the thin layers
+    int seg_i, hb_i, n_i;
+    { int kt = kt_begin; seg_i = kt % p.segs; kt /= p.segs; hb_i = kt % Hk; n_i = kt / Hk; }
+    int pass = 0;
     for (int it = 0; it < n_iters; ++it) {
-      int kt = kt_begin + it / npass;
-      const int pass = it % npass;
       const int yoff = co0 + (pass == 2 ? p.y_lo : 0), xoff = ci0 + (pass == 1 ? p.x_lo : 0);
-      const int w0 = (kt % p.segs) * p.tw; kt /= p.segs;
-      const int h = kt % p.H;
-      const int n = kt / p.H;
+      const int w0 = seg_i * p.tw;
+      const int h = hb_i - (p.mstack ? 2 : 0);
+      const int n = n_i;
+      if (++pass == npass) {
+        pass = 0;
+        if (++seg_i == p.segs) { seg_i = 0; if (++hb_i == Hk) { hb_i = 0; ++n_i; } }
+      }
       ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
       if (ptx::elect_one()) {
         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
         ptx::mbar_expect_tx(full_bar(stage), a_tx + b_tx);
+        if (p.mstack) {
+          for (int sft = 0; sft < 3; ++sft)       // dY rows h, h+1, h+2 -> M blocks 0, 1, 2 (block 3 is never read back)
+            ptx::tma_load_4d(a_dst + (uint32_t)sft * (uint32_t)p.tw * 64u, &tmY, full_bar(stage), yoff, w0, h + sft, n);
+        } else
         for (int blk = 0; blk < nblk_a; ++blk)
           ptx::tma_load_4d(a_dst + (uint32_t)blk * kABox, &tmY, full_bar(stage), yoff + blk * 64, w0, h, n);
         for (int blk = 0; blk < nblk_b; ++blk)
@@ -1922,6 +1946,18 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const int ksteps = p.tw / 16;
     const int tpg = p.tpg, Nn = p.N;
     const uint32_t step_a16 = (16u * 128u) >> 4, step_b16 = (16u * brow) >> 4;
+    // mstack: A = four 32-channel SWIZZLE_64B blocks (dY rows h, h+1, h+2, unused) tw * 64 bytes apart, M = 128
+    uint64_t dam;
+    {
+      uint64_t d = 0;
+      d |= (uint64_t)((((uint32_t)p.tw * 64u) >> 4) & 0x3FFF) << 16;               // LBO: next M block (next dY row)
+      d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;                                 // SBO: next 8 pixel rows
+      d |= (uint64_t)1 << 46;
+      d |= (uint64_t)4 << 61;                                                      // SWIZZLE_64B
+      dam = d;
+    }
+    const uint32_t idesc_ms = umma_idesc_bf16_mn((uint32_t)(3 * p.N), 128u);
+    const uint32_t step_am16 = (16u * 64u) >> 4;
     uint32_t tapoff16[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -1938,7 +1974,11 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const uint32_t accum = it != 0 ? 1u : 0u;
         // K step outermost: consecutive MMAs go to DIFFERENT accumulators, so a dependent accumulation is
         // never issued back to back
-        if (p.stack) {
+        if (p.mstack) {
+          const uint64_t adm = dam + (uint64_t)(a_addr >> 4);
+          for (int ks = 0; ks < ksteps; ++ks)
+            ptx::umma_bf16(tmem_base, adm + (uint64_t)(ks * step_am16), bd0s + (uint64_t)(ks * step_b16), idesc_ms, accum | (uint32_t)ks);
+        } else if (p.stack) {
           for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -1969,7 +2009,7 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
     tc_wgrad_epilogue(tmem_base, smem_base, (uint32_t)p.stages * stage_bytes, p.N, p.tpg, p.tpg == 9 ? 0 : grp * 3, 1,
-                      co0, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi, p.m64);
+                      co0, p.Cout, ci0, p.Cin, row, q, p.dw_acc, p.skip_epi, p.mstack ? 3 : p.m64);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -3032,15 +3072,21 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     n.x = x; n.dy = dy; n.x_ld = x_ld; n.dy_ld = dy_ld; n.B = B; n.H = H; n.W = W;
     TcWgrad3Params& p = n.p;
     p.B = B; p.H = H; p.W = W; p.Cin = t.Cin; p.Cout = t.Cout;
-    // K pixels per stage: the multiple of 16 in {64,48,32} that wastes the fewest pixels per row
+    // K pixels per stage: the multiple of 16 in {64,48,32} with the lowest cost per image row = (padded pixels + a fixed
+    // per-stage cost worth ~24 pixels: barrier round trips and 2-5 TMA loads per stage.  W = 736 used to pick 32 (no
+    // padding, 23 stages of 2 K steps) and ran 1.7x slower per pixel than W = 192 with 64)
     int best_tw = 64; long long best_cost = -1;
     for (int tw = 64; tw >= 32; tw -= 16) {
-      const long long cost = (long long)((W + tw - 1) / tw) * tw;
+      const long long cost = (long long)((W + tw - 1) / tw) * (tw + tc_env_int("FU_TC_W3_STAGE_COST", 24));
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
     }
     p.tw = best_tw; p.segs = (W + p.tw - 1) / p.tw;
     if (t.Cin <= 32) { p.N = 32; p.cb = 32; p.tpg = 9; p.groups = 1; }
     else { p.N = t.Cin > 64 ? 128 : 64; p.cb = 64; p.tpg = 3; p.groups = 3; }
+    // filter rows stacked along M (see TcWgrad3Params::mstack): Cout <= 32, one in-channel block, bf16 storage
+    p.mstack = (t.Cout <= 32 && p.N == p.cb && t.Cin <= p.N && !t.split && tc_env_int("FU_TC_W3_STACK", 1) &&
+                tc_env_int("FU_TC_W3_MSTACK", 1)) ? 1 : 0;
+    if (p.mstack) { p.tpg = 3; p.groups = 1; }
     const int nrows = p.tpg == 9 ? 3 : 1;
     const size_t b_box = ((size_t)(p.tw + 2) * nrows * p.cb * 2 + 1023) / 1024 * 1024;
     p.b_stage_bytes = (unsigned)(b_box * (p.N / p.cb));
@@ -3056,7 +3102,7 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long units = (long long)p.co_tiles * p.ci_tiles * p.groups;
-    const long long total_kt = (long long)B * H * p.segs;
+    const long long total_kt = (long long)B * (p.mstack ? H + 2 : H) * p.segs;
     const long long max_splits = (total_kt + 7) / 8;
     long long splits = tc_pick_splits(units, max_splits, sms, tc_env_int("FU_TC_WGRAD3_WAVES", 1));
     const long long per = (total_kt + splits - 1) / splits;
@@ -3070,8 +3116,8 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     {
       long long dims[4] = {t.Cout + p.y_lo, W, H, B};
       long long str[4] = {1, dy_ld, (long long)W * dy_ld, (long long)H * W * dy_ld};
-      int box[4] = {64, p.tw, 1, 1};
-      if (tc_make_map(&n.y, dy, 4, dims, str, box, 128)) return -1;
+      int box[4] = {p.mstack ? 32 : 64, p.tw, 1, 1};
+      if (tc_make_map(&n.y, dy, 4, dims, str, box, p.mstack ? 64 : 128)) return -1;
     }
     {
       long long dims[4] = {t.Cin + p.x_lo, W, H, B};

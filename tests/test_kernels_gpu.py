@@ -203,6 +203,8 @@ HALO_SHAPES = [  # B, Cin, Cout, H, W  -- 3x3 convs wide enough for the halo ker
     (5, 64, 64, 24, 24),      # odd number of pixel tiles (last pair half empty)
     (2, 32, 64, 20, 96),      # weight gradient: 48-pixel K tiles, nine taps per CTA (Cin = 32)
     (1, 128, 64, 12, 192),    # weight gradient: 64-pixel K tiles, 128-channel B tiles
+    (2, 32, 32, 3, 64),       # weight gradient with the filter rows stacked along M (Cout <= 32): fewer image rows than shifts + 1
+    (1, 64, 32, 7, 130),      # same, 192 accumulator columns, three ragged row segments
 ]
 
 
