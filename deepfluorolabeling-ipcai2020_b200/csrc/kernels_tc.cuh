@@ -1679,6 +1679,9 @@ struct TcWgradParams {
   int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1): drop the accumulators instead of adding them
   int m64;                      // 0: M = 128 MMAs; 1/2: M = 64 (out-channels <= 64), value = TMEM row layout (see epilogue)
   int b5;                       // B operand gathered with stride 2 (5-D map), taps = 2x2, pixel grid (W, H), B = 1
+  int kpix;                     // pixels (K) per pipeline stage: 64, or 128 where three such stages fit shared memory (the
+                                // kernel spends a roughly constant ~800-1000 cycles per stage on barrier round trips and TMA
+                                // issue, which bounds the 1x1 / 2x2 layers: 4 MMAs per 64-pixel stage)
   // split-bf16 x3 parity mode: every pixel tile is visited three times, (dY_hi, X_hi), (dY_hi, X_lo), (dY_lo, X_hi);
   // y_lo / x_lo are the channel offsets of the lo halves in the two (twin) maps
   int split, y_lo, x_lo;
@@ -1692,7 +1695,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   uint8_t* smem = smem_raw + (smem_base - raw);
   // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role-local scalars can live in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  constexpr uint32_t kBox = 64u * 128u;                 // 64 pixels x 64 channels bf16
+  const uint32_t kBox = (uint32_t)p.kpix * 128u;        // kpix pixels x 64 channels bf16
   const int nblk_b = p.N / 64;
   const uint32_t a_bytes = 2u * kBox;
   const uint32_t b_bytes = (uint32_t)(p.taps_per_cta * nblk_b) * kBox;
@@ -1738,13 +1741,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   if (warp == 0) {
     // whole warp loops, one elected lane issues the TMA loads
     int stage = 0; uint32_t phase = 0;
+    // pixel-tile coordinates advanced incrementally (no integer divisions in the per-stage loop)
+    int wi, hi, ni;
+    { int pt = pt_begin; wi = pt % p.tiles_w; pt /= p.tiles_w; hi = pt % p.tiles_h; ni = pt / p.tiles_h; }
+    int pass = 0;
     for (int it = 0; it < n_iters; ++it) {
-      int pt = pt_begin + it / npass;
-      const int pass = it % npass;
       const int yoff = co0 + (pass == 2 ? p.y_lo : 0), xoff = ci0 + (pass == 1 ? p.x_lo : 0);
-      const int w0 = (pt % p.tiles_w) * p.tw; pt /= p.tiles_w;
-      const int h0 = (pt % p.tiles_h) * p.th; pt /= p.tiles_h;
-      const int n0 = pt * p.tn;
+      const int w0 = wi * p.tw, h0 = hi * p.th, n0 = ni * p.tn;
+      if (++pass == npass) {
+        pass = 0;
+        if (++wi == p.tiles_w) { wi = 0; if (++hi == p.tiles_h) { hi = 0; ++ni; } }
+      }
       ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
       if (ptx::elect_one()) {
         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
@@ -1772,9 +1779,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       if (ptx::elect_one()) {
         const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
         const uint64_t ad0 = umma_desc_at(dbase, a_addr);
-        // 64 pixels = 4 x K16; 16 pixel rows = 2048 B = +128 in the address field.  K step outermost so that
-        // consecutive MMAs accumulate into different taps' accumulators.
-        for (int ks = 0; ks < 4; ++ks) {
+        // kpix pixels = kpix / 16 K steps; 16 pixel rows = 2048 B = +128 in the address field.  K step outermost so
+        // that consecutive MMAs accumulate into different taps' accumulators.
+        const int ksteps = p.kpix >> 4;
+        for (int ks = 0; ks < ksteps; ++ks) {
           for (int t = 0; t < p.taps_per_cta; ++t) {
             const uint64_t bd0 = umma_desc_at(dbase, a_addr + a_bytes + (uint32_t)(t * nblk_b) * kBox);
             ptx::umma_bf16(tmem_base + (uint32_t)(t * p.N), ad0 + (uint64_t)(128 * ks), bd0 + (uint64_t)(128 * ks), idesc,
@@ -1846,8 +1854,9 @@ tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint8_t* smem = smem_raw + (smem_base - raw);
   // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role-local scalars can live in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  constexpr uint32_t kABox = 64u * 128u;                   // room for 64 pixels x 64 channels
-  const uint32_t a_bytes = 2u * kABox;
+  const uint32_t kABox = (uint32_t)p.tw * 128u;            // one 64-channel box of tw pixels (a multiple of 1024: tw % 16 == 0)
+  // A region of a stage: two 64-channel boxes, or (mstack) four 32-channel blocks; tw <= 128 pixels
+  const uint32_t a_bytes = p.mstack ? 4u * (uint32_t)p.tw * 64u : 2u * kABox;
   const uint32_t brow = (uint32_t)p.cb * 2u;                // bytes per pixel row of a B box
   const int nrows = p.tpg == 9 ? 3 : 1;                     // halo rows held per stage
   const int nblk_b = p.N / p.cb;
@@ -2966,12 +2975,12 @@ inline bool tc_wgrad_eligible(const TcConv& t, const void* x, int x_ld, const vo
   return t.enabled && tc_ptr_ok(x, x_ld) && tc_ptr_ok(dy, dy_ld) && getenv("FU_TC_NO_WGRAD") == nullptr;
 }
 
-inline void tc_pick_tile64(int B, int H, int W, int& tw, int& th, int& tn) {
+inline void tc_pick_tile64(int B, int H, int W, int& tw, int& th, int& tn, int npx = 64) {
   long long best = -1;
-  tw = 8; th = 8; tn = 1;
-  for (int a = 1; a <= 64; a <<= 1)
-    for (int b = 1; a * b <= 64; b <<= 1) {
-      const int c = 64 / (a * b);
+  tw = 8; th = 8; tn = npx / 64;
+  for (int a = 1; a <= npx; a <<= 1)
+    for (int b = 1; a * b <= npx; b <<= 1) {
+      const int c = npx / (a * b);
       const long long tiles = (long long)((W + a - 1) / a) * ((H + b - 1) / b) * ((B + c - 1) / c);
       const long long key = tiles * 1024 - a;
       if (best < 0 || key < best) { best = key; tw = a; th = b; tn = c; }
@@ -2997,12 +3006,18 @@ inline int tc_wgrad_common(TcConv& t, const void* a, int a_ld, int M, const void
     p.Cin = Nn; p.Cout = M; p.ksz = ksz; p.pad = ksz == 3 ? 1 : 0; p.b5 = s2;
     p.taps_per_cta = ksz; p.groups = ksz;
     p.N = Nn > 64 ? 128 : 64;
-    if (s2) { p.B = 1; p.H = (int)Rg; p.W = W; tc_pick_tile64(1, (int)Rg, W, p.tw, p.th, p.tn); p.tn = 1; }
-    else { p.B = B; p.H = H; p.W = W; tc_pick_tile64(B, H, W, p.tw, p.th, p.tn); }
-    if (s2 && p.tw * p.th != 64) { tc_err() = "strided wgrad: no 64-pixel tile"; return -1; }
+    // 128-pixel stages when at least three of them fit and every CTA still gets a few
+    p.kpix = ((2 + p.taps_per_cta * (p.N / 64)) * 16384 * 3 + 2048 <= 227 * 1024 && (long long)B * H * W >= 148ll * 4 * 128 &&
+              tc_env_int("FU_TC_WGRAD_KPIX", 128) == 128) ? 128 : 64;
+    if (s2) {
+      p.B = 1; p.H = (int)Rg; p.W = W;
+      tc_pick_tile64(1, (int)Rg, W, p.tw, p.th, p.tn, p.kpix); p.tn = 1;
+      if (p.tw * p.th != p.kpix) { p.kpix = 64; tc_pick_tile64(1, (int)Rg, W, p.tw, p.th, p.tn); p.tn = 1; }
+    } else { p.B = B; p.H = H; p.W = W; tc_pick_tile64(B, H, W, p.tw, p.th, p.tn, p.kpix); }
+    if (s2 && p.tw * p.th != 64 && p.tw * p.th != p.kpix) { tc_err() = "strided wgrad: no 64-pixel tile"; return -1; }
     p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_b = (p.B + p.tn - 1) / p.tn;
     p.co_tiles = (M + 127) / 128; p.ci_tiles = (Nn + p.N - 1) / p.N;
-    const size_t stage_bytes = (size_t)(2 + p.taps_per_cta * (p.N / 64)) * 8192;
+    const size_t stage_bytes = (size_t)(2 + p.taps_per_cta * (p.N / 64)) * 128 * p.kpix;
     const size_t fixed = 1024 + 8 * (2 * kTcMaxStages + 4);
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (stages > kTcMaxStages) stages = kTcMaxStages;
@@ -3075,24 +3090,26 @@ inline int tc_wgrad3(TcConv& t, const void* x, int x_ld, const void* dy, int dy_
     // K pixels per stage: the multiple of 16 in {64,48,32} with the lowest cost per image row = (padded pixels + a fixed
     // per-stage cost worth ~24 pixels: barrier round trips and 2-5 TMA loads per stage.  W = 736 used to pick 32 (no
     // padding, 23 stages of 2 K steps) and ran 1.7x slower per pixel than W = 192 with 64)
-    int best_tw = 64; long long best_cost = -1;
-    for (int tw = 64; tw >= 32; tw -= 16) {
-      const long long cost = (long long)((W + tw - 1) / tw) * (tw + tc_env_int("FU_TC_W3_STAGE_COST", 24));
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
-    }
-    p.tw = best_tw; p.segs = (W + p.tw - 1) / p.tw;
     if (t.Cin <= 32) { p.N = 32; p.cb = 32; p.tpg = 9; p.groups = 1; }
     else { p.N = t.Cin > 64 ? 128 : 64; p.cb = 64; p.tpg = 3; p.groups = 3; }
     // filter rows stacked along M (see TcWgrad3Params::mstack): Cout <= 32, one in-channel block, bf16 storage
     p.mstack = (t.Cout <= 32 && p.N == p.cb && t.Cin <= p.N && !t.split && tc_env_int("FU_TC_W3_STACK", 1) &&
                 tc_env_int("FU_TC_W3_MSTACK", 1)) ? 1 : 0;
     if (p.mstack) { p.tpg = 3; p.groups = 1; }
+    // (a stage holds up to 128 pixels: these kernels run at a roughly constant ~800 cycles per stage -- barrier round
+    //  trips, TMA issue -- whatever the stage holds, so on the wide levels fewer, larger stages win)
+    int best_tw = 64; long long best_cost = -1;
+    for (int tw = tc_env_int("FU_TC_W3_MAXTW", 128); tw >= 32; tw -= 16) {
+      const long long cost = (long long)((W + tw - 1) / tw) * (tw + tc_env_int("FU_TC_W3_STAGE_COST", 24));
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
+    }
+    p.tw = best_tw; p.segs = (W + p.tw - 1) / p.tw;
     const int nrows = p.tpg == 9 ? 3 : 1;
     const size_t b_box = ((size_t)(p.tw + 2) * nrows * p.cb * 2 + 1023) / 1024 * 1024;
     p.b_stage_bytes = (unsigned)(b_box * (p.N / p.cb));
     p.stack = (p.N == p.cb && tc_env_int("FU_TC_W3_STACK", 1)) ? 1 : 0;
     p.co_tiles = (t.Cout + 127) / 128; p.ci_tiles = (t.Cin + p.N - 1) / p.N;
-    const size_t stage_bytes = 2 * 8192 + p.b_stage_bytes;
+    const size_t stage_bytes = (p.mstack ? (size_t)4 * p.tw * 64 : (size_t)2 * p.tw * 128) + p.b_stage_bytes;
     const size_t fixed = 1024 + 8 * (2 * kTcMaxStages + 4);
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (stages > kTcMaxStages) stages = kTcMaxStages;
