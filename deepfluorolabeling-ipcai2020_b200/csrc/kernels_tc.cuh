@@ -336,6 +336,12 @@ struct TcConvParams {
                                 // that an issuer one tile ahead is never a whole ring round ahead; see TcConv3Params)
   FastDiv fd_ntiles, fd_tw, fd_th;     // tile decode: divisions by n_tiles, tiles_w, tiles_h
   int cs_shift;                 // log2(CS)
+  int alias_staging;            // 1 (every CTA has exactly one tile): the epilogue's staging tiles overlay the operand stages,
+                                // which are dead once the tile's last MMA has completed, so the whole shared memory holds
+                                // operands in flight.  The deep layers (12x12, 24x24: 144 tiles) are bound by the bytes in
+                                // flight per SM: 32-48 KB per K iteration against 256-512 tensor cycles needs more than the
+                                // 3-4 stages left beside 64 KB of staging (ncu: the MMA warp polls its full barrier ~2x per
+                                // iteration, tensor pipe 36 % busy, profiles/r02_ncu_deep_conv_512.txt)
   int t_smem;                   // 1: the second epilogue operand `t` is brought into shared memory by the TMA producer
                                 // (map tmT, two tiles per epilogue group, laid out like the staging tile) instead of being
                                 // loaded from global memory by the epilogue threads: with 1-8 MMAs per tile the accumulator
@@ -371,12 +377,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t row_bytes = (uint32_t)p.KC * 2u;
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t staging_off = (uint32_t)p.stages * stage_bytes;
+  const uint32_t staging_off = p.alias_staging ? 0u : (uint32_t)p.stages * stage_bytes;
   // F32: one 128-row x 32-column fp32 chunk (16 KB) per staging tile, always double buffered
   const uint32_t staging_bytes = F32 ? 16384u : 128u * (uint32_t)p.BN * 2u;
   const int vlen = p.c5 ? p.Cst : p.N;                              // channels of the bias / bn vectors
   const int nstg = F32 ? 2 : p.nstaging;                             // 1 or 2 staging tiles (double buffered stores)
-  const uint32_t tbuf_off = staging_off + (uint32_t)(G * nstg) * staging_bytes;  // `t` tiles [G][kTcTBufs] (t_smem)
+  const uint32_t tbuf_off = (uint32_t)p.stages * stage_bytes +
+                            (p.alias_staging ? 0u : (uint32_t)(G * nstg) * staging_bytes);  // `t` tiles [G][kTcTBufs] (t_smem)
   const uint32_t vec_off = tbuf_off + (p.t_smem ? (uint32_t)(G * kTcTBufs) * staging_bytes : 0u);   // bias | bn_a | bn_b, [3][vlen] floats
   const uint32_t park_off = vec_off + 3u * (uint32_t)vlen * 4u;     // (F32) statistics partials [G][4][2][BN] floats
   const uint32_t bar_off = (park_off + (F32 ? (uint32_t)(G * 8 * p.BN) * 4u : 0u) + 7u) & ~7u;
@@ -503,8 +510,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();
         }
+        // (tap, channel chunk) advanced incrementally: this loop bounds the deep layers -- the MMA warp polls its full
+        //  barrier ~2x per iteration (ncu, 512->512 @12x12) -- and two integer divisions were half of its instructions
+        int tap = 0, vc = 0, kh = 0, kw = 0;
         for (int kit = 0; kit < k_iters; ++kit) {
-          const int tap = kit / vchunks, vc = kit - tap * vchunks;
           int c0 = vc * p.KC, cb0 = c0;
           if (F32) {                       // pass 0: (hi, W_hi), pass 1: (hi, W_lo), pass 2: (lo, W_hi)
             const int pass = vc / cchunks;
@@ -512,14 +521,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             cb0 = c0 + (pass == 1 ? p.b_lo : 0);
             c0 += pass == 2 ? p.a_lo : 0;
           }
-          const int kh = tap / p.ksz, kw = tap - kh * p.ksz;
+          const int tap_c = tap, kh_c = kh, kw_c = kw;
+          if (++vc == vchunks) { vc = 0; ++tap; if (++kw == p.ksz) { kw = 0; ++kh; } }
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
             ptx::mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
-            if (p.a5) ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kw, w0, kh, h0);
-            else ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw - p.pad, h0 + kh - p.pad, n0);
-            ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), cb0, tap, nb);
+            if (p.a5) ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kw_c, w0, kh_c, h0);
+            else ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw_c - p.pad, h0 + kh_c - p.pad, n0);
+            ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), cb0, tap_c, nb);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -2499,13 +2509,20 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   const size_t fixed = 1024 /*alignment slack*/ + staging + (size_t)12 * N + 16 + 8 * (2 * kTcMaxStages + 18 + 16);
   const size_t budget = 227 * 1024;
   p.a_lo = t.split ? x_ld / 2 : 0; p.b_lo = t.split ? K : 0;
+  const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+  c.grid = (int)(total_tiles < sms ? total_tiles : sms);
   int stages = (int)((budget - fixed) / stage_bytes);
   if (stages > kTcMaxStages) stages = kTcMaxStages;
   if (stages < 2) { tc_err() = "tile does not fit shared memory"; return nullptr; }
+  size_t fixed_run = fixed;
+  if (total_tiles <= sms && !t.split && stages < kTcMaxStages && tc_env_int("FU_TC_ALIAS_STAGING", 1)) {
+    // one tile per CTA: the staging tiles overlay the (by then idle) operand stages
+    int st2 = (int)((budget - (fixed - staging)) / stage_bytes);
+    if (st2 > kTcMaxStages) st2 = kTcMaxStages;
+    if (st2 > stages && (size_t)st2 * stage_bytes >= staging) { p.alias_staging = 1; stages = st2; fixed_run = fixed - staging; }
+  }
   p.stages = stages;
-  c.smem = fixed + (size_t)stages * stage_bytes;
-  const long long total_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
-  c.grid = (int)(total_tiles < sms ? total_tiles : sms);
+  c.smem = fixed_run + (size_t)stages * stage_bytes;
   // A: activation (K channels, W, H, B); split mode: the twin's [hi | lo] halves are one channel range
   {
     long long dims[4] = {K + p.a_lo, W, H, B};
