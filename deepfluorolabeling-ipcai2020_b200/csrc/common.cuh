@@ -96,6 +96,21 @@ inline cudaError_t fu_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size
   cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+// same, as thread-block clusters of `cluster` CTAs along x (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t fu_launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                     unsigned cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 2u : 1u;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // process-wide switch (FU_PDL=0 turns programmatic dependent launch off)
 inline bool fu_pdl_enabled() {
   static int v = -1;

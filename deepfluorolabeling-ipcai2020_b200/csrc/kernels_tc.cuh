@@ -106,6 +106,28 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// multicast variants: the box lands at the same shared-memory offset (and signals the mbarrier at the same offset) in
+// every CTA of the cluster whose bit is set in `mask`
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -172,6 +194,11 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// the same arrival on the mbarrier at this offset in every CTA of the cluster selected by `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -342,6 +369,19 @@ struct TcConvParams {
                                 // flight per SM: 32-48 KB per K iteration against 256-512 tensor cycles needs more than the
                                 // 3-4 stages left beside 64 KB of staging (ncu: the MMA warp polls its full barrier ~2x per
                                 // iteration, tensor pipe 36 % busy, profiles/r02_ncu_deep_conv_512.txt)
+  int kpair;                    // 1: a pipeline stage holds TWO 64-channel K chunks of both operands, each pair fetched by one
+                                // TMA instruction (A through a 5-D view whose slowest box dimension is the chunk index, so
+                                // the two [pixels][64] tiles land back to back; B likewise in 4-D): half as many barrier
+                                // round trips, TMA issues and elected sections per FLOP.  The deep layers run at the
+                                // producer / issuer warps' loop rate (~600-700 cycles per 4-MMA iteration against 256
+                                // tensor cycles; ncu: the producer never waits for a free stage), not at a memory limit
+  int mc;                       // 0: no cluster.  1 / 2: launched as clusters of two CTAs (one tile each) that share their A
+                                // tile (1: same pixels, neighbouring N tiles) or their B tile (2: same N tile, neighbouring
+                                // pixel tiles).  The shared operand of K iteration k is loaded by CTA k % 2 and MULTICAST into
+                                // both, so each CTA pulls 25-33 % fewer bytes through the L2: the deep layers move
+                                // 144 CTAs x 32-48 KB per iteration = 10-12 TB/s, which is the L2's limit, not the tensor
+                                // pipe's (36 % busy).  Stage release is cluster-wide: every MMA warp commits to the empty
+                                // barrier of BOTH CTAs (count 2).
   int t_smem;                   // 1: the second epilogue operand `t` is brought into shared memory by the TMA producer
                                 // (map tmT, two tiles per epilogue group, laid out like the staging tile) instead of being
                                 // loaded from global memory by the epilogue threads: with 1-8 MMAs per tile the accumulator
@@ -376,7 +416,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int prod_warp = 4 * G, mma_warp = 4 * G + 1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2u;
   const uint32_t a_bytes = 128u * row_bytes, b_bytes = (uint32_t)p.BN * row_bytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t kp = p.kpair ? 2u : 1u;                   // K chunks per stage: [A0 A1 | B0 B1]
+  const uint32_t stage_bytes = kp * (a_bytes + b_bytes);
   const uint32_t staging_off = p.alias_staging ? 0u : (uint32_t)p.stages * stage_bytes;
   // F32: one 128-row x 32-column fp32 chunk (16 KB) per staging tile, always double buffered
   const uint32_t staging_bytes = F32 ? 16384u : 128u * (uint32_t)p.BN * 2u;
@@ -403,7 +444,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   while (tmem_cols < (uint32_t)(NACC * p.BN)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), p.mc ? 2u : 1u); }
     for (int a = 0; a < NACC; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 128); }
     for (int i = 0; i < G * kTcTBufs; ++i) { ptx::mbar_init(tt_full(i), 1); ptx::mbar_init(tt_empty(i), 128); }
     if (p.t_smem) ptx::prefetch_tmap(&tmT);
@@ -462,14 +503,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.mc) ptx::cluster_sync();          // the peer's barriers are initialised before anything is multicast into them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *slot_ptr;
+  const uint32_t crank = p.mc ? ptx::cluster_ctarank() : 0u;
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
   const int total_tiles = tiles_m * p.n_tiles;
   const int cchunks = p.Cin / p.KC;
   const int vchunks = F32 ? 3 * cchunks : cchunks;          // split mode: three passes per real channel chunk
-  const int k_iters = p.ksz * p.ksz * vchunks;
+  const int k_iters = p.ksz * p.ksz * vchunks / (int)kp;    // pipeline stages per tile
   const uint32_t a_tx = (uint32_t)(p.tw * p.th * p.tn) * row_bytes;
 
   auto decode = [&](int tile, int& w0, int& h0, int& n0, int& nb) {
@@ -521,15 +564,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             cb0 = c0 + (pass == 1 ? p.b_lo : 0);
             c0 += pass == 2 ? p.a_lo : 0;
           }
-          const int tap_c = tap, kh_c = kh, kw_c = kw;
-          if (++vc == vchunks) { vc = 0; ++tap; if (++kw == p.ksz) { kw = 0; ++kh; } }
+          const int tap_c = tap, kh_c = kh, kw_c = kw, vc_c = vc;
+          vc += (int)kp;
+          if (vc == vchunks) { vc = 0; ++tap; if (++kw == p.ksz) { kw = 0; ++kh; } }
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
-            ptx::mbar_expect_tx(full_bar(stage), a_tx + b_bytes);
+            ptx::mbar_expect_tx(full_bar(stage), kp * (a_tx + b_bytes));
+            const bool mine = ((uint32_t)kit & 1u) == crank;       // (cluster) this CTA loads the shared operand of this iteration
+            if (p.kpair) {
+              // chunks vc_c, vc_c + 1 of both operands: A tiles back to back (dense: a_tx bytes each), B tiles behind them
+              ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), 0, w0 + kw_c - p.pad, h0 + kh_c - p.pad, n0, vc_c);
+              ptx::tma_load_4d(a_dst + 2u * a_bytes, &tmB, full_bar(stage), 0, tap_c, nb, vc_c);
+            } else
             if (p.a5) ptx::tma_load_5d(a_dst, &tmA, full_bar(stage), c0, kw_c, w0, kh_c, h0);
+            else if (p.mc == 1) { if (mine) ptx::tma_load_4d_mc(a_dst, &tmA, full_bar(stage), c0, w0 + kw_c - p.pad, h0 + kh_c - p.pad, n0, (uint16_t)3); }
             else ptx::tma_load_4d(a_dst, &tmA, full_bar(stage), c0, w0 + kw_c - p.pad, h0 + kh_c - p.pad, n0);
-            ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), cb0, tap_c, nb);
+            if (p.kpair) { }
+            else if (p.mc == 2) { if (mine) ptx::tma_load_3d_mc(a_dst + a_bytes, &tmB, full_bar(stage), cb0, tap_c, nb, (uint16_t)3); }
+            else ptx::tma_load_3d(a_dst + a_bytes, &tmB, full_bar(stage), cb0, tap_c, nb);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -569,10 +622,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // +32 B per K step = +2 in the address field of the descriptors' low words (see umma_bf16_lo)
             const uint32_t a_lo = dlo + ((smem_base + (uint32_t)stage * stage_bytes) >> 4);
             const uint32_t first = kit != 0 ? 1u : 0u;
+            if (p.kpair) {          // (KC = 64) two chunks: A tiles a_tx bytes apart, B tiles behind both A slots
+              tc_mma_tap<4>(d_tmem, 0u, false, a_lo, 0u, a_lo + 2u * a16, dhi, idesc, first);
+              tc_mma_tap<4>(d_tmem, 0u, false, a_lo + (a_tx >> 4), 0u, a_lo + 2u * a16 + (b_bytes >> 4), dhi, idesc, 1u);
+            } else
             if (ksteps == 4) tc_mma_tap<4>(d_tmem, 0u, false, a_lo, 0u, a_lo + a16, dhi, idesc, first);
             else if (ksteps == 2) tc_mma_tap<2>(d_tmem, 0u, false, a_lo, 0u, a_lo + a16, dhi, idesc, first);
             else tc_mma_tap<1>(d_tmem, 0u, false, a_lo, 0u, a_lo + a16, dhi, idesc, first);
-            ptx::umma_commit(empty_bar(stage));          // frees the smem stage when these MMAs retire
+            if (p.mc) ptx::umma_commit_mc(empty_bar(stage), (uint16_t)3);   // (cluster) the stage is refilled for both CTAs at once
+            else ptx::umma_commit(empty_bar(stage));     // frees the smem stage when these MMAs retire
             if (kit == k_iters - 1) ptx::umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
           }
           __syncwarp();
@@ -913,6 +971,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.mc) ptx::cluster_sync();          // no CTA leaves while its peer may still signal its barriers
   if (warp == mma_warp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, tmem_cols);
@@ -2501,8 +2560,17 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   p.n_tiles = N / p.BN;
   p.fd_ntiles = FastDiv(p.n_tiles); p.fd_tw = FastDiv(p.tiles_w); p.fd_th = FastDiv(p.tiles_h);
   p.cs_shift = p.CS == 64 ? 6 : 5;
-  const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2;
+  // two 64-channel K chunks per pipeline stage on the deep layers (see TcConvParams::kpair)
+  p.kpair = (!t.split && p.KC == 64 && (K / 64) % 2 == 0 && ((p.tw * p.th * p.tn) % 8) == 0 && t.k * t.k * (K / 64) >= 16 &&
+             p.BN >= 128 && tc_env_int("FU_TC_KPAIR", 1)) ? 1 : 0;
   p.nstaging = p.BN <= 64 ? 2 : 1;
+  if (p.kpair) {      // only where three double stages fit (beside, or overlaid by, the staging tiles): 128-column tiles
+    const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / p.BN);
+    const size_t stg = (size_t)tc_pick_groups(p.BN, t.k * t.k * (K / p.KC), p.KC / 16) * p.nstaging * 128 * p.BN * 2;
+    const size_t avail = (size_t)227 * 1024 - 4096 - (size_t)12 * N - (tiles <= sms ? 0 : stg);
+    if (avail < (size_t)3 * 2 * (128 + p.BN) * p.KC * 2) p.kpair = 0;
+  }
+  const size_t stage_bytes = (size_t)(128 + p.BN) * p.KC * 2 * (p.kpair ? 2 : 1);
   c.G = tc_pick_groups(p.BN, t.k * t.k * (K / p.KC) * (t.split ? 3 : 1), p.KC / 16);
   if (t.split && c.G > 2) c.G = 2;
   const size_t staging = t.split ? (size_t)c.G * 2 * 16384 + (size_t)c.G * 8 * p.BN * 4 : (size_t)c.G * p.nstaging * 128 * p.BN * 2;
@@ -2523,6 +2591,19 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   }
   p.stages = stages;
   c.smem = fixed_run + (size_t)stages * stage_bytes;
+  if (p.kpair) {
+    // the channel dimension split as (64, K/64) with the chunk index as the SLOWEST box dimension: a box of two chunks
+    // arrives as two back-to-back [pixels][64] (resp. [BN][64]) tiles
+    const int taps = t.k * t.k;
+    long long da[5] = {64, W, H, B, K / 64};
+    long long sa[5] = {1, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, 64};
+    int ba[5] = {64, p.tw, p.th, p.tn, 2};
+    if (tc_make_map(&c.a, x, 5, da, sa, ba, 128)) return nullptr;
+    long long db[4] = {64, taps, N, K / 64};
+    long long sb[4] = {1, K, (long long)taps * K, 64};
+    int bb[4] = {64, 1, p.BN, 2};
+    if (tc_make_map(&c.b, dir == 0 ? t.w_fwd : t.w_dgrad, 4, db, sb, bb, 128)) return nullptr;
+  } else {
   // A: activation (K channels, W, H, B); split mode: the twin's [hi | lo] halves are one channel range
   {
     long long dims[4] = {K + p.a_lo, W, H, B};
@@ -2538,6 +2619,7 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
     long long str[3] = {1, Kw, (long long)taps * Kw};
     int box[3] = {p.KC, 1, p.BN};
     if (tc_make_map(&c.b, dir == 0 ? t.w_fwd : t.w_dgrad, 3, dims, str, box, p.KC * 2)) return nullptr;
+  }
   }
   // C: output (N channels, W, H, B), bf16 or (split) fp32
   {
@@ -2873,6 +2955,22 @@ inline int tc_launch(TcConv::Cached* c, cudaStream_t stream, fu_counters* cnt) {
     const int k_iters = c->p.ksz * c->p.ksz * (c->p.Cin / c->p.KC) * (c->f32 ? 3 : 1);
     c->p.dual = (c->p.stages >= 2 * k_iters && tc_env_int("FU_TC_DUAL", 1)) ? 1 : 0;
   }
+  {
+    // clusters of two one-tile CTAs sharing an operand through TMA multicast (see TcConvParams::mc)
+    const long long total_tiles = (long long)c->p.tiles_w * c->p.tiles_h * c->p.tiles_b * c->p.n_tiles;
+    const int k_iters = c->p.ksz * c->p.ksz * (c->p.Cin / c->p.KC);
+    c->p.mc = 0;
+    if (!c->f32 && !c->p.a5 && !c->p.c5 && !c->p.dual && !c->p.kpair && c->grid == total_tiles && (c->grid % 2) == 0 && k_iters >= 8 &&
+        tc_env_int("FU_TC_MC", 0)) {      // measured 3-8 % SLOWER on the 12x12 / 24x24 layers: off unless asked for
+      if (c->p.n_tiles % 2 == 0) c->p.mc = 1;
+      else if (c->p.n_tiles == 1) c->p.mc = 2;
+    }
+  }
+  if (c->p.mc) {
+    if (G_run == 4) fu_launch_cluster(tc_conv_kernel<4, false>, dim3(c->grid), dim3(96 + 128 * 4), c->smem, stream, pdl, 2u, c->a, c->b, c->c, c->tm_t, c->p);
+    else if (G_run == 2) fu_launch_cluster(tc_conv_kernel<2, false>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, 2u, c->a, c->b, c->c, c->tm_t, c->p);
+    else fu_launch_cluster(tc_conv_kernel<1, false>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, 2u, c->a, c->b, c->c, c->tm_t, c->p);
+  } else
   if (c->f32 && c->G == 2) fu_launch(tc_conv_kernel<2, true>, dim3(c->grid), dim3(96 + 128 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
   else if (c->f32) fu_launch(tc_conv_kernel<1, true>, dim3(c->grid), dim3(96 + 128), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
   else if (G_run == 4) fu_launch(tc_conv_kernel<4, false>, dim3(c->grid), dim3(96 + 128 * 4), c->smem, stream, pdl, c->a, c->b, c->c, c->tm_t, c->p);
