@@ -2562,7 +2562,7 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   p.cs_shift = p.CS == 64 ? 6 : 5;
   // two 64-channel K chunks per pipeline stage on the deep layers (see TcConvParams::kpair)
   p.kpair = (!t.split && p.KC == 64 && (K / 64) % 2 == 0 && ((p.tw * p.th * p.tn) % 8) == 0 && t.k * t.k * (K / 64) >= 16 &&
-             p.BN >= 128 && tc_env_int("FU_TC_KPAIR", 1)) ? 1 : 0;
+             p.BN >= tc_env_int("FU_TC_KPAIR_MINBN", 64) && tc_env_int("FU_TC_KPAIR", 1)) ? 1 : 0;
   p.nstaging = p.BN <= 64 ? 2 : 1;
   if (p.kpair) {      // only where three double stages fit (beside, or overlaid by, the staging tiles): 128-column tiles
     const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / p.BN);
