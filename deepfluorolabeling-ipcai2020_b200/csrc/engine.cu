@@ -1331,13 +1331,13 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     // resident blocks per SM: 3 with the landmark head (168 registers, 64.5 KB), 2 without (255 registers)
     const unsigned gridh = (unsigned)std::min<long long>((P0 + 255) / 256, (long long)e->num_sms * (c.num_lands == 14 ? 3 : 2));
     if (c.num_lands == 14) {
-      LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, (heads_bwd_smem_bytes<32, 7, 21, 14>()), reinterpret_cast<const T*>(feat.p), feat.ld,
+      LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, (sizeof(T) == 2 ? heads_bwd_smem_bytes_mma<32, 7, 21, 14>() : heads_bwd_smem_bytes<32, 7, 21, 14>()), reinterpret_cast<const T*>(feat.p), feat.ld,
              tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,
              reinterpret_cast<T*>(d_feat.p), d_feat.ld, e->heads_gacc, B, HW, c.do_soft_max);
       LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
              gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
     } else {
-      LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 1, 0>), gridh, 128, (heads_bwd_smem_bytes<32, 7, 1, 0>()), reinterpret_cast<const T*>(feat.p), feat.ld,
+      LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 1, 0>), gridh, 128, (sizeof(T) == 2 ? heads_bwd_smem_bytes_mma<32, 7, 1, 0>() : heads_bwd_smem_bytes<32, 7, 1, 0>()), reinterpret_cast<const T*>(feat.p), feat.ld,
              tdata(e, e->seg.w_idx), (const float*)nullptr, (const float*)nullptr, d_seg, (const float*)nullptr,
              reinterpret_cast<T*>(d_feat.p), d_feat.ld, e->heads_gacc, B, HW, c.do_soft_max);
       LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,

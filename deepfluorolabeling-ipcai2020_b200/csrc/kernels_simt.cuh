@@ -795,6 +795,36 @@ constexpr size_t heads_bwd_smem_bytes() {
   typedef HeadsDims<CF, NC, NF, NL> D;
   return sizeof(float) * ((size_t)(D::NLp + D::NCAT + NC) * 256 + NC * CF + (NL > 0 ? NL * D::NCATP : 4));
 }
+// bf16 storage: the two outer-product reductions run on the tensor cores (warp-level mma.sync over bf16 copies of the
+// per-pixel vectors), see heads_bwd_fused_kernel.  Shared memory: fp32 dheat rows + bf16 [rows][256 + 8] tiles.
+template <int CF, int NC, int NL>
+struct HeadsMma {
+  static constexpr int MR = NL + NC;                         // gradient rows: dheat (NL), dlg (NC)
+  static constexpr int MT = (MR + 15) / 16;                  // 16-row tiles
+  static constexpr int NB = CF + (NL > 0 ? NC : 0);          // columns: feat (CF) [, logits (NC)]
+  static constexpr int NT = (NB + 7) / 8;                    // 8-column tiles
+  static constexpr int PITCH = 256 + 8;                      // bf16 elements per row: 528 B, conflict-free ldmatrix rows
+  static constexpr int NLp = NL > 0 ? NL : 1;
+};
+template <int CF, int NC, int NF, int NL>
+constexpr size_t heads_bwd_smem_bytes_mma() {
+  typedef HeadsDims<CF, NC, NF, NL> D;
+  typedef HeadsMma<CF, NC, NL> M;
+  return sizeof(float) * ((size_t)M::NLp * 256 + NC * CF + (NL > 0 ? NL * D::NCATP : 4)) +
+         2 * (size_t)(M::MT * 16 + M::NT * 8) * M::PITCH;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 
 template <typename T, int CF, int NC, int NF, int NL>
 __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
@@ -809,11 +839,29 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
   constexpr int NTA = (NLp + TA - 1) / TA, NTB = (NCAT + TB - 1) / TB;
   static_assert(NTA * NTB + CF <= 128, "outer-product tiles must fit one block");
   extern __shared__ __align__(16) float heads_smem[];
-  float* s_v = heads_smem;                       // [ROWS][256] per-pixel vectors, one column per pixel
-  float* s_wseg = s_v + ROWS * 256;              // [NC][CF]
+  // bf16 storage: outer products on the tensor cores.  The per-pixel vectors are ALSO written as bf16 rows
+  // A_s = [dheat ; dlg] (MT*16 rows) and B_s = [feat ; logits] (NT*8 rows), 256 pixels (K) per row; warp w owns the
+  // 8-column tiles w, w + 4 of  G = A_s B_s^T  and runs 16 K steps of mma.sync.m16n8k16 per chunk with fp32 accumulators
+  // kept in registers for the whole (persistent) block.  The fp32 version below read 5 float4 per 24 FMAs from shared
+  // memory and was bound by its bandwidth (~80 of the kernel's 240 us at B = 32 @192x192).
+  constexpr bool kMma = sizeof(T) == 2;
+  typedef HeadsMma<CF, NC, NL> MM;
+  float* s_v = heads_smem;                       // [ROWS][256] per-pixel vectors, one column per pixel (kMma: dheat rows only)
+  float* s_wseg = s_v + (kMma ? NLp : ROWS) * 256;   // [NC][CF]
   float* s_w21 = s_wseg + NC * CF;               // [NL][NCATP]
+  bf16* A_s = reinterpret_cast<bf16*>(s_w21 + (NL > 0 ? NL * NCATP : 4));   // [MT*16][PITCH]
+  bf16* B_s = A_s + MM::MT * 16 * MM::PITCH;                                 // [NT*8][PITCH]
   for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
   heads_fold_w21<CF, NC, NF, NL>(w1, w2, s_w21);
+  if (kMma) {       // padding rows are never written: zero everything once
+    uint32_t* z = reinterpret_cast<uint32_t*>(A_s);
+    for (int i = threadIdx.x; i < (MM::MT * 16 + MM::NT * 8) * MM::PITCH / 2; i += blockDim.x) z[i] = 0u;
+  }
+  float macc[MM::MT][2][4];
+#pragma unroll
+  for (int i = 0; i < MM::MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { macc[i][j][0] = macc[i][j][1] = macc[i][j][2] = macc[i][j][3] = 0.f; }
   const int tid = threadIdx.x;
   // outer-product ownership
   const bool own_g1 = NL > 0 && tid < NTA * NTB;
@@ -856,7 +904,11 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
     for (int u = 0; u < 2; ++u) {
       float* col = s_v + u * 128 + tid;
 #pragma unroll
-      for (int l = 0; l < NLp; ++l) col[l * 256] = (NL > 0 && d_heat && ok[u]) ? d_heat[(n[u] * NL + l) * HW + hw[u]] : 0.f;
+      for (int l = 0; l < NLp; ++l) {
+        const float dv = (NL > 0 && d_heat && ok[u]) ? d_heat[(n[u] * NL + l) * HW + hw[u]] : 0.f;
+        col[l * 256] = dv;
+        if (kMma && NL > 0) A_s[l * MM::PITCH + u * 128 + tid] = __float2bfloat16_rn(dv);
+      }
 #pragma unroll
       for (int k = 0; k < D::NCP; ++k) dlg[u][k] = (k < NC && d_seg && ok[u]) ? d_seg[(n[u] * NC + k) * HW + hw[u]] : 0.f;
     }
@@ -865,10 +917,19 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       float* col = s_v + u * 128 + tid;           // row r of this pixel at col[r*256]
+      if (kMma) {
 #pragma unroll
-      for (int c = 0; c < CF; ++c) col[(NLp + c) * 256] = f[u][c];
+        for (int c = 0; c < CF; ++c) B_s[c * MM::PITCH + u * 128 + tid] = __float2bfloat16_rn(f[u][c]);
+        if (NL > 0) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) col[(NLp + CF + k) * 256] = lg[u][k];
+          for (int k = 0; k < NC; ++k) B_s[(CF + k) * MM::PITCH + u * 128 + tid] = __float2bfloat16_rn(lg[u][k]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CF; ++c) col[(NLp + c) * 256] = f[u][c];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) col[(NLp + CF + k) * 256] = lg[u][k];
+      }
       if (do_softmax && d_seg) {
         float mx = lg[u][0];
 #pragma unroll
@@ -917,8 +978,13 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
     }
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      s_v[(NLp + NCAT + k) * 256 + tid] = dlg[0][k];
-      s_v[(NLp + NCAT + k) * 256 + 128 + tid] = dlg[1][k];
+      if (kMma) {
+        A_s[(NL + k) * MM::PITCH + tid] = __float2bfloat16_rn(dlg[0][k]);
+        A_s[(NL + k) * MM::PITCH + 128 + tid] = __float2bfloat16_rn(dlg[1][k]);
+      } else {
+        s_v[(NLp + NCAT + k) * 256 + tid] = dlg[0][k];
+        s_v[(NLp + NCAT + k) * 256 + 128 + tid] = dlg[1][k];
+      }
 #pragma unroll
       for (int c = 0; c < CF; c += 4) {
         const float4 w = *reinterpret_cast<const float4*>(q_wseg + k * CF + c);
@@ -937,6 +1003,31 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
         st4(d_feat + pix[u] * d_ld + c, make_float4(df[u][c], df[u][c + 1], df[u][c + 2], df[u][c + 3]));
     }
     __syncthreads();
+    if (kMma) {
+      // G += A_s B_s^T over the chunk's 256 pixels: this warp's 8-column tiles wq, wq + 4
+      const int lane = tid & 31, wq = tid >> 5;
+      const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(A_s) +
+                              2u * (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * MM::PITCH + 8 * (lane >> 4));
+      const uint32_t b_base = (uint32_t)__cvta_generic_to_shared(B_s) +
+                              2u * (uint32_t)((lane & 7) * MM::PITCH + 8 * ((lane >> 3) & 1));
+#pragma unroll 4
+      for (int ks = 0; ks < 16; ++ks) {
+        uint32_t af[MM::MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MM::MT; ++mt) ldsm_x4(a_base + 2u * (uint32_t)(mt * 16 * MM::PITCH + ks * 16), af[mt]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int nt = wq + 4 * j;
+          if (nt < MM::NT) {
+            uint32_t bfr[2];
+            ldsm_x2(b_base + 2u * (uint32_t)(nt * 8 * MM::PITCH + ks * 16), bfr);
+#pragma unroll
+            for (int mt = 0; mt < MM::MT; ++mt) mma_bf16_16816(macc[mt][j], af[mt], bfr);
+          }
+        }
+      }
+      continue;          // (the next chunk's leading __syncthreads orders these reads before its writes)
+    }
     // outer products over the chunk's 256 pixels (float4 along the pixel axis); out-of-range pixels hold zeros
     if (own_g1) {
 #pragma unroll 2
@@ -966,6 +1057,24 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
         }
       }
     }
+  }
+  if (kMma) {
+    // fragment (mt, j): rows mt*16 + lane/4 (+8), columns (wq + 4j)*8 + 2*(lane%4) (+1)
+    const int lane = tid & 31, wq = tid >> 5;
+#pragma unroll
+    for (int mt = 0; mt < MM::MT; ++mt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int nt = wq + 4 * j;
+        if (nt >= MM::NT) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = mt * 16 + (lane >> 2) + 8 * (e >> 1), colx = nt * 8 + 2 * (lane & 3) + (e & 1);
+          if (row < NL) { if (colx < NCAT) atomicAdd(g_acc + row * NCAT + colx, macc[mt][j][e]); }
+          else if (row < NL + NC && colx < CF) atomicAdd(g_acc + NLp * NCAT * (NL > 0 ? 1 : 0) + (row - NL) * CF + colx, macc[mt][j][e]);
+        }
+      }
+    return;
   }
   if (own_g1) {
 #pragma unroll
