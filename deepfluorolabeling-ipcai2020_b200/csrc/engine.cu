@@ -845,7 +845,9 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
       // C_in = 1 fast path: persistent blocks, two per SM
       const int TW = 256 / (cw.Cout / 8);
       const long long tiles = (long long)((W + TW - 1) / TW) * ((H + cin1_tile_h(cw.k) - 1) / cin1_tile_h(cw.k)) * B;
-      const unsigned grid = (unsigned)std::min<long long>(tiles, 4ll * e->num_sms);
+      // whole waves of the kernel's resident blocks (3 per SM for the 1x1, 2 for the 3x3 variant): 4 x SMs was 1.33 waves
+      // of the 1x1 kernel
+      const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)e->num_sms * (cw.k == 1 ? 3 : 2) * tc_env_int("FU_CIN1_WAVES", 1));
       const size_t sm1 = cin1_smem_bytes(cw.k, cw.Cout, false);
       if (cw.k == 3) LAUNCH_SMEM(e, (conv_cin1_kernel<T, 3>), grid, 256, sm1, a);
       else LAUNCH_SMEM(e, (conv_cin1_kernel<T, 1>), grid, 256, sm1, a);
@@ -1174,7 +1176,7 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
     if (cw.Cin == 1) {
       const int TW = 256 / (cw.Cout / 8);
       const long long tiles = (long long)((W + TW - 1) / TW) * ((H + cin1_tile_h(cw.k) - 1) / cin1_tile_h(cw.k)) * B;
-      const unsigned grid = (unsigned)std::min<long long>(tiles, 4ll * e->num_sms);
+      const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)e->num_sms * (cw.k == 1 ? 3 : 2) * tc_env_int("FU_CIN1_WAVES", 1));
       const size_t sm1 = cin1_smem_bytes(cw.k, cw.Cout, true);
       if (cw.k == 3) LAUNCH_SMEM(e, (wgrad_cin1_kernel<T, 3>), grid, 256, sm1, a);
       else LAUNCH_SMEM(e, (wgrad_cin1_kernel<T, 1>), grid, 256, sm1, a);
