@@ -368,7 +368,7 @@ struct TcConvParams {
                                 // operands in flight.  The deep layers (12x12, 24x24: 144 tiles) are bound by the bytes in
                                 // flight per SM: 32-48 KB per K iteration against 256-512 tensor cycles needs more than the
                                 // 3-4 stages left beside 64 KB of staging (ncu: the MMA warp polls its full barrier ~2x per
-                                // iteration, tensor pipe 36 % busy, profiles/r02_ncu_deep_conv_512.txt)
+                                // iteration, tensor pipe 36 % busy, profiles/r02_ncu_deep_conv_512_before.txt)
   int kpair;                    // 1: a pipeline stage holds TWO 64-channel K chunks of both operands, each pair fetched by one
                                 // TMA instruction (A through a 5-D view whose slowest box dimension is the chunk index, so
                                 // the two [pixels][64] tiles land back to back; B likewise in 4-D): half as many barrier
@@ -1907,7 +1907,7 @@ struct TcWgrad3Params {
                                 //    32-channel (SWIZZLE_64B) blocks one leading-dimension offset apart: accumulator rows
                                 //    [32 s, 32 s + 32) hold sum dY[h+s] (x) X[h+1] = filter row kh = 2 - s, so ONE M = 128 MMA
                                 //    per 16 pixels replaces three M = 64 ones (which run at half rate with half their rows
-                                //    unused: the tensor pipe was 54 % busy doing 25 % useful work, profiles/r02_ncu_thin_wgrad3.txt).
+                                //    unused: the tensor pipe was 54 % busy doing 25 % useful work, profiles/r02_ncu_thin_wgrad3_before.txt).
                                 //    Row bands run over h = -2 .. H-1; TMA zero-fills the rows outside the image.
   int skip_epi;                 // diagnostics only (FU_TC_WGRAD_NOEPI=1)
   int m64;                      // see TcWgradParams
