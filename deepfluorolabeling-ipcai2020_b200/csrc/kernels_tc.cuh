@@ -2505,7 +2505,9 @@ inline long long tc_pick_splits(long long units, long long max_splits, int sms, 
 // bottleneck), 2 up to 128 columns, 1 for 256-column tiles (TMEM holds 2G accumulators of BN columns)
 inline int tc_pick_groups(int BN, int k_iters, int ksteps) {
   const int g_env = tc_env_int("FU_TC_EPI_GROUPS", 0);
-  int G = (BN <= 64 && k_iters * ksteps <= 48) ? 4 : (BN <= 128 ? 2 : 1);
+  // (four groups only for 32-column tiles: at 64 columns their staging + `t` tiles leave 1-2 operand stages --
+  //  residual 1x1 128->64 @96x96: 48 us with four groups, 33 with two)
+  int G = (BN <= 32 && k_iters * ksteps <= 48) ? 4 : (BN <= 128 ? 2 : 1);
   if (g_env == 1 || g_env == 2 || g_env == 4) G = g_env;
   while (2 * G * BN > 512) G >>= 1;
   return G < 1 ? 1 : G;
