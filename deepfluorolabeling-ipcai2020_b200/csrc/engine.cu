@@ -39,6 +39,12 @@ struct View {
   int ld = 0;         // pixel stride, in elements
   char* sp = nullptr; // parity_tc mode: channel 0 of the hi half of this view's split-bf16 twin (kernels_tc.cuh:
                       // split_f32_kernel); twin pixel stride 2*ld bf16 elements, lo half ld elements after the hi half
+  // planar buffer (plane > 0): channels [k*planeC, (k+1)*planeC) are a contiguous (pixels, planeC) tensor at p + k*plane.
+  // Used for the gradient of the 32-channel skip concat in bf16 storage: its two halves are read separately (up-conv
+  // backward / encoder block backward), and a 64-byte half of a 128-byte pixel costs a full line of DRAM traffic per
+  // read (ncu: 226 MB instead of 151 MB for the BN backward of the first encoder block).
+  size_t plane = 0;
+  int planeC = 0;
 };
 
 struct TensorSlot {
@@ -260,6 +266,12 @@ inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 inline View slice(const View& v, int c0, int C, int esz) {
   View o;
+  if (v.plane) {          // whole planes only
+    o.p = v.p + (size_t)(c0 / v.planeC) * v.plane;
+    o.C = C;
+    o.ld = v.planeC;
+    return o;
+  }
   o.p = v.p + (size_t)c0 * esz;
   o.C = C;
   o.ld = v.ld;
@@ -514,6 +526,14 @@ void carve_plan(fu_engine* e, Plan& pl, Bump& b, int B, int H, int W) {
   for (int l = 0; l < D - 1; ++l) {
     pl.cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz, &pl);
     pl.d_cat[l] = take_view(b, pix(l), 2 * e->chans[l], 2 * e->chans[l], esz, &pl);
+    // halves narrower than a 128-byte line, written by the fused tensor-core data gradient of the decoder block (which
+    // can store plane by plane): two planes instead of interleaved halves
+    if (e->cfg.precision == FU_PRECISION_BF16 && e->chans[l] * esz < 128 && e->chans[l] % 32 == 0 && c.do_res &&
+        !e->dec.empty() && e->dec[D - 2 - l].convs[0].tc.enabled && e->dec[D - 2 - l].res.tc.enabled &&
+        (W >> l) >= tc_env_int("FU_TC_V2_MINW", 48) && (H >> l) >= 8 && tc_env_int("FU_DCAT_PLANAR", 1)) {
+      pl.d_cat[l].plane = (size_t)pix(l) * e->chans[l] * esz;
+      pl.d_cat[l].planeC = e->chans[l];
+    }
   }
   for (int l = 1; l < D; ++l) {
     pl.down[l] = take_view(b, pix(l), e->chans[l - 1], e->chans[l - 1], esz, &pl);
@@ -1286,14 +1306,15 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
         e->set_tag(2.0 * M * cw.Cin * cw.Cout * 10.0, (M * (d_in->C + 2.0 * blk.C)) * e->esz, "conv3_dgrad %dx%d %d->%d",
                    H, W, cw.Cout, cw.Cin);
         if (e->prof) e->prof_begin("tc_conv_kernel");
-        const int trc = tc_conv_dgrad(cw.tc, dy0.p, dy0.ld, d_in->p, d_in->ld, B, H, W, 0, e->stream, &e->cnt,
-                                      st, &blk.res.tc, go.p, go.ld);
+        const int trc = tc_conv_dgrad(cw.tc, dy0.p, dy0.ld, d_in->p, d_in->plane ? d_in->planeC : d_in->ld, B, H, W, 0, e->stream, &e->cnt,
+                                      st, &blk.res.tc, go.p, go.ld, d_in->plane / e->esz, d_in->planeC);
         if (e->prof) e->prof_end();
         if (trc == 0) { fused = true; if (st && in_sums) *in_sums = true; }
         else if (trc != -2) return e->fail(FU_ERR_CUDA, "fused residual dgrad launch failed: %s", tc_last_error());
         else if (e->prof) { cudaEventDestroy(e->prof_recs.back().a); cudaEventDestroy(e->prof_recs.back().b); e->prof_recs.pop_back(); }
       }
       if (!fused) {
+        if (d_in->plane) return e->fail(FU_ERR_CUDA, "planar skip gradient needs the fused tensor-core data gradient (set FU_DCAT_PLANAR=0)");
         if ((rc = conv_dgrad<T>(e, cw, blk.dy[0], *d_in, B, H, W, 0, blk.has_res ? nullptr : st, in_sums))) return rc;
         if (blk.has_res && (rc = conv_dgrad<T>(e, blk.res, g, *d_in, B, H, W, 1, st, in_sums))) return rc;
       }
@@ -1707,6 +1728,7 @@ int fu_debug_copy(fu_engine* e, const char* name, float* dst, int64_t capacity, 
   else if (nm == "hcat") { v = pl.hcat; lvl = 0; }
   else if (nm == "d_hcat") { v = pl.d_hcat; lvl = 0; }
   if (!v.p || lvl < 0) return e->fail(FU_ERR_ARG, "fu_debug_copy: unknown or unmaterialised tensor '%s'", name);
+  if (v.plane) return e->fail(FU_ERR_ARG, "fu_debug_copy: '%s' is stored as planes (FU_DCAT_PLANAR=0 for the interleaved layout)", name);
   const int h = pl.H >> lvl, w = pl.W >> lvl;
   shape4[0] = pl.B; shape4[1] = v.C; shape4[2] = h; shape4[3] = w;
   const int64_t need = (int64_t)pl.B * v.C * h * w;

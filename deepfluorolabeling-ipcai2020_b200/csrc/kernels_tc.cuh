@@ -1060,6 +1060,8 @@ struct TcConv3Params {
   FastDiv fd_ntiles, fd_timg, fd_tw;   // divisions by n_tiles, tiles_w * tiles_h, tiles_w (tile decode, every role, every tile)
   int cs_shift;                 // log2(CS)
   int baton_kh;                 // filter row (0..2) of a super tile's last section at which the issuer passes the baton
+  int planeC;                   // > 0: the output is PLANAR -- channels [k*planeC, (k+1)*planeC) form a contiguous (pixels, planeC)
+                                // tensor k (5-D store map with the plane index as its last coordinate); CS == planeC
 };
 
 // S = epilogue sets.  A set is one group of 4 warps per pixel tile of the pair; super tile i of a CTA is drained
@@ -1106,7 +1108,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t vec_off = staging_off + (uint32_t)(S * p.npair) * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
   // statistics partials per epilogue group (tc3_park_floats): F32 [4][2][BN] floats; bf16 one float4 per (thread, sub-box)
   const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;
-  const uint32_t park_floats = tc3_park_floats(p.BN, p.CS);
+  // (bf16: the partials are parked in the group's own staging tile at flush time, no separate region)
+  const uint32_t park_floats = F32 ? tc3_park_floats(p.BN, p.CS) : 0u;
   const uint32_t bar_off = (stat_off + (uint32_t)(S * p.npair) * park_floats * 4u + 7u) & ~7u;
   const uint32_t bar_base = smem_base + bar_off;
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -1424,7 +1427,11 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // amplify into visibly different gradients (tools/diag_repeat2.py).
       auto flush_stats = [&]() {
         if (p.stat && s_nb >= 0) {
-          float* park = reinterpret_cast<float*>(smem + stat_off) + gi * (int)park_floats;   // [128 threads][nsub][4]
+          // the partials are parked in this group's staging tile ([128 threads][nsub][4] floats <= 4 KB of its >= 8 KB):
+          // a flush happens once per CTA (or per N tile), and a dedicated region cost 8-16 KB of shared memory that
+          // some layers need for their fourth operand stage (and with it the second MMA issuer)
+          float* park = reinterpret_cast<float*>(staging);
+          if (et == 0) ptx::tma_store_wait_read();       // no store may still be reading the tile
           ptx::named_bar_sync(bar_id, 128);
 #pragma unroll
           for (int sub = 0; sub < 4; ++sub)
@@ -1444,6 +1451,11 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 v += park[((w * 32 + ro * cpw + (cc >> 1)) * nsub + sub) * 4 + comp];
             atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
           }
+          ptx::named_bar_sync(bar_id, 128);
+          // the statistics scan relies on never-written staging rows reading as zeros: put them back
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub)
+            if (sub < nsub) *reinterpret_cast<float4*>(park + (et * nsub + sub) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
           ptx::named_bar_sync(bar_id, 128);
         }
       };
@@ -1643,8 +1655,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
           if (et == 0) {
-            for (int s2 = 0; s2 < p.BN / p.CS; ++s2)
-              ptx::tma_store_4d(&tmC, stg_addr + (uint32_t)s2 * sub_bytes, nb + s2 * p.CS, w0, h0, n);
+            for (int s2 = 0; s2 < p.BN / p.CS; ++s2) {
+              if (p.planeC) ptx::tma_store_5d(&tmC, stg_addr + (uint32_t)s2 * sub_bytes, 0, w0, h0, n, (nb + s2 * p.CS) / p.planeC);
+              else ptx::tma_store_4d(&tmC, stg_addr + (uint32_t)s2 * sub_bytes, nb + s2 * p.CS, w0, h0, n);
+            }
             ptx::tma_store_commit();
           }
           if (p.stat) {
@@ -2753,10 +2767,11 @@ inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
 
 // res / x2: (dir 1 only) the block's 1x1 shortcut and the gradient G of the block output: dX = conv3x3^T(x) + conv1x1^T(x2)
 inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W,
-                                     const TcConv* res = nullptr, const void* x2 = nullptr, int x2_ld = 0) {
+                                     const TcConv* res = nullptr, const void* x2 = nullptr, int x2_ld = 0,
+                                     long long y_plane = 0, int y_planeC = 0) {
   for (auto& c : t.cache3)
     if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == H && c.W == W && c.dir == dir &&
-        c.x2 == x2 && c.x2_ld == x2_ld)
+        c.x2 == x2 && c.x2_ld == x2_ld && c.p.planeC == y_planeC)
       return &c;
   TcConv::Cached3 c;
   memset(&c, 0, sizeof(c));
@@ -2771,6 +2786,11 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   int bn = 128;
   while (N % bn) bn >>= 1;
   p.BN = bn; p.CS = (bn >= 64 && !t.split) ? 64 : 32;
+  p.planeC = 0;
+  if (y_planeC) {               // planar output: one store box per plane slice
+    if (t.split || y_planeC != 32 || N % y_planeC) { tc_err() = "planar output: 32-channel planes, bf16 storage only"; return nullptr; }
+    p.planeC = y_planeC; p.CS = 32;
+  }
   p.n_tiles = N / bn;
   p.a_lo = t.split ? x_ld / 2 : 0; p.b_lo = t.split ? K : 0;
   p.a2_lo = t.split ? x2_ld / 2 : 0; p.b2_lo = p.b_lo;
@@ -2799,21 +2819,36 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   // preference order when shared memory is short: (2 sets, 2 staging tiles) -> (2 sets, 1) -> (1 set, 2) -> (1 set, 1)
   p.nstg = (p.BN <= 64 && !t.split && tc_env_int("FU_TC_STAGING2", 1)) ? 2 : 1;
   const int want_S = c.S, want_nstg = p.nstg;
-  for (int attempt = 0;; ++attempt) {
-    if (attempt == 1) { if (want_S == 2 && want_nstg == 2) { c.S = 2; p.nstg = 1; } else continue; }
-    if (attempt == 2) { if (want_S == 2) { c.S = 1; p.nstg = want_nstg; } else continue; }
-    if (attempt == 3) { c.S = 1; p.nstg = 1; }
-    const size_t staging = t.split ? (size_t)c.S * p.npair * 32768 : (size_t)c.S * p.npair * 128 * p.BN * 2 * p.nstg;
-    const size_t fixed = 1024 + staging + (size_t)12 * N + (size_t)c.S * p.npair * tc3_park_floats(p.BN, p.CS) * 4 + 16 + 8 * 48;
-    p.resident = (p.n_tiles == 1 && fixed + wbytes + 2 * a_stage <= budget && tc_env_int("FU_TC_RESIDENT", 1)) ? 1 : 0;
-    if (p.resident) {
+  // candidate (epilogue sets, staging tiles) in order of preference
+  int cand[4][2]; int ncand = 0;
+  cand[ncand][0] = want_S; cand[ncand++][1] = want_nstg;
+  if (want_S == 2 && want_nstg == 2) { cand[ncand][0] = 2; cand[ncand++][1] = 1; }
+  if (want_S == 2) { cand[ncand][0] = 1; cand[ncand++][1] = want_nstg; }
+  if (want_S != 1 || want_nstg != 1) { cand[ncand][0] = 1; cand[ncand++][1] = 1; }
+  auto fixed_of = [&](int S_, int nstg_) {
+    const size_t staging = t.split ? (size_t)S_ * p.npair * 32768 : (size_t)S_ * p.npair * 128 * p.BN * 2 * nstg_;
+    return 1024 + staging + (size_t)12 * N + (t.split ? (size_t)S_ * p.npair * tc3_park_floats(p.BN, p.CS) * 4 : 0) + 16 + 8 * 48;
+  };
+  // A stages one super tile consumes: with fewer than twice that many the two MMA issuers (and their baton) are off,
+  // which costs more than a second staging tile gains (32->64 data gradient @192x192: 89 us with 4 stages and one staging
+  // tile, 112 us with 2 stages and two).  Pass 0 only accepts resident configurations that keep them, pass 1 any resident one.
+  const int a_per_tile_h = (K / p.KC) * (t.split ? 3 : 1) * (p.halo1 ? 1 : 3) * (p.res ? 2 : 1);
+  const bool dual_possible = tc_env_int("FU_TC_DUAL", 1) != 0 && 2 * a_per_tile_h <= 4;
+  p.resident = 0;
+  for (int pass = dual_possible ? 0 : 1; pass < 2 && !p.resident; ++pass)
+    for (int ci = 0; ci < ncand && !p.resident; ++ci) {
+      const size_t fixed = fixed_of(cand[ci][0], cand[ci][1]);
+      if (p.n_tiles != 1 || fixed + wbytes + 2 * a_stage > budget || !tc_env_int("FU_TC_RESIDENT", 1)) continue;
       int as = (int)((budget - fixed - wbytes) / a_stage);
-      p.a_stages = as > 4 ? 4 : as;
-      p.b_stages = 1;
-      c.smem = fixed + wbytes + (size_t)p.a_stages * a_stage;
-      break;
+      if (as > 4) as = 4;
+      if (pass == 0 && as < 2 * a_per_tile_h) continue;
+      p.resident = 1; c.S = cand[ci][0]; p.nstg = cand[ci][1];
+      p.a_stages = as; p.b_stages = 1;
+      c.smem = fixed + wbytes + (size_t)as * a_stage;
     }
-    if (attempt < 3) continue;       // retry with less epilogue staging before giving up residency
+  if (!p.resident) {
+    c.S = 1; p.nstg = 1;
+    const size_t fixed = fixed_of(1, 1);
     p.a_stages = 2;
     if (fixed + 3 * a_stage + 6 * b_bytes <= budget) p.a_stages = 3;
     if (fixed + (size_t)p.a_stages * a_stage + 2 * b_bytes > budget) { tc_err() = "halo tile does not fit shared memory"; return nullptr; }
@@ -2822,7 +2857,6 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     if (bs < 2) { tc_err() = "halo tile does not fit shared memory"; return nullptr; }
     p.b_stages = bs;
     c.smem = fixed + (size_t)p.a_stages * a_stage + (size_t)bs * b_bytes;
-    break;
   }
   const long long m_tiles = (long long)p.tiles_w * p.tiles_h * B;
   const long long total_super = (m_tiles + p.npair - 1) / p.npair * p.n_tiles;
@@ -2850,7 +2884,12 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     int box[3] = {p.KC, 1, p.BN};
     if (tc_make_map(&c.b, dir == 0 ? t.w_fwd : t.w_dgrad, 3, dims, str, box, p.KC * 2)) return nullptr;
   }
-  {
+  if (p.planeC) {
+    long long dims[5] = {p.planeC, W, H, B, N / p.planeC};
+    long long str[5] = {1, p.planeC, (long long)W * p.planeC, (long long)H * W * p.planeC, y_plane};
+    int box[5] = {p.CS, p.two, p.th, 1, 1};
+    if (tc_make_map(&c.c, y, 5, dims, str, box, p.CS * 2)) return nullptr;
+  } else {
     long long dims[4] = {N, W, H, B};
     long long str[4] = {1, y_ld, (long long)W * y_ld, (long long)H * W * y_ld};
     int box[4] = {p.CS, p.two, p.th, 1};
@@ -3028,9 +3067,11 @@ inline bool tc_dgrad_can_fuse_res(const TcConv& t, const TcConv& res, int H, int
 }
 inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
                          cudaStream_t stream, fu_counters* cnt, double* stat = nullptr, const TcConv* res = nullptr,
-                         const void* g = nullptr, int g_ld = 0) {
+                         const void* g = nullptr, int g_ld = 0, long long dx_plane = 0, int dx_planeC = 0) {
+  if (dx_planeC && (!tc_use_v2(t, H, W) || accumulate)) { tc_err() = "planar output needs the halo kernel"; return -1; }
   if (tc_use_v2(t, H, W)) {
-    TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W, res, g, g_ld);
+    TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W, res, g, g_ld, dx_plane, dx_planeC);
+    if (!c3 && dx_planeC) return -1;
     if (c3) {
       c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = stat; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
       tc_set_t(t, c3->p, accumulate ? dx : nullptr, dx_ld);
