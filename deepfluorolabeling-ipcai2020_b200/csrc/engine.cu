@@ -775,7 +775,8 @@ int run_wgrad(fu_engine* e, const WgradCall& c) {
   return FU_OK;
 }
 
-inline dim3 red_grid(fu_engine* e, long long P, int C, int max_lanes = kRedLanes) {
+// bps: resident blocks per SM of the kernel the grid is for (its __launch_bounds__): the grid is capped at whole waves of them
+inline dim3 red_grid(fu_engine* e, long long P, int C, int max_lanes = kRedLanes, int bps = 4) {
   const int cvecs = C / (e->esz == 2 ? 8 : 4);     // Vec<T>::N channels per thread
   const int lanes = cvecs < max_lanes ? cvecs : max_lanes;
   const int rows = 256 / lanes;
@@ -789,7 +790,8 @@ inline dim3 red_grid(fu_engine* e, long long P, int C, int max_lanes = kRedLanes
   const unsigned gy = (unsigned)((cvecs + lanes - 1) / lanes);
   while (per > per_min && (P + rows * per - 1) / (rows * per) * gy < (long long)e->num_sms * 3 / 2) per >>= 1;
   long long gx = (P + (long long)rows * per - 1) / ((long long)rows * per);
-  const long long cap = std::max<long long>((long long)e->num_sms * 8 / gy, 1);
+  static const int waves = tc_env_int("FU_RED_WAVES", 1);   // measured @192x192: apply 47.4 (2 waves) -> 42.4 us (1), reduce 38.3 -> 35.4
+  const long long cap = std::max<long long>((long long)e->num_sms * bps * (max_lanes == kRedLanes ? waves : 2) / gy, 1);
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, gy);
@@ -1271,13 +1273,14 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
       } else {
         LAUNCH(e, (bn_bwd_reduce_kernel<T>), rg, 256, dp, d.ld, reinterpret_cast<const T*>(r.p),
                r.ld, b.mean, b.invstd, P, b.C, b.bstat);
-        LAUNCH(e, (act_bwd_kernel<T>), rg, 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
+        // (the apply kernel holds 3 blocks per SM: 8 x SMs blocks were 2.6 waves of it)
+        LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, b.C, kRedLanes, 3), 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
                reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, 1, b.mean, b.invstd, fin, P, b.C, cw.bsum);
       }
     } else {
       BnBwdFin fin;
       memset(&fin, 0, sizeof(fin));
-      LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, blk.C), 256, dp, d.ld,
+      LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, blk.C, kRedLanes, 3), 256, dp, d.ld,
              reinterpret_cast<const T*>(blk.r[i].p), blk.r[i].ld, reinterpret_cast<T*>(blk.dy[i].p),
              blk.dy[i].ld, 0, nullptr, nullptr, fin, P, blk.C, cw.bsum);
     }
