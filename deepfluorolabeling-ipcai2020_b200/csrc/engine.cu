@@ -1822,7 +1822,8 @@ int fu_loss_forward(const fu_loss_desc* d, double* sums, float* loss_out, void* 
   a.sums = sums;
   const size_t ws = (size_t)fu_loss_workspace_doubles(a.B, a.NC, a.NL) * sizeof(double);
   if (cudaMemsetAsync(sums, 0, ws, st) != cudaSuccess) { g_create_error = "fu_loss_forward: memset failed"; return FU_ERR_CUDA; }
-  const dim3 grid((unsigned)((a.Ht + kLossRows - 1) / kLossRows), (unsigned)(a.B * (a.NC + a.NL)));
+  a.rows = loss_rows_per_block(a.Ht, (long long)a.B * (a.NC + a.NL));
+  const dim3 grid((unsigned)((a.Ht + a.rows - 1) / a.rows), (unsigned)(a.B * (a.NC + a.NL)));
   loss_sums_kernel<<<grid, 256, 0, st>>>(a);
   loss_finalize_kernel<<<1, 256, 0, st>>>(a, loss_out);
   cudaError_t ce = cudaPeekAtLastError();
@@ -1839,7 +1840,8 @@ int fu_loss_backward(const fu_loss_desc* d, const double* sums, const float* dlo
   if (r0 < 0 || c0 < 0 || r0 + q.a.Ht > H || c0 + q.a.Wt > W) { g_create_error = "fu_loss_backward: window outside the output"; return FU_ERR_ARG; }
   q.a.sums = const_cast<double*>(sums);
   q.dloss = dloss; q.d_seg = d_seg; q.d_heat = d_heat; q.H = H; q.W = W; q.r0 = r0; q.c0 = c0;
-  const dim3 grid((unsigned)((H + kLossRows - 1) / kLossRows), (unsigned)(q.a.B * (q.a.NC + q.a.NL)));
+  q.a.rows = loss_rows_per_block(H, (long long)q.a.B * (q.a.NC + q.a.NL));
+  const dim3 grid((unsigned)((H + q.a.rows - 1) / q.a.rows), (unsigned)(q.a.B * (q.a.NC + q.a.NL)));
   loss_backward_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
   cudaError_t ce = cudaPeekAtLastError();
   if (ce != cudaSuccess) { g_create_error = std::string("fu_loss_backward: ") + cudaGetErrorString(ce); return FU_ERR_CUDA; }

@@ -22,9 +22,19 @@ struct LossArgs {
   int skip_bg;
   float dice_wgt, heat_wgt;
   double* sums;                 // [B][NC*3 + NL*5]
+  int rows;                     // image rows per block (loss_rows_per_block): warp w takes rows w, w+8, ...; lanes stride the columns
 };
 
-constexpr int kLossRows = 16;        // image rows per block: warp w takes rows w, w+8; lanes stride the columns
+// Rows per block: whole planes when there are enough planes to fill the machine (B = 32 @192x192: 672 planes), else chunks
+// sized for ~4 blocks per SM.  16-row blocks (8064 of them at B = 32) spent most of their time in the five block-level
+// fp64 reductions and atomics each block ends with: 61 + 95 us for two passes over 180 + 250 MB.
+inline int loss_rows_per_block(int rows_total, long long planes, int sms = 148) {
+  long long r = ((long long)rows_total * planes + (long long)sms * 4 - 1) / ((long long)sms * 4);
+  r = (r + 7) / 8 * 8;
+  if (r < 8) r = 8;
+  if (r > rows_total) r = rows_total;
+  return (int)r;
+}
 
 __device__ __forceinline__ double block_sum_double(double v, double* sm) {
   // 256 threads: warp shuffle, then one value per warp through shared memory
@@ -49,7 +59,7 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
   const int plane = blockIdx.y;
   const int b = plane / (p.NC + p.NL), c = plane - b * (p.NC + p.NL);
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int r_begin = blockIdx.x * kLossRows, r_end = min(r_begin + kLossRows, p.Ht);
+  const int r_begin = blockIdx.x * p.rows, r_end = min(r_begin + p.rows, p.Ht);
   const int per = p.NC * 3 + p.NL * 5;
   if (c < p.NC) {
     const float* x = p.seg + b * p.seg_sb + c * p.seg_sc;
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q)
   const int per = p.NC * 3 + p.NL * 5;
   const long long n_full = (long long)q.H * q.W;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int R_begin = blockIdx.x * kLossRows, R_end = min(R_begin + kLossRows, q.H);
+  const int R_begin = blockIdx.x * p.rows, R_end = min(R_begin + p.rows, q.H);
   const float up = *q.dloss;
   if (c < p.NC) {
     float* g = q.d_seg + ((long long)b * p.NC + c) * n_full;
