@@ -788,8 +788,7 @@ inline dim3 red_grid(fu_engine* e, long long P, int C, int max_lanes = kRedLanes
   static const int per_env = tc_env_int("FU_RED_PER_MIN", 2);
   const int per_min = max_lanes == kRedLanes ? per_env : 16;      // (the forward apply kernel keeps its round-1 grid)
   const unsigned gy = (unsigned)((cvecs + lanes - 1) / lanes);
-  static const int fill2 = tc_env_int("FU_RED_FILL2", 3);        // target blocks = fill2 / 2 x SMs before pixel rows per thread shrink
-  while (per > per_min && (P + rows * per - 1) / (rows * per) * gy < (long long)e->num_sms * fill2 / 2) per >>= 1;
+  while (per > per_min && (P + rows * per - 1) / (rows * per) * gy < (long long)e->num_sms * 3 / 2) per >>= 1;
   long long gx = (P + (long long)rows * per - 1) / ((long long)rows * per);
   static const int waves = tc_env_int("FU_RED_WAVES", 1);   // measured @192x192: apply 47.4 (2 waves) -> 42.4 us (1), reduce 38.3 -> 35.4
   const long long cap = std::max<long long>((long long)e->num_sms * bps * (max_lanes == kRedLanes ? waves : 2) / gy, 1);
@@ -1148,7 +1147,7 @@ int flush_deferred_sums(fu_engine* e) {
 // stat / stat_done: see tc_conv_dgrad; *stat_done is set when the (tensor-core) kernel produced the sums
 template <typename T>
 int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, int H, int W, int accumulate,
-               double* stat = nullptr, bool* stat_done = nullptr, const TcBnReduce* bnr = nullptr, bool* bnr_done = nullptr) {
+               double* stat = nullptr, bool* stat_done = nullptr) {
   {
     const double M = (double)B * H * W;
     e->set_tag(2.0 * M * cw.Cin * cw.Cout * cw.k * cw.k, (M * (dx.C + dy.C)) * e->esz + 2.0 * cw.Cin * cw.Cout * cw.k * cw.k,
@@ -1158,8 +1157,7 @@ int conv_dgrad(fu_engine* e, ConvW& cw, const View& dy, const View& dx, int B, i
   if (tc_dgrad_eligible(cw.tc, dyo.p, dyo.ld, dx.p, dx.ld)) {
     { const int src = ensure_split(e, dy, (long long)B * H * W); if (src) return src; }
     if (e->prof) e->prof_begin("tc_conv_kernel");
-    const int trc = tc_conv_dgrad(cw.tc, dyo.p, dyo.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt, stat, nullptr, nullptr, 0,
-                                  0, 0, bnr, bnr_done);
+    const int trc = tc_conv_dgrad(cw.tc, dyo.p, dyo.ld, dx.p, dx.ld, B, H, W, accumulate, e->stream, &e->cnt, stat);
     if (e->prof) e->prof_end();
     if (trc)
       return e->fail(FU_ERR_CUDA, "tensor-core dgrad launch failed: %s", tc_last_error());
@@ -1241,7 +1239,6 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
     if (!bn && (rc = channel_sum_to<T>(e, g, P, blk.res.bsum, gptr(e, flat, blk.res.b_idx)))) return rc;
   }
   View d = g;
-  bool reduced = false;          // the BatchNorm-backward sums of layer i were accumulated by the data gradient that produced d
   for (int i = nd - 1; i >= 0; --i) {
     View r = blk.r[i];
     ConvW& cw = blk.convs[i];
@@ -1274,10 +1271,8 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
         LAUNCH(e, (bn_act_bwd_coop_kernel<T>), rg, 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
                reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, b.mean, b.invstd, fin, b.bstat, P, b.C, cw.bsum, e->coop_bar);
       } else {
-        if (!reduced)
         LAUNCH(e, (bn_bwd_reduce_kernel<T>), rg, 256, dp, d.ld, reinterpret_cast<const T*>(r.p),
                r.ld, b.mean, b.invstd, P, b.C, b.bstat);
-        reduced = false;
         // (the apply kernel holds 3 blocks per SM: 8 x SMs blocks were 2.6 waves of it)
         LAUNCH(e, (act_bwd_kernel<T>), red_grid(e, P, b.C, kRedLanes, 3), 256, dp, d.ld, reinterpret_cast<const T*>(r.p), r.ld,
                reinterpret_cast<T*>(blk.dy[i].p), blk.dy[i].ld, 1, b.mean, b.invstd, fin, P, b.C, cw.bsum);
@@ -1297,20 +1292,7 @@ int block_backward(fu_engine* e, Block& blk, const View& x_in, const View& g, co
       if ((rc = conv_wgrad<T>(e, cw, conv_in, blk.dy[i], B, H, W, gptr(e, flat, cw.w_idx)))) return rc;
     }
     if (i > 0) {
-      // the previous layer's BatchNorm-backward reduction (over dz_i and r_{i-1}) rides in this launch's epilogue when the
-      // halo kernel runs it (bf16 storage, W >= 48)
-      TcBnReduce br;
-      // Off by default: measured break-even.  B = 32 @192x192: the reduction kernels of the four fused BatchNorms go
-      // (act_bwd family 0.857 -> 0.750 ms) but the thin data gradients, which are epilogue-bound, pay for the scan
-      // (32->32 @192x192 53 -> 84 us, 64->64 @96x96 33 -> 46 us; conv3_dgrad 0.890 -> 0.977 ms): 5.286 vs 5.280 ms per step.
-      static const int bnr_fuse = tc_env_int("FU_BNR_FUSE", 0);
-      static const int coop_off = tc_env_int("FU_BN_COOP", 0) == 0;      // (the cooperative kernel does its own reduction)
-      const bool want = bn && bnr_fuse && coop_off && e->cfg.precision == FU_PRECISION_BF16;
-      if (want) {
-        BNL& bp = blk.bns[i - 1];
-        br.r = blk.r[i - 1].p; br.r_ld = blk.r[i - 1].ld; br.mean = bp.mean; br.invstd = bp.invstd; br.out = bp.bstat; br.copy_stride = 2 * bp.C;
-      }
-      if ((rc = conv_dgrad<T>(e, cw, blk.dy[i], blk.dz[i], B, H, W, 0, nullptr, nullptr, want ? &br : nullptr, &reduced))) return rc;
+      if ((rc = conv_dgrad<T>(e, cw, blk.dy[i], blk.dz[i], B, H, W, 0))) return rc;
       d = blk.dz[i];
     } else if (d_in) {
       // the LAST writer of *d_in also sums it per channel: that is the bias gradient of the up / downsample conv

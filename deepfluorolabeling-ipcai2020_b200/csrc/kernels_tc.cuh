@@ -1028,40 +1028,6 @@ __device__ __forceinline__ void tc_stats_scan(const uint8_t* tile, uint32_t sub_
   }
 }
 
-// The same scan with a second operand: acc[sub] = {sum d even ch, odd ch, sum d * (r - mean) even, odd}; d from the bf16
-// staging tile, r from a shared-memory tile of the same layout (the TMA producer loaded it through a map with the output's
-// box geometry; what lies outside the image is zero in both).
-template <int PITCH>
-__device__ __forceinline__ void tc_bnr_scan(const uint8_t* tile, const uint8_t* rtile, uint32_t sub_bytes, int nsub, int CS, int q,
-                                            int lane, float (&acc)[4][4], const float* mean_nb) {
-  constexpr int RPL = 128 / PITCH;
-  constexpr int CPW = PITCH / 4;
-  constexpr uint32_t SMASK = PITCH == 128 ? 7u : 3u;
-  const uint32_t base = (uint32_t)(32 * q + lane / CPW) * PITCH + (uint32_t)(lane % CPW) * 4u;
-#pragma unroll
-  for (int sub = 0; sub < 4; ++sub) {
-    if (sub < nsub) {
-      const uint8_t* tp = tile + (uint32_t)sub * sub_bytes;
-      const uint8_t* rp = rtile + (uint32_t)sub * sub_bytes;
-      const int ch = sub * CS + 2 * (lane % CPW);
-      const float mu0 = mean_nb[ch], mu1 = mean_nb[ch + 1];
-      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll 1
-      for (int i0 = 0; i0 < 32 / RPL; i0 += 8) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t off = (base ^ (((uint32_t)k & SMASK) << 4)) + (uint32_t)(i0 + k) * 128u;
-          const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tp + off));
-          const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rp + off));
-          a0 += d2.x; a1 += d2.y;
-          b0 = fmaf(d2.x, r2.x - mu0, b0); b1 = fmaf(d2.y, r2.y - mu1, b1);
-        }
-      }
-      acc[sub][0] += a0; acc[sub][1] += a1; acc[sub][2] += b0; acc[sub][3] += b1;
-    }
-  }
-}
-
 struct TcConv3Params {
   int B, H, W, K, N;
   int KC, BN, CS;
@@ -1094,16 +1060,6 @@ struct TcConv3Params {
   FastDiv fd_ntiles, fd_timg, fd_tw;   // divisions by n_tiles, tiles_w * tiles_h, tiles_w (tile decode, every role, every tile)
   int cs_shift;                 // log2(CS)
   int baton_kh;                 // filter row (0..2) of a super tile's last section at which the issuer passes the baton
-  // BatchNorm-backward reduction fused into the data gradient that PRODUCES the BatchNorm's output gradient (dir 1, bf16):
-  // per channel  sum dz  and  sum dz * (r - mean) * invstd  over the stored tile, added into the [copies][2][N] fp64
-  // accumulators the BN apply kernel reads (bn_bwd_reduce_kernel's output format), so that kernel's pass over dz and r
-  // (two tensor reads and a launch per BatchNorm) is replaced by one read of r here.  bnr_r == nullptr: off.
-  const bf16* bnr_r; int bnr_ld;
-  const float* bnr_mean; const float* bnr_invstd;
-  double* bnr_out; int bnr_copy_stride;
-  int bnr_buf;                  // shared memory holds one r tile per epilogue group (map tmR, loaded by the TMA producer one super
-                                // tile ahead, laid out like the staging tile): the epilogue threads' own 4-byte global loads of r
-                                // put two memory latencies into every tile and doubled the thin data gradients (53 -> 109 us)
   int planeC;                   // > 0: the output is PLANAR -- channels [k*planeC, (k+1)*planeC) form a contiguous (pixels, planeC)
                                 // tensor k (5-D store map with the plane index as its last coordinate); CS == planeC
 };
@@ -1116,7 +1072,7 @@ template <int S, bool F32 = false>
 __global__ void __launch_bounds__(96 + 256 * S, 1)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmR, const TcConv3Params p) {
+                const __grid_constant__ CUtensorMap tmB2, const TcConv3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t smem_base = (raw + 1023u) & ~1023u;
@@ -1149,8 +1105,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int nstg = p.nstg;
   const uint32_t staging_bytes = F32 ? 32768u : (uint32_t)nstg * tile_bytes;      // per epilogue group
   constexpr int NACC = 2 * S;              // TMEM accumulator stages (each: npair tiles of BN columns)
-  const uint32_t rbuf_off = staging_off + (uint32_t)(S * p.npair) * staging_bytes;  // (bnr_buf) one r tile per epilogue group
-  const uint32_t vec_off = rbuf_off + (p.bnr_buf ? (uint32_t)(S * p.npair) * tile_bytes : 0u);   // bias | bn_a | bn_b, [3][N] floats
+  const uint32_t vec_off = staging_off + (uint32_t)(S * p.npair) * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
   // statistics partials per epilogue group (tc3_park_floats): F32 [4][2][BN] floats; bf16 one float4 per (thread, sub-box)
   const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;
   // (bf16: the partials are parked in the group's own staging tile at flush time, no separate region)
@@ -1165,8 +1120,6 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto t_empty = [&](int a) { return bar_base + 8u * (uint32_t)(36 + a); };
   const uint32_t res_bar = bar_base + 8u * 40u;
   auto baton_bar = [&](int x) { return bar_base + 8u * (uint32_t)(42 + x); };
-  auto r_full = [&](int g) { return bar_base + 8u * (uint32_t)(44 + g); };       // r tiles: one per epilogue group (<= 4)
-  auto r_empty = [&](int g) { return bar_base + 8u * (uint32_t)(48 + g); };
   const uint32_t slot_addr = bar_base + 8u * 41u;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * 41u);
   uint32_t tmem_cols = 32;
@@ -1180,9 +1133,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int a = 0; a < NACC; ++a) { ptx::mbar_init(t_full(a), 1); ptx::mbar_init(t_empty(a), 128u * (uint32_t)p.npair); }
     ptx::mbar_init(res_bar, 1);
     ptx::mbar_init(baton_bar(0), 1); ptx::mbar_init(baton_bar(1), 1);
-    for (int g = 0; g < 4; ++g) { ptx::mbar_init(r_full(g), 1); ptx::mbar_init(r_empty(g), 128); }
     ptx::fence_barrier_init();
-    if (p.bnr_buf) ptx::prefetch_tmap(&tmR);
     ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmB); ptx::prefetch_tmap(&tmC);
     if (p.res) { ptx::prefetch_tmap(&tmA2); ptx::prefetch_tmap(&tmB2); }
   }
@@ -1194,18 +1145,17 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* vec = reinterpret_cast<float*>(smem + vec_off);
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
       vec[i] = p.bias ? p.bias[i] : 0.f;
-      vec[p.N + i] = p.bnr_r ? p.bnr_mean[i] : (p.bn_a ? p.bn_a[i] : 1.f);     // (bnr: the BatchNorm's batch means ride in the unused slot)
+      vec[p.N + i] = p.bn_a ? p.bn_a[i] : 1.f;
       vec[2 * p.N + i] = p.bn_a ? p.bn_b[i] : 0.f;
     }
     if (F32) {
       float* park = reinterpret_cast<float*>(smem + stat_off);
       for (int i = threadIdx.x; i < S * p.npair * (int)park_floats; i += blockDim.x) park[i] = 0.f;
-    } else if (p.stat || p.bnr_r) {
+    } else if (p.stat) {
       // rows of the staging tiles that no valid pixel maps to are never written: they must read as zeros in the
       // statistics scan
-      // (likewise the r tiles behind them: TMA only ever writes the box rows, and 0 x stale NaN would poison the sums)
       uint4* z = reinterpret_cast<uint4*>(smem + staging_off);
-      for (int i = threadIdx.x; i < (int)((vec_off - staging_off) / 16u); i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = threadIdx.x; i < (int)((uint32_t)(S * p.npair) * staging_bytes / 16u); i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   ptx::tc_fence_before();
@@ -1470,14 +1420,13 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 4; ++i) { sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f; }
       int s_nb = -1;
-      uint32_t rph = 0;                             // phase of this group's r tile barrier (bnr_buf)
       int sbuf = 0;                                 // staging buffer of the next tile (bf16, BN <= 64: double buffered)
       // Deterministic flush: every thread parks its partial sums, then one thread per (statistic, channel) adds the
       // partials of the 4 warps (and, for 64-byte rows, of the two lanes that share a column pair) in a fixed order.
       // Float atomics here would make BN statistics differ by ~1e-7 run to run, which bf16 rounding + the network
       // amplify into visibly different gradients (tools/diag_repeat2.py).
       auto flush_stats = [&]() {
-        if ((p.stat || p.bnr_r) && s_nb >= 0) {
+        if (p.stat && s_nb >= 0) {
           // the partials are parked in this group's staging tile ([128 threads][nsub][4] floats <= 4 KB of its >= 8 KB):
           // a flush happens once per CTA (or per N tile), and a dedicated region cost 8-16 KB of shared memory that
           // some layers need for their fourth operand stage (and with it the second MMA issuer)
@@ -1500,10 +1449,6 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int w = 0; w < 4; ++w)
               for (int ro = 0; ro < rpl; ++ro)
                 v += park[((w * 32 + ro * cpw + (cc >> 1)) * nsub + sub) * 4 + comp];
-            if (p.bnr_r)       // [sum dz | sum dz * xhat] into this CTA's copy of the BatchNorm's backward accumulators
-              atomicAdd(p.bnr_out + (size_t)(blockIdx.x % kRedCopies) * p.bnr_copy_stride + which * p.N + s_nb + c,
-                        (double)(which ? v * p.bnr_invstd[s_nb + c] : v));
-            else
             atomicAdd(p.stat + which * p.N + s_nb + c, (double)v);
           }
           ptx::named_bar_sync(bar_id, 128);
@@ -1514,22 +1459,6 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::named_bar_sync(bar_id, 128);
         }
       };
-      // (bnr) this group fetches its own r tiles, one tile ahead: the load of tile i + 1 is issued right after the scan of
-      // tile i has released the buffer, a whole super-tile period before it is needed -- the producer warp must not wait for
-      // epilogue progress (it did in a first version and lost its run-ahead: 53 -> 110 us)
-      auto load_r = [&](int st_) {
-        int nt_, sp_;
-        p.fd_ntiles.divmod(st_, sp_, nt_);
-        const int mt_ = sp_ * p.npair + grp;
-        if (mt_ >= m_tiles) return;
-        int w0_, h0_, n_;
-        decode_m(mt_, w0_, h0_, n_);
-        const uint32_t dst = smem_base + rbuf_off + (uint32_t)gi * tile_bytes;
-        ptx::mbar_expect_tx(r_full(gi), (uint32_t)(p.two * p.th) * (uint32_t)p.BN * 2u);
-        for (int s2 = 0; s2 < p.BN / p.CS; ++s2)
-          ptx::tma_load_4d(dst + (uint32_t)s2 * sub_bytes, &tmR, r_full(gi), nt_ * p.BN + s2 * p.CS, w0_, h0_, n_);
-      };
-      if (p.bnr_r && et == 0 && blockIdx.x + set * (int)gridDim.x < total_super) load_r(blockIdx.x + set * (int)gridDim.x);
       for (int st = blockIdx.x + set * (int)gridDim.x; st < total_super; st += S * (int)gridDim.x) {
         int nt, sp;
         p.fd_ntiles.divmod(st, sp, nt);
@@ -1630,7 +1559,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           acc += S; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
           continue;
         }
-        if ((p.stat || p.bnr_r) && nb != s_nb) { flush_stats(); s_nb = nb; }
+        if (p.stat && nb != s_nb) { flush_stats(); s_nb = nb; }
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
         uint8_t* stg = staging + (uint32_t)sbuf * tile_bytes;
         const uint32_t stg_addr = staging_addr + (uint32_t)sbuf * tile_bytes;
@@ -1736,14 +1665,6 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // per-channel sum / sum of squares of the stored (bf16) tile; rows no pixel maps to hold zeros
             if (pitch == 128) tc_stats_scan<128>(stg, sub_bytes, nsub, q, lane, sacc);
             else tc_stats_scan<64>(stg, sub_bytes, nsub, q, lane, sacc);
-          } else if (p.bnr_r) {
-            const uint8_t* rt = smem + rbuf_off + (uint32_t)gi * tile_bytes;
-            ptx::mbar_wait(r_full(gi), rph);
-            if (pitch == 128) tc_bnr_scan<128>(stg, rt, sub_bytes, nsub, p.CS, q, lane, sacc, vec + p.N + nb);
-            else tc_bnr_scan<64>(stg, rt, sub_bytes, nsub, p.CS, q, lane, sacc, vec + p.N + nb);
-            rph ^= 1u;
-            ptx::named_bar_sync(bar_id, 128);        // every thread of the group is done with the r tile
-            if (et == 0 && st + S * (int)gridDim.x < total_super) load_r(st + S * (int)gridDim.x);
           }
           if (nstg == 1) {
             if (et == 0) ptx::tma_store_wait_read();   // staging may be overwritten after this
@@ -2505,7 +2426,6 @@ struct TcConv {
   struct Cached3 {
     const void *x, *y, *x2; int x_ld, y_ld, x2_ld, B, H, W, dir;     // x2: second source of the fused residual dgrad (or null)
     CUtensorMap a, b, c, a2, b2; TcConv3Params p; int grid; size_t smem; int S; int f32;
-    CUtensorMap rmap; const void* r_ptr; int r_ld;       // r tiles of the fused BatchNorm-backward reduction (bnr_buf)
   };
   std::vector<Cached3> cache3;
   struct Cached {
@@ -2848,10 +2768,10 @@ inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
 // res / x2: (dir 1 only) the block's 1x1 shortcut and the gradient G of the block output: dX = conv3x3^T(x) + conv1x1^T(x2)
 inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld, void* y, int y_ld, int B, int H, int W,
                                      const TcConv* res = nullptr, const void* x2 = nullptr, int x2_ld = 0,
-                                     long long y_plane = 0, int y_planeC = 0, int bnr_buf = 0) {
+                                     long long y_plane = 0, int y_planeC = 0) {
   for (auto& c : t.cache3)
     if (c.x == x && c.y == y && c.x_ld == x_ld && c.y_ld == y_ld && c.B == B && c.H == H && c.W == W && c.dir == dir &&
-        c.x2 == x2 && c.x2_ld == x2_ld && c.p.planeC == y_planeC && c.p.bnr_buf == bnr_buf)
+        c.x2 == x2 && c.x2_ld == x2_ld && c.p.planeC == y_planeC)
       return &c;
   TcConv::Cached3 c;
   memset(&c, 0, sizeof(c));
@@ -2905,11 +2825,9 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   if (want_S == 2 && want_nstg == 2) { cand[ncand][0] = 2; cand[ncand++][1] = 1; }
   if (want_S == 2) { cand[ncand][0] = 1; cand[ncand++][1] = want_nstg; }
   if (want_S != 1 || want_nstg != 1) { cand[ncand][0] = 1; cand[ncand++][1] = 1; }
-  p.bnr_buf = bnr_buf;
   auto fixed_of = [&](int S_, int nstg_) {
     const size_t staging = t.split ? (size_t)S_ * p.npair * 32768 : (size_t)S_ * p.npair * 128 * p.BN * 2 * nstg_;
-    const size_t rbufs = bnr_buf ? (size_t)S_ * p.npair * 128 * p.BN * 2 : 0;      // one r tile per epilogue group
-    return 1024 + staging + rbufs + (size_t)12 * N + (t.split ? (size_t)S_ * p.npair * tc3_park_floats(p.BN, p.CS) * 4 : 0) + 16 + 8 * 56;
+    return 1024 + staging + (size_t)12 * N + (t.split ? (size_t)S_ * p.npair * tc3_park_floats(p.BN, p.CS) * 4 : 0) + 16 + 8 * 48;
   };
   // A stages one super tile consumes: with fewer than twice that many the two MMA issuers (and their baton) are off,
   // which costs more than a second staging tile gains (32->64 data gradient @192x192: 89 us with 4 stages and one staging
@@ -2977,7 +2895,7 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     int box[4] = {p.CS, p.two, p.th, 1};
     if (tc_make_map(&c.c, y, 4, dims, str, box, t.split ? 128 : p.CS * 2, t.split)) return nullptr;
   }
-  c.a2 = c.a; c.b2 = c.b; c.rmap = c.c; c.r_ptr = nullptr; c.r_ld = 0;
+  c.a2 = c.a; c.b2 = c.b;
   if (p.res) {
     long long dims[4] = {K + p.a2_lo, W, H, B};
     long long str[4] = {1, x2_ld, (long long)W * x2_ld, (long long)H * W * x2_ld};
@@ -3010,9 +2928,9 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
   }
   c->p.dbg = dbg ? dbg_buf : nullptr;
   const bool pdl = fu_pdl_enabled() && !dbg;
-  if (c->f32) fu_launch(tc_conv3_kernel<1, true>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->rmap, c->p);
-  else if (c->S == 2) fu_launch(tc_conv3_kernel<2, false>, dim3(c->grid), dim3(96 + 256 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->rmap, c->p);
-  else fu_launch(tc_conv3_kernel<1, false>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->rmap, c->p);
+  if (c->f32) fu_launch(tc_conv3_kernel<1, true>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else if (c->S == 2) fu_launch(tc_conv3_kernel<2, false>, dim3(c->grid), dim3(96 + 256 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else fu_launch(tc_conv3_kernel<1, false>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
   if (dbg) {
     long long h[4 * 24 * 4];
     cudaStreamSynchronize(stream);
@@ -3135,8 +3053,6 @@ inline int tc_conv_forward(TcConv& t, const void* x, int x_ld, void* y, int y_ld
   return tc_launch(c, stream, cnt);
 }
 
-// BatchNorm-backward reduction to fuse into a data gradient (TcConv3Params::bnr_*)
-struct TcBnReduce { const void* r; int r_ld; const float* mean; const float* invstd; double* out; int copy_stride; };
 inline bool tc_dgrad_eligible(const TcConv& t, const void* dy, int dy_ld, const void* dx, int dx_ld) {
   return t.enabled && tc_ptr_ok(dy, dy_ld) && (t.split ? tc_ptr_ok_f32(dx, dx_ld) : tc_ptr_ok(dx, dx_ld));
 }
@@ -3151,30 +3067,13 @@ inline bool tc_dgrad_can_fuse_res(const TcConv& t, const TcConv& res, int H, int
 }
 inline int tc_conv_dgrad(TcConv& t, const void* dy, int dy_ld, void* dx, int dx_ld, int B, int H, int W, int accumulate,
                          cudaStream_t stream, fu_counters* cnt, double* stat = nullptr, const TcConv* res = nullptr,
-                         const void* g = nullptr, int g_ld = 0, long long dx_plane = 0, int dx_planeC = 0,
-                         const TcBnReduce* bnr = nullptr, bool* bnr_done = nullptr) {
+                         const void* g = nullptr, int g_ld = 0, long long dx_plane = 0, int dx_planeC = 0) {
   if (dx_planeC && (!tc_use_v2(t, H, W) || accumulate)) { tc_err() = "planar output needs the halo kernel"; return -1; }
   if (tc_use_v2(t, H, W)) {
-    const bool want_bnr = bnr && !stat && !accumulate && !t.split && !dx_planeC && !res;    // (the statistics partials serve one purpose per launch)
-    TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W, res, g, g_ld, dx_plane, dx_planeC, want_bnr ? 1 : 0);
-    if (!c3 && want_bnr) c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W, res, g, g_ld, dx_plane, dx_planeC, 0);    // no room for the r tiles
+    TcConv::Cached3* c3 = tc_prepare3(t, 1, dy, dy_ld, dx, dx_ld, B, H, W, res, g, g_ld, dx_plane, dx_planeC);
     if (!c3 && dx_planeC) return -1;
     if (c3) {
       c3->p.bias = nullptr; c3->p.relu = 0; c3->p.stat = stat; c3->p.bn_a = nullptr; c3->p.bn_b = nullptr;
-      c3->p.bnr_r = nullptr;
-      if (want_bnr && c3->p.bnr_buf) {
-        if (c3->r_ptr != bnr->r || c3->r_ld != bnr->r_ld) {
-          const int N = t.Cin;
-          long long dims[4] = {N, W, H, B};
-          long long str[4] = {1, bnr->r_ld, (long long)W * bnr->r_ld, (long long)H * W * bnr->r_ld};
-          int box[4] = {c3->p.CS, c3->p.two, c3->p.th, 1};
-          if (tc_make_map(&c3->rmap, bnr->r, 4, dims, str, box, c3->p.CS * 2)) return -1;
-          c3->r_ptr = bnr->r; c3->r_ld = bnr->r_ld;
-        }
-        c3->p.bnr_r = reinterpret_cast<const bf16*>(bnr->r); c3->p.bnr_ld = bnr->r_ld; c3->p.bnr_mean = bnr->mean;
-        c3->p.bnr_invstd = bnr->invstd; c3->p.bnr_out = bnr->out; c3->p.bnr_copy_stride = bnr->copy_stride;
-        if (bnr_done) *bnr_done = true;
-      }
       tc_set_t(t, c3->p, accumulate ? dx : nullptr, dx_ld);
       return tc_launch3(c3, stream, cnt);
     }
