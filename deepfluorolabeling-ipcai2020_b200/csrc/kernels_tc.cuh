@@ -27,6 +27,9 @@
 // packed fp32x2 epilogue arithmetic (FADD2 / FFMA2): measured on the B200 and left off -- the thin 3x3 layers do not
 // change (32->32 @192x192 forward 63.6 vs 64.0 us) and the 1x1 layers with a second epilogue operand get slower
 // (64->32 @192x192: 98.7 -> 113 us), see gpurun A/B in DESIGN.md section 5
+#ifndef FU_TC_TIMELINE
+#define FU_TC_TIMELINE 0
+#endif
 #ifndef FU_EPI_PACKED
 #define FU_EPI_PACKED 0
 #endif
@@ -1163,10 +1166,16 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *slot_ptr;
 
+// (timeline stamps of CTA 0, FU_TC_DBG=1: compiled in only with -DFU_TC_TIMELINE=1 -- the checks sat in every role's per-tile
+//  path of a kernel whose two-set instantiation runs at its register cap)
+#if FU_TC_TIMELINE
 #define FU_DBG(role, idx, ev)                                                                       \
   do {                                                                                              \
     if (p.dbg && blockIdx.x == 0 && (idx) < 24) p.dbg[((role) * 24 + (idx)) * 4 + (ev)] = clock64(); \
   } while (0)
+#else
+#define FU_DBG(role, idx, ev) do { } while (0)
+#endif
   const int tiles_img = p.tiles_w * p.tiles_h;
   const int m_tiles = tiles_img * p.B;
   const int supers_m = (m_tiles + p.npair - 1) / p.npair;
@@ -1595,7 +1604,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const float2 r1 = fu_add2(make_float2(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])), make_float2(b4.z, b4.w));
               f[k] = r0.x; f[k + 1] = r0.y; f[k + 2] = r1.x; f[k + 3] = r1.y;
             }
-            if (p.t && valid) {
+            if (S < 2 && p.t && valid) {          // (the two-set instantiation runs at its register cap and does not carry this path)
               const bf16* tp = p.t + pix * p.t_ld + c0;
 #pragma unroll
               for (int k = 0; k < 32; k += 8) {
@@ -2929,7 +2938,7 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
   c->p.dbg = dbg ? dbg_buf : nullptr;
   const bool pdl = fu_pdl_enabled() && !dbg;
   if (c->f32) fu_launch(tc_conv3_kernel<1, true>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
-  else if (c->S == 2) fu_launch(tc_conv3_kernel<2, false>, dim3(c->grid), dim3(96 + 256 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else if (c->S == 2 && !c->p.t) fu_launch(tc_conv3_kernel<2, false>, dim3(c->grid), dim3(96 + 256 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
   else fu_launch(tc_conv3_kernel<1, false>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
   if (dbg) {
     long long h[4 * 24 * 4];
