@@ -1065,6 +1065,24 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     // paper heads (7 classes, 39 -> 21 -> 14): one fused pass
     const long long P = (long long)B * HW;
     const unsigned gridf = (unsigned)std::min<long long>((P + 255) / 256, (long long)e->num_sms * 4);   // 4 resident blocks/SM (126 regs)
+    if constexpr (sizeof(T) == 2) {
+      // bf16 storage: the two 1x1 products as warp-level tensor-core MMAs (heads_fwd_mma_kernel); FU_HEADS_MMA=0: CUDA cores
+      static const bool use_mma = tc_env_int("FU_HEADS_MMA", 1) != 0;
+      if (use_mma && P < (1ll << 30) && feat.ld % 8 == 0 && reinterpret_cast<uintptr_t>(feat.p) % 16 == 0) {
+        const unsigned gridm = (unsigned)std::min<long long>((P + 63) / 64, (long long)e->num_sms * 6);      // 6 resident blocks per SM (launch bounds)
+        if (c.num_lands == 14)
+          LAUNCH(e, (heads_fwd_mma_kernel<32, 7, 21, 14>), gridm, 128,
+                 reinterpret_cast<const bf16*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx),
+                 tdata(e, e->lands[1].w_idx), reinterpret_cast<bf16*>(lg.p), seg, logits, heat, (int)P, (int)HW, FastDiv((int)HW),
+                 c.do_soft_max);
+        else
+          LAUNCH(e, (heads_fwd_mma_kernel<32, 7, 1, 0>), gridm, 128,
+                 reinterpret_cast<const bf16*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), (const float*)nullptr,
+                 (const float*)nullptr, reinterpret_cast<bf16*>(lg.p), seg, logits, (float*)nullptr, (int)P, (int)HW,
+                 FastDiv((int)HW), c.do_soft_max);
+        return FU_OK;
+      }
+    }
     if (c.num_lands == 14)
       LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 21, 14>), gridf, 128,
              reinterpret_cast<const T*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx),

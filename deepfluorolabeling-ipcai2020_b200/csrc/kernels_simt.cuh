@@ -826,6 +826,166 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// --------------------------------------------------------------------------
+// Fused heads forward on the tensor cores (bf16 storage; the paper heads: 32 features, 7 classes, 39 -> 21 -> 14).
+// The CUDA-core kernel above spends 784 FMAs per pixel and ran at a quarter of its issue rate (109 us for 1.18 M pixels
+// against ~30 us of HBM time).  Here a warp owns 16-pixel tiles and the two small matrix products are warp-level
+// mma.sync.m16n8k16 over the features exactly as they are stored:
+//   * A (features): the contraction index may be permuted freely as long as A and B agree, so thread (g, t) of the warp
+//     takes channels 8t .. 8t+7 of pixels g and g + 8 -- ONE 16-byte load per pixel row feeds both K steps, and a warp
+//     instruction reads 8 x 64 contiguous bytes (every sector fully used);
+//   * B (weights): kept in registers for the whole persistent block as split bf16 pairs W = hi + lo (two MMAs per
+//     product), so the fp32 weights lose nothing to the bf16 operand format (~2^-17 relative);
+//   * the logits accumulator fragment of a tile IS the A fragment of the third K step of the landmark product
+//     (heat = W21 [feat ; logits]); the logits go in as hi + lo as well (three MMAs: hi*hi, hi*lo, lo*hi);
+//   * softmax over the 7 classes of a pixel = two xor-shuffles among the 4 threads that hold its row;
+//   * the fp32 NCHW outputs are written straight from the accumulator fragments: a warp store covers 4 planes x
+//     8 consecutive pixels = four fully written 32-byte sectors.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t heads_pack_hi(float a, float b, float& ra, float& rb) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  ra = a - __bfloat162float(ha); rb = b - __bfloat162float(hb);
+  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+__device__ __forceinline__ uint32_t heads_pack(float a, float b) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+
+template <int CF, int NC, int NF, int NL>
+__global__ void __launch_bounds__(128, 6) heads_fwd_mma_kernel(const bf16* __restrict__ feat, int ld, const float* wseg, const float* w1,
+                                                            const float* w2, bf16* logits_nhwc, float* seg, float* logits_out,
+                                                            float* heat, int P, int HW, FastDiv fd_hw, int do_softmax) {
+  pdl_wait(); pdl_trigger();
+  typedef HeadsDims<CF, NC, NF, NL> D;
+  static_assert(CF == 32 && NC <= 8 && NL <= 16, "fragment layout below: 32 features, <= 8 classes, <= 16 landmarks");
+  constexpr int NT = NL > 8 ? 2 : (NL > 0 ? 1 : 0);          // 8-column tiles of the landmark product
+  __shared__ __align__(16) float s_wseg[NC * CF];
+  __shared__ __align__(16) float s_w21[NL > 0 ? NL * D::NCATP : 4];
+  for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
+  heads_fold_w21<CF, NC, NF, NL>(w1, w2, s_w21);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // B fragments (hi | lo).  K step s of the feature part: logical k = 2t, 2t+1 | 2t+8, 2t+9  <->  channels 8t+4s .. 8t+4s+3
+  uint32_t bs_hi[2][2], bs_lo[2][2];                          // logits: [K step][b0 | b1], column n = g (class)
+  uint32_t bh_hi[NT > 0 ? NT : 1][3][2], bh_lo[NT > 0 ? NT : 1][3][2];   // landmarks: [N tile][K step (2: the logits)][b0 | b1]
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 8 * t + 4 * ks + 2 * h;
+      const float a = g < NC ? s_wseg[g * CF + c] : 0.f, b = g < NC ? s_wseg[g * CF + c + 1] : 0.f;
+      float ra, rb;
+      bs_hi[ks][h] = heads_pack_hi(a, b, ra, rb);
+      bs_lo[ks][h] = heads_pack(ra, rb);
+    }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int l = 8 * j + g;
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float a = 0.f, b = 0.f;
+        if (l < NL) {
+          if (ks < 2) { const int c = 8 * t + 4 * ks + 2 * h; a = s_w21[l * D::NCATP + c]; b = s_w21[l * D::NCATP + c + 1]; }
+          else if (h == 0) {                                  // logical k = class 2t, 2t+1 (padded columns of W21 hold zeros)
+            a = (2 * t) < NC ? s_w21[l * D::NCATP + CF + 2 * t] : 0.f;
+            b = (2 * t + 1) < NC ? s_w21[l * D::NCATP + CF + 2 * t + 1] : 0.f;
+          }
+        }
+        float ra, rb;
+        bh_hi[j][ks][h] = heads_pack_hi(a, b, ra, rb);
+        bh_lo[j][ks][h] = heads_pack(ra, rb);
+      }
+  }
+  const int warp_g = blockIdx.x * 4 + (threadIdx.x >> 5), nwarps = gridDim.x * 4;
+  const int ntiles = (P + 15) >> 4;
+  // (the feature rows of the warp's next tile are requested before the current tile is worked on)
+  auto load_rows = [&](int tile, uint4& q0, uint4& q1) {
+    const int r0 = tile * 16 + g, r1 = r0 + 8;
+    q0 = make_uint4(0u, 0u, 0u, 0u); q1 = q0;
+    if (r0 < P) q0 = *reinterpret_cast<const uint4*>(feat + (long long)r0 * ld + 8 * t);
+    if (r1 < P) q1 = *reinterpret_cast<const uint4*>(feat + (long long)r1 * ld + 8 * t);
+  };
+  uint4 nq0, nq1;
+  load_rows(warp_g, nq0, nq1);
+  for (int tile = warp_g; tile < ntiles; tile += nwarps) {
+    const int r0 = tile * 16 + g, r1 = r0 + 8;
+    const bool ok0 = r0 < P, ok1 = r1 < P;
+    const uint4 q0 = nq0, q1 = nq1;
+    load_rows(tile + nwarps, nq0, nq1);
+    const uint32_t a_k0[4] = {q0.x, q1.x, q0.y, q1.y}, a_k1[4] = {q0.z, q1.z, q0.w, q1.w};
+    float lg[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(lg, a_k0, bs_hi[0]); mma_bf16_16816(lg, a_k1, bs_hi[1]);
+    mma_bf16_16816(lg, a_k0, bs_lo[0]); mma_bf16_16816(lg, a_k1, bs_lo[1]);
+    // lg[0], lg[1]: pixel r0, classes 2t, 2t+1;  lg[2], lg[3]: pixel r1
+    const int n0 = fd_hw.div(ok0 ? r0 : 0), n1 = fd_hw.div(ok1 ? r1 : 0);
+    const int hw0 = (ok0 ? r0 : 0) - n0 * HW, hw1 = (ok1 ? r1 : 0) - n1 * HW;
+    const bool c0ok = 2 * t < NC, c1ok = 2 * t + 1 < NC;
+    if (logits_nhwc) {
+      if (c1ok) {
+        if (ok0) *reinterpret_cast<uint32_t*>(logits_nhwc + (long long)r0 * ld + 2 * t) = heads_pack(lg[0], lg[1]);
+        if (ok1) *reinterpret_cast<uint32_t*>(logits_nhwc + (long long)r1 * ld + 2 * t) = heads_pack(lg[2], lg[3]);
+      } else if (c0ok) {
+        if (ok0) logits_nhwc[(long long)r0 * ld + 2 * t] = __float2bfloat16_rn(lg[0]);
+        if (ok1) logits_nhwc[(long long)r1 * ld + 2 * t] = __float2bfloat16_rn(lg[2]);
+      }
+    }
+    float* seg0 = seg + ((long long)n0 * NC + 2 * t) * HW + hw0;
+    float* seg1 = seg + ((long long)n1 * NC + 2 * t) * HW + hw1;
+    if (logits_out) {
+      float* lo0 = logits_out + ((long long)n0 * NC + 2 * t) * HW + hw0;
+      float* lo1 = logits_out + ((long long)n1 * NC + 2 * t) * HW + hw1;
+      if (ok0 && c0ok) lo0[0] = lg[0];
+      if (ok0 && c1ok) lo0[HW] = lg[1];
+      if (ok1 && c0ok) lo1[0] = lg[2];
+      if (ok1 && c1ok) lo1[HW] = lg[3];
+    }
+    if (do_softmax) {
+      float m0 = fmaxf(c0ok ? lg[0] : -INFINITY, c1ok ? lg[1] : -INFINITY);
+      float m1 = fmaxf(c0ok ? lg[2] : -INFINITY, c1ok ? lg[3] : -INFINITY);
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      const float e00 = c0ok ? expf(lg[0] - m0) : 0.f, e01 = c1ok ? expf(lg[1] - m0) : 0.f;
+      const float e10 = c0ok ? expf(lg[2] - m1) : 0.f, e11 = c1ok ? expf(lg[3] - m1) : 0.f;
+      float s0 = e00 + e01, s1 = e10 + e11;
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float i0 = 1.f / s0, i1 = 1.f / s1;
+      if (ok0 && c0ok) seg0[0] = e00 * i0;
+      if (ok0 && c1ok) seg0[HW] = e01 * i0;
+      if (ok1 && c0ok) seg1[0] = e10 * i1;
+      if (ok1 && c1ok) seg1[HW] = e11 * i1;
+    } else {
+      if (ok0 && c0ok) seg0[0] = lg[0];
+      if (ok0 && c1ok) seg0[HW] = lg[1];
+      if (ok1 && c0ok) seg1[0] = lg[2];
+      if (ok1 && c1ok) seg1[HW] = lg[3];
+    }
+    if (NT > 0) {
+      // third K step: A = [logits | 0], hi + lo
+      float r00, r01, r10, r11;
+      const uint32_t al_hi[4] = {heads_pack_hi(c0ok ? lg[0] : 0.f, c1ok ? lg[1] : 0.f, r00, r01),
+                                 heads_pack_hi(c0ok ? lg[2] : 0.f, c1ok ? lg[3] : 0.f, r10, r11), 0u, 0u};
+      const uint32_t al_lo[4] = {heads_pack(r00, r01), heads_pack(r10, r11), 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float h4[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(h4, a_k0, bh_hi[j][0]); mma_bf16_16816(h4, a_k1, bh_hi[j][1]);
+        mma_bf16_16816(h4, a_k0, bh_lo[j][0]); mma_bf16_16816(h4, a_k1, bh_lo[j][1]);
+        mma_bf16_16816(h4, al_hi, bh_hi[j][2]); mma_bf16_16816(h4, al_hi, bh_lo[j][2]); mma_bf16_16816(h4, al_lo, bh_hi[j][2]);
+        const int l = 8 * j + 2 * t;
+        float* h0 = heat + ((long long)n0 * NL + l) * HW + hw0;
+        float* h1 = heat + ((long long)n1 * NL + l) * HW + hw1;
+        if (ok0 && l < NL) h0[0] = h4[0];
+        if (ok0 && l + 1 < NL) h0[HW] = h4[1];
+        if (ok1 && l < NL) h1[0] = h4[2];
+        if (ok1 && l + 1 < NL) h1[HW] = h4[3];
+      }
+    }
+  }
+}
+
 template <typename T, int CF, int NC, int NF, int NL>
 __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(const T* feat, int ld, const float* wseg, const float* w1,
                                                               const float* w2, const float* d_seg, const float* d_heat,

@@ -220,6 +220,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // true in exactly one lane of a fully converged warp.  Code guarded by it is known by the compiler to run
 // in a single thread, so tcgen05.mma / cp.async.bulk.tensor (which take uniform registers) are emitted as
@@ -1063,6 +1073,13 @@ struct TcConv3Params {
   FastDiv fd_ntiles, fd_timg, fd_tw;   // divisions by n_tiles, tiles_w * tiles_h, tiles_w (tile decode, every role, every tile)
   int cs_shift;                 // log2(CS)
   int baton_kh;                 // filter row (0..2) of a super tile's last section at which the issuer passes the baton
+  int stack;                    // 1: the three kw taps of a filter row are ONE MMA with N = 3 * BN (the resident weight tiles of a
+                                //    filter row are adjacent in shared memory, i.e. already one [3 * BN][KC] operand) against the
+                                //    kw = 0 view of the halo tile: accumulator block kw of box position m holds X[m + kh*twb] * W[kh][kw],
+                                //    and the epilogue forms out[m] = blk0[m] + blk1[m + 1] + blk2[m + 2] with two warp shuffles per
+                                //    column.  The A operand (128 rows re-read by every MMA whatever its N) is fetched three times
+                                //    less often.  Needs twb | 32 (valid columns never reach across a warp's 32 lanes), BN = 32.
+  int nacc;                     // TMEM accumulator stages (2 * S; S when stacked: 3 * BN columns per tile)
   int planeC;                   // > 0: the output is PLANAR -- channels [k*planeC, (k+1)*planeC) form a contiguous (pixels, planeC)
                                 // tensor k (5-D store map with the plane index as its last coordinate); CS == planeC
 };
@@ -1071,7 +1088,10 @@ struct TcConv3Params {
 // by set i % S from TMEM stage i % (2S).  The thin layers (BN <= 64: 18-72 MMAs per tile) are bound by the
 // epilogue's per-warp latency chain, not by the tensor pipe (FU_TC_DBG timeline: ~3600 cycles per super tile of
 // which the MMAs take 2000), so they run two sets.
-template <int S, bool F32 = false>
+// STK: the kw-stacked form (TcConv3Params::stack) -- a template parameter because the two-set instantiation runs at its
+// register cap: with the stacked epilogue merely compiled in, every other thin layer paid 120 instead of 32 bytes of spills
+// (same-box A/B of the whole step: 5.235 vs 5.194 ms).
+template <int S, bool F32 = false, bool STK = false>
 __global__ void __launch_bounds__(96 + 256 * S, 1)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
@@ -1107,7 +1127,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tile_bytes = 128u * (uint32_t)p.BN * 2u;
   const int nstg = p.nstg;
   const uint32_t staging_bytes = F32 ? 32768u : (uint32_t)nstg * tile_bytes;      // per epilogue group
-  constexpr int NACC = 2 * S;              // TMEM accumulator stages (each: npair tiles of BN columns)
+  const int NACC = p.nacc;                 // TMEM accumulator stages (each: npair tiles of acc_cols columns)
+  const uint32_t acc_cols = (uint32_t)p.BN * (STK ? 3u : 1u);
   const uint32_t vec_off = staging_off + (uint32_t)(S * p.npair) * staging_bytes;   // bias | bn_a | bn_b, [3][N] floats
   // statistics partials per epilogue group (tc3_park_floats): F32 [4][2][BN] floats; bf16 one float4 per (thread, sub-box)
   const uint32_t stat_off = vec_off + 3u * (uint32_t)p.N * 4u;
@@ -1126,7 +1147,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t slot_addr = bar_base + 8u * 41u;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8u * 41u);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(NACC * p.npair * p.BN)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(NACC * p.npair) * acc_cols) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 8; ++s) {
@@ -1295,11 +1316,11 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t bat_phase = 0; bool bat_first = mw == 0;
       int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_bf16((uint32_t)p.BN);
+      const uint32_t idesc1 = umma_idesc_bf16((uint32_t)p.BN);                 // one tap (and the 1x1 second source)
+      const uint32_t idesc = STK ? umma_idesc_bf16(3u * (uint32_t)p.BN) : idesc1;
       const uint64_t dbase = umma_desc_kmajor(0, row_bytes);
       const int ksteps = p.KC / 16;
       const int npair = p.npair, resident = p.resident, halo1 = p.halo1, a_stages = p.a_stages, b_stages = p.b_stages;
-      const uint32_t BNc = (uint32_t)p.BN;
       const uint32_t a_tile16 = p.a_tile_bytes >> 4, b16 = b_bytes >> 4;
       // offset (in 16-byte units) of a tap's view into the halo tile: kh image rows + kw pixels
       const uint32_t kh16 = ((uint32_t)p.twb * row_bytes) >> 4, kw16 = halo1 ? (row_bytes >> 4) : 0u;
@@ -1324,7 +1345,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 1);     // (dbg) accumulator free, before the fence
         ptx::tc_fence_after();
         if (lane == 0) FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 0);
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * npair) * BNc, d1 = d0 + BNc;
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * npair) * acc_cols, d1 = d0 + acc_cols;
         uint32_t accum = 0;                       // 0 only for the very first MMA into each accumulator
         for (int c = 0; c < cchunks; ++c) {
           for (int g = 0; g < groups; ++g) {
@@ -1342,7 +1363,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (c == 0 && g == 0) FU_DBG(0, (st - (int)blockIdx.x) / (int)gridDim.x, 2);   // (dbg) first MMA about to issue
                 const uint32_t b_lo0 = dlo + ((smem_base + b_off + (uint32_t)(w_index(c) * 9) * b_bytes) >> 4);
                 // (halo1: all nine taps; otherwise one A load per kw and only the taps with kw == g)
-                tc_mma_taps_resident(ksteps, d0, d1, two, a_lo0, a_tile16, b_lo0, b16, kh16, kw16, halo1 ? -1 : g, dhi, idesc, accum,
+                // (stacked: one N = 3 * BN MMA per filter row = the "taps with kw == 0" walk over three-tile-wide weight rows)
+                tc_mma_taps_resident(ksteps, d0, d1, two, a_lo0, a_tile16, b_lo0, b16, kh16, kw16, STK ? 0 : (halo1 ? -1 : g), dhi, idesc, accum,
                                      (use_baton && last_group) ? baton_bar(mw ^ 1) : 0u, p.baton_kh);
                 ptx::umma_commit(a_empty(as));
                 if (last_group) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
@@ -1386,9 +1408,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                : smem_base + b_off + (uint32_t)bs * b_bytes;
               const uint32_t b_lo = dlo + (b_addr >> 4);
               if (use_baton && c == cchunks - 1) ptx::mbar_arrive(baton_bar(mw ^ 1));     // last section of this super tile
-              if (ksteps == 4) tc_mma_tap<4>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
-              else if (ksteps == 2) tc_mma_tap<2>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
-              else tc_mma_tap<1>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc, accum);
+              // (stacked: into block 0 of the accumulator, which the epilogue reads unshifted)
+              if (ksteps == 4) tc_mma_tap<4>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc1, accum);
+              else if (ksteps == 2) tc_mma_tap<2>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc1, accum);
+              else tc_mma_tap<1>(d0, d1, two, a_lo, a_lo + a_tile16, b_lo, dhi, idesc1, accum);
               if (!resident) ptx::umma_commit(b_empty(bs));
               ptx::umma_commit(a_empty(as));
               if (c == cchunks - 1) { ptx::umma_commit(t_full(acc)); FU_DBG(1, (st - (int)blockIdx.x) / (int)gridDim.x, 2); }
@@ -1497,7 +1520,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             decode_m(mt, w0, h0, n);
             const bool valid = row_ok && (w0 + wq) < p.W && (h0 + hi) < p.H;
             const long long pix = ((long long)n * p.H + (h0 + hi)) * p.W + (w0 + wq);
-            const uint32_t t_base = tmem_base + (uint32_t)((acc * p.npair + grp) * p.BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_base = tmem_base + (uint32_t)(acc * p.npair + grp) * acc_cols + ((uint32_t)(q * 32) << 16);
             for (int j = 0; j < p.BN / 32; ++j) {
               uint32_t v[32];
               ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
@@ -1587,7 +1610,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (et == 0) FU_DBG(2 + grp, (st - (int)blockIdx.x) / (int)gridDim.x, 1);
         if (mt < m_tiles) {
           const long long pix = ((long long)n * p.H + (h0 + hi)) * p.W + (w0 + wq);
-          const uint32_t t_base = tmem_base + (uint32_t)((acc * p.npair + grp) * p.BN) + ((uint32_t)(q * 32) << 16);
+          const uint32_t t_base = tmem_base + (uint32_t)(acc * p.npair + grp) * acc_cols + ((uint32_t)(q * 32) << 16);
           // ReLU without a BatchNorm behind it is applied to the packed bf16 pairs (16 instead of 32 instructions per
           // chunk; rounding is monotonic and keeps zero, so relu(bf16(x)) == bf16(relu(x)))
           const bool relu_packed = p.relu && !p.post;
@@ -1595,6 +1618,21 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t v[32];
             ptx::tmem_ld32(t_base + (uint32_t)(j * 32), v);
             ptx::tmem_ld_wait();
+            if constexpr (STK) {
+              // out[m] = blk0[m] + blk1[m + 1] + blk2[m + 2]: box positions m + 1, m + 2 of a valid output column are lanes
+              // of the same warp (twb divides 32); the lanes whose neighbours would be another warp's are halo columns
+              uint32_t u[32];
+              ptx::tmem_ld32(t_base + (uint32_t)(p.BN + j * 32), u);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                v[k] = __float_as_uint(__uint_as_float(v[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[k]), 1));
+              ptx::tmem_ld32(t_base + (uint32_t)(2 * p.BN + j * 32), u);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                v[k] = __float_as_uint(__uint_as_float(v[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[k]), 2));
+            }
             const int c0 = nb + j * 32;
             float f[32];
 #pragma unroll
@@ -2759,8 +2797,11 @@ inline bool tc_use_v2(const TcConv& t, int H, int W) {
   return t.kind == 0 && t.k == 3 && W >= tc_env_int("FU_TC_V2_MINW", 48) && H >= 8 && tc_env_int("FU_TC_V2", 1) != 0;
 }
 
-inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
-  long long best = -1;
+// warp_rows: 0 any box width; 1 prefer a box width that divides a warp (16 / 32: what the kw-stacked MMAs need) when
+// that costs at most 4 % more tiles; 2 only such widths
+inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th, int warp_rows = 0) {
+  long long best = -1, best_w = -1, tiles_best = 0, tiles_w = 0;
+  int twb_w = 16, th_w = 8;
   twb = 16; th = 8;
   for (int a = 8; a <= 66; a += (halo1 ? 1 : 8)) {
     int b = 128 / a;
@@ -2770,8 +2811,10 @@ inline void tc_pick_halo_tile(int H, int W, bool halo1, int& twb, int& th) {
     if (two < 1) continue;
     const long long tiles = (long long)((W + two - 1) / two) * ((H + b - 1) / b);
     const long long key = tiles * 4096 + (long long)(b + 2) * a;
-    if (best < 0 || key < best) { best = key; twb = a; th = b; }
+    if (best < 0 || key < best) { best = key; twb = a; th = b; tiles_best = tiles; }
+    if ((a == 16 || a == 32) && (best_w < 0 || key < best_w)) { best_w = key; twb_w = a; th_w = b; tiles_w = tiles; }
   }
+  if (best_w >= 0 && (warp_rows == 2 || (warp_rows == 1 && tiles_w * 100 <= tiles_best * 104))) { twb = twb_w; th = th_w; }
 }
 
 // res / x2: (dir 1 only) the block's 1x1 shortcut and the gradient G of the block output: dX = conv3x3^T(x) + conv1x1^T(x2)
@@ -2805,7 +2848,16 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
   p.a2_lo = t.split ? x2_ld / 2 : 0; p.b2_lo = p.b_lo;
   p.halo1 = tc_env_int("FU_TC_HALO1", 1) ? 1 : 0;
   p.npair = tc_env_int("FU_TC_PAIR", 1) ? 2 : 1;
-  tc_pick_halo_tile(H, W, p.halo1 != 0, p.twb, p.th);
+  // (a layer that can run the kw-stacked MMAs -- 32 output columns, weights that will be resident -- prefers box widths 16 / 32)
+  const int stack_env = tc_env_int("FU_TC_STACK", 0);      // 0: off (default, see below), 1: K >= 64 layers, 2: every 32-column layer
+  // Measured (B = 32 @192x192, us per launch, stacked vs not): K = 64: forward 67.8 vs 78.6, data gradient 63.2 vs 73.7 (@96x96 19.3
+  // vs 25.4); K = 32: 64.2 vs 51.2 / 47.9 vs 43.1 -- with 18 MMAs per tile those layers are bound by their epilogue, which the
+  // stacked form makes heavier (three accumulator blocks to read, 64 shuffles per thread).  So: K >= 64 only (FU_TC_STACK=2: all).
+  // In the graph-replayed step the K >= 64 gains do not show (same-box A/B against the build without this code: 5.1589 vs 5.1582 ms
+  // per step), so the mode is opt-in.  What the experiment established: per-MMA cost of these kernels is ~40 + 1.2 * N cycles
+  // (N = 32: 55-75, N = 64: 100-150, N = 96 stacked: ~140), i.e. proportional to N, not dominated by re-reading the A rows.
+  const bool stack_cand = stack_env && p.halo1 && !t.split && p.BN == 32 && p.n_tiles == 1 && (K >= 64 || stack_env >= 2);
+  tc_pick_halo_tile(H, W, p.halo1 != 0, p.twb, p.th, stack_cand ? 2 : 0);
   p.two = p.twb - 2;
   p.tiles_w = (W + p.two - 1) / p.two; p.tiles_h = (H + p.th - 1) / p.th;
   p.fd_ntiles = FastDiv(p.n_tiles); p.fd_timg = FastDiv(p.tiles_w * p.tiles_h); p.fd_tw = FastDiv(p.tiles_w);
@@ -2867,6 +2919,9 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     p.b_stages = bs;
     c.smem = fixed + (size_t)p.a_stages * a_stage + (size_t)bs * b_bytes;
   }
+  // kw-stacked MMAs (TcConv3Params::stack): 32-column layers with resident weights whose box width divides a warp
+  p.stack = (p.resident && p.halo1 && !t.split && p.BN == 32 && (p.twb == 16 || p.twb == 32) && p.twb * p.th <= 128 && stack_cand && c.S == 2) ? 1 : 0;
+  p.nacc = p.stack ? 2 : 2 * c.S;
   const long long m_tiles = (long long)p.tiles_w * p.tiles_h * B;
   const long long total_super = (m_tiles + p.npair - 1) / p.npair * p.n_tiles;
   int dev = 0, sms = 148;
@@ -2915,6 +2970,10 @@ inline TcConv::Cached3* tc_prepare3(TcConv& t, int dir, const void* x, int x_ld,
     int wb[3] = {p.KC, 1, p.BN};
     if (tc_make_map(&c.b2, res->w_dgrad, 3, wd, ws, wb, p.KC * 2)) return nullptr;      // [Cin][1][Cout] of the 1x1
   }
+  if (tc_env_int("FU_TC_VERBOSE", 0))
+    fprintf(stderr, "[tc_conv3] dir %d B %d %dx%d K %d N %d: KC %d BN %d box %dx%d (valid %dx%d) tiles %lld S %d nstg %d resident %d a_stages %d "
+            "b_stages %d dual %d stack %d nacc %d res %d grid %d smem %zu\n", dir, B, H, W, K, N, p.KC, p.BN, p.twb, p.th + 2, p.two, p.th,
+            m_tiles, c.S, p.nstg, p.resident, p.a_stages, p.b_stages, p.dual, p.stack, p.nacc, p.res, c.grid, (size_t)c.smem);
   t.cache3.push_back(c);
   return &t.cache3.back();
 }
@@ -2924,6 +2983,7 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
   if (tc_attr_needed(attr_done)) {
     if (cudaFuncSetAttribute(tc_conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_conv3_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(tc_conv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       tc_err() = "cudaFuncSetAttribute(max dynamic smem, conv3) failed";
       return -1;
@@ -2938,6 +2998,7 @@ inline int tc_launch3(TcConv::Cached3* c, cudaStream_t stream, fu_counters* cnt)
   c->p.dbg = dbg ? dbg_buf : nullptr;
   const bool pdl = fu_pdl_enabled() && !dbg;
   if (c->f32) fu_launch(tc_conv3_kernel<1, true>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
+  else if (c->S == 2 && !c->p.t && c->p.stack) fu_launch(tc_conv3_kernel<2, false, true>, dim3(c->grid), dim3(96 + 256 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
   else if (c->S == 2 && !c->p.t) fu_launch(tc_conv3_kernel<2, false>, dim3(c->grid), dim3(96 + 256 * 2), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
   else fu_launch(tc_conv3_kernel<1, false>, dim3(c->grid), dim3(96 + 256), c->smem, stream, pdl, c->a, c->b, c->c, c->a2, c->b2, c->p);
   if (dbg) {

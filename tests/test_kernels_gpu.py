@@ -208,7 +208,10 @@ HALO_SHAPES = [  # B, Cin, Cout, H, W  -- 3x3 convs wide enough for the halo ker
 ]
 
 
-@pytest.mark.parametrize("env", [{}, {"FU_TC_HALO1": "0"}, {"FU_TC_PAIR": "0"}, {"FU_TC_RESIDENT": "0"}])
+# FU_TC_STACK=2: every 32-column layer takes box widths 16 / 32 and with them the kw-stacked MMAs (N = 96, partial sums
+# shifted together by warp shuffles in the epilogue); 0: never
+@pytest.mark.parametrize("env", [{}, {"FU_TC_HALO1": "0"}, {"FU_TC_PAIR": "0"}, {"FU_TC_RESIDENT": "0"}, {"FU_TC_STACK": "2"},
+                                 {"FU_TC_STACK": "2", "FU_TC_EPI_SETS": "1"}, {"FU_TC_STACK": "0"}])
 @pytest.mark.parametrize("shape", HALO_SHAPES)
 def test_tc_halo_conv_fwd_dgrad(pkg, shape, env):
     """Second-generation 3x3 kernel (one halo load per chunk, taps = row-shifted descriptor views, paired
