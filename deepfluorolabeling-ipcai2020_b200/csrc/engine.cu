@@ -1067,7 +1067,7 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
     const unsigned gridf = (unsigned)std::min<long long>((P + 255) / 256, (long long)e->num_sms * 4);   // 4 resident blocks/SM (126 regs)
     if constexpr (sizeof(T) == 2) {
       // bf16 storage: the two 1x1 products as warp-level tensor-core MMAs (heads_fwd_mma_kernel); FU_HEADS_MMA=0: CUDA cores
-      static const bool use_mma = tc_env_int("FU_HEADS_MMA", 1) != 0;
+      const bool use_mma = tc_env_int("FU_HEADS_MMA", 1) != 0;
       if (use_mma && P < (1ll << 30) && feat.ld % 8 == 0 && reinterpret_cast<uintptr_t>(feat.p) % 16 == 0) {
         const unsigned gridm = (unsigned)std::min<long long>((P + 63) / 64, (long long)e->num_sms * 6);      // 6 resident blocks per SM (launch bounds)
         if (c.num_lands == 14)
@@ -1374,7 +1374,31 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
     CUDA_TRY(e, cudaMemsetAsync(e->heads_gacc, 0, gbytes, e->stream));
     // resident blocks per SM: 3 with the landmark head (168 registers, 64.5 KB), 2 without (255 registers)
     const unsigned gridh = (unsigned)std::min<long long>((P0 + 255) / 256, (long long)e->num_sms * (c.num_lands == 14 ? 3 : 2));
-    if (c.num_lands == 14) {
+    bool heads_done = false;
+    if constexpr (sizeof(T) == 2) {
+      // bf16 storage: every product of the heads' backward as warp-level tensor-core MMAs (heads_bwd_mma_kernel)
+      const bool use_mma = tc_env_int("FU_HEADS_MMA", 1) != 0;
+      if (use_mma && P0 < (1ll << 30) && feat.ld % 8 == 0 && d_feat.ld % 8 == 0 && reinterpret_cast<uintptr_t>(feat.p) % 16 == 0 &&
+          reinterpret_cast<uintptr_t>(d_feat.p) % 16 == 0) {
+        const unsigned gridm = (unsigned)std::min<long long>((P0 + 63) / 64, (long long)e->num_sms * 3);
+        if (c.num_lands == 14) {
+          LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 21, 14>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
+                 tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,
+                 reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max);
+          LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
+                 gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
+        } else {
+          LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 1, 0>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
+                 tdata(e, e->seg.w_idx), (const float*)nullptr, (const float*)nullptr, d_seg, (const float*)nullptr,
+                 reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max);
+          LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
+                 gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0);
+        }
+        heads_done = true;
+      }
+    }
+    if (heads_done) {
+    } else if (c.num_lands == 14) {
       LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, (sizeof(T) == 2 ? heads_bwd_smem_bytes_mma<32, 7, 21, 14>() : heads_bwd_smem_bytes<32, 7, 21, 14>()), reinterpret_cast<const T*>(feat.p), feat.ld,
              tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,
              reinterpret_cast<T*>(d_feat.p), d_feat.ld, e->heads_gacc, B, HW, c.do_soft_max);

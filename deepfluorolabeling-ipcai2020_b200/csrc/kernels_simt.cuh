@@ -1249,6 +1249,235 @@ __global__ void __launch_bounds__(128, NL > 0 ? 3 : 2) heads_bwd_fused_kernel(co
   }
 }
 
+// --------------------------------------------------------------------------
+// Fused heads backward on the tensor cores (bf16 storage), the counterpart of heads_fwd_mma_kernel: a warp owns 16-pixel
+// tiles and every product is a warp-level mma.sync.m16n8k16 on fragments that never leave registers:
+//   logits  = feat Wseg^T                       (recomputed; split-bf16 weights)
+//   dcat    = dheat W21                         (A = dheat hi + lo, loaded from the fp32 NCHW planes in fragment order)
+//   dlg     = dcat[CF:] + softmax'(dseg)        (accumulator-fragment layout: a pixel's classes sit in 4 neighbouring lanes)
+//   dfeat   = dcat[:CF] + dlg Wseg              (the dlg fragment is the A operand; output columns are permuted so a thread
+//                                                ends up with 8 contiguous channels of a pixel = one 16-byte store)
+//   G1  += dheat^T [feat ; logits],  Gseg += dlg^T feat   (K = the tile's 16 pixels: `movmatrix.trans` turns the 8x8
+//                                                blocks of the fragments above into the transposed operands; bf16 single
+//                                                pass like the ldmatrix version in heads_bwd_fused_kernel)
+// The CUDA-core kernel spent ~1000 FMAs per pixel plus a shared-memory round trip of every per-pixel vector (164 us for
+// 1.18 M pixels against ~40 us of HBM time).
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+// accumulate with a B fragment whose second half (k = 8 .. 15) is zero
+__device__ __forceinline__ void mma_bf16_16816_b0(float (&c)[4], const uint32_t (&a)[4], uint32_t b0) {
+  const uint32_t b[2] = {b0, 0u};
+  mma_bf16_16816(c, a, b);
+}
+
+template <int CF, int NC, int NF, int NL>
+__global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __restrict__ feat, int ld, const float* wseg, const float* w1,
+                                                               const float* w2, const float* __restrict__ d_seg,
+                                                               const float* __restrict__ d_heat, bf16* d_feat, int d_ld,
+                                                               float* g_acc /*[NL*(CF+NC) + NC*CF]*/, int P, int HW, FastDiv fd_hw,
+                                                               int do_softmax) {
+  pdl_wait(); pdl_trigger();
+  typedef HeadsDims<CF, NC, NF, NL> D;
+  static_assert(CF == 32 && NC <= 8 && NL <= 16, "fragment layout below: 32 features, <= 8 classes, <= 16 landmarks");
+  constexpr int NCAT = D::NCAT, NCATP = D::NCATP;
+  constexpr bool kL = NL > 0;
+  constexpr int NG1 = kL ? NL * NCAT : 0, NG = NG1 + NC * CF;
+  __shared__ __align__(16) float s_wseg[NC * CF];
+  __shared__ __align__(16) float s_w21[kL ? NL * NCATP : 4];
+  __shared__ float s_g[NG];
+  for (int i = threadIdx.x; i < NC * CF; i += blockDim.x) s_wseg[i] = wseg[i];
+  for (int i = threadIdx.x; i < NG; i += blockDim.x) s_g[i] = 0.f;
+  heads_fold_w21<CF, NC, NF, NL>(w1, w2, s_w21);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // ---- weight fragments (hi | lo), resident in registers ----
+  uint32_t bl_hi[2][2], bl_lo[2][2];                 // logits: K = features (permuted: step s, half h <-> channels 8t+4s+2h ..), n = class g
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 8 * t + 4 * ks + 2 * h;
+      const float a = g < NC ? s_wseg[g * CF + c] : 0.f, b = g < NC ? s_wseg[g * CF + c + 1] : 0.f;
+      float ra, rb;
+      bl_hi[ks][h] = heads_pack_hi(a, b, ra, rb);
+      bl_lo[ks][h] = heads_pack(ra, rb);
+    }
+  // output columns of the dfeat tiles: column n = g of tile j <-> channel 8 (g / 2) + 2 j + (g & 1), so that a thread's
+  // accumulator columns 2t, 2t+1 of tiles 0..3 are channels 8t .. 8t+7
+  uint32_t bd_hi[kL ? 5 : 1][2], bd_lo[kL ? 5 : 1][2];   // dcat: K = landmark, n = cat column (tile 4: class g)
+  if (kL) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int col = j < 4 ? 8 * (g >> 1) + 2 * j + (g & 1) : CF + g;
+      const bool cok = j < 4 || g < NC;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int l = 2 * t + 8 * h;
+        const float a = (cok && l < NL) ? s_w21[l * NCATP + col] : 0.f, b = (cok && l + 1 < NL) ? s_w21[(l + 1) * NCATP + col] : 0.f;
+        float ra, rb;
+        bd_hi[j][h] = heads_pack_hi(a, b, ra, rb);
+        bd_lo[j][h] = heads_pack(ra, rb);
+      }
+    }
+  }
+  uint32_t bf_hi[4], bf_lo[4];                       // dfeat += dlg Wseg: K = class (b1 = 0), n = channel as above
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = 8 * (g >> 1) + 2 * j + (g & 1);
+    const float a = (2 * t) < NC ? s_wseg[(2 * t) * CF + col] : 0.f, b = (2 * t + 1) < NC ? s_wseg[(2 * t + 1) * CF + col] : 0.f;
+    float ra, rb;
+    bf_hi[j] = heads_pack_hi(a, b, ra, rb);
+    bf_lo[j] = heads_pack(ra, rb);
+  }
+  // ---- weight-gradient accumulators: G1 tiles (s, h) = features 8t+4s+2h.., tile 4 = logits; Gseg tiles (s, h) ----
+  float g1[kL ? 5 : 1][4], gs[4][4];
+#pragma unroll
+  for (int j = 0; j < (kL ? 5 : 1); ++j) g1[j][0] = g1[j][1] = g1[j][2] = g1[j][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) gs[j][0] = gs[j][1] = gs[j][2] = gs[j][3] = 0.f;
+
+  const int warp_g = blockIdx.x * 4 + (threadIdx.x >> 5), nwarps = gridDim.x * 4;
+  const int ntiles = (P + 15) >> 4;
+  auto load_rows = [&](int tile, uint4& q0, uint4& q1) {
+    const int r0 = tile * 16 + g, r1 = r0 + 8;
+    q0 = make_uint4(0u, 0u, 0u, 0u); q1 = q0;
+    if (r0 < P) q0 = *reinterpret_cast<const uint4*>(feat + (long long)r0 * ld + 8 * t);
+    if (r1 < P) q1 = *reinterpret_cast<const uint4*>(feat + (long long)r1 * ld + 8 * t);
+  };
+  uint4 nq0, nq1;
+  load_rows(warp_g, nq0, nq1);
+  const bool c0ok = 2 * t < NC, c1ok = 2 * t + 1 < NC;
+  for (int tile = warp_g; tile < ntiles; tile += nwarps) {
+    const int r0 = tile * 16 + g, r1 = r0 + 8;
+    const bool ok0 = r0 < P, ok1 = r1 < P;
+    const uint4 q0 = nq0, q1 = nq1;
+    load_rows(tile + nwarps, nq0, nq1);
+    const int n0 = fd_hw.div(ok0 ? r0 : 0), n1 = fd_hw.div(ok1 ? r1 : 0);
+    const int hw0 = (ok0 ? r0 : 0) - n0 * HW, hw1 = (ok1 ? r1 : 0) - n1 * HW;
+    // upstream gradients in fragment order (a warp load covers 4 planes x 8 consecutive pixels)
+    float ds[4] = {0.f, 0.f, 0.f, 0.f};
+    if (d_seg) {
+      const float* p0 = d_seg + ((long long)n0 * NC + 2 * t) * HW + hw0;
+      const float* p1 = d_seg + ((long long)n1 * NC + 2 * t) * HW + hw1;
+      if (ok0 && c0ok) ds[0] = p0[0];
+      if (ok0 && c1ok) ds[1] = p0[HW];
+      if (ok1 && c0ok) ds[2] = p1[0];
+      if (ok1 && c1ok) ds[3] = p1[HW];
+    }
+    uint32_t ah_hi[4] = {0u, 0u, 0u, 0u}, ah_lo[4] = {0u, 0u, 0u, 0u};      // dheat: rows = pixels, K = landmark
+    if (kL && d_heat) {
+      float dh[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int l = 2 * t + 8 * h + e;
+          dh[0][2 * h + e] = (ok0 && l < NL) ? d_heat[((long long)n0 * NL + l) * HW + hw0] : 0.f;
+          dh[1][2 * h + e] = (ok1 && l < NL) ? d_heat[((long long)n1 * NL + l) * HW + hw1] : 0.f;
+        }
+      float ra, rb;
+      ah_hi[0] = heads_pack_hi(dh[0][0], dh[0][1], ra, rb); ah_lo[0] = heads_pack(ra, rb);
+      ah_hi[1] = heads_pack_hi(dh[1][0], dh[1][1], ra, rb); ah_lo[1] = heads_pack(ra, rb);
+      ah_hi[2] = heads_pack_hi(dh[0][2], dh[0][3], ra, rb); ah_lo[2] = heads_pack(ra, rb);
+      ah_hi[3] = heads_pack_hi(dh[1][2], dh[1][3], ra, rb); ah_lo[3] = heads_pack(ra, rb);
+    }
+    const uint32_t a_k0[4] = {q0.x, q1.x, q0.y, q1.y}, a_k1[4] = {q0.z, q1.z, q0.w, q1.w};
+    float lg[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(lg, a_k0, bl_hi[0]); mma_bf16_16816(lg, a_k1, bl_hi[1]);
+    mma_bf16_16816(lg, a_k0, bl_lo[0]); mma_bf16_16816(lg, a_k1, bl_lo[1]);
+    // dlg (softmax backward): lg[0], lg[1] / ds[0], ds[1]: pixel r0, classes 2t, 2t+1; [2], [3]: pixel r1
+    float dlg[4] = {ds[0], ds[1], ds[2], ds[3]};
+    if (do_softmax && d_seg) {
+      float m0 = fmaxf(c0ok ? lg[0] : -INFINITY, c1ok ? lg[1] : -INFINITY);
+      float m1 = fmaxf(c0ok ? lg[2] : -INFINITY, c1ok ? lg[3] : -INFINITY);
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float pr[4] = {c0ok ? expf(lg[0] - m0) : 0.f, c1ok ? expf(lg[1] - m0) : 0.f,
+                     c0ok ? expf(lg[2] - m1) : 0.f, c1ok ? expf(lg[3] - m1) : 0.f};
+      float s0 = pr[0] + pr[1], s1 = pr[2] + pr[3];
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float i0 = 1.f / s0, i1 = 1.f / s1;
+      pr[0] *= i0; pr[1] *= i0; pr[2] *= i1; pr[3] *= i1;
+      float d0 = fmaf(pr[0], ds[0], pr[1] * ds[1]), d1 = fmaf(pr[2], ds[2], pr[3] * ds[3]);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 2); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+      dlg[0] = pr[0] * (ds[0] - d0); dlg[1] = pr[1] * (ds[1] - d0);
+      dlg[2] = pr[2] * (ds[2] - d1); dlg[3] = pr[3] * (ds[3] - d1);
+    }
+    // dcat = dheat W21: tiles 0..3 -> dfeat (permuted columns), tile 4 -> into dlg
+    float dc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dc[j][0] = dc[j][1] = dc[j][2] = dc[j][3] = 0.f;
+    if (kL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mma_bf16_16816(dc[j], ah_hi, bd_hi[j]); mma_bf16_16816(dc[j], ah_hi, bd_lo[j]); mma_bf16_16816(dc[j], ah_lo, bd_hi[j]);
+      }
+      mma_bf16_16816(dlg, ah_hi, bd_hi[4]); mma_bf16_16816(dlg, ah_hi, bd_lo[4]); mma_bf16_16816(dlg, ah_lo, bd_hi[4]);
+    }
+    // dfeat += dlg Wseg
+    float r00, r01, r10, r11;
+    const uint32_t al_hi[4] = {heads_pack_hi(dlg[0], dlg[1], r00, r01), heads_pack_hi(dlg[2], dlg[3], r10, r11), 0u, 0u};
+    const uint32_t al_lo[4] = {heads_pack(r00, r01), heads_pack(r10, r11), 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mma_bf16_16816_b0(dc[j], al_hi, bf_hi[j]); mma_bf16_16816_b0(dc[j], al_hi, bf_lo[j]); mma_bf16_16816_b0(dc[j], al_lo, bf_hi[j]);
+    }
+    if (ok0) *reinterpret_cast<uint4*>(d_feat + (long long)r0 * d_ld + 8 * t) =
+        make_uint4(heads_pack(dc[0][0], dc[0][1]), heads_pack(dc[1][0], dc[1][1]), heads_pack(dc[2][0], dc[2][1]), heads_pack(dc[3][0], dc[3][1]));
+    if (ok1) *reinterpret_cast<uint4*>(d_feat + (long long)r1 * d_ld + 8 * t) =
+        make_uint4(heads_pack(dc[0][2], dc[0][3]), heads_pack(dc[1][2], dc[1][3]), heads_pack(dc[2][2], dc[2][3]), heads_pack(dc[3][2], dc[3][3]));
+    // ---- weight gradients: K = the 16 pixels of the tile ----
+    // B' tiles: features (step s, half h): pixels 0..7 / 8..15 of that 8-channel block, transposed; tile 4: the logits
+    uint32_t bt[kL ? 5 : 4][2];
+    bt[0][0] = movm_trans(a_k0[0]); bt[0][1] = movm_trans(a_k0[1]);
+    bt[1][0] = movm_trans(a_k0[2]); bt[1][1] = movm_trans(a_k0[3]);
+    bt[2][0] = movm_trans(a_k1[0]); bt[2][1] = movm_trans(a_k1[1]);
+    bt[3][0] = movm_trans(a_k1[2]); bt[3][1] = movm_trans(a_k1[3]);
+    // A' (dlg^T): rows = classes (8 .. 15: zero), K = pixels
+    const uint32_t at_s[4] = {movm_trans(al_hi[0]), 0u, movm_trans(al_hi[1]), 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mma_bf16_16816(gs[j], at_s, bt[j]);
+    if (kL) {
+      bt[kL ? 4 : 0][0] = movm_trans(heads_pack(lg[0], lg[1])); bt[kL ? 4 : 0][1] = movm_trans(heads_pack(lg[2], lg[3]));
+      // A' (dheat^T): rows = landmarks, K = pixels
+      const uint32_t at_h[4] = {movm_trans(ah_hi[0]), movm_trans(ah_hi[2]), movm_trans(ah_hi[1]), movm_trans(ah_hi[3])};
+#pragma unroll
+      for (int j = 0; j < 5; ++j) mma_bf16_16816(g1[j], at_h, bt[j]);
+    }
+  }
+  // ---- block reduction of the weight-gradient fragments, then one global atomic per element and block ----
+  // fragment columns 2t, 2t+1 of feature tile (s, h) = 2s + h are channels 8t + 4s + 2h (+1); rows g, g + 8
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int ch = 8 * t + 4 * (j >> 1) + 2 * (j & 1) + e;
+      if (g < NC) atomicAdd(&s_g[NG1 + g * CF + ch], gs[j][e]);
+      if (kL) {
+        if (g < NL) atomicAdd(&s_g[g * NCAT + ch], g1[j][e]);
+        if (g + 8 < NL) atomicAdd(&s_g[(g + 8) * NCAT + ch], g1[j][2 + e]);
+      }
+    }
+  if (kL) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = 2 * t + e;
+      if (k < NC) {
+        if (g < NL) atomicAdd(&s_g[g * NCAT + CF + k], g1[kL ? 4 : 0][e]);
+        if (g + 8 < NL) atomicAdd(&s_g[(g + 8) * NCAT + CF + k], g1[kL ? 4 : 0][2 + e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NG; i += blockDim.x) atomicAdd(g_acc + i, s_g[i]);
+}
+
 // dW2 = G1 W1^T, dW1 = W2^T G1, dWseg = Gseg  (G's accumulated by heads_bwd_fused_kernel)
 __global__ void heads_bwd_finalize_kernel(const float* g_acc, const float* w1, const float* w2, float* dwseg, float* dw1,
                                           float* dw2, int CF, int NC, int NF, int NL) {

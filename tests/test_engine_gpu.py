@@ -557,3 +557,46 @@ def test_eager_forward_after_graph_replays_uses_the_updated_weights(pkg, precisi
             d = rel_l2(vals["graph"][k][which].cpu(), vals["eager"][k][which].cpu())
             assert d < 0.1 * move, (k, which, d, move)
     assert rel_l2(vals["graph"][2][1].cpu(), vals["graph"][0][1].cpu()) > 0.1
+
+
+@pytest.mark.parametrize("shape", [
+    (3, 6, 6, 2, 14),         # B, H, W, depth, num_lands: 108 pixels -- ragged last 16-pixel tile, tiles straddle images
+    (2, 48, 80, 3, 14),
+    (5, 36, 28, 2, 0),        # seg-only head
+])
+@pytest.mark.parametrize("softmax", [True, False])
+def test_tensor_core_heads_agree_with_cuda_core_heads(pkg, shape, softmax):
+    """bf16 mode: the heads on warp-level tensor-core MMAs (heads_fwd_mma_kernel / heads_bwd_mma_kernel, split-bf16 weights)
+    against the fp32-FMA heads kernels (FU_HEADS_MMA=0) behind the SAME network: the features that reach the heads are
+    bit-identical, so the outputs must agree to fp32 rounding and the gradients to the bf16 rounding of d_feat."""
+    dev = torch.device("cuda:0")
+    Bq, Hq, Wq, depth, nl = shape
+    kw = dict(n_classes=7, depth=depth, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=nl, do_soft_max=softmax)
+    x = torch.randn(Bq, 1, Hq, Wq, generator=torch.Generator().manual_seed(5)).to(dev)
+    res = {}
+    for mode in ("mma", "fma"):
+        os.environ["FU_HEADS_MMA"] = "1" if mode == "mma" else "0"
+        try:
+            torch.manual_seed(0)
+            net = pkg.UNet(precision="bf16", **kw).to(dev).train()
+            out = net(x)
+            seg, heat = out if nl else (out, torch.zeros(1, device=dev))
+            d_seg = torch.randn(seg.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+            d_heat = torch.randn(heat.shape, generator=torch.Generator().manual_seed(4)).to(dev)
+            ((seg * d_seg).sum() + ((heat * d_heat).sum() if nl else 0.0)).backward()
+            torch.cuda.synchronize()
+            res[mode] = (seg.detach().cpu(), heat.detach().cpu(),
+                         {n: p.grad.cpu() for n, p in net.named_parameters() if p.grad is not None})
+        finally:
+            os.environ.pop("FU_HEADS_MMA", None)
+    assert rel_l2(res["mma"][0], res["fma"][0]) < 1e-5, rel_l2(res["mma"][0], res["fma"][0])
+    if nl:
+        # (the landmark product takes the logits as fp32 in the FMA kernel and as hi + lo bf16 pairs here)
+        assert rel_l2(res["mma"][1], res["fma"][1]) < 2e-5, rel_l2(res["mma"][1], res["fma"][1])
+    for k, v in res["mma"][2].items():
+        w = res["fma"][2][k]
+        head = k.startswith(("seg", "lands", "last"))
+        e = rel_l2(v, w)
+        # head weights: same bf16 single-pass outer products in both, different summation order; everything upstream
+        # sees d_feat rounded to bf16 from values that differ in the last fp32 bits (a rounding flip = 2^-9 of one element)
+        assert e < (5e-3 if head else 3e-2), (k, e)
