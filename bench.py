@@ -54,6 +54,9 @@ def parse():
                     help="launch every step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--torch-loss", action="store_true",
                     help="use the PyTorch DiceAndHeatMapLoss2D on cropped views instead of the fused device loss")
+    ap.add_argument("--loss-in-heads", action="store_true",
+                    help="the loss inside the heads kernels (UNet.forward_loss; bf16 only).  Default: the fused device loss as separate "
+                         "kernels after the network, which measures faster (DESIGN.md section 5)")
     ap.add_argument("--seg-only", action="store_true",
                     help="num_lands=0 network with DiceLoss2D (train.py:327; BASELINE configs[2]: --batch 8 --size 736 --tile 718)")
     ap.add_argument("--heatmap-wgt", type=float, default=0.5,
@@ -234,7 +237,9 @@ def config_dict(args, world, graphed=False, e2e_inputs=""):
             "per_gpu_batch": args.batch, "global_batch": args.batch * world, "net_input": args.size, "tile": args.tile,
             "parallelism": f"dp{world}", "precision": args.precision,
             "loss": "torch DiceAndHeatMapLoss2D on cropped views" if args.torch_loss
-                    else "fused device DiceAndHeatMapLoss2D (crop folded in)",
+                    else ("fused device DiceAndHeatMapLoss2D (crop folded in)" if (not args.loss_in_heads or args.precision != "bf16")
+                          else "DiceAndHeatMapLoss2D inside the heads kernels (UNet.forward_loss: sums from the head kernel, "
+                               "gradient formed in the backward head kernel; crop folded in)"),
             "optimizer": "torch.optim.SGD(momentum 0.9, nesterov, wd 1e-4, fused=True)",
             "launch": "one CUDA-graph replay per step (GraphedStep)" if graphed else "eager launches",
             "e2e_inputs": e2e_inputs,
@@ -270,7 +275,7 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
 def measure(torch, dist, pkg, dev, rank, world, local, *, batch, size, tile, precision, seg_only, heatmap_wgt, steps, warmup,
-            graph=True, torch_loss=False, host_prep=False, profile=True, e2e=True, clocks=True):
+            graph=True, torch_loss=False, host_prep=False, profile=True, e2e=True, clocks=True, loss_in_heads=False):
     """Times one configuration: device-resident `value`, end-to-end `e2e`, and the roofline of the 3x3 conv family
     from per-kernel CUDA events.  Returns a dict; every rank must call it with the same arguments."""
     torch.manual_seed(0)
@@ -284,6 +289,7 @@ def measure(torch, dist, pkg, dev, rank, world, local, *, batch, size, tile, pre
     # train.py:324's loss.  Default: the fused device version (same value and gradient, tests/test_loss_gpu.py),
     # which folds the output crop of train.py:414-417 into its indexing.
     fused_loss = not torch_loss
+    in_heads = fused_loss and loss_in_heads and precision == "bf16"      # the loss inside the heads kernels (opt-in)
     if seg_only:
         crit = (pkg.FusedDiceLoss2D if fused_loss else pkg.DiceLoss2D)(skip_bg=False)                     # train.py:327
     else:
@@ -300,6 +306,11 @@ def measure(torch, dist, pkg, dev, rank, world, local, *, batch, size, tile, pre
 
     def train_step(x, mask, heat=None):
         opt.zero_grad(set_to_none=True)
+        if in_heads:
+            loss = net.forward_loss(x, mask if seg_only else (mask, heat), crit)
+            loss.backward()
+            opt.step()
+            return loss
         if seg_only:
             seg = net(x)
             loss = crit(seg, mask) if fused_loss else crit(pkg.center_crop(seg, mask.shape), mask)
@@ -507,7 +518,7 @@ def run_ours(args):
         finish(torch, dist, world)
         return
 
-    common = dict(graph=not args.no_graph, torch_loss=args.torch_loss, host_prep=args.host_prep)
+    common = dict(graph=not args.no_graph, torch_loss=args.torch_loss, host_prep=args.host_prep, loss_in_heads=args.loss_in_heads)
     main = measure(torch, dist, pkg, dev, rank, world, local, batch=args.batch, size=args.size, tile=args.tile,
                    precision=args.precision, seg_only=args.seg_only, heatmap_wgt=args.heatmap_wgt, steps=args.steps,
                    warmup=args.warmup, profile=not args.no_profile, **common)

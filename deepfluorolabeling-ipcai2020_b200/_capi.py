@@ -48,7 +48,7 @@ EXPORTS = ["fu_engine_create", "fu_engine_destroy", "fu_last_error", "fu_num_ten
            "fu_tensor_get_info", "fu_grad_numel", "fu_bind_tensors", "fu_forward", "fu_backward",
            "fu_set_bucket_callback", "fu_early_grad_numel",
            "fu_get_counters", "fu_build_info", "fu_test_conv", "fu_profile_enable", "fu_profile_report", "fu_debug_copy",
-           "fu_loss_workspace_doubles", "fu_loss_forward", "fu_loss_backward",
+           "fu_loss_workspace_doubles", "fu_loss_forward", "fu_loss_backward", "fu_forward_loss", "fu_backward_loss",
            "fu_prep_tiles", "fu_heatmap_targets", "fu_ensemble_workspace_words", "fu_ensemble_combine",
            "fu_extract_landmarks"]
 
@@ -106,6 +106,10 @@ def lib():
     L.fu_loss_forward.restype = i32
     L.fu_loss_backward.argtypes = [C.POINTER(FuLossDesc), vp, vp, i32, i32, i32, i32, vp, vp, vp]
     L.fu_loss_backward.restype = i32
+    L.fu_forward_loss.argtypes = [vp, vp, i32, i32, i32, i64, C.POINTER(FuLossDesc), i32, i32, vp, vp, vp, vp, vp]
+    L.fu_forward_loss.restype = i32
+    L.fu_backward_loss.argtypes = [vp, C.POINTER(FuLossDesc), i32, i32, vp, vp, vp, vp, vp]
+    L.fu_backward_loss.restype = i32
     f32 = C.c_float
     L.fu_prep_tiles.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
     L.fu_prep_tiles.restype = i32

@@ -121,6 +121,13 @@ struct fu_engine {
   char* wgrad_scr = nullptr; size_t wgrad_scr_bytes = 0;   // tensor-core weight-gradient accumulators
   float *ones = nullptr, *zeros = nullptr;
   float* heads_gacc = nullptr;   // [NL*(CF+NC) + NC*CF] accumulators of the fused heads backward
+  // the training loss inside the heads kernels (fu_forward_loss / fu_backward_loss): set for the duration of such a call
+  const HeadsLoss* lossf = nullptr;
+  const float* lossf_dloss = nullptr;
+  bool lossf_noseg = false;      // fu_forward_loss was given no seg output: the class probabilities stay in the head kernel
+  LossArgs lossf_args;           // sizes / weights of the loss (finalisation, coefficient kernel)
+  float* loss_coef = nullptr;    // [B][NC*2 + NL*3] per-plane gradient coefficients (own allocation, grows with B)
+  size_t loss_coef_floats = 0;
   unsigned* coop_bar = nullptr;  // {arrival count, generation} of the grid barrier in bn_act_bwd_coop_kernel (self-resetting)
   int coop_blocks_per_sm = -1;   // resident blocks per SM of that kernel (occupancy query, once); 0 = do not use it
   // batched weight pack / weight-gradient unpack (kernels_tc.cuh): device job tables and what they hold
@@ -1070,19 +1077,39 @@ int forward_t(fu_engine* e, const float* x, int B, int H, int W, int training, f
       const bool use_mma = tc_env_int("FU_HEADS_MMA", 1) != 0;
       if (use_mma && P < (1ll << 30) && feat.ld % 8 == 0 && reinterpret_cast<uintptr_t>(feat.p) % 16 == 0) {
         const unsigned gridm = (unsigned)std::min<long long>((P + 63) / 64, (long long)e->num_sms * 6);      // 6 resident blocks per SM (launch bounds)
+        HeadsLoss hl;
+        memset(&hl, 0, sizeof(hl));
+        if (e->lossf) {
+          // the loss sums leave the head kernel (3 resident blocks per SM: 26 fp64 accumulators per thread)
+          hl = *e->lossf;
+          if (e->lossf_noseg) seg = nullptr;
+          const unsigned gridl = (unsigned)std::min<long long>((P + 63) / 64, (long long)e->num_sms * 3);
+          if (c.num_lands == 14)
+            LAUNCH(e, (heads_fwd_mma_kernel<32, 7, 21, 14, true>), gridl, 128,
+                   reinterpret_cast<const bf16*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx),
+                   tdata(e, e->lands[1].w_idx), reinterpret_cast<bf16*>(lg.p), seg, logits, heat, (int)P, (int)HW, FastDiv((int)HW),
+                   c.do_soft_max, hl);
+          else
+            LAUNCH(e, (heads_fwd_mma_kernel<32, 7, 1, 0, true>), gridl, 128,
+                   reinterpret_cast<const bf16*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), (const float*)nullptr,
+                   (const float*)nullptr, reinterpret_cast<bf16*>(lg.p), seg, logits, (float*)nullptr, (int)P, (int)HW,
+                   FastDiv((int)HW), c.do_soft_max, hl);
+          return FU_OK;
+        }
         if (c.num_lands == 14)
           LAUNCH(e, (heads_fwd_mma_kernel<32, 7, 21, 14>), gridm, 128,
                  reinterpret_cast<const bf16*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx),
                  tdata(e, e->lands[1].w_idx), reinterpret_cast<bf16*>(lg.p), seg, logits, heat, (int)P, (int)HW, FastDiv((int)HW),
-                 c.do_soft_max);
+                 c.do_soft_max, hl);
         else
           LAUNCH(e, (heads_fwd_mma_kernel<32, 7, 1, 0>), gridm, 128,
                  reinterpret_cast<const bf16*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), (const float*)nullptr,
                  (const float*)nullptr, reinterpret_cast<bf16*>(lg.p), seg, logits, (float*)nullptr, (int)P, (int)HW,
-                 FastDiv((int)HW), c.do_soft_max);
+                 FastDiv((int)HW), c.do_soft_max, hl);
         return FU_OK;
       }
     }
+    if (e->lossf) return e->fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_forward_loss: the fused loss needs bf16 storage and the tensor-core heads (FU_HEADS_MMA)");
     if (c.num_lands == 14)
       LAUNCH(e, (heads_fwd_fused_kernel<T, 32, 7, 21, 14>), gridf, 128,
              reinterpret_cast<const T*>(feat.p), feat.ld, tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx),
@@ -1381,22 +1408,47 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
       if (use_mma && P0 < (1ll << 30) && feat.ld % 8 == 0 && d_feat.ld % 8 == 0 && reinterpret_cast<uintptr_t>(feat.p) % 16 == 0 &&
           reinterpret_cast<uintptr_t>(d_feat.p) % 16 == 0) {
         const unsigned gridm = (unsigned)std::min<long long>((P0 + 63) / 64, (long long)e->num_sms * 3);
-        if (c.num_lands == 14) {
+        HeadsLoss hl;
+        memset(&hl, 0, sizeof(hl));
+        if (e->lossf) {
+          hl = *e->lossf;
+          const LossArgs& la = e->lossf_args;
+          LAUNCH(e, loss_coef_kernel, (unsigned)((B * (la.NC + la.NL) + 127) / 128), 128, (const double*)hl.sums, e->lossf_dloss,
+                 e->loss_coef, B, la.NC, la.NL, la.Ht, la.Wt, la.skip_bg, la.dice_wgt, la.heat_wgt);
+          hl.coef = e->loss_coef;
+          if (c.num_lands == 14)
+            LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 21, 14, true>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
+                   tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), (const float*)nullptr,
+                   (const float*)nullptr, reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW,
+                   FastDiv((int)HW), c.do_soft_max, hl);
+          else
+            LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 1, 0, true>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
+                   tdata(e, e->seg.w_idx), (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
+                   (const float*)nullptr, reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW,
+                   FastDiv((int)HW), c.do_soft_max, hl);
+          if (c.num_lands == 14)
+            LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
+                   gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
+          else
+            LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
+                   gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0);
+        } else if (c.num_lands == 14) {
           LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 21, 14>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
                  tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,
-                 reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max);
+                 reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max, hl);
           LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
                  gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
         } else {
           LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 1, 0>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
                  tdata(e, e->seg.w_idx), (const float*)nullptr, (const float*)nullptr, d_seg, (const float*)nullptr,
-                 reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max);
+                 reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max, hl);
           LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
                  gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0);
         }
         heads_done = true;
       }
     }
+    if (!heads_done && e->lossf) return e->fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_backward_loss: the fused loss needs bf16 storage and the tensor-core heads");
     if (heads_done) {
     } else if (c.num_lands == 14) {
       LAUNCH_SMEM(e, (heads_bwd_fused_kernel<T, 32, 7, 21, 14>), gridh, 128, (sizeof(T) == 2 ? heads_bwd_smem_bytes_mma<32, 7, 21, 14>() : heads_bwd_smem_bytes<32, 7, 21, 14>()), reinterpret_cast<const T*>(feat.p), feat.ld,
@@ -1630,6 +1682,7 @@ void fu_engine_destroy(fu_engine* e) {
   if (e->dscr_fwd) cudaFree(e->dscr_fwd);
   if (e->dscr_bwd) cudaFree(e->dscr_bwd);
   if (e->wgrad_scr) cudaFree(e->wgrad_scr);
+  if (e->loss_coef) cudaFree(e->loss_coef);
   if (e->pack_tbl) cudaFree(e->pack_tbl);
   if (e->unpack_tbl) cudaFree(e->unpack_tbl);
   if (e->side) cudaStreamDestroy(e->side);
@@ -1884,10 +1937,106 @@ int fu_loss_backward(const fu_loss_desc* d, const double* sums, const float* dlo
   q.dloss = dloss; q.d_seg = d_seg; q.d_heat = d_heat; q.H = H; q.W = W; q.r0 = r0; q.c0 = c0;
   q.a.rows = loss_rows_per_block(H, (long long)q.a.B * (q.a.NC + q.a.NL));
   const dim3 grid((unsigned)((H + q.a.rows - 1) / q.a.rows), (unsigned)(q.a.B * (q.a.NC + q.a.NL)));
-  loss_backward_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+  // 16-byte path: full rows of 4-column groups, aligned plane origins (the prediction pointers address the window origin)
+  auto al16 = [](const void* p_) { return reinterpret_cast<uintptr_t>(p_) % 16 == 0; };
+  const float* seg0 = q.a.seg - ((long long)r0 * q.a.seg_sr + c0);
+  const float* heat0 = q.a.heat ? q.a.heat - ((long long)r0 * q.a.heat_sr + c0) : nullptr;
+  const bool vec4 = W % 4 == 0 && q.a.seg_sr % 4 == 0 && q.a.seg_sb % 4 == 0 && q.a.seg_sc % 4 == 0 && al16(seg0) && al16(d_seg) &&
+                    (!heat0 || (q.a.heat_sr % 4 == 0 && q.a.heat_sb % 4 == 0 && q.a.heat_sc % 4 == 0 && al16(heat0) && al16(d_heat))) &&
+                    tc_env_int("FU_LOSS_VEC", 1) != 0;
+  if (vec4) loss_backward_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+  else loss_backward_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
   cudaError_t ce = cudaPeekAtLastError();
   if (ce != cudaSuccess) { g_create_error = std::string("fu_loss_backward: ") + cudaGetErrorString(ce); return FU_ERR_CUDA; }
   return FU_OK;
+}
+
+// ---- the loss inside the heads kernels (SURVEY 8f row 1 as specified) ----
+static int heads_loss_setup(fu_engine* e, const fu_loss_desc* d, int B, int H, int W, int r0, int c0, HeadsLoss& hl, const char* who) {
+  LossArgs& a = e->lossf_args;
+  fu_loss_desc dd = *d;
+  // the prediction pointers of the descriptor are not used here (the predictions never leave the head kernels); loss_args
+  // only validates their presence
+  static const float dummy = 0.f;
+  dd.seg = &dummy; if (dd.num_lands > 0) dd.heat = &dummy; else dd.heat = nullptr;
+  int rc = loss_args(&dd, a);
+  if (rc) return e->fail(rc, "%s: %s", who, g_create_error.c_str());
+  const fu_config& c = e->cfg;
+  if (c.precision != FU_PRECISION_BF16 || e->Cf != 32 || c.n_classes != 7 ||
+      !(c.num_lands == 0 || (c.num_lands == 14 && e->lands.size() == 2 && e->lands[0].Cout == 21)))
+    return e->fail(FU_ERR_UNSUPPORTED_SHAPE, "%s: bf16 storage and the paper heads (32 features, 7 classes, 0 or 14 landmarks) only", who);
+  if (a.B != B || a.NC != c.n_classes || a.NL != c.num_lands)
+    return e->fail(FU_ERR_ARG, "%s: the loss descriptor's batch / class / landmark counts do not match the network", who);
+  if (((long long)H * W) % 16 != 0)
+    return e->fail(FU_ERR_UNSUPPORTED_SHAPE, "%s: H * W must be a multiple of 16", who);
+  if (r0 < 0 || c0 < 0 || r0 + a.Ht > H || c0 + a.Wt > W) return e->fail(FU_ERR_ARG, "%s: window outside the output", who);
+  memset(&hl, 0, sizeof(hl));
+  hl.mask = a.mask; hl.mask_sb = a.mask_sb; hl.mask_sc = a.mask_sc; hl.mask_sr = a.mask_sr;
+  hl.heat_t = a.heat_t; hl.heat_t_sb = a.heat_t_sb; hl.heat_t_sc = a.heat_t_sc; hl.heat_t_sr = a.heat_t_sr;
+  hl.Ht = a.Ht; hl.Wt = a.Wt; hl.r0 = r0; hl.c0 = c0; hl.W = W; hl.fd_w = FastDiv(W);
+  return FU_OK;
+}
+
+int fu_forward_loss(fu_engine* e, const float* x, int B, int H, int W, int64_t weights_version, const fu_loss_desc* d, int r0, int c0,
+                    double* sums, float* loss_out, float* seg, float* heat, void* stream) {
+  if (!e) return FU_ERR_ARG;
+  if (!d || !sums || !loss_out) return e->fail(FU_ERR_ARG, "fu_forward_loss: null descriptor / workspace / output");
+  if (e->cfg.num_lands > 0 && !heat) return e->fail(FU_ERR_ARG, "fu_forward_loss: heat must be non-null when num_lands > 0 (fu_backward_loss reads it)");
+  if (!tc_env_int("FU_HEADS_MMA", 1)) return e->fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_forward_loss: needs the tensor-core heads (FU_HEADS_MMA=0 is set)");
+  HeadsLoss hl;
+  int rc = heads_loss_setup(e, d, B, H, W, r0, c0, hl, "fu_forward_loss");
+  if (rc) return rc;
+  hl.sums = sums;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    DeviceScope dev_scope(e->device);
+    const size_t ws = (size_t)fu_loss_workspace_doubles(B, e->cfg.n_classes, e->cfg.num_lands) * sizeof(double);
+    CUDA_TRY(e, cudaMemsetAsync(sums, 0, ws, st));
+  }
+  e->lossf = &hl; e->lossf_noseg = seg == nullptr;
+  // (seg may be NULL: the class probabilities then never leave the head kernel; fu_forward itself insists on a pointer,
+  //  which the head launch drops again -- lossf_noseg)
+  rc = fu_forward(e, x, B, H, W, 1, 1, weights_version, seg ? seg : loss_out, nullptr, heat, stream);
+  e->lossf = nullptr; e->lossf_noseg = false;
+  if (rc) return rc;
+  {
+    DeviceScope dev_scope(e->device);
+    LossArgs a = e->lossf_args;
+    a.sums = sums;
+    loss_finalize_kernel<<<1, 256, 0, st>>>(a, loss_out);
+    e->cnt.kernel_launches++;
+    cudaError_t ce = cudaPeekAtLastError();
+    if (ce != cudaSuccess) return e->fail(FU_ERR_CUDA, "fu_forward_loss: %s", cudaGetErrorString(ce));
+  }
+  return FU_OK;
+}
+
+int fu_backward_loss(fu_engine* e, const fu_loss_desc* d, int r0, int c0, const double* sums, const float* dloss, const float* heat,
+                     float* flat_grads, void* stream) {
+  if (!e) return FU_ERR_ARG;
+  if (!e->saved) return e->fail(FU_ERR_STATE, "fu_backward_loss without a saved forward (call fu_forward_loss first)");
+  if (!d || !sums || !dloss) return e->fail(FU_ERR_ARG, "fu_backward_loss: null descriptor / workspace / upstream gradient");
+  if (e->cfg.num_lands > 0 && !heat) return e->fail(FU_ERR_ARG, "fu_backward_loss: heat (the forward's heat-map output) must be non-null");
+  if (!tc_env_int("FU_HEADS_MMA", 1)) return e->fail(FU_ERR_UNSUPPORTED_SHAPE, "fu_backward_loss: needs the tensor-core heads (FU_HEADS_MMA=0 is set)");
+  const int B = e->plan.B, H = e->plan.H, W = e->plan.W;
+  HeadsLoss hl;
+  int rc = heads_loss_setup(e, d, B, H, W, r0, c0, hl, "fu_backward_loss");
+  if (rc) return rc;
+  hl.sums = const_cast<double*>(sums);
+  hl.heat = heat;
+  const size_t need = (size_t)B * (2 * e->cfg.n_classes + 3 * e->cfg.num_lands);
+  if (need > e->loss_coef_floats) {
+    DeviceScope dev_scope(e->device);
+    // (grows only when the batch size does: never inside a captured step that was warmed up at its own shapes)
+    if (e->loss_coef) cudaFree(e->loss_coef);
+    e->loss_coef = nullptr; e->loss_coef_floats = 0;
+    CUDA_TRY(e, cudaMalloc(&e->loss_coef, need * sizeof(float)));
+    e->loss_coef_floats = need;
+  }
+  e->lossf = &hl; e->lossf_dloss = dloss;
+  rc = fu_backward(e, nullptr, nullptr, flat_grads, stream);
+  e->lossf = nullptr; e->lossf_dloss = nullptr;
+  return rc;
 }
 
 const char* fu_build_info(void) {

@@ -28,6 +28,9 @@ struct LossArgs {
 // Rows per block: whole planes when there are enough planes to fill the machine (B = 32 @192x192: 672 planes), else chunks
 // sized for ~4 blocks per SM.  16-row blocks (8064 of them at B = 32) spent most of their time in the five block-level
 // fp64 reductions and atomics each block ends with: 61 + 95 us for two passes over 180 + 250 MB.
+// (Measured later and not kept: chunks sized for ~6 waves -- sums pass unchanged at 60 us, gradient pass 46 -> 50 us.  The sums
+// pass does not respond to more loads in flight, fp32 partials or finer chunks either: it runs right behind the head kernel
+// that wrote 99 MB of predictions, i.e. against the L2's write-back of those lines.)
 inline int loss_rows_per_block(int rows_total, long long planes, int sms = 148) {
   long long r = ((long long)rows_total * planes + (long long)sms * 4 - 1) / ((long long)sms * 4);
   r = (r + 7) / 8 * 8;
@@ -53,9 +56,30 @@ __device__ __forceinline__ double block_sum_double(double v, double* sm) {
   return t;    // valid in thread 0
 }
 
+// N sums at once: one shuffle tree per value, one shared-memory exchange, threads 0..N-1 end up with the totals
+template <int N>
+__device__ __forceinline__ double block_sum_n(double (&v)[N], double (*sm)[8]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) sm[k][w] = v[k];
+  }
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < N) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[threadIdx.x][i];
+  }
+  return t;    // thread k < N: total of value k
+}
+
 // grid: (row chunks of the window, B*(NC+NL) planes)
 __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
-  __shared__ double sm[8];
+  __shared__ double sm[5][8];
   const int plane = blockIdx.y;
   const int b = plane / (p.NC + p.NL), c = plane - b * (p.NC + p.NL);
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -65,40 +89,67 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
     const float* x = p.seg + b * p.seg_sb + c * p.seg_sc;
     const float* t = p.mask + b * p.mask_sb + c * p.mask_sc;
     double s_tp = 0.0, s_tt = 0.0, s_pp = 0.0;
-    for (int r = r_begin + wrp; r < r_end; r += 8) {
-      const float* xr = x + (long long)r * p.seg_sr;
-      const float* tr = t + (long long)r * p.mask_sr;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;              // <= 8 columns per lane and row: fp32 is exact enough here
-      for (int col = lane; col < p.Wt; col += 32) {
-        const float xv = xr[col], tv = tr[col];
-        a0 = fmaf(tv, xv, a0); a1 = fmaf(tv, tv, a1); a2 = fmaf(xv, xv, a2);
+    // four rows per warp at a time: eight independent loads per lane and column step (one row at a time left the pass
+    // latency bound: 58 us for 180 MB)
+    for (int r = r_begin + wrp; r < r_end; r += 32) {
+      const float* xr[4]; const float* tr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ru = min(r + 8 * u, r_end - 1);        // (clamped rows are loaded and not counted)
+        xr[u] = x + (long long)ru * p.seg_sr; tr[u] = t + (long long)ru * p.mask_sr;
       }
-      s_tp += (double)a0; s_tt += (double)a1; s_pp += (double)a2;
+      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};   // <= 8 columns per lane and row
+      for (int col = lane; col < p.Wt; col += 32) {
+        float xv[4], tv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xv[u] = xr[u][col]; tv[u] = tr[u][col]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a0[u] = fmaf(tv[u], xv[u], a0[u]); a1[u] = fmaf(tv[u], tv[u], a1[u]); a2[u] = fmaf(xv[u], xv[u], a2[u]); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + 8 * u < r_end) { s_tp += (double)a0[u]; s_tt += (double)a1[u]; s_pp += (double)a2[u]; }
     }
-    s_tp = block_sum_double(s_tp, sm); s_tt = block_sum_double(s_tt, sm); s_pp = block_sum_double(s_pp, sm);
-    if (threadIdx.x == 0) {
-      double* o = p.sums + (long long)b * per + c * 3;
-      atomicAdd(o, s_tp); atomicAdd(o + 1, s_tt); atomicAdd(o + 2, s_pp);
-    }
+    double v3[3] = {s_tp, s_tt, s_pp};
+    const double tot = block_sum_n<3>(v3, sm);
+    if (threadIdx.x < 3) atomicAdd(p.sums + (long long)b * per + c * 3 + threadIdx.x, tot);
   } else {
     const int l = c - p.NC;
     const float* x = p.heat + b * p.heat_sb + l * p.heat_sc;
     const float* y = p.heat_t + b * p.heat_t_sb + l * p.heat_t_sc;
     double sx = 0.0, sxx = 0.0, sy = 0.0, syy = 0.0, sxy = 0.0;
-    for (int r = r_begin + wrp; r < r_end; r += 8) {
-      const float* xr = x + (long long)r * p.heat_sr;
-      const float* yr = y + (long long)r * p.heat_t_sr;
-      for (int col = lane; col < p.Wt; col += 32) {
-        const double xv = xr[col], yv = yr[col];     // fp64 throughout: the variances below are differences of sums
-        sx += xv; sxx += xv * xv; sy += yv; syy += yv * yv; sxy += xv * yv;
+    for (int r = r_begin + wrp; r < r_end; r += 32) {
+      const float* xr[4]; const float* yr[4];
+      bool on[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        on[u] = r + 8 * u < r_end;
+        const int ru = min(r + 8 * u, r_end - 1);
+        xr[u] = x + (long long)ru * p.heat_sr; yr[u] = y + (long long)ru * p.heat_t_sr;
       }
+      // fp32 over the <= 8 columns a lane sees of a row, fp64 from there on (the variances are differences of sums: a
+      // partial of <= 8 terms carries <= 5e-7 relative error and the ~6000 partials of a plane average it out; element-wise
+      // fp64 arithmetic -- 7 fp64-pipe operations per element -- was what bounded this pass, 58 us for 180 MB)
+      float m[4][5];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m[u][0] = m[u][1] = m[u][2] = m[u][3] = m[u][4] = 0.f;
+      for (int col = lane; col < p.Wt; col += 32) {
+        float xf[4], yf[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xf[u] = xr[u][col]; yf[u] = yr[u][col]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          m[u][0] += xf[u]; m[u][1] = fmaf(xf[u], xf[u], m[u][1]); m[u][2] += yf[u]; m[u][3] = fmaf(yf[u], yf[u], m[u][3]);
+          m[u][4] = fmaf(xf[u], yf[u], m[u][4]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (on[u]) { sx += (double)m[u][0]; sxx += (double)m[u][1]; sy += (double)m[u][2]; syy += (double)m[u][3]; sxy += (double)m[u][4]; }
     }
-    sx = block_sum_double(sx, sm); sxx = block_sum_double(sxx, sm); sy = block_sum_double(sy, sm);
-    syy = block_sum_double(syy, sm); sxy = block_sum_double(sxy, sm);
-    if (threadIdx.x == 0) {
-      double* o = p.sums + (long long)b * per + p.NC * 3 + l * 5;
-      atomicAdd(o, sx); atomicAdd(o + 1, sxx); atomicAdd(o + 2, sy); atomicAdd(o + 3, syy); atomicAdd(o + 4, sxy);
-    }
+    double v5[5] = {sx, sxx, sy, syy, sxy};
+    const double tot = block_sum_n<5>(v5, sm);
+    if (threadIdx.x < 5) atomicAdd(p.sums + (long long)b * per + p.NC * 3 + l * 5 + threadIdx.x, tot);
   }
 }
 
@@ -149,7 +200,39 @@ struct LossBwdArgs {
   int H, W, r0, c0;             // full output size and window origin
 };
 
+// Four columns per thread: the block's rows x (W / 4) column groups are dealt to the threads as one flat index space, the
+// gradient leaves as aligned 16-byte stores and the predictions arrive as aligned 16-byte loads (full-plane addresses);
+// the targets sit at window coordinates (misaligned by the crop origin) and are read as scalars.  v = f(target, prediction).
+// Preconditions (checked by the launcher): W % 4 == 0, prediction row stride % 4 == 0, plane bases 16-byte aligned.
+template <typename F>
+__device__ __forceinline__ void loss_bwd_rows_vec4(const LossBwdArgs& q, const float* x_full /* plane origin (full tensor) */, int x_sr,
+                                                   const float* t, int t_sr, float* g, int R_begin, int R_end, bool plane_on, F f) {
+  const LossArgs& p = q.a;
+  const int W4 = q.W >> 2;
+  const int items = (R_end - R_begin) * W4;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const int rr = i / W4, c4 = i - rr * W4;
+    const int R = R_begin + rr, C = c4 * 4;
+    const int r = R - q.r0, col = C - q.c0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (plane_on && r >= 0 && r < p.Ht && col + 3 >= 0 && col < p.Wt) {
+      const float4 xv = *reinterpret_cast<const float4*>(x_full + (long long)R * x_sr + C);
+      const float* tr = t + (long long)r * t_sr;
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cc = col + k;
+        o[k] = (cc >= 0 && cc < p.Wt) ? f(tr[cc], xs[k]) : 0.f;
+      }
+      v = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    *reinterpret_cast<float4*>(g + (long long)R * q.W + C) = v;
+  }
+}
+
 // grid: (row chunks of the FULL plane, B*(NC+NL) planes); zeros outside the window
+template <bool VEC4>
 __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q) {
   const LossArgs& p = q.a;
   const int plane = blockIdx.y;
@@ -169,6 +252,12 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q)
     const float fden = (float)den, fnum = (float)num;
     const float* x = p.seg + b * p.seg_sb + c * p.seg_sc;
     const float* t = p.mask + b * p.mask_sb + c * p.mask_sc;
+    if (VEC4) {
+      // (p.seg addresses the window origin: step back to the plane origin)
+      loss_bwd_rows_vec4(q, x - ((long long)q.r0 * p.seg_sr + q.c0), p.seg_sr, t, p.mask_sr, g, R_begin, R_end, k != 0.f,
+                         [=](float tv, float xv) { return k * (-2.f * tv * fden - 2.f * xv * fnum); });
+      return;
+    }
     for (int R = R_begin + wrp; R < R_end; R += 8) {
       const int r = R - q.r0;
       const bool row_in = r >= 0 && r < p.Ht && k != 0.f;
@@ -193,6 +282,11 @@ __global__ void __launch_bounds__(256) loss_backward_kernel(const LossBwdArgs q)
     const float mx = (float)t.mx, my = (float)t.my;
     const float* x = p.heat + b * p.heat_sb + l * p.heat_sc;
     const float* y = p.heat_t + b * p.heat_t_sb + l * p.heat_t_sc;
+    if (VEC4) {
+      loss_bwd_rows_vec4(q, x - ((long long)q.r0 * p.heat_sr + q.c0), p.heat_sr, y, p.heat_t_sr, g, R_begin, R_end, true,
+                         [=](float yv, float xv) { return ka * (yv - my) - kb * (xv - mx); });
+      return;
+    }
     for (int R = R_begin + wrp; R < R_end; R += 8) {
       const int r = R - q.r0;
       const bool row_in = r >= 0 && r < p.Ht;

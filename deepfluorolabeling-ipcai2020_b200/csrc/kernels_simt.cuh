@@ -400,6 +400,14 @@ __global__ void __launch_bounds__(256) wgrad_small_cin_kernel(const SmallCinWgra
 // --------------------------------------------------------------------------
 template <typename T> struct Ld8;
 template <> struct Ld8<float> {
+  struct Raw { float4 a, b; };          // 8 elements as loaded (kept packed while several loads are in flight)
+  static __device__ __forceinline__ Raw ldraw(const float* p) {
+    Raw r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+  }
+  static __device__ __forceinline__ Raw zero() { Raw r; r.a = r.b = make_float4(0.f, 0.f, 0.f, 0.f); return r; }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -410,6 +418,17 @@ template <> struct Ld8<float> {
   }
 };
 template <> struct Ld8<bf16> {
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw ldraw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ void unpack(const Raw& u, float (&v)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
   static __device__ __forceinline__ void ld(const bf16* p, float (&v)[8]) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -474,6 +493,9 @@ __device__ __forceinline__ void cin1_window(const T* xp, int x_ld, float* sx, in
   }
 }
 
+// (3x3, measured and not kept: fetching the NEXT tile's halo into registers before working on the current one -- the
+//  global-load latency between the two barriers is not what bounds these kernels: forward 53.7 -> 55.7 us, weight gradient
+//  75.7 -> 80.3 us at 32 x 192 x 192.)
 // y = [relu](conv_K(x) + bias) [+ bn_a*t + bn_b], optional per-channel sum / sum of squares (SmallCinArgs, Cin == 1)
 template <typename T, int K>
 __global__ void __launch_bounds__(256, K == 1 ? 3 : 2) conv_cin1_kernel(const SmallCinArgs p) {
@@ -501,12 +523,27 @@ __global__ void __launch_bounds__(256, K == 1 ? 3 : 2) conv_cin1_kernel(const Sm
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
   const int tiles_w = (p.W + TW - 1) / TW, tiles_h = (p.H + TH - 1) / TH;
   const int total = tiles_w * tiles_h * p.B;
+  auto tile_origin = [&](int tile, int& n, int& h0, int& w0) {
+    n = tile / (tiles_w * tiles_h);
+    const int rem = tile - n * (tiles_w * tiles_h);
+    h0 = (rem / tiles_w) * TH; w0 = (rem % tiles_w) * TW;
+  };
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int n = tile / (tiles_w * tiles_h), rem = tile - n * (tiles_w * tiles_h);
-    const int h0 = (rem / tiles_w) * TH, w0 = (rem % tiles_w) * TW;
+    int n, h0, w0;
+    tile_origin(tile, n, h0, w0);
     const int wc = w0 + slot;
     float xw[TH + 2 * (K / 2)][K];
     cin1_window<T, K>(xp, p.x_ld, sx, n, h0, w0, slot, TW, p.H, p.W, xw);
+    // (the second epilogue operand of all rows is requested before any row is worked on)
+    // (1x1 only: the 3x3 variant holds 72 weights in registers and is never given a second operand by the engine)
+    typename Ld8<T>::Raw traw[K == 1 ? TH : 1];
+    if (K == 1 && p.t) {
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {
+        const int h = h0 + r;
+        traw[r] = (h < p.H && wc < p.W) ? Ld8<T>::ldraw(tp + (((long long)n * p.H + h) * p.W + wc) * p.t_ld + g * 8) : Ld8<T>::zero();
+      }
+    }
 #pragma unroll
     for (int r = 0; r < TH; ++r) {
       const int h = h0 + r;
@@ -523,7 +560,8 @@ __global__ void __launch_bounds__(256, K == 1 ? 3 : 2) conv_cin1_kernel(const Sm
         }
         if (p.t) {
           float tv[8];
-          Ld8<T>::ld(tp + pix * p.t_ld + g * 8, tv);
+          if constexpr (K == 1) Ld8<T>::unpack(traw[r], tv);
+          else Ld8<T>::ld(tp + pix * p.t_ld + g * 8, tv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(ba[j], tv[j], acc[j]);
         }
@@ -587,9 +625,14 @@ __global__ void __launch_bounds__(256, K == 1 ? 3 : 2) wgrad_cin1_kernel(const S
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   const int tiles_w = (p.W + TW - 1) / TW, tiles_h = (p.H + TH - 1) / TH;
   const int total = tiles_w * tiles_h * p.B;
+  auto tile_origin = [&](int tile, int& n, int& h0, int& w0) {
+    n = tile / (tiles_w * tiles_h);
+    const int rem = tile - n * (tiles_w * tiles_h);
+    h0 = (rem / tiles_w) * TH; w0 = (rem % tiles_w) * TW;
+  };
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int n = tile / (tiles_w * tiles_h), rem = tile - n * (tiles_w * tiles_h);
-    const int h0 = (rem / tiles_w) * TH, w0 = (rem % tiles_w) * TW;
+    int n, h0, w0;
+    tile_origin(tile, n, h0, w0);
     const int wc = w0 + slot;
     float d[TH][8];
 #pragma unroll
@@ -851,10 +894,25 @@ __device__ __forceinline__ uint32_t heads_pack(float a, float b) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
 }
 
-template <int CF, int NC, int NF, int NL>
-__global__ void __launch_bounds__(128, 6) heads_fwd_mma_kernel(const bf16* __restrict__ feat, int ld, const float* wseg, const float* w1,
+// The training loss inside the heads kernels (Dice / NCC partial sums from the head kernel's epilogue, the loss
+// gradient formed in the backward head kernel's prologue).  Targets are (B, C, Ht, Wt) fp32 planes addressed through the centre-crop
+// window (origin r0, c0 of the full H x W output; util.py:92-114 as called at train.py:414-417).
+struct HeadsLoss {
+  const float* mask; long long mask_sb, mask_sc; int mask_sr;            // segmentation targets: batch, channel, row strides
+  const float* heat_t; long long heat_t_sb, heat_t_sc; int heat_t_sr;    // heat-map targets
+  int Ht, Wt, r0, c0;
+  FastDiv fd_w;               // division by the full output width W
+  int W;
+  double* sums;               // forward: [B][NC*3 + NL*5] (kernels_loss.cuh), zeroed by the caller
+  const float* coef;          // backward: [B][NC*2 + NL*3] per-plane coefficients (loss_coef_kernel)
+  const float* heat;          // backward: the heat-map predictions the forward stored, (B, NL, H, W)
+};
+
+template <int CF, int NC, int NF, int NL, bool LOSS = false>
+__global__ void __launch_bounds__(128, LOSS ? 3 : 6) heads_fwd_mma_kernel(const bf16* __restrict__ feat, int ld, const float* wseg, const float* w1,
                                                             const float* w2, bf16* logits_nhwc, float* seg, float* logits_out,
-                                                            float* heat, int P, int HW, FastDiv fd_hw, int do_softmax) {
+                                                            float* heat, int P, int HW, FastDiv fd_hw, int do_softmax,
+                                                            const HeadsLoss lossp) {
   pdl_wait(); pdl_trigger();
   typedef HeadsDims<CF, NC, NF, NL> D;
   static_assert(CF == 32 && NC <= 8 && NL <= 16, "fragment layout below: 32 features, <= 8 classes, <= 16 landmarks");
@@ -904,16 +962,57 @@ __global__ void __launch_bounds__(128, 6) heads_fwd_mma_kernel(const bf16* __res
   auto load_rows = [&](int tile, uint4& q0, uint4& q1) {
     const int r0 = tile * 16 + g, r1 = r0 + 8;
     q0 = make_uint4(0u, 0u, 0u, 0u); q1 = q0;
-    if (r0 < P) q0 = *reinterpret_cast<const uint4*>(feat + (long long)r0 * ld + 8 * t);
-    if (r1 < P) q1 = *reinterpret_cast<const uint4*>(feat + (long long)r1 * ld + 8 * t);
+    if (tile < ntiles && r0 < P) q0 = *reinterpret_cast<const uint4*>(feat + (long long)r0 * ld + 8 * t);
+    if (tile < ntiles && r1 < P) q1 = *reinterpret_cast<const uint4*>(feat + (long long)r1 * ld + 8 * t);
+  };
+  // LOSS: a warp walks a CONTIGUOUS range of tiles, so its loss sums stay in registers until the image index changes (the
+  // caller guarantees H * W % 16 == 0: a tile never straddles two images); otherwise tiles are dealt round-robin.
+  const int tpw = LOSS ? (ntiles + nwarps - 1) / nwarps : 1;
+  const int t_first = LOSS ? warp_g * tpw : warp_g, t_step = LOSS ? 1 : nwarps;
+  const int t_end = LOSS ? min(ntiles, t_first + tpw) : ntiles;
+  // per-thread loss sums of the current image: Dice (t p, t t, p p) for classes 2t, 2t+1; NCC (x, xx, y, yy, xy) for
+  // landmarks 8j + 2t, 8j + 2t + 1.  fp32 per tile (two pixels), fp64 across tiles (the NCC variances are differences of sums)
+  double ld_acc[LOSS ? 2 : 1][3], ln_acc[LOSS && NT > 0 ? 2 * NT : 1][5];
+  int cur_n = -1;
+  if (LOSS) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) ld_acc[LOSS ? i : 0][0] = ld_acc[LOSS ? i : 0][1] = ld_acc[LOSS ? i : 0][2] = 0.0;
+#pragma unroll
+    for (int i = 0; i < (NT > 0 ? 2 * NT : 1); ++i)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) ln_acc[LOSS && NT > 0 ? i : 0][k] = 0.0;
+  }
+  auto flush_loss = [&]() {
+    if (!LOSS || cur_n < 0) return;
+    constexpr int per = NC * 3 + NL * 5;
+    double* o = lossp.sums + (long long)cur_n * per;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double v = ld_acc[LOSS ? i : 0][k];
+        v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0 && 2 * t + i < NC) atomicAdd(o + (2 * t + i) * 3 + k, v);
+        ld_acc[LOSS ? i : 0][k] = 0.0;
+      }
+#pragma unroll
+    for (int i = 0; i < (NT > 0 ? 2 * NT : 0); ++i)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        double v = ln_acc[LOSS && NT > 0 ? i : 0][k];
+        v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+        const int l = 8 * (i >> 1) + 2 * t + (i & 1);
+        if (g == 0 && l < NL) atomicAdd(o + NC * 3 + l * 5 + k, v);
+        ln_acc[LOSS && NT > 0 ? i : 0][k] = 0.0;
+      }
   };
   uint4 nq0, nq1;
-  load_rows(warp_g, nq0, nq1);
-  for (int tile = warp_g; tile < ntiles; tile += nwarps) {
+  load_rows(t_first, nq0, nq1);
+  for (int tile = t_first; tile < t_end; tile += t_step) {
     const int r0 = tile * 16 + g, r1 = r0 + 8;
     const bool ok0 = r0 < P, ok1 = r1 < P;
     const uint4 q0 = nq0, q1 = nq1;
-    load_rows(tile + nwarps, nq0, nq1);
+    load_rows(tile + t_step < t_end ? tile + t_step : ntiles, nq0, nq1);
     const uint32_t a_k0[4] = {q0.x, q1.x, q0.y, q1.y}, a_k1[4] = {q0.z, q1.z, q0.w, q1.w};
     float lg[4] = {0.f, 0.f, 0.f, 0.f};
     mma_bf16_16816(lg, a_k0, bs_hi[0]); mma_bf16_16816(lg, a_k1, bs_hi[1]);
@@ -922,6 +1021,23 @@ __global__ void __launch_bounds__(128, 6) heads_fwd_mma_kernel(const bf16* __res
     const int n0 = fd_hw.div(ok0 ? r0 : 0), n1 = fd_hw.div(ok1 ? r1 : 0);
     const int hw0 = (ok0 ? r0 : 0) - n0 * HW, hw1 = (ok1 ? r1 : 0) - n1 * HW;
     const bool c0ok = 2 * t < NC, c1ok = 2 * t + 1 < NC;
+    // LOSS: window coordinates of the two pixels (inside the crop window or not) and the image the tile belongs to
+    bool in0 = false, in1 = false;
+    long long toff0 = 0, toff1 = 0, hoff0 = 0, hoff1 = 0;      // offsets of the pixels inside a target plane (mask | heat_t)
+    if (LOSS) {
+      if (n0 != cur_n) { flush_loss(); cur_n = n0; }
+      int row, col;
+      lossp.fd_w.divmod(hw0, row, col);
+      row -= lossp.r0; col -= lossp.c0;
+      in0 = ok0 && row >= 0 && row < lossp.Ht && col >= 0 && col < lossp.Wt;
+      toff0 = (long long)n0 * lossp.mask_sb + (long long)row * lossp.mask_sr + col;
+      hoff0 = (long long)n0 * lossp.heat_t_sb + (long long)row * lossp.heat_t_sr + col;
+      lossp.fd_w.divmod(hw1, row, col);
+      row -= lossp.r0; col -= lossp.c0;
+      in1 = ok1 && row >= 0 && row < lossp.Ht && col >= 0 && col < lossp.Wt;
+      toff1 = (long long)n1 * lossp.mask_sb + (long long)row * lossp.mask_sr + col;
+      hoff1 = (long long)n1 * lossp.heat_t_sb + (long long)row * lossp.heat_t_sr + col;
+    }
     if (logits_nhwc) {
       if (c1ok) {
         if (ok0) *reinterpret_cast<uint32_t*>(logits_nhwc + (long long)r0 * ld + 2 * t) = heads_pack(lg[0], lg[1]);
@@ -933,6 +1049,7 @@ __global__ void __launch_bounds__(128, 6) heads_fwd_mma_kernel(const bf16* __res
     }
     float* seg0 = seg + ((long long)n0 * NC + 2 * t) * HW + hw0;
     float* seg1 = seg + ((long long)n1 * NC + 2 * t) * HW + hw1;
+    float pv[4];                  // the segmentation output of the two pixels (classes 2t, 2t+1)
     if (logits_out) {
       float* lo0 = logits_out + ((long long)n0 * NC + 2 * t) * HW + hw0;
       float* lo1 = logits_out + ((long long)n1 * NC + 2 * t) * HW + hw1;
@@ -952,15 +1069,28 @@ __global__ void __launch_bounds__(128, 6) heads_fwd_mma_kernel(const bf16* __res
       s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
       s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       const float i0 = 1.f / s0, i1 = 1.f / s1;
-      if (ok0 && c0ok) seg0[0] = e00 * i0;
-      if (ok0 && c1ok) seg0[HW] = e01 * i0;
-      if (ok1 && c0ok) seg1[0] = e10 * i1;
-      if (ok1 && c1ok) seg1[HW] = e11 * i1;
+      pv[0] = e00 * i0; pv[1] = e01 * i0; pv[2] = e10 * i1; pv[3] = e11 * i1;
     } else {
-      if (ok0 && c0ok) seg0[0] = lg[0];
-      if (ok0 && c1ok) seg0[HW] = lg[1];
-      if (ok1 && c0ok) seg1[0] = lg[2];
-      if (ok1 && c1ok) seg1[HW] = lg[3];
+      pv[0] = lg[0]; pv[1] = lg[1]; pv[2] = lg[2]; pv[3] = lg[3];
+    }
+    if (seg) {
+      if (ok0 && c0ok) seg0[0] = pv[0];
+      if (ok0 && c1ok) seg0[HW] = pv[1];
+      if (ok1 && c0ok) seg1[0] = pv[2];
+      if (ok1 && c1ok) seg1[HW] = pv[3];
+    }
+    if (LOSS) {
+      // Dice sums (dice.py:20-55) of the two pixels, classes 2t, 2t+1
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool cok = i ? c1ok : c0ok;
+        const float t0 = (in0 && cok) ? lossp.mask[toff0 + (long long)(2 * t + i) * lossp.mask_sc] : 0.f;
+        const float t1 = (in1 && cok) ? lossp.mask[toff1 + (long long)(2 * t + i) * lossp.mask_sc] : 0.f;
+        const float p0 = (in0 && cok) ? pv[i] : 0.f, p1 = (in1 && cok) ? pv[2 + i] : 0.f;
+        ld_acc[LOSS ? i : 0][0] += (double)fmaf(t0, p0, t1 * p1);
+        ld_acc[LOSS ? i : 0][1] += (double)fmaf(t0, t0, t1 * t1);
+        ld_acc[LOSS ? i : 0][2] += (double)fmaf(p0, p0, p1 * p1);
+      }
     }
     if (NT > 0) {
       // third K step: A = [logits | 0], hi + lo
@@ -981,9 +1111,24 @@ __global__ void __launch_bounds__(128, 6) heads_fwd_mma_kernel(const bf16* __res
         if (ok0 && l + 1 < NL) h0[HW] = h4[1];
         if (ok1 && l < NL) h1[0] = h4[2];
         if (ok1 && l + 1 < NL) h1[HW] = h4[3];
+        if (LOSS) {
+          // NCC moments (ncc.py:12-38) of the two pixels, landmarks l, l + 1
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const bool lok = l + i < NL;
+            const float x0 = (in0 && lok) ? h4[i] : 0.f, x1 = (in1 && lok) ? h4[2 + i] : 0.f;
+            const float y0 = (in0 && lok) ? lossp.heat_t[hoff0 + (long long)(l + i) * lossp.heat_t_sc] : 0.f;
+            const float y1 = (in1 && lok) ? lossp.heat_t[hoff1 + (long long)(l + i) * lossp.heat_t_sc] : 0.f;
+            double* a = ln_acc[LOSS && NT > 0 ? 2 * j + i : 0];
+            a[0] += (double)(x0 + x1); a[1] += (double)fmaf(x0, x0, x1 * x1);
+            a[2] += (double)(y0 + y1); a[3] += (double)fmaf(y0, y0, y1 * y1);
+            a[4] += (double)fmaf(x0, y0, x1 * y1);
+          }
+        }
       }
     }
   }
+  flush_loss();
 }
 
 template <typename T, int CF, int NC, int NF, int NL>
@@ -1274,12 +1419,16 @@ __device__ __forceinline__ void mma_bf16_16816_b0(float (&c)[4], const uint32_t 
   mma_bf16_16816(c, a, b);
 }
 
-template <int CF, int NC, int NF, int NL>
+// LOSS: d_seg / d_heat are not read; the gradient of the training loss w.r.t. the two outputs is formed per pixel from the
+// targets, the recomputed class probabilities, the stored heat-map predictions and the per-plane coefficients of
+// loss_coef_kernel (closed forms of kernels_loss.cuh:loss_backward_kernel): inside the crop window
+//   d_seg = A t + Bc p,   d_heat = ka y - kb x + kc;   zero outside.
+template <int CF, int NC, int NF, int NL, bool LOSS = false>
 __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __restrict__ feat, int ld, const float* wseg, const float* w1,
                                                                const float* w2, const float* __restrict__ d_seg,
                                                                const float* __restrict__ d_heat, bf16* d_feat, int d_ld,
                                                                float* g_acc /*[NL*(CF+NC) + NC*CF]*/, int P, int HW, FastDiv fd_hw,
-                                                               int do_softmax) {
+                                                               int do_softmax, const HeadsLoss lossp) {
   pdl_wait(); pdl_trigger();
   typedef HeadsDims<CF, NC, NF, NL> D;
   static_assert(CF == 32 && NC <= 8 && NL <= 16, "fragment layout below: 32 features, <= 8 classes, <= 16 landmarks");
@@ -1358,9 +1507,28 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
     load_rows(tile + nwarps, nq0, nq1);
     const int n0 = fd_hw.div(ok0 ? r0 : 0), n1 = fd_hw.div(ok1 ? r1 : 0);
     const int hw0 = (ok0 ? r0 : 0) - n0 * HW, hw1 = (ok1 ? r1 : 0) - n1 * HW;
+    // LOSS: window coordinates of the two pixels
+    bool in0 = false, in1 = false;
+    long long toff0 = 0, toff1 = 0, hoff0 = 0, hoff1 = 0;
+    const float* cf0 = nullptr; const float* cf1 = nullptr;
+    if (LOSS) {
+      int row, col;
+      lossp.fd_w.divmod(hw0, row, col);
+      row -= lossp.r0; col -= lossp.c0;
+      in0 = ok0 && row >= 0 && row < lossp.Ht && col >= 0 && col < lossp.Wt;
+      toff0 = (long long)n0 * lossp.mask_sb + (long long)row * lossp.mask_sr + col;
+      hoff0 = (long long)n0 * lossp.heat_t_sb + (long long)row * lossp.heat_t_sr + col;
+      lossp.fd_w.divmod(hw1, row, col);
+      row -= lossp.r0; col -= lossp.c0;
+      in1 = ok1 && row >= 0 && row < lossp.Ht && col >= 0 && col < lossp.Wt;
+      toff1 = (long long)n1 * lossp.mask_sb + (long long)row * lossp.mask_sr + col;
+      hoff1 = (long long)n1 * lossp.heat_t_sb + (long long)row * lossp.heat_t_sr + col;
+      cf0 = lossp.coef + (long long)n0 * (NC * 2 + NL * 3);
+      cf1 = lossp.coef + (long long)n1 * (NC * 2 + NL * 3);
+    }
     // upstream gradients in fragment order (a warp load covers 4 planes x 8 consecutive pixels)
     float ds[4] = {0.f, 0.f, 0.f, 0.f};
-    if (d_seg) {
+    if (!LOSS && d_seg) {
       const float* p0 = d_seg + ((long long)n0 * NC + 2 * t) * HW + hw0;
       const float* p1 = d_seg + ((long long)n1 * NC + 2 * t) * HW + hw1;
       if (ok0 && c0ok) ds[0] = p0[0];
@@ -1369,13 +1537,28 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
       if (ok1 && c1ok) ds[3] = p1[HW];
     }
     uint32_t ah_hi[4] = {0u, 0u, 0u, 0u}, ah_lo[4] = {0u, 0u, 0u, 0u};      // dheat: rows = pixels, K = landmark
-    if (kL && d_heat) {
+    if (kL && (LOSS || d_heat)) {
       float dh[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int l = 2 * t + 8 * h + e;
+          if (LOSS) {
+            float v0 = 0.f, v1 = 0.f;
+            if (in0 && l < NL) {
+              const float x = lossp.heat[((long long)n0 * NL + l) * HW + hw0], y = lossp.heat_t[hoff0 + (long long)l * lossp.heat_t_sc];
+              const float* c3 = cf0 + NC * 2 + l * 3;
+              v0 = fmaf(c3[0], y, fmaf(-c3[1], x, c3[2]));
+            }
+            if (in1 && l < NL) {
+              const float x = lossp.heat[((long long)n1 * NL + l) * HW + hw1], y = lossp.heat_t[hoff1 + (long long)l * lossp.heat_t_sc];
+              const float* c3 = cf1 + NC * 2 + l * 3;
+              v1 = fmaf(c3[0], y, fmaf(-c3[1], x, c3[2]));
+            }
+            dh[0][2 * h + e] = v0; dh[1][2 * h + e] = v1;
+            continue;
+          }
           dh[0][2 * h + e] = (ok0 && l < NL) ? d_heat[((long long)n0 * NL + l) * HW + hw0] : 0.f;
           dh[1][2 * h + e] = (ok1 && l < NL) ? d_heat[((long long)n1 * NL + l) * HW + hw1] : 0.f;
         }
@@ -1391,7 +1574,17 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
     mma_bf16_16816(lg, a_k0, bl_lo[0]); mma_bf16_16816(lg, a_k1, bl_lo[1]);
     // dlg (softmax backward): lg[0], lg[1] / ds[0], ds[1]: pixel r0, classes 2t, 2t+1; [2], [3]: pixel r1
     float dlg[4] = {ds[0], ds[1], ds[2], ds[3]};
-    if (do_softmax && d_seg) {
+    auto loss_dseg = [&](const float (&p4)[4]) {       // LOSS: d_seg of the two pixels from the targets and the predictions p4
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool cok = i ? c1ok : c0ok;
+        const int c = 2 * t + i;
+        ds[i] = (in0 && cok) ? fmaf(cf0[2 * c], lossp.mask[toff0 + (long long)c * lossp.mask_sc], cf0[2 * c + 1] * p4[i]) : 0.f;
+        ds[2 + i] = (in1 && cok) ? fmaf(cf1[2 * c], lossp.mask[toff1 + (long long)c * lossp.mask_sc], cf1[2 * c + 1] * p4[2 + i]) : 0.f;
+      }
+    };
+    if (LOSS && !do_softmax) { loss_dseg(lg); dlg[0] = ds[0]; dlg[1] = ds[1]; dlg[2] = ds[2]; dlg[3] = ds[3]; }
+    if (do_softmax && (LOSS || d_seg)) {
       float m0 = fmaxf(c0ok ? lg[0] : -INFINITY, c1ok ? lg[1] : -INFINITY);
       float m1 = fmaxf(c0ok ? lg[2] : -INFINITY, c1ok ? lg[3] : -INFINITY);
       m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
@@ -1403,6 +1596,7 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
       s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       const float i0 = 1.f / s0, i1 = 1.f / s1;
       pr[0] *= i0; pr[1] *= i0; pr[2] *= i1; pr[3] *= i1;
+      if (LOSS) loss_dseg(pr);
       float d0 = fmaf(pr[0], ds[0], pr[1] * ds[1]), d1 = fmaf(pr[2], ds[2], pr[3] * ds[3]);
       d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
       d0 += __shfl_xor_sync(0xffffffffu, d0, 2); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
@@ -1476,6 +1670,38 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NG; i += blockDim.x) atomicAdd(g_acc + i, s_g[i]);
+}
+
+// Per-plane coefficients of the loss gradient (closed forms of loss_backward_kernel) from the forward's sums and the
+// upstream gradient of the loss: class planes (A, Bc), landmark planes (ka, kb, kc).  One thread per plane.
+__global__ void loss_coef_kernel(const double* __restrict__ sums, const float* __restrict__ dloss, float* __restrict__ coef,
+                                 int B, int NC, int NL, int Ht, int Wt, int skip_bg, float dice_wgt, float heat_wgt) {
+  pdl_wait(); pdl_trigger();
+  const int per = NC * 3 + NL * 5, cper = NC * 2 + NL * 3;
+  const double up = (double)*dloss;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * (NC + NL); i += gridDim.x * blockDim.x) {
+    const int b = i / (NC + NL), c = i - b * (NC + NL);
+    if (c < NC) {
+      const int c_first = skip_bg ? 1 : 0;
+      const double* s = sums + (long long)b * per + c * 3;
+      const double num = -2.0 * s[0] + 1.0e-4, den = s[1] + s[2] + 1.0e-4;
+      const double k = c < c_first ? 0.0 : up * dice_wgt / ((double)(NC - c_first) * B) / (den * den);
+      coef[(long long)b * cper + 2 * c] = (float)(-2.0 * k * den);
+      coef[(long long)b * cper + 2 * c + 1] = (float)(-2.0 * k * num);
+    } else {
+      const int l = c - NC;
+      const double N = (double)Ht * Wt;
+      const double* m = sums + (long long)b * per + NC * 3 + l * 5;
+      const double mx = m[0] / N, my = m[2] / N;
+      const double vxx = fmax(m[1] - N * mx * mx, 0.0), vyy = fmax(m[3] - N * my * my, 0.0);
+      const double sdx = sqrt(vxx / (N - 1.0)), sdy = sqrt(vyy / (N - 1.0));
+      const double sxy_c = m[4] - N * mx * my, den = N * sdx * sdy + 1.0e-8;
+      const double w = up * heat_wgt * -0.5 / ((double)B * NL);
+      const double ka = w / den, kb = sdx > 0.0 ? w * sxy_c * N * sdy / ((N - 1.0) * sdx * den * den) : 0.0;
+      float* o = coef + (long long)b * cper + NC * 2 + l * 3;
+      o[0] = (float)ka; o[1] = (float)kb; o[2] = (float)(kb * mx - ka * my);
+    }
+  }
 }
 
 // dW2 = G1 W1^T, dW1 = W2^T G1, dWseg = Gseg  (G's accumulated by heads_bwd_fused_kernel)

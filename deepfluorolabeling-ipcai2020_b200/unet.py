@@ -78,6 +78,72 @@ class _UNetFunction(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
+class _UNetLossFunction(torch.autograd.Function):
+    """Network forward + training loss as ONE autograd node (train.py:407-422 without the output tensors in between): the
+    head kernel reduces the Dice / NCC sums of its own outputs, the backward head kernel forms the loss gradient per pixel
+    (include/fluoro_unet.h: fu_forward_loss / fu_backward_loss)."""
+
+    @staticmethod
+    def forward(ctx, net, x, tgt_seg, tgt_heat, skip_bg, dice_wgt, heat_wgt, *params):
+        L = _capi.lib()
+        B, _, H, W = x.shape
+        nc, nl = net._cfg["n_classes"], net._cfg["num_lands"]
+        Ht, Wt = tgt_seg.shape[-2:]
+        r0, c0 = int((H - Ht) / 2), int((W - Wt) / 2)              # util.py:99-103
+        d = _capi.FuLossDesc()
+        d.mask = tgt_seg.data_ptr()
+        d.mask_stride[:] = [tgt_seg.stride(0), tgt_seg.stride(1), tgt_seg.stride(2)]
+        if nl > 0:
+            d.heat_t = tgt_heat.data_ptr()
+            d.heat_t_stride[:] = [tgt_heat.stride(0), tgt_heat.stride(1), tgt_heat.stride(2)]
+        d.B, d.n_classes, d.num_lands, d.Ht, d.Wt = B, nc, nl, Ht, Wt
+        d.skip_bg, d.dice_wgt, d.heat_wgt = int(skip_bg), float(dice_wgt), float(heat_wgt)
+        sums = torch.empty(int(L.fu_loss_workspace_doubles(B, nc, nl)), device=x.device, dtype=torch.float64)
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        heat = torch.empty((B, nl, H, W), device=x.device, dtype=torch.float32) if nl > 0 else None
+        version = 0
+        for p in net._state_cache[3]:
+            version += p._version
+        version = (version & 0xFFFFFFFF) | (net._pack_epoch << 32)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        net._generation += 1
+        rc = L.fu_forward_loss(net._handle, x.data_ptr(), B, H, W, version, C.byref(d), r0, c0, sums.data_ptr(), loss.data_ptr(),
+                               None, heat.data_ptr() if heat is not None else None, stream)
+        if rc != 0:
+            msg = _capi.last_error(net._handle)
+            if rc == _capi.FU_ERR_UNSUPPORTED_SHAPE:
+                raise ValueError(msg)
+            raise RuntimeError(f"fu_forward_loss failed ({rc}): {msg}")
+        ctx.net, ctx.generation = net, net._generation
+        ctx.desc, ctx.geom = d, (r0, c0)
+        ctx.keep = (tgt_seg, tgt_heat, sums, heat)                   # the descriptor holds raw addresses of these
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        net = ctx.net
+        if ctx.generation != net._generation:
+            raise RuntimeError("UNet.backward: the engine's saved activations were overwritten by a later "
+                               "forward; run backward before the next forward (as train.py:407-422 does)")
+        L = _capi.lib()
+        _, _, sums, heat = ctx.keep
+        dev = net._handle_device
+        flat = torch.empty(net._grad_numel, device=dev, dtype=torch.float32)
+        dloss = dloss.contiguous().float()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        net._install_bucket_callback(flat)
+        rc = L.fu_backward_loss(net._handle, C.byref(ctx.desc), ctx.geom[0], ctx.geom[1], sums.data_ptr(), dloss.data_ptr(),
+                                heat.data_ptr() if heat is not None else None, flat.data_ptr(), stream)
+        if rc != 0:
+            raise RuntimeError(f"fu_backward_loss failed ({rc}): {_capi.last_error(net._handle)}")
+        net._pack_epoch = (net._pack_epoch + 1) & 0x3FFFFFFF
+        if net.grad_hook is not None:
+            net.grad_hook(flat)
+        net.last_flat_grad = flat
+        grads = [flat[off:off + numel].view(shape) for name, shape, numel, off in net._grad_params]
+        return (None,) * 7 + tuple(grads)
+
+
 class UNet(nn.Module):
     def __init__(self, in_channels=1, n_classes=2, depth=5, wf=6,
                  padding=False, pad_mode='zeros',
@@ -412,6 +478,49 @@ class UNet(nn.Module):
         buf = C.create_string_buffer(int(n) + 16)
         L.fu_profile_report(self._handle, buf, n + 16)
         return [json.loads(l) for l in buf.value.decode().splitlines() if l.strip()]
+
+    def forward_loss(self, x, target, criterion):
+        """loss = criterion(center_crop(net(x)), target) of train.py:407-420 as ONE engine call pair: the Dice / NCC sums are
+        reduced by the head kernel itself and `loss.backward()` forms the loss gradient inside the backward head kernel, so
+        neither the (B, 7 + 14, H, W) outputs nor their gradients make a round trip through HBM.
+
+        criterion: FusedDiceLoss2D (target = mask) or FusedDiceAndHeatMapLoss2D (target = (mask, heat-maps)); targets are
+        fp32 CUDA tensors of the cropped size.  Needs precision='bf16', the paper heads and H*W % 16 == 0 -- anything else
+        raises ValueError (use `criterion(net(x), target)`, which runs the same arithmetic as separate kernels).  The module
+        must be in train() mode; gradients reach every parameter exactly as through forward()."""
+        from . import losses
+        if isinstance(criterion, losses.FusedDiceAndHeatMapLoss2D):
+            tgt_seg, tgt_heat = target
+            skip_bg, dice_wgt, heat_wgt = criterion.skip_bg, criterion.dice_wgt, criterion.heatmap_wgt
+        elif isinstance(criterion, losses.FusedDiceLoss2D):
+            tgt_seg, tgt_heat = target, None
+            skip_bg, dice_wgt, heat_wgt = criterion.skip_bg, 1.0, 0.0
+        else:
+            raise TypeError("forward_loss: criterion must be FusedDiceLoss2D or FusedDiceAndHeatMapLoss2D")
+        if not self.training:
+            raise RuntimeError("forward_loss is a training-step call: put the module in train() mode")
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or not x.is_cuda or x.dtype != torch.float32:
+            raise ValueError("forward_loss expects a (B,C,H,W) float32 CUDA tensor")
+        if x.shape[1] != self._cfg["in_channels"]:
+            raise ValueError(f"expected {self._cfg['in_channels']} input channels, got {x.shape[1]}")
+        nl = self._cfg["num_lands"]
+        if (nl > 0) != (tgt_heat is not None):
+            raise ValueError("forward_loss: heat-map targets must be given exactly when the network has a landmark head")
+        for name, t in (("mask", tgt_seg), ("heat-map target", tgt_heat)):
+            if t is None:
+                continue
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.stride(-1) == 1):
+                raise ValueError(f"forward_loss: {name} must be a 4-D float32 CUDA tensor with unit column stride")
+        B, _, H, W = x.shape
+        if tuple(tgt_seg.shape[:2]) != (B, self._cfg["n_classes"]) or tgt_seg.shape[-2] > H or tgt_seg.shape[-1] > W:
+            raise ValueError(f"forward_loss: mask {tuple(tgt_seg.shape)} does not fit the network output")
+        if tgt_heat is not None and tuple(tgt_heat.shape) != (B, nl) + tuple(tgt_seg.shape[-2:]):
+            raise ValueError("forward_loss: heat-map target shape disagrees with the mask")
+        x = x.contiguous()
+        self._ensure_engine(x.device)
+        self._bind(x.device)
+        params, self._grad_params = self._state_cache[1], self._state_cache[2]
+        return _UNetLossFunction.apply(self, x, tgt_seg, tgt_heat, skip_bg, dice_wgt, heat_wgt, *params)
 
     # ------------------------------------------------------------------
     # nn.Module interface

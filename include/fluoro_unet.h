@@ -193,6 +193,22 @@ int fu_loss_forward(const fu_loss_desc* d, double* sums, float* loss_out, void* 
 int fu_loss_backward(const fu_loss_desc* d, const double* sums, const float* dloss, int H, int W,
                      int r0, int c0, float* d_seg, float* d_heat, void* stream);
 
+/* The same loss INSIDE the network's head kernels (SURVEY 8f row 1 as specified; replaces the sequence
+ * net(x) -> center_crop -> DiceAndHeatMapLoss2D -> loss.backward() of train.py:407-422 for one training step):
+ *   fu_forward_loss  = fu_forward(training = 1, save = 1) whose head kernel also reduces the Dice / NCC sums of its own
+ *                      outputs against the targets of `d` (d->seg / d->heat are ignored: the predictions need not leave
+ *                      the kernel), then the one-block finalisation -> loss_out (one device float).  `seg` may be NULL
+ *                      (class probabilities are then not written at all); `heat` (B,num_lands,H,W) is written and must be
+ *                      handed to fu_backward_loss unchanged.  (r0, c0) is the crop-window origin (util.py:99-103).
+ *   fu_backward_loss = fu_backward whose head kernel forms d_seg / d_heat per pixel from the targets, the sums and the
+ *                      upstream gradient `dloss` (one device float) -- no gradient tensors are written or read.
+ * bf16 storage, the paper heads (32 features, 7 classes, 0 or 14 landmarks) and H*W % 16 == 0 only:
+ * FU_ERR_UNSUPPORTED_SHAPE otherwise (use fu_forward + fu_loss_forward + fu_loss_backward + fu_backward). */
+int fu_forward_loss(fu_engine* e, const float* x, int B, int H, int W, int64_t weights_version, const fu_loss_desc* d,
+                    int r0, int c0, double* sums, float* loss_out, float* seg, float* heat, void* stream);
+int fu_backward_loss(fu_engine* e, const fu_loss_desc* d, int r0, int c0, const double* sums, const float* dloss,
+                     const float* heat, float* flat_grads, void* stream);
+
 /* ---- callers either side of the path ---------------------------------------
  * Sample preparation before the network and inference post-processing after it, as device kernels
  * on the tensors the reference's host code holds (fp32 NCHW, u1 labels).  Stateless (no engine

@@ -94,3 +94,61 @@ def test_fused_loss_rejects_cpu_tensors(pkg):
     seg = torch.rand(1, 7, 8, 8)
     with pytest.raises(RuntimeError):
         pkg.FusedDiceLoss2D()(seg, seg)
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=3, H=48, W=64, crop=(6, 6), nl=14, skip_bg=False, softmax=True),     # dual head, centre crop as train.py:414-417
+    dict(B=2, H=32, W=48, crop=(0, 0), nl=14, skip_bg=True, softmax=True),      # no crop, background class skipped
+    dict(B=5, H=40, W=24, crop=(4, 2), nl=0, skip_bg=False, softmax=True),      # seg-only (train.py:327), uneven crop
+    dict(B=2, H=48, W=48, crop=(6, 6), nl=14, skip_bg=False, softmax=False),    # logits as segmentation output
+])
+def test_loss_inside_the_heads_kernels_matches_the_separate_loss(pkg, case):
+    """UNet.forward_loss (fu_forward_loss / fu_backward_loss: Dice / NCC sums from the head kernel, loss gradient formed in the
+    backward head kernel) against criterion(net(x), target) -- the same network, the same arithmetic as separate kernels.  The
+    loss must agree to fp32 rounding and every parameter gradient to the bf16 rounding of the head's feature gradient."""
+    dev = torch.device("cuda:0")
+    B, H, W, nl = case["B"], case["H"], case["W"], case["nl"]
+    kw = dict(n_classes=7, depth=3, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=nl, do_soft_max=case["softmax"])
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 1, H, W, generator=g).to(dev)
+    Ht, Wt = H - 2 * case["crop"][0], W - 2 * case["crop"][1]
+    mask = torch.nn.functional.one_hot(torch.randint(0, 7, (B, Ht, Wt), generator=g), 7).permute(0, 3, 1, 2).float().contiguous().to(dev)
+    heat = torch.rand(B, nl, Ht, Wt, generator=g).to(dev) if nl else None
+    crit = (pkg.FusedDiceAndHeatMapLoss2D(skip_bg=case["skip_bg"], heatmap_wgt=0.5) if nl else pkg.FusedDiceLoss2D(skip_bg=case["skip_bg"]))
+    target = (mask, heat) if nl else mask
+    res = {}
+    for mode in ("fused", "separate"):
+        torch.manual_seed(0)
+        net = pkg.UNet(precision="bf16", **kw).to(dev).train()
+        if mode == "fused":
+            loss = net.forward_loss(x, target, crit)
+        else:
+            loss = crit(net(x), target)
+        (loss * 3.0).backward()                 # a non-trivial upstream gradient
+        torch.cuda.synchronize()
+        res[mode] = (float(loss), {n: p.grad.cpu() for n, p in net.named_parameters() if p.grad is not None},
+                     {n: b.cpu() for n, b in net.named_buffers()})
+    lf, ls = res["fused"][0], res["separate"][0]
+    assert abs(lf - ls) < 2e-6 * max(1.0, abs(ls)), (lf, ls)
+    assert set(res["fused"][1]) == set(res["separate"][1])
+    for k, v in res["fused"][1].items():
+        w = res["separate"][1][k]
+        e = float((v.double() - w.double()).norm() / (w.double().norm() + 1e-30))
+        assert e < (5e-3 if k.startswith(("seg", "lands")) else 3e-2), (k, e)
+    for k, v in res["fused"][2].items():        # BN running statistics: the forward is the same forward
+        assert torch.allclose(v.double(), res["separate"][2][k].double(), rtol=1e-6, atol=1e-9), k
+
+
+def test_forward_loss_rejects_what_it_cannot_fuse(pkg):
+    dev = torch.device("cuda:0")
+    kw = dict(n_classes=7, depth=2, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=0)
+    x = torch.randn(1, 1, 16, 16).to(dev)
+    mask = torch.zeros(1, 7, 16, 16, device=dev)
+    net32 = pkg.UNet(precision="fp32", **kw).to(dev).train()
+    with pytest.raises(ValueError):
+        net32.forward_loss(x, mask, pkg.FusedDiceLoss2D(skip_bg=False))          # parity modes keep the separate kernels
+    net = pkg.UNet(precision="bf16", **kw).to(dev).train()
+    with pytest.raises(TypeError):
+        net.forward_loss(x, mask, pkg.DiceLoss2D(skip_bg=False))
+    with pytest.raises(RuntimeError):
+        net.eval().forward_loss(x, mask, pkg.FusedDiceLoss2D(skip_bg=False))
