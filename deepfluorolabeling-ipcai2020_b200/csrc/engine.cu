@@ -119,6 +119,13 @@ struct fu_engine {
   double* dscr_fwd = nullptr; size_t dscr_fwd_bytes = 0;
   double* dscr_bwd = nullptr; size_t dscr_bwd_bytes = 0;
   char* wgrad_scr = nullptr; size_t wgrad_scr_bytes = 0;   // tensor-core weight-gradient accumulators
+  bool wgrad_scr_clean = false;  // all zeros: set by a backward that ran to its end (tc_unpack_batched_kernel reads and clears)
+  // Slices of the flat gradient buffer that the unpack launches OVERWRITE (97 % of it) need no zeroing: after the first
+  // backward of a plan only the gaps between them (biases, BatchNorm, first layer, heads: accumulated with atomics) are
+  // zeroed, by one kernel over a table of ranges.
+  std::vector<std::pair<long long, long long>> cover_now;   // (offset, floats) of this backward's unpack jobs
+  bool gaps_valid = false; unsigned long long cover_hash = 0;
+  long long* gap_tbl = nullptr; int n_gaps = 0; int gap_cap = 0;
   float *ones = nullptr, *zeros = nullptr;
   float* heads_gacc = nullptr;   // [NL*(CF+NC) + NC*CF] accumulators of the fused heads backward
   // the training loss inside the heads kernels (fu_forward_loss / fu_backward_loss): set for the duration of such a call
@@ -583,6 +590,7 @@ void carve_plan(fu_engine* e, Plan& pl, Bump& b, int B, int H, int W) {
 int ensure_plan(fu_engine* e, int B, int H, int W) {
   Plan& pl = e->plan;
   if (pl.valid && pl.B == B && pl.H == H && pl.W == W) return FU_OK;
+  e->gaps_valid = false;          // a new plan may send other layers through the tensor-core weight gradients
   const int D = e->cfg.depth;
   if (B < 1 || H < 1 || W < 1 || (H % (1 << (D - 1))) || (W % (1 << (D - 1))))
     return e->fail(FU_ERR_UNSUPPORTED_SHAPE,
@@ -1154,10 +1162,63 @@ int channel_sum_to(fu_engine* e, const View& d, long long P, double* scratch, fl
   return FU_OK;
 }
 
+__global__ void __launch_bounds__(256) zero_ranges_kernel(float* base, const long long* __restrict__ ranges /* (offset, floats) pairs */, int n) {
+  pdl_wait(); pdl_trigger();
+  // (every block walks every range: the ranges are few (~100) and of very different lengths)
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  for (int r = 0; r < n; ++r) {
+    float* p = base + ranges[2 * r];
+    const long long len = ranges[2 * r + 1];
+    for (long long i = t0; i < len; i += step) p[i] = 0.f;
+  }
+}
+
+// After a backward: which slices of the flat gradient did the unpack launches overwrite?  The first time (per plan) the gaps
+// between them are tabulated for zero_ranges_kernel; afterwards the coverage must not change (same plan, same kernels) --
+// a backward that covered something else than its zeroing assumed fails loudly.
+int update_flat_gaps(fu_engine* e) {
+  std::sort(e->cover_now.begin(), e->cover_now.end());
+  unsigned long long h = 1469598103934665603ull;
+  for (const auto& c : e->cover_now) { h = (h ^ (unsigned long long)c.first) * 1099511628211ull; h = (h ^ (unsigned long long)c.second) * 1099511628211ull; }
+  if (e->gaps_valid) {
+    if (h != e->cover_hash) {
+      e->gaps_valid = false;
+      return e->fail(FU_ERR_STATE, "internal: the weight-gradient unpack coverage changed between two backward passes of one plan");
+    }
+    return FU_OK;
+  }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(e->stream, &cap);
+  if (cap != cudaStreamCaptureStatusNone || !tc_env_int("FU_FLAT_GAPS", 1)) return FU_OK;   // (tabulated outside captures only)
+  std::vector<long long> tbl;
+  long long pos = 0;
+  for (const auto& c : e->cover_now) {
+    if (c.first < pos) return FU_OK;                      // overlapping slices: keep the full memset
+    if (c.first > pos) { tbl.push_back(pos); tbl.push_back(c.first - pos); }
+    pos = c.first + c.second;
+  }
+  if (pos > e->grad_numel) return FU_OK;
+  if (pos < e->grad_numel) { tbl.push_back(pos); tbl.push_back(e->grad_numel - pos); }
+  const int n = (int)(tbl.size() / 2);
+  long long gap_total = 0;
+  for (int i = 0; i < n; ++i) gap_total += tbl[2 * i + 1];
+  if (gap_total * 4 > e->grad_numel || n > 4096) return FU_OK;      // little is overwritten (CUDA-core modes): keep the plain memset
+  if (n > e->gap_cap) {
+    if (e->gap_tbl) cudaFree(e->gap_tbl);
+    e->gap_tbl = nullptr; e->gap_cap = 0;
+    CUDA_TRY(e, cudaMalloc(&e->gap_tbl, (size_t)(n + 16) * 2 * sizeof(long long)));
+    e->gap_cap = n + 16;
+  }
+  if (n > 0) CUDA_TRY(e, cudaMemcpy(e->gap_tbl, tbl.data(), tbl.size() * sizeof(long long), cudaMemcpyHostToDevice));
+  e->n_gaps = n; e->cover_hash = h; e->gaps_valid = true;
+  return FU_OK;
+}
+
 // [taps][M][N] accumulators of the tensor-core weight gradients registered so far -> torch layout, one launch.
 // part 0 = the mid-backward flush (device table half 0), part 1 = the final one.
 int flush_unpack(fu_engine* e, float* flat, int part) {
   if (e->batch.unpack.empty()) return FU_OK;
+  for (const auto& j : e->batch.unpack) e->cover_now.push_back({j.dw_off, (long long)j.M * j.N * j.taps});
   const int half = fu_engine::kJobCap / 2;
   e->set_tag(0, 0, "wgrad_unpack");
   if (e->prof) e->prof_begin("tc_unpack_batched_kernel");
@@ -1384,10 +1445,16 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   e->batch.unpack.clear();
   e->batch.flat = flat;
   struct SinkGuard { SinkGuard(TcBatch* b) { tc_batch() = b; } ~SinkGuard() { tc_batch() = nullptr; } } sink_guard(&e->batch);
-  CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
+  e->cover_now.clear();
+  if (e->gaps_valid && e->n_gaps > 0) {
+    LAUNCH(e, zero_ranges_kernel, (unsigned)(e->num_sms * 2), 256, flat, (const long long*)e->gap_tbl, e->n_gaps);
+  } else if (!e->gaps_valid) {
+    CUDA_TRY(e, cudaMemsetAsync(flat, 0, (size_t)e->grad_numel * sizeof(float), e->stream));
+  }
   CUDA_TRY(e, cudaMemsetAsync(e->dscr_bwd, 0, e->dscr_bwd_bytes, e->stream));
-  if (e->cfg.precision != FU_PRECISION_FP32 && e->wgrad_scr_bytes > 512)
+  if (e->cfg.precision != FU_PRECISION_FP32 && e->wgrad_scr_bytes > 512 && !e->wgrad_scr_clean)
     CUDA_TRY(e, cudaMemsetAsync(e->wgrad_scr, 0, e->wgrad_scr_bytes, e->stream));
+  e->wgrad_scr_clean = false;
   // ---- heads ----
   e->set_tag(0, 0, "heads_bwd");
   View feat = slice(pl.hcat, 0, e->Cf, esz);
@@ -1605,7 +1672,9 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
   }
   side_join(e);                  // every weight gradient has been accumulated before anything reads it
   if ((rc = flush_unpack(e, flat, 1))) return rc;     // the shallow layers' gradients (the deep ones went out mid-way)
-  return flush_deferred_sums(e);
+  if ((rc = flush_deferred_sums(e))) return rc;
+  e->wgrad_scr_clean = true;     // every accumulator that was written this step has been read and cleared
+  return update_flat_gaps(e);
 }
 
 int validate(const fu_config* c, std::string& why) {
@@ -1682,6 +1751,7 @@ void fu_engine_destroy(fu_engine* e) {
   if (e->dscr_fwd) cudaFree(e->dscr_fwd);
   if (e->dscr_bwd) cudaFree(e->dscr_bwd);
   if (e->wgrad_scr) cudaFree(e->wgrad_scr);
+  if (e->gap_tbl) cudaFree(e->gap_tbl);
   if (e->loss_coef) cudaFree(e->loss_coef);
   if (e->pack_tbl) cudaFree(e->pack_tbl);
   if (e->unpack_tbl) cudaFree(e->unpack_tbl);

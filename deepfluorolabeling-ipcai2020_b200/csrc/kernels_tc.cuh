@@ -2280,7 +2280,10 @@ __global__ void __launch_bounds__(256) tc_pack_batched_kernel(const TcPackJob* j
   else tc_pack_tile<1>(J, lb, tile);
 }
 
-// dw[(m*N + n)*taps + t] = acc[(t*M + m)*N + n]: tiles of 8 m x 32 n, reads and writes both contiguous
+// dw[(m*N + n)*taps + t] = acc[(t*M + m)*N + n]: tiles of 8 m x 32 n, reads and writes both contiguous.
+// READ AND CLEAR: every accumulator element is zeroed right after it is read, so the accumulators are clean for the next
+// step's split-K reductions and the engine does not memset them (136 MB at the head of every backward, on the critical
+// path) -- the zeros are written here instead, on the side stream beside the data-gradient chain.
 __global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJob* jobs, int njobs, float* base) {
   pdl_wait(); pdl_trigger();
   __shared__ int s_job;
@@ -2291,8 +2294,8 @@ __global__ void __launch_bounds__(256) tc_unpack_batched_kernel(const TcUnpackJo
   const int m0 = (lb / tiles_n) * 8, n0 = (lb % tiles_n) * 32;
   const int lane = threadIdx.x & 31, m = threadIdx.x >> 5;      // warp = one m row, lane = n column
   if (m0 + m < J.M) {
-    const float* src = J.acc + ((long long)(m0 + m)) * J.N + n0 + lane;
-    for (int t = 0; t < taps; ++t) tile[m][lane * taps + t] = src[(long long)t * J.M * J.N];
+    float* src = const_cast<float*>(J.acc) + ((long long)(m0 + m)) * J.N + n0 + lane;
+    for (int t = 0; t < taps; ++t) { tile[m][lane * taps + t] = src[(long long)t * J.M * J.N]; src[(long long)t * J.M * J.N] = 0.f; }
   }
   __syncwarp();
   if (m0 + m < J.M) {

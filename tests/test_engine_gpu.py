@@ -600,3 +600,31 @@ def test_tensor_core_heads_agree_with_cuda_core_heads(pkg, shape, softmax):
         # head weights: same bf16 single-pass outer products in both, different summation order; everything upstream
         # sees d_feat rounded to bf16 from values that differ in the last fp32 bits (a rounding flip = 2^-9 of one element)
         assert e < (5e-3 if head else 3e-2), (k, e)
+
+
+def test_repeated_backward_passes_give_the_same_gradients(pkg):
+    """The first backward of a plan zeroes the whole flat gradient and the weight-gradient accumulators; later ones zero
+    only the gaps the unpack launches do not overwrite and rely on the accumulators having been read-and-cleared
+    (engine.cu: update_flat_gaps, tc_unpack_batched_kernel).  Same weights, same input: every pass must return the same
+    gradients, also after the engine has switched to another input shape and back."""
+    dev = torch.device("cuda:0")
+    kw = dict(n_classes=7, depth=4, wf=5, batch_norm=True, padding=True, max_pool=False, num_lands=14)
+    torch.manual_seed(0)
+    net = pkg.UNet(precision="bf16", **kw).to(dev).train()
+    g = torch.Generator().manual_seed(9)
+    xs = {s: torch.randn(2, 1, s[0], s[1], generator=g).to(dev) for s in ((64, 96), (48, 48))}
+
+    def grads(x):
+        net.zero_grad(set_to_none=True)
+        seg, heat = net(x)
+        (seg.square().mean() + heat.square().mean()).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    # BN running statistics move between passes, batch statistics (train mode) do not depend on them
+    ref = {s: grads(x) for s, x in xs.items()}
+    for _ in range(2):
+        for s, x in xs.items():
+            got = grads(x)
+            for k, v in got.items():
+                e = rel_l2(v.cpu(), ref[s][k].cpu())
+                assert e < 1e-4, (s, k, e)          # split-K reductions add in a run-dependent order: not bit-identical
