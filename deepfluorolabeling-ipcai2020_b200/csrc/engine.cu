@@ -878,6 +878,17 @@ int conv_forward(fu_engine* e, ConvW& cw, const View& x, const View& y, int B, i
     a.B = B; a.H = H; a.W = W; a.k = cw.k; a.pad = cw.k / 2; a.relu = relu;
     if (t) { a.t = t->p; a.t_ld = t->ld; a.bn_a = bn_a; a.bn_b = bn_b; }
     a.stat = stat;
+    if constexpr (sizeof(T) == 2) {
+      // bf16 storage, 3x3, 32 output channels, no second epilogue operand: warp-level tensor-core MMAs (conv_cin1_mma_kernel)
+      if (cw.Cin == 1 && cw.Cout == 32 && cw.k == 3 && !t && W % 16 == 0 && y.ld % 8 == 0 && aligned(y.p, 16) &&
+          (long long)B * H * W < (1ll << 30) && tc_env_int("FU_CIN1_MMA", 1)) {
+        const long long tiles = (long long)B * H * (W / 16);
+        const unsigned grid = (unsigned)std::min<long long>((tiles + 3) / 4, (long long)e->num_sms * tc_env_int("FU_CIN1_BPS", 16));      // blocks per SM: 8 -> 48.7 us, 16 -> 43.4 us (finer tail)
+        LAUNCH(e, (conv_cin1_mma_kernel<3>), grid, 128, reinterpret_cast<const bf16*>(x.p), x.ld, reinterpret_cast<bf16*>(y.p), y.ld,
+               tdata(e, cw.w_idx), tdata(e, cw.b_idx), relu, stat, B, H, W);
+        return FU_OK;
+      }
+    }
     if (cw.Cin == 1) {
       // C_in = 1 fast path: persistent blocks, two per SM
       const int TW = 256 / (cw.Cout / 8);
@@ -1301,6 +1312,21 @@ int conv_wgrad(fu_engine* e, ConvW& cw, const View& x, const View& dy, int B, in
     memset(&a, 0, sizeof(a));
     a.x = x.p; a.x_ld = x.ld; a.Cin = cw.Cin; a.dy = dy.p; a.dy_ld = dy.ld; a.Cout = cw.Cout;
     a.B = B; a.H = H; a.W = W; a.k = cw.k; a.pad = cw.k / 2; a.dw = dw;
+    if constexpr (sizeof(T) == 2) {
+      // bf16 storage, 32 output channels: dW = dY^T x patches on warp-level tensor-core MMAs (wgrad_cin1_mma_kernel)
+      if (cw.Cin == 1 && cw.Cout == 32 && (cw.k == 3 || cw.k == 1) && W % 16 == 0 && dy.ld % 8 == 0 && aligned(dy.p, 16) &&
+          (long long)B * H * W < (1ll << 30) && tc_env_int("FU_CIN1_MMA", 1)) {
+        const long long tiles = (long long)B * H * (W / 16);
+        const unsigned grid = (unsigned)std::min<long long>((tiles + 3) / 4, (long long)e->num_sms * 8);
+        if (cw.k == 3)
+          LAUNCH(e, (wgrad_cin1_mma_kernel<3>), grid, 128, reinterpret_cast<const bf16*>(x.p), x.ld, reinterpret_cast<const bf16*>(dy.p),
+                 dy.ld, dw, B, H, W);
+        else
+          LAUNCH(e, (wgrad_cin1_mma_kernel<1>), grid, 128, reinterpret_cast<const bf16*>(x.p), x.ld, reinterpret_cast<const bf16*>(dy.p),
+                 dy.ld, dw, B, H, W);
+        return FU_OK;
+      }
+    }
     if (cw.Cin == 1) {
       const int TW = 256 / (cw.Cout / 8);
       const long long tiles = (long long)((W + TW - 1) / TW) * ((H + cin1_tile_h(cw.k) - 1) / cin1_tile_h(cw.k)) * B;

@@ -1672,6 +1672,217 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
   for (int i = threadIdx.x; i < NG; i += blockDim.x) atomicAdd(g_acc + i, s_g[i]);
 }
 
+// --------------------------------------------------------------------------
+// First layer (C_in = 1, 32 output channels, bf16 storage) on warp-level tensor-core MMAs.  The CUDA-core kernels above spend
+// 288 FMAs per pixel (3x3) and sit on the step's critical path at both ends: the 3x3 forward is the first kernel of the
+// step, and its weight gradient can only start when the LAST data-gradient kernel of the backward has finished.
+// A warp owns tiles of 16 consecutive pixels of an image row (W % 16 == 0):
+//   forward:  y[16 pix][32] = patches[16 pix][9 taps -> K = 16] x W^T; the patch fragment is built from <= 3 scalar loads per
+//             pixel of the (L1-resident) single-channel input; weights as split-bf16 pairs in registers; output columns permuted
+//             so that a thread ends up with 8 contiguous channels of a pixel (one 16-byte store), bias / ReLU / BatchNorm
+//             statistics on the accumulator fragments;
+//   wgrad:    dW[32][9] = dY^T[32][16 pix] x patches[16 pix][9]; dY arrives as one 16-byte load per pixel row and is
+//             transposed in registers (movmatrix), accumulators persist over the block's tiles.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cin1_x_raw(const bf16* __restrict__ x, int x_ld, int n, int ih, int iw, int H, int W) {
+  return (ih >= 0 && ih < H && iw >= 0 && iw < W)
+             ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(x) + ((long long)(n * H + ih) * W + iw) * x_ld) : 0u;
+}
+
+// The (K x (16 + K - 1)) input window of a 16-pixel tile, zero padded, staged by the warp in its own shared-memory slice
+// (<= 2 coalesced loads per lane instead of 8 scattered, predicated 2-byte gathers per lane and tile); read back as
+// sw[r * 18 + c], c = pixel offset + kw.
+template <int K>
+__device__ __forceinline__ void cin1_stage_window(const bf16* __restrict__ x, int x_ld, unsigned short* sw, int n, int h, int w0, int H, int W,
+                                                  int lane) {
+  constexpr int PAD = K / 2, XW = 16 + 2 * PAD;
+  __syncwarp();                                   // the previous tile's readers are done
+#pragma unroll
+  for (int q = 0; q < (K * XW + 31) / 32; ++q) {
+    const int i = lane + 32 * q;
+    if (i < K * XW) {
+      const int r = i / XW, c = i - r * XW;
+      sw[r * 18 + c] = (unsigned short)cin1_x_raw(x, x_ld, n, h + r - PAD, w0 + c - PAD, H, W);
+    }
+  }
+  __syncwarp();
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) conv_cin1_mma_kernel(const bf16* __restrict__ x, int x_ld, bf16* __restrict__ y, int y_ld,
+                                                            const float* __restrict__ w /* (32, 1, K, K) */, const float* bias,
+                                                            int relu, double* stat, int B, int H, int W) {
+  pdl_wait(); pdl_trigger();
+  constexpr int KK = K * K, PAD = K / 2, CO = 32;
+  static_assert(KK <= 16, "taps must fit one K step");
+  __shared__ float part[4][2 * CO];
+  __shared__ unsigned short s_win[4][3 * 18];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  unsigned short* sw = s_win[wrp];
+  // B fragments: K = tap, column n = g of tile j <-> channel 8 (g / 2) + 2 j + (g & 1)
+  uint32_t bw_hi[4][2], bw_lo[4][2];
+  float bb[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ch = 8 * (g >> 1) + 2 * j + (g & 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int tap = 2 * t + 8 * h;
+      const float a = tap < KK ? w[ch * KK + tap] : 0.f, b = tap + 1 < KK ? w[ch * KK + tap + 1] : 0.f;
+      float ra, rb;
+      bw_hi[j][h] = heads_pack_hi(a, b, ra, rb);
+      bw_lo[j][h] = heads_pack(ra, rb);
+    }
+    // accumulator columns 2t, 2t+1 of tile j are channels 8t + 2j, 8t + 2j + 1
+    bb[j][0] = bias ? bias[8 * t + 2 * j] : 0.f; bb[j][1] = bias ? bias[8 * t + 2 * j + 1] : 0.f;
+  }
+  float cs[4][2], cq[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { cs[j][0] = cs[j][1] = cq[j][0] = cq[j][1] = 0.f; }
+  const int W16 = W >> 4;
+  const int ntiles = B * H * W16;
+  const int warp_g = blockIdx.x * 4 + wrp, nwarps = gridDim.x * 4;
+  for (int tile = warp_g; tile < ntiles; tile += nwarps) {
+    const int rr = tile / W16, w0 = (tile - rr * W16) * 16;
+    const int n = rr / H, h = rr - n * H;
+    // patch fragments: row g / g + 8 = pixels w0 + g / w0 + g + 8; K = taps 2t, 2t+1 | 2t+8, 2t+9
+    uint32_t a[4];
+    cin1_stage_window<K>(x, x_ld, sw, n, h, w0, H, W, lane);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int tap = 2 * t + (e & 1) + 8 * (e >> 1);
+        v[e] = tap < KK ? (uint32_t)sw[(tap / K) * 18 + g + 8 * half + tap % K] : 0u;
+      }
+      a[half] = v[0] | (v[1] << 16);
+      a[2 + half] = v[2] | (v[3] << 16);
+    }
+    const long long pix0 = ((long long)n * H + h) * W + w0;
+    uint32_t o0[4], o1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(c, a, bw_hi[j]);
+      mma_bf16_16816(c, a, bw_lo[j]);
+      c[0] += bb[j][0]; c[1] += bb[j][1]; c[2] += bb[j][0]; c[3] += bb[j][1];
+      if (relu) { c[0] = fmaxf(c[0], 0.f); c[1] = fmaxf(c[1], 0.f); c[2] = fmaxf(c[2], 0.f); c[3] = fmaxf(c[3], 0.f); }
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(c[0], c[1]), p1 = __floats2bfloat162_rn(c[2], c[3]);
+      o0[j] = *reinterpret_cast<const uint32_t*>(&p0); o1[j] = *reinterpret_cast<const uint32_t*>(&p1);
+      if (stat) {     // statistics of the STORED (rounded) values, as every other producer of a BatchNorm input does
+        const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+        cs[j][0] += f0.x + f1.x; cs[j][1] += f0.y + f1.y;
+        cq[j][0] = fmaf(f0.x, f0.x, fmaf(f1.x, f1.x, cq[j][0])); cq[j][1] = fmaf(f0.y, f0.y, fmaf(f1.y, f1.y, cq[j][1]));
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (pix0 + g) * y_ld + 8 * t) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+    *reinterpret_cast<uint4*>(y + (pix0 + g + 8) * y_ld + 8 * t) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+  }
+  if (stat) {
+    // lanes with equal t hold the same channels: fixed-order shuffle tree over g, then the block's four warps in order
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          cs[j][e] += __shfl_xor_sync(0xffffffffu, cs[j][e], o);
+          cq[j][e] += __shfl_xor_sync(0xffffffffu, cq[j][e], o);
+        }
+    if (g == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          part[wrp][8 * t + 2 * j + e] = cs[j][e];
+          part[wrp][CO + 8 * t + 2 * j + e] = cq[j][e];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * CO) {
+      const float v = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
+      atomicAdd(&stat[threadIdx.x], (double)v);
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) wgrad_cin1_mma_kernel(const bf16* __restrict__ x, int x_ld, const bf16* __restrict__ dy, int dy_ld,
+                                                             float* dw /* (32, 1, K, K) */, int B, int H, int W) {
+  pdl_wait(); pdl_trigger();
+  constexpr int KK = K * K, PAD = K / 2, CO = 32, NT = KK > 8 ? 2 : 1;
+  __shared__ float s_dw[CO * KK];
+  __shared__ unsigned short s_win[4][3 * 18];
+  for (int i = threadIdx.x; i < CO * KK; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  unsigned short* sw = s_win[wrp];
+  float acc[2][NT][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  const int W16 = W >> 4;
+  const int ntiles = B * H * W16;
+  const int warp_g = blockIdx.x * 4 + wrp, nwarps = gridDim.x * 4;
+  auto load_rows = [&](int tile, uint4& q0, uint4& q1) {
+    q0 = make_uint4(0u, 0u, 0u, 0u); q1 = q0;
+    if (tile < ntiles) {
+      const long long pix0 = (long long)tile * 16;        // (tiles are numbered in pixel order: 16 consecutive pixels)
+      q0 = *reinterpret_cast<const uint4*>(dy + (pix0 + g) * dy_ld + 8 * t);
+      q1 = *reinterpret_cast<const uint4*>(dy + (pix0 + g + 8) * dy_ld + 8 * t);
+    }
+  };
+  uint4 nq0, nq1;
+  load_rows(warp_g, nq0, nq1);
+  for (int tile = warp_g; tile < ntiles; tile += nwarps) {
+    const uint4 q0 = nq0, q1 = nq1;
+    load_rows(tile + nwarps, nq0, nq1);
+    const int rr = tile / W16, w0 = (tile - rr * W16) * 16;
+    const int n = rr / H, h = rr - n * H;
+    // dY^T: block j of a thread's 16-byte row = logical columns (2t, 2t+1) <-> channels 8t + 2j (+1); transposed, row g' of
+    // block j is channel 8 (g' / 2) + 2 j + (g' & 1), K = pixels
+    const uint32_t lo[4] = {movm_trans(q0.x), movm_trans(q0.y), movm_trans(q0.z), movm_trans(q0.w)};    // pixels 0..7
+    const uint32_t hi[4] = {movm_trans(q1.x), movm_trans(q1.y), movm_trans(q1.z), movm_trans(q1.w)};    // pixels 8..15
+    // patches as B operand: K = pixels 2t, 2t+1 | 2t+8, 2t+9, column n = tap g (tile 1: tap 8 in column 0)
+    uint32_t b[NT][2];
+    cin1_stage_window<K>(x, x_ld, sw, n, h, w0, H, W, lane);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int tap = 8 * j + g;
+      uint32_t v[4] = {0u, 0u, 0u, 0u};
+      if (tap < KK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (uint32_t)sw[(tap / K) * 18 + 2 * t + (e & 1) + 8 * (e >> 1) + tap % K];
+      }
+      b[j][0] = v[0] | (v[1] << 16); b[j][1] = v[2] | (v[3] << 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t a[4] = {lo[2 * i], lo[2 * i + 1], hi[2 * i], hi[2 * i + 1]};
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma_bf16_16816(acc[i][j], a, b[j]);
+    }
+  }
+  // fragment (i, j): rows g (block 2i) and g + 8 (block 2i + 1) -> channels; columns 2t, 2t+1 -> taps 8j + 2t (+1)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int tap = 8 * j + 2 * t + e;
+        if (tap < KK) {
+          const int ch0 = 8 * (g >> 1) + 2 * (2 * i) + (g & 1), ch1 = 8 * (g >> 1) + 2 * (2 * i + 1) + (g & 1);
+          atomicAdd(&s_dw[ch0 * KK + tap], acc[i][j][e]);
+          atomicAdd(&s_dw[ch1 * KK + tap], acc[i][j][2 + e]);
+        }
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CO * KK; i += blockDim.x) atomicAdd(dw + i, s_dw[i]);
+}
+
 // Per-plane coefficients of the loss gradient (closed forms of loss_backward_kernel) from the forward's sums and the
 // upstream gradient of the loss: class planes (A, Bc), landmark planes (ka, kb, kc).  One thread per plane.
 __global__ void loss_coef_kernel(const double* __restrict__ sums, const float* __restrict__ dloss, float* __restrict__ coef,
