@@ -126,6 +126,7 @@ struct fu_engine {
   std::vector<std::pair<long long, long long>> cover_now;   // (offset, floats) of this backward's unpack jobs
   bool gaps_valid = false; unsigned long long cover_hash = 0;
   long long* gap_tbl = nullptr; int n_gaps = 0; int gap_cap = 0;
+  std::vector<long long> gap_host;          // host copy of the table (source of the stream-ordered upload)
   float *ones = nullptr, *zeros = nullptr;
   float* heads_gacc = nullptr;   // [NL*(CF+NC) + NC*CF] accumulators of the fused heads backward
   // the training loss inside the heads kernels (fu_forward_loss / fu_backward_loss): set for the duration of such a call
@@ -1215,12 +1216,14 @@ int update_flat_gaps(fu_engine* e) {
   for (int i = 0; i < n; ++i) gap_total += tbl[2 * i + 1];
   if (gap_total * 4 > e->grad_numel || n > 4096) return FU_OK;      // little is overwritten (CUDA-core modes): keep the plain memset
   if (n > e->gap_cap) {
-    if (e->gap_tbl) cudaFree(e->gap_tbl);
+    if (e->gap_tbl) { cudaStreamSynchronize(e->stream); cudaFree(e->gap_tbl); }
     e->gap_tbl = nullptr; e->gap_cap = 0;
     CUDA_TRY(e, cudaMalloc(&e->gap_tbl, (size_t)(n + 16) * 2 * sizeof(long long)));
     e->gap_cap = n + 16;
   }
-  if (n > 0) CUDA_TRY(e, cudaMemcpy(e->gap_tbl, tbl.data(), tbl.size() * sizeof(long long), cudaMemcpyHostToDevice));
+  // (ordered on the engine's stream: an earlier backward's zero_ranges_kernel may still be reading the old table)
+  e->gap_host = tbl;
+  if (n > 0) CUDA_TRY(e, cudaMemcpyAsync(e->gap_tbl, e->gap_host.data(), e->gap_host.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
   e->n_gaps = n; e->cover_hash = h; e->gaps_valid = true;
   return FU_OK;
 }
