@@ -2619,8 +2619,11 @@ inline TcConv::Cached* tc_prepare(TcConv& t, int dir, const void* x, int x_ld, v
   // ... and the other way round on the smallest levels (6x6: 9 pixel tiles): narrower N tiles until at least ~60 % of
   // the SMs have one (72 CTAs of 128 columns leave half the machine idle; 144 of 64 columns re-read A twice as often
   // but finish sooner)
+  // (32-column tiles only when 64-column ones would leave three quarters of the machine idle: every N tile re-reads the same A
+  //  tiles through the L2, and at 1024 -> 512 @6x6 (data gradient, 144 k-iterations) 144 CTAs of 32 columns took 46.3 us where 72 CTAs
+  //  of 64 columns take 30.9 us and 36 of 128 columns 35.5 us)
   if (getenv("FU_TC_BN_MAX") == nullptr)
-    while (bn > 32 && (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / bn) * 10 < 6ll * sms) bn >>= 1;
+    while (bn > 32 && (long long)p.tiles_w * p.tiles_h * p.tiles_b * (N / bn) * 10 < (bn > 64 ? 6ll : 2ll) * sms) bn >>= 1;
   p.BN = bn;
   p.CS = (bn >= 64 && !t.split) ? 64 : 32;
   p.n_tiles = N / p.BN;
