@@ -1503,7 +1503,7 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
       const bool use_mma = tc_env_int("FU_HEADS_MMA", 1) != 0;
       if (use_mma && P0 < (1ll << 30) && feat.ld % 8 == 0 && d_feat.ld % 8 == 0 && reinterpret_cast<uintptr_t>(feat.p) % 16 == 0 &&
           reinterpret_cast<uintptr_t>(d_feat.p) % 16 == 0) {
-        const unsigned gridm = (unsigned)std::min<long long>((P0 + 63) / 64, (long long)e->num_sms * 3);
+        const unsigned gridm = (unsigned)std::min<long long>((P0 + 63) / 64, (long long)e->num_sms * 4);      // 4 resident blocks per SM
         HeadsLoss hl;
         memset(&hl, 0, sizeof(hl));
         if (e->lossf) {
@@ -2018,7 +2018,16 @@ int fu_loss_forward(const fu_loss_desc* d, double* sums, float* loss_out, void* 
   if (cudaMemsetAsync(sums, 0, ws, st) != cudaSuccess) { g_create_error = "fu_loss_forward: memset failed"; return FU_ERR_CUDA; }
   a.rows = loss_rows_per_block(a.Ht, (long long)a.B * (a.NC + a.NL));
   const dim3 grid((unsigned)((a.Ht + a.rows - 1) / a.rows), (unsigned)(a.B * (a.NC + a.NL)));
-  loss_sums_kernel<<<grid, 256, 0, st>>>(a);
+  {
+    auto al8 = [](const void* p_) { return reinterpret_cast<uintptr_t>(p_) % 8 == 0; };
+    auto even = [](long long v) { return (v & 1) == 0; };
+    const bool vec2 = even(a.Wt) && al8(a.seg) && al8(a.mask) && even(a.seg_sb) && even(a.seg_sc) && even(a.seg_sr) && even(a.mask_sb) &&
+                      even(a.mask_sc) && even(a.mask_sr) &&
+                      (!a.heat || (al8(a.heat) && al8(a.heat_t) && even(a.heat_sb) && even(a.heat_sc) && even(a.heat_sr) &&
+                                   even(a.heat_t_sb) && even(a.heat_t_sc) && even(a.heat_t_sr))) && tc_env_int("FU_LOSS_VEC", 1) != 0;
+    if (vec2) loss_sums_kernel<true><<<grid, 256, 0, st>>>(a);
+    else loss_sums_kernel<false><<<grid, 256, 0, st>>>(a);
+  }
   loss_finalize_kernel<<<1, 256, 0, st>>>(a, loss_out);
   cudaError_t ce = cudaPeekAtLastError();
   if (ce != cudaSuccess) { g_create_error = std::string("fu_loss_forward: ") + cudaGetErrorString(ce); return FU_ERR_CUDA; }

@@ -78,6 +78,10 @@ __device__ __forceinline__ double block_sum_n(double (&v)[N], double (*sm)[8]) {
 }
 
 // grid: (row chunks of the window, B*(NC+NL) planes)
+// VEC2: two columns per lane and load (8-byte loads; the window origin of the predictions is 8- but not 16-byte aligned for the
+// reference's crops: (192 - 180) / 2 = 6 columns).  The pass is bound by bytes in flight -- 3.3 TB/s with 4-byte loads, measured
+// alone under ncu -- not by arithmetic.  Preconditions (launcher): Wt, all strides even, all plane / window bases 8-byte aligned.
+template <bool VEC2>
 __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
   __shared__ double sm[5][8];
   const int plane = blockIdx.y;
@@ -99,6 +103,18 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
         xr[u] = x + (long long)ru * p.seg_sr; tr[u] = t + (long long)ru * p.mask_sr;
       }
       float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};   // <= 8 columns per lane and row
+      if (VEC2) {
+        for (int col = lane; col < (p.Wt >> 1); col += 32) {
+          float2 xv[4], tv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { xv[u] = reinterpret_cast<const float2*>(xr[u])[col]; tv[u] = reinterpret_cast<const float2*>(tr[u])[col]; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a0[u] = fmaf(tv[u].x, xv[u].x, fmaf(tv[u].y, xv[u].y, a0[u])); a1[u] = fmaf(tv[u].x, tv[u].x, fmaf(tv[u].y, tv[u].y, a1[u]));
+            a2[u] = fmaf(xv[u].x, xv[u].x, fmaf(xv[u].y, xv[u].y, a2[u]));
+          }
+        }
+      } else
       for (int col = lane; col < p.Wt; col += 32) {
         float xv[4], tv[4];
 #pragma unroll
@@ -133,6 +149,19 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(const LossArgs p) {
       float m[4][5];
 #pragma unroll
       for (int u = 0; u < 4; ++u) m[u][0] = m[u][1] = m[u][2] = m[u][3] = m[u][4] = 0.f;
+      if (VEC2) {
+        for (int col = lane; col < (p.Wt >> 1); col += 32) {
+          float2 xf[4], yf[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { xf[u] = reinterpret_cast<const float2*>(xr[u])[col]; yf[u] = reinterpret_cast<const float2*>(yr[u])[col]; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            m[u][0] += xf[u].x + xf[u].y; m[u][1] = fmaf(xf[u].x, xf[u].x, fmaf(xf[u].y, xf[u].y, m[u][1]));
+            m[u][2] += yf[u].x + yf[u].y; m[u][3] = fmaf(yf[u].x, yf[u].x, fmaf(yf[u].y, yf[u].y, m[u][3]));
+            m[u][4] = fmaf(xf[u].x, yf[u].x, fmaf(xf[u].y, yf[u].y, m[u][4]));
+          }
+        }
+      } else
       for (int col = lane; col < p.Wt; col += 32) {
         float xf[4], yf[4];
 #pragma unroll

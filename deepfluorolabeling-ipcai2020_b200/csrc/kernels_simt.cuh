@@ -1424,7 +1424,7 @@ __device__ __forceinline__ void mma_bf16_16816_b0(float (&c)[4], const uint32_t 
 // loss_coef_kernel (closed forms of kernels_loss.cuh:loss_backward_kernel): inside the crop window
 //   d_seg = A t + Bc p,   d_heat = ka y - kb x + kc;   zero outside.
 template <int CF, int NC, int NF, int NL, bool LOSS = false>
-__global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __restrict__ feat, int ld, const float* wseg, const float* w1,
+__global__ void __launch_bounds__(128, 4) heads_bwd_mma_kernel(const bf16* __restrict__ feat, int ld, const float* wseg, const float* w1,
                                                                const float* w2, const float* __restrict__ d_seg,
                                                                const float* __restrict__ d_heat, bf16* d_feat, int d_ld,
                                                                float* g_acc /*[NL*(CF+NC) + NC*CF]*/, int P, int HW, FastDiv fd_hw,
@@ -1482,6 +1482,22 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
     bf_hi[j] = heads_pack_hi(a, b, ra, rb);
     bf_lo[j] = heads_pack(ra, rb);
   }
+  // The 36 fragment words go to shared memory ([word][lane]: the four warps hold identical values) and are re-read at their use:
+  // with them in registers the kernel needed 160 registers = 3 blocks (12 warps) per SM, too few loads in flight for a pass
+  // that moves 250 MB; now 4 blocks per SM.
+  __shared__ uint32_t s_frag[36][32];
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s_frag[i][lane] = bl_hi[i >> 1][i & 1]; s_frag[4 + i][lane] = bl_lo[i >> 1][i & 1]; }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      s_frag[8 + i][lane] = kL ? bd_hi[kL ? i >> 1 : 0][i & 1] : 0u; s_frag[18 + i][lane] = kL ? bd_lo[kL ? i >> 1 : 0][i & 1] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s_frag[28 + i][lane] = bf_hi[i]; s_frag[32 + i][lane] = bf_lo[i]; }
+  }
+  __syncthreads();
+  auto frag2 = [&](int i, uint32_t (&b)[2]) { b[0] = s_frag[i][lane]; b[1] = s_frag[i + 1][lane]; };
   // ---- weight-gradient accumulators: G1 tiles (s, h) = features 8t+4s+2h.., tile 4 = logits; Gseg tiles (s, h) ----
   float g1[kL ? 5 : 1][4], gs[4][4];
 #pragma unroll
@@ -1500,6 +1516,33 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
   uint4 nq0, nq1;
   load_rows(warp_g, nq0, nq1);
   const bool c0ok = 2 * t < NC, c1ok = 2 * t + 1 < NC;
+  // upstream gradients of a tile in fragment order (a warp load covers 4 planes x 8 consecutive pixels); like the feature rows
+  // they are requested one tile ahead (not in the LOSS variant, which derives them from targets and predictions)
+  auto load_grads = [&](int tile, float (&ds)[4], float (&dh)[2][4]) {
+    const int r0 = tile * 16 + g, r1 = r0 + 8;
+    const bool ok0 = r0 < P, ok1 = r1 < P;
+    const int n0 = fd_hw.div(ok0 ? r0 : 0), n1 = fd_hw.div(ok1 ? r1 : 0);
+    const int hw0 = (ok0 ? r0 : 0) - n0 * HW, hw1 = (ok1 ? r1 : 0) - n1 * HW;
+    ds[0] = ds[1] = ds[2] = ds[3] = 0.f;
+    if (d_seg) {
+      const float* p0 = d_seg + ((long long)n0 * NC + 2 * t) * HW + hw0;
+      const float* p1 = d_seg + ((long long)n1 * NC + 2 * t) * HW + hw1;
+      if (ok0 && c0ok) ds[0] = p0[0];
+      if (ok0 && c1ok) ds[1] = p0[HW];
+      if (ok1 && c0ok) ds[2] = p1[0];
+      if (ok1 && c1ok) ds[3] = p1[HW];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int l = 2 * t + 8 * h + e;
+        dh[0][2 * h + e] = (kL && d_heat && ok0 && l < NL) ? d_heat[((long long)n0 * NL + l) * HW + hw0] : 0.f;
+        dh[1][2 * h + e] = (kL && d_heat && ok1 && l < NL) ? d_heat[((long long)n1 * NL + l) * HW + hw1] : 0.f;
+      }
+  };
+  float nds[4] = {0.f, 0.f, 0.f, 0.f}, ndh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  if (!LOSS && warp_g < ntiles) load_grads(warp_g, nds, ndh);
   for (int tile = warp_g; tile < ntiles; tile += nwarps) {
     const int r0 = tile * 16 + g, r1 = r0 + 8;
     const bool ok0 = r0 < P, ok1 = r1 < P;
@@ -1527,15 +1570,11 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
       cf1 = lossp.coef + (long long)n1 * (NC * 2 + NL * 3);
     }
     // upstream gradients in fragment order (a warp load covers 4 planes x 8 consecutive pixels)
-    float ds[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!LOSS && d_seg) {
-      const float* p0 = d_seg + ((long long)n0 * NC + 2 * t) * HW + hw0;
-      const float* p1 = d_seg + ((long long)n1 * NC + 2 * t) * HW + hw1;
-      if (ok0 && c0ok) ds[0] = p0[0];
-      if (ok0 && c1ok) ds[1] = p0[HW];
-      if (ok1 && c0ok) ds[2] = p1[0];
-      if (ok1 && c1ok) ds[3] = p1[HW];
-    }
+    float ds[4] = {nds[0], nds[1], nds[2], nds[3]};
+    float dhp[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dhp[0][i] = ndh[0][i]; dhp[1][i] = ndh[1][i]; }
+    if (!LOSS && tile + nwarps < ntiles) load_grads(tile + nwarps, nds, ndh);
     uint32_t ah_hi[4] = {0u, 0u, 0u, 0u}, ah_lo[4] = {0u, 0u, 0u, 0u};      // dheat: rows = pixels, K = landmark
     if (kL && (LOSS || d_heat)) {
       float dh[2][4];
@@ -1559,8 +1598,8 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
             dh[0][2 * h + e] = v0; dh[1][2 * h + e] = v1;
             continue;
           }
-          dh[0][2 * h + e] = (ok0 && l < NL) ? d_heat[((long long)n0 * NL + l) * HW + hw0] : 0.f;
-          dh[1][2 * h + e] = (ok1 && l < NL) ? d_heat[((long long)n1 * NL + l) * HW + hw1] : 0.f;
+          dh[0][2 * h + e] = dhp[0][2 * h + e];
+          dh[1][2 * h + e] = dhp[1][2 * h + e];
         }
       float ra, rb;
       ah_hi[0] = heads_pack_hi(dh[0][0], dh[0][1], ra, rb); ah_lo[0] = heads_pack(ra, rb);
@@ -1570,8 +1609,11 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
     }
     const uint32_t a_k0[4] = {q0.x, q1.x, q0.y, q1.y}, a_k1[4] = {q0.z, q1.z, q0.w, q1.w};
     float lg[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_bf16_16816(lg, a_k0, bl_hi[0]); mma_bf16_16816(lg, a_k1, bl_hi[1]);
-    mma_bf16_16816(lg, a_k0, bl_lo[0]); mma_bf16_16816(lg, a_k1, bl_lo[1]);
+    {
+      uint32_t b[2];
+      frag2(0, b); mma_bf16_16816(lg, a_k0, b); frag2(2, b); mma_bf16_16816(lg, a_k1, b);
+      frag2(4, b); mma_bf16_16816(lg, a_k0, b); frag2(6, b); mma_bf16_16816(lg, a_k1, b);
+    }
     // dlg (softmax backward): lg[0], lg[1] / ds[0], ds[1]: pixel r0, classes 2t, 2t+1; [2], [3]: pixel r1
     float dlg[4] = {ds[0], ds[1], ds[2], ds[3]};
     auto loss_dseg = [&](const float (&p4)[4]) {       // LOSS: d_seg of the two pixels from the targets and the predictions p4
@@ -1610,9 +1652,15 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
     if (kL) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        mma_bf16_16816(dc[j], ah_hi, bd_hi[j]); mma_bf16_16816(dc[j], ah_hi, bd_lo[j]); mma_bf16_16816(dc[j], ah_lo, bd_hi[j]);
+        uint32_t bh[2], bl2[2];
+        frag2(8 + 2 * j, bh); frag2(18 + 2 * j, bl2);
+        mma_bf16_16816(dc[j], ah_hi, bh); mma_bf16_16816(dc[j], ah_hi, bl2); mma_bf16_16816(dc[j], ah_lo, bh);
       }
-      mma_bf16_16816(dlg, ah_hi, bd_hi[4]); mma_bf16_16816(dlg, ah_hi, bd_lo[4]); mma_bf16_16816(dlg, ah_lo, bd_hi[4]);
+      {
+        uint32_t bh[2], bl2[2];
+        frag2(16, bh); frag2(26, bl2);
+        mma_bf16_16816(dlg, ah_hi, bh); mma_bf16_16816(dlg, ah_hi, bl2); mma_bf16_16816(dlg, ah_lo, bh);
+      }
     }
     // dfeat += dlg Wseg
     float r00, r01, r10, r11;
@@ -1620,7 +1668,8 @@ __global__ void __launch_bounds__(128, 3) heads_bwd_mma_kernel(const bf16* __res
     const uint32_t al_lo[4] = {heads_pack(r00, r01), heads_pack(r10, r11), 0u, 0u};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      mma_bf16_16816_b0(dc[j], al_hi, bf_hi[j]); mma_bf16_16816_b0(dc[j], al_hi, bf_lo[j]); mma_bf16_16816_b0(dc[j], al_lo, bf_hi[j]);
+      const uint32_t fh = s_frag[28 + j][lane], fl = s_frag[32 + j][lane];
+      mma_bf16_16816_b0(dc[j], al_hi, fh); mma_bf16_16816_b0(dc[j], al_hi, fl); mma_bf16_16816_b0(dc[j], al_lo, fh);
     }
     if (ok0) *reinterpret_cast<uint4*>(d_feat + (long long)r0 * d_ld + 8 * t) =
         make_uint4(heads_pack(dc[0][0], dc[0][1]), heads_pack(dc[1][0], dc[1][1]), heads_pack(dc[2][0], dc[2][1]), heads_pack(dc[3][0], dc[3][1]));
