@@ -1523,23 +1523,23 @@ int backward_t(fu_engine* e, const float* d_seg, const float* d_heat, float* fla
                    (const float*)nullptr, reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW,
                    FastDiv((int)HW), c.do_soft_max, hl);
           if (c.num_lands == 14)
-            LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
-                   gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
+            { SideScope side(e);      /* produces weight gradients only: off the data-gradient chain */ LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
+                   gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14); }
           else
-            LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
-                   gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0);
+            { SideScope side(e);      /* produces weight gradients only: off the data-gradient chain */ LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
+                   gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0); }
         } else if (c.num_lands == 14) {
           LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 21, 14>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
                  tdata(e, e->seg.w_idx), tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx), d_seg, d_heat,
                  reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max, hl);
-          LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
-                 gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14);
+          { SideScope side(e);      /* produces weight gradients only: off the data-gradient chain */ LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, tdata(e, e->lands[0].w_idx), tdata(e, e->lands[1].w_idx),
+                 gptr(e, flat, e->seg.w_idx), gptr(e, flat, e->lands[0].w_idx), gptr(e, flat, e->lands[1].w_idx), 32, 7, 21, 14); }
         } else {
           LAUNCH(e, (heads_bwd_mma_kernel<32, 7, 1, 0>), gridm, 128, reinterpret_cast<const bf16*>(feat.p), feat.ld,
                  tdata(e, e->seg.w_idx), (const float*)nullptr, (const float*)nullptr, d_seg, (const float*)nullptr,
                  reinterpret_cast<bf16*>(d_feat.p), d_feat.ld, e->heads_gacc, (int)P0, (int)HW, FastDiv((int)HW), c.do_soft_max, hl);
-          LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
-                 gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0);
+          { SideScope side(e);      /* produces weight gradients only: off the data-gradient chain */ LAUNCH(e, heads_bwd_finalize_kernel, 8, 256, e->heads_gacc, (const float*)nullptr, (const float*)nullptr,
+                 gptr(e, flat, e->seg.w_idx), (float*)nullptr, (float*)nullptr, 32, 7, 1, 0); }
         }
         heads_done = true;
       }

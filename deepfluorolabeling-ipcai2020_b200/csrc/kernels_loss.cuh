@@ -28,9 +28,8 @@ struct LossArgs {
 // Rows per block: whole planes when there are enough planes to fill the machine (B = 32 @192x192: 672 planes), else chunks
 // sized for ~4 blocks per SM.  16-row blocks (8064 of them at B = 32) spent most of their time in the five block-level
 // fp64 reductions and atomics each block ends with: 61 + 95 us for two passes over 180 + 250 MB.
-// (Measured later and not kept: chunks sized for ~6 waves -- sums pass unchanged at 60 us, gradient pass 46 -> 50 us.  The sums
-// pass does not respond to more loads in flight, fp32 partials or finer chunks either: it runs right behind the head kernel
-// that wrote 99 MB of predictions, i.e. against the L2's write-back of those lines.)
+// (Measured later and not kept: chunks sized for ~6 waves -- sums pass unchanged at 60 us, gradient pass 46 -> 50 us.  What the
+// sums pass did respond to was wider loads: loss_sums_kernel<VEC2>.)
 inline int loss_rows_per_block(int rows_total, long long planes, int sms = 148) {
   long long r = ((long long)rows_total * planes + (long long)sms * 4 - 1) / ((long long)sms * 4);
   r = (r + 7) / 8 * 8;
