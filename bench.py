@@ -488,11 +488,14 @@ def measure(torch, dist, pkg, dev, rank, world, local, *, batch, size, tile, pre
         for i in range(2):
             e2e_step_sync(i)
         sync_ms = timed(e2e_step_sync, steps) / steps
-        res["e2e"] = {"value": B * world / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-                      "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms, "inputs": note,
-                      "loss_read": "every step, from a pinned host slot, one step behind the launch (the last one before the timed region ends)",
-                      "sequential": {"value": B * world / (sync_ms * 1e-3), "ms_per_step": sync_ms,
-                                     "loss_read": "loss.item() of step i before step i + 1 is issued"}}
+        # headline: the reference's own sequence (train.py:430: loss.item() of step i before step i + 1 is issued); the pipelined
+        # read (every step's loss still read inside the timed region, one step behind the launch) is reported beside it
+        res["e2e"] = {"value": B * world / (sync_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": 4, "ms_per_step": sync_ms, "inputs": note,
+                      "loss_read": "loss.item() of step i before step i + 1 is issued",
+                      "pipelined": {"value": B * world / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
+                                    "loss_read": "every step, from a pinned host slot, one step behind the launch "
+                                                 "(the last one before the timed region ends)"}}
 
     # ---- per-kernel device time (CUDA events inside the engine) -> roofline of the 3x3 conv family ----
     if profile:
